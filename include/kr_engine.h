@@ -1,0 +1,417 @@
+/*
+ * kr_engine.h — C ABI of the batched RayCluster reconcile engine (B200 / sm_100a).
+ *
+ * This is the drop-in boundary a cgo shim binds.  Plain C,
+ * plain pointers and sizes, no callbacks, no C++ exceptions across the boundary.
+ * Every entry point cites the reference interface (ray-project/kuberay, paths
+ * relative to the reference root) whose *decision half* it replaces; the Go
+ * side keeps performing the side effects (Create/Delete/Eventf/ExpectScalePod/
+ * Status().Update) in the recorded order.
+ *
+ * Data model: one *snapshot* = every watched RayCluster, its worker groups and
+ * every cached Pod, packed as little-endian SoA columns.  Strings are interned
+ * to u32 ids host-side (id 0 = absent; the empty string is a normal id).
+ * Pod order in the snapshot IS the informer List order and is honoured
+ * (reference deletes "the first -diff items in List order",
+ * ray-operator/controllers/ray/raycluster_controller.go:916-918).
+ */
+#ifndef KR_ENGINE_H_
+#define KR_ENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Interner convention: id 0 = "absent" (label/annotation/field not present), id 1 = the empty string "".
+ * In HeadInfo-like fields (pod IP, names, service IP) the empty string MUST be encoded as 0. */
+#define KR_ID_ABSENT 0u
+#define KR_ID_EMPTY_STRING 1u
+
+/* ------------------------------------------------------------------ enums */
+
+/* clusters.flags bits */
+enum {
+  KR_CF_SUSPEND            = 1u << 0,  /* spec.suspend != nil && *spec.suspend            (raycluster_controller.go:632,651,1680,1696) */
+  KR_CF_SUSPEND_SET_FALSE  = 1u << 1,  /* spec.suspend != nil && !*spec.suspend           (:1667) */
+  KR_CF_AUTOSCALING        = 1u << 2,  /* utils.IsAutoscalingEnabled(&spec)                (:898) */
+  KR_CF_UPGRADE_RECREATE   = 1u << 3,  /* spec.upgradeStrategy.type == Recreate            (:1134) */
+  KR_CF_SKIP_HEAD_RESTART  = 1u << 4,  /* annotation ray.io/disable-provisioned-head-restart == "true" (:1127) */
+  KR_CF_HEAD_EXPECT_OK     = 1u << 5,  /* rayClusterScaleExpectation.IsSatisfied(ns,name,HeadGroup) (:689) — evaluated in Go */
+  KR_CF_SKIP               = 1u << 6,  /* deletionTimestamp set / managed by external controller / validation failed: no decisions, no status (:152-185,290) */
+  KR_CF_ENDPOINTS_CHANGED  = 1u << 7,  /* host evaluated updateEndpoints (:1747-1783) and the map differs from old status */
+  KR_CF_OLD_REASON_NONEMPTY= 1u << 8   /* old status.reason != ""                           (consistency.go:17) */
+};
+
+/* clusters.suspend_status: utils.FindRayClusterSuspendStatus (utils/util.go:153-162), evaluated host-side */
+enum { KR_SUSPEND_NONE = 0, KR_SUSPEND_SUSPENDING = 1, KR_SUSPEND_SUSPENDED = 2 };
+
+/* clusters.ext_err_kind: error returned by a sub-reconciler that ran BEFORE reconcilePods
+ * (raycluster_controller.go:296-314) or, in status-only re-evaluation after an API failure,
+ * one of the ErrFailed* markers (utils/constant.go:322-334).  != 0 => decisions are skipped. */
+enum {
+  KR_EXT_ERR_NONE = 0,
+  KR_EXT_ERR_PLAIN = 1,
+  KR_EXT_ERR_FAILED_DELETE_ALL_PODS = 2,
+  KR_EXT_ERR_FAILED_DELETE_HEAD_POD = 3,
+  KR_EXT_ERR_FAILED_CREATE_HEAD_POD = 4,
+  KR_EXT_ERR_FAILED_DELETE_WORKER_POD = 5,
+  KR_EXT_ERR_FAILED_CREATE_WORKER_POD = 6
+};
+
+/* condition status codes (metav1.ConditionStatus) */
+enum { KR_COND_ABSENT = 0, KR_COND_TRUE = 1, KR_COND_FALSE = 2, KR_COND_UNKNOWN = 3 };
+
+/* condition slots (apis/ray/v1/raycluster_types.go:362-374) */
+enum {
+  KR_COND_PROVISIONED = 0,
+  KR_COND_HEAD_POD_READY = 1,
+  KR_COND_REPLICA_FAILURE = 2,
+  KR_COND_SUSPENDING = 3,
+  KR_COND_SUSPENDED = 4,
+  KR_NUM_CONDS = 5
+};
+
+/* condition (reason,message) variants the controller itself writes; anything else is KR_CV_OTHER */
+enum {
+  KR_CV_NONE = 0,
+  KR_CV_PROV_ALL_READY = 1,        /* AllPodRunningAndReadyFirstTime / "All Ray Pods are ready for the first time" (:1630-1635) */
+  KR_CV_PROV_PROVISIONING = 2,     /* RayClusterPodsProvisioning / "RayCluster Pods are being provisioned for first time" (:1637-1642) */
+  KR_CV_PROV_SUSPENDED = 3,        /* RayClusterPodsProvisioning / "RayCluster has been suspended" (:1649-1654) */
+  KR_CV_CANONICAL = 4,             /* Suspending/Suspended: reason == type, empty message (:1655-1691) */
+  KR_CV_HEAD_FROM_POD = 5,         /* HeadPodReady copied from the head pod (reason/message ids in the record) (:1621-1622) */
+  KR_CV_HEAD_NOT_FOUND = 6,        /* HeadPodNotFound / "Head Pod not found" (:1613-1619) */
+  /* ReplicaFailure slot: variant = the KR_EXT_ERR_FAILED_* kind (2..6) that names the reason (:1564-1571) */
+  KR_CV_OTHER = 255
+};
+
+/* cluster state (apis/ray/v1/raycluster_types.go:268-274) */
+enum { KR_STATE_EMPTY = 0, KR_STATE_READY = 1, KR_STATE_FAILED = 2, KR_STATE_SUSPENDED = 3, KR_STATE_OTHER = 4 };
+
+/* groups.flags bits */
+enum {
+  KR_GF_SUSPEND       = 1u << 0,   /* worker.Suspend != nil && *worker.Suspend (:766; utils/util.go:391) */
+  KR_GF_EXPECT_OK     = 1u << 1,   /* IsSatisfied(ns, cluster, groupName) (:752) — evaluated in Go */
+  KR_GF_REPLICAS_NIL  = 1u << 2,
+  KR_GF_MIN_NIL       = 1u << 3,
+  KR_GF_MAX_NIL       = 1u << 4
+};
+
+/* pods.packed bit fields */
+#define KR_PP_NODE_TYPE_SHIFT 0   /* 2 bits: 0 none/other, 1 head, 2 worker, 3 redis-cleanup (label ray.io/node-type) */
+#define KR_PP_PHASE_SHIFT     2   /* 3 bits: 0 "", 1 Pending, 2 Running, 3 Succeeded, 4 Failed, 5 Unknown */
+#define KR_PP_READY_SHIFT     5   /* 2 bits: PodReady condition: 0 absent, 1 True, 2 False, 3 Unknown */
+#define KR_PP_RESTART_NEVER   (1u << 7)   /* spec.restartPolicy == Never */
+#define KR_PP_RAY_TERMINATED  (1u << 8)   /* getRayContainerStateTerminated(pod) != nil (:1237-1248) */
+#define KR_PP_HAS_DELETION_TS (1u << 9)
+#define KR_PP_HAS_REPLICA_IDX (1u << 10)  /* label ray.io/worker-group-replica-index present AND strconv.Atoi succeeded (:857-860) */
+enum { KR_NT_NONE = 0, KR_NT_HEAD = 1, KR_NT_WORKER = 2, KR_NT_REDIS = 3 };
+enum { KR_PHASE_EMPTY = 0, KR_PHASE_PENDING = 1, KR_PHASE_RUNNING = 2, KR_PHASE_SUCCEEDED = 3, KR_PHASE_FAILED = 4, KR_PHASE_UNKNOWN = 5 };
+
+/* per-pod action codes (results) */
+enum {
+  KR_ACT_KEEP = 0,
+  KR_ACT_DELETE_ALL_SUSPEND = 1,     /* deleteAllPods on suspension (:633) */
+  KR_ACT_DELETE_ALL_RECREATE = 2,    /* deleteAllPods on Recreate upgrade (:659) */
+  KR_ACT_DELETE_HEAD = 3,            /* unhealthy head (:701) */
+  KR_ACT_DELETE_GROUP_SUSPEND = 4,   /* suspended worker group (:767) */
+  KR_ACT_DELETE_UNHEALTHY = 5,       /* shouldDeletePod worker (:796) */
+  KR_ACT_DELETE_WTD = 6,             /* named in scaleStrategy.workersToDelete and listed in its group (:822) */
+  KR_ACT_DELETE_RANDOM = 7,          /* list-prefix "random" delete (:917-919) */
+  KR_ACT_DELETE_MH_INCOMPLETE = 8,   /* multi-host: incomplete replica cleanup (:978) */
+  KR_ACT_DELETE_MH_UNHEALTHY = 9,    /* multi-host: unhealthy replica (:999) */
+  KR_ACT_DELETE_MH_WTD = 10,         /* multi-host: autoscaler scale-down request (:1030) */
+  KR_ACT_DELETE_MH_SCALE_DOWN = 11,  /* multi-host: scaling down (:1114) */
+  KR_ACT_ORPHAN = 255                /* pod matched no RayCluster in the snapshot */
+};
+
+/* cluster_results.path */
+enum {
+  KR_PATH_NORMAL = 0,
+  KR_PATH_SKIPPED = 1,               /* KR_CF_SKIP or ext_err_kind != 0 */
+  KR_PATH_SUSPENDING_DELETE_ALL = 2, /* :631-644 */
+  KR_PATH_SUSPENDED_NOOP = 3,        /* :646-654 */
+  KR_PATH_RECREATE_DELETE_ALL = 4    /* :657-670 */
+};
+
+/* cluster_results.head_action */
+enum {
+  KR_HEAD_NONE = 0,
+  KR_HEAD_EXPECT_PENDING = 1,        /* :689-690 */
+  KR_HEAD_DELETE = 2,                /* :700-711, reconcile aborts with error */
+  KR_HEAD_CREATE = 3,                /* :735 */
+  KR_HEAD_SKIP_RESTART = 4,          /* :714-732, reconcile returns nil early */
+  KR_HEAD_MULTIPLE = 5               /* :738-747, error */
+};
+
+/* cluster_results.err_kind: which plain error reconcilePods returned (never an ErrFailed* marker:
+ * those arise only from API-call failures) */
+enum {
+  KR_ERR_NONE = 0,
+  KR_ERR_HEAD_DELETED = 1,           /* errstd.New(reason) :711 */
+  KR_ERR_MULTIPLE_HEADS = 2,         /* :747; err_arg = count */
+  KR_ERR_UNHEALTHY_WORKERS = 3,      /* "delete %d unhealthy worker Pods" :811; err_arg = count */
+  KR_ERR_MH_INCOMPLETE = 4,          /* :982 */
+  KR_ERR_MH_WTD = 5,                 /* :1034; err_arg = pods deleted */
+  KR_ERR_MH_NOT_MULTIPLE = 6,        /* :1060 */
+  KR_ERR_EXTERNAL = 7,               /* ext_err_kind != 0 */
+  KR_ERR_NEGATIVE_EXPECTED = 8       /* expected < 0 with delete allowed: the Go code would index out of range (:917); engine refuses */
+};
+
+/* cluster_results.status_err: calculateStatus returned an error => no status write (:1608-1611,1704-1706,1721-1745) */
+enum {
+  KR_SERR_NONE = 0,
+  KR_SERR_MULTIPLE_HEADS = 1,        /* common/association.go:192-194 */
+  KR_SERR_NO_HEAD_SERVICE = 2,
+  KR_SERR_MULTIPLE_HEAD_SERVICES = 3,
+  KR_SERR_EMPTY_SERVICE_IP = 4
+};
+
+/* group_results.flags */
+enum {
+  KR_GR_PROCESSED       = 1u << 0,   /* loop body reached this group */
+  KR_GR_EXPECT_PENDING  = 1u << 1,   /* :752-755 */
+  KR_GR_SUSPENDED       = 1u << 2,   /* :766-775 */
+  KR_GR_MULTIHOST       = 1u << 3,   /* :777-784 */
+  KR_GR_WTD_EXECUTED    = 1u << 4,   /* the WorkersToDelete loop (:817-835) ran: every resolved wtd entry is a Delete call */
+  KR_GR_ABORTED         = 1u << 5,   /* reconcilePods returned from inside this group */
+  KR_GR_RANDOM_DELETE_OFF = 1u << 6, /* diff<0 but autoscaler owns deletions (:929-931) */
+  KR_GR_CREATE_TRUNCATED = 1u << 7   /* create arena exhausted: n_create was clipped (engine limit, not reference behaviour) */
+};
+
+/* heads.annot_state / heads.version_state (raycluster_controller.go:1153-1168) */
+enum { KR_ANNOT_EMPTY = 0, KR_ANNOT_HASH32 = 1, KR_ANNOT_OTHER = 2 };
+enum { KR_VER_EMPTY = 0, KR_VER_CURRENT = 1, KR_VER_DIFFERENT = 2 };
+
+/* head service ip kind (raycluster_controller.go:1726-1744) */
+enum { KR_SVCIP_NORMAL = 0, KR_SVCIP_EMPTY = 1, KR_SVCIP_NONE = 2 /* "None": headless => head pod IP */ };
+
+/* error codes */
+enum {
+  KR_OK = 0,
+  KR_E_INVALID = -1,
+  KR_E_CAPACITY = -2,
+  KR_E_CUDA = -3,
+  KR_E_STATE = -4,
+  KR_E_NO_DEVICE = -5
+};
+
+/* -------------------------------------------------------------- config */
+
+typedef struct kr_engine kr_engine;
+
+typedef struct kr_config {
+  int32_t  device;          /* CUDA ordinal */
+  uint32_t max_clusters;
+  uint32_t max_groups;
+  uint32_t max_wtd;         /* total scaleStrategy.workersToDelete names */
+  uint32_t max_pods;
+  uint32_t max_heads;       /* rows of the head-aux table */
+  uint32_t max_jobs;        /* RayJob roll-up rows */
+  uint32_t max_creates;     /* capacity of the replica-index arena (ints) */
+  uint64_t max_json_bytes;  /* muted-spec JSON arena */
+} kr_config;
+
+/* process-level switches read at reconcile time in the reference */
+typedef struct kr_flags {
+  uint8_t  gate_status_conditions;   /* features.RayClusterStatusConditions (pkg/features/features.go:56-62), default 1 */
+  uint8_t  gate_multihost_indexing;  /* features.RayMultiHostIndexing, default 1 */
+  uint8_t  env_random_pod_delete;    /* strings.ToLower(os.Getenv("ENABLE_RANDOM_POD_DELETE")) == "true" (:905) */
+  uint8_t  skip_hash;                /* 1 => do not run the hash kernel (hash[] zeroed; Recreate gate treats hash as unknown) — test/bench knob only */
+  uint32_t id_head_not_found_reason; /* interned id of "HeadPodNotFound" */
+  uint32_t id_head_not_found_msg;    /* interned id of "Head Pod not found" */
+} kr_flags;
+
+typedef struct kr_sizes {
+  uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs;
+  uint64_t json_bytes;
+} kr_sizes;
+
+/* ------------------------------------------------- snapshot (host arenas) */
+
+/* All pointers below are engine-owned pinned host memory (cudaHostAlloc) sized
+ * for kr_config capacities; the caller fills the first kr_sizes entries.
+ * Go fills them through unsafe.Slice, so C never retains a Go pointer. */
+typedef struct kr_snapshot_bufs {
+  /* clusters [n_clusters]  — apis/ray/v1/raycluster_types.go:13-53, 277-348 */
+  uint32_t *c_ns_id, *c_name_id;
+  uint64_t *c_uid_hash;            /* sharding key */
+  uint32_t *c_flags;               /* KR_CF_* */
+  uint8_t  *c_suspend_status;      /* KR_SUSPEND_* */
+  uint8_t  *c_ext_err_kind;        /* KR_EXT_ERR_* */
+  uint32_t *c_ext_err_msg_id;
+  uint32_t *c_group_off, *c_group_cnt;   /* worker groups in spec order */
+  uint64_t *c_json_off;            /* offset into json[]; must be 16-byte aligned */
+  uint32_t *c_json_len;
+  /* old status (the copy taken at raycluster_controller.go:188) */
+  uint8_t  *c_old_state;           /* KR_STATE_* */
+  int32_t  *c_old_counts;          /* [5*n]: ready, available, desired, min, max */
+  uint8_t  *c_old_cond_status;     /* [5*n]: KR_COND_* per slot */
+  uint8_t  *c_old_cond_variant;    /* [5*n]: KR_CV_* per slot (ReplicaFailure: KR_EXT_ERR_* kind or KR_CV_OTHER) */
+  uint32_t *c_old_cond_reason_id;  /* [n]: HeadPodReady reason */
+  uint32_t *c_old_cond_msg_id;     /* [2*n]: [0]=HeadPodReady message, [1]=ReplicaFailure message */
+  uint32_t *c_old_head_ids;        /* [4*n]: podIP, serviceIP, podName, serviceName (HeadInfo, :376-386) */
+  /* head Service (raycluster_controller.go:1721-1745) */
+  uint8_t  *c_svc_count;           /* 0, 1, 2 (= more than one) */
+  uint8_t  *c_svc_ip_kind;         /* KR_SVCIP_* */
+  uint32_t *c_svc_ip_id, *c_svc_name_id;
+
+  /* groups [n_groups] — WorkerGroupSpec, raycluster_types.go:157-207 */
+  uint32_t *g_cluster_idx, *g_name_id;
+  int32_t  *g_replicas, *g_min, *g_max, *g_num_hosts;
+  uint32_t *g_flags;               /* KR_GF_* */
+  uint32_t *g_wtd_off, *g_wtd_cnt;
+
+  /* workersToDelete names [n_wtd], grouped by group in spec order */
+  uint32_t *w_name_id;
+
+  /* pods [n_pods] in informer List order */
+  uint32_t *p_ns_id, *p_cluster_name_id, *p_group_name_id, *p_name_id, *p_packed;
+  int32_t  *p_replica_index;
+  uint32_t *p_replica_name_id;
+
+  /* head-aux rows [n_heads]: one per pod whose node-type label is head */
+  uint32_t *h_pod_idx;
+  uint8_t  *h_ready_status;        /* FindHeadPodReadyCondition(...).Status as KR_COND_* (utils/util.go:81-124) */
+  uint32_t *h_ready_reason_id, *h_ready_msg_id;
+  uint32_t *h_pod_ip_id;
+  uint8_t  *h_annot_state;         /* KR_ANNOT_* of ray.io/upgrade-strategy-recreate-hash */
+  uint8_t  *h_version_state;       /* KR_VER_* of ray.io/kuberay-version vs utils.KUBERAY_VERSION */
+  uint8_t  *h_annot_hash;          /* [32*n]: the annotation's 32 chars when KR_ANNOT_HASH32 */
+
+  /* RayJob roll-up rows [n_jobs] — rayjob_controller.go:203-216,343,880-905 */
+  uint32_t *j_ns_id, *j_cluster_name_id;
+  uint32_t *j_summary_id;          /* interned id of the canonical encoding of the job's current status.rayClusterStatus compare-fields */
+  uint32_t *c_summary_id;          /* [n_clusters]: same encoding of the RayCluster's stored status */
+
+  /* muted-spec JSON arena (bytes produced by Go json.Marshal, utils/util.go:629,645-661) */
+  uint8_t  *json;
+} kr_snapshot_bufs;
+
+/* ------------------------------------------------------------- results */
+
+typedef struct kr_cluster_result {      /* 96 bytes */
+  uint8_t  path;                 /* KR_PATH_* */
+  uint8_t  head_action;          /* KR_HEAD_* */
+  uint8_t  err_kind;             /* KR_ERR_* : reconcileErr != nil iff != 0 */
+  uint8_t  status_err;           /* KR_SERR_* */
+  uint8_t  new_state;            /* KR_STATE_* */
+  uint8_t  state_changed;        /* StateTransitionTimes[new_state] = now (:1711-1716) */
+  uint8_t  needs_status_write;   /* InconsistentRayClusterStatus(old,new) (utils/consistency.go:16-34) && status_err == 0 */
+  uint8_t  head_update_annotations; /* KubeRay version changed: re-annotate head pod (:1155-1162) */
+  int32_t  stop_after_group;     /* group index inside which reconcilePods returned; group_cnt if it ran through; -1 if it returned before the worker loop */
+  int32_t  err_arg;
+  int32_t  n_pods;               /* len(runtimePods.Items) (:1583) */
+  int32_t  n_heads;
+  int32_t  head_pod_idx;         /* first head pod in list order, -1 if none */
+  int32_t  counts[5];            /* ready, available, desired, min, max (utils/util.go:407-474) */
+  uint8_t  cond_status[8];       /* [KR_NUM_CONDS] KR_COND_* after calculateStatus; rest padding */
+  uint8_t  cond_variant[8];      /* [KR_NUM_CONDS] KR_CV_* */
+  uint32_t head_ready_reason_id, head_ready_msg_id;
+  uint32_t head_ids[4];          /* podIP, serviceIP, podName, serviceName */
+  uint32_t pod_start;            /* this cluster's pods are sorted_pod_idx[pod_start .. pod_start+n_pods) in list order */
+  uint32_t reserved;
+} kr_cluster_result;
+
+typedef struct kr_group_result {        /* 32 bytes */
+  int32_t  expected;             /* int(GetWorkerGroupDesiredReplicas) (utils/util.go:386-404) */
+  int32_t  n_list;               /* len(workerPods.Items) (:761) */
+  int32_t  n_unhealthy;          /* :794 */
+  int32_t  n_running;            /* len(runningPods.Items) (:837-842); multi-host: valid replica groups (:1055) */
+  int32_t  diff;                 /* :849; multi-host: replicasToCreate (:1064) */
+  uint32_t n_create;             /* pods to create */
+  uint32_t create_off;           /* first replica index of this group in create_idx[] (one entry per pod; multi-host: per replica) */
+  uint32_t flags;                /* KR_GR_* */
+} kr_group_result;
+
+typedef struct kr_job_result {          /* 8 bytes */
+  int32_t  cluster_idx;          /* -1: RayCluster not in snapshot */
+  uint8_t  cluster_state;        /* KR_STATE_* of the stored RayCluster status */
+  uint8_t  not_ready;            /* rayCluster.Status.State != Ready (rayjob_controller.go:209) */
+  uint8_t  status_changed;       /* InconsistentRayClusterStatus(job.status.rayClusterStatus, cluster.status) (:885) */
+  uint8_t  reserved;
+} kr_job_result;
+
+/* Engine-owned pinned host arenas, valid until the next kr_snapshot_begin. */
+typedef struct kr_results_view {
+  const kr_cluster_result *clusters;   /* [n_clusters] */
+  const char              *hash;       /* [32*n_clusters] base32hex(sha1(json)) (utils/util.go:628-640) */
+  const kr_group_result   *groups;     /* [n_groups] */
+  const int32_t           *wtd_pod_idx;/* [n_wtd]: pod (same namespace, same name) the Delete call resolves to, -1 = NotFound */
+  const uint32_t          *sorted_pod_idx; /* [n_pods]: pods bucketed by cluster, list order kept; orphans last */
+  const uint8_t           *sorted_action;  /* [n_pods]: KR_ACT_* aligned with sorted_pod_idx */
+  const int32_t           *create_idx; /* [n_create_total] replica indices (:869-881,1081-1094) */
+  const kr_job_result     *jobs;       /* [n_jobs] */
+  uint32_t n_create_total;
+  uint32_t n_orphans;
+  uint32_t n_actions;              /* pods with action != KEEP (orphans excluded) */
+  uint32_t reserved;
+} kr_results_view;
+
+/* Per-kernel device times of the last kr_reconcile_batch (CUDA events on the engine's streams). */
+#define KR_MAX_KERNEL_TIMES 24
+typedef struct kr_profile {
+  float    h2d_ms, kernels_ms, d2h_ms;      /* whole phases */
+  uint32_t n_kernels;                       /* kernels launched by the last batch (our own, not library) */
+  float    kernel_ms[KR_MAX_KERNEL_TIMES];  /* valid only after kr_reconcile_batch_profiled */
+  const char *kernel_name[KR_MAX_KERNEL_TIMES];
+} kr_profile;
+
+/* --------------------------------------------------------- entry points */
+
+/* Number of CUDA devices visible; <0 on error. */
+int kr_device_count(void);
+
+/* Create/destroy an engine bound to one device.  Replaces nothing in the reference;
+ * a cgo shim calls it once from main() next to ctrl.NewManager (ray-operator/main.go:239-243). */
+int  kr_engine_create(const kr_config *cfg, kr_engine **out);
+void kr_engine_destroy(kr_engine *e);
+
+/* Begin filling a snapshot: returns the pinned arenas.  Replaces the per-object
+ * r.Get / cached r.List reads (raycluster_controller.go:114,674,761,1583; common/association.go:83-130,184). */
+int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out);
+
+/* Upload the filled snapshot (host -> HBM, async on the engine stream, then synchronised). */
+int kr_snapshot_commit(kr_engine *e);
+
+/* Run the whole decision + status pass over the committed snapshot and copy the results back.
+ * Replaces the decision halves of reconcilePods (raycluster_controller.go:619-935), reconcileMultiHostWorkerGroup
+ * (:963-1125), shouldRecreatePodsForUpgrade (:1132-1171), shouldDeletePod (:1181-1231), calculateStatus (:1552-1719),
+ * GetWorkerGroupDesiredReplicas/Calculate*Replicas (utils/util.go:386-474), CheckAllPodsRunning (:584-603),
+ * GenerateHashWithoutReplicasAndWorkersToDelete (:642-665, SHA-1 + base32hex half) and
+ * InconsistentRayClusterStatus (utils/consistency.go:16-34); RayJob roll-up rayjob_controller.go:209-216,343,885. */
+int kr_reconcile_batch(kr_engine *e, const kr_flags *flags, kr_results_view *out);
+
+/* Same pass, kernels only: no D2H copy, results stay in HBM (bench "value" leg; also used under ncu). */
+int kr_reconcile_device_only(kr_engine *e, const kr_flags *flags);
+
+/* Same as kr_reconcile_device_only but serialises the kernels and brackets each with CUDA events. */
+int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile *prof);
+
+/* Copy results of the last device-only pass to the host arenas. */
+int kr_results_fetch(kr_engine *e, kr_results_view *out);
+
+/* Stand-alone batched hash: base32hex(sha1(bytes[offsets[i]..offsets[i+1]))) for i<n into out32xN
+ * (32 chars per message, no terminator).  Replaces utils.GenerateJsonHash's digest half (utils/util.go:634-637);
+ * also used by rayservice_controller.go:1130-1157,1244 callers.  Host buffers; copies included. */
+int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, uint32_t n, char *out32xN);
+
+/* Timings of the last batch. */
+int kr_last_profile(kr_engine *e, kr_profile *prof);
+
+/* Device pointer + byte size of the per-group delta records (kr_group_result[n_groups]) of the last pass:
+ * the payload of the optional cross-GPU all-gather; the caller owns the collective. */
+int kr_group_results_device(kr_engine *e, const void **dev_ptr, uint64_t *bytes);
+
+/* Last error text for this engine (never NULL). */
+const char *kr_last_error(kr_engine *e);
+
+/* Algorithmic bytes of one pass over the committed snapshot (144/cluster + 56/group + 4/wtd
+ * + 33/pod + json bytes), and of the hash kernel alone (json bytes + 32/cluster). */
+int kr_algorithmic_bytes(kr_engine *e, uint64_t *pass_bytes, uint64_t *hash_bytes, uint64_t *match_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KR_ENGINE_H_ */

@@ -1,0 +1,240 @@
+"""ctypes / numpy mirror of include/kr_engine.h (the C ABI of the reconcile engine).
+
+Keep this file in lock-step with the header: tests/test_abi.py checks struct sizes and that the
+built library exports every declared symbol.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+# ---------------------------------------------------------------- enums (include/kr_engine.h)
+ID_ABSENT, ID_EMPTY_STRING = 0, 1
+
+CF_SUSPEND = 1 << 0
+CF_SUSPEND_SET_FALSE = 1 << 1
+CF_AUTOSCALING = 1 << 2
+CF_UPGRADE_RECREATE = 1 << 3
+CF_SKIP_HEAD_RESTART = 1 << 4
+CF_HEAD_EXPECT_OK = 1 << 5
+CF_SKIP = 1 << 6
+CF_ENDPOINTS_CHANGED = 1 << 7
+CF_OLD_REASON_NONEMPTY = 1 << 8
+
+SUSPEND_NONE, SUSPEND_SUSPENDING, SUSPEND_SUSPENDED = 0, 1, 2
+
+(EXT_ERR_NONE, EXT_ERR_PLAIN, EXT_ERR_FAILED_DELETE_ALL_PODS, EXT_ERR_FAILED_DELETE_HEAD_POD,
+ EXT_ERR_FAILED_CREATE_HEAD_POD, EXT_ERR_FAILED_DELETE_WORKER_POD, EXT_ERR_FAILED_CREATE_WORKER_POD) = range(7)
+
+COND_ABSENT, COND_TRUE, COND_FALSE, COND_UNKNOWN = 0, 1, 2, 3
+COND_PROVISIONED, COND_HEAD_POD_READY, COND_REPLICA_FAILURE, COND_SUSPENDING, COND_SUSPENDED = range(5)
+NUM_CONDS = 5
+
+CV_NONE, CV_PROV_ALL_READY, CV_PROV_PROVISIONING, CV_PROV_SUSPENDED, CV_CANONICAL, CV_HEAD_FROM_POD, CV_HEAD_NOT_FOUND = range(7)
+CV_OTHER = 255
+
+STATE_EMPTY, STATE_READY, STATE_FAILED, STATE_SUSPENDED, STATE_OTHER = range(5)
+
+GF_SUSPEND = 1 << 0
+GF_EXPECT_OK = 1 << 1
+GF_REPLICAS_NIL = 1 << 2
+GF_MIN_NIL = 1 << 3
+GF_MAX_NIL = 1 << 4
+
+PP_NODE_TYPE_SHIFT, PP_PHASE_SHIFT, PP_READY_SHIFT = 0, 2, 5
+PP_RESTART_NEVER = 1 << 7
+PP_RAY_TERMINATED = 1 << 8
+PP_HAS_DELETION_TS = 1 << 9
+PP_HAS_REPLICA_IDX = 1 << 10
+NT_NONE, NT_HEAD, NT_WORKER, NT_REDIS = range(4)
+PHASE_EMPTY, PHASE_PENDING, PHASE_RUNNING, PHASE_SUCCEEDED, PHASE_FAILED, PHASE_UNKNOWN = range(6)
+
+(ACT_KEEP, ACT_DELETE_ALL_SUSPEND, ACT_DELETE_ALL_RECREATE, ACT_DELETE_HEAD, ACT_DELETE_GROUP_SUSPEND,
+ ACT_DELETE_UNHEALTHY, ACT_DELETE_WTD, ACT_DELETE_RANDOM, ACT_DELETE_MH_INCOMPLETE, ACT_DELETE_MH_UNHEALTHY,
+ ACT_DELETE_MH_WTD, ACT_DELETE_MH_SCALE_DOWN) = range(12)
+ACT_ORPHAN = 255
+
+PATH_NORMAL, PATH_SKIPPED, PATH_SUSPENDING_DELETE_ALL, PATH_SUSPENDED_NOOP, PATH_RECREATE_DELETE_ALL = range(5)
+HEAD_NONE, HEAD_EXPECT_PENDING, HEAD_DELETE, HEAD_CREATE, HEAD_SKIP_RESTART, HEAD_MULTIPLE = range(6)
+(ERR_NONE, ERR_HEAD_DELETED, ERR_MULTIPLE_HEADS, ERR_UNHEALTHY_WORKERS, ERR_MH_INCOMPLETE, ERR_MH_WTD,
+ ERR_MH_NOT_MULTIPLE, ERR_EXTERNAL, ERR_NEGATIVE_EXPECTED) = range(9)
+SERR_NONE, SERR_MULTIPLE_HEADS, SERR_NO_HEAD_SERVICE, SERR_MULTIPLE_HEAD_SERVICES, SERR_EMPTY_SERVICE_IP = range(5)
+
+GR_PROCESSED = 1 << 0
+GR_EXPECT_PENDING = 1 << 1
+GR_SUSPENDED = 1 << 2
+GR_MULTIHOST = 1 << 3
+GR_WTD_EXECUTED = 1 << 4
+GR_ABORTED = 1 << 5
+GR_RANDOM_DELETE_OFF = 1 << 6
+GR_CREATE_TRUNCATED = 1 << 7
+
+ANNOT_EMPTY, ANNOT_HASH32, ANNOT_OTHER = 0, 1, 2
+VER_EMPTY, VER_CURRENT, VER_DIFFERENT = 0, 1, 2
+SVCIP_NORMAL, SVCIP_EMPTY, SVCIP_NONE = 0, 1, 2
+
+KR_OK, KR_E_INVALID, KR_E_CAPACITY, KR_E_CUDA, KR_E_STATE, KR_E_NO_DEVICE = 0, -1, -2, -3, -4, -5
+MAX_KERNEL_TIMES = 24
+
+# ---------------------------------------------------------------- snapshot columns
+# (field, numpy dtype, per-row multiplicity, dimension)   — order == struct kr_snapshot_bufs
+u8, u32, i32, u64 = np.uint8, np.uint32, np.int32, np.uint64
+COLUMNS = [
+    ("c_ns_id", u32, 1, "clusters"), ("c_name_id", u32, 1, "clusters"), ("c_uid_hash", u64, 1, "clusters"),
+    ("c_flags", u32, 1, "clusters"), ("c_suspend_status", u8, 1, "clusters"), ("c_ext_err_kind", u8, 1, "clusters"),
+    ("c_ext_err_msg_id", u32, 1, "clusters"), ("c_group_off", u32, 1, "clusters"), ("c_group_cnt", u32, 1, "clusters"),
+    ("c_json_off", u64, 1, "clusters"), ("c_json_len", u32, 1, "clusters"),
+    ("c_old_state", u8, 1, "clusters"), ("c_old_counts", i32, 5, "clusters"),
+    ("c_old_cond_status", u8, 5, "clusters"), ("c_old_cond_variant", u8, 5, "clusters"),
+    ("c_old_cond_reason_id", u32, 1, "clusters"), ("c_old_cond_msg_id", u32, 2, "clusters"),
+    ("c_old_head_ids", u32, 4, "clusters"),
+    ("c_svc_count", u8, 1, "clusters"), ("c_svc_ip_kind", u8, 1, "clusters"),
+    ("c_svc_ip_id", u32, 1, "clusters"), ("c_svc_name_id", u32, 1, "clusters"),
+    ("g_cluster_idx", u32, 1, "groups"), ("g_name_id", u32, 1, "groups"),
+    ("g_replicas", i32, 1, "groups"), ("g_min", i32, 1, "groups"), ("g_max", i32, 1, "groups"), ("g_num_hosts", i32, 1, "groups"),
+    ("g_flags", u32, 1, "groups"), ("g_wtd_off", u32, 1, "groups"), ("g_wtd_cnt", u32, 1, "groups"),
+    ("w_name_id", u32, 1, "wtd"),
+    ("p_ns_id", u32, 1, "pods"), ("p_cluster_name_id", u32, 1, "pods"), ("p_group_name_id", u32, 1, "pods"),
+    ("p_name_id", u32, 1, "pods"), ("p_packed", u32, 1, "pods"), ("p_replica_index", i32, 1, "pods"),
+    ("p_replica_name_id", u32, 1, "pods"),
+    ("h_pod_idx", u32, 1, "heads"), ("h_ready_status", u8, 1, "heads"), ("h_ready_reason_id", u32, 1, "heads"),
+    ("h_ready_msg_id", u32, 1, "heads"), ("h_pod_ip_id", u32, 1, "heads"), ("h_annot_state", u8, 1, "heads"),
+    ("h_version_state", u8, 1, "heads"), ("h_annot_hash", u8, 32, "heads"),
+    ("j_ns_id", u32, 1, "jobs"), ("j_cluster_name_id", u32, 1, "jobs"), ("j_summary_id", u32, 1, "jobs"),
+    ("c_summary_id", u32, 1, "clusters"),
+    ("json", u8, 1, "json"),
+]
+DIMS = ["clusters", "groups", "wtd", "pods", "heads", "jobs", "json"]
+_CT = {np.uint8: C.c_uint8, np.uint32: C.c_uint32, np.int32: C.c_int32, np.uint64: C.c_uint64}
+
+
+class kr_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_clusters", C.c_uint32), ("max_groups", C.c_uint32), ("max_wtd", C.c_uint32),
+                ("max_pods", C.c_uint32), ("max_heads", C.c_uint32), ("max_jobs", C.c_uint32), ("max_creates", C.c_uint32),
+                ("max_json_bytes", C.c_uint64)]
+
+
+class kr_flags(C.Structure):
+    _fields_ = [("gate_status_conditions", C.c_uint8), ("gate_multihost_indexing", C.c_uint8), ("env_random_pod_delete", C.c_uint8),
+                ("skip_hash", C.c_uint8), ("id_head_not_found_reason", C.c_uint32), ("id_head_not_found_msg", C.c_uint32)]
+
+
+class kr_sizes(C.Structure):
+    _fields_ = [("n_clusters", C.c_uint32), ("n_groups", C.c_uint32), ("n_wtd", C.c_uint32), ("n_pods", C.c_uint32),
+                ("n_heads", C.c_uint32), ("n_jobs", C.c_uint32), ("json_bytes", C.c_uint64)]
+
+
+class kr_snapshot_bufs(C.Structure):
+    _fields_ = [(name, C.POINTER(_CT[dt])) for (name, dt, _m, _d) in COLUMNS]
+
+
+cluster_result_dtype = np.dtype([
+    ("path", u8), ("head_action", u8), ("err_kind", u8), ("status_err", u8), ("new_state", u8), ("state_changed", u8),
+    ("needs_status_write", u8), ("head_update_annotations", u8),
+    ("stop_after_group", i32), ("err_arg", i32), ("n_pods", i32), ("n_heads", i32), ("head_pod_idx", i32),
+    ("counts", i32, (5,)), ("cond_status", u8, (8,)), ("cond_variant", u8, (8,)),
+    ("head_ready_reason_id", u32), ("head_ready_msg_id", u32), ("head_ids", u32, (4,)), ("pod_start", u32), ("reserved", u32),
+], align=True)
+group_result_dtype = np.dtype([
+    ("expected", i32), ("n_list", i32), ("n_unhealthy", i32), ("n_running", i32), ("diff", i32),
+    ("n_create", u32), ("create_off", u32), ("flags", u32),
+], align=True)
+job_result_dtype = np.dtype([
+    ("cluster_idx", i32), ("cluster_state", u8), ("not_ready", u8), ("status_changed", u8), ("reserved", u8),
+], align=True)
+assert cluster_result_dtype.itemsize == 96 and group_result_dtype.itemsize == 32 and job_result_dtype.itemsize == 8
+
+
+class kr_results_view(C.Structure):
+    _fields_ = [("clusters", C.c_void_p), ("hash", C.c_void_p), ("groups", C.c_void_p), ("wtd_pod_idx", C.c_void_p),
+                ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
+                ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class kr_profile(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("kernels_ms", C.c_float), ("d2h_ms", C.c_float), ("n_kernels", C.c_uint32),
+                ("kernel_ms", C.c_float * MAX_KERNEL_TIMES), ("kernel_name", C.c_char_p * MAX_KERNEL_TIMES)]
+
+
+class kr_oracle_out(C.Structure):  # oracle/kr_oracle.h (test infrastructure; declared here only for layout sharing)
+    _fields_ = [("clusters", C.c_void_p), ("hash", C.c_void_p), ("groups", C.c_void_p), ("wtd_pod_idx", C.c_void_p),
+                ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
+                ("create_cap", C.c_uint32), ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32)]
+
+
+# every symbol include/kr_engine.h declares
+ENGINE_SYMBOLS = [
+    "kr_device_count", "kr_engine_create", "kr_engine_destroy", "kr_snapshot_begin", "kr_snapshot_commit",
+    "kr_reconcile_batch", "kr_reconcile_device_only", "kr_reconcile_batch_profiled", "kr_results_fetch",
+    "kr_hash_batch", "kr_last_profile", "kr_group_results_device", "kr_last_error", "kr_algorithmic_bytes",
+]
+
+
+def default_flags(**kw) -> kr_flags:
+    """Process-level switches at their reference defaults (pkg/features/features.go:56-62; env unset)."""
+    f = kr_flags()
+    f.gate_status_conditions = 1
+    f.gate_multihost_indexing = 1
+    f.env_random_pod_delete = 0
+    f.skip_hash = 0
+    f.id_head_not_found_reason = 0
+    f.id_head_not_found_msg = 0
+    for k, v in kw.items():
+        setattr(f, k, v)
+    return f
+
+
+class Results:
+    """Owned numpy copy of one pass's results (engine or oracle) — same fields as kr_results_view."""
+
+    FIELDS = ["clusters", "hash", "groups", "wtd_pod_idx", "sorted_pod_idx", "sorted_action", "create_idx", "jobs"]
+
+    def __init__(self, sizes: kr_sizes, create_cap: int):
+        self.clusters = np.zeros(sizes.n_clusters, dtype=cluster_result_dtype)
+        self.hash = np.zeros((sizes.n_clusters, 32), dtype=np.uint8)
+        self.groups = np.zeros(sizes.n_groups, dtype=group_result_dtype)
+        self.wtd_pod_idx = np.zeros(sizes.n_wtd, dtype=np.int32)
+        self.sorted_pod_idx = np.zeros(sizes.n_pods, dtype=np.uint32)
+        self.sorted_action = np.zeros(sizes.n_pods, dtype=np.uint8)
+        self.create_idx = np.zeros(max(create_cap, 1), dtype=np.int32)
+        self.jobs = np.zeros(sizes.n_jobs, dtype=job_result_dtype)
+        self.n_create_total = 0
+        self.n_orphans = 0
+        self.n_actions = 0
+
+    def hash_strings(self):
+        return [bytes(r).decode("ascii", "replace") for r in self.hash]
+
+    def diff(self, other: "Results") -> list[str]:
+        """Field-by-field byte comparison; returns human-readable mismatches (empty == bit-exact parity)."""
+        out = []
+        for k in ("n_create_total", "n_orphans", "n_actions"):
+            if getattr(self, k) != getattr(other, k):
+                out.append(f"{k}: {getattr(self, k)} != {getattr(other, k)}")
+        for name in self.FIELDS:
+            a, b = getattr(self, name), getattr(other, name)
+            if name == "create_idx":
+                n = min(self.n_create_total, other.n_create_total)
+                a, b = a[:n], b[:n]
+            if a.shape != b.shape:
+                out.append(f"{name}: shape {a.shape} != {b.shape}")
+                continue
+            if a.dtype.names:
+                for fld in a.dtype.names:
+                    if fld == "reserved":
+                        continue
+                    neq = a[fld] != b[fld]
+                    if neq.ndim > 1:
+                        neq = neq.any(axis=tuple(range(1, neq.ndim)))
+                    if neq.any():
+                        i = int(np.flatnonzero(neq)[0])
+                        out.append(f"{name}.{fld}: {int(neq.sum())} rows differ, first at [{i}]: {a[fld][i]} != {b[fld][i]}")
+            else:
+                neq = a != b
+                if neq.ndim > 1:
+                    neq = neq.any(axis=1)
+                if neq.any():
+                    i = int(np.flatnonzero(neq)[0])
+                    out.append(f"{name}: {int(neq.sum())} entries differ, first at [{i}]: {a[i]} != {b[i]}")
+        return out
