@@ -1,0 +1,582 @@
+// kr_engine.cu — C ABI (include/kr_engine.h) of the batched reconcile engine: arenas, streams, kernel schedule.
+//
+// One engine = one device, two streams: M (match -> sort -> decide -> creates) and H (hash), joined by events.
+// Inputs live in ONE pinned host arena and ONE device arena with identical layouts computed per snapshot from
+// kr_sizes, so kr_snapshot_commit is a single contiguous H2D copy; results likewise come back in one D2H copy
+// (+ one for the replica-index arena when pods are to be created).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kr_kernels.cuh"
+
+using namespace kr;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+inline uint32_t pow2_at_least(uint64_t x) { uint32_t p = 16; while (p < x) p <<= 1; return p; }
+
+struct InLayout {  // offsets of every input column inside the snapshot arena
+  size_t off[64];
+  size_t total;
+};
+
+// (element size, per-row multiplicity, dimension index) in the order of kr_snapshot_bufs
+enum { D_CLUSTERS, D_GROUPS, D_WTD, D_PODS, D_HEADS, D_JOBS, D_JSON };
+struct ColDesc { uint8_t elem, mult, dim; };
+const ColDesc kCols[] = {
+    {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {8, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {1, 1, D_CLUSTERS}, {1, 1, D_CLUSTERS},
+    {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {8, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS},
+    {1, 1, D_CLUSTERS}, {4, 5, D_CLUSTERS}, {1, 5, D_CLUSTERS}, {1, 5, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {4, 2, D_CLUSTERS},
+    {4, 4, D_CLUSTERS}, {1, 1, D_CLUSTERS}, {1, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS},
+    {4, 1, D_GROUPS}, {4, 1, D_GROUPS}, {4, 1, D_GROUPS}, {4, 1, D_GROUPS}, {4, 1, D_GROUPS}, {4, 1, D_GROUPS},
+    {4, 1, D_GROUPS}, {4, 1, D_GROUPS}, {4, 1, D_GROUPS},
+    {4, 1, D_WTD},
+    {4, 1, D_PODS}, {4, 1, D_PODS}, {4, 1, D_PODS}, {4, 1, D_PODS}, {4, 1, D_PODS}, {4, 1, D_PODS}, {4, 1, D_PODS},
+    {4, 1, D_HEADS}, {1, 1, D_HEADS}, {4, 1, D_HEADS}, {4, 1, D_HEADS}, {4, 1, D_HEADS}, {1, 1, D_HEADS}, {1, 1, D_HEADS}, {1, 32, D_HEADS},
+    {4, 1, D_JOBS}, {4, 1, D_JOBS}, {4, 1, D_JOBS}, {4, 1, D_CLUSTERS},
+    {1, 1, D_JSON},
+};
+constexpr int kNumCols = sizeof(kCols) / sizeof(kCols[0]);
+static_assert(sizeof(kr_snapshot_bufs) == kNumCols * sizeof(void *), "kCols must mirror kr_snapshot_bufs");
+static_assert(sizeof(SnapDev) == kNumCols * sizeof(void *), "SnapDev must mirror kr_snapshot_bufs");
+static_assert(sizeof(kr_cluster_result) == 96 && sizeof(kr_group_result) == 32 && sizeof(kr_job_result) == 8, "result record sizes");
+
+void dims_of(const kr_sizes &n, uint64_t d[7]) {
+  d[D_CLUSTERS] = n.n_clusters; d[D_GROUPS] = n.n_groups; d[D_WTD] = n.n_wtd; d[D_PODS] = n.n_pods;
+  d[D_HEADS] = n.n_heads; d[D_JOBS] = n.n_jobs; d[D_JSON] = n.json_bytes;
+}
+
+InLayout in_layout(const kr_sizes &n) {
+  InLayout L;
+  uint64_t d[7];
+  dims_of(n, d);
+  size_t o = 0;
+  for (int i = 0; i < kNumCols; i++) {
+    L.off[i] = o;
+    o = align_up(o + (size_t)kCols[i].elem * kCols[i].mult * d[kCols[i].dim]);
+  }
+  L.total = o;
+  return L;
+}
+
+struct OutLayout {  // results arena
+  size_t totals, clusters, hash, groups, wtd, sorted_idx, sorted_act, jobs, fixed_total, create, total;
+};
+OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
+  OutLayout L;
+  size_t o = 0;
+  L.totals = o; o = align_up(o + 16);
+  L.clusters = o; o = align_up(o + sizeof(kr_cluster_result) * (size_t)n.n_clusters);
+  L.hash = o; o = align_up(o + 32 * (size_t)n.n_clusters);
+  L.groups = o; o = align_up(o + sizeof(kr_group_result) * (size_t)n.n_groups);
+  L.wtd = o; o = align_up(o + 4 * (size_t)n.n_wtd);
+  L.sorted_idx = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.sorted_act = o; o = align_up(o + (size_t)n.n_pods);
+  L.jobs = o; o = align_up(o + sizeof(kr_job_result) * (size_t)n.n_jobs);
+  L.fixed_total = o;
+  L.create = o; o = align_up(o + 4 * (size_t)create_cap);
+  L.total = o;
+  return L;
+}
+
+struct ScratchLayout {
+  // 0xFF-initialised region first
+  size_t cl_keys, cl_vals, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
+  size_t wt_next, rows, keys0, keys1, vals0, vals1, hist, gacc, deferred, total;
+  uint32_t cl_slots, wt_slots, aux_slots, ntiles;
+};
+ScratchLayout scratch_layout(const kr_sizes &n) {
+  ScratchLayout L;
+  L.cl_slots = pow2_at_least(2ull * n.n_clusters);
+  L.wt_slots = pow2_at_least(2ull * n.n_wtd);
+  L.aux_slots = pow2_at_least(2ull * n.n_heads);
+  L.ntiles = (uint32_t)((n.n_pods + kSortTile - 1) / kSortTile);
+  if (L.ntiles == 0) L.ntiles = 1;
+  size_t o = 0;
+  L.cl_keys = o; o = align_up(o + 8 * (size_t)L.cl_slots);
+  L.cl_vals = o; o = align_up(o + 4 * (size_t)L.cl_slots);
+  L.wt_keys = o; o = align_up(o + 8 * (size_t)L.wt_slots);
+  L.wt_head = o; o = align_up(o + 4 * (size_t)L.wt_slots);
+  L.aux_keys = o; o = align_up(o + 4 * (size_t)L.aux_slots);
+  L.aux_vals = o; o = align_up(o + 4 * (size_t)L.aux_slots);
+  L.ff_total = o;
+  L.wt_next = o; o = align_up(o + 4 * (size_t)n.n_wtd);
+  L.rows = o; o = align_up(o + 16 * (size_t)n.n_pods);
+  L.keys0 = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.keys1 = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.vals0 = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.vals1 = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.hist = o; o = align_up(o + 4 * (size_t)kRadix * L.ntiles);
+  L.gacc = o; o = align_up(o + 16 * (size_t)n.n_groups);
+  L.deferred = o; o = align_up(o + (size_t)n.n_clusters);
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+struct kr_engine {
+  kr_config cfg{};
+  cudaStream_t sm = nullptr, sh = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+  cudaEvent_t ev_k[KR_MAX_KERNEL_TIMES + 1]{};
+  uint8_t *h_in = nullptr, *d_in = nullptr, *d_scratch = nullptr, *d_out = nullptr, *h_out = nullptr;
+  size_t in_cap = 0, scratch_cap = 0, out_cap = 0;
+  kr_sizes sizes{};
+  InLayout il{};
+  OutLayout ol{};
+  ScratchLayout sl{};
+  bool begun = false, committed = false, ran = false;
+  uint32_t n_recreate = 0;  // clusters with KR_CF_UPGRADE_RECREATE (decide phase 1 needed)
+  kr_profile prof{};
+  std::string err;
+  // kr_hash_batch staging
+  uint8_t *hb_h = nullptr, *hb_d = nullptr;
+  size_t hb_cap = 0;
+  int sm_count = 148;
+};
+
+namespace {
+
+int fail(kr_engine *e, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess) return fail(e, KR_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+kr_sizes cap_sizes(const kr_config &c) {
+  kr_sizes n;
+  n.n_clusters = c.max_clusters; n.n_groups = c.max_groups; n.n_wtd = c.max_wtd; n.n_pods = c.max_pods;
+  n.n_heads = c.max_heads; n.n_jobs = c.max_jobs; n.json_bytes = c.max_json_bytes;
+  return n;
+}
+
+void bind_in(const InLayout &L, uint8_t *base, void *struct_of_ptrs) {
+  void **p = reinterpret_cast<void **>(struct_of_ptrs);
+  for (int i = 0; i < kNumCols; i++) p[i] = base + L.off[i];
+}
+
+ResDev bind_out(const OutLayout &L, uint8_t *base) {
+  ResDev r;
+  r.totals = reinterpret_cast<uint32_t *>(base + L.totals);
+  r.clusters = reinterpret_cast<kr_cluster_result *>(base + L.clusters);
+  r.hash = reinterpret_cast<char *>(base + L.hash);
+  r.groups = reinterpret_cast<kr_group_result *>(base + L.groups);
+  r.wtd_pod_idx = reinterpret_cast<uint32_t *>(base + L.wtd);
+  r.sorted_pod_idx = reinterpret_cast<uint32_t *>(base + L.sorted_idx);
+  r.sorted_action = base + L.sorted_act;
+  r.jobs = reinterpret_cast<kr_job_result *>(base + L.jobs);
+  r.create_idx = reinterpret_cast<int32_t *>(base + L.create);
+  return r;
+}
+
+ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
+  ScratchDev s;
+  s.cl_keys = reinterpret_cast<uint64_t *>(b + L.cl_keys); s.cl_vals = reinterpret_cast<uint32_t *>(b + L.cl_vals); s.cl_mask = L.cl_slots - 1;
+  s.wt_keys = reinterpret_cast<uint64_t *>(b + L.wt_keys); s.wt_head = reinterpret_cast<uint32_t *>(b + L.wt_head);
+  s.wt_next = reinterpret_cast<uint32_t *>(b + L.wt_next); s.wt_mask = L.wt_slots - 1;
+  s.aux_keys = reinterpret_cast<uint32_t *>(b + L.aux_keys); s.aux_vals = reinterpret_cast<uint32_t *>(b + L.aux_vals); s.aux_mask = L.aux_slots - 1;
+  s.rows = reinterpret_cast<uint4 *>(b + L.rows);
+  s.keys[0] = reinterpret_cast<uint32_t *>(b + L.keys0); s.keys[1] = reinterpret_cast<uint32_t *>(b + L.keys1);
+  s.vals[0] = reinterpret_cast<uint32_t *>(b + L.vals0); s.vals[1] = reinterpret_cast<uint32_t *>(b + L.vals1);
+  s.hist = reinterpret_cast<uint32_t *>(b + L.hist);
+  s.gacc = reinterpret_cast<int32_t *>(b + L.gacc);
+  s.deferred = b + L.deferred;
+  return s;
+}
+
+// Launches the whole pass.  profile: serialise everything on stream M and bracket each kernel with events.
+int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
+  const kr_sizes &n = e->sizes;
+  SnapDev s;
+  bind_in(e->il, e->d_in, &s);
+  ResDev r = bind_out(e->ol, e->d_out);
+  ScratchDev sc = bind_scratch(e->sl, e->d_scratch);
+  Sizes z{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
+  cudaStream_t M = e->sm, H = profile ? e->sm : e->sh;
+  int k = 0;
+  auto mark = [&](const char *name) {
+    if (profile && k < KR_MAX_KERNEL_TIMES) { e->prof.kernel_name[k] = name; cudaEventRecord(e->ev_k[k], M); }
+    k++;
+  };
+  e->prof.n_kernels = 0;
+
+  // --- stream H: hash (only needs the committed snapshot)
+  const bool do_hash = !f.skip_hash && n.n_clusters > 0;
+  if (!profile) { CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0)); }
+  auto launch_hash = [&]() {
+    if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {
+      uint32_t blocks = (n.n_clusters + 31) / 32;
+      k_hash<1><<<blocks, 32, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash);
+    } else {
+      uint32_t blocks = (n.n_clusters + 127) / 128;
+      k_hash<4><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash);
+    }
+  };
+  if (!profile) {
+    if (do_hash) launch_hash();
+    else if (n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, H));
+    CK(cudaEventRecord(e->ev_hash, H));
+  }
+
+  // --- stream M
+  CK(cudaMemsetAsync(e->d_scratch, 0xFF, e->sl.ff_total, M));
+  if (n.n_wtd) CK(cudaMemsetAsync(r.wtd_pod_idx, 0xFF, 4 * (size_t)n.n_wtd, M));
+  CK(cudaMemsetAsync(r.totals, 0, 16, M));
+  if (n.n_clusters) CK(cudaMemsetAsync(sc.deferred, 0, n.n_clusters, M));
+  {
+    uint32_t items = n.n_clusters + n.n_groups + n.n_heads;
+    if (items) { mark("k_build_tables"); k_build_tables<<<(items + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
+  }
+  const uint32_t ntiles = e->sl.ntiles;
+  uint32_t bits = 1;
+  while ((1ull << bits) <= n.n_clusters) bits++;  // keys are in [0, n_clusters]
+  const int passes = (int)((bits + kRadixBits - 1) / kRadixBits);
+  const uint32_t *sorted_keys = sc.keys[0];
+  if (n.n_pods) {
+    mark("k_match");
+    k_match<<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+      if (p > 0) { mark("k_hist"); k_hist<<<ntiles, kSortThreads, 0, M>>>(sc.keys[cur], sc.hist, n.n_pods, p * kRadixBits); }
+      mark("k_scan_hist");
+      k_scan_hist<<<1, 1024, 0, M>>>(sc.hist, (uint32_t)kRadix * ntiles);
+      mark("k_scatter");
+      uint32_t *vout = (p == passes - 1) ? r.sorted_pod_idx : sc.vals[cur ^ 1];
+      k_scatter<<<ntiles, kSortThreads, 0, M>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1], vout, sc.hist, n.n_pods, p * kRadixBits, p == 0);
+      cur ^= 1;
+      if (p != passes - 1) { /* vals ping-pong follows keys */ }
+    }
+    sorted_keys = sc.keys[cur];
+    // vals ping-pong: pass p reads vals[cur_before] (except pass 0) and wrote vals[cur_after]; see k_scatter call above
+  }
+  DecideArgs da{s, sc, r, z, f, sorted_keys, 0};
+  {
+    uint32_t warps = n.n_clusters + 1;
+    mark("k_decide");
+    k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
+  }
+  if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
+  if (profile) {
+    if (do_hash) { mark("k_hash"); launch_hash(); }
+    else if (n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, M));
+  } else {
+    CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
+  }
+  if (e->n_recreate > 0 && do_hash) {
+    da.phase = 1;
+    uint32_t warps = n.n_clusters + 1;
+    mark("k_decide_phase1");
+    k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
+  }
+  if (n.n_groups) {
+    mark("k_scan_creates");
+    k_scan_creates<<<1, 1024, 0, M>>>(r, n.n_groups);
+    mark("k_create_fill");
+    k_create_fill<<<(n.n_groups + 3) / 4, 128, 0, M>>>(s, sc, r, z, f, e->cfg.max_creates);
+  }
+  if (profile && k <= KR_MAX_KERNEL_TIMES) cudaEventRecord(e->ev_k[k < KR_MAX_KERNEL_TIMES ? k : KR_MAX_KERNEL_TIMES], M);
+  e->prof.n_kernels = (uint32_t)k;
+  CK(cudaGetLastError());
+  return KR_OK;
+}
+
+int fetch_results(kr_engine *e, kr_results_view *out) {
+  const kr_sizes &n = e->sizes;
+  CK(cudaEventRecord(e->ev_b, e->sm));
+  CK(cudaMemcpyAsync(e->h_out, e->d_out, e->ol.fixed_total, cudaMemcpyDeviceToHost, e->sm));
+  CK(cudaStreamSynchronize(e->sm));
+  const uint32_t *tot = reinterpret_cast<const uint32_t *>(e->h_out + e->ol.totals);
+  uint32_t n_create = tot[0];
+  if (n_create > e->cfg.max_creates) {
+    CK(cudaEventRecord(e->ev_c, e->sm));
+    return fail(e, KR_E_CAPACITY, "pods to create (%u) exceed kr_config.max_creates (%u)", n_create, e->cfg.max_creates);
+  }
+  if (n_create) {
+    CK(cudaMemcpyAsync(e->h_out + e->ol.create, e->d_out + e->ol.create, 4 * (size_t)n_create, cudaMemcpyDeviceToHost, e->sm));
+  }
+  CK(cudaEventRecord(e->ev_c, e->sm));
+  CK(cudaStreamSynchronize(e->sm));
+  if (tot[3] & KR_TOTALS_ERR_MH_UNSUPPORTED)
+    return fail(e, KR_E_INVALID, "multi-host worker groups (numOfHosts>1 with RayMultiHostIndexing) are not handled by this engine build");
+  if (out) {
+    ResDev hr = bind_out(e->ol, e->h_out);
+    out->clusters = hr.clusters; out->hash = hr.hash; out->groups = hr.groups;
+    out->wtd_pod_idx = reinterpret_cast<const int32_t *>(hr.wtd_pod_idx);
+    out->sorted_pod_idx = hr.sorted_pod_idx; out->sorted_action = hr.sorted_action; out->create_idx = hr.create_idx; out->jobs = hr.jobs;
+    out->n_create_total = n_create; out->n_orphans = tot[1]; out->n_actions = tot[2]; out->reserved = 0;
+    (void)n;
+  }
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_c) == cudaSuccess) e->prof.d2h_ms = ms;
+  return KR_OK;
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+
+extern "C" {
+
+int kr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return KR_E_NO_DEVICE; }
+  return n;
+}
+
+int kr_engine_create(const kr_config *cfg, kr_engine **out) {
+  if (!cfg || !out) return KR_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return KR_E_NO_DEVICE; }
+  if (cfg->device < 0 || cfg->device >= ndev) return KR_E_INVALID;
+  kr_engine *e = new kr_engine();
+  e->cfg = *cfg;
+  auto bail = [&](int code) { kr_engine_destroy(e); return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(KR_E_CUDA);
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  kr_sizes cap = cap_sizes(*cfg);
+  e->in_cap = in_layout(cap).total;
+  e->scratch_cap = scratch_layout(cap).total;
+  e->out_cap = out_layout(cap, cfg->max_creates).total;
+  if (cudaStreamCreateWithFlags(&e->sm, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaStreamCreateWithFlags(&e->sh, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
+  cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_hash, cudaEventDisableTiming);
+  cudaEventCreate(&e->ev_a); cudaEventCreate(&e->ev_b); cudaEventCreate(&e->ev_c);
+  for (auto &ev : e->ev_k) cudaEventCreate(&ev);
+  if (cudaHostAlloc((void **)&e->h_in, e->in_cap, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaHostAlloc((void **)&e->h_out, e->out_cap, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaMalloc((void **)&e->d_in, e->in_cap) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaMalloc((void **)&e->d_scratch, e->scratch_cap) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
+  *out = e;
+  return KR_OK;
+}
+
+void kr_engine_destroy(kr_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->sm) cudaStreamSynchronize(e->sm);
+  if (e->sh) cudaStreamSynchronize(e->sh);
+  if (e->h_in) cudaFreeHost(e->h_in);
+  if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->hb_h) cudaFreeHost(e->hb_h);
+  if (e->d_in) cudaFree(e->d_in);
+  if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->d_out) cudaFree(e->d_out);
+  if (e->hb_d) cudaFree(e->hb_d);
+  for (auto ev : {e->ev_fork, e->ev_hash, e->ev_a, e->ev_b, e->ev_c}) if (ev) cudaEventDestroy(ev);
+  for (auto ev : e->ev_k) if (ev) cudaEventDestroy(ev);
+  if (e->sm) cudaStreamDestroy(e->sm);
+  if (e->sh) cudaStreamDestroy(e->sh);
+  delete e;
+}
+
+int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out) {
+  if (!e || !sizes || !out) return KR_E_INVALID;
+  const kr_config &c = e->cfg;
+  if (sizes->n_clusters > c.max_clusters || sizes->n_groups > c.max_groups || sizes->n_wtd > c.max_wtd || sizes->n_pods > c.max_pods ||
+      sizes->n_heads > c.max_heads || sizes->n_jobs > c.max_jobs || sizes->json_bytes > c.max_json_bytes)
+    return fail(e, KR_E_CAPACITY, "snapshot exceeds the engine capacities given to kr_engine_create");
+  if (sizes->n_clusters >= 0xFFFFFFF0u || sizes->n_pods >= 0xFFFFFFF0u) return fail(e, KR_E_CAPACITY, "too many rows");
+  CK(cudaSetDevice(c.device));
+  CK(cudaStreamSynchronize(e->sm));  // previous results are invalidated from here on
+  e->sizes = *sizes;
+  e->il = in_layout(*sizes);
+  e->ol = out_layout(*sizes, c.max_creates);
+  e->sl = scratch_layout(*sizes);
+  if (e->il.total > e->in_cap || e->ol.total > e->out_cap || e->sl.total > e->scratch_cap)
+    return fail(e, KR_E_CAPACITY, "internal: layout exceeds arena");
+  bind_in(e->il, e->h_in, out);
+  e->begun = true; e->committed = false; e->ran = false;
+  return KR_OK;
+}
+
+int kr_snapshot_commit(kr_engine *e) {
+  if (!e || !e->begun) return e ? fail(e, KR_E_STATE, "kr_snapshot_commit before kr_snapshot_begin") : KR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  // cheap host-side checks of the invariants the kernels rely on
+  kr_snapshot_bufs hb;
+  bind_in(e->il, e->h_in, &hb);
+  const kr_sizes &n = e->sizes;
+  uint32_t n_recreate = 0;
+  uint64_t goff = 0;
+  for (uint32_t c = 0; c < n.n_clusters; c++) {
+    if (hb.c_group_off[c] != goff) return fail(e, KR_E_INVALID, "cluster %u: groups must be stored in cluster order (group_off %u != %llu)", c, hb.c_group_off[c], (unsigned long long)goff);
+    if (hb.c_group_cnt[c] >= 0xFFFFu) return fail(e, KR_E_CAPACITY, "cluster %u has %u worker groups (limit 65534)", c, hb.c_group_cnt[c]);
+    goff += hb.c_group_cnt[c];
+    if (hb.c_json_off[c] & 15) return fail(e, KR_E_INVALID, "cluster %u: json offset not 16-byte aligned", c);
+    if (hb.c_json_off[c] + hb.c_json_len[c] > n.json_bytes) return fail(e, KR_E_INVALID, "cluster %u: json range outside arena", c);
+    if (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) n_recreate++;
+  }
+  if (goff != n.n_groups) return fail(e, KR_E_INVALID, "sum of group_cnt (%llu) != n_groups (%u)", (unsigned long long)goff, n.n_groups);
+  e->n_recreate = n_recreate;
+  CK(cudaEventRecord(e->ev_a, e->sm));
+  CK(cudaMemcpyAsync(e->d_in, e->h_in, e->il.total, cudaMemcpyHostToDevice, e->sm));
+  CK(cudaEventRecord(e->ev_b, e->sm));
+  CK(cudaStreamSynchronize(e->sm));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.h2d_ms = ms;
+  e->committed = true;
+  return KR_OK;
+}
+
+int kr_reconcile_device_only(kr_engine *e, const kr_flags *flags) {
+  if (!e || !flags) return KR_E_INVALID;
+  if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaEventRecord(e->ev_a, e->sm));
+  int rc = launch_pass(e, *flags, false);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_b, e->sm));
+  CK(cudaStreamSynchronize(e->sm));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
+  e->ran = true;
+  return KR_OK;
+}
+
+int kr_reconcile_batch(kr_engine *e, const kr_flags *flags, kr_results_view *out) {
+  if (!e || !flags || !out) return KR_E_INVALID;
+  if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaEventRecord(e->ev_a, e->sm));
+  int rc = launch_pass(e, *flags, false);
+  if (rc) return rc;
+  e->ran = true;
+  // ev_b is recorded at the head of fetch_results: kernels_ms = ev_a..ev_b, d2h_ms = ev_b..ev_c
+  rc = fetch_results(e, out);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
+  return rc;
+}
+
+int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile *prof) {
+  if (!e || !flags) return KR_E_INVALID;
+  if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaEventRecord(e->ev_a, e->sm));
+  int rc = launch_pass(e, *flags, true);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_b, e->sm));
+  CK(cudaStreamSynchronize(e->sm));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
+  uint32_t k = e->prof.n_kernels < KR_MAX_KERNEL_TIMES ? e->prof.n_kernels : KR_MAX_KERNEL_TIMES;
+  for (uint32_t i = 0; i < k; i++) {
+    float t = 0;
+    cudaEventElapsedTime(&t, e->ev_k[i], e->ev_k[i + 1]);
+    e->prof.kernel_ms[i] = t;
+  }
+  e->ran = true;
+  if (prof) *prof = e->prof;
+  return KR_OK;
+}
+
+int kr_results_fetch(kr_engine *e, kr_results_view *out) {
+  if (!e || !out) return KR_E_INVALID;
+  if (!e->ran) return fail(e, KR_E_STATE, "no pass has run on the committed snapshot");
+  CK(cudaSetDevice(e->cfg.device));
+  return fetch_results(e, out);
+}
+
+int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, uint32_t n, char *out32xN) {
+  if (!e || (!bytes && n) || !offsets || (!out32xN && n)) return KR_E_INVALID;
+  if (n == 0) return KR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  // staging layout: [aligned offsets (n+0) u64 | lens u32 | bytes, each message 16-byte aligned | out 32n]
+  size_t data = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (offsets[i + 1] < offsets[i]) return fail(e, KR_E_INVALID, "offsets must be non-decreasing");
+    if (offsets[i + 1] - offsets[i] > 0xFFFFFFFFull) return fail(e, KR_E_CAPACITY, "message %u longer than 4 GiB", i);
+    data += align_up(offsets[i + 1] - offsets[i], 16);
+  }
+  size_t o_off = 0, o_len = align_up(8 * (size_t)n), o_data = align_up(o_len + 4 * (size_t)n), o_out = align_up(o_data + data + 16), total = o_out + 32 * (size_t)n;
+  if (total > e->hb_cap) {
+    if (e->hb_h) cudaFreeHost(e->hb_h);
+    if (e->hb_d) cudaFree(e->hb_d);
+    e->hb_h = nullptr; e->hb_d = nullptr; e->hb_cap = 0;
+    size_t cap = total + total / 4;
+    CK(cudaHostAlloc((void **)&e->hb_h, cap, cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&e->hb_d, cap));
+    e->hb_cap = cap;
+  }
+  uint64_t *so = reinterpret_cast<uint64_t *>(e->hb_h + o_off);
+  uint32_t *sl = reinterpret_cast<uint32_t *>(e->hb_h + o_len);
+  size_t cur = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    size_t len = offsets[i + 1] - offsets[i];
+    so[i] = cur; sl[i] = (uint32_t)len;
+    memcpy(e->hb_h + o_data + cur, bytes + offsets[i], len);
+    size_t pad = align_up(len, 16) - len;
+    if (pad) memset(e->hb_h + o_data + cur + len, 0, pad);
+    cur += len + pad;
+  }
+  CK(cudaMemcpyAsync(e->hb_d, e->hb_h, o_data + data, cudaMemcpyHostToDevice, e->sh));
+  const uint8_t *db = e->hb_d + o_data;
+  const uint64_t *doff = reinterpret_cast<const uint64_t *>(e->hb_d + o_off);
+  const uint32_t *dlen = reinterpret_cast<const uint32_t *>(e->hb_d + o_len);
+  char *dout = reinterpret_cast<char *>(e->hb_d + o_out);
+  if (n <= (uint32_t)e->sm_count * 4 * 32) k_hash<1><<<(n + 31) / 32, 32, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout);
+  else k_hash<4><<<(n + 127) / 128, 128, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->hb_h + o_out, dout, 32 * (size_t)n, cudaMemcpyDeviceToHost, e->sh));
+  CK(cudaStreamSynchronize(e->sh));
+  memcpy(out32xN, e->hb_h + o_out, 32 * (size_t)n);
+  return KR_OK;
+}
+
+int kr_last_profile(kr_engine *e, kr_profile *prof) {
+  if (!e || !prof) return KR_E_INVALID;
+  *prof = e->prof;
+  return KR_OK;
+}
+
+int kr_group_results_device(kr_engine *e, const void **dev_ptr, uint64_t *bytes) {
+  if (!e || !dev_ptr || !bytes) return KR_E_INVALID;
+  if (!e->ran) return fail(e, KR_E_STATE, "no pass has run");
+  *dev_ptr = e->d_out + e->ol.groups;
+  *bytes = sizeof(kr_group_result) * (uint64_t)e->sizes.n_groups;
+  return KR_OK;
+}
+
+const char *kr_last_error(kr_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int kr_algorithmic_bytes(kr_engine *e, uint64_t *pass_bytes, uint64_t *hash_bytes, uint64_t *match_bytes) {
+  if (!e || !e->begun) return KR_E_INVALID;
+  const kr_sizes &n = e->sizes;
+  // compulsory traffic only — every input column read once, every output written once
+  uint64_t json = 0;
+  if (e->committed) {
+    kr_snapshot_bufs hb;
+    bind_in(e->il, e->h_in, &hb);
+    for (uint32_t c = 0; c < n.n_clusters; c++) json += hb.c_json_len[c];
+  } else json = n.json_bytes;
+  uint64_t hashb = json + 32ull * n.n_clusters;
+  uint64_t matchb = 144ull * n.n_clusters - 32ull * n.n_clusters + 56ull * n.n_groups + 4ull * n.n_wtd + 33ull * n.n_pods;
+  if (pass_bytes) *pass_bytes = hashb + matchb;
+  if (hash_bytes) *hash_bytes = hashb;
+  if (match_bytes) *match_bytes = matchb;
+  return KR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,990 @@
+// kr_kernels.cuh — sm_100a kernels of the batched reconcile engine.
+//
+// Integer / hash work: no tensor cores.  What matters here: coalesced SoA column streaming,
+// shared-memory staging (hash chunks, per-tile digit counters, per-warp group accumulators), warp-ballot /
+// match_any group-by, grids sized in multiples of the SM count.
+//
+// Pipeline of one pass (engine stream M unless noted):
+//   k_build_tables  cluster table (ns,name)->idx, workersToDelete-name table, head-aux table
+//   k_match         per pod: label/selector match -> cluster idx + group slot, 16-byte pod row, radix digit histogram
+//   k_scan_hist / k_scatter / k_hist   stable LSD radix sort of pod indices by cluster idx (list order kept)
+//   k_decide        one warp per RayCluster: head decision, per-group diff, ordered deletes, status roll-up
+//   k_scan_creates / k_create_fill     replica-index allocation for pods to create
+//   k_jobs          RayJob -> RayCluster status roll-up join
+//   k_hash          (stream H, concurrent) SHA-1 + base32hex of every muted-spec JSON
+//
+// Reference semantics restated here are cited per function (paths relative to
+// ray-operator/controllers/ray/ in ray-project/kuberay).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kr_engine.h"
+
+namespace kr {
+
+// ------------------------------------------------------------------------------------------------ device views
+
+struct SnapDev {  // device mirror of kr_snapshot_bufs
+  const uint32_t *c_ns_id, *c_name_id;
+  const uint64_t *c_uid_hash;
+  const uint32_t *c_flags;
+  const uint8_t *c_suspend_status, *c_ext_err_kind;
+  const uint32_t *c_ext_err_msg_id, *c_group_off, *c_group_cnt;
+  const uint64_t *c_json_off;
+  const uint32_t *c_json_len;
+  const uint8_t *c_old_state;
+  const int32_t *c_old_counts;
+  const uint8_t *c_old_cond_status, *c_old_cond_variant;
+  const uint32_t *c_old_cond_reason_id, *c_old_cond_msg_id, *c_old_head_ids;
+  const uint8_t *c_svc_count, *c_svc_ip_kind;
+  const uint32_t *c_svc_ip_id, *c_svc_name_id;
+  const uint32_t *g_cluster_idx, *g_name_id;
+  const int32_t *g_replicas, *g_min, *g_max, *g_num_hosts;
+  const uint32_t *g_flags, *g_wtd_off, *g_wtd_cnt;
+  const uint32_t *w_name_id;
+  const uint32_t *p_ns_id, *p_cluster_name_id, *p_group_name_id, *p_name_id, *p_packed;
+  const int32_t *p_replica_index;
+  const uint32_t *p_replica_name_id;
+  const uint32_t *h_pod_idx;
+  const uint8_t *h_ready_status;
+  const uint32_t *h_ready_reason_id, *h_ready_msg_id, *h_pod_ip_id;
+  const uint8_t *h_annot_state, *h_version_state, *h_annot_hash;
+  const uint32_t *j_ns_id, *j_cluster_name_id, *j_summary_id, *c_summary_id;
+  const uint8_t *json;
+};
+
+struct ResDev {  // device results arena
+  kr_cluster_result *clusters;
+  char *hash;
+  kr_group_result *groups;
+  uint32_t *wtd_pod_idx;  // unsigned for atomicMin; 0xFFFFFFFF == -1 == NotFound
+  uint32_t *sorted_pod_idx;
+  uint8_t *sorted_action;
+  int32_t *create_idx;
+  kr_job_result *jobs;
+  uint32_t *totals;  // [0]=n_create_total [1]=n_orphans [2]=n_actions [3]=error flags
+};
+
+struct ScratchDev {
+  uint64_t *cl_keys; uint32_t *cl_vals; uint32_t cl_mask;      // cluster table
+  uint64_t *wt_keys; uint32_t *wt_head; uint32_t *wt_next; uint32_t wt_mask;  // workersToDelete-name table
+  uint32_t *aux_keys; uint32_t *aux_vals; uint32_t aux_mask;   // pod idx -> head-aux row
+  uint4 *rows;                                                 // 16-byte pod rows, original order
+  uint32_t *keys[2]; uint32_t *vals[2];                        // radix ping-pong
+  uint32_t *hist;                                              // [256 * ntiles] digit-major
+  int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
+  uint8_t *deferred;                                           // [n_clusters] decide phase 0 left it for phase 1 (needs the hash)
+};
+
+struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
+
+// row.w layout: low 16 bits = p_packed low bits (+ KR_ROW_WTD_OWN), high 16 bits = group slot inside the cluster
+#define KR_ROW_WTD_OWN (1u << 11)   // named by its own group's scaleStrategy.workersToDelete
+#define KR_ROW_NO_GROUP 0xFFFFu
+#define KR_TOTALS_ERR_MH_UNSUPPORTED 1u
+
+// error bits in totals[3]
+#define KR_DEVERR_TABLE_FULL 2u
+
+static constexpr int kSortThreads = 256;
+static constexpr int kSortItems = 8;
+static constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per tile
+static constexpr int kRadixBits = 8;
+static constexpr int kRadix = 1 << kRadixBits;
+
+// ------------------------------------------------------------------------------------------------ small helpers
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint64_t key2(uint32_t a, uint32_t b) { return ((uint64_t)a << 32) | b; }
+#define KR_EMPTY64 0xFFFFFFFFFFFFFFFFull
+#define KR_EMPTY32 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__device__ __forceinline__ uint32_t pp_node_type(uint32_t f) { return (f >> KR_PP_NODE_TYPE_SHIFT) & 3u; }
+__device__ __forceinline__ uint32_t pp_phase(uint32_t f) { return (f >> KR_PP_PHASE_SHIFT) & 7u; }
+__device__ __forceinline__ uint32_t pp_ready(uint32_t f) { return (f >> KR_PP_READY_SHIFT) & 3u; }
+
+// shouldDeletePod (raycluster_controller.go:1181-1231)
+__device__ __forceinline__ bool should_delete(uint32_t f) {
+  uint32_t ph = pp_phase(f);
+  return ph == KR_PHASE_FAILED || ph == KR_PHASE_SUCCEEDED ||
+         (ph == KR_PHASE_RUNNING && (f & KR_PP_RAY_TERMINATED) && (f & KR_PP_RESTART_NEVER));
+}
+
+// utils.GetWorkerGroupDesiredReplicas (utils/util.go:386-404); int32 multiply wraps like Go's
+__device__ __forceinline__ int32_t desired_replicas(int32_t replicas, int32_t mn, int32_t mx, int32_t hosts, uint32_t gf) {
+  int32_t minr = (gf & KR_GF_MIN_NIL) ? 0 : mn;
+  int32_t maxr = (gf & KR_GF_MAX_NIL) ? INT32_MAX : mx;
+  if (gf & KR_GF_SUSPEND) return 0;
+  int32_t w;
+  if ((gf & KR_GF_REPLICAS_NIL) || replicas < minr) w = minr;
+  else if (replicas > maxr) w = maxr;
+  else w = replicas;
+  return (int32_t)((uint32_t)w * (uint32_t)hosts);
+}
+
+__device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uint32_t name, uint32_t &out) {
+  if (name == 0) return false;
+  uint64_t k = key2(ns, name);
+  uint32_t i = (uint32_t)mix64(k) & sc.cl_mask;
+  while (true) {
+    uint64_t kk = __ldg(&sc.cl_keys[i]);
+    if (kk == k) { out = __ldg(&sc.cl_vals[i]); return true; }
+    if (kk == KR_EMPTY64) return false;
+    i = (i + 1) & sc.cl_mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_build_tables
+// One thread per cluster / workersToDelete entry / head-aux row.  Tables were memset to 0xFF.
+
+__global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n.n_clusters) {
+    uint64_t k = key2(s.c_ns_id[t], s.c_name_id[t]);
+    uint32_t i = (uint32_t)mix64(k) & sc.cl_mask;
+    while (true) {
+      unsigned long long prev = atomicCAS((unsigned long long *)&sc.cl_keys[i], KR_EMPTY64, k);
+      if (prev == KR_EMPTY64 || prev == k) { atomicMin(&sc.cl_vals[i], t); break; }  // duplicate (ns,name): lowest index wins
+      i = (i + 1) & sc.cl_mask;
+    }
+    return;
+  }
+  t -= n.n_clusters;
+  if (t < n.n_groups) {
+    // every workersToDelete name of this group: Delete(ns of the cluster, name) (raycluster_controller.go:817-822)
+    uint32_t c = s.g_cluster_idx[t];
+    uint32_t ns = s.c_ns_id[c];
+    uint32_t off = s.g_wtd_off[t], cnt = s.g_wtd_cnt[t];
+    for (uint32_t w = 0; w < cnt; w++) {
+      uint32_t e = off + w;
+      uint64_t k = key2(ns, s.w_name_id[e]);
+      uint32_t i = (uint32_t)mix64(k) & sc.wt_mask;
+      while (true) {
+        unsigned long long prev = atomicCAS((unsigned long long *)&sc.wt_keys[i], KR_EMPTY64, k);
+        if (prev == KR_EMPTY64 || prev == k) {
+          // push e on the slot's chain
+          uint32_t old = atomicExch(&sc.wt_head[i], e);
+          sc.wt_next[e] = old;  // KR_EMPTY32 terminates (wt_head memset to 0xFF)
+          break;
+        }
+        i = (i + 1) & sc.wt_mask;
+      }
+    }
+    return;
+  }
+  t -= n.n_groups;
+  if (t < n.n_heads) {
+    uint32_t p = s.h_pod_idx[t];
+    uint32_t i = mix32(p) & sc.aux_mask;
+    while (true) {
+      uint32_t prev = atomicCAS(&sc.aux_keys[i], KR_EMPTY32, p);
+      if (prev == KR_EMPTY32 || prev == p) { atomicMin(&sc.aux_vals[i], t); break; }
+      i = (i + 1) & sc.aux_mask;
+    }
+  }
+}
+
+__device__ __forceinline__ int32_t aux_lookup(const ScratchDev &sc, uint32_t p) {
+  uint32_t i = mix32(p) & sc.aux_mask;
+  while (true) {
+    uint32_t k = sc.aux_keys[i];
+    if (k == p) return (int32_t)sc.aux_vals[i];
+    if (k == KR_EMPTY32) return -1;
+    i = (i + 1) & sc.aux_mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_match
+// The selector match (common/association.go:83-130): pod -> RayCluster by (namespace, ray.io/cluster), then
+// ray.io/group against the cluster's worker groups.  Streams 7 coalesced columns (28 B/pod), writes one 16-byte row
+// + 4-byte sort key per pod, and the pass-0 digit histogram of its tile.
+
+__global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc, ResDev r, Sizes n, int has_wtd) {
+  __shared__ uint32_t s_hist[kRadix];
+  const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = tile * kSortTile + warp * (32 * kSortItems) + lane;
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    uint32_t p = base + it * 32;
+    if (p >= n.n_pods) continue;
+    uint32_t ns = __ldg(&s.p_ns_id[p]), cn = __ldg(&s.p_cluster_name_id[p]), gn = __ldg(&s.p_group_name_id[p]);
+    uint32_t nm = __ldg(&s.p_name_id[p]), pk = __ldg(&s.p_packed[p]);
+    int32_t ri = __ldg(&s.p_replica_index[p]);
+    uint32_t rn = __ldg(&s.p_replica_name_id[p]);
+    uint32_t c = n.n_clusters, slot = KR_ROW_NO_GROUP, g0 = 0;
+    uint32_t found;
+    if (cl_lookup(sc, ns, cn, found)) {
+      c = found;
+      g0 = __ldg(&s.c_group_off[c]);
+      uint32_t G = __ldg(&s.c_group_cnt[c]);
+      if (gn != 0)
+        for (uint32_t gi = 0; gi < G; gi++)
+          if (__ldg(&s.g_name_id[g0 + gi]) == gn) { slot = gi; break; }  // group names are unique (pkg/webhooks/v1/raycluster_webhook.go:74)
+    }
+    uint32_t flags = pk & 0x7FFu;
+    if (has_wtd) {
+      // label-set intersection against the (tiny) workersToDelete-name table
+      uint64_t k = key2(ns, nm);
+      uint32_t i = (uint32_t)mix64(k) & sc.wt_mask;
+      while (true) {
+        uint64_t kk = __ldg(&sc.wt_keys[i]);
+        if (kk == KR_EMPTY64) break;
+        if (kk == k) {
+          for (uint32_t e = sc.wt_head[i]; e != KR_EMPTY32; e = sc.wt_next[e]) {
+            atomicMin(&r.wtd_pod_idx[e], p);
+            // is e one of this pod's own group's names?  (group g lists wtd entries [off, off+cnt))
+            if (slot != KR_ROW_NO_GROUP) {
+              uint32_t g = g0 + slot;
+              uint32_t off = __ldg(&s.g_wtd_off[g]);
+              if (e >= off && e < off + __ldg(&s.g_wtd_cnt[g])) flags |= KR_ROW_WTD_OWN;
+            }
+          }
+          break;
+        }
+        i = (i + 1) & sc.wt_mask;
+      }
+    }
+    sc.rows[p] = make_uint4(nm, rn, (uint32_t)ri, (slot << 16) | flags);
+    sc.keys[0][p] = c;
+    atomicAdd(&s_hist[c & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  sc.hist[threadIdx.x * ntiles + tile] = s_hist[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort (stable LSD)
+
+__global__ void __launch_bounds__(kSortThreads) k_hist(const uint32_t *__restrict__ keys, uint32_t *__restrict__ hist, uint32_t n, int shift) {
+  __shared__ uint32_t s_hist[kRadix];
+  const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = tile * kSortTile + threadIdx.x;
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    uint32_t i = base + it * kSortThreads;
+    if (i < n) atomicAdd(&s_hist[(__ldg(&keys[i]) >> shift) & (kRadix - 1)], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * ntiles + tile] = s_hist[threadIdx.x];
+}
+
+// exclusive scan of m = 256*ntiles counters in place; one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_hist(uint32_t *__restrict__ a, uint32_t m) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t per = (m + 1023) / 1024;
+  const uint32_t lo = min(t * per, m), hi = min(lo + per, m);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += a[i];
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = s_warp[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += y; }
+    s_warp[lane] = v;
+  }
+  __syncthreads();
+  uint32_t run = x - sum + (w ? s_warp[w - 1] : 0);
+  for (uint32_t i = lo; i < hi; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+}
+
+// Stable scatter of one tile: warp-match ranking keeps equal digits in original order.
+// first_pass: values are the identity (pod index == position). write_keys: needed unless the consumer only wants values.
+__global__ void __launch_bounds__(kSortThreads) k_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                          uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                          const uint32_t *__restrict__ hist, uint32_t n, int shift, int first_pass) {
+  __shared__ uint32_t s_cnt[kSortThreads / 32][kRadix];
+  __shared__ uint32_t s_base[kRadix];
+  const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < kRadix; i += 32) s_cnt[warp][i] = 0;
+  s_base[threadIdx.x] = hist[threadIdx.x * ntiles + tile];
+  __syncwarp();
+  const uint32_t base = tile * kSortTile + warp * (32 * kSortItems) + lane;
+  uint32_t key[kSortItems], rank[kSortItems];
+  const uint32_t lt = lanemask_lt();
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    uint32_t i = base + it * 32;
+    bool valid = i < n;
+    key[it] = valid ? __ldg(&keys_in[i]) : 0u;
+    uint32_t d = valid ? ((key[it] >> shift) & (kRadix - 1)) : kRadix;  // sentinel digit for the ragged tail
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    uint32_t prefix = __popc(peers & lt);
+    uint32_t old = 0;
+    if (valid) old = s_cnt[warp][d];
+    __syncwarp();
+    if (valid && prefix == 0) s_cnt[warp][d] = old + __popc(peers);
+    __syncwarp();
+    rank[it] = old + prefix;
+  }
+  __syncthreads();
+  {  // per digit: exclusive scan over the 8 warps, add the tile's global base
+    uint32_t d = threadIdx.x, run = s_base[d];
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; w++) { uint32_t v = s_cnt[w][d]; s_cnt[w][d] = run; run += v; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    uint32_t i = base + it * 32;
+    if (i >= n) continue;
+    uint32_t d = (key[it] >> shift) & (kRadix - 1);
+    uint32_t dst = s_cnt[warp][d] + rank[it];
+    keys_out[dst] = key[it];
+    vals_out[dst] = first_pass ? i : __ldg(&vals_in[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_decide
+
+#define KR_SMEM_GROUPS 32  // clusters with more worker groups than this spill their accumulators to global scratch
+static constexpr int kDecideWarps = 4;
+
+// group processing modes (internal)
+enum { GM_UNPROCESSED = 0, GM_SKIP = 1, GM_SUSPENDED = 2, GM_UNHEALTHY = 3, GM_NORMAL = 4, GM_MULTIHOST = 5 };
+
+// first index i in [0,n) with a[i] >= v; warp-cooperative 32-ary search, result uniform across the warp
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict__ a, uint32_t n, uint32_t v, uint32_t lane) {
+  uint32_t lo = 0, hi = n;  // answer in [lo, hi]
+  while (hi - lo > 32) {
+    uint32_t step = (hi - lo + 31) / 32;  // probe points lo + (l+1)*step - 1
+    uint32_t idx = lo + (lane + 1) * step - 1;
+    bool ge = (idx >= hi) ? true : (__ldg(&a[idx]) >= v);
+    uint32_t b = __ballot_sync(0xFFFFFFFFu, ge);
+    uint32_t first = __ffs(b) - 1;  // b != 0 because the last probe is >= hi or ge
+    uint32_t nlo = lo + first * step, nhi = min(hi, lo + (first + 1) * step - 1);
+    lo = nlo; hi = nhi;
+  }
+  uint32_t idx = lo + lane;
+  bool ge = (idx >= hi) ? true : (__ldg(&a[idx]) >= v);
+  uint32_t b = __ballot_sync(0xFFFFFFFFu, ge);
+  return lo + (__ffs(b) - 1);
+}
+
+struct DecideArgs {
+  SnapDev s; ScratchDev sc; ResDev r; Sizes n; kr_flags f;
+  const uint32_t *sorted_keys;  // cluster idx per sorted position
+  int phase;                    // 0: everything that does not need the hash; 1: only clusters deferred by phase 0
+};
+
+// calculateStatus (raycluster_controller.go:1552-1719) + InconsistentRayClusterStatus (utils/consistency.go:16-34).
+// Scalar code, executed by lane 0 only.
+__device__ void status_rollup(const DecideArgs &a, uint32_t c, kr_cluster_result &cr, uint32_t P, uint32_t n_heads, int32_t head_pod,
+                              uint32_t head_name_id, int32_t ready, int32_t available, bool all_running) {
+  const SnapDev &s = a.s;
+  const uint32_t cf = s.c_flags[c];
+  const bool gate = a.f.gate_status_conditions != 0;
+  const bool reconcile_err = cr.err_kind != KR_ERR_NONE;
+  const uint8_t ek = s.c_ext_err_kind[c];
+  uint8_t cst[KR_NUM_CONDS], cvr[KR_NUM_CONDS];
+#pragma unroll
+  for (int k = 0; k < KR_NUM_CONDS; k++) { cst[k] = s.c_old_cond_status[5 * (size_t)c + k]; cvr[k] = s.c_old_cond_variant[5 * (size_t)c + k]; }
+  uint32_t hpr_reason = s.c_old_cond_reason_id[c], hpr_msg = s.c_old_cond_msg_id[2 * (size_t)c], rf_msg = s.c_old_cond_msg_id[2 * (size_t)c + 1];
+  if (gate) {  // :1563-1577
+    if (reconcile_err) {
+      if (ek >= KR_EXT_ERR_FAILED_DELETE_ALL_PODS && ek <= KR_EXT_ERR_FAILED_CREATE_WORKER_POD) {
+        cst[KR_COND_REPLICA_FAILURE] = KR_COND_TRUE; cvr[KR_COND_REPLICA_FAILURE] = ek; rf_msg = s.c_ext_err_msg_id[c];
+      }
+    } else {
+      cst[KR_COND_REPLICA_FAILURE] = KR_COND_ABSENT; cvr[KR_COND_REPLICA_FAILURE] = KR_CV_NONE; rf_msg = 0;
+    }
+  }
+  int32_t desired = 0, minr = 0; long long maxr = 0;  // utils/util.go:407-442
+  const uint32_t G = s.c_group_cnt[c], g0 = s.c_group_off[c];
+  for (uint32_t gi = 0; gi < G; gi++) {
+    uint32_t g = g0 + gi, gf = s.g_flags[g];
+    int32_t hosts = s.g_num_hosts[g];
+    desired = (int32_t)((uint32_t)desired + (uint32_t)desired_replicas(s.g_replicas[g], s.g_min[g], s.g_max[g], hosts, gf));
+    if (gf & KR_GF_SUSPEND) continue;
+    int32_t mn = (gf & KR_GF_MIN_NIL) ? 0 : s.g_min[g];
+    int32_t mx = (gf & KR_GF_MAX_NIL) ? INT32_MAX : s.g_max[g];
+    minr = (int32_t)((uint32_t)minr + (uint32_t)mn * (uint32_t)hosts);
+    maxr += (long long)mx * (long long)hosts;
+  }
+  int32_t maxc = maxr > INT32_MAX ? INT32_MAX : (maxr < INT32_MIN ? INT32_MIN : (int32_t)maxr);  // utils/util.go:284-292
+
+  cr.n_pods = (int32_t)P; cr.n_heads = (int32_t)n_heads; cr.head_pod_idx = head_pod;
+  uint8_t serr = KR_SERR_NONE;  // :1608-1611, :1785-1806, :1721-1745
+  if (n_heads > 1) serr = KR_SERR_MULTIPLE_HEADS;
+  else if (s.c_svc_count[c] == 0) serr = KR_SERR_NO_HEAD_SERVICE;
+  else if (s.c_svc_count[c] > 1) serr = KR_SERR_MULTIPLE_HEAD_SERVICES;
+  else if (s.c_svc_ip_kind[c] == KR_SVCIP_EMPTY) serr = KR_SERR_EMPTY_SERVICE_IP;
+  cr.status_err = serr;
+  if (serr != KR_SERR_NONE) return;
+
+  const uint8_t old_state = s.c_old_state[c];
+  uint8_t new_state = old_state;
+  bool reason_cleared = false;
+  if (!reconcile_err && (long long)P == (long long)desired + 1 && all_running) { new_state = KR_STATE_READY; reason_cleared = true; }  // :1599-1604
+
+  uint32_t head_pod_ip = 0, head_pod_name = 0;
+  int32_t aux = -1;
+  if (n_heads == 1) {
+    aux = aux_lookup(a.sc, (uint32_t)head_pod);
+    head_pod_ip = aux >= 0 ? s.h_pod_ip_id[aux] : 0;
+    head_pod_name = head_name_id;
+  }
+  if (gate) {
+    if (n_heads == 0) {  // :1613-1619
+      cst[KR_COND_HEAD_POD_READY] = KR_COND_FALSE; cvr[KR_COND_HEAD_POD_READY] = KR_CV_HEAD_NOT_FOUND;
+      hpr_reason = a.f.id_head_not_found_reason; hpr_msg = a.f.id_head_not_found_msg;
+    } else {             // :1621-1622
+      cst[KR_COND_HEAD_POD_READY] = aux >= 0 ? s.h_ready_status[aux] : (uint8_t)KR_COND_FALSE;
+      cvr[KR_COND_HEAD_POD_READY] = KR_CV_HEAD_FROM_POD;
+      hpr_reason = aux >= 0 ? s.h_ready_reason_id[aux] : 0; hpr_msg = aux >= 0 ? s.h_ready_msg_id[aux] : 0;
+    }
+    const uint8_t ss = s.c_suspend_status[c];
+    if (cst[KR_COND_PROVISIONED] != KR_COND_TRUE && ss != KR_SUSPEND_SUSPENDED) {  // :1625-1644
+      if (all_running) { cst[KR_COND_PROVISIONED] = KR_COND_TRUE; cvr[KR_COND_PROVISIONED] = KR_CV_PROV_ALL_READY; }
+      else { cst[KR_COND_PROVISIONED] = KR_COND_FALSE; cvr[KR_COND_PROVISIONED] = KR_CV_PROV_PROVISIONING; }
+    }
+    if (ss == KR_SUSPEND_SUSPENDING) {  // :1646-1693
+      if (P == 0) {
+        cst[KR_COND_PROVISIONED] = KR_COND_FALSE; cvr[KR_COND_PROVISIONED] = KR_CV_PROV_SUSPENDED;
+        cst[KR_COND_SUSPENDING] = KR_COND_FALSE; cvr[KR_COND_SUSPENDING] = KR_CV_CANONICAL;
+        cst[KR_COND_SUSPENDED] = KR_COND_TRUE; cvr[KR_COND_SUSPENDED] = KR_CV_CANONICAL;
+      }
+    } else if (ss == KR_SUSPEND_SUSPENDED) {
+      if (cf & KR_CF_SUSPEND_SET_FALSE) { cst[KR_COND_SUSPENDED] = KR_COND_FALSE; cvr[KR_COND_SUSPENDED] = KR_CV_CANONICAL; }
+    } else {
+      cst[KR_COND_SUSPENDED] = KR_COND_FALSE; cvr[KR_COND_SUSPENDED] = KR_CV_CANONICAL;
+      cst[KR_COND_SUSPENDING] = (cf & KR_CF_SUSPEND) ? KR_COND_TRUE : KR_COND_FALSE; cvr[KR_COND_SUSPENDING] = KR_CV_CANONICAL;
+    }
+  }
+  if ((cf & KR_CF_SUSPEND) && P == 0) new_state = KR_STATE_SUSPENDED;  // :1696-1698
+
+  uint32_t svc_ip = s.c_svc_ip_id[c];
+  if (s.c_svc_ip_kind[c] == KR_SVCIP_NONE) svc_ip = (n_heads == 1) ? head_pod_ip : 0;  // :1732-1742
+  uint32_t head_ids[4] = {head_pod_ip, svc_ip, head_pod_name, s.c_svc_name_id[c]};
+
+  cr.new_state = new_state;
+  cr.state_changed = new_state != old_state;
+  cr.counts[0] = ready; cr.counts[1] = available; cr.counts[2] = desired; cr.counts[3] = minr; cr.counts[4] = maxc;
+#pragma unroll
+  for (int k = 0; k < KR_NUM_CONDS; k++) { cr.cond_status[k] = cst[k]; cr.cond_variant[k] = cvr[k]; }
+  cr.head_ready_reason_id = hpr_reason; cr.head_ready_msg_id = hpr_msg;
+#pragma unroll
+  for (int k = 0; k < 4; k++) cr.head_ids[k] = head_ids[k];
+
+  bool inc = new_state != old_state;  // utils/consistency.go:16-34
+  if (reason_cleared && (cf & KR_CF_OLD_REASON_NONEMPTY)) inc = true;
+#pragma unroll
+  for (int k = 0; k < 5; k++) if (s.c_old_counts[5 * (size_t)c + k] != cr.counts[k]) inc = true;
+  if (cf & KR_CF_ENDPOINTS_CHANGED) inc = true;
+#pragma unroll
+  for (int k = 0; k < 4; k++) if (s.c_old_head_ids[4 * (size_t)c + k] != head_ids[k]) inc = true;
+#pragma unroll
+  for (int k = 0; k < KR_NUM_CONDS; k++) {
+    uint8_t os = s.c_old_cond_status[5 * (size_t)c + k], ov = s.c_old_cond_variant[5 * (size_t)c + k];
+    if (os != cst[k]) { inc = true; continue; }
+    if (cst[k] == KR_COND_ABSENT) continue;
+    if (k == KR_COND_HEAD_POD_READY) {
+      if (s.c_old_cond_reason_id[c] != hpr_reason || s.c_old_cond_msg_id[2 * (size_t)c] != hpr_msg) inc = true;
+    } else if (k == KR_COND_REPLICA_FAILURE) {
+      if (ov != cvr[k] || s.c_old_cond_msg_id[2 * (size_t)c + 1] != rf_msg) inc = true;
+    } else if (ov != cvr[k]) inc = true;
+  }
+  cr.needs_status_write = inc ? 1 : 0;
+}
+
+// reconcilePods (raycluster_controller.go:619-935) for one RayCluster, by one warp.
+__global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
+  __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
+  __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = blockIdx.x * kDecideWarps + warp;
+  const SnapDev &s = a.s;
+  const uint32_t Nc = a.n.n_clusters, Np = a.n.n_pods;
+  if (c > Nc) return;
+  const uint32_t lt = lanemask_lt();
+
+  if (c == Nc) {  // the orphan bucket: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot
+    if (a.phase != 0) return;
+    uint32_t st = warp_lower_bound(a.sorted_keys, Np, Nc, lane);
+    for (uint32_t i = st + lane; i < Np; i += 32) a.r.sorted_action[i] = KR_ACT_ORPHAN;
+    if (lane == 0) a.r.totals[1] = Np - st;
+    return;
+  }
+  if (a.phase == 1 && !a.sc.deferred[c]) return;
+
+  const uint32_t seg0 = warp_lower_bound(a.sorted_keys, Np, c, lane);
+  const uint32_t seg1 = warp_lower_bound(a.sorted_keys, Np, c + 1, lane);
+  const uint32_t P = seg1 - seg0;
+  const uint32_t cf = s.c_flags[c];
+  const uint32_t G = s.c_group_cnt[c], g0 = s.c_group_off[c];
+  const bool gate = a.f.gate_status_conditions != 0;
+  const uint8_t suspend_status = s.c_suspend_status[c];
+
+  // accumulators: shared memory for the common case, global scratch for clusters with many groups
+  int32_t *acc_list, *acc_unh, *acc_wtd, *acc_rank, *g_mode, *g_prefix;
+  if (G <= KR_SMEM_GROUPS) {
+    acc_list = s_acc[warp][0]; acc_unh = s_acc[warp][1]; acc_wtd = s_acc[warp][2]; acc_rank = s_acc[warp][3];
+    g_mode = s_mode[warp][0]; g_prefix = s_mode[warp][1];
+    if (lane < KR_SMEM_GROUPS) { acc_list[lane] = 0; acc_unh[lane] = 0; acc_wtd[lane] = 0; acc_rank[lane] = 0; g_mode[lane] = GM_UNPROCESSED; g_prefix[lane] = 0; }
+  } else {
+    const uint32_t Ng = a.n.n_groups;
+    acc_list = a.sc.gacc + g0; acc_unh = a.sc.gacc + Ng + g0; acc_wtd = a.sc.gacc + 2 * (size_t)Ng + g0; acc_rank = a.sc.gacc + 3 * (size_t)Ng + g0;
+    // modes reuse the diff / create_off fields of the (not yet written) group results as scratch
+    g_mode = nullptr; g_prefix = nullptr;
+    for (uint32_t gi = lane; gi < G; gi += 32) { acc_list[gi] = 0; acc_unh[gi] = 0; acc_wtd[gi] = 0; acc_rank[gi] = 0; }
+  }
+  __syncwarp();
+
+  // ---------------- scan 1: counts over the cluster's pods (list order)
+  int32_t ready = 0, available = 0, n_heads = 0;
+  bool all_running = P > 0;  // CheckAllPodsRunning (utils/util.go:584-603)
+  uint32_t first_head_pos = 0xFFFFFFFFu;
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    bool valid = i < seg1;
+    uint4 row = make_uint4(0, 0, 0, 0);
+    if (valid) row = a.sc.rows[a.r.sorted_pod_idx[i]];
+    uint32_t fl = row.w & 0xFFFFu, slot = valid ? (row.w >> 16) : KR_ROW_NO_GROUP;
+    uint32_t nt = pp_node_type(fl), ph = pp_phase(fl), rd = pp_ready(fl);
+    bool w_run = valid && nt == KR_NT_WORKER && ph == KR_PHASE_RUNNING;
+    available += __popc(__ballot_sync(0xFFFFFFFFu, w_run));
+    ready += __popc(__ballot_sync(0xFFFFFFFFu, w_run && rd == KR_COND_TRUE));
+    bool not_ok = valid && (ph != KR_PHASE_RUNNING || rd == KR_COND_FALSE || rd == KR_COND_UNKNOWN);
+    if (__any_sync(0xFFFFFFFFu, not_ok)) all_running = false;
+    uint32_t hb = __ballot_sync(0xFFFFFFFFu, valid && nt == KR_NT_HEAD);
+    if (hb) { if (n_heads == 0) first_head_pos = b + (__ffs(hb) - 1); n_heads += __popc(hb); }
+    // warp-ballot group-by on the group slot
+    uint32_t gkey = (slot < G) ? slot : KR_ROW_NO_GROUP;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, gkey);
+    if (gkey != KR_ROW_NO_GROUP) {
+      uint32_t ub = __ballot_sync(peers, should_delete(fl));
+      uint32_t wb = __ballot_sync(peers, (fl & KR_ROW_WTD_OWN) != 0);
+      if ((peers & lt) == 0) {  // leader of its group in this chunk
+        acc_list[gkey] += __popc(peers);
+        acc_unh[gkey] += __popc(ub & peers);
+        acc_wtd[gkey] += __popc(wb & peers);
+      }
+    }
+    __syncwarp();
+  }
+
+  // head pod (first in list order) fields
+  int32_t head_pod = -1; uint32_t head_flags = 0, head_name = 0;
+  if (n_heads > 0) {
+    head_pod = (int32_t)a.r.sorted_pod_idx[first_head_pos];
+    uint4 hrow = a.sc.rows[head_pod];
+    head_flags = hrow.w & 0xFFFFu; head_name = hrow.x;
+  }
+
+  // ---------------- scalar decisions (uniform across the warp)
+  kr_cluster_result cr;
+  {
+    uint32_t *z = reinterpret_cast<uint32_t *>(&cr);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(cr) / 4); k++) z[k] = 0;
+  }
+  cr.head_pod_idx = -1; cr.stop_after_group = -1; cr.pod_start = seg0;
+  uint8_t all_action = KR_ACT_KEEP;  // action applied to every pod of the cluster (delete-all paths)
+  bool head_delete = false;
+  bool run_groups = false;
+
+  if (cf & KR_CF_SKIP) {
+    cr.path = KR_PATH_SKIPPED;
+  } else if (s.c_ext_err_kind[c] != KR_EXT_ERR_NONE) {
+    cr.path = KR_PATH_SKIPPED; cr.err_kind = KR_ERR_EXTERNAL;  // :308-314
+  } else if (suspend_status == KR_SUSPEND_SUSPENDING || (!gate && (cf & KR_CF_SUSPEND))) {
+    cr.path = KR_PATH_SUSPENDING_DELETE_ALL; all_action = KR_ACT_DELETE_ALL_SUSPEND;  // :629-644
+  } else if (gate && (suspend_status == KR_SUSPEND_SUSPENDED || (cf & KR_CF_SUSPEND))) {
+    cr.path = KR_PATH_SUSPENDED_NOOP;  // :646-654
+  } else {
+    bool recreate = false;
+    if ((cf & KR_CF_UPGRADE_RECREATE) && n_heads > 0) {  // shouldRecreatePodsForUpgrade :1132-1171
+      int32_t aux = aux_lookup(a.sc, (uint32_t)head_pod);
+      uint8_t ver = aux >= 0 ? s.h_version_state[aux] : (uint8_t)KR_VER_EMPTY;
+      uint8_t ast = aux >= 0 ? s.h_annot_state[aux] : (uint8_t)KR_ANNOT_EMPTY;
+      if (ver == KR_VER_DIFFERENT) cr.head_update_annotations = 1;
+      else if (ast == KR_ANNOT_OTHER) recreate = true;
+      else if (ast == KR_ANNOT_HASH32 && !a.f.skip_hash) {
+        if (a.phase == 0) {  // the hash kernel runs concurrently on another stream: decide this cluster in phase 1
+          if (lane == 0) a.sc.deferred[c] = 1;
+          return;
+        }
+        const uint8_t *ah = s.h_annot_hash + 32 * (size_t)aux;
+        const char *hh = a.r.hash + 32 * (size_t)c;
+        bool ne = ah[lane] != (uint8_t)hh[lane];
+        recreate = __any_sync(0xFFFFFFFFu, ne);
+      }
+    }
+    if (recreate) {
+      cr.path = KR_PATH_RECREATE_DELETE_ALL; all_action = KR_ACT_DELETE_ALL_RECREATE;  // :657-670
+    } else {
+      cr.path = KR_PATH_NORMAL;
+      // head (:673-748)
+      if (!(cf & KR_CF_HEAD_EXPECT_OK)) { cr.head_action = KR_HEAD_EXPECT_PENDING; run_groups = true; }
+      else if (n_heads == 1) {
+        if (should_delete(head_flags)) { cr.head_action = KR_HEAD_DELETE; cr.err_kind = KR_ERR_HEAD_DELETED; head_delete = true; }
+        else run_groups = true;
+      } else if (n_heads == 0) {
+        bool provisioned = s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED] == KR_COND_TRUE;
+        if (provisioned && (cf & KR_CF_SKIP_HEAD_RESTART)) cr.head_action = KR_HEAD_SKIP_RESTART;
+        else { cr.head_action = KR_HEAD_CREATE; run_groups = true; }
+      } else {
+        cr.head_action = KR_HEAD_MULTIPLE; cr.err_kind = KR_ERR_MULTIPLE_HEADS; cr.err_arg = n_heads;
+      }
+    }
+  }
+
+  // worker groups in spec order (:751-933): O(1) per group from the scan-1 counters
+  bool any_multihost = false;
+  if (run_groups) {
+    const bool autoscaling = (cf & KR_CF_AUTOSCALING) != 0;
+    cr.stop_after_group = (int32_t)G;
+    for (uint32_t gi = 0; gi < G; gi++) {
+      const uint32_t g = g0 + gi, gf = s.g_flags[g];
+      kr_group_result gr;
+      gr.expected = 0; gr.n_list = 0; gr.n_unhealthy = 0; gr.n_running = 0; gr.diff = 0; gr.n_create = 0; gr.create_off = 0;
+      gr.flags = KR_GR_PROCESSED;
+      int32_t mode = GM_SKIP, prefix = 0;
+      bool abort_here = false;
+      if (!(gf & KR_GF_EXPECT_OK)) {
+        gr.flags |= KR_GR_EXPECT_PENDING;
+      } else {
+        const int32_t hosts = s.g_num_hosts[g];
+        const int32_t expected = desired_replicas(s.g_replicas[g], s.g_min[g], s.g_max[g], hosts, gf);
+        const int32_t n_list = acc_list[gi], n_unh = acc_unh[gi], n_wtd = acc_wtd[gi];
+        gr.expected = expected; gr.n_list = n_list;
+        if (gf & KR_GF_SUSPEND) { gr.flags |= KR_GR_SUSPENDED; mode = GM_SUSPENDED; }
+        else if (hosts > 1 && a.f.gate_multihost_indexing) { gr.flags |= KR_GR_MULTIHOST; mode = GM_MULTIHOST; any_multihost = true; }
+        else if (n_unh > 0) {  // :786-812
+          gr.n_unhealthy = n_unh; gr.flags |= KR_GR_ABORTED; mode = GM_UNHEALTHY;
+          cr.err_kind = KR_ERR_UNHEALTHY_WORKERS; cr.err_arg = n_unh; abort_here = true;
+        } else {
+          gr.flags |= KR_GR_WTD_EXECUTED; mode = GM_NORMAL;  // :814-849
+          const int32_t running = n_list - n_wtd;
+          const int32_t diff = expected - running;
+          gr.n_running = running; gr.diff = diff;
+          if (diff > 0) gr.n_create = (uint32_t)diff;
+          else if (diff < 0) {
+            if (!autoscaling || a.f.env_random_pod_delete) {  // :898-928
+              long long remove = -(long long)diff;
+              if (remove > running) {  // expected < 0: the Go loop would index past runningPods (:917)
+                prefix = running; gr.flags |= KR_GR_ABORTED;
+                cr.err_kind = KR_ERR_NEGATIVE_EXPECTED; cr.err_arg = expected; abort_here = true;
+              } else prefix = (int32_t)remove;
+            } else gr.flags |= KR_GR_RANDOM_DELETE_OFF;
+          }
+        }
+      }
+      __syncwarp();  // every lane has read this group's counters before lane 0 recycles their cells
+      if (g_mode) { if (lane == 0) { g_mode[gi] = mode; g_prefix[gi] = prefix; } }
+      if (lane == 0) {
+        a.r.groups[g] = gr;
+        if (!g_mode) { a.sc.gacc[g] = mode; a.sc.gacc[a.n.n_groups + g] = prefix; }  // spill: reuse n_list/n_unh cells (already consumed)
+      }
+      if (abort_here) { cr.stop_after_group = (int32_t)gi; break; }
+    }
+  }
+  // groups never reached keep an all-zero record
+  if (!(cf & KR_CF_SKIP)) {
+    int32_t reached = run_groups ? (cr.stop_after_group == (int32_t)G ? (int32_t)G : cr.stop_after_group + 1) : 0;
+    for (uint32_t gi = reached + lane; gi < G; gi += 32) {
+      kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
+      a.r.groups[g0 + gi] = z;
+      if (!g_mode) { a.sc.gacc[g0 + gi] = GM_UNPROCESSED; a.sc.gacc[a.n.n_groups + g0 + gi] = 0; }
+    }
+  } else {
+    for (uint32_t gi = lane; gi < G; gi += 32) {
+      kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
+      a.r.groups[g0 + gi] = z;
+    }
+  }
+  if (any_multihost && lane == 0) atomicOr(&a.r.totals[3], KR_TOTALS_ERR_MH_UNSUPPORTED);
+  __syncwarp();
+  const int32_t *mode_arr = g_mode ? g_mode : a.sc.gacc + g0;
+  const int32_t *prefix_arr = g_prefix ? g_prefix : a.sc.gacc + a.n.n_groups + g0;
+
+  // ---------------- scan 2: per-pod actions in list order
+  uint32_t n_act = 0;
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    bool valid = i < seg1;
+    uint32_t pod = valid ? a.r.sorted_pod_idx[i] : 0;
+    uint8_t act = KR_ACT_KEEP;
+    uint32_t gkey = KR_ROW_NO_GROUP, fl = 0;
+    if (valid && run_groups) {
+      uint32_t w = a.sc.rows[pod].w;
+      fl = w & 0xFFFFu;
+      uint32_t slot = w >> 16;
+      if (slot < G) gkey = slot;
+    }
+    int32_t mode = (gkey != KR_ROW_NO_GROUP) ? mode_arr[gkey] : GM_UNPROCESSED;
+    bool candidate = false;  // running pod of a group in normal mode: subject to the ordered delete prefix
+    if (all_action != KR_ACT_KEEP) act = valid ? all_action : (uint8_t)KR_ACT_KEEP;
+    else if (head_delete) { if (valid && (int32_t)pod == head_pod) act = KR_ACT_DELETE_HEAD; }
+    else if (mode == GM_SUSPENDED) act = KR_ACT_DELETE_GROUP_SUSPEND;
+    else if (mode == GM_UNHEALTHY) { if (should_delete(fl)) act = KR_ACT_DELETE_UNHEALTHY; }
+    else if (mode == GM_NORMAL) {
+      if (fl & KR_ROW_WTD_OWN) act = KR_ACT_DELETE_WTD;
+      else candidate = true;
+    }
+    // stable rank among the running pods of the same group: ballot group-by + per-group cursor
+    uint32_t ckey = candidate ? gkey : KR_ROW_NO_GROUP;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, ckey);
+    if (candidate) {
+      int32_t cur = acc_rank[ckey];
+      __syncwarp(peers);
+      int32_t rank = cur + __popc(peers & lt);
+      if ((peers & lt) == 0) acc_rank[ckey] = cur + __popc(peers);
+      if (rank < prefix_arr[ckey]) act = KR_ACT_DELETE_RANDOM;  // runningPods.Items[0 .. -diff) (:916-919)
+    }
+    __syncwarp();
+    if (valid) a.r.sorted_action[i] = act;
+    n_act += __popc(__ballot_sync(0xFFFFFFFFu, valid && act != KR_ACT_KEEP));
+  }
+
+  // ---------------- status roll-up + record
+  if (lane == 0) {
+    if (!(cf & KR_CF_SKIP))
+      status_rollup(a, c, cr, P, (uint32_t)n_heads, head_pod, head_name, ready, available, all_running);
+    a.r.clusters[c] = cr;
+    if (n_act) atomicAdd(&a.r.totals[2], n_act);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ creates
+
+// exclusive scan of group n_create -> create_off, total in totals[0]; one block
+__global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, uint32_t n_groups) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t per = (n_groups + 1023) / 1024;
+  const uint32_t lo = min(t * per, n_groups), hi = min(lo + per, n_groups);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += r.groups[i].n_create;
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = s_warp[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += y; }
+    s_warp[lane] = v;
+  }
+  __syncthreads();
+  uint32_t run = x - sum + (w ? s_warp[w - 1] : 0);
+  for (uint32_t i = lo; i < hi; i++) { uint32_t v = r.groups[i].n_create; r.groups[i].create_off = run; run += v; }
+  if (t == 1023) r.totals[0] = run;
+}
+
+// Lowest free ray.io/worker-group-replica-index values for the pods to create (raycluster_controller.go:854-881).
+// One warp per group; candidate indices are swept in windows of 1024 bits held in shared memory.
+__global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, ResDev r, Sizes n, kr_flags f, uint32_t create_cap) {
+  __shared__ uint32_t s_bits[4][32];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * 4 + warp;
+  if (g >= n.n_groups) return;
+  const kr_group_result gr = r.groups[g];
+  if (gr.n_create == 0 || (gr.flags & KR_GR_MULTIHOST)) return;
+  if ((uint64_t)gr.create_off + gr.n_create > create_cap) return;  // host reports KR_E_CAPACITY from totals[0]
+  int32_t *out = r.create_idx + gr.create_off;
+  if (!f.gate_multihost_indexing) {  // createWorkerPod without an index (:884-889)
+    for (uint32_t k = lane; k < gr.n_create; k += 32) out[k] = -1;
+    return;
+  }
+  const uint32_t c = s.g_cluster_idx[g];
+  const uint32_t slot = g - s.c_group_off[c];
+  const kr_cluster_result *cr = &r.clusters[c];
+  const uint32_t seg0 = cr->pod_start, seg1 = seg0 + (uint32_t)cr->n_pods;
+  const uint64_t bound = (uint64_t)gr.n_running + gr.n_create;  // the n_create lowest free indices all lie below this
+  uint32_t written = 0;
+  for (uint64_t w0 = 0; w0 < bound && written < gr.n_create; w0 += 1024) {
+    s_bits[warp][lane] = 0;
+    __syncwarp();
+    for (uint32_t b = seg0; b < seg1; b += 32) {
+      uint32_t i = b + lane;
+      if (i < seg1 && r.sorted_action[i] == KR_ACT_KEEP) {  // runningPods: listed and not deleted by name
+        uint4 row = sc.rows[r.sorted_pod_idx[i]];
+        if ((row.w >> 16) == slot && (row.w & KR_PP_HAS_REPLICA_IDX)) {
+          int32_t idx = (int32_t)row.z;
+          if (idx >= 0 && (uint64_t)idx >= w0 && (uint64_t)idx < w0 + 1024 && (uint64_t)idx < bound)
+            atomicOr(&s_bits[warp][(idx - w0) >> 5], 1u << ((idx - w0) & 31));
+        }
+      }
+    }
+    __syncwarp();
+    uint32_t word = s_bits[warp][lane];
+    uint64_t wbase = w0 + 32ull * lane;
+    uint32_t freeb = ~word;
+    if (wbase >= bound) freeb = 0;
+    else if (bound - wbase < 32) freeb &= (1u << (uint32_t)(bound - wbase)) - 1;
+    uint32_t cnt = __popc(freeb), x = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    uint32_t pos = written + x - cnt;
+    while (freeb && pos < gr.n_create) {
+      uint32_t bit = __ffs(freeb) - 1;
+      freeb &= freeb - 1;
+      out[pos++] = (int32_t)(wbase + bit);
+    }
+    written += __shfl_sync(0xFFFFFFFFu, x, 31);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_jobs
+// RayJob roll-up (rayjob_controller.go:203-216, 343, 885): join by (namespace, status.rayClusterName).
+__global__ void __launch_bounds__(256) k_jobs(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n.n_jobs) return;
+  kr_job_result jr; jr.cluster_idx = -1; jr.cluster_state = 0; jr.not_ready = 0; jr.status_changed = 0; jr.reserved = 0;
+  uint32_t c;
+  if (cl_lookup(sc, s.j_ns_id[j], s.j_cluster_name_id[j], c)) {
+    jr.cluster_idx = (int32_t)c;
+    jr.cluster_state = s.c_old_state[c];
+    jr.not_ready = s.c_old_state[c] != KR_STATE_READY;
+    jr.status_changed = s.j_summary_id[j] != s.c_summary_id[c];
+  }
+  r.jobs[j] = jr;
+}
+
+// ------------------------------------------------------------------------------------------------ k_hash
+// base32hex(sha1(json)) per RayCluster (utils/util.go:628-640).  One lane per message (SHA-1 is a serial chain per
+// message); the warp stages 128 bytes of each of its 32 messages per step with coalesced 16-byte loads into an
+// XOR-swizzled shared tile, so the per-lane reads are conflict-free LDS.128.
+
+__device__ __forceinline__ uint32_t rol(uint32_t x, int k) { return __funnelshift_l(x, x, k); }
+__device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ void sha1_rounds(uint32_t (&w)[16], uint32_t (&h)[5]) {
+  uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+#pragma unroll
+  for (int i = 0; i < 80; i++) {
+    uint32_t wi;
+    if (i < 16) wi = w[i];
+    else { wi = rol(w[(i - 3) & 15] ^ w[(i - 8) & 15] ^ w[(i - 14) & 15] ^ w[i & 15], 1); w[i & 15] = wi; }
+    uint32_t f, k;
+    if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999u; }
+    else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
+    else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
+    else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
+    uint32_t t = rol(a, 5) + f + e + k + wi;
+    e = d; d = c; c = rol(b, 30); b = a; a = t;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_hash(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ off,
+                                                     const uint32_t *__restrict__ len32, const uint64_t *__restrict__ off_end,
+                                                     uint32_t n, char *__restrict__ out) {
+  // tile[warp][message lane][8 x 16-byte pieces], piece index XOR (lane & 7)
+  __shared__ uint4 s_tile[WARPS][32][8];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t m = (blockIdx.x * WARPS + warp) * 32 + lane;
+  const bool have = m < n;
+  uint64_t moff = 0, mlen = 0;
+  if (have) { moff = off[m]; mlen = len32 ? (uint64_t)len32[m] : (off_end[m] - moff); }
+  const uint32_t nblocks = have ? (uint32_t)((mlen + 8) / 64 + 1) : 0;
+  uint32_t max_blocks = nblocks;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) max_blocks = max(max_blocks, __shfl_xor_sync(0xFFFFFFFFu, max_blocks, d));
+  uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
+  const uint64_t mlen16 = (mlen + 15) & ~15ull;  // arena is padded to 16 bytes per message
+  const uint32_t sub = lane & 7, grp = lane >> 3;
+
+  uint4 pre[8];
+  auto fetch = [&](uint32_t chunk) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t src_lane = 4 * r + grp;  // message whose piece this lane fetches
+      uint64_t o = __shfl_sync(0xFFFFFFFFu, moff, src_lane);
+      uint64_t l16 = __shfl_sync(0xFFFFFFFFu, mlen16, src_lane);
+      uint64_t pos = (uint64_t)chunk * 128 + sub * 16;
+      pre[r] = (pos < l16) ? __ldg(reinterpret_cast<const uint4 *>(bytes + o + pos)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  const uint32_t nchunks = (max_blocks + 1) / 2;
+  if (nchunks) fetch(0);
+  for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t src_lane = 4 * r + grp;
+      s_tile[warp][src_lane][sub ^ (src_lane & 7)] = pre[r];
+    }
+    __syncwarp();
+    if (chunk + 1 < nchunks) fetch(chunk + 1);  // software prefetch: loads in flight during the 160 rounds below
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t blk = chunk * 2 + half;
+      if (blk >= nblocks) continue;
+      uint32_t w[16];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint4 v = s_tile[warp][lane][(half * 4 + q) ^ (lane & 7)];
+        w[4 * q] = bswap(v.x); w[4 * q + 1] = bswap(v.y); w[4 * q + 2] = bswap(v.z); w[4 * q + 3] = bswap(v.w);
+      }
+      uint64_t bstart = (uint64_t)blk * 64;
+      if (bstart + 64 > mlen) {  // tail block(s): 0x80 terminator, zero fill, 64-bit big-endian bit length (FIPS 180-4 §5.1.1)
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          uint64_t wpos = bstart + 4 * q;
+          uint32_t v = w[q];
+          if (wpos >= mlen) v = (wpos == mlen) ? 0x80000000u : 0u;
+          else if (wpos + 4 > mlen) {
+            uint32_t keep = (uint32_t)(mlen - wpos);  // 1..3 bytes of message in this word
+            uint32_t mask = 0xFFFFFFFFu << (8 * (4 - keep));
+            v = (v & mask) | (0x80u << (8 * (3 - keep)));
+          }
+          w[q] = v;
+        }
+        if (blk == nblocks - 1) { uint64_t bits = mlen * 8; w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+      }
+      sha1_rounds(w, h);
+    }
+  }
+  if (!have) return;
+  // base32hex: 4 groups of 40 bits -> 8 chars each
+  uint32_t o32[8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    // 40-bit group j = bits [40j, 40j+40) of h0||h1||h2||h3||h4
+    uint64_t v;
+    switch (j) {
+      case 0: v = ((uint64_t)h[0] << 8) | (h[1] >> 24); break;
+      case 1: v = ((uint64_t)(h[1] & 0xFFFFFFu) << 16) | (h[2] >> 16); break;
+      case 2: v = ((uint64_t)(h[2] & 0xFFFFu) << 24) | (h[3] >> 8); break;
+      default: v = ((uint64_t)(h[3] & 0xFFu) << 32) | h[4]; break;
+    }
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t cc = (uint32_t)(v >> (35 - 5 * k)) & 31u;
+      uint32_t ch = cc < 10 ? ('0' + cc) : ('A' + cc - 10);
+      if (k < 4) lo |= ch << (8 * k); else hi |= ch << (8 * (k - 4));
+    }
+    o32[2 * j] = lo; o32[2 * j + 1] = hi;
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(out + 32 * (size_t)m);
+  dst[0] = make_uint4(o32[0], o32[1], o32[2], o32[3]);
+  dst[1] = make_uint4(o32[4], o32[5], o32[6], o32[7]);
+}
+
+}  // namespace kr

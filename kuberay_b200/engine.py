@@ -1,0 +1,211 @@
+"""ctypes binding of the C-ABI library libkrengine.so (include/kr_engine.h) — the product path.
+
+There is NO CPU fallback: if the CUDA library is missing or no device is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+from .snapshot import Snapshot
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkrengine.so")
+_LIB = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kr_engine error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile libkrengine.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    deps = [os.path.join(src, f) for f in ("kr_engine.cu", "kr_kernels.cuh")] + [os.path.join(_HERE, "..", "include", "kr_engine.h")]
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if stale:
+        subprocess.check_call(["make", "-s", "-C", src, "-B", "NVCCFLAGS=-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC"])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'`; there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        P = C.POINTER
+        L.kr_device_count.restype = C.c_int
+        L.kr_engine_create.argtypes = [P(abi.kr_config), P(C.c_void_p)]
+        L.kr_engine_destroy.argtypes = [C.c_void_p]
+        L.kr_engine_destroy.restype = None
+        L.kr_snapshot_begin.argtypes = [C.c_void_p, P(abi.kr_sizes), P(abi.kr_snapshot_bufs)]
+        L.kr_snapshot_commit.argtypes = [C.c_void_p]
+        L.kr_reconcile_batch.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_results_view)]
+        L.kr_reconcile_device_only.argtypes = [C.c_void_p, P(abi.kr_flags)]
+        L.kr_reconcile_batch_profiled.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_profile)]
+        L.kr_results_fetch.argtypes = [C.c_void_p, P(abi.kr_results_view)]
+        L.kr_hash_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.kr_last_profile.argtypes = [C.c_void_p, P(abi.kr_profile)]
+        L.kr_group_results_device.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_uint64)]
+        L.kr_last_error.argtypes = [C.c_void_p]
+        L.kr_last_error.restype = C.c_char_p
+        L.kr_algorithmic_bytes.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
+        for name in abi.ENGINE_SYMBOLS:
+            getattr(L, name)  # raises AttributeError if the header and the library drifted apart
+        _LIB = L
+    return _LIB
+
+
+def _np_view(ptr: int, dtype, count: int) -> np.ndarray:
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    dt = np.dtype(dtype)
+    buf = (C.c_uint8 * (dt.itemsize * count)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=count)
+
+
+class Engine:
+    """One engine == one GPU.  Mirrors the C ABI call sequence: begin -> (fill) -> commit -> reconcile."""
+
+    def __init__(self, device: int = 0, max_clusters=0, max_groups=0, max_wtd=0, max_pods=0, max_heads=0, max_jobs=0,
+                 max_creates=0, max_json_bytes=0):
+        self._L = lib()
+        n = self._L.kr_device_count()
+        if n <= 0:
+            raise EngineError(abi.KR_E_NO_DEVICE, "no CUDA device visible (this engine has no CPU fallback)")
+        self.cfg = abi.kr_config(device, max_clusters, max_groups, max_wtd, max_pods, max_heads, max_jobs, max_creates, max_json_bytes)
+        self._h = C.c_void_p()
+        rc = self._L.kr_engine_create(C.byref(self.cfg), C.byref(self._h))
+        if rc != 0:
+            raise EngineError(rc, "kr_engine_create failed")
+        self.sizes = None
+
+    @classmethod
+    def for_snapshot(cls, snap: Snapshot, device: int = 0, max_creates: int | None = None, slack: float = 1.0) -> "Engine":
+        d = snap.dims
+        up = lambda x: int(x * slack) + 1  # noqa: E731
+        if max_creates is None:
+            max_creates = max(1024, d["pods"] // 2)
+        return cls(device, up(d["clusters"]), up(d["groups"]), up(d["wtd"]), up(d["pods"]), up(d["heads"]), up(d["jobs"]),
+                   max_creates, up(d["json"]))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, self._L.kr_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._L.kr_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- snapshot
+    def begin(self, sizes: abi.kr_sizes) -> dict[str, np.ndarray]:
+        """kr_snapshot_begin: returns numpy views over the engine-owned pinned arenas, keyed by column name."""
+        bufs = abi.kr_snapshot_bufs()
+        self._check(self._L.kr_snapshot_begin(self._h, C.byref(sizes), C.byref(bufs)))
+        self.sizes = abi.kr_sizes.from_buffer_copy(sizes)
+        dims = {"clusters": sizes.n_clusters, "groups": sizes.n_groups, "wtd": sizes.n_wtd, "pods": sizes.n_pods,
+                "heads": sizes.n_heads, "jobs": sizes.n_jobs, "json": sizes.json_bytes}
+        views = {}
+        for name, dt, mult, dim in abi.COLUMNS:
+            ptr = C.cast(getattr(bufs, name), C.c_void_p).value
+            views[name] = _np_view(ptr, dt, dims[dim] * mult)
+        return views
+
+    def fill(self, views: dict[str, np.ndarray], snap: Snapshot):
+        """Host-side packing stand-in: copy pre-packed columns into the pinned arenas."""
+        for name, *_ in abi.COLUMNS:
+            if views[name].size:
+                np.copyto(views[name], snap.cols[name])
+
+    def commit(self):
+        self._check(self._L.kr_snapshot_commit(self._h))
+
+    def load(self, snap: Snapshot):
+        views = self.begin(snap.sizes())
+        self.fill(views, snap)
+        self.commit()
+        return views
+
+    # -- passes
+    def reconcile(self, flags: abi.kr_flags, copy: bool = True) -> abi.Results:
+        view = abi.kr_results_view()
+        self._check(self._L.kr_reconcile_batch(self._h, C.byref(flags), C.byref(view)))
+        return self._results(view, copy)
+
+    def reconcile_device_only(self, flags: abi.kr_flags):
+        self._check(self._L.kr_reconcile_device_only(self._h, C.byref(flags)))
+
+    def reconcile_profiled(self, flags: abi.kr_flags) -> dict:
+        prof = abi.kr_profile()
+        self._check(self._L.kr_reconcile_batch_profiled(self._h, C.byref(flags), C.byref(prof)))
+        return self._profile_dict(prof, kernels=True)
+
+    def fetch(self, copy: bool = True) -> abi.Results:
+        view = abi.kr_results_view()
+        self._check(self._L.kr_results_fetch(self._h, C.byref(view)))
+        return self._results(view, copy)
+
+    def last_profile(self) -> dict:
+        prof = abi.kr_profile()
+        self._check(self._L.kr_last_profile(self._h, C.byref(prof)))
+        return self._profile_dict(prof, kernels=False)
+
+    @staticmethod
+    def _profile_dict(prof: abi.kr_profile, kernels: bool) -> dict:
+        d = {"h2d_ms": prof.h2d_ms, "kernels_ms": prof.kernels_ms, "d2h_ms": prof.d2h_ms, "n_kernels": prof.n_kernels}
+        if kernels:
+            k = min(prof.n_kernels, abi.MAX_KERNEL_TIMES)
+            d["kernels"] = [((prof.kernel_name[i] or b"?").decode(), prof.kernel_ms[i]) for i in range(k)]
+        return d
+
+    def algorithmic_bytes(self) -> dict:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.kr_algorithmic_bytes(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"pass": a.value, "hash": b.value, "match": c.value}
+
+    def group_results_device(self) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._L.kr_group_results_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def hash_batch(self, messages: list[bytes]) -> list[str]:
+        n = len(messages)
+        if n == 0:
+            return []
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(m) for m in messages])
+        blob = np.frombuffer(b"".join(messages) or b"\0", dtype=np.uint8)
+        out = np.zeros(32 * n, dtype=np.uint8)
+        self._check(self._L.kr_hash_batch(self._h, blob.ctypes.data, offs.ctypes.data, n, out.ctypes.data))
+        return [bytes(out[32 * i:32 * i + 32]).decode("ascii") for i in range(n)]
+
+    def _results(self, view: abi.kr_results_view, copy: bool) -> abi.Results:
+        s = self.sizes
+        res = abi.Results.__new__(abi.Results)
+        res.clusters = _np_view(view.clusters, abi.cluster_result_dtype, s.n_clusters)
+        res.hash = _np_view(view.hash, np.uint8, 32 * s.n_clusters).reshape(s.n_clusters, 32)
+        res.groups = _np_view(view.groups, abi.group_result_dtype, s.n_groups)
+        res.wtd_pod_idx = _np_view(view.wtd_pod_idx, np.int32, s.n_wtd)
+        res.sorted_pod_idx = _np_view(view.sorted_pod_idx, np.uint32, s.n_pods)
+        res.sorted_action = _np_view(view.sorted_action, np.uint8, s.n_pods)
+        res.create_idx = _np_view(view.create_idx, np.int32, view.n_create_total)
+        res.jobs = _np_view(view.jobs, abi.job_result_dtype, s.n_jobs)
+        res.n_create_total, res.n_orphans, res.n_actions = view.n_create_total, view.n_orphans, view.n_actions
+        if copy:
+            for name in abi.Results.FIELDS:
+                setattr(res, name, getattr(res, name).copy())
+        return res
