@@ -356,6 +356,7 @@ typedef struct kr_profile {
   uint32_t n_kernels;                       /* kernels launched by the last batch (our own, not library) */
   float    kernel_ms[KR_MAX_KERNEL_TIMES];  /* valid only after kr_reconcile_batch_profiled */
   const char *kernel_name[KR_MAX_KERNEL_TIMES];
+  uint64_t h2d_bytes, d2h_bytes;            /* bytes moved by the last commit / the last results fetch */
 } kr_profile;
 
 /* --------------------------------------------------------- entry points */
@@ -403,6 +404,10 @@ int kr_last_profile(kr_engine *e, kr_profile *prof);
 /* Device pointer + byte size of the per-group delta records (kr_group_result[n_groups]) of the last pass:
  * the payload of the optional cross-GPU all-gather; the caller owns the collective. */
 int kr_group_results_device(kr_engine *e, const void **dev_ptr, uint64_t *bytes);
+
+/* Copy those records device-to-device into a caller-owned device buffer (e.g. a torch tensor handed to
+ * torch.distributed.all_gather over NCCL); synchronises the engine stream before returning. */
+int kr_group_results_copy(kr_engine *e, void *dst_device, uint64_t dst_capacity_bytes);
 
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);

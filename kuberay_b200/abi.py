@@ -154,7 +154,8 @@ class kr_results_view(C.Structure):
 
 class kr_profile(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernels_ms", C.c_float), ("d2h_ms", C.c_float), ("n_kernels", C.c_uint32),
-                ("kernel_ms", C.c_float * MAX_KERNEL_TIMES), ("kernel_name", C.c_char_p * MAX_KERNEL_TIMES)]
+                ("kernel_ms", C.c_float * MAX_KERNEL_TIMES), ("kernel_name", C.c_char_p * MAX_KERNEL_TIMES),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class kr_oracle_out(C.Structure):  # oracle/kr_oracle.h (test infrastructure; declared here only for layout sharing)
@@ -167,7 +168,7 @@ class kr_oracle_out(C.Structure):  # oracle/kr_oracle.h (test infrastructure; de
 ENGINE_SYMBOLS = [
     "kr_device_count", "kr_engine_create", "kr_engine_destroy", "kr_snapshot_begin", "kr_snapshot_commit",
     "kr_reconcile_batch", "kr_reconcile_device_only", "kr_reconcile_batch_profiled", "kr_results_fetch",
-    "kr_hash_batch", "kr_last_profile", "kr_group_results_device", "kr_last_error", "kr_algorithmic_bytes",
+    "kr_hash_batch", "kr_last_profile", "kr_group_results_device", "kr_group_results_copy", "kr_last_error", "kr_algorithmic_bytes",
 ]
 
 

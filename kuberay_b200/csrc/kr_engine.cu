@@ -73,7 +73,7 @@ struct OutLayout {  // results arena
 OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
   OutLayout L;
   size_t o = 0;
-  L.totals = o; o = align_up(o + 16);
+  L.totals = o; o = align_up(o + 32);
   L.clusters = o; o = align_up(o + sizeof(kr_cluster_result) * (size_t)n.n_clusters);
   L.hash = o; o = align_up(o + 32 * (size_t)n.n_clusters);
   L.groups = o; o = align_up(o + sizeof(kr_group_result) * (size_t)n.n_groups);
@@ -89,8 +89,8 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 
 struct ScratchLayout {
   // 0xFF-initialised region first
-  size_t cl_keys, cl_vals, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t wt_next, rows, keys0, keys1, vals0, vals1, hist, gacc, deferred, total;
+  size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, cstart, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles;
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
@@ -101,13 +101,13 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.ntiles = (uint32_t)((n.n_pods + kSortTile - 1) / kSortTile);
   if (L.ntiles == 0) L.ntiles = 1;
   size_t o = 0;
-  L.cl_keys = o; o = align_up(o + 8 * (size_t)L.cl_slots);
-  L.cl_vals = o; o = align_up(o + 4 * (size_t)L.cl_slots);
+  L.cl_slots_off = o; o = align_up(o + 16 * (size_t)L.cl_slots);
   L.wt_keys = o; o = align_up(o + 8 * (size_t)L.wt_slots);
   L.wt_head = o; o = align_up(o + 4 * (size_t)L.wt_slots);
   L.aux_keys = o; o = align_up(o + 4 * (size_t)L.aux_slots);
   L.aux_vals = o; o = align_up(o + 4 * (size_t)L.aux_slots);
   L.ff_total = o;
+  L.cl_rec = o; o = align_up(o + 16 * (size_t)n.n_clusters);
   L.wt_next = o; o = align_up(o + 4 * (size_t)n.n_wtd);
   L.rows = o; o = align_up(o + 16 * (size_t)n.n_pods);
   L.keys0 = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -115,8 +115,12 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.vals0 = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.vals1 = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.hist = o; o = align_up(o + 4 * (size_t)kRadix * L.ntiles);
+  L.row_total = o; o = align_up(o + 4 * (size_t)kRadix);
   L.gacc = o; o = align_up(o + 16 * (size_t)n.n_groups);
-  L.deferred = o; o = align_up(o + (size_t)n.n_clusters);
+  L.gcreate = o; o = align_up(o + 4 * (size_t)n.n_groups + 32);
+  L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
+  L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
+  L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.total = o;
   return L;
 }
@@ -142,6 +146,16 @@ struct kr_engine {
   uint8_t *hb_h = nullptr, *hb_d = nullptr;
   size_t hb_cap = 0;
   int sm_count = 148;
+  // the whole pass (both streams) captured once per (layout, flags, n_recreate) and replayed
+  cudaGraphExec_t gexec = nullptr;
+  kr_flags gflags{};
+  bool gvalid = false;
+  bool use_graph = true;
+  // pipeline choice: fast = count/place/in-warp sort (every bucket <= 1024 pods); radix = general stable LSD sort.
+  bool force_radix = false;   // sticky per layout: set when a pass met a bucket the fast pipeline cannot sort
+  bool ran_fast = false;
+  bool env_radix = false;     // KR_FORCE_RADIX=1: always take the general pipeline (tests)
+  uint32_t *h_totals = nullptr;  // pinned copy of the device totals (pipeline fallback check)
 };
 
 namespace {
@@ -190,7 +204,8 @@ ResDev bind_out(const OutLayout &L, uint8_t *base) {
 
 ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   ScratchDev s;
-  s.cl_keys = reinterpret_cast<uint64_t *>(b + L.cl_keys); s.cl_vals = reinterpret_cast<uint32_t *>(b + L.cl_vals); s.cl_mask = L.cl_slots - 1;
+  s.cl_slots = reinterpret_cast<uint4 *>(b + L.cl_slots_off); s.cl_mask = L.cl_slots - 1;
+  s.cl_rec = reinterpret_cast<uint4 *>(b + L.cl_rec);
   s.wt_keys = reinterpret_cast<uint64_t *>(b + L.wt_keys); s.wt_head = reinterpret_cast<uint32_t *>(b + L.wt_head);
   s.wt_next = reinterpret_cast<uint32_t *>(b + L.wt_next); s.wt_mask = L.wt_slots - 1;
   s.aux_keys = reinterpret_cast<uint32_t *>(b + L.aux_keys); s.aux_vals = reinterpret_cast<uint32_t *>(b + L.aux_vals); s.aux_mask = L.aux_slots - 1;
@@ -198,8 +213,12 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.keys[0] = reinterpret_cast<uint32_t *>(b + L.keys0); s.keys[1] = reinterpret_cast<uint32_t *>(b + L.keys1);
   s.vals[0] = reinterpret_cast<uint32_t *>(b + L.vals0); s.vals[1] = reinterpret_cast<uint32_t *>(b + L.vals1);
   s.hist = reinterpret_cast<uint32_t *>(b + L.hist);
+  s.row_total = reinterpret_cast<uint32_t *>(b + L.row_total);
   s.gacc = reinterpret_cast<int32_t *>(b + L.gacc);
-  s.deferred = b + L.deferred;
+  s.gcreate = reinterpret_cast<uint32_t *>(b + L.gcreate);
+  s.deferred_list = reinterpret_cast<uint32_t *>(b + L.deferred_list);
+  s.ccount = reinterpret_cast<uint32_t *>(b + L.ccount);
+  s.cstart = reinterpret_cast<uint32_t *>(b + L.cstart);
   return s;
 }
 
@@ -240,35 +259,44 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
   // --- stream M
   CK(cudaMemsetAsync(e->d_scratch, 0xFF, e->sl.ff_total, M));
   if (n.n_wtd) CK(cudaMemsetAsync(r.wtd_pod_idx, 0xFF, 4 * (size_t)n.n_wtd, M));
-  CK(cudaMemsetAsync(r.totals, 0, 16, M));
-  if (n.n_clusters) CK(cudaMemsetAsync(sc.deferred, 0, n.n_clusters, M));
+  CK(cudaMemsetAsync(r.totals, 0, 32, M));
   {
     uint32_t items = n.n_clusters + n.n_groups + n.n_heads;
     if (items) { mark("k_build_tables"); k_build_tables<<<(items + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
   }
   const uint32_t ntiles = e->sl.ntiles;
-  uint32_t bits = 1;
-  while ((1ull << bits) <= n.n_clusters) bits++;  // keys are in [0, n_clusters]
-  const int passes = (int)((bits + kRadixBits - 1) / kRadixBits);
+  const bool fast = !e->force_radix;
+  e->ran_fast = fast;
   const uint32_t *sorted_keys = sc.keys[0];
-  if (n.n_pods) {
+  if (n.n_pods && fast) {
+    CK(cudaMemsetAsync(sc.ccount, 0, 4 * ((size_t)n.n_clusters + 2), M));
     mark("k_match");
-    k_match<<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+    k_match<true><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+    mark("k_scan_counts");
+    k_scan_counts<<<1, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, r.totals);
+    mark("k_place");
+    k_place<<<(n.n_pods + 1023) / 1024, 256, 0, M>>>(sc.keys[0], sc.keys[1], sc.cstart, sc.vals[0], n.n_pods);
+  } else if (n.n_pods) {
+    uint32_t bits = 1;
+    while ((1ull << bits) <= n.n_clusters) bits++;  // keys are in [0, n_clusters]
+    const int passes = (int)((bits + kRadixBits - 1) / kRadixBits);
+    mark("k_match");
+    k_match<false><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
     int cur = 0;
     for (int p = 0; p < passes; p++) {
       if (p > 0) { mark("k_hist"); k_hist<<<ntiles, kSortThreads, 0, M>>>(sc.keys[cur], sc.hist, n.n_pods, p * kRadixBits); }
-      mark("k_scan_hist");
-      k_scan_hist<<<1, 1024, 0, M>>>(sc.hist, (uint32_t)kRadix * ntiles);
+      mark("k_scan_rows");
+      k_scan_rows<<<kRadix, kRowScanThreads, 0, M>>>(sc.hist, sc.row_total, ntiles);
       mark("k_scatter");
       uint32_t *vout = (p == passes - 1) ? r.sorted_pod_idx : sc.vals[cur ^ 1];
-      k_scatter<<<ntiles, kSortThreads, 0, M>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1], vout, sc.hist, n.n_pods, p * kRadixBits, p == 0);
+      k_scatter<<<ntiles, kSortThreads, 0, M>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1], vout, sc.hist, sc.row_total, n.n_pods, p * kRadixBits, p == 0);
       cur ^= 1;
-      if (p != passes - 1) { /* vals ping-pong follows keys */ }
     }
     sorted_keys = sc.keys[cur];
-    // vals ping-pong: pass p reads vals[cur_before] (except pass 0) and wrote vals[cur_after]; see k_scatter call above
+  } else if (fast) {
+    CK(cudaMemsetAsync(sc.cstart, 0, 4 * ((size_t)n.n_clusters + 2), M));
   }
-  DecideArgs da{s, sc, r, z, f, sorted_keys, 0};
+  DecideArgs da{s, sc, r, z, f, sorted_keys, sc.vals[0], fast ? 1 : 0, 0};
   {
     uint32_t warps = n.n_clusters + 1;
     mark("k_decide");
@@ -283,13 +311,13 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
   }
   if (e->n_recreate > 0 && do_hash) {
     da.phase = 1;
-    uint32_t warps = n.n_clusters + 1;
+    uint32_t warps = e->n_recreate;  // upper bound on the deferred list
     mark("k_decide_phase1");
     k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
   }
   if (n.n_groups) {
     mark("k_scan_creates");
-    k_scan_creates<<<1, 1024, 0, M>>>(r, n.n_groups);
+    k_scan_creates<<<1, 1024, 0, M>>>(r, sc.gcreate, n.n_groups);
     mark("k_create_fill");
     k_create_fill<<<(n.n_groups + 3) / 4, 128, 0, M>>>(s, sc, r, z, f, e->cfg.max_creates);
   }
@@ -297,6 +325,43 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
   e->prof.n_kernels = (uint32_t)k;
   CK(cudaGetLastError());
   return KR_OK;
+}
+
+// Replays the captured CUDA graph of the pass (captures it first when the layout / flags changed).
+int run_pass_once(kr_engine *e, const kr_flags &f) {
+  if (!e->use_graph) return launch_pass(e, f, false);
+  if (!e->gvalid || memcmp(&e->gflags, &f, sizeof f) != 0) {
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+    e->gvalid = false;
+    CK(cudaStreamBeginCapture(e->sm, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_pass(e, f, false);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(e->sm, &g);
+    if (rc != KR_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+    if (ce != cudaSuccess) return fail(e, KR_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&e->gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(e, KR_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    e->gflags = f;
+    e->gvalid = true;
+  }
+  CK(cudaGraphLaunch(e->gexec, e->sm));
+  return KR_OK;
+}
+
+// Runs the pass; if the fast pipeline met a bucket it cannot sort (> 1024 pods in one RayCluster or among the orphans),
+// switches this layout to the radix pipeline and runs again.  Leaves the stream synchronised.
+int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
+  for (int attempt = 0; attempt < 2; attempt++) {
+    int rc = run_pass_once(e, f);
+    if (rc) return rc;
+    if (done) CK(cudaEventRecord(done, e->sm));
+    CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
+    CK(cudaStreamSynchronize(e->sm));
+    if (e->ran_fast && (e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { e->force_radix = true; e->gvalid = false; continue; }
+    return KR_OK;
+  }
+  return fail(e, KR_E_STATE, "internal: radix pipeline flagged a big bucket");
 }
 
 int fetch_results(kr_engine *e, kr_results_view *out) {
@@ -327,6 +392,7 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
   }
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_c) == cudaSuccess) e->prof.d2h_ms = ms;
+  e->prof.d2h_bytes = e->ol.fixed_total + 4ull * n_create;
   return KR_OK;
 }
 
@@ -368,6 +434,10 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaMalloc((void **)&e->d_in, e->in_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_scratch, e->scratch_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
+  if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
+  if (const char *g = getenv("KR_FORCE_RADIX")) e->env_radix = (g[0] == '1');
+  e->force_radix = e->env_radix;
+  if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   *out = e;
   return KR_OK;
 }
@@ -380,10 +450,12 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->h_in) cudaFreeHost(e->h_in);
   if (e->h_out) cudaFreeHost(e->h_out);
   if (e->hb_h) cudaFreeHost(e->hb_h);
+  if (e->h_totals) cudaFreeHost(e->h_totals);
   if (e->d_in) cudaFree(e->d_in);
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->d_out) cudaFree(e->d_out);
   if (e->hb_d) cudaFree(e->hb_d);
+  if (e->gexec) cudaGraphExecDestroy(e->gexec);
   for (auto ev : {e->ev_fork, e->ev_hash, e->ev_a, e->ev_b, e->ev_c}) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_k) if (ev) cudaEventDestroy(ev);
   if (e->sm) cudaStreamDestroy(e->sm);
@@ -400,6 +472,7 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
   if (sizes->n_clusters >= 0xFFFFFFF0u || sizes->n_pods >= 0xFFFFFFF0u) return fail(e, KR_E_CAPACITY, "too many rows");
   CK(cudaSetDevice(c.device));
   CK(cudaStreamSynchronize(e->sm));  // previous results are invalidated from here on
+  if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) { e->gvalid = false; e->force_radix = e->env_radix; }  // layout (hence every kernel argument) changes
   e->sizes = *sizes;
   e->il = in_layout(*sizes);
   e->ol = out_layout(*sizes, c.max_creates);
@@ -429,6 +502,7 @@ int kr_snapshot_commit(kr_engine *e) {
     if (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) n_recreate++;
   }
   if (goff != n.n_groups) return fail(e, KR_E_INVALID, "sum of group_cnt (%llu) != n_groups (%u)", (unsigned long long)goff, n.n_groups);
+  if (n_recreate != e->n_recreate) e->gvalid = false;  // decide phase 1 launch shape depends on it
   e->n_recreate = n_recreate;
   CK(cudaEventRecord(e->ev_a, e->sm));
   CK(cudaMemcpyAsync(e->d_in, e->h_in, e->il.total, cudaMemcpyHostToDevice, e->sm));
@@ -436,6 +510,7 @@ int kr_snapshot_commit(kr_engine *e) {
   CK(cudaStreamSynchronize(e->sm));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.h2d_ms = ms;
+  e->prof.h2d_bytes = e->il.total;
   e->committed = true;
   return KR_OK;
 }
@@ -445,10 +520,8 @@ int kr_reconcile_device_only(kr_engine *e, const kr_flags *flags) {
   if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaEventRecord(e->ev_a, e->sm));
-  int rc = launch_pass(e, *flags, false);
+  int rc = run_pass(e, *flags, e->ev_b);
   if (rc) return rc;
-  CK(cudaEventRecord(e->ev_b, e->sm));
-  CK(cudaStreamSynchronize(e->sm));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
   e->ran = true;
@@ -460,14 +533,12 @@ int kr_reconcile_batch(kr_engine *e, const kr_flags *flags, kr_results_view *out
   if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaEventRecord(e->ev_a, e->sm));
-  int rc = launch_pass(e, *flags, false);
+  int rc = run_pass(e, *flags, e->ev_k[KR_MAX_KERNEL_TIMES]);
   if (rc) return rc;
   e->ran = true;
-  // ev_b is recorded at the head of fetch_results: kernels_ms = ev_a..ev_b, d2h_ms = ev_b..ev_c
-  rc = fetch_results(e, out);
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
-  return rc;
+  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_k[KR_MAX_KERNEL_TIMES]) == cudaSuccess) e->prof.kernels_ms = ms;
+  return fetch_results(e, out);  // d2h_ms = ev_b..ev_c
 }
 
 int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile *prof) {
@@ -478,7 +549,16 @@ int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile 
   int rc = launch_pass(e, *flags, true);
   if (rc) return rc;
   CK(cudaEventRecord(e->ev_b, e->sm));
+  CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
   CK(cudaStreamSynchronize(e->sm));
+  if (e->ran_fast && (e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) {
+    e->force_radix = true; e->gvalid = false;
+    CK(cudaEventRecord(e->ev_a, e->sm));
+    rc = launch_pass(e, *flags, true);
+    if (rc) return rc;
+    CK(cudaEventRecord(e->ev_b, e->sm));
+    CK(cudaStreamSynchronize(e->sm));
+  }
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
   uint32_t k = e->prof.n_kernels < KR_MAX_KERNEL_TIMES ? e->prof.n_kernels : KR_MAX_KERNEL_TIMES;
@@ -513,6 +593,7 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
   size_t o_off = 0, o_len = align_up(8 * (size_t)n), o_data = align_up(o_len + 4 * (size_t)n), o_out = align_up(o_data + data + 16), total = o_out + 32 * (size_t)n;
   if (total > e->hb_cap) {
     if (e->hb_h) cudaFreeHost(e->hb_h);
+  if (e->h_totals) cudaFreeHost(e->h_totals);
     if (e->hb_d) cudaFree(e->hb_d);
     e->hb_h = nullptr; e->hb_d = nullptr; e->hb_cap = 0;
     size_t cap = total + total / 4;
@@ -556,6 +637,17 @@ int kr_group_results_device(kr_engine *e, const void **dev_ptr, uint64_t *bytes)
   if (!e->ran) return fail(e, KR_E_STATE, "no pass has run");
   *dev_ptr = e->d_out + e->ol.groups;
   *bytes = sizeof(kr_group_result) * (uint64_t)e->sizes.n_groups;
+  return KR_OK;
+}
+
+int kr_group_results_copy(kr_engine *e, void *dst_device, uint64_t dst_capacity_bytes) {
+  if (!e || !dst_device) return KR_E_INVALID;
+  if (!e->ran) return fail(e, KR_E_STATE, "no pass has run");
+  uint64_t bytes = sizeof(kr_group_result) * (uint64_t)e->sizes.n_groups;
+  if (bytes > dst_capacity_bytes) return fail(e, KR_E_CAPACITY, "destination too small (%llu < %llu)", (unsigned long long)dst_capacity_bytes, (unsigned long long)bytes);
+  CK(cudaSetDevice(e->cfg.device));
+  if (bytes) CK(cudaMemcpyAsync(dst_device, e->d_out + e->ol.groups, bytes, cudaMemcpyDeviceToDevice, e->sm));
+  CK(cudaStreamSynchronize(e->sm));
   return KR_OK;
 }
 

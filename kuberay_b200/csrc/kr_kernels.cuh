@@ -64,18 +64,22 @@ struct ResDev {  // device results arena
   uint8_t *sorted_action;
   int32_t *create_idx;
   kr_job_result *jobs;
-  uint32_t *totals;  // [0]=n_create_total [1]=n_orphans [2]=n_actions [3]=error flags
+  uint32_t *totals;  // [0]=n_create_total [1]=n_orphans [2]=n_actions [3]=error flags [4]=clusters deferred to decide phase 1
 };
 
 struct ScratchDev {
-  uint64_t *cl_keys; uint32_t *cl_vals; uint32_t cl_mask;      // cluster table
+  uint4 *cl_slots; uint32_t cl_mask;                           // cluster table: {key lo, key hi, cluster idx, -} per 16-byte slot
+  uint4 *cl_rec;                                               // [n_clusters] {group_off, group_cnt, name id of group 0, -}
   uint64_t *wt_keys; uint32_t *wt_head; uint32_t *wt_next; uint32_t wt_mask;  // workersToDelete-name table
   uint32_t *aux_keys; uint32_t *aux_vals; uint32_t aux_mask;   // pod idx -> head-aux row
   uint4 *rows;                                                 // 16-byte pod rows, original order
   uint32_t *keys[2]; uint32_t *vals[2];                        // radix ping-pong
   uint32_t *hist;                                              // [256 * ntiles] digit-major
+  uint32_t *row_total;                                         // [256] per-digit totals of the current pass
+  uint32_t *gcreate;                                           // [n_groups] dense n_create (input of the creates scan)
+  uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]
+  uint32_t *deferred_list;                                     // clusters left for decide phase 1 (count in totals[4])
   int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
-  uint8_t *deferred;                                           // [n_clusters] decide phase 0 left it for phase 1 (needs the hash)
 };
 
 struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
@@ -84,6 +88,7 @@ struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
 #define KR_ROW_WTD_OWN (1u << 11)   // named by its own group's scaleStrategy.workersToDelete
 #define KR_ROW_NO_GROUP 0xFFFFu
 #define KR_TOTALS_ERR_MH_UNSUPPORTED 1u
+#define KR_TOTALS_BIG_BUCKET 2u        // fast pipeline only: some cluster (or the orphan bucket) holds more pods than the in-warp sort takes
 
 // error bits in totals[3]
 #define KR_DEVERR_TABLE_FULL 2u
@@ -135,12 +140,11 @@ __device__ __forceinline__ int32_t desired_replicas(int32_t replicas, int32_t mn
 
 __device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uint32_t name, uint32_t &out) {
   if (name == 0) return false;
-  uint64_t k = key2(ns, name);
-  uint32_t i = (uint32_t)mix64(k) & sc.cl_mask;
+  uint32_t i = (uint32_t)mix64(key2(ns, name)) & sc.cl_mask;
   while (true) {
-    uint64_t kk = __ldg(&sc.cl_keys[i]);
-    if (kk == k) { out = __ldg(&sc.cl_vals[i]); return true; }
-    if (kk == KR_EMPTY64) return false;
+    uint4 sl = __ldg(&sc.cl_slots[i]);  // one 16-byte load: key and value together
+    if (sl.x == name && sl.y == ns) { out = sl.z; return true; }
+    if (sl.x == KR_EMPTY32 && sl.y == KR_EMPTY32) return false;
     i = (i + 1) & sc.cl_mask;
   }
 }
@@ -151,13 +155,18 @@ __device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uin
 __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n.n_clusters) {
-    uint64_t k = key2(s.c_ns_id[t], s.c_name_id[t]);
+    uint32_t ns = s.c_ns_id[t], name = s.c_name_id[t];
+    uint64_t k = key2(ns, name);
     uint32_t i = (uint32_t)mix64(k) & sc.cl_mask;
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(sc.cl_slots);  // [2*i] = key (x = name, y = ns), [2*i+1] low word = idx
+    const unsigned long long kk = ((unsigned long long)ns << 32) | name;
     while (true) {
-      unsigned long long prev = atomicCAS((unsigned long long *)&sc.cl_keys[i], KR_EMPTY64, k);
-      if (prev == KR_EMPTY64 || prev == k) { atomicMin(&sc.cl_vals[i], t); break; }  // duplicate (ns,name): lowest index wins
+      unsigned long long prev = atomicCAS(&slots[2 * (size_t)i], KR_EMPTY64, kk);
+      if (prev == KR_EMPTY64 || prev == kk) { atomicMin(reinterpret_cast<uint32_t *>(&slots[2 * (size_t)i + 1]), t); break; }  // duplicate (ns,name): lowest index wins
       i = (i + 1) & sc.cl_mask;
     }
+    uint32_t g0 = s.c_group_off[t], G = s.c_group_cnt[t];
+    sc.cl_rec[t] = make_uint4(g0, G, G ? s.g_name_id[g0] : 0u, 0u);
     return;
   }
   t -= n.n_clusters;
@@ -210,35 +219,69 @@ __device__ __forceinline__ int32_t aux_lookup(const ScratchDev &sc, uint32_t p) 
 // ray.io/group against the cluster's worker groups.  Streams 7 coalesced columns (28 B/pod), writes one 16-byte row
 // + 4-byte sort key per pod, and the pass-0 digit histogram of its tile.
 
+// kFast: the count/place/sort-in-warp pipeline (per-cluster arrival rank by a returning atomic, no radix histogram).
+// The loop is phased — all column loads, then all table probes, then all record loads — so that each thread keeps
+// 8 independent memory requests in flight per phase instead of walking one pod's dependent chain at a time.
+template <bool kFast>
 __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc, ResDev r, Sizes n, int has_wtd) {
   __shared__ uint32_t s_hist[kRadix];
   const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  s_hist[threadIdx.x] = 0;
-  __syncthreads();
+  if (!kFast) { s_hist[threadIdx.x] = 0; __syncthreads(); }
   const uint32_t base = tile * kSortTile + warp * (32 * kSortItems) + lane;
+  uint32_t ns[kSortItems], cn[kSortItems], gn[kSortItems], nm[kSortItems], pk[kSortItems], rn[kSortItems], ri[kSortItems];
+  // phase A: 7 coalesced column loads per pod
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    uint32_t p = base + it * 32;
+    bool v = p < n.n_pods;
+    ns[it] = v ? __ldg(&s.p_ns_id[p]) : 0u; cn[it] = v ? __ldg(&s.p_cluster_name_id[p]) : 0u;
+    gn[it] = v ? __ldg(&s.p_group_name_id[p]) : 0u; nm[it] = v ? __ldg(&s.p_name_id[p]) : 0u;
+    pk[it] = v ? __ldg(&s.p_packed[p]) : 0u; ri[it] = v ? (uint32_t)__ldg(&s.p_replica_index[p]) : 0u;
+    rn[it] = v ? __ldg(&s.p_replica_name_id[p]) : 0u;
+  }
+  // phase B: hash-join probe (namespace, ray.io/cluster) -> cluster idx; first slot of every pod in flight together
+  uint32_t c[kSortItems], pi[kSortItems];
+  uint4 sl[kSortItems];
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    pi[it] = (uint32_t)mix64(key2(ns[it], cn[it])) & sc.cl_mask;
+    sl[it] = __ldg(&sc.cl_slots[pi[it]]);
+  }
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    c[it] = n.n_clusters;
+    if (cn[it] != 0) {
+      uint4 q = sl[it];
+      uint32_t i = pi[it];
+      while (true) {
+        if (q.x == cn[it] && q.y == ns[it]) { c[it] = q.z; break; }
+        if (q.x == KR_EMPTY32 && q.y == KR_EMPTY32) break;
+        i = (i + 1) & sc.cl_mask;
+        q = __ldg(&sc.cl_slots[i]);
+      }
+    }
+  }
+  // phase C: the cluster's group record
+  uint4 rec[kSortItems];
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) rec[it] = (c[it] < n.n_clusters) ? __ldg(&sc.cl_rec[c[it]]) : make_uint4(0, 0, 0, 0);
+  // phase D: ray.io/group against the cluster's worker groups, workersToDelete-name intersection, outputs
 #pragma unroll
   for (int it = 0; it < kSortItems; it++) {
     uint32_t p = base + it * 32;
     if (p >= n.n_pods) continue;
-    uint32_t ns = __ldg(&s.p_ns_id[p]), cn = __ldg(&s.p_cluster_name_id[p]), gn = __ldg(&s.p_group_name_id[p]);
-    uint32_t nm = __ldg(&s.p_name_id[p]), pk = __ldg(&s.p_packed[p]);
-    int32_t ri = __ldg(&s.p_replica_index[p]);
-    uint32_t rn = __ldg(&s.p_replica_name_id[p]);
-    uint32_t c = n.n_clusters, slot = KR_ROW_NO_GROUP, g0 = 0;
-    uint32_t found;
-    if (cl_lookup(sc, ns, cn, found)) {
-      c = found;
-      g0 = __ldg(&s.c_group_off[c]);
-      uint32_t G = __ldg(&s.c_group_cnt[c]);
-      if (gn != 0)
-        for (uint32_t gi = 0; gi < G; gi++)
-          if (__ldg(&s.g_name_id[g0 + gi]) == gn) { slot = gi; break; }  // group names are unique (pkg/webhooks/v1/raycluster_webhook.go:74)
+    uint32_t slot = KR_ROW_NO_GROUP, g0 = rec[it].x;
+    if (c[it] < n.n_clusters && gn[it] != 0) {
+      if (rec[it].y && rec[it].z == gn[it]) slot = 0;
+      else
+        for (uint32_t gi = 1; gi < rec[it].y; gi++)
+          if (__ldg(&s.g_name_id[g0 + gi]) == gn[it]) { slot = gi; break; }  // group names are unique (pkg/webhooks/v1/raycluster_webhook.go:74)
     }
-    uint32_t flags = pk & 0x7FFu;
+    uint32_t flags = pk[it] & 0x7FFu;
     if (has_wtd) {
-      // label-set intersection against the (tiny) workersToDelete-name table
-      uint64_t k = key2(ns, nm);
+      // label-set intersection against the (tiny, cache-resident) workersToDelete-name table
+      uint64_t k = key2(ns[it], nm[it]);
       uint32_t i = (uint32_t)mix64(k) & sc.wt_mask;
       while (true) {
         uint64_t kk = __ldg(&sc.wt_keys[i]);
@@ -246,8 +289,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
         if (kk == k) {
           for (uint32_t e = sc.wt_head[i]; e != KR_EMPTY32; e = sc.wt_next[e]) {
             atomicMin(&r.wtd_pod_idx[e], p);
-            // is e one of this pod's own group's names?  (group g lists wtd entries [off, off+cnt))
-            if (slot != KR_ROW_NO_GROUP) {
+            if (slot != KR_ROW_NO_GROUP) {  // is e one of this pod's own group's names?
               uint32_t g = g0 + slot;
               uint32_t off = __ldg(&s.g_wtd_off[g]);
               if (e >= off && e < off + __ldg(&s.g_wtd_cnt[g])) flags |= KR_ROW_WTD_OWN;
@@ -258,12 +300,112 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
         i = (i + 1) & sc.wt_mask;
       }
     }
-    sc.rows[p] = make_uint4(nm, rn, (uint32_t)ri, (slot << 16) | flags);
-    sc.keys[0][p] = c;
-    atomicAdd(&s_hist[c & (kRadix - 1)], 1u);
+    sc.rows[p] = make_uint4(nm[it], rn[it], ri[it], (slot << 16) | flags);
+    sc.keys[0][p] = c[it];
+    if (kFast) sc.keys[1][p] = atomicAdd(&sc.ccount[c[it]], 1u);  // arrival rank inside the cluster's bucket (bucket n_clusters = orphans)
+    else atomicAdd(&s_hist[c[it] & (kRadix - 1)], 1u);
   }
+  if (!kFast) {
+    __syncthreads();
+    sc.hist[threadIdx.x * ntiles + tile] = s_hist[threadIdx.x];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fast pipeline: scan + place
+// Exclusive scan of the per-cluster pod counts (bucket n_clusters = orphans) -> cstart[0 .. n_clusters+1].
+// Flags buckets too large for the in-warp sort (the engine then re-runs the pass on the radix pipeline).
+#define KR_FAST_MAX_BUCKET 1024u
+__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict__ ccount, uint32_t *__restrict__ cstart, uint32_t nb, uint32_t *totals) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  sc.hist[threadIdx.x * ntiles + tile] = s_hist[threadIdx.x];
+  bool big = false;
+  for (uint32_t base = 0; base < nb; base += 8192) {
+    uint32_t i0 = base + t * 8;
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < nb) ? ccount[i0 + k] : 0u;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { sum += v[k]; big |= v[k] > KR_FAST_MAX_BUCKET; }
+    uint32_t x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t wv = s_warp[lane], wx = wv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
+    uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
+    uint32_t run = s_carry + woff + x - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (i0 + k < nb) cstart[i0 + k] = run; run += v[k]; }
+    __syncthreads();
+    if (t == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (t == 0) cstart[nb] = s_carry;
+  if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
+}
+
+// pod -> its slot in the cluster's bucket: cstart[cluster] + arrival rank (order inside a bucket is fixed up by the
+// in-warp sort in k_decide, so the result does not depend on the order the atomics landed in).
+__global__ void __launch_bounds__(256) k_place(const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
+                                               const uint32_t *__restrict__ cstart, uint32_t *__restrict__ out, uint32_t n) {
+  uint32_t p = blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; k++, p += 256)
+    if (p < n) out[__ldg(&cstart[__ldg(&key[p])]) + __ldg(&rank[p])] = p;
+}
+
+// Bitonic sort of 32*K values held K per lane (element g = lane*K + k); ascending.
+template <int K>
+__device__ __forceinline__ void warp_bitonic_sort(uint32_t (&v)[K], uint32_t lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= K) {
+        const int ls = stride / K;
+        const bool lower = (lane & ls) == 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v[k], ls);
+          bool asc = ((lane * K + k) & size) == 0;
+          v[k] = (asc == lower) ? min(v[k], o) : max(v[k], o);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if ((k & stride) == 0) {
+            bool asc = ((lane * K + k) & size) == 0;
+            uint32_t lo = min(v[k], v[k + stride]), hi = max(v[k], v[k + stride]);
+            v[k] = asc ? lo : hi; v[k + stride] = asc ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Sort one bucket of pod indices ascending (= informer List order): in[0..P) -> out[0..P), P <= 32*K.
+template <int K>
+__device__ __forceinline__ void warp_sort_bucket(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t P, uint32_t lane) {
+  uint32_t v[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { uint32_t g = lane * K + k; v[k] = g < P ? in[g] : 0xFFFFFFFFu; }
+  warp_bitonic_sort<K>(v, lane);
+#pragma unroll
+  for (int k = 0; k < K; k++) { uint32_t g = lane * K + k; if (g < P) out[g] = v[k]; }
+}
+
+__device__ __forceinline__ void warp_sort_dispatch(const uint32_t *in, uint32_t *out, uint32_t P, uint32_t lane) {
+  if (P <= 32) warp_sort_bucket<1>(in, out, P, lane);
+  else if (P <= 128) warp_sort_bucket<4>(in, out, P, lane);
+  else if (P <= 256) warp_sort_bucket<8>(in, out, P, lane);
+  else warp_sort_bucket<32>(in, out, P, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ radix sort (stable LSD)
@@ -283,41 +425,62 @@ __global__ void __launch_bounds__(kSortThreads) k_hist(const uint32_t *__restric
   hist[threadIdx.x * ntiles + tile] = s_hist[threadIdx.x];
 }
 
-// exclusive scan of m = 256*ntiles counters in place; one block of 1024 threads
-__global__ void __launch_bounds__(1024) k_scan_hist(uint32_t *__restrict__ a, uint32_t m) {
-  __shared__ uint32_t s_warp[32];
+// Exclusive scan along each digit row of hist[256][ntiles] in place (block d = digit d) + the row total.
+// k_scatter turns the 256 row totals into digit bases itself, so no single-block scan sits on the critical path.
+static constexpr int kRowScanThreads = 128;
+__global__ void __launch_bounds__(kRowScanThreads) k_scan_rows(uint32_t *__restrict__ hist, uint32_t *__restrict__ row_total, uint32_t ntiles) {
+  __shared__ uint32_t s_warp[kRowScanThreads / 32];
+  __shared__ uint32_t s_carry;
+  uint32_t *row = hist + (size_t)blockIdx.x * ntiles;
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const uint32_t per = (m + 1023) / 1024;
-  const uint32_t lo = min(t * per, m), hi = min(lo + per, m);
-  uint32_t sum = 0;
-  for (uint32_t i = lo; i < hi; i++) sum += a[i];
-  uint32_t x = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
-  if (lane == 31) s_warp[w] = x;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  if (w == 0) {
-    uint32_t v = s_warp[lane];
+  for (uint32_t base = 0; base < ntiles; base += kRowScanThreads * 4) {
+    uint32_t i0 = base + t * 4;
+    uint32_t v[4];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += y; }
-    s_warp[lane] = v;
+    for (int k = 0; k < 4; k++) v[k] = (i0 + k < ntiles) ? row[i0 + k] : 0u;
+    uint32_t sum = v[0] + v[1] + v[2] + v[3], x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kRowScanThreads / 32; k++) { uint32_t wv = s_warp[k]; if (k < (int)w) woff += wv; total += wv; }
+    uint32_t run = s_carry + woff + x - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i0 + k < ntiles) row[i0 + k] = run; run += v[k]; }
+    __syncthreads();
+    if (t == 0) s_carry += total;
+    __syncthreads();
   }
-  __syncthreads();
-  uint32_t run = x - sum + (w ? s_warp[w - 1] : 0);
-  for (uint32_t i = lo; i < hi; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+  if (t == 0) row_total[blockIdx.x] = s_carry;
 }
 
 // Stable scatter of one tile: warp-match ranking keeps equal digits in original order.
 // first_pass: values are the identity (pod index == position). write_keys: needed unless the consumer only wants values.
 __global__ void __launch_bounds__(kSortThreads) k_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                                                          const uint32_t *__restrict__ hist, uint32_t n, int shift, int first_pass) {
+                                                          const uint32_t *__restrict__ hist, const uint32_t *__restrict__ row_total,
+                                                          uint32_t n, int shift, int first_pass) {
   __shared__ uint32_t s_cnt[kSortThreads / 32][kRadix];
   __shared__ uint32_t s_base[kRadix];
+  __shared__ uint32_t s_wsum[kSortThreads / 32];
   const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = lane; i < kRadix; i += 32) s_cnt[warp][i] = 0;
-  s_base[threadIdx.x] = hist[threadIdx.x * ntiles + tile];
+  {  // digit base = exclusive scan of the 256 row totals (thread d owns digit d) + this tile's offset inside the row
+    uint32_t tot = __ldg(&row_total[threadIdx.x]), x = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int k = 0; k < kSortThreads / 32; k++) if (k < (int)warp) woff += s_wsum[k];
+    s_base[threadIdx.x] = woff + x - tot + __ldg(&hist[threadIdx.x * ntiles + tile]);
+  }
   __syncwarp();
   const uint32_t base = tile * kSortTile + warp * (32 * kSortItems) + lane;
   uint32_t key[kSortItems], rank[kSortItems];
@@ -383,7 +546,9 @@ __device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict_
 
 struct DecideArgs {
   SnapDev s; ScratchDev sc; ResDev r; Sizes n; kr_flags f;
-  const uint32_t *sorted_keys;  // cluster idx per sorted position
+  const uint32_t *sorted_keys;  // radix pipeline: cluster idx per sorted position
+  const uint32_t *unsorted;     // fast pipeline: pods bucketed by cluster in arrival order (sorted per bucket here)
+  int fast;
   int phase;                    // 0: everything that does not need the hash; 1: only clusters deferred by phase 0
 };
 
@@ -512,23 +677,30 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
   __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t c = blockIdx.x * kDecideWarps + warp;
   const SnapDev &s = a.s;
   const uint32_t Nc = a.n.n_clusters, Np = a.n.n_pods;
-  if (c > Nc) return;
+  uint32_t c = blockIdx.x * kDecideWarps + warp;
+  if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
+    if (c >= a.r.totals[4]) return;
+    c = a.sc.deferred_list[c];
+  } else if (c > Nc) return;
   const uint32_t lt = lanemask_lt();
 
+  uint32_t seg0, seg1;
+  if (a.fast) {
+    seg0 = a.sc.cstart[c]; seg1 = a.sc.cstart[c + 1];
+    // informer List order inside the bucket: sort the pod indices ascending (skipped in phase 1: already done)
+    if (a.phase == 0 && seg1 - seg0 <= KR_FAST_MAX_BUCKET) { warp_sort_dispatch(a.unsorted + seg0, a.r.sorted_pod_idx + seg0, seg1 - seg0, lane); __syncwarp(); }
+  } else {
+    seg0 = warp_lower_bound(a.sorted_keys, Np, c, lane);
+    seg1 = (c == Nc) ? Np : warp_lower_bound(a.sorted_keys, Np, c + 1, lane);
+  }
   if (c == Nc) {  // the orphan bucket: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot
     if (a.phase != 0) return;
-    uint32_t st = warp_lower_bound(a.sorted_keys, Np, Nc, lane);
-    for (uint32_t i = st + lane; i < Np; i += 32) a.r.sorted_action[i] = KR_ACT_ORPHAN;
-    if (lane == 0) a.r.totals[1] = Np - st;
+    for (uint32_t i = seg0 + lane; i < seg1; i += 32) a.r.sorted_action[i] = KR_ACT_ORPHAN;
+    if (lane == 0) a.r.totals[1] = seg1 - seg0;
     return;
   }
-  if (a.phase == 1 && !a.sc.deferred[c]) return;
-
-  const uint32_t seg0 = warp_lower_bound(a.sorted_keys, Np, c, lane);
-  const uint32_t seg1 = warp_lower_bound(a.sorted_keys, Np, c + 1, lane);
   const uint32_t P = seg1 - seg0;
   const uint32_t cf = s.c_flags[c];
   const uint32_t G = s.c_group_cnt[c], g0 = s.c_group_off[c];
@@ -621,7 +793,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
       else if (ast == KR_ANNOT_OTHER) recreate = true;
       else if (ast == KR_ANNOT_HASH32 && !a.f.skip_hash) {
         if (a.phase == 0) {  // the hash kernel runs concurrently on another stream: decide this cluster in phase 1
-          if (lane == 0) a.sc.deferred[c] = 1;
+          if (lane == 0) a.sc.deferred_list[atomicAdd(&a.r.totals[4], 1u)] = c;
           return;
         }
         const uint8_t *ah = s.h_annot_hash + 32 * (size_t)aux;
@@ -694,6 +866,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
       if (g_mode) { if (lane == 0) { g_mode[gi] = mode; g_prefix[gi] = prefix; } }
       if (lane == 0) {
         a.r.groups[g] = gr;
+        a.sc.gcreate[g] = gr.n_create;
         if (!g_mode) { a.sc.gacc[g] = mode; a.sc.gacc[a.n.n_groups + g] = prefix; }  // spill: reuse n_list/n_unh cells (already consumed)
       }
       if (abort_here) { cr.stop_after_group = (int32_t)gi; break; }
@@ -705,12 +878,14 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
     for (uint32_t gi = reached + lane; gi < G; gi += 32) {
       kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
       a.r.groups[g0 + gi] = z;
+      a.sc.gcreate[g0 + gi] = 0;
       if (!g_mode) { a.sc.gacc[g0 + gi] = GM_UNPROCESSED; a.sc.gacc[a.n.n_groups + g0 + gi] = 0; }
     }
   } else {
     for (uint32_t gi = lane; gi < G; gi += 32) {
       kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
       a.r.groups[g0 + gi] = z;
+      a.sc.gcreate[g0 + gi] = 0;
     }
   }
   if (any_multihost && lane == 0) atomicOr(&a.r.totals[3], KR_TOTALS_ERR_MH_UNSUPPORTED);
@@ -768,29 +943,44 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
 
 // ------------------------------------------------------------------------------------------------ creates
 
-// exclusive scan of group n_create -> create_off, total in totals[0]; one block
-__global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, uint32_t n_groups) {
+// exclusive scan of the dense n_create array -> groups[].create_off, total in totals[0].  One block; every thread
+// loads 8 consecutive counters per sweep (two 16-byte loads), so a sweep of 8192 groups costs one memory round trip.
+__global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, const uint32_t *__restrict__ gcreate, uint32_t n_groups) {
   __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const uint32_t per = (n_groups + 1023) / 1024;
-  const uint32_t lo = min(t * per, n_groups), hi = min(lo + per, n_groups);
-  uint32_t sum = 0;
-  for (uint32_t i = lo; i < hi; i++) sum += r.groups[i].n_create;
-  uint32_t x = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
-  if (lane == 31) s_warp[w] = x;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  if (w == 0) {
-    uint32_t v = s_warp[lane];
+  for (uint32_t base = 0; base < n_groups; base += 8192) {
+    uint32_t i0 = base + t * 8;
+    uint32_t v[8];
+    if (i0 + 8 <= n_groups) {
+      uint4 a0 = *reinterpret_cast<const uint4 *>(gcreate + i0), a1 = *reinterpret_cast<const uint4 *>(gcreate + i0 + 4);
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    } else {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += y; }
-    s_warp[lane] = v;
+      for (int k = 0; k < 8; k++) v[k] = (i0 + k < n_groups) ? gcreate[i0 + k] : 0u;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += v[k];
+    uint32_t x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t wv = s_warp[lane], wx = wv;  // every warp scans the 32 warp sums redundantly
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
+    uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
+    uint32_t run = s_carry + woff + x - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (i0 + k < n_groups) r.groups[i0 + k].create_off = run; run += v[k]; }
+    __syncthreads();
+    if (t == 0) s_carry += total;
+    __syncthreads();
   }
-  __syncthreads();
-  uint32_t run = x - sum + (w ? s_warp[w - 1] : 0);
-  for (uint32_t i = lo; i < hi; i++) { uint32_t v = r.groups[i].n_create; r.groups[i].create_off = run; run += v; }
-  if (t == 1023) r.totals[0] = run;
+  if (t == 0) r.totals[0] = s_carry;
 }
 
 // Lowest free ray.io/worker-group-replica-index values for the pods to create (raycluster_controller.go:854-881).

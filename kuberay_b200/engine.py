@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
         L.kr_hash_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.kr_last_profile.argtypes = [C.c_void_p, P(abi.kr_profile)]
         L.kr_group_results_device.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_uint64)]
+        L.kr_group_results_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.kr_last_error.argtypes = [C.c_void_p]
         L.kr_last_error.restype = C.c_char_p
         L.kr_algorithmic_bytes.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
@@ -166,7 +167,8 @@ class Engine:
 
     @staticmethod
     def _profile_dict(prof: abi.kr_profile, kernels: bool) -> dict:
-        d = {"h2d_ms": prof.h2d_ms, "kernels_ms": prof.kernels_ms, "d2h_ms": prof.d2h_ms, "n_kernels": prof.n_kernels}
+        d = {"h2d_ms": prof.h2d_ms, "kernels_ms": prof.kernels_ms, "d2h_ms": prof.d2h_ms, "n_kernels": prof.n_kernels,
+             "h2d_bytes": prof.h2d_bytes, "d2h_bytes": prof.d2h_bytes}
         if kernels:
             k = min(prof.n_kernels, abi.MAX_KERNEL_TIMES)
             d["kernels"] = [((prof.kernel_name[i] or b"?").decode(), prof.kernel_ms[i]) for i in range(k)]
@@ -181,6 +183,9 @@ class Engine:
         p, n = C.c_void_p(), C.c_uint64()
         self._check(self._L.kr_group_results_device(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def group_results_copy(self, dst_device_ptr: int, capacity_bytes: int):
+        self._check(self._L.kr_group_results_copy(self._h, C.c_void_p(dst_device_ptr), capacity_bytes))
 
     def hash_batch(self, messages: list[bytes]) -> list[str]:
         n = len(messages)

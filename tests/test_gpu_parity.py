@@ -51,6 +51,42 @@ def test_parity_flag_variants(oracle_mod):
         _parity(snap, f, oracle_mod)
 
 
+def test_parity_big_bucket_falls_back_to_radix(oracle_mod):
+    # one RayCluster with 3000 pods: the fast pipeline's in-warp sort takes <= 1024 per bucket, the engine must switch
+    # to the radix pipeline by itself and still be bit-exact
+    snap, flags = synthetic.generate(synthetic.SynthParams(n_clusters=20, pods_per_cluster=3000, groups=2))
+    _parity(snap, flags, oracle_mod)
+
+
+def test_parity_radix_pipeline_forced(oracle_mod, monkeypatch):
+    monkeypatch.setenv("KR_FORCE_RADIX", "1")
+    snap, flags = synthetic.generate(synthetic.config("C2", groups=2))
+    _parity(snap, flags, oracle_mod)
+    snap, flags = synthetic.generate(synthetic.config("C3"))
+    _parity(snap, flags, oracle_mod)
+
+
+def test_parity_without_cuda_graph(oracle_mod, monkeypatch):
+    monkeypatch.setenv("KR_NO_GRAPH", "1")
+    snap, flags = synthetic.generate(synthetic.config("C2"))
+    _parity(snap, flags, oracle_mod)
+
+
+def test_repeated_passes_are_identical(oracle_mod):
+    snap, flags = synthetic.generate(synthetic.config("C2"))
+    eng = Engine.for_snapshot(snap)
+    try:
+        eng.load(snap)
+        first = eng.reconcile(flags)
+        for _ in range(3):
+            again = eng.reconcile(flags)
+            assert not first.diff(again)
+        eng.commit()
+        assert not first.diff(eng.reconcile(flags))
+    finally:
+        eng.close()
+
+
 def test_hash_batch_matches_hashlib():
     import base64
     import hashlib
