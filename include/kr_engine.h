@@ -57,7 +57,8 @@ enum {
   KR_EXT_ERR_FAILED_DELETE_HEAD_POD = 3,
   KR_EXT_ERR_FAILED_CREATE_HEAD_POD = 4,
   KR_EXT_ERR_FAILED_DELETE_WORKER_POD = 5,
-  KR_EXT_ERR_FAILED_CREATE_WORKER_POD = 6
+  KR_EXT_ERR_FAILED_CREATE_WORKER_POD = 6,
+  KR_EXT_ERR_STATUS_ONLY_NIL = 7   /* status-only evaluation with reconcileErr == nil: decisions skipped (replays calculateStatus(ctx, instance, nil)) */
 };
 
 /* condition status codes (metav1.ConditionStatus) */
@@ -166,6 +167,12 @@ enum {
   KR_SERR_NO_HEAD_SERVICE = 2,
   KR_SERR_MULTIPLE_HEAD_SERVICES = 3,
   KR_SERR_EMPTY_SERVICE_IP = 4
+};
+
+/* cluster_results.status_flags */
+enum {
+  KR_SF_READY_BRANCH = 1u << 0,      /* State = ready and Reason = "" were assigned this pass (:1599-1604) */
+  KR_SF_ALL_PODS_RUNNING = 1u << 1   /* utils.CheckAllPodsRunning(runtimePods) (utils/util.go:584-603) */
 };
 
 /* group_results.flags */
@@ -311,7 +318,7 @@ typedef struct kr_cluster_result {      /* 96 bytes */
   uint32_t head_ready_reason_id, head_ready_msg_id;
   uint32_t head_ids[4];          /* podIP, serviceIP, podName, serviceName */
   uint32_t pod_start;            /* this cluster's pods are sorted_pod_idx[pod_start .. pod_start+n_pods) in list order */
-  uint32_t reserved;
+  uint32_t status_flags;         /* KR_SF_* */
 } kr_cluster_result;
 
 typedef struct kr_group_result {        /* 32 bytes */

@@ -25,7 +25,8 @@ CF_OLD_REASON_NONEMPTY = 1 << 8
 SUSPEND_NONE, SUSPEND_SUSPENDING, SUSPEND_SUSPENDED = 0, 1, 2
 
 (EXT_ERR_NONE, EXT_ERR_PLAIN, EXT_ERR_FAILED_DELETE_ALL_PODS, EXT_ERR_FAILED_DELETE_HEAD_POD,
- EXT_ERR_FAILED_CREATE_HEAD_POD, EXT_ERR_FAILED_DELETE_WORKER_POD, EXT_ERR_FAILED_CREATE_WORKER_POD) = range(7)
+ EXT_ERR_FAILED_CREATE_HEAD_POD, EXT_ERR_FAILED_DELETE_WORKER_POD, EXT_ERR_FAILED_CREATE_WORKER_POD,
+ EXT_ERR_STATUS_ONLY_NIL) = range(8)
 
 COND_ABSENT, COND_TRUE, COND_FALSE, COND_UNKNOWN = 0, 1, 2, 3
 COND_PROVISIONED, COND_HEAD_POD_READY, COND_REPLICA_FAILURE, COND_SUSPENDING, COND_SUSPENDED = range(5)
@@ -60,6 +61,8 @@ HEAD_NONE, HEAD_EXPECT_PENDING, HEAD_DELETE, HEAD_CREATE, HEAD_SKIP_RESTART, HEA
 (ERR_NONE, ERR_HEAD_DELETED, ERR_MULTIPLE_HEADS, ERR_UNHEALTHY_WORKERS, ERR_MH_INCOMPLETE, ERR_MH_WTD,
  ERR_MH_NOT_MULTIPLE, ERR_EXTERNAL, ERR_NEGATIVE_EXPECTED) = range(9)
 SERR_NONE, SERR_MULTIPLE_HEADS, SERR_NO_HEAD_SERVICE, SERR_MULTIPLE_HEAD_SERVICES, SERR_EMPTY_SERVICE_IP = range(5)
+
+SF_READY_BRANCH, SF_ALL_PODS_RUNNING = 1, 2
 
 GR_PROCESSED = 1 << 0
 GR_EXPECT_PENDING = 1 << 1
@@ -134,7 +137,7 @@ cluster_result_dtype = np.dtype([
     ("needs_status_write", u8), ("head_update_annotations", u8),
     ("stop_after_group", i32), ("err_arg", i32), ("n_pods", i32), ("n_heads", i32), ("head_pod_idx", i32),
     ("counts", i32, (5,)), ("cond_status", u8, (8,)), ("cond_variant", u8, (8,)),
-    ("head_ready_reason_id", u32), ("head_ready_msg_id", u32), ("head_ids", u32, (4,)), ("pod_start", u32), ("reserved", u32),
+    ("head_ready_reason_id", u32), ("head_ready_msg_id", u32), ("head_ids", u32, (4,)), ("pod_start", u32), ("status_flags", u32),
 ], align=True)
 group_result_dtype = np.dtype([
     ("expected", i32), ("n_list", i32), ("n_unhealthy", i32), ("n_running", i32), ("diff", i32),

@@ -644,6 +644,7 @@ __device__ void status_rollup(const DecideArgs &a, uint32_t c, kr_cluster_result
 
   cr.new_state = new_state;
   cr.state_changed = new_state != old_state;
+  cr.status_flags = (reason_cleared ? KR_SF_READY_BRANCH : 0u) | (all_running ? KR_SF_ALL_PODS_RUNNING : 0u);
   cr.counts[0] = ready; cr.counts[1] = available; cr.counts[2] = desired; cr.counts[3] = minr; cr.counts[4] = maxc;
 #pragma unroll
   for (int k = 0; k < KR_NUM_CONDS; k++) { cr.cond_status[k] = cst[k]; cr.cond_variant[k] = cvr[k]; }
@@ -778,7 +779,8 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
   if (cf & KR_CF_SKIP) {
     cr.path = KR_PATH_SKIPPED;
   } else if (s.c_ext_err_kind[c] != KR_EXT_ERR_NONE) {
-    cr.path = KR_PATH_SKIPPED; cr.err_kind = KR_ERR_EXTERNAL;  // :308-314
+    cr.path = KR_PATH_SKIPPED;  // :308-314
+    cr.err_kind = s.c_ext_err_kind[c] == KR_EXT_ERR_STATUS_ONLY_NIL ? KR_ERR_NONE : KR_ERR_EXTERNAL;
   } else if (suspend_status == KR_SUSPEND_SUSPENDING || (!gate && (cf & KR_CF_SUSPEND))) {
     cr.path = KR_PATH_SUSPENDING_DELETE_ALL; all_action = KR_ACT_DELETE_ALL_SUSPEND;  // :629-644
   } else if (gate && (suspend_status == KR_SUSPEND_SUSPENDED || (cf & KR_CF_SUSPEND))) {

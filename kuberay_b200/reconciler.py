@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference RayClusterReconciler for the hot path.
+
+This is the Python statement of what the Go shim does around the engine: it packs the watched objects,
+asks a *backend* for one batched pass, and then performs the side effects the reference performs — Delete / Create /
+Eventf / the returned error — in the reference's order, reading them off the DecisionRecord / StatusRecord instead of
+recomputing them per object:
+
+  reconcile_pods(instance)            ~ RayClusterReconciler.reconcilePods      (raycluster_controller.go:619-935)
+  calculate_status(instance, err)     ~ RayClusterReconciler.calculateStatus     (raycluster_controller.go:1552-1719)
+  update_status(instance, new)        ~ updateRayClusterStatus                   (raycluster_controller.go:1951-1966)
+
+`backend` is anything with `run(snapshot, flags) -> abi.Results`: the CUDA engine (EngineBackend below) in production and
+on the GPU tests; the tests inject the CPU oracle to pin the semantics against the reference's own test tables.
+The FakeClient mirrors controller-runtime's fake client as the reference's unit tests use it: List returns objects ordered
+by name, Delete removes immediately (raycluster_controller_unit_test.go:445-448,484).
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+
+from . import abi
+from . import snapshot as snapmod
+
+# event reasons (utils/constant.go:337-438)
+EV_DELETED_POD = "DeletedPod"
+EV_DELETED_HEAD_POD = "DeletedHeadPod"
+EV_DELETED_WORKER_POD = "DeletedWorkerPod"
+EV_CREATED_HEAD_POD = "CreatedHeadPod"
+EV_CREATED_WORKER_POD = "CreatedWorkerPod"
+
+
+@dataclass
+class Env:
+    """Process-level switches the reference reads at reconcile time."""
+    status_conditions_gate: bool = True      # features.RayClusterStatusConditions
+    multihost_indexing_gate: bool = True     # features.RayMultiHostIndexing
+    enable_random_pod_delete: bool = False   # ENABLE_RANDOM_POD_DELETE == "true"
+
+
+class FakeClient:
+    """Minimal object store: RayClusters by (ns,name), Pods by (ns,name)."""
+
+    def __init__(self, clusters=(), pods=(), jobs=()):
+        self.clusters = {(c.get("namespace", "default"), c["name"]): copy.deepcopy(c) for c in clusters}
+        self.pods = {(p.get("namespace", "default"), p["name"]): copy.deepcopy(p) for p in pods}
+        self.jobs = [copy.deepcopy(j) for j in jobs]
+        self.events: list[tuple[str, str, str]] = []   # (type, reason, message)
+        self._gen = 0
+
+    def list_pods(self) -> list[dict]:
+        return [self.pods[k] for k in sorted(self.pods)]  # fake client Lists come back name-ordered
+
+    def delete_pod(self, ns: str, name: str) -> bool:
+        return self.pods.pop((ns, name), None) is not None
+
+    def create_pod(self, pod: dict):
+        self.pods[(pod.get("namespace", "default"), pod["name"])] = pod
+
+    def gen_suffix(self) -> str:
+        self._gen += 1
+        return f"{self._gen:05d}"
+
+    def pods_of(self, ns: str, cluster: str, **labels) -> list[dict]:
+        out = []
+        for p in self.list_pods():
+            lb = p.get("labels") or {}
+            if p.get("namespace", "default") == ns and lb.get(snapmod.RAY_CLUSTER_LABEL) == cluster and all(lb.get(k) == v for k, v in labels.items()):
+                out.append(p)
+        return out
+
+
+class EngineBackend:
+    """The product backend: the CUDA engine through the C ABI (raises if the library / a GPU is missing)."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def run(self, snap, flags):
+        from .engine import Engine
+        eng = Engine.for_snapshot(snap, device=self.device)
+        try:
+            eng.load(snap)
+            return eng.reconcile(flags)
+        finally:
+            eng.close()
+
+
+@dataclass
+class PassResult:
+    snap: object
+    meta: snapmod.PackMeta
+    res: abi.Results
+    pods: list = field(default_factory=list)
+
+
+class RayClusterReconciler:
+    def __init__(self, client: FakeClient, backend, env: Env | None = None):
+        self.client = client
+        self.backend = backend
+        self.env = env or Env()
+
+    # ------------------------------------------------------------------ one batched pass over everything in the client
+    def _pass(self, overrides: dict | None = None) -> PassResult:
+        clusters = []
+        for key in sorted(self.client.clusters):
+            c = copy.deepcopy(self.client.clusters[key])
+            if overrides and key in overrides:
+                c.update(overrides[key])
+            clusters.append(c)
+        pods = self.client.list_pods()
+        snap, meta = snapmod.pack_objects(clusters, pods, self.client.jobs)
+        f = meta.flags
+        f.gate_status_conditions = 1 if self.env.status_conditions_gate else 0
+        f.gate_multihost_indexing = 1 if self.env.multihost_indexing_gate else 0
+        f.env_random_pod_delete = 1 if self.env.enable_random_pod_delete else 0
+        res = self.backend.run(snap, f)
+        return PassResult(snap, meta, res, pods)
+
+    @staticmethod
+    def _cluster_index(pr: PassResult, ns: str, name: str) -> int:
+        return pr.meta.cluster_keys.index((ns, name))
+
+    # ------------------------------------------------------------------ reconcilePods
+    def reconcile_pods(self, ns: str, name: str) -> str | None:
+        """Returns the error string reconcilePods would return, or None.  Side effects go to the FakeClient."""
+        pr = self._pass()
+        ci = self._cluster_index(pr, ns, name)
+        return self._apply_decisions(pr, ci)
+
+    def _apply_decisions(self, pr: PassResult, ci: int) -> str | None:
+        cl = self.client
+        res, snap, meta = pr.res, pr.snap, pr.meta
+        cr = res.clusters[ci]
+        ns, cname = meta.cluster_keys[ci]
+        cluster = cl.clusters[(ns, cname)]
+        seg = range(int(cr["pod_start"]), int(cr["pod_start"]) + int(cr["n_pods"])) if cr["path"] != abi.PATH_SKIPPED or cr["n_pods"] else range(0)
+        # pods of this cluster in list order with their actions (n_pods is 0 for CF_SKIP clusters)
+        listed = [(int(res.sorted_pod_idx[i]), int(res.sorted_action[i])) for i in seg]
+        ev = cl.events.append
+        path = int(cr["path"])
+        if path == abi.PATH_SKIPPED:
+            return "external error" if cr["err_kind"] == abi.ERR_EXTERNAL else None
+        if path == abi.PATH_SUSPENDING_DELETE_ALL:  # :633-643
+            for pi, act in listed:
+                if act == abi.ACT_DELETE_ALL_SUSPEND:
+                    cl.delete_pod(*meta.pod_keys[pi])
+            ev(("Normal", EV_DELETED_POD, f"Deleted Pods for RayCluster {ns}/{cname} due to suspension"))
+            return None
+        if path == abi.PATH_SUSPENDED_NOOP:
+            return None
+        if path == abi.PATH_RECREATE_DELETE_ALL:    # :659-669
+            for pi, act in listed:
+                if act == abi.ACT_DELETE_ALL_RECREATE:
+                    cl.delete_pod(*meta.pod_keys[pi])
+            ev(("Normal", EV_DELETED_POD, f"Deleted all Pods for RayCluster {ns}/{cname} due to spec change with Recreate upgradeStrategy"))
+            return None
+        if cr["head_update_annotations"]:           # :1155-1162
+            hp = cl.pods.get(meta.pod_keys[int(cr["head_pod_idx"])])
+            if hp is not None:
+                hp.setdefault("annotations", {})[snapmod.RECREATE_HASH_ANNOT] = bytes(res.hash[ci]).decode()
+                hp["annotations"][snapmod.KUBERAY_VERSION_ANNOT] = snapmod.KUBERAY_VERSION
+        ha = int(cr["head_action"])
+        if ha == abi.HEAD_DELETE:                   # :700-711
+            pi = next(pi for pi, act in listed if act == abi.ACT_DELETE_HEAD)
+            pod = pr.pods[pi]
+            cl.delete_pod(*meta.pod_keys[pi])
+            ev(("Normal", EV_DELETED_HEAD_POD, f"Deleted head Pod {ns}/{pod['name']}; Pod status: {pod.get('phase', '')}; Pod restart policy: {pod.get('restartPolicy', '')}; "
+                f"Ray container terminated status: {snapmod.ray_container_terminated(pod)}"))
+            return self._should_delete_reason(pod, "head")
+        if ha == abi.HEAD_SKIP_RESTART:
+            return None
+        if ha == abi.HEAD_MULTIPLE:                 # :738-747
+            names = [pr.pods[pi]["name"] for pi, _ in listed if (pr.pods[pi].get("labels") or {}).get(snapmod.RAY_NODE_TYPE_LABEL) == "head"]
+            return f"{int(cr['err_arg'])} head pods found {names}. Please delete extra head pods"
+        if ha == abi.HEAD_CREATE:                   # :735, createHeadPod :1307-1337
+            pod = self._build_pod(cluster, "head", "headgroup", f"{cname}-head-{cl.gen_suffix()}")
+            pod.setdefault("annotations", {})[snapmod.RECREATE_HASH_ANNOT] = bytes(res.hash[ci]).decode()
+            pod["annotations"][snapmod.KUBERAY_VERSION_ANNOT] = snapmod.KUBERAY_VERSION
+            cl.create_pod(pod)
+            ev(("Normal", EV_CREATED_HEAD_POD, f"Created head Pod {ns}/{pod['name']}"))
+        # worker groups in spec order (:751-933)
+        groups = (cluster.get("spec") or {}).get("workerGroupSpecs") or []
+        g0 = int(snap.c_group_off[ci])
+        for gi, grp in enumerate(groups):
+            gr = res.groups[g0 + gi]
+            fl = int(gr["flags"])
+            if not fl & abi.GR_PROCESSED:
+                break
+            gname = grp["groupName"]
+            in_group = [(pi, act) for pi, act in listed if (pr.pods[pi].get("labels") or {}).get(snapmod.RAY_NODE_GROUP_LABEL) == gname]
+            if fl & abi.GR_EXPECT_PENDING:
+                continue
+            if fl & abi.GR_SUSPENDED:               # :766-775
+                for pi, act in in_group:
+                    if act == abi.ACT_DELETE_GROUP_SUSPEND:
+                        cl.delete_pod(*meta.pod_keys[pi])
+                ev(("Normal", EV_DELETED_WORKER_POD, f"Deleted all pods for suspended worker group {gname} in RayCluster {ns}/{cname}"))
+                continue
+            if fl & abi.GR_MULTIHOST:
+                err = self._apply_multihost(pr, ci, gi, grp, in_group)
+                if err:
+                    return err
+                continue
+            unhealthy = [pi for pi, act in in_group if act == abi.ACT_DELETE_UNHEALTHY]
+            for pi in unhealthy:                    # :790-806
+                pod = pr.pods[pi]
+                cl.delete_pod(*meta.pod_keys[pi])
+                ev(("Normal", EV_DELETED_WORKER_POD, f"Deleted worker Pod {ns}/{pod['name']}; Pod status: {pod.get('phase', '')}; Pod restart policy: {pod.get('restartPolicy', '')}; "
+                    f"Ray container terminated status: {snapmod.ray_container_terminated(pod)}"))
+            if unhealthy:
+                return f"delete {len(unhealthy)} unhealthy worker Pods"  # :811
+            if fl & abi.GR_WTD_EXECUTED:            # :817-835: one Delete per name, NotFound tolerated
+                w0 = int(snap.g_wtd_off[g0 + gi])
+                names = grp.get("workersToDelete") or (grp.get("scaleStrategy") or {}).get("workersToDelete") or []
+                for k, nm in enumerate(names):
+                    pi = int(res.wtd_pod_idx[w0 + k])
+                    if pi >= 0 and cl.delete_pod(*meta.pod_keys[pi]):
+                        ev(("Normal", EV_DELETED_WORKER_POD, f"Deleted pod {ns}/{nm}"))
+                if "workersToDelete" in grp:
+                    grp["workersToDelete"] = []
+                elif "scaleStrategy" in grp:
+                    grp["scaleStrategy"]["workersToDelete"] = []
+            for k in range(int(gr["n_create"])):    # :865-890
+                idx = int(res.create_idx[int(gr["create_off"]) + k])
+                pod = self._build_pod(cluster, "worker", gname, f"{cname}-{gname}-worker-{cl.gen_suffix()}")
+                if self.env.multihost_indexing_gate:
+                    pod["labels"][snapmod.REPLICA_INDEX_LABEL] = str(idx)
+                cl.create_pod(pod)
+                ev(("Normal", EV_CREATED_WORKER_POD, f"Created worker Pod {ns}/{pod['name']}"))
+            for pi, act in in_group:                # :916-928
+                if act == abi.ACT_DELETE_RANDOM:
+                    cl.delete_pod(*meta.pod_keys[pi])
+                    ev(("Normal", EV_DELETED_WORKER_POD, f"Deleted Pod {ns}/{pr.pods[pi]['name']}"))
+            if fl & abi.GR_ABORTED:
+                return f"negative desired replicas ({int(gr['expected'])})"
+        return None
+
+    def _apply_multihost(self, pr, ci, gi, grp, in_group) -> str | None:
+        """reconcileMultiHostWorkerGroup side effects (:963-1125)."""
+        cl, res, snap, meta = self.client, pr.res, pr.snap, pr.meta
+        ns, cname = meta.cluster_keys[ci]
+        cluster = cl.clusters[(ns, cname)]
+        gr = res.groups[int(snap.c_group_off[ci]) + gi]
+        cr = res.clusters[ci]
+        gname = grp["groupName"]
+        reasons = {abi.ACT_DELETE_MH_INCOMPLETE: "cleanup of incomplete multi-host group", abi.ACT_DELETE_MH_WTD: "autoscaler scale-down request",
+                   abi.ACT_DELETE_MH_SCALE_DOWN: "scaling down"}
+        for pi, act in in_group:
+            if act in (abi.ACT_DELETE_MH_INCOMPLETE, abi.ACT_DELETE_MH_UNHEALTHY, abi.ACT_DELETE_MH_WTD, abi.ACT_DELETE_MH_SCALE_DOWN):
+                pod = pr.pods[pi]
+                if cl.delete_pod(*meta.pod_keys[pi]):
+                    why = reasons.get(act) or self._should_delete_reason(pod, "worker")
+                    cl.events.append(("Normal", EV_DELETED_WORKER_POD, f"Deleted worker Pod {ns}/{pod['name']} for group {gname}: {why}"))
+        ek = int(cr["err_kind"])
+        if int(gr["flags"]) & abi.GR_ABORTED:
+            if ek == abi.ERR_MH_INCOMPLETE:
+                return "cleaned up incomplete replica group, requeueing"
+            if ek == abi.ERR_MH_WTD:
+                return f"deleted {int(cr['err_arg'])} worker Pods based on ScaleStrategy, requeueing"
+            if ek == abi.ERR_MH_NOT_MULTIPLE:
+                return f"desired worker pods ({int(gr['expected'])}) is not a multiple of NumOfHosts ({grp.get('numOfHosts', 1)}) for group {gname}"
+        if int(gr["flags"]) & abi.GR_WTD_EXECUTED:
+            if "workersToDelete" in grp:
+                grp["workersToDelete"] = []
+        hosts = int(grp.get("numOfHosts", 1))
+        for k in range(int(gr["n_create"])):        # one entry per replica group (:1082-1094)
+            idx = int(res.create_idx[int(gr["create_off"]) + k])
+            rname = f"{gname}-{cl.gen_suffix()}"
+            for j in range(hosts):
+                pod = self._build_pod(cluster, "worker", gname, f"{cname}-{gname}-worker-{cl.gen_suffix()}")
+                pod["labels"][snapmod.REPLICA_INDEX_LABEL] = str(idx)
+                pod["labels"][snapmod.REPLICA_NAME_LABEL] = rname
+                pod["labels"]["ray.io/replica-host-index"] = str(j)
+                cl.create_pod(pod)
+                cl.events.append(("Normal", EV_CREATED_WORKER_POD, f"Created worker Pod {ns}/{pod['name']}"))
+        return None
+
+    @staticmethod
+    def _build_pod(cluster: dict, node_type: str, group: str, name: str) -> dict:
+        """labelPod (common/pod.go:775-799) — only the labels the selectors read matter to the path."""
+        cname = cluster["name"]
+        return {"namespace": cluster.get("namespace", "default"), "name": name, "phase": "", "restartPolicy": "Always",
+                "labels": {"ray.io/is-ray-node": "yes", snapmod.RAY_CLUSTER_LABEL: cname, snapmod.RAY_NODE_TYPE_LABEL: node_type,
+                           snapmod.RAY_NODE_GROUP_LABEL: group, "ray.io/identifier": f"{cname}-{node_type}"},
+                "annotations": {}}
+
+    @staticmethod
+    def _should_delete_reason(pod: dict, node_type: str) -> str:
+        """The reason string of shouldDeletePod (:1181-1231) — it is what reconcilePods returns as the error (:711)."""
+        ph = pod.get("phase", "")
+        if ph in ("Failed", "Succeeded"):
+            return (f"The {node_type} Pod {pod['name']} status is {ph} which is a terminal state. "
+                    "KubeRay will delete the Pod and create new Pods in the next reconciliation if necessary.")
+        return (f"The Pod status of the {node_type} Pod {pod['name']} is {ph}, and the Ray container terminated status is "
+                f"{snapmod.ray_container_terminated(pod)}. The container is unable to restart due to its restart policy {pod.get('restartPolicy', '')}, so KubeRay will delete it.")
+
+    # ------------------------------------------------------------------ calculateStatus
+    def calculate_status(self, ns: str, name: str, reconcile_err=None) -> tuple[dict | None, str | None]:
+        """-> (new status dict, calculate error).  reconcile_err: None, a plain string, or ("FailedCreateHeadPod", "message")."""
+        if reconcile_err is None:
+            ext = {"kind": abi.EXT_ERR_STATUS_ONLY_NIL}
+        elif isinstance(reconcile_err, tuple):
+            ext = {"kind": snapmod._REPLICA_FAILURE_KIND[reconcile_err[0]], "message": reconcile_err[1]}
+        else:
+            ext = {"kind": abi.EXT_ERR_PLAIN, "message": str(reconcile_err)}
+        pr = self._pass({(ns, name): {"extErr": ext}})
+        ci = self._cluster_index(pr, ns, name)
+        return self.status_from_record(pr, ci)
+
+    def status_from_record(self, pr: PassResult, ci: int) -> tuple[dict | None, str | None]:
+        res, meta = pr.res, pr.meta
+        it = meta.interner
+        cr = res.clusters[ci]
+        ns, cname = meta.cluster_keys[ci]
+        old = copy.deepcopy(self.client.clusters[(ns, cname)].get("status") or {})
+        serr = int(cr["status_err"])
+        if serr:
+            return None, {abi.SERR_MULTIPLE_HEADS: "found multiple heads", abi.SERR_NO_HEAD_SERVICE: "unable to find head service",
+                          abi.SERR_MULTIPLE_HEAD_SERVICES: "found multiple head services", abi.SERR_EMPTY_SERVICE_IP: "head service IP is empty"}[serr]
+        new = old
+        st = int(cr["new_state"])
+        if st != abi.STATE_OTHER:
+            new["state"] = snapmod.STATE_NAMES[st]
+        if int(cr["status_flags"]) & abi.SF_READY_BRANCH:
+            new["reason"] = ""  # :1601-1602
+        keys = ["readyWorkerReplicas", "availableWorkerReplicas", "desiredWorkerReplicas", "minWorkerReplicas", "maxWorkerReplicas"]
+        for k, v in zip(keys, cr["counts"]):
+            new[k] = int(v)
+        conds_old = {c["type"]: c for c in old.get("conditions") or []}
+        conds = []
+        order = [c["type"] for c in old.get("conditions") or []]
+        for slot in range(abi.NUM_CONDS):
+            t = snapmod.COND_NAMES[slot]
+            if t not in order and cr["cond_status"][slot] != abi.COND_ABSENT:
+                order.append(t)
+        for t in order:
+            slot = snapmod._COND_SLOT.get(t)
+            if slot is None:
+                conds.append(conds_old[t]); continue
+            stc = int(cr["cond_status"][slot])
+            if stc == abi.COND_ABSENT:
+                continue
+            var = int(cr["cond_variant"][slot])
+            cond = dict(conds_old.get(t) or {"type": t})
+            cond["status"] = {abi.COND_TRUE: "True", abi.COND_FALSE: "False", abi.COND_UNKNOWN: "Unknown"}[stc]
+            if slot == abi.COND_PROVISIONED and var in snapmod.PROV_VARIANT_STRINGS:
+                cond["reason"], cond["message"] = snapmod.PROV_VARIANT_STRINGS[var]
+            elif slot in (abi.COND_SUSPENDING, abi.COND_SUSPENDED) and var == abi.CV_CANONICAL:
+                cond["reason"], cond["message"] = t, ""
+            elif slot == abi.COND_HEAD_POD_READY and var in (abi.CV_HEAD_FROM_POD, abi.CV_HEAD_NOT_FOUND):
+                cond["reason"] = it.str(int(cr["head_ready_reason_id"])) or ""
+                cond["message"] = it.str(int(cr["head_ready_msg_id"])) or ""
+            elif slot == abi.COND_REPLICA_FAILURE and var in snapmod.REPLICA_FAILURE_NAMES:
+                cond["reason"] = snapmod.REPLICA_FAILURE_NAMES[var]
+                mid = int(pr.snap.c_ext_err_msg_id[ci])
+                if int(pr.snap.c_ext_err_kind[ci]) == var:
+                    cond["message"] = it.str(mid) or ""
+            conds.append(cond)
+        new["conditions"] = conds
+        hid = [int(x) for x in cr["head_ids"]]
+        new["head"] = {"podIP": it.str(hid[0]) or "", "serviceIP": it.str(hid[1]) or "", "podName": it.str(hid[2]) or "", "serviceName": it.str(hid[3]) or ""}
+        cluster = self.client.clusters[(ns, cname)]
+        svc = cluster.get("headService", {"count": 1, "clusterIP": "10.0.0.1", "name": f"{cname}-head-svc"})
+        new["endpoints"] = snapmod.compute_endpoints(old.get("endpoints"), svc)
+        new["_needs_write"] = bool(cr["needs_status_write"])
+        new["_state_changed"] = bool(cr["state_changed"])
+        return new, None
+
+    def update_status(self, ns: str, name: str, new_status: dict, now: str = "now") -> bool:
+        """updateRayClusterStatus (:1951-1966): write iff InconsistentRayClusterStatus; returns `inconsistent`."""
+        inconsistent = bool(new_status.pop("_needs_write", False))
+        changed = bool(new_status.pop("_state_changed", False))
+        new_status["lastUpdateTime"] = now
+        if changed:
+            new_status.setdefault("stateTransitionTimes", {})[new_status.get("state", "")] = now
+        if inconsistent:
+            self.client.clusters[(ns, name)]["status"] = new_status
+        return inconsistent
+
+    # ------------------------------------------------------------------ the full Reconcile body for one key (:296-355)
+    def reconcile(self, ns: str, name: str, now: str = "now") -> tuple[float, str | None]:
+        """-> (requeue seconds, error).  One pass feeds both the decisions and the status, as the engine produces them."""
+        pr = self._pass()
+        ci = self._cluster_index(pr, ns, name)
+        err = self._apply_decisions(pr, ci)
+        new, cerr = self.status_from_record(pr, ci)
+        inconsistent = False
+        if cerr is None:
+            inconsistent = self.update_status(ns, name, new, now)
+        final = err or cerr
+        if final or inconsistent:
+            return 2.0, final      # DefaultRequeueDuration (:51,338-340)
+        return 300.0, None         # RAYCLUSTER_DEFAULT_REQUEUE_SECONDS (utils/constant.go:149-150)

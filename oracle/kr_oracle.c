@@ -640,6 +640,7 @@ static void calculate_status(const octx *x, oscratch *t, uint32_t c, kr_cluster_
 
   cr->new_state = new_state;
   cr->state_changed = new_state != old_state; /* :1711-1716 */
+  cr->status_flags = (reason_cleared ? KR_SF_READY_BRANCH : 0u) | (all_running ? KR_SF_ALL_PODS_RUNNING : 0u);
   cr->counts[0] = ready; cr->counts[1] = available; cr->counts[2] = desired; cr->counts[3] = minr; cr->counts[4] = maxc;
   for (int k = 0; k < KR_NUM_CONDS; k++) { cr->cond_status[k] = cst[k]; cr->cond_variant[k] = cvr[k]; }
   cr->head_ready_reason_id = hpr_reason; cr->head_ready_msg_id = hpr_msg;
@@ -691,7 +692,8 @@ static void reconcile_cluster(octx *x, oscratch *t, uint32_t c, ivec *creates) {
   uint32_t cf = s->c_flags[c];
   if (cf & KR_CF_SKIP) { cr->path = KR_PATH_SKIPPED; return; }
   if (s->c_ext_err_kind[c] != KR_EXT_ERR_NONE) { /* an earlier sub-reconciler failed: reconcilePods not reached (:308-314) */
-    cr->path = KR_PATH_SKIPPED; cr->err_kind = KR_ERR_EXTERNAL;
+    cr->path = KR_PATH_SKIPPED;
+    cr->err_kind = s->c_ext_err_kind[c] == KR_EXT_ERR_STATUS_ONLY_NIL ? KR_ERR_NONE : KR_ERR_EXTERNAL;
   } else {
     reconcile_pods(x, t, c, h, cr, creates);
   }

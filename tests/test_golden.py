@@ -1,0 +1,294 @@
+"""Replay of the reference's own known-answer tests (tests/golden/*.json, transcribed from the Go test files cited inside)
+through the host-side reconciler mirror.  Every scenario runs against the CPU oracle (pins the oracle; `-m "not gpu"`) and
+against the CUDA engine through the C ABI (`-m gpu`)."""
+import copy
+import json
+import os
+
+import pytest
+
+from kuberay_b200 import abi, snapshot as snapmod
+from kuberay_b200.reconciler import Env, EngineBackend, FakeClient, RayClusterReconciler
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        return json.load(f)
+
+
+class OracleBackend:
+    def run(self, snap, flags):
+        from oracle import oracle
+        return oracle.run(snap, flags)
+
+
+@pytest.fixture(params=["oracle", pytest.param("engine", marks=pytest.mark.gpu)])
+def backend(request):
+    return OracleBackend() if request.param == "oracle" else EngineBackend(0)
+
+
+NS, CN = "default", "raycluster-sample"
+SC = load("reconcile_scenarios")
+
+
+def make_client(sc, cluster_patch=None):
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    pods = copy.deepcopy(SC["base"]["pods"])
+    for k, v in (sc.get("patch_spec") or {}).items():
+        cluster["spec"][k] = v
+    for k, v in (sc.get("patch_group") or {}).items():
+        cluster["spec"]["workerGroupSpecs"][0][k] = v
+    if cluster_patch:
+        cluster.update(cluster_patch)
+    for p in pods:
+        p.update((sc.get("patch_pods") or {}).get(p["name"], {}))
+    client = FakeClient([cluster], pods)
+    for name in sc.get("pre_delete") or []:
+        assert client.delete_pod(NS, name)
+    return client
+
+
+def workers(client):
+    return [p for p in client.pods_of(NS, CN, **{"ray.io/group": "small-group"})]
+
+
+def heads(client):
+    return client.pods_of(NS, CN, **{"ray.io/node-type": "head"})
+
+
+@pytest.mark.parametrize("sc", SC["scenarios"], ids=[s["name"] for s in SC["scenarios"]])
+def test_reconcile_pods_scenarios(sc, backend):
+    """raycluster_controller_unit_test.go: the scenario tests on fixture F0 (citation in each fixture entry)."""
+    client = make_client(sc)
+    r = RayClusterReconciler(client, backend, Env(**sc.get("env", {})))
+    before = {p["name"] for p in workers(client)}
+    err = r.reconcile_pods(NS, CN)
+    assert (err is not None) == sc["want_err"], err
+    after = {p["name"] for p in workers(client)}
+    assert len(after) == sc["want_workers"], sorted(after)
+    for gone in sc.get("want_gone", []):
+        assert gone not in after
+    if "want_heads" in sc:
+        assert len(heads(client)) == sc["want_heads"]
+    if "want_random_deletes" in sc:
+        named = set(sc["patch_group"]["workersToDelete"])
+        assert len((before - after) - named) == sc["want_random_deletes"]
+    if "want_creates" in sc:
+        assert len(after - before) == sc["want_creates"] and len(before - after) == sc["want_deletes"]
+    # pods that remain are all non-failed
+    assert all(p.get("phase") not in ("Failed", "Succeeded") for p in workers(client))
+
+
+def test_terminated_workers_multi_pass(backend):
+    """Test_TerminatedWorkers_NoAutoscaler raycluster_controller_unit_test.go:2093-2221"""
+    tw = SC["terminated_workers"]
+    client = make_client(tw)
+    r = RayClusterReconciler(client, backend)
+    for step in tw["passes"]:
+        for p in workers(client):  # envtest-style: newly created pods are patched to Running by the test (:2125-2129)
+            if p.get("phase", "") == "":
+                p["phase"] = "Running"
+        if "set_phase" in step:
+            workers(client)[0]["phase"] = step["set_phase"]["first_worker"]
+        err = r.reconcile_pods(NS, CN)
+        assert (err is not None) == step["want_err"], err
+        if err:
+            assert err.startswith("delete 1 unhealthy worker Pods")  # :811
+        assert len(workers(client)) == step["want_workers"]
+
+
+def test_terminated_head_restart_policy(backend):
+    """Test_TerminatedHead_RestartPolicy :2223-2309 and Test_RunningPods_RayContainerTerminated :2311-2378"""
+    th = SC["terminated_head"]
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    cluster["spec"]["workerGroupSpecs"] = []
+    client = FakeClient([cluster], [copy.deepcopy(SC["base"]["pods"][0])])
+    r = RayClusterReconciler(client, backend)
+    for step in th["steps"]:
+        if "head" in step:
+            hp = heads(client)[0]
+            hp.update(step["head"])
+            hp.pop("containerStatuses", None) if "rayContainerTerminated" in step["head"] else None
+        err = r.reconcile_pods(NS, CN)
+        assert (err is not None) == step["want_err"], err
+        assert len(client.pods) == step["want_pods"]
+        for p in client.pods.values():
+            if p.get("phase", "") == "":
+                p["phase"] = "Running"
+
+
+@pytest.mark.parametrize("case", load("recreate_upgrade")["cases"], ids=lambda c: c["name"])
+def test_should_recreate_pods_for_upgrade(case, backend):
+    """TestShouldRecreatePodsForUpgrade raycluster_controller_unit_test.go:3680-3814"""
+    from kuberay_b200 import specjson
+    import base64
+    import hashlib
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    cluster["spec"]["upgradeStrategy"] = case["upgradeStrategy"]
+    cluster["spec"]["workerGroupSpecs"][0]["workersToDelete"] = []
+    current = base64.b32hexencode(hashlib.sha1(specjson.muted_spec_json(cluster["spec"])).digest()).decode()
+    pods = []
+    if case["head"] is not None:
+        hp = copy.deepcopy(SC["base"]["pods"][0])
+        hp["annotations"] = {snapmod.RECREATE_HASH_ANNOT: current if case["head"]["hash"] == "<current>" else case["head"]["hash"],
+                             snapmod.KUBERAY_VERSION_ANNOT: snapmod.KUBERAY_VERSION if case["head"]["version"] == "<current>" else case["head"]["version"]}
+        pods.append(hp)
+    client = FakeClient([cluster], pods)
+    r = RayClusterReconciler(client, backend)
+    pr = r._pass()
+    got = int(pr.res.clusters[0]["path"]) == abi.PATH_RECREATE_DELETE_ALL
+    assert got == case["want"]
+    assert bytes(pr.res.hash[0]).decode() == current  # the engine's hash is the annotation the controller would write
+    if case["head"] and case["head"]["version"] not in ("<current>", ""):
+        assert pr.res.clusters[0]["head_update_annotations"] == 1  # :1155-1162
+
+
+# ------------------------------------------------------------------------------------------------ calculateStatus
+
+def status_fixture(n_workers=3, ready="True", svc_ip="aaa.bbb.ccc.ddd"):
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    cluster["spec"]["workerGroupSpecs"][0]["workersToDelete"] = []
+    cluster["headService"] = {"count": 1, "clusterIP": svc_ip, "name": "raycluster-sample-head-svc"}
+    cond = [{"type": "Ready", "status": ready}]
+    pods = [{"namespace": NS, "name": "headNode", "labels": {"ray.io/cluster": CN, "ray.io/node-type": "head"}, "phase": "Running", "podIP": "1.2.3.4", "conditions": copy.deepcopy(cond)}]
+    for i in range(n_workers):
+        pods.append({"namespace": NS, "name": f"workerNode-{i}", "labels": {"ray.io/cluster": CN, "ray.io/node-type": "worker"}, "phase": "Running", "podIP": "1.2.3.4", "conditions": copy.deepcopy(cond)})
+    return cluster, pods
+
+
+def cond_of(status, t):
+    return next((c for c in status.get("conditions") or [] if c["type"] == t), None)
+
+
+def test_calculate_status(backend):
+    """TestCalculateStatus raycluster_controller_unit_test.go:1611-1723"""
+    cluster, pods = status_fixture()
+    client = FakeClient([cluster], pods)
+    r = RayClusterReconciler(client, backend, Env(status_conditions_gate=False))
+    new, err = r.calculate_status(NS, CN, None)
+    assert err is None
+    assert new["head"]["podIP"] == "1.2.3.4" and new["head"]["serviceIP"] == "aaa.bbb.ccc.ddd" and new["head"]["serviceName"] == "raycluster-sample-head-svc"
+    assert new["state"] == "ready" and new["_state_changed"]          # StateTransitionTimes[ready] = LastUpdateTime (:1711-1716)
+    new, err = r.calculate_status(NS, CN, ("FailedCreateHeadPod", "invalid"))
+    assert err is None and not new.get("conditions")                   # gate off => no conditions
+    r.env = Env(status_conditions_gate=True)
+    new, _ = r.calculate_status(NS, CN, None)
+    assert cond_of(new, "HeadPodReady")["status"] == "True"
+    client.pods[(NS, "headNode")]["conditions"] = [{"type": "Ready", "status": "False"}]
+    for k in [k for k in client.pods if k[1].startswith("workerNode")]:
+        client.delete_pod(*k)
+    new, _ = r.calculate_status(NS, CN, None)
+    assert cond_of(new, "HeadPodReady")["status"] == "False"
+    client.pods[(NS, "headNode")]["phase"] = "Failed"
+    new, _ = r.calculate_status(NS, CN, None)
+    assert cond_of(new, "HeadPodReady")["status"] == "False"
+    new, err = r.calculate_status(NS, CN, ("FailedCreateHeadPod", "invalid"))
+    assert err is None
+    rf = cond_of(new, "ReplicaFailure")
+    assert rf["status"] == "True" and rf["reason"] == "FailedCreateHeadPod" and rf["message"] == "invalid"
+
+
+def test_calculate_status_without_desired_replicas(backend):
+    """TestCalculateStatusWithoutDesiredReplicas :1727-1780 — only the head exists, desired 3 => State stays empty"""
+    cluster, pods = status_fixture(n_workers=0)
+    client = FakeClient([cluster], pods)
+    new, err = RayClusterReconciler(client, backend).calculate_status(NS, CN, None)
+    assert err is None and new.get("state", "") == "" and new.get("reason", "") == "" and not new["_state_changed"]
+
+
+def test_calculate_status_with_suspended_worker_groups(backend):
+    """TestCalculateStatusWithSuspendedWorkerGroups :1784-1847"""
+    cluster, pods = status_fixture(n_workers=0)
+    cluster["spec"]["workerGroupSpecs"][0].update({"suspend": True, "minReplicas": 100, "maxReplicas": 100, "replicas": 100})
+    client = FakeClient([cluster], pods)
+    new, err = RayClusterReconciler(client, backend).calculate_status(NS, CN, None)
+    assert err is None
+    assert (new["desiredWorkerReplicas"], new["minWorkerReplicas"], new["maxWorkerReplicas"], new["state"]) == (0, 0, 0, "ready")
+
+
+def test_calculate_status_reconcile_error_back_and_forth(backend):
+    """TestCalculateStatusWithReconcileErrorBackAndForth :1851-1944: err -> nil -> err; State "" -> ready -> stays ready"""
+    cluster, pods = status_fixture()
+    client = FakeClient([cluster], pods)
+    r = RayClusterReconciler(client, backend)
+    new, _ = r.calculate_status(NS, CN, "invalid")
+    assert new.get("state", "") == ""
+    r.update_status(NS, CN, new)
+    new, _ = r.calculate_status(NS, CN, None)
+    assert new["state"] == "ready" and new["_state_changed"]
+    r.update_status(NS, CN, new, now="t1")
+    new, _ = r.calculate_status(NS, CN, "invalid2")
+    assert new["state"] == "ready" and not new["_state_changed"]       # transition time unchanged on the 3rd call
+    r.update_status(NS, CN, new, now="t2")
+    assert client.clusters[(NS, CN)]["status"]["stateTransitionTimes"]["ready"] == "t1"
+
+
+def test_rayclusterprovisioned_condition(backend):
+    """TestRayClusterProvisionedCondition :1946-2042"""
+    steps = load("status_scenarios")["provisioned"]["steps"]
+    cluster, pods = status_fixture(n_workers=1, ready="False")
+    cluster["spec"]["workerGroupSpecs"][0]["replicas"] = 1
+    client = FakeClient([cluster], pods)
+    r = RayClusterReconciler(client, backend)
+    for st in steps:
+        client.pods[(NS, "headNode")]["conditions"] = [{"type": "Ready", "status": st["head_ready"]}]
+        client.pods[(NS, "workerNode-0")]["conditions"] = [{"type": "Ready", "status": st["worker_ready"]}]
+        new, err = r.calculate_status(NS, CN, None)
+        assert err is None
+        c = cond_of(new, "RayClusterProvisioned")
+        assert [c["status"], c["reason"]] == st["want"]
+        r.update_status(NS, CN, new)
+
+
+def test_state_transition_times_no_state_change(backend):
+    """TestStateTransitionTimes_NoStateChange :2044-2091"""
+    cluster, pods = status_fixture()
+    cluster["status"] = {"state": "ready", "stateTransitionTimes": {"ready": "t-earlier"}}
+    client = FakeClient([cluster], pods)
+    r = RayClusterReconciler(client, backend)
+    new, _ = r.calculate_status(NS, CN, None)
+    assert not new["_state_changed"]
+    r.update_status(NS, CN, new, now="t-now")
+    assert client.clusters[(NS, CN)]["status"]["stateTransitionTimes"]["ready"] == "t-earlier"
+
+
+@pytest.mark.parametrize("case", load("inconsistent_status")["cases"], ids=lambda c: c["name"])
+def test_inconsistent_ray_cluster_status(case, backend):
+    """TestInconsistentRayClusterStatus utils/consistency_test.go:16-146 — replayed through the RayJob roll-up join
+    (rayjob_controller.go:885): job.status.rayClusterStatus (old) vs the RayCluster's stored status (new)."""
+    gold = load("inconsistent_status")
+    old = gold["old"]
+    new = copy.deepcopy(old)
+    new.update(case.get("set", {}))
+    new.setdefault("endpoints", {}).update(case.get("set_endpoint", {}))
+    new.setdefault("head", {}).update(case.get("set_head", {}))
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    cluster["status"] = new
+    job = {"namespace": NS, "name": "rayjob-sample", "status": {"rayClusterName": CN, "rayClusterStatus": old}}
+    client = FakeClient([cluster], [], [job])
+    pr = RayClusterReconciler(client, backend)._pass()
+    jr = pr.res.jobs[0]
+    assert jr["cluster_idx"] == 0
+    assert bool(jr["status_changed"]) == case["want"]
+    assert bool(jr["not_ready"]) == (new["state"] != "ready")
+
+
+def test_full_reconcile_loop_converges(backend):
+    """Reconcile() end to end on F0 until quiescent: decisions, status write, requeue policy (raycluster_controller.go:296-355)."""
+    sc = {"patch_group": {"workersToDelete": []}, "patch_spec": {"enableInTreeAutoscaling": False}}
+    client = make_client(sc)
+    for p in client.pods.values():
+        p["conditions"] = [{"type": "Ready", "status": "True"}]
+        if p["name"] != "headNode":
+            p["labels"]["ray.io/node-type"] = "worker"
+    r = RayClusterReconciler(client, backend)
+    requeue, err = r.reconcile(NS, CN)
+    assert err is None and requeue == 2.0             # two prefix deletes + first status write => short requeue
+    assert len(workers(client)) == 3
+    requeue, err = r.reconcile(NS, CN)
+    st = client.clusters[(NS, CN)]["status"]
+    assert err is None and st["state"] == "ready" and st["readyWorkerReplicas"] == 3 and st["desiredWorkerReplicas"] == 3
+    requeue, err = r.reconcile(NS, CN)
+    assert (requeue, err) == (300.0, None)            # nothing left to do: periodic resync only

@@ -1,0 +1,196 @@
+"""CPU tests: the oracle's scalar pieces against the reference's known-answer tables (tests/golden, transcribed from the Go
+tests cited in each fixture), SHA-1 / base32hex standards vectors, and the host-only evaluations of the packer."""
+import base64
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from kuberay_b200 import abi, snapshot as snapmod, specjson
+from kuberay_b200.reconciler import FakeClient, RayClusterReconciler
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        return json.load(f)
+
+
+class OracleBackend:
+    def run(self, snap, flags):
+        from oracle import oracle
+        return oracle.run(snap, flags)
+
+
+ARITH = load("replica_arithmetic")
+
+
+@pytest.mark.parametrize("c", ARITH["desired_replicas"]["cases"])
+def test_get_worker_group_desired_replicas(c, oracle_mod):
+    """utils/util_test.go:555-601"""
+    assert oracle_mod.desired_replicas(c["replicas"], c["min"], c["max"], c["hosts"], c["suspend"]) == c["want"]
+
+
+def test_desired_replicas_int32_wrap(oracle_mod):
+    """the multiply is an int32 multiply in Go (utils/util.go:403): 2^30 * 4 wraps to 0, (2^30+1)*4 wraps to 4"""
+    assert oracle_mod.desired_replicas(2 ** 30, 0, None, 4) == 0
+    assert oracle_mod.desired_replicas(2 ** 30 + 1, 0, None, 4) == 4
+    assert oracle_mod.desired_replicas(2 ** 31 - 1, 0, None, 2) == -2
+
+
+def _cluster_with_groups(groups):
+    wg = []
+    for i, g in enumerate(groups):
+        wg.append({"groupName": f"g{i}", "replicas": g.get("replicas", g.get("min")), "minReplicas": g.get("min"), "maxReplicas": g.get("max"),
+                   "numOfHosts": g.get("hosts", 1), "suspend": g.get("suspend")})
+        if "replicas" in g and g["replicas"] is None:
+            wg[-1]["replicas"] = None
+    return {"namespace": "default", "name": "c", "spec": {"headGroupSpec": {"rayStartParams": {}}, "workerGroupSpecs": wg}, "specJson": "{}"}
+
+
+def _status_counts(groups, pods=()):
+    client = FakeClient([_cluster_with_groups(groups)], pods)
+    pr = RayClusterReconciler(client, OracleBackend())._pass()
+    return pr.res.clusters[0]
+
+
+@pytest.mark.parametrize("c", ARITH["min_max"]["cases"], ids=lambda c: c["name"])
+def test_calculate_min_and_max_replicas(c):
+    """utils/util_test.go:603-710"""
+    cr = _status_counts(c["groups"])
+    assert (int(cr["counts"][3]), int(cr["counts"][4])) == (c["want_min"], c["want_max"])
+
+
+@pytest.mark.parametrize("c", ARITH["desired_cluster"]["cases"], ids=lambda c: c["name"])
+def test_calculate_desired_replicas(c):
+    """utils/util_test.go:712-800"""
+    assert int(_status_counts(c["groups"])["counts"][2]) == c["want"]
+
+
+@pytest.mark.parametrize("c", ARITH["max_overflow"]["cases"], ids=lambda c: c["name"])
+def test_calculate_max_replicas_overflow(c):
+    """utils/util_test.go:802-894"""
+    assert int(_status_counts(c["groups"])["counts"][4]) == c["want_max"]
+
+
+def _pod(name, node_type=None, phase="Running", ready=None, **kw):
+    labels = {"ray.io/cluster": "c"}
+    if node_type:
+        labels["ray.io/node-type"] = node_type
+    p = {"namespace": "default", "name": name, "labels": labels, "phase": phase}
+    if ready is not None:
+        p["conditions"] = [{"type": "Ready", "status": ready}]
+    p.update(kw)
+    return p
+
+
+def test_calculate_available_and_ready_replicas():
+    """utils/util_test.go:408-475"""
+    g = ARITH["available_ready"]
+    pods = [_pod(p["name"], p.get("nodeType"), p["phase"], p.get("ready")) for p in g["pods"]]
+    cr = _status_counts([{"min": 0, "max": 5, "replicas": 3}], pods)
+    assert int(cr["counts"][1]) == g["want_available"] and int(cr["counts"][0]) == g["want_ready"]
+
+
+@pytest.mark.parametrize("c", ARITH["check_all_pods_running"]["cases"], ids=lambda c: c["name"])
+def test_check_all_pods_running(c):
+    """utils/util_test.go:58-130"""
+    pods = [_pod(f"p{i}", "worker", p["phase"], p.get("ready")) for i, p in enumerate(c["pods"])]
+    cr = _status_counts([{"min": 0, "max": 5, "replicas": 0}], pods)
+    assert bool(int(cr["status_flags"]) & abi.SF_ALL_PODS_RUNNING) == c["want"]
+
+
+@pytest.mark.parametrize("c", load("should_delete_pod")["cases"])
+def test_should_delete_pod(c, oracle_mod):
+    """raycluster_controller_unit_test.go:2380-2503"""
+    pod = {"name": "p", "phase": c["phase"], "restartPolicy": c["restartPolicy"], "rayContainerTerminated": c["terminated"]}
+    pk, _ = snapmod.pack_pod_word(pod)
+    assert bool(oracle_mod.lib().kr_oracle_should_delete(pk)) == c["want"]
+
+
+HPR = load("head_pod_ready")
+
+
+@pytest.mark.parametrize("c", HPR["status_cases"])
+def test_find_head_pod_ready_condition_status(c):
+    """utils/util_test.go:934-970"""
+    pod = {"phase": c["phase"], "conditions": [{"type": "Ready", "status": c["ready"], "reason": "ContainersNotReady"}]}
+    assert snapmod.head_pod_ready_condition(pod)[0] == c["want_status"]
+
+
+@pytest.mark.parametrize("c", HPR["message_cases"], ids=lambda c: c["name"])
+def test_find_head_pod_ready_message(c):
+    """utils/util_test.go:972-1038"""
+    pod = {"phase": "Pending", "conditions": [{"type": "Ready", "status": "False", "reason": "ContainersNotReady", "message": c["message"]}],
+           "containerStatuses": c["containerStatuses"]}
+    _, reason, message = snapmod.head_pod_ready_condition(pod)
+    assert (reason, message) == (c["want_reason"], c["want_message"])
+
+
+def test_sha1_and_base32hex_vectors(oracle_mod):
+    v = load("sha1_vectors")
+    for c in v["sha1"]:
+        assert oracle_mod.sha1(c["msg"].encode()).hex() == c["hex"]
+    for msg, enc in v["base32hex"]:
+        assert base64.b32hexencode(msg.encode()).decode() == enc  # pins the python encoder the next loop leans on
+    rng = np.random.default_rng(7)
+    for n in [0, 1, 54, 55, 56, 57, 63, 64, 65, 119, 120, 121, 127, 128, 1000, 6144, 70000]:
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert oracle_mod.sha1(m) == hashlib.sha1(m).digest()
+        assert oracle_mod.hash32(m) == base64.b32hexencode(hashlib.sha1(m).digest()).decode()  # 20 bytes -> 32 chars, no padding
+
+
+def test_hash_relations_of_the_muted_spec():
+    """TestGenerateHashWithoutReplicasAndWorkersToDelete rayservice_controller_unit_test.go:39-97 (relational: no literal digest
+    exists anywhere in the reference)."""
+    sc = load("reconcile_scenarios")["base"]["cluster"]["spec"]
+
+    def h(spec):
+        return base64.b32hexencode(hashlib.sha1(specjson.muted_spec_json(spec)).digest()).decode()
+
+    import copy
+    base = h(sc)
+    s2 = copy.deepcopy(sc); s2["workerGroupSpecs"][0]["replicas"] += 1
+    assert h(s2) == base
+    s3 = copy.deepcopy(sc); s3["rayVersion"] = "2.100.0"
+    assert h(s3) != base
+    s4 = copy.deepcopy(sc); s4["headGroupSpec"]["template"]["spec"]["tolerations"] = [{"key": "k", "operator": "Exists"}]
+    s4["workerGroupSpecs"][0]["template"]["spec"]["tolerations"] = [{"key": "k", "operator": "Exists"}]
+    assert h(s4) == base
+    s5 = copy.deepcopy(sc); s5["headGroupSpec"]["template"]["spec"]["schedulingGates"] = [{"name": "kueue.x-k8s.io/admission"}]
+    assert h(s5) == base
+    s6 = copy.deepcopy(sc); s6["workerGroupSpecs"][0]["workersToDelete"] = ["a", "b"]; s6["workerGroupSpecs"][0]["minReplicas"] = 7
+    s6["upgradeStrategy"] = {"type": "Recreate"}
+    assert h(s6) == base
+    assert len(base) == 32 and set(base) <= set("0123456789ABCDEFGHIJKLMNOPQRSTUV")
+
+
+def test_muted_spec_json_follows_go_encoding_rules():
+    """omitempty, null for nil'ed non-omitempty pointers, sorted map keys, HTML escaping."""
+    spec = {"rayVersion": "2.9<&>", "headGroupSpec": {"rayStartParams": {"b": "2", "a": "1"}, "template": {"spec": {"containers": [{"name": "h"}]}}},
+            "workerGroupSpecs": [{"groupName": "g", "replicas": 3, "minReplicas": 0, "maxReplicas": 5, "rayStartParams": {}, "numOfHosts": 0,
+                                  "template": {"spec": {"containers": [{"name": "w"}]}}}]}
+    got = specjson.muted_spec_json(spec).decode()
+    assert got == ('{"headGroupSpec":{"template":{"spec":{"containers":[{"name":"h"}]}},"rayStartParams":{"a":"1","b":"2"}},'
+                   '"rayVersion":"2.9\\u003c\\u0026\\u003e","workerGroupSpecs":[{"groupName":"g","minReplicas":null,"maxReplicas":null,'
+                   '"rayStartParams":{},"template":{"spec":{"containers":[{"name":"w"}]}},"scaleStrategy":{}}]}')
+
+
+def test_find_suspend_status_order():
+    """utils/util.go:153-162: first True among Suspending / Suspended in slice order"""
+    conds = [{"type": "RayClusterSuspended", "status": "True"}, {"type": "RayClusterSuspending", "status": "True"}]
+    assert snapmod.find_suspend_status(conds) == abi.SUSPEND_SUSPENDED
+    assert snapmod.find_suspend_status(list(reversed(conds))) == abi.SUSPEND_SUSPENDING
+    assert snapmod.find_suspend_status([{"type": "RayClusterSuspending", "status": "False"}]) == abi.SUSPEND_NONE
+
+
+def test_atoi_semantics_of_replica_index_label():
+    """strconv.Atoi (raycluster_controller.go:857-860): sign allowed, no spaces, invalid => label ignored"""
+    def idx(v):
+        pk, r = snapmod.pack_pod_word({"name": "p", "labels": {snapmod.REPLICA_INDEX_LABEL: v}})
+        return (bool(pk & abi.PP_HAS_REPLICA_IDX), r)
+    assert idx("7") == (True, 7) and idx("+7") == (True, 7) and idx("-3") == (True, -3) and idx("007") == (True, 7)
+    assert idx(" 7")[0] is False and idx("7a")[0] is False and idx("")[0] is False and idx("1_0")[0] is False
