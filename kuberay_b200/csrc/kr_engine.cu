@@ -90,7 +90,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, cstart, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, cstart, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles;
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
@@ -121,6 +121,13 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
+  L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.mh_name = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.mh_meta = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.mh_cnt = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.mh_flg = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.mh_act = o; o = align_up(o + (size_t)n.n_pods);
+  L.mh_head = o; o = align_up(o + (size_t)n.n_pods);
   L.total = o;
   return L;
 }
@@ -219,6 +226,9 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.deferred_list = reinterpret_cast<uint32_t *>(b + L.deferred_list);
   s.ccount = reinterpret_cast<uint32_t *>(b + L.ccount);
   s.cstart = reinterpret_cast<uint32_t *>(b + L.cstart);
+  s.mh_rep = reinterpret_cast<uint32_t *>(b + L.mh_rep); s.mh_name = reinterpret_cast<uint32_t *>(b + L.mh_name);
+  s.mh_meta = reinterpret_cast<uint32_t *>(b + L.mh_meta); s.mh_cnt = reinterpret_cast<uint32_t *>(b + L.mh_cnt);
+  s.mh_flg = reinterpret_cast<uint32_t *>(b + L.mh_flg); s.mh_act = b + L.mh_act; s.mh_head = b + L.mh_head;
   return s;
 }
 
@@ -380,8 +390,6 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
   }
   CK(cudaEventRecord(e->ev_c, e->sm));
   CK(cudaStreamSynchronize(e->sm));
-  if (tot[3] & KR_TOTALS_ERR_MH_UNSUPPORTED)
-    return fail(e, KR_E_INVALID, "multi-host worker groups (numOfHosts>1 with RayMultiHostIndexing) are not handled by this engine build");
   if (out) {
     ResDev hr = bind_out(e->ol, e->h_out);
     out->clusters = hr.clusters; out->hash = hr.hash; out->groups = hr.groups;

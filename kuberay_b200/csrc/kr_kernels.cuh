@@ -77,6 +77,8 @@ struct ScratchDev {
   uint32_t *hist;                                              // [256 * ntiles] digit-major
   uint32_t *row_total;                                         // [256] per-digit totals of the current pass
   uint32_t *gcreate;                                           // [n_groups] dense n_create (input of the creates scan)
+  uint32_t *mh_rep, *mh_name, *mh_meta, *mh_cnt, *mh_flg;      // multi-host scratch, indexed by sorted position
+  uint8_t *mh_act, *mh_head;                                   // per position: action of a multi-host pod / first pod of a valid replica
   uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]
   uint32_t *deferred_list;                                     // clusters left for decide phase 1 (count in totals[4])
   int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
@@ -534,14 +536,15 @@ __device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict_
     uint32_t idx = lo + (lane + 1) * step - 1;
     bool ge = (idx >= hi) ? true : (__ldg(&a[idx]) >= v);
     uint32_t b = __ballot_sync(0xFFFFFFFFu, ge);
-    uint32_t first = __ffs(b) - 1;  // b != 0 because the last probe is >= hi or ge
+    if (b == 0) return hi;  // every probe (the last one sits at hi-1 at the earliest) is < v: the answer is hi itself
+    uint32_t first = __ffs(b) - 1;
     uint32_t nlo = lo + first * step, nhi = min(hi, lo + (first + 1) * step - 1);
     lo = nlo; hi = nhi;
   }
   uint32_t idx = lo + lane;
   bool ge = (idx >= hi) ? true : (__ldg(&a[idx]) >= v);
   uint32_t b = __ballot_sync(0xFFFFFFFFu, ge);
-  return lo + (__ffs(b) - 1);
+  return b ? lo + (__ffs(b) - 1) : hi;
 }
 
 struct DecideArgs {
@@ -671,6 +674,137 @@ __device__ void status_rollup(const DecideArgs &a, uint32_t c, kr_cluster_result
     } else if (ov != cvr[k]) inc = true;
   }
   cr.needs_status_write = inc ? 1 : 0;
+}
+
+// reconcileMultiHostWorkerGroup (raycluster_controller.go:963-1125) for one worker group, by one warp.
+// Replicas (pods sharing ray.io/worker-group-replica-name) are identified by the list position of their first pod, so
+// "first appearance in list order" — the deterministic stand-in for the reference's Go-map iteration (SURVEY Appendix
+// A.5) — is simply ascending position.  Cost O(pods x replicas / 32); every sweep is a coalesced 4-byte column read.
+// Returns the KR_ERR_* kind (0 = nil).
+#define KR_MH_NONE 0xFFFFFFFFu        // not a member of this group
+#define KR_MH_UNASSIGNED 0xFFFFFFFEu  // member with a replica-name label, replica not identified yet
+#define KR_MH_NOREP 0xFFFFFFFDu       // member without the label: belongs to no replica
+#define KR_MHF_DELETED 1u
+#define KR_MHF_WTD 2u
+#define KR_MHF_SCALE 4u
+__device__ int decide_multihost(const DecideArgs &a, uint32_t slot, uint32_t seg0, uint32_t seg1, int32_t expected, int32_t H,
+                                bool delete_allowed, uint32_t wtd_cnt, kr_group_result &gr, int32_t &err_arg, uint32_t lane) {
+  uint32_t *rep = a.sc.mh_rep, *name = a.sc.mh_name, *meta = a.sc.mh_meta, *cnt = a.sc.mh_cnt, *flg = a.sc.mh_flg;
+  uint8_t *act = a.sc.mh_act, *headv = a.sc.mh_head;
+  const uint32_t lt = lanemask_lt();
+  // 0. per-position columns of this group (valid only while this group is being decided)
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    if (i < seg1) {
+      uint4 row = a.sc.rows[a.r.sorted_pod_idx[i]];
+      bool member = (row.w >> 16) == slot;
+      rep[i] = member ? (row.y ? KR_MH_UNASSIGNED : KR_MH_NOREP) : KR_MH_NONE;
+      if (member) { name[i] = row.y; meta[i] = row.w & 0xFFFFu; act[i] = KR_ACT_KEEP; headv[i] = 0; }
+    }
+  }
+  __syncwarp();
+  // 1. replicaMap (:967-972): peel replicas off in order of first appearance
+  uint32_t cursor = seg0, first_incomplete = KR_MH_NONE, m_empty = KR_MH_NONE;
+  int32_t incomplete_cnt = 0;
+  while (true) {
+    uint32_t m = KR_MH_NONE;
+    for (uint32_t b = cursor; b < seg1; b += 32) {
+      uint32_t i = b + lane;
+      uint32_t bal = __ballot_sync(0xFFFFFFFFu, i < seg1 && rep[i] == KR_MH_UNASSIGNED);
+      if (bal) { m = b + (__ffs(bal) - 1); break; }
+    }
+    if (m == KR_MH_NONE) break;
+    const uint32_t nm = name[m];
+    uint32_t count = 0;
+    for (uint32_t b = m; b < seg1; b += 32) {
+      uint32_t i = b + lane;
+      bool hit = i < seg1 && rep[i] == KR_MH_UNASSIGNED && name[i] == nm;
+      if (hit) rep[i] = m;
+      count += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+    }
+    if (lane == 0) { cnt[m] = count; flg[m] = 0; }
+    if (nm == KR_ID_EMPTY_STRING) m_empty = m;
+    if ((int64_t)count < (int64_t)H && first_incomplete == KR_MH_NONE) { first_incomplete = m; incomplete_cnt = (int32_t)count; }
+    cursor = m + 1;
+    __syncwarp();
+  }
+  // 2. incomplete replica groups (:975-984)
+  if (first_incomplete != KR_MH_NONE) {
+    for (uint32_t b = seg0; b < seg1; b += 32) { uint32_t i = b + lane; if (i < seg1 && rep[i] == first_incomplete) act[i] = KR_ACT_DELETE_MH_INCOMPLETE; }
+    gr.flags |= KR_GR_ABORTED; err_arg = incomplete_cnt;
+    __syncwarp();
+    return KR_ERR_MH_INCOMPLETE;
+  }
+  // 3. unhealthy replica groups (:987-1007): a pod marks its replica; unlabelled pods resolve to the "" replica if one exists
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    if (i < seg1 && rep[i] != KR_MH_NONE && should_delete(meta[i])) {
+      uint32_t r = rep[i] == KR_MH_NOREP ? m_empty : rep[i];
+      if (r != KR_MH_NONE) atomicOr(&flg[r], KR_MHF_DELETED);
+    }
+  }
+  __syncwarp();
+  int32_t n_unh = 0;
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    bool hit = i < seg1 && rep[i] < KR_MH_NOREP && (flg[rep[i]] & KR_MHF_DELETED);
+    if (hit) act[i] = KR_ACT_DELETE_MH_UNHEALTHY;
+    n_unh += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+  }
+  gr.n_unhealthy = n_unh;
+  // 4. explicit deletions from the autoscaler (:1010-1038)
+  if (wtd_cnt > 0) {
+    for (uint32_t b = seg0; b < seg1; b += 32) {
+      uint32_t i = b + lane;
+      if (i < seg1 && rep[i] != KR_MH_NONE && (meta[i] & KR_ROW_WTD_OWN)) {
+        uint32_t r = rep[i] == KR_MH_NOREP ? m_empty : rep[i];
+        if (r != KR_MH_NONE) atomicOr(&flg[r], KR_MHF_WTD);
+      }
+    }
+    __syncwarp();
+    int32_t n_del = 0;
+    for (uint32_t b = seg0; b < seg1; b += 32) {
+      uint32_t i = b + lane;
+      bool hit = i < seg1 && rep[i] < KR_MH_NOREP && (flg[rep[i]] & KR_MHF_WTD);
+      if (hit && act[i] == KR_ACT_KEEP) act[i] = KR_ACT_DELETE_MH_WTD;
+      n_del += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+    }
+    gr.flags |= KR_GR_WTD_EXECUTED;
+    if (n_del > 0) { gr.flags |= KR_GR_ABORTED; err_arg = n_del; __syncwarp(); return KR_ERR_MH_WTD; }
+  }
+  // 5. diff by replica (:1042-1064)
+  int32_t running = 0;
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    bool ok = i < seg1 && rep[i] == i && !(flg[i] & KR_MHF_DELETED);  // first pod of a healthy, complete replica
+    if (ok) headv[i] = 1;
+    running += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+  }
+  gr.n_running = running;
+  if (expected % H != 0) { gr.flags |= KR_GR_ABORTED; err_arg = expected; __syncwarp(); return KR_ERR_MH_NOT_MULTIPLE; }
+  const int32_t to_create = expected / H - running;
+  gr.diff = to_create;
+  if (to_create > 0) gr.n_create = (uint32_t)to_create;  // one replica index per new replica group; k_create_fill allocates them
+  else if (to_create < 0) {
+    if (delete_allowed) {  // :1104-1118 — the first -to_create valid replicas in first-appearance order
+      int32_t seen = 0;
+      const int32_t remove = -to_create;
+      for (uint32_t b = seg0; b < seg1 && seen < remove; b += 32) {
+        uint32_t i = b + lane;
+        bool ok = i < seg1 && rep[i] == i && !(flg[i] & KR_MHF_DELETED);
+        uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok && seen + (int32_t)__popc(bal & lt) < remove) flg[i] |= KR_MHF_SCALE;
+        seen += __popc(bal);
+      }
+      __syncwarp();
+      for (uint32_t b = seg0; b < seg1; b += 32) {
+        uint32_t i = b + lane;
+        if (i < seg1 && rep[i] < KR_MH_NOREP && (flg[rep[i]] & KR_MHF_SCALE)) act[i] = KR_ACT_DELETE_MH_SCALE_DOWN;
+      }
+    } else gr.flags |= KR_GR_RANDOM_DELETE_OFF;
+  }
+  __syncwarp();
+  return KR_ERR_NONE;
 }
 
 // reconcilePods (raycluster_controller.go:619-935) for one RayCluster, by one warp.
@@ -824,7 +958,6 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
   }
 
   // worker groups in spec order (:751-933): O(1) per group from the scan-1 counters
-  bool any_multihost = false;
   if (run_groups) {
     const bool autoscaling = (cf & KR_CF_AUTOSCALING) != 0;
     cr.stop_after_group = (int32_t)G;
@@ -843,7 +976,12 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
         const int32_t n_list = acc_list[gi], n_unh = acc_unh[gi], n_wtd = acc_wtd[gi];
         gr.expected = expected; gr.n_list = n_list;
         if (gf & KR_GF_SUSPEND) { gr.flags |= KR_GR_SUSPENDED; mode = GM_SUSPENDED; }
-        else if (hosts > 1 && a.f.gate_multihost_indexing) { gr.flags |= KR_GR_MULTIHOST; mode = GM_MULTIHOST; any_multihost = true; }
+        else if (hosts > 1 && a.f.gate_multihost_indexing) {  // :777-784
+          gr.flags |= KR_GR_MULTIHOST; mode = GM_MULTIHOST;
+          int32_t earg = 0;
+          int ek = decide_multihost(a, gi, seg0, seg1, expected, hosts, !autoscaling || a.f.env_random_pod_delete, s.g_wtd_cnt[g], gr, earg, lane);
+          if (ek != KR_ERR_NONE) { cr.err_kind = (uint8_t)ek; cr.err_arg = earg; abort_here = true; }
+        }
         else if (n_unh > 0) {  // :786-812
           gr.n_unhealthy = n_unh; gr.flags |= KR_GR_ABORTED; mode = GM_UNHEALTHY;
           cr.err_kind = KR_ERR_UNHEALTHY_WORKERS; cr.err_arg = n_unh; abort_here = true;
@@ -890,7 +1028,6 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
       a.sc.gcreate[g0 + gi] = 0;
     }
   }
-  if (any_multihost && lane == 0) atomicOr(&a.r.totals[3], KR_TOTALS_ERR_MH_UNSUPPORTED);
   __syncwarp();
   const int32_t *mode_arr = g_mode ? g_mode : a.sc.gacc + g0;
   const int32_t *prefix_arr = g_prefix ? g_prefix : a.sc.gacc + a.n.n_groups + g0;
@@ -914,6 +1051,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
     if (all_action != KR_ACT_KEEP) act = valid ? all_action : (uint8_t)KR_ACT_KEEP;
     else if (head_delete) { if (valid && (int32_t)pod == head_pod) act = KR_ACT_DELETE_HEAD; }
     else if (mode == GM_SUSPENDED) act = KR_ACT_DELETE_GROUP_SUSPEND;
+    else if (mode == GM_MULTIHOST) act = a.sc.mh_act[i];
     else if (mode == GM_UNHEALTHY) { if (should_delete(fl)) act = KR_ACT_DELETE_UNHEALTHY; }
     else if (mode == GM_NORMAL) {
       if (fl & KR_ROW_WTD_OWN) act = KR_ACT_DELETE_WTD;
@@ -993,7 +1131,8 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
   const uint32_t g = blockIdx.x * 4 + warp;
   if (g >= n.n_groups) return;
   const kr_group_result gr = r.groups[g];
-  if (gr.n_create == 0 || (gr.flags & KR_GR_MULTIHOST)) return;
+  if (gr.n_create == 0) return;
+  const bool mh = (gr.flags & KR_GR_MULTIHOST) != 0;  // multi-host: in-use indices = label of the first pod of every valid replica (:1067-1077)
   if ((uint64_t)gr.create_off + gr.n_create > create_cap) return;  // host reports KR_E_CAPACITY from totals[0]
   int32_t *out = r.create_idx + gr.create_off;
   if (!f.gate_multihost_indexing) {  // createWorkerPod without an index (:884-889)
@@ -1011,7 +1150,7 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
     __syncwarp();
     for (uint32_t b = seg0; b < seg1; b += 32) {
       uint32_t i = b + lane;
-      if (i < seg1 && r.sorted_action[i] == KR_ACT_KEEP) {  // runningPods: listed and not deleted by name
+      if (i < seg1 && (mh ? sc.mh_head[i] != 0 : r.sorted_action[i] == KR_ACT_KEEP)) {  // runningPods: listed and not deleted by name
         uint4 row = sc.rows[r.sorted_pod_idx[i]];
         if ((row.w >> 16) == slot && (row.w & KR_PP_HAS_REPLICA_IDX)) {
           int32_t idx = (int32_t)row.z;

@@ -217,10 +217,8 @@ class RayClusterReconciler:
                     pi = int(res.wtd_pod_idx[w0 + k])
                     if pi >= 0 and cl.delete_pod(*meta.pod_keys[pi]):
                         ev(("Normal", EV_DELETED_WORKER_POD, f"Deleted pod {ns}/{nm}"))
-                if "workersToDelete" in grp:
-                    grp["workersToDelete"] = []
-                elif "scaleStrategy" in grp:
-                    grp["scaleStrategy"]["workersToDelete"] = []
+                # (:835 clears worker.ScaleStrategy.WorkersToDelete on the loop's COPY of the group spec only — the CR keeps
+                #  the names until the autoscaler removes them; later passes see NotFound and move on)
             for k in range(int(gr["n_create"])):    # :865-890
                 idx = int(res.create_idx[int(gr["create_off"]) + k])
                 pod = self._build_pod(cluster, "worker", gname, f"{cname}-{gname}-worker-{cl.gen_suffix()}")
@@ -260,9 +258,6 @@ class RayClusterReconciler:
                 return f"deleted {int(cr['err_arg'])} worker Pods based on ScaleStrategy, requeueing"
             if ek == abi.ERR_MH_NOT_MULTIPLE:
                 return f"desired worker pods ({int(gr['expected'])}) is not a multiple of NumOfHosts ({grp.get('numOfHosts', 1)}) for group {gname}"
-        if int(gr["flags"]) & abi.GR_WTD_EXECUTED:
-            if "workersToDelete" in grp:
-                grp["workersToDelete"] = []
         hosts = int(grp.get("numOfHosts", 1))
         for k in range(int(gr["n_create"])):        # one entry per replica group (:1082-1094)
             idx = int(res.create_idx[int(gr["create_off"]) + k])

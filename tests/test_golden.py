@@ -292,3 +292,94 @@ def test_full_reconcile_loop_converges(backend):
     assert err is None and st["state"] == "ready" and st["readyWorkerReplicas"] == 3 and st["desiredWorkerReplicas"] == 3
     requeue, err = r.reconcile(NS, CN)
     assert (requeue, err) == (300.0, None)            # nothing left to do: periodic resync only
+
+
+# ------------------------------------------------------------------------------------------------ multi-host worker groups
+def mh_client(replicas=3, hosts=4, autoscaling=True):
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    cluster["spec"]["enableInTreeAutoscaling"] = autoscaling
+    cluster["spec"]["workerGroupSpecs"][0].update({"replicas": replicas, "minReplicas": 0, "maxReplicas": 4, "numOfHosts": hosts, "workersToDelete": []})
+    return FakeClient([cluster], [copy.deepcopy(SC["base"]["pods"][0])])
+
+
+def run_all(client):
+    for p in client.pods.values():
+        if p.get("phase", "") == "":
+            p["phase"] = "Running"
+
+
+def replica_groups(client):
+    groups = {}
+    for p in workers(client):
+        groups.setdefault(p["labels"][snapmod.REPLICA_NAME_LABEL], []).append(p)
+    return groups
+
+
+def test_multihost_group_lifecycle(backend):
+    """raycluster_controller_test.go:925-1123 (envtest "multi-host" suite) restated on the fake client:
+    replicas=3 x numOfHosts=4 -> 12 pods in 3 replica groups with indices 0..2 and host indices 0..3; autoscaler scale-down
+    by workersToDelete removes whole replica groups; scale-up reuses the lowest free replica index."""
+    client = mh_client()
+    r = RayClusterReconciler(client, backend)
+    assert r.reconcile_pods(NS, CN) is None
+    run_all(client)
+    groups = replica_groups(client)
+    assert len(workers(client)) == 12 and len(groups) == 3
+    assert sorted(g[0]["labels"][snapmod.REPLICA_INDEX_LABEL] for g in groups.values()) == ["0", "1", "2"]
+    for g in groups.values():
+        assert sorted(p["labels"]["ray.io/replica-host-index"] for p in g) == ["0", "1", "2", "3"]
+        assert len({p["labels"][snapmod.REPLICA_INDEX_LABEL] for p in g}) == 1
+    assert r.reconcile_pods(NS, CN) is None and len(workers(client)) == 12   # steady
+    new, _ = r.calculate_status(NS, CN, None)
+    assert (new["desiredWorkerReplicas"], new["minWorkerReplicas"], new["maxWorkerReplicas"]) == (12, 0, 16)
+
+    # autoscaler scale-down: replicas 3 -> 2, one pod of the victim replica group named in workersToDelete (:1010-1038)
+    victim = next(g for g in groups.values() if g[0]["labels"][snapmod.REPLICA_INDEX_LABEL] == "1")
+    grp = client.clusters[(NS, CN)]["spec"]["workerGroupSpecs"][0]
+    grp["replicas"], grp["workersToDelete"] = 2, [victim[2]["name"]]
+    err = r.reconcile_pods(NS, CN)
+    assert err == "deleted 4 worker Pods based on ScaleStrategy, requeueing"
+    assert len(workers(client)) == 8
+    grp["workersToDelete"] = []  # cleanUpWorkersToDelete: the autoscaler clears the list (raycluster_controller_test.go:1095-1097)
+    assert r.reconcile_pods(NS, CN) is None and len(workers(client)) == 8
+
+    # scale back up: the freed replica index 1 is reused (:1081-1094)
+    grp["replicas"] = 3
+    assert r.reconcile_pods(NS, CN) is None
+    run_all(client)
+    groups = replica_groups(client)
+    assert len(workers(client)) == 12 and sorted(g[0]["labels"][snapmod.REPLICA_INDEX_LABEL] for g in groups.values()) == ["0", "1", "2"]
+
+
+def test_multihost_incomplete_and_unhealthy_replicas(backend):
+    """:975-1007 — an externally deleted pod makes its replica group incomplete: the remaining pods are deleted and the pass
+    aborts; an unhealthy pod takes its whole replica group with it and the replacement is created in the same pass."""
+    client = mh_client(replicas=2)
+    r = RayClusterReconciler(client, backend)
+    assert r.reconcile_pods(NS, CN) is None
+    run_all(client)
+    g0 = next(iter(replica_groups(client).values()))
+    client.delete_pod(NS, g0[0]["name"])
+    err = r.reconcile_pods(NS, CN)
+    assert err and err.startswith("cleaned up incomplete replica group") and len(workers(client)) == 4
+    assert r.reconcile_pods(NS, CN) is None
+    run_all(client)
+    assert len(workers(client)) == 8 and len(replica_groups(client)) == 2
+    # unhealthy pod: whole replica group deleted (:986-1007) and replaced (:1079-1094) without an error
+    sick = next(iter(replica_groups(client).values()))
+    sick[1]["phase"] = "Failed"
+    sick_names = {p["name"] for p in sick}
+    assert r.reconcile_pods(NS, CN) is None
+    assert not sick_names & {p["name"] for p in workers(client)} and len(workers(client)) == 8
+
+
+def test_multihost_random_scale_down_only_without_autoscaler(backend):
+    """:1095-1121"""
+    for autoscaling, want in ((True, 12), (False, 8)):
+        client = mh_client(replicas=3, autoscaling=autoscaling)
+        r = RayClusterReconciler(client, backend)
+        assert r.reconcile_pods(NS, CN) is None
+        run_all(client)
+        client.clusters[(NS, CN)]["spec"]["workerGroupSpecs"][0]["replicas"] = 2
+        assert r.reconcile_pods(NS, CN) is None
+        assert len(workers(client)) == want and all(len(g) == 4 for g in replica_groups(client).values())

@@ -44,6 +44,18 @@ def test_parity_many_groups_spill(oracle_mod):
     _parity(snap, flags, oracle_mod)
 
 
+def test_parity_multihost_groups(oracle_mod, monkeypatch):
+    # numOfHosts=4 groups with replica-name labels, incomplete / unhealthy / scale-down replicas in the mix
+    params = synthetic.SynthParams(n_clusters=400, pods_per_cluster=41, groups=2, multihost_frac=0.5)
+    snap, flags = synthetic.generate(params)
+    got = _parity(snap, flags, oracle_mod)
+    acts = set(np.unique(got.sorted_action).tolist())
+    assert {abi.ACT_DELETE_MH_UNHEALTHY, abi.ACT_DELETE_MH_INCOMPLETE} & acts
+    assert (got.groups["flags"] & abi.GR_MULTIHOST).any()
+    monkeypatch.setenv("KR_FORCE_RADIX", "1")
+    _parity(snap, flags, oracle_mod)
+
+
 def test_parity_flag_variants(oracle_mod):
     snap, flags = synthetic.generate(synthetic.config("C2"))
     for kw in (dict(env_random_pod_delete=1), dict(gate_status_conditions=0), dict(gate_multihost_indexing=0)):
@@ -63,6 +75,15 @@ def test_parity_radix_pipeline_forced(oracle_mod, monkeypatch):
     snap, flags = synthetic.generate(synthetic.config("C2", groups=2))
     _parity(snap, flags, oracle_mod)
     snap, flags = synthetic.generate(synthetic.config("C3"))
+    _parity(snap, flags, oracle_mod)
+
+
+@pytest.mark.parametrize("ppc", [1, 2, 33, 41, 63, 64, 65, 127])
+def test_parity_odd_cluster_sizes_both_pipelines(ppc, oracle_mod, monkeypatch):
+    params = synthetic.SynthParams(n_clusters=257, pods_per_cluster=ppc, groups=1)
+    snap, flags = synthetic.generate(params)
+    _parity(snap, flags, oracle_mod)
+    monkeypatch.setenv("KR_FORCE_RADIX", "1")
     _parity(snap, flags, oracle_mod)
 
 
