@@ -109,10 +109,15 @@ def cpu_arm(snap, flags, budget_s: float, threads: int):
     dt = time.perf_counter() - t0
     rate = probe / max(dt, 1e-9)
     sample = int(min(nc, max(probe, rate * budget_s)))
-    t0 = time.perf_counter()
-    oracle.run_range(snap, flags, 0, sample, list_mode=oracle.NS_SCAN, threads=threads)
-    dt = time.perf_counter() - t0
-    return sample / dt, sample, dt
+    # a bounded sample of the workload; when the whole snapshot takes less than the budget it is repeated instead
+    done, t0 = 0, time.perf_counter()
+    while True:
+        oracle.run_range(snap, flags, 0, sample, list_mode=oracle.NS_SCAN, threads=threads)
+        done += sample
+        dt = time.perf_counter() - t0
+        if sample < nc or dt >= budget_s:
+            break
+    return done / dt, done, dt
 
 
 def run_reference(args, rank: int, world: int):
@@ -135,7 +140,7 @@ def run_reference(args, rank: int, world: int):
         "config": {"workload": f"{args.workload}: {params.n_clusters} RayClusters x {params.pods_per_cluster} pods, {params.groups} worker group(s), 100 clusters/namespace",
                    "note": "CPU restatement (C), NOT the Go controller: no Go toolchain in this image; namespace-scan cached List per selector as in controller-runtime"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} of {snap.dims['clusters']} clusters per step, each reconciled against the full snapshot (G+4 namespace scans + SHA-1 of its spec JSON)"},
+                         "sample": f"{sample} reconciles per step over the {snap.dims['clusters']}-cluster snapshot (each = G+4 namespace-scan Lists + SHA-1 of its spec JSON)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -304,7 +309,7 @@ def main():
             threads = os.cpu_count() or 1
             v, sample, dt = cpu_arm(snap, flags, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample} of {nc_local} clusters reconciled against the full snapshot in {dt:.1f} s (CPU restatement in C, namespace-scan Lists; not the Go controller)"}
+                                    "sample": f"{sample} reconciles over the {nc_local}-cluster snapshot in {dt:.1f} s (CPU restatement in C, namespace-scan Lists; not the Go controller)"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
