@@ -254,10 +254,10 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
   auto launch_hash = [&]() {
     if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {
       uint32_t blocks = (n.n_clusters + 31) / 32;
-      k_hash<1><<<blocks, 32, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash);
+      k_hash2<1, 0><<<blocks, 32, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
     } else {
       uint32_t blocks = (n.n_clusters + 127) / 128;
-      k_hash<4><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash);
+      k_hash2<4, 1><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
     }
   };
   if (!profile) {
@@ -625,8 +625,8 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
   const uint64_t *doff = reinterpret_cast<const uint64_t *>(e->hb_d + o_off);
   const uint32_t *dlen = reinterpret_cast<const uint32_t *>(e->hb_d + o_len);
   char *dout = reinterpret_cast<char *>(e->hb_d + o_out);
-  if (n <= (uint32_t)e->sm_count * 4 * 32) k_hash<1><<<(n + 31) / 32, 32, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout);
-  else k_hash<4><<<(n + 127) / 128, 128, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout);
+  if (n <= (uint32_t)e->sm_count * 4 * 32) k_hash2<1, 0><<<(n + 31) / 32, 32, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout, 1u);
+  else k_hash2<4, 1><<<(n + 127) / 128, 128, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout, 1u);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->hb_h + o_out, dout, 32 * (size_t)n, cudaMemcpyDeviceToHost, e->sh));
   CK(cudaStreamSynchronize(e->sh));
