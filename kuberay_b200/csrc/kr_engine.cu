@@ -136,7 +136,9 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
 
 struct kr_engine {
   kr_config cfg{};
-  cudaStream_t sm = nullptr, sh = nullptr;
+  cudaStream_t sm = nullptr, sh = nullptr, sg = nullptr, scopy = nullptr;
+  cudaEvent_t ev_h2d0 = nullptr, ev_cols = nullptr, ev_json = nullptr;  // commit: copy start, columns landed, JSON landed
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   cudaEvent_t ev_k[KR_MAX_KERNEL_TIMES + 1]{};
   uint8_t *h_in = nullptr, *d_in = nullptr, *d_scratch = nullptr, *d_out = nullptr, *h_out = nullptr;
@@ -161,6 +163,7 @@ struct kr_engine {
   // pipeline choice: fast = count/place/in-warp sort (every bucket <= 1024 pods); radix = general stable LSD sort.
   bool force_radix = false;   // sticky per layout: set when a pass met a bucket the fast pipeline cannot sort
   bool ran_fast = false;
+  bool h2d_timed = true;      // h2d_ms of the last commit has been read back from its events
   bool env_radix = false;     // KR_FORCE_RADIX=1: always take the general pipeline (tests)
   uint32_t *h_totals = nullptr;  // pinned copy of the device totals (pipeline fallback check)
 };
@@ -233,7 +236,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
 }
 
 // Launches the whole pass.  profile: serialise everything on stream M and bracket each kernel with events.
-int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
+int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = false) {
   const kr_sizes &n = e->sizes;
   SnapDev s;
   bind_in(e->il, e->d_in, &s);
@@ -250,7 +253,11 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
 
   // --- stream H: hash (only needs the committed snapshot)
   const bool do_hash = !f.skip_hash && n.n_clusters > 0;
+  // the committed snapshot: columns gate stream M, the JSON arena gates the hash
+  const unsigned wflag = capturing ? cudaEventWaitExternal : cudaEventWaitDefault;
+  CK(cudaStreamWaitEvent(M, e->ev_cols, wflag));
   if (!profile) { CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0)); }
+  CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
   auto launch_hash = [&]() {
     if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {
       uint32_t blocks = (n.n_clusters + 31) / 32;
@@ -308,9 +315,17 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile) {
   }
   DecideArgs da{s, sc, r, z, f, sorted_keys, sc.vals[0], fast ? 1 : 0, 0};
   {
+    // fast pipeline: k_decide_small (buckets kept in registers) and the general k_decide run side by side
+    cudaStream_t G2 = (fast && !profile) ? e->sg : M;
+    if (fast && !profile) { CK(cudaEventRecord(e->ev_fork2, M)); CK(cudaStreamWaitEvent(G2, e->ev_fork2, 0)); }
     uint32_t warps = n.n_clusters + 1;
     mark("k_decide");
-    k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
+    k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, G2>>>(da);
+    if (fast && n.n_clusters) {
+      mark("k_decide_small");
+      k_decide_small<<<(n.n_clusters + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
+    }
+    if (fast && !profile) { CK(cudaEventRecord(e->ev_join2, G2)); CK(cudaStreamWaitEvent(M, e->ev_join2, 0)); }
   }
   if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
   if (profile) {
@@ -344,7 +359,7 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
     if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
     e->gvalid = false;
     CK(cudaStreamBeginCapture(e->sm, cudaStreamCaptureModeThreadLocal));
-    int rc = launch_pass(e, f, false);
+    int rc = launch_pass(e, f, false, true);
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->sm, &g);
     if (rc != KR_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
@@ -368,6 +383,11 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
     if (done) CK(cudaEventRecord(done, e->sm));
     CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
+    if (!e->h2d_timed) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_json) == cudaSuccess) e->prof.h2d_ms = ms;
+      e->h2d_timed = true;
+    }
     if (e->ran_fast && (e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { e->force_radix = true; e->gvalid = false; continue; }
     return KR_OK;
   }
@@ -433,6 +453,11 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   e->out_cap = out_layout(cap, cfg->max_creates).total;
   if (cudaStreamCreateWithFlags(&e->sm, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaStreamCreateWithFlags(&e->sh, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaStreamCreateWithFlags(&e->sg, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaStreamCreateWithFlags(&e->scopy, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
+  cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
+  cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_hash, cudaEventDisableTiming);
   cudaEventCreate(&e->ev_a); cudaEventCreate(&e->ev_b); cudaEventCreate(&e->ev_c);
@@ -468,6 +493,11 @@ void kr_engine_destroy(kr_engine *e) {
   for (auto ev : e->ev_k) if (ev) cudaEventDestroy(ev);
   if (e->sm) cudaStreamDestroy(e->sm);
   if (e->sh) cudaStreamDestroy(e->sh);
+  if (e->sg) cudaStreamDestroy(e->sg);
+  if (e->scopy) { cudaStreamSynchronize(e->scopy); cudaStreamDestroy(e->scopy); }
+  for (auto ev : {e->ev_h2d0, e->ev_cols, e->ev_json}) if (ev) cudaEventDestroy(ev);
+  if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   delete e;
 }
 
@@ -479,6 +509,7 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
     return fail(e, KR_E_CAPACITY, "snapshot exceeds the engine capacities given to kr_engine_create");
   if (sizes->n_clusters >= 0xFFFFFFF0u || sizes->n_pods >= 0xFFFFFFF0u) return fail(e, KR_E_CAPACITY, "too many rows");
   CK(cudaSetDevice(c.device));
+  CK(cudaStreamSynchronize(e->scopy));
   CK(cudaStreamSynchronize(e->sm));  // previous results are invalidated from here on
   if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) { e->gvalid = false; e->force_radix = e->env_radix; }  // layout (hence every kernel argument) changes
   e->sizes = *sizes;
@@ -512,12 +543,17 @@ int kr_snapshot_commit(kr_engine *e) {
   if (goff != n.n_groups) return fail(e, KR_E_INVALID, "sum of group_cnt (%llu) != n_groups (%u)", (unsigned long long)goff, n.n_groups);
   if (n_recreate != e->n_recreate) e->gvalid = false;  // decide phase 1 launch shape depends on it
   e->n_recreate = n_recreate;
-  CK(cudaEventRecord(e->ev_a, e->sm));
-  CK(cudaMemcpyAsync(e->d_in, e->h_in, e->il.total, cudaMemcpyHostToDevice, e->sm));
-  CK(cudaEventRecord(e->ev_b, e->sm));
-  CK(cudaStreamSynchronize(e->sm));
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.h2d_ms = ms;
+  // Asynchronous, in two parts on the copy stream: every column first, the spec-JSON arena (the larger half) second.
+  // The pass waits on the two events, so match/place/decide run while the JSON is still crossing PCIe and only the hash
+  // (and what depends on it) waits for the second part.  Nothing here blocks the host.
+  CK(cudaStreamSynchronize(e->sm));  // a pass still reading the previous snapshot must finish before it is overwritten
+  const size_t json_off = e->il.off[kNumCols - 1];
+  CK(cudaEventRecord(e->ev_h2d0, e->scopy));
+  if (json_off) CK(cudaMemcpyAsync(e->d_in, e->h_in, json_off, cudaMemcpyHostToDevice, e->scopy));
+  CK(cudaEventRecord(e->ev_cols, e->scopy));
+  if (e->il.total > json_off) CK(cudaMemcpyAsync(e->d_in + json_off, e->h_in + json_off, e->il.total - json_off, cudaMemcpyHostToDevice, e->scopy));
+  CK(cudaEventRecord(e->ev_json, e->scopy));
+  e->h2d_timed = false;
   e->prof.h2d_bytes = e->il.total;
   e->committed = true;
   return KR_OK;

@@ -69,7 +69,7 @@ struct ResDev {  // device results arena
 
 struct ScratchDev {
   uint4 *cl_slots; uint32_t cl_mask;                           // cluster table: {key lo, key hi, cluster idx, -} per 16-byte slot
-  uint4 *cl_rec;                                               // [n_clusters] {group_off, group_cnt, name id of group 0, -}
+  uint4 *cl_rec;                                               // [n_clusters] {group_off, group_cnt, name id of group 0, bit0 = has a multi-host group}
   uint64_t *wt_keys; uint32_t *wt_head; uint32_t *wt_next; uint32_t wt_mask;  // workersToDelete-name table
   uint32_t *aux_keys; uint32_t *aux_vals; uint32_t aux_mask;   // pod idx -> head-aux row
   uint4 *rows;                                                 // 16-byte pod rows, original order
@@ -112,6 +112,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   return x;
 }
 __device__ __forceinline__ uint64_t key2(uint32_t a, uint32_t b) { return ((uint64_t)a << 32) | b; }
+// slot hash of an (a, b) id pair: two 32-bit multiplies + one finalizer (the tables are small and 2x over-provisioned)
+__device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) { return mix32(a * 0x9E3779B1u ^ (b * 0x85EBCA77u + 0x165667B1u)); }
 #define KR_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define KR_EMPTY32 0xFFFFFFFFu
 
@@ -142,7 +144,7 @@ __device__ __forceinline__ int32_t desired_replicas(int32_t replicas, int32_t mn
 
 __device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uint32_t name, uint32_t &out) {
   if (name == 0) return false;
-  uint32_t i = (uint32_t)mix64(key2(ns, name)) & sc.cl_mask;
+  uint32_t i = hash_pair(ns, name) & sc.cl_mask;
   while (true) {
     uint4 sl = __ldg(&sc.cl_slots[i]);  // one 16-byte load: key and value together
     if (sl.x == name && sl.y == ns) { out = sl.z; return true; }
@@ -158,8 +160,7 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n.n_clusters) {
     uint32_t ns = s.c_ns_id[t], name = s.c_name_id[t];
-    uint64_t k = key2(ns, name);
-    uint32_t i = (uint32_t)mix64(k) & sc.cl_mask;
+    uint32_t i = hash_pair(ns, name) & sc.cl_mask;
     unsigned long long *slots = reinterpret_cast<unsigned long long *>(sc.cl_slots);  // [2*i] = key (x = name, y = ns), [2*i+1] low word = idx
     const unsigned long long kk = ((unsigned long long)ns << 32) | name;
     while (true) {
@@ -167,8 +168,9 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
       if (prev == KR_EMPTY64 || prev == kk) { atomicMin(reinterpret_cast<uint32_t *>(&slots[2 * (size_t)i + 1]), t); break; }  // duplicate (ns,name): lowest index wins
       i = (i + 1) & sc.cl_mask;
     }
-    uint32_t g0 = s.c_group_off[t], G = s.c_group_cnt[t];
-    sc.cl_rec[t] = make_uint4(g0, G, G ? s.g_name_id[g0] : 0u, 0u);
+    uint32_t g0 = s.c_group_off[t], G = s.c_group_cnt[t], mh = 0;
+    for (uint32_t gi = 0; gi < G; gi++) mh |= (s.g_num_hosts[g0 + gi] > 1) ? 1u : 0u;
+    sc.cl_rec[t] = make_uint4(g0, G, G ? s.g_name_id[g0] : 0u, mh);  // .w bit 0: some worker group has numOfHosts > 1
     return;
   }
   t -= n.n_clusters;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
     for (uint32_t w = 0; w < cnt; w++) {
       uint32_t e = off + w;
       uint64_t k = key2(ns, s.w_name_id[e]);
-      uint32_t i = (uint32_t)mix64(k) & sc.wt_mask;
+      uint32_t i = hash_pair(ns, s.w_name_id[e]) & sc.wt_mask;
       while (true) {
         unsigned long long prev = atomicCAS((unsigned long long *)&sc.wt_keys[i], KR_EMPTY64, k);
         if (prev == KR_EMPTY64 || prev == k) {
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
   uint4 sl[kSortItems];
 #pragma unroll
   for (int it = 0; it < kSortItems; it++) {
-    pi[it] = (uint32_t)mix64(key2(ns[it], cn[it])) & sc.cl_mask;
+    pi[it] = hash_pair(ns[it], cn[it]) & sc.cl_mask;
     sl[it] = __ldg(&sc.cl_slots[pi[it]]);
   }
 #pragma unroll
@@ -268,6 +270,19 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
   uint4 rec[kSortItems];
 #pragma unroll
   for (int it = 0; it < kSortItems; it++) rec[it] = (c[it] < n.n_clusters) ? __ldg(&sc.cl_rec[c[it]]) : make_uint4(0, 0, 0, 0);
+  // phase C': first probe of the (tiny, cache-resident) workersToDelete-name table for every pod, and the bucket ranks
+  uint32_t wi[kSortItems];
+  uint64_t wk[kSortItems];
+  if (has_wtd) {
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) { wi[it] = hash_pair(ns[it], nm[it]) & sc.wt_mask; wk[it] = __ldg(&sc.wt_keys[wi[it]]); }
+  }
+  uint32_t rank[kSortItems];
+  if (kFast) {
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++)  // arrival rank inside the cluster's bucket (bucket n_clusters = orphans); 8 atomics in flight
+      rank[it] = (base + it * 32 < n.n_pods) ? atomicAdd(&sc.ccount[c[it]], 1u) : 0u;
+  }
   // phase D: ray.io/group against the cluster's worker groups, workersToDelete-name intersection, outputs
 #pragma unroll
   for (int it = 0; it < kSortItems; it++) {
@@ -282,12 +297,10 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
     }
     uint32_t flags = pk[it] & 0x7FFu;
     if (has_wtd) {
-      // label-set intersection against the (tiny, cache-resident) workersToDelete-name table
-      uint64_t k = key2(ns[it], nm[it]);
-      uint32_t i = (uint32_t)mix64(k) & sc.wt_mask;
-      while (true) {
-        uint64_t kk = __ldg(&sc.wt_keys[i]);
-        if (kk == KR_EMPTY64) break;
+      const uint64_t k = key2(ns[it], nm[it]);
+      uint32_t i = wi[it];
+      uint64_t kk = wk[it];
+      while (kk != KR_EMPTY64) {
         if (kk == k) {
           for (uint32_t e = sc.wt_head[i]; e != KR_EMPTY32; e = sc.wt_next[e]) {
             atomicMin(&r.wtd_pod_idx[e], p);
@@ -300,11 +313,12 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
           break;
         }
         i = (i + 1) & sc.wt_mask;
+        kk = __ldg(&sc.wt_keys[i]);
       }
     }
     sc.rows[p] = make_uint4(nm[it], rn[it], ri[it], (slot << 16) | flags);
     sc.keys[0][p] = c[it];
-    if (kFast) sc.keys[1][p] = atomicAdd(&sc.ccount[c[it]], 1u);  // arrival rank inside the cluster's bucket (bucket n_clusters = orphans)
+    if (kFast) sc.keys[1][p] = rank[it];
     else atomicAdd(&s_hist[c[it] & (kRadix - 1)], 1u);
   }
   if (!kFast) {
@@ -807,52 +821,69 @@ __device__ int decide_multihost(const DecideArgs &a, uint32_t slot, uint32_t seg
   return KR_ERR_NONE;
 }
 
-// reconcilePods (raycluster_controller.go:619-935) for one RayCluster, by one warp.
-__global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
-  __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
-  __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const SnapDev &s = a.s;
-  const uint32_t Nc = a.n.n_clusters, Np = a.n.n_pods;
-  uint32_t c = blockIdx.x * kDecideWarps + warp;
-  if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
-    if (c >= a.r.totals[4]) return;
-    c = a.sc.deferred_list[c];
-  } else if (c > Nc) return;
-  const uint32_t lt = lanemask_lt();
+#define LDG(x) __ldg(&(x))
 
-  uint32_t seg0, seg1;
-  if (a.fast) {
-    seg0 = a.sc.cstart[c]; seg1 = a.sc.cstart[c + 1];
-    // informer List order inside the bucket: sort the pod indices ascending (skipped in phase 1: already done)
-    if (a.phase == 0 && seg1 - seg0 <= KR_FAST_MAX_BUCKET) { warp_sort_dispatch(a.unsorted + seg0, a.r.sorted_pod_idx + seg0, seg1 - seg0, lane); __syncwarp(); }
-  } else {
-    seg0 = warp_lower_bound(a.sorted_keys, Np, c, lane);
-    seg1 = (c == Nc) ? Np : warp_lower_bound(a.sorted_keys, Np, c + 1, lane);
+// Bitonic sort of 32*K values held K per lane, STRIPED (element g = k*32 + lane), ascending.  Striped order is what the
+// chunked scans of k_decide want: register k of lane l is list position k*32+l, and loads/stores are fully coalesced.
+template <int K>
+__device__ __forceinline__ void warp_bitonic_sort_striped(uint32_t (&v)[K], uint32_t lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride < 32) {
+        const bool lower = (lane & stride) == 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v[k], stride);
+          bool asc = ((k * 32 + lane) & size) == 0;
+          v[k] = (asc == lower) ? min(v[k], o) : max(v[k], o);
+        }
+      } else {
+        const int ks = stride / 32;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if ((k & ks) == 0) {
+            const bool asc = ((k * 32) & size) == 0;  // size >= 64 here: the lane bits do not reach it
+            uint32_t lo = min(v[k], v[k + ks]), hi = max(v[k], v[k + ks]);
+            v[k] = asc ? lo : hi; v[k + ks] = asc ? hi : lo;
+          }
+        }
+      }
+    }
   }
-  if (c == Nc) {  // the orphan bucket: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot
-    if (a.phase != 0) return;
-    for (uint32_t i = seg0 + lane; i < seg1; i += 32) a.r.sorted_action[i] = KR_ACT_ORPHAN;
-    if (lane == 0) a.r.totals[1] = seg1 - seg0;
-    return;
-  }
+}
+
+// reconcilePods (raycluster_controller.go:619-935) + calculateStatus for one RayCluster, by one warp.
+// K > 0: the cluster's bucket (<= 32*K pods) is sorted and kept in registers — pod index pidx[k] and row word pw[k] of list
+// position k*32+lane — so the two scans below touch no memory.  K == 0: positions are read from sorted_pod_idx / rows
+// (radix pipeline, buckets larger than 256 pods, and phase 1).
+template <int K, bool kMH>
+__device__ __forceinline__ void decide_cluster(const DecideArgs &a, const uint32_t c, const uint32_t seg0, const uint32_t seg1,
+                                               uint32_t (&pidx)[K ? K : 1], uint32_t (&pw)[K ? K : 1],
+                                               int32_t (&s_acc)[4][KR_SMEM_GROUPS], int32_t (&s_mode)[2][KR_SMEM_GROUPS], const uint32_t lane) {
+  const SnapDev &s = a.s;
+  const uint32_t lt = lanemask_lt();
   const uint32_t P = seg1 - seg0;
-  const uint32_t cf = s.c_flags[c];
-  const uint32_t G = s.c_group_cnt[c], g0 = s.c_group_off[c];
+  const uint32_t nchunks = (P + 31) / 32;
+  // cluster scalars: independent read-only loads, issued together
+  const uint32_t cf = LDG(s.c_flags[c]);
+  const uint32_t G = LDG(s.c_group_cnt[c]), g0 = LDG(s.c_group_off[c]);
+  const uint8_t suspend_status = LDG(s.c_suspend_status[c]);
+  const uint8_t ext_err = LDG(s.c_ext_err_kind[c]);
+  const uint8_t old_prov = LDG(s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED]);
   const bool gate = a.f.gate_status_conditions != 0;
-  const uint8_t suspend_status = s.c_suspend_status[c];
 
   // accumulators: shared memory for the common case, global scratch for clusters with many groups
   int32_t *acc_list, *acc_unh, *acc_wtd, *acc_rank, *g_mode, *g_prefix;
   if (G <= KR_SMEM_GROUPS) {
-    acc_list = s_acc[warp][0]; acc_unh = s_acc[warp][1]; acc_wtd = s_acc[warp][2]; acc_rank = s_acc[warp][3];
-    g_mode = s_mode[warp][0]; g_prefix = s_mode[warp][1];
+    acc_list = s_acc[0]; acc_unh = s_acc[1]; acc_wtd = s_acc[2]; acc_rank = s_acc[3];
+    g_mode = s_mode[0]; g_prefix = s_mode[1];
     if (lane < KR_SMEM_GROUPS) { acc_list[lane] = 0; acc_unh[lane] = 0; acc_wtd[lane] = 0; acc_rank[lane] = 0; g_mode[lane] = GM_UNPROCESSED; g_prefix[lane] = 0; }
   } else {
     const uint32_t Ng = a.n.n_groups;
     acc_list = a.sc.gacc + g0; acc_unh = a.sc.gacc + Ng + g0; acc_wtd = a.sc.gacc + 2 * (size_t)Ng + g0; acc_rank = a.sc.gacc + 3 * (size_t)Ng + g0;
-    // modes reuse the diff / create_off fields of the (not yet written) group results as scratch
-    g_mode = nullptr; g_prefix = nullptr;
+    g_mode = nullptr; g_prefix = nullptr;  // modes recycle the n_list / n_unhealthy cells once they are consumed
     for (uint32_t gi = lane; gi < G; gi += 32) { acc_list[gi] = 0; acc_unh[gi] = 0; acc_wtd[gi] = 0; acc_rank[gi] = 0; }
   }
   __syncwarp();
@@ -860,27 +891,30 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
   // ---------------- scan 1: counts over the cluster's pods (list order)
   int32_t ready = 0, available = 0, n_heads = 0;
   bool all_running = P > 0;  // CheckAllPodsRunning (utils/util.go:584-603)
-  uint32_t first_head_pos = 0xFFFFFFFFu;
-  for (uint32_t b = seg0; b < seg1; b += 32) {
-    uint32_t i = b + lane;
-    bool valid = i < seg1;
-    uint4 row = make_uint4(0, 0, 0, 0);
-    if (valid) row = a.sc.rows[a.r.sorted_pod_idx[i]];
-    uint32_t fl = row.w & 0xFFFFu, slot = valid ? (row.w >> 16) : KR_ROW_NO_GROUP;
-    uint32_t nt = pp_node_type(fl), ph = pp_phase(fl), rd = pp_ready(fl);
-    bool w_run = valid && nt == KR_NT_WORKER && ph == KR_PHASE_RUNNING;
+  int32_t head_pod = -1;     // first head in list order
+#pragma unroll
+  for (int k = 0; k < (K ? K : 1 << 30); k++) {
+    if ((uint32_t)k >= nchunks) break;
+    const uint32_t i = seg0 + k * 32 + lane;
+    const bool valid = i < seg1;
+    uint32_t pod, w;
+    if (K) { pod = pidx[K ? k : 0]; w = pw[K ? k : 0]; }
+    else { pod = valid ? LDG(a.r.sorted_pod_idx[i]) : 0u; w = valid ? reinterpret_cast<const uint32_t *>(a.sc.rows)[4 * (size_t)pod + 3] : 0u; }
+    const uint32_t fl = w & 0xFFFFu, slot = valid ? (w >> 16) : KR_ROW_NO_GROUP;
+    const uint32_t nt = pp_node_type(fl), ph = pp_phase(fl), rd = pp_ready(fl);
+    const bool w_run = valid && nt == KR_NT_WORKER && ph == KR_PHASE_RUNNING;
     available += __popc(__ballot_sync(0xFFFFFFFFu, w_run));
     ready += __popc(__ballot_sync(0xFFFFFFFFu, w_run && rd == KR_COND_TRUE));
-    bool not_ok = valid && (ph != KR_PHASE_RUNNING || rd == KR_COND_FALSE || rd == KR_COND_UNKNOWN);
+    const bool not_ok = valid && (ph != KR_PHASE_RUNNING || rd == KR_COND_FALSE || rd == KR_COND_UNKNOWN);
     if (__any_sync(0xFFFFFFFFu, not_ok)) all_running = false;
-    uint32_t hb = __ballot_sync(0xFFFFFFFFu, valid && nt == KR_NT_HEAD);
-    if (hb) { if (n_heads == 0) first_head_pos = b + (__ffs(hb) - 1); n_heads += __popc(hb); }
+    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, valid && nt == KR_NT_HEAD);
+    if (hb) { if (n_heads == 0) head_pod = (int32_t)__shfl_sync(0xFFFFFFFFu, pod, __ffs(hb) - 1); n_heads += __popc(hb); }
     // warp-ballot group-by on the group slot
-    uint32_t gkey = (slot < G) ? slot : KR_ROW_NO_GROUP;
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, gkey);
+    const uint32_t gkey = (slot < G) ? slot : KR_ROW_NO_GROUP;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, gkey);
     if (gkey != KR_ROW_NO_GROUP) {
-      uint32_t ub = __ballot_sync(peers, should_delete(fl));
-      uint32_t wb = __ballot_sync(peers, (fl & KR_ROW_WTD_OWN) != 0);
+      const uint32_t ub = __ballot_sync(peers, should_delete(fl));
+      const uint32_t wb = __ballot_sync(peers, (fl & KR_ROW_WTD_OWN) != 0);
       if ((peers & lt) == 0) {  // leader of its group in this chunk
         acc_list[gkey] += __popc(peers);
         acc_unh[gkey] += __popc(ub & peers);
@@ -890,13 +924,8 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
     __syncwarp();
   }
 
-  // head pod (first in list order) fields
-  int32_t head_pod = -1; uint32_t head_flags = 0, head_name = 0;
-  if (n_heads > 0) {
-    head_pod = (int32_t)a.r.sorted_pod_idx[first_head_pos];
-    uint4 hrow = a.sc.rows[head_pod];
-    head_flags = hrow.w & 0xFFFFu; head_name = hrow.x;
-  }
+  uint32_t head_flags = 0, head_name = 0;
+  if (n_heads > 0) { uint4 hrow = __ldg(&a.sc.rows[head_pod]); head_flags = hrow.w & 0xFFFFu; head_name = hrow.x; }
 
   // ---------------- scalar decisions (uniform across the warp)
   kr_cluster_result cr;
@@ -912,9 +941,9 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
 
   if (cf & KR_CF_SKIP) {
     cr.path = KR_PATH_SKIPPED;
-  } else if (s.c_ext_err_kind[c] != KR_EXT_ERR_NONE) {
+  } else if (ext_err != KR_EXT_ERR_NONE) {
     cr.path = KR_PATH_SKIPPED;  // :308-314
-    cr.err_kind = s.c_ext_err_kind[c] == KR_EXT_ERR_STATUS_ONLY_NIL ? KR_ERR_NONE : KR_ERR_EXTERNAL;
+    cr.err_kind = ext_err == KR_EXT_ERR_STATUS_ONLY_NIL ? KR_ERR_NONE : KR_ERR_EXTERNAL;
   } else if (suspend_status == KR_SUSPEND_SUSPENDING || (!gate && (cf & KR_CF_SUSPEND))) {
     cr.path = KR_PATH_SUSPENDING_DELETE_ALL; all_action = KR_ACT_DELETE_ALL_SUSPEND;  // :629-644
   } else if (gate && (suspend_status == KR_SUSPEND_SUSPENDED || (cf & KR_CF_SUSPEND))) {
@@ -948,8 +977,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
         if (should_delete(head_flags)) { cr.head_action = KR_HEAD_DELETE; cr.err_kind = KR_ERR_HEAD_DELETED; head_delete = true; }
         else run_groups = true;
       } else if (n_heads == 0) {
-        bool provisioned = s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED] == KR_COND_TRUE;
-        if (provisioned && (cf & KR_CF_SKIP_HEAD_RESTART)) cr.head_action = KR_HEAD_SKIP_RESTART;
+        if (old_prov == KR_COND_TRUE && (cf & KR_CF_SKIP_HEAD_RESTART)) cr.head_action = KR_HEAD_SKIP_RESTART;
         else { cr.head_action = KR_HEAD_CREATE; run_groups = true; }
       } else {
         cr.head_action = KR_HEAD_MULTIPLE; cr.err_kind = KR_ERR_MULTIPLE_HEADS; cr.err_arg = n_heads;
@@ -962,7 +990,8 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
     const bool autoscaling = (cf & KR_CF_AUTOSCALING) != 0;
     cr.stop_after_group = (int32_t)G;
     for (uint32_t gi = 0; gi < G; gi++) {
-      const uint32_t g = g0 + gi, gf = s.g_flags[g];
+      const uint32_t g = g0 + gi, gf = LDG(s.g_flags[g]);
+      const int32_t hosts = LDG(s.g_num_hosts[g]), g_rep = LDG(s.g_replicas[g]), g_mn = LDG(s.g_min[g]), g_mx = LDG(s.g_max[g]);
       kr_group_result gr;
       gr.expected = 0; gr.n_list = 0; gr.n_unhealthy = 0; gr.n_running = 0; gr.diff = 0; gr.n_create = 0; gr.create_off = 0;
       gr.flags = KR_GR_PROCESSED;
@@ -971,15 +1000,14 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
       if (!(gf & KR_GF_EXPECT_OK)) {
         gr.flags |= KR_GR_EXPECT_PENDING;
       } else {
-        const int32_t hosts = s.g_num_hosts[g];
-        const int32_t expected = desired_replicas(s.g_replicas[g], s.g_min[g], s.g_max[g], hosts, gf);
+        const int32_t expected = desired_replicas(g_rep, g_mn, g_mx, hosts, gf);
         const int32_t n_list = acc_list[gi], n_unh = acc_unh[gi], n_wtd = acc_wtd[gi];
         gr.expected = expected; gr.n_list = n_list;
         if (gf & KR_GF_SUSPEND) { gr.flags |= KR_GR_SUSPENDED; mode = GM_SUSPENDED; }
-        else if (hosts > 1 && a.f.gate_multihost_indexing) {  // :777-784
+        else if (kMH && hosts > 1 && a.f.gate_multihost_indexing) {  // :777-784 (clusters with such groups never reach the <.., false> instantiations)
           gr.flags |= KR_GR_MULTIHOST; mode = GM_MULTIHOST;
           int32_t earg = 0;
-          int ek = decide_multihost(a, gi, seg0, seg1, expected, hosts, !autoscaling || a.f.env_random_pod_delete, s.g_wtd_cnt[g], gr, earg, lane);
+          int ek = decide_multihost(a, gi, seg0, seg1, expected, hosts, !autoscaling || a.f.env_random_pod_delete, LDG(s.g_wtd_cnt[g]), gr, earg, lane);
           if (ek != KR_ERR_NONE) { cr.err_kind = (uint8_t)ek; cr.err_arg = earg; abort_here = true; }
         }
         else if (n_unh > 0) {  // :786-812
@@ -1003,29 +1031,23 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
         }
       }
       __syncwarp();  // every lane has read this group's counters before lane 0 recycles their cells
-      if (g_mode) { if (lane == 0) { g_mode[gi] = mode; g_prefix[gi] = prefix; } }
       if (lane == 0) {
+        if (g_mode) { g_mode[gi] = mode; g_prefix[gi] = prefix; }
+        else { a.sc.gacc[g] = mode; a.sc.gacc[a.n.n_groups + g] = prefix; }
         a.r.groups[g] = gr;
         a.sc.gcreate[g] = gr.n_create;
-        if (!g_mode) { a.sc.gacc[g] = mode; a.sc.gacc[a.n.n_groups + g] = prefix; }  // spill: reuse n_list/n_unh cells (already consumed)
       }
       if (abort_here) { cr.stop_after_group = (int32_t)gi; break; }
     }
   }
   // groups never reached keep an all-zero record
-  if (!(cf & KR_CF_SKIP)) {
-    int32_t reached = run_groups ? (cr.stop_after_group == (int32_t)G ? (int32_t)G : cr.stop_after_group + 1) : 0;
+  {
+    const int32_t reached = ((cf & KR_CF_SKIP) || !run_groups) ? 0 : (cr.stop_after_group == (int32_t)G ? (int32_t)G : cr.stop_after_group + 1);
     for (uint32_t gi = reached + lane; gi < G; gi += 32) {
       kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
       a.r.groups[g0 + gi] = z;
       a.sc.gcreate[g0 + gi] = 0;
       if (!g_mode) { a.sc.gacc[g0 + gi] = GM_UNPROCESSED; a.sc.gacc[a.n.n_groups + g0 + gi] = 0; }
-    }
-  } else {
-    for (uint32_t gi = lane; gi < G; gi += 32) {
-      kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
-      a.r.groups[g0 + gi] = z;
-      a.sc.gcreate[g0 + gi] = 0;
     }
   }
   __syncwarp();
@@ -1034,36 +1056,39 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
 
   // ---------------- scan 2: per-pod actions in list order
   uint32_t n_act = 0;
-  for (uint32_t b = seg0; b < seg1; b += 32) {
-    uint32_t i = b + lane;
-    bool valid = i < seg1;
-    uint32_t pod = valid ? a.r.sorted_pod_idx[i] : 0;
-    uint8_t act = KR_ACT_KEEP;
-    uint32_t gkey = KR_ROW_NO_GROUP, fl = 0;
-    if (valid && run_groups) {
-      uint32_t w = a.sc.rows[pod].w;
-      fl = w & 0xFFFFu;
-      uint32_t slot = w >> 16;
-      if (slot < G) gkey = slot;
+#pragma unroll
+  for (int k = 0; k < (K ? K : 1 << 30); k++) {
+    if ((uint32_t)k >= nchunks) break;
+    const uint32_t i = seg0 + k * 32 + lane;
+    const bool valid = i < seg1;
+    uint32_t pod, w = 0;
+    if (K) { pod = pidx[K ? k : 0]; w = pw[K ? k : 0]; }
+    else {
+      pod = valid ? LDG(a.r.sorted_pod_idx[i]) : 0u;
+      if (valid && run_groups) w = reinterpret_cast<const uint32_t *>(a.sc.rows)[4 * (size_t)pod + 3];
     }
-    int32_t mode = (gkey != KR_ROW_NO_GROUP) ? mode_arr[gkey] : GM_UNPROCESSED;
+    uint8_t act = KR_ACT_KEEP;
+    uint32_t gkey = KR_ROW_NO_GROUP;
+    const uint32_t fl = w & 0xFFFFu;
+    if (valid && run_groups && (w >> 16) < G) gkey = w >> 16;
+    const int32_t mode = (gkey != KR_ROW_NO_GROUP) ? mode_arr[gkey] : GM_UNPROCESSED;
     bool candidate = false;  // running pod of a group in normal mode: subject to the ordered delete prefix
     if (all_action != KR_ACT_KEEP) act = valid ? all_action : (uint8_t)KR_ACT_KEEP;
     else if (head_delete) { if (valid && (int32_t)pod == head_pod) act = KR_ACT_DELETE_HEAD; }
     else if (mode == GM_SUSPENDED) act = KR_ACT_DELETE_GROUP_SUSPEND;
-    else if (mode == GM_MULTIHOST) act = a.sc.mh_act[i];
+    else if (kMH && mode == GM_MULTIHOST) act = a.sc.mh_act[i];
     else if (mode == GM_UNHEALTHY) { if (should_delete(fl)) act = KR_ACT_DELETE_UNHEALTHY; }
     else if (mode == GM_NORMAL) {
       if (fl & KR_ROW_WTD_OWN) act = KR_ACT_DELETE_WTD;
       else candidate = true;
     }
     // stable rank among the running pods of the same group: ballot group-by + per-group cursor
-    uint32_t ckey = candidate ? gkey : KR_ROW_NO_GROUP;
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, ckey);
+    const uint32_t ckey = candidate ? gkey : KR_ROW_NO_GROUP;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ckey);
     if (candidate) {
-      int32_t cur = acc_rank[ckey];
+      const int32_t cur = acc_rank[ckey];
       __syncwarp(peers);
-      int32_t rank = cur + __popc(peers & lt);
+      const int32_t rank = cur + __popc(peers & lt);
       if ((peers & lt) == 0) acc_rank[ckey] = cur + __popc(peers);
       if (rank < prefix_arr[ckey]) act = KR_ACT_DELETE_RANDOM;  // runningPods.Items[0 .. -diff) (:916-919)
     }
@@ -1079,6 +1104,79 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
     a.r.clusters[c] = cr;
     if (n_act) atomicAdd(&a.r.totals[2], n_act);
   }
+}
+
+// Sort a bucket of <= 32*K pod indices in registers, publish it (sorted_pod_idx), gather the row words, decide.
+template <int K>
+__device__ __forceinline__ void decide_cluster_regs(const DecideArgs &a, uint32_t c, uint32_t seg0, uint32_t seg1,
+                                                    int32_t (&s_acc)[4][KR_SMEM_GROUPS], int32_t (&s_mode)[2][KR_SMEM_GROUPS], uint32_t lane) {
+  uint32_t pidx[K], pw[K];
+  const uint32_t P = seg1 - seg0;
+#pragma unroll
+  for (int k = 0; k < K; k++) { uint32_t g = k * 32 + lane; pidx[k] = g < P ? LDG(a.unsorted[seg0 + g]) : 0xFFFFFFFFu; }
+  warp_bitonic_sort_striped<K>(pidx, lane);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    uint32_t g = k * 32 + lane;
+    pw[k] = 0;
+    if (g < P) { a.r.sorted_pod_idx[seg0 + g] = pidx[k]; pw[k] = reinterpret_cast<const uint32_t *>(a.sc.rows)[4 * (size_t)pidx[k] + 3]; }
+    else pidx[k] = 0;
+  }
+  __syncwarp();  // sorted_pod_idx of this bucket is visible to the whole warp (decide_multihost re-reads it)
+  decide_cluster<K, false>(a, c, seg0, seg1, pidx, pw, s_acc, s_mode, lane);
+}
+
+// Is this cluster decided by k_decide_small (bucket sorted and kept in registers)?  Fast pipeline, phase 0, at most 256
+// pods, no multi-host worker group (those need the memory-resident sweeps of decide_multihost).
+__device__ __forceinline__ bool small_path(const DecideArgs &a, uint32_t c, uint32_t P) {
+  return a.fast && a.phase == 0 && P <= 256 && !(a.f.gate_multihost_indexing && (__ldg(&a.sc.cl_rec[c]).w & 1u));
+}
+
+// Common case: one warp per RayCluster with <= 256 pods, everything after the bucket load stays in registers.
+__global__ void __launch_bounds__(kDecideWarps * 32) k_decide_small(DecideArgs a) {
+  __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
+  __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = blockIdx.x * kDecideWarps + warp;
+  if (c >= a.n.n_clusters) return;
+  const uint32_t seg0 = LDG(a.sc.cstart[c]), seg1 = LDG(a.sc.cstart[c + 1]);
+  const uint32_t P = seg1 - seg0;
+  if (!small_path(a, c, P)) return;
+  if (P <= 128) decide_cluster_regs<4>(a, c, seg0, seg1, s_acc[warp], s_mode[warp], lane);
+  else decide_cluster_regs<8>(a, c, seg0, seg1, s_acc[warp], s_mode[warp], lane);
+}
+
+// General case: radix pipeline (all clusters), big buckets, clusters with multi-host groups, phase 1, the orphan bucket.
+__global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
+  __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];
+  __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t Nc = a.n.n_clusters, Np = a.n.n_pods;
+  uint32_t c = blockIdx.x * kDecideWarps + warp;
+  if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
+    if (c >= a.r.totals[4]) return;
+    c = a.sc.deferred_list[c];
+  } else if (c > Nc) return;
+
+  uint32_t seg0, seg1;
+  if (a.fast) { seg0 = LDG(a.sc.cstart[c]); seg1 = LDG(a.sc.cstart[c + 1]); }
+  else {
+    seg0 = warp_lower_bound(a.sorted_keys, Np, c, lane);
+    seg1 = (c == Nc) ? Np : warp_lower_bound(a.sorted_keys, Np, c + 1, lane);
+  }
+  const uint32_t P = seg1 - seg0;
+  if (c == Nc) {  // the orphan bucket: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot
+    if (a.phase != 0) return;
+    if (a.fast && P <= KR_FAST_MAX_BUCKET) { warp_sort_dispatch(a.unsorted + seg0, a.r.sorted_pod_idx + seg0, P, lane); __syncwarp(); }
+    for (uint32_t i = seg0 + lane; i < seg1; i += 32) a.r.sorted_action[i] = KR_ACT_ORPHAN;
+    if (lane == 0) a.r.totals[1] = P;
+    return;
+  }
+  if (small_path(a, c, P)) return;  // k_decide_small owns it
+  // fast pipeline, phase 0: informer List order inside the bucket = ascending pod index (phase 1 finds it already sorted)
+  if (a.fast && a.phase == 0 && P <= KR_FAST_MAX_BUCKET) { warp_sort_dispatch(a.unsorted + seg0, a.r.sorted_pod_idx + seg0, P, lane); __syncwarp(); }
+  uint32_t d0[1] = {0}, d1[1] = {0};
+  decide_cluster<0, true>(a, c, seg0, seg1, d0, d1, s_acc[warp], s_mode[warp], lane);
 }
 
 // ------------------------------------------------------------------------------------------------ creates
