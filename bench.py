@@ -167,6 +167,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -310,7 +314,7 @@ def main():
             v, sample, dt = cpu_arm(snap, flags, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{sample} reconciles over the {nc_local}-cluster snapshot in {dt:.1f} s (CPU restatement in C, namespace-scan Lists; not the Go controller)"}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()

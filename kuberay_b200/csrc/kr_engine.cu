@@ -90,7 +90,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, cstart, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles;
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
@@ -121,6 +121,7 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
+  L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.ntiles + 8));
   L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.mh_name = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.mh_meta = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -229,6 +230,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.deferred_list = reinterpret_cast<uint32_t *>(b + L.deferred_list);
   s.ccount = reinterpret_cast<uint32_t *>(b + L.ccount);
   s.cstart = reinterpret_cast<uint32_t *>(b + L.cstart);
+  s.tile_orph = reinterpret_cast<uint32_t *>(b + L.tile_orph);
   s.mh_rep = reinterpret_cast<uint32_t *>(b + L.mh_rep); s.mh_name = reinterpret_cast<uint32_t *>(b + L.mh_name);
   s.mh_meta = reinterpret_cast<uint32_t *>(b + L.mh_meta); s.mh_cnt = reinterpret_cast<uint32_t *>(b + L.mh_cnt);
   s.mh_flg = reinterpret_cast<uint32_t *>(b + L.mh_flg); s.mh_act = b + L.mh_act; s.mh_head = b + L.mh_head;
@@ -290,9 +292,9 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     mark("k_match");
     k_match<true><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
     mark("k_scan_counts");
-    k_scan_counts<<<1, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, r.totals);
+    k_scan_counts<<<1, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, sc.tile_orph, ntiles, r.totals);
     mark("k_place");
-    k_place<<<(n.n_pods + 1023) / 1024, 256, 0, M>>>(sc.keys[0], sc.keys[1], sc.cstart, sc.vals[0], n.n_pods);
+    k_place<<<(n.n_pods + 1023) / 1024, 256, 0, M>>>(sc.keys[0], sc.keys[1], sc.cstart, sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters);
   } else if (n.n_pods) {
     uint32_t bits = 1;
     while ((1ull << bits) <= n.n_clusters) bits++;  // keys are in [0, n_clusters]

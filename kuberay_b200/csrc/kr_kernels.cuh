@@ -79,6 +79,7 @@ struct ScratchDev {
   uint32_t *gcreate;                                           // [n_groups] dense n_create (input of the creates scan)
   uint32_t *mh_rep, *mh_name, *mh_meta, *mh_cnt, *mh_flg;      // multi-host scratch, indexed by sorted position
   uint8_t *mh_act, *mh_head;                                   // per position: action of a multi-host pod / first pod of a valid replica
+  uint32_t *tile_orph;                                         // fast pipeline: orphans per k_match tile -> exclusive prefix
   uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]
   uint32_t *deferred_list;                                     // clusters left for decide phase 1 (count in totals[4])
   int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
@@ -277,11 +278,30 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
 #pragma unroll
     for (int it = 0; it < kSortItems; it++) { wi[it] = hash_pair(ns[it], nm[it]) & sc.wt_mask; wk[it] = __ldg(&sc.wt_keys[wi[it]]); }
   }
-  uint32_t rank[kSortItems];
+  uint32_t rank[kSortItems], orank[kSortItems], woff = 0;
   if (kFast) {
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++)  // arrival rank inside the cluster's bucket (bucket n_clusters = orphans); 8 atomics in flight
-      rank[it] = (base + it * 32 < n.n_pods) ? atomicAdd(&sc.ccount[c[it]], 1u) : 0u;
+    for (int it = 0; it < kSortItems; it++)  // arrival rank inside the cluster's bucket; 8 atomics in flight
+      rank[it] = (base + it * 32 < n.n_pods && c[it] < n.n_clusters) ? atomicAdd(&sc.ccount[c[it]], 1u) : 0u;
+    // Orphans (no RayCluster) need no decision, only List order, and their bucket has no size bound: give them a STABLE rank
+    // right here — thread order inside a tile is pod order (warp, then item, then lane) — plus the tile's orphan count, which
+    // k_scan_counts turns into a per-tile prefix.  No atomics, no sort.
+    __shared__ uint32_t s_worph[kSortThreads / 32];
+    uint32_t wcount = 0;
+    const uint32_t ltm = lanemask_lt();
+#pragma unroll
+    for (int it = 0; it < kSortItems; it++) {  // (kept apart from rank[]: nothing here may wait for the atomics above)
+      bool orph = (base + it * 32 < n.n_pods) && c[it] == n.n_clusters;
+      uint32_t bal = __ballot_sync(0xFFFFFFFFu, orph);
+      orank[it] = wcount + __popc(bal & ltm);
+      wcount += __popc(bal);
+    }
+    if (lane == 0) s_worph[warp] = wcount;
+    __syncthreads();
+    uint32_t ttot = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kSortThreads / 32; w2++) { uint32_t v = s_worph[w2]; if (w2 < (int)warp) woff += v; ttot += v; }
+    if (threadIdx.x == 0) { sc.tile_orph[tile] = ttot; if (ttot) atomicAdd(&sc.ccount[n.n_clusters], ttot); }
   }
   // phase D: ray.io/group against the cluster's worker groups, workersToDelete-name intersection, outputs
 #pragma unroll
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
     }
     sc.rows[p] = make_uint4(nm[it], rn[it], ri[it], (slot << 16) | flags);
     sc.keys[0][p] = c[it];
-    if (kFast) sc.keys[1][p] = rank[it];
+    if (kFast) sc.keys[1][p] = (c[it] == n.n_clusters) ? orank[it] + woff : rank[it];
     else atomicAdd(&s_hist[c[it] & (kRadix - 1)], 1u);
   }
   if (!kFast) {
@@ -331,21 +351,20 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
 // Exclusive scan of the per-cluster pod counts (bucket n_clusters = orphans) -> cstart[0 .. n_clusters+1].
 // Flags buckets too large for the in-warp sort (the engine then re-runs the pass on the radix pipeline).
 #define KR_FAST_MAX_BUCKET 1024u
-__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict__ ccount, uint32_t *__restrict__ cstart, uint32_t nb, uint32_t *totals) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
+// One-block exclusive scan of n counters, 8 consecutive values per thread per sweep; returns the total (valid in thread 0..).
+__device__ __forceinline__ uint32_t block_scan_excl(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n, uint32_t big_limit,
+                                                    bool &big, uint32_t *s_warp, uint32_t *s_carry) {
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) s_carry = 0;
+  if (t == 0) *s_carry = 0;
   __syncthreads();
-  bool big = false;
-  for (uint32_t base = 0; base < nb; base += 8192) {
+  for (uint32_t base = 0; base < n; base += 8192) {
     uint32_t i0 = base + t * 8;
     uint32_t v[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (i0 + k < nb) ? ccount[i0 + k] : 0u;
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
     uint32_t sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { sum += v[k]; big |= v[k] > KR_FAST_MAX_BUCKET; }
+    for (int k = 0; k < 8; k++) { sum += v[k]; big |= (i0 + k < big_limit) && v[k] > KR_FAST_MAX_BUCKET; }
     uint32_t x = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
@@ -355,25 +374,42 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
     uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
-    uint32_t run = s_carry + woff + x - sum;
+    uint32_t run = *s_carry + woff + x - sum;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { if (i0 + k < nb) cstart[i0 + k] = run; run += v[k]; }
+    for (int k = 0; k < 8; k++) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
     __syncthreads();
-    if (t == 0) s_carry += total;
+    if (t == 0) *s_carry += total;
     __syncthreads();
   }
-  if (t == 0) cstart[nb] = s_carry;
+  return *s_carry;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict__ ccount, uint32_t *__restrict__ cstart, uint32_t nb,
+                                                      uint32_t *__restrict__ tile_orph, uint32_t ntiles, uint32_t *totals) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  bool big = false;
+  uint32_t tot = block_scan_excl(ccount, cstart, nb, nb - 1, big, s_warp, &s_carry);  // the last bucket (orphans) is exempt: it is never sorted
+  if (threadIdx.x == 0) cstart[nb] = tot;
   if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
+  bool dummy = false;
+  block_scan_excl(tile_orph, tile_orph, ntiles, 0, dummy, s_warp, &s_carry);  // orphans per tile -> orphans before the tile
 }
 
 // pod -> its slot in the cluster's bucket: cstart[cluster] + arrival rank (order inside a bucket is fixed up by the
 // in-warp sort in k_decide, so the result does not depend on the order the atomics landed in).
 __global__ void __launch_bounds__(256) k_place(const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
-                                               const uint32_t *__restrict__ cstart, uint32_t *__restrict__ out, uint32_t n) {
+                                               const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ tile_orph,
+                                               uint32_t *__restrict__ out, uint32_t n, uint32_t n_clusters) {
   uint32_t p = blockIdx.x * 1024 + threadIdx.x;
 #pragma unroll
   for (int k = 0; k < 4; k++, p += 256)
-    if (p < n) out[__ldg(&cstart[__ldg(&key[p])]) + __ldg(&rank[p])] = p;
+    if (p < n) {
+      uint32_t c = __ldg(&key[p]);
+      uint32_t pos = __ldg(&cstart[c]) + __ldg(&rank[p]);
+      if (c == n_clusters) pos += __ldg(&tile_orph[p / kSortTile]);  // orphans: already in List order, bucket of any size
+      out[pos] = p;
+    }
 }
 
 // Bitonic sort of 32*K values held K per lane (element g = lane*K + k); ascending.
@@ -1167,8 +1203,10 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
   const uint32_t P = seg1 - seg0;
   if (c == Nc) {  // the orphan bucket: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot
     if (a.phase != 0) return;
-    if (a.fast && P <= KR_FAST_MAX_BUCKET) { warp_sort_dispatch(a.unsorted + seg0, a.r.sorted_pod_idx + seg0, P, lane); __syncwarp(); }
-    for (uint32_t i = seg0 + lane; i < seg1; i += 32) a.r.sorted_action[i] = KR_ACT_ORPHAN;
+    for (uint32_t i = seg0 + lane; i < seg1; i += 32) {
+      if (a.fast) a.r.sorted_pod_idx[i] = LDG(a.unsorted[i]);  // k_match/k_place put the orphans in List order already
+      a.r.sorted_action[i] = KR_ACT_ORPHAN;
+    }
     if (lane == 0) a.r.totals[1] = P;
     return;
   }

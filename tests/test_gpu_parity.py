@@ -70,6 +70,20 @@ def test_parity_big_bucket_falls_back_to_radix(oracle_mod):
     _parity(snap, flags, oracle_mod)
 
 
+def test_many_orphans_stay_on_the_fast_pipeline(oracle_mod):
+    # 20 % of the pods name a RayCluster that is not in the snapshot: the orphan bucket (5000 pods) is ordered without a sort
+    snap, flags = synthetic.generate(synthetic.SynthParams(n_clusters=500, pods_per_cluster=50, groups=1, orphan_frac=0.2))
+    got = _parity(snap, flags, oracle_mod)
+    assert got.n_orphans == 5000
+    eng = Engine.for_snapshot(snap)
+    try:
+        eng.load(snap)
+        names = [k for k, _ in eng.reconcile_profiled(flags)["kernels"]]
+    finally:
+        eng.close()
+    assert "k_place" in names and "k_scatter" not in names
+
+
 def test_parity_radix_pipeline_forced(oracle_mod, monkeypatch):
     monkeypatch.setenv("KR_FORCE_RADIX", "1")
     snap, flags = synthetic.generate(synthetic.config("C2", groups=2))
