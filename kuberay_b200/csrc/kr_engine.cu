@@ -90,7 +90,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles;
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
@@ -120,6 +120,8 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.gcreate = o; o = align_up(o + 4 * (size_t)n.n_groups + 32);
   L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
+  L.chain = o;  // directly after ccount: one memset clears both
+  o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.ntiles / 8192 + (size_t)n.n_groups / 8192 + 8));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.ntiles + 8));
   L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -229,6 +231,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.gcreate = reinterpret_cast<uint32_t *>(b + L.gcreate);
   s.deferred_list = reinterpret_cast<uint32_t *>(b + L.deferred_list);
   s.ccount = reinterpret_cast<uint32_t *>(b + L.ccount);
+  s.chain = reinterpret_cast<uint32_t *>(b + L.chain);
   s.cstart = reinterpret_cast<uint32_t *>(b + L.cstart);
   s.tile_orph = reinterpret_cast<uint32_t *>(b + L.tile_orph);
   s.mh_rep = reinterpret_cast<uint32_t *>(b + L.mh_rep); s.mh_name = reinterpret_cast<uint32_t *>(b + L.mh_name);
@@ -288,11 +291,12 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   e->ran_fast = fast;
   const uint32_t *sorted_keys = sc.keys[0];
   if (n.n_pods && fast) {
-    CK(cudaMemsetAsync(sc.ccount, 0, 4 * ((size_t)n.n_clusters + 2), M));
+    CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));  // per-cluster counts + the chained-scan cells
     mark("k_match");
     k_match<true><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
     mark("k_scan_counts");
-    k_scan_counts<<<1, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, sc.tile_orph, ntiles, r.totals);
+    const uint32_t nch_c = (n.n_clusters + 1 + kScanChunk - 1) / kScanChunk, nch_t = (ntiles + kScanChunk - 1) / kScanChunk;
+    k_scan_counts<<<nch_c + nch_t, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, nch_c, sc.tile_orph, ntiles, sc.chain, r.totals);
     mark("k_place");
     k_place<<<(n.n_pods + 1023) / 1024, 256, 0, M>>>(sc.keys[0], sc.keys[1], sc.cstart, sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters);
   } else if (n.n_pods) {
@@ -313,6 +317,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     }
     sorted_keys = sc.keys[cur];
   } else if (fast) {
+    CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));
     CK(cudaMemsetAsync(sc.cstart, 0, 4 * ((size_t)n.n_clusters + 2), M));
   }
   DecideArgs da{s, sc, r, z, f, sorted_keys, sc.vals[0], fast ? 1 : 0, 0};
@@ -344,7 +349,10 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   }
   if (n.n_groups) {
     mark("k_scan_creates");
-    k_scan_creates<<<1, 1024, 0, M>>>(r, sc.gcreate, n.n_groups);
+    const uint32_t nch_g = (n.n_groups + kScanChunk - 1) / kScanChunk;
+    uint32_t *gchain = sc.chain + 2 * ((size_t)(n.n_clusters + 1 + kScanChunk - 1) / kScanChunk + (e->sl.ntiles + kScanChunk - 1) / kScanChunk);
+    if (e->force_radix) CK(cudaMemsetAsync(gchain, 0, 8 * (size_t)nch_g, M));  // (the fast pipeline cleared the cells together with ccount)
+    k_scan_creates<<<nch_g, 1024, 0, M>>>(r, sc.gcreate, n.n_groups, gchain);
     mark("k_create_fill");
     k_create_fill<<<(n.n_groups + 3) / 4, 128, 0, M>>>(s, sc, r, z, f, e->cfg.max_creates);
   }

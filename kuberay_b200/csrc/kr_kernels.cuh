@@ -80,6 +80,7 @@ struct ScratchDev {
   uint32_t *mh_rep, *mh_name, *mh_meta, *mh_cnt, *mh_flg;      // multi-host scratch, indexed by sorted position
   uint8_t *mh_act, *mh_head;                                   // per position: action of a multi-host pod / first pod of a valid replica
   uint32_t *tile_orph;                                         // fast pipeline: orphans per k_match tile -> exclusive prefix
+  uint32_t *chain;                                             // chained-scan hand-off cells {ready, carry} (zeroed with ccount)
   uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]
   uint32_t *deferred_list;                                     // clusters left for decide phase 1 (count in totals[4])
   int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
@@ -351,49 +352,74 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
 // Exclusive scan of the per-cluster pod counts (bucket n_clusters = orphans) -> cstart[0 .. n_clusters+1].
 // Flags buckets too large for the in-warp sort (the engine then re-runs the pass on the radix pipeline).
 #define KR_FAST_MAX_BUCKET 1024u
-// One-block exclusive scan of n counters, 8 consecutive values per thread per sweep; returns the total (valid in thread 0..).
-__device__ __forceinline__ uint32_t block_scan_excl(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n, uint32_t big_limit,
-                                                    bool &big, uint32_t *s_warp, uint32_t *s_carry) {
+// Chained multi-block exclusive scan: block `chunk` scans 8192 consecutive counters (8 per thread), waits for the inclusive
+// carry of block chunk-1, adds it and publishes its own.  Blocks are dispatched in index order, so a waiting block's
+// predecessor is always running or done.  v[] returns this thread's 8 exclusive prefixes; chain = {ready flag, carry} pairs,
+// zeroed before the launch.
+static constexpr uint32_t kScanChunk = 8192;
+__device__ __forceinline__ uint32_t chained_scan_chunk(const uint32_t *__restrict__ in, uint32_t n, uint32_t chunk, uint32_t *chain,
+                                                       uint32_t big_limit, bool &big, uint32_t (&excl)[8], uint32_t *s_warp, uint32_t *s_prefix) {
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) *s_carry = 0;
+  const uint32_t i0 = chunk * kScanChunk + t * 8;
+  uint32_t v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { sum += v[k]; big |= (i0 + k < big_limit) && v[k] > KR_FAST_MAX_BUCKET; }
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_warp[w] = x;
   __syncthreads();
-  for (uint32_t base = 0; base < n; base += 8192) {
-    uint32_t i0 = base + t * 8;
-    uint32_t v[8];
+  uint32_t wv = s_warp[lane], wx = wv;
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { sum += v[k]; big |= (i0 + k < big_limit) && v[k] > KR_FAST_MAX_BUCKET; }
-    uint32_t x = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
-    if (lane == 31) s_warp[w] = x;
-    __syncthreads();
-    uint32_t wv = s_warp[lane], wx = wv;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
-    uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
-    uint32_t run = *s_carry + woff + x - sum;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
-    __syncthreads();
-    if (t == 0) *s_carry += total;
-    __syncthreads();
+  for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
+  const uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
+  if (t == 0) {
+    uint32_t prefix = 0;
+    if (chunk > 0) {
+      volatile uint32_t *prev = chain + 2 * (size_t)(chunk - 1);
+      while (prev[0] == 0) {}
+      __threadfence();
+      prefix = prev[1];
+    }
+    chain[2 * (size_t)chunk + 1] = prefix + total;
+    __threadfence();
+    reinterpret_cast<volatile uint32_t *>(chain)[2 * (size_t)chunk] = 1;
+    *s_prefix = prefix;
   }
-  return *s_carry;
+  __syncthreads();
+  uint32_t run = *s_prefix + woff + x - sum;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { excl[k] = run; run += v[k]; }
+  return *s_prefix + total;  // inclusive carry after this chunk
 }
 
-__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict__ ccount, uint32_t *__restrict__ cstart, uint32_t nb,
-                                                      uint32_t *__restrict__ tile_orph, uint32_t ntiles, uint32_t *totals) {
+// Bucket starts: exclusive scan of the per-cluster pod counts (blocks [0, nchunks_c)) and of the per-tile orphan counts
+// (the remaining blocks).  Flags real clusters too large for the in-warp sort (the orphan bucket is exempt: it is never sorted).
+__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict__ ccount, uint32_t *__restrict__ cstart, uint32_t nb, uint32_t nchunks_c,
+                                                      uint32_t *__restrict__ tile_orph, uint32_t ntiles, uint32_t *chain, uint32_t *totals) {
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_prefix;
+  uint32_t excl[8];
   bool big = false;
-  uint32_t tot = block_scan_excl(ccount, cstart, nb, nb - 1, big, s_warp, &s_carry);  // the last bucket (orphans) is exempt: it is never sorted
-  if (threadIdx.x == 0) cstart[nb] = tot;
-  if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
-  bool dummy = false;
-  block_scan_excl(tile_orph, tile_orph, ntiles, 0, dummy, s_warp, &s_carry);  // orphans per tile -> orphans before the tile
+  if (blockIdx.x < nchunks_c) {
+    const uint32_t chunk = blockIdx.x;
+    uint32_t carry = chained_scan_chunk(ccount, nb, chunk, chain, nb - 1, big, excl, s_warp, &s_prefix);
+    const uint32_t i0 = chunk * kScanChunk + threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (i0 + k < nb) cstart[i0 + k] = excl[k];
+    if (chunk == nchunks_c - 1 && threadIdx.x == 0) cstart[nb] = carry;
+    if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
+  } else {
+    const uint32_t chunk = blockIdx.x - nchunks_c;
+    chained_scan_chunk(tile_orph, ntiles, chunk, chain + 2 * (size_t)nchunks_c, 0, big, excl, s_warp, &s_prefix);
+    __syncthreads();  // every thread of the block has read its inputs (in place)
+    const uint32_t i0 = chunk * kScanChunk + threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (i0 + k < ntiles) tile_orph[i0 + k] = excl[k];
+  }
 }
 
 // pod -> its slot in the cluster's bucket: cstart[cluster] + arrival rank (order inside a bucket is fixed up by the
@@ -1219,44 +1245,18 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
 
 // ------------------------------------------------------------------------------------------------ creates
 
-// exclusive scan of the dense n_create array -> groups[].create_off, total in totals[0].  One block; every thread
-// loads 8 consecutive counters per sweep (two 16-byte loads), so a sweep of 8192 groups costs one memory round trip.
-__global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, const uint32_t *__restrict__ gcreate, uint32_t n_groups) {
+// exclusive scan of the dense n_create array -> groups[].create_off, total in totals[0] (chained multi-block scan).
+__global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, const uint32_t *__restrict__ gcreate, uint32_t n_groups, uint32_t *chain) {
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t == 0) s_carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < n_groups; base += 8192) {
-    uint32_t i0 = base + t * 8;
-    uint32_t v[8];
-    if (i0 + 8 <= n_groups) {
-      uint4 a0 = *reinterpret_cast<const uint4 *>(gcreate + i0), a1 = *reinterpret_cast<const uint4 *>(gcreate + i0 + 4);
-      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-    } else {
+  __shared__ uint32_t s_prefix;
+  uint32_t excl[8];
+  bool big = false;
+  const uint32_t chunk = blockIdx.x;
+  uint32_t carry = chained_scan_chunk(gcreate, n_groups, chunk, chain, 0, big, excl, s_warp, &s_prefix);
+  const uint32_t i0 = chunk * kScanChunk + threadIdx.x * 8;
 #pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = (i0 + k < n_groups) ? gcreate[i0 + k] : 0u;
-    }
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) sum += v[k];
-    uint32_t x = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
-    if (lane == 31) s_warp[w] = x;
-    __syncthreads();
-    uint32_t wv = s_warp[lane], wx = wv;  // every warp scans the 32 warp sums redundantly
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
-    uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
-    uint32_t run = s_carry + woff + x - sum;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { if (i0 + k < n_groups) r.groups[i0 + k].create_off = run; run += v[k]; }
-    __syncthreads();
-    if (t == 0) s_carry += total;
-    __syncthreads();
-  }
-  if (t == 0) r.totals[0] = s_carry;
+  for (int k = 0; k < 8; k++) if (i0 + k < n_groups) r.groups[i0 + k].create_off = excl[k];
+  if (chunk == gridDim.x - 1 && threadIdx.x == 0) r.totals[0] = carry;
 }
 
 // Lowest free ray.io/worker-group-replica-index values for the pods to create (raycluster_controller.go:854-881).
