@@ -167,6 +167,7 @@ struct kr_engine {
   bool force_radix = false;   // sticky per layout: set when a pass met a bucket the fast pipeline cannot sort
   bool ran_fast = false;
   bool h2d_timed = true;      // h2d_ms of the last commit has been read back from its events
+  bool no_fuse = false;       // KR_NO_FUSE=1: always take the separate scan kernels (tests; large snapshots take them anyway)
   bool env_radix = false;     // KR_FORCE_RADIX=1: always take the general pipeline (tests)
   uint32_t *h_totals = nullptr;  // pinned copy of the device totals (pipeline fallback check)
 };
@@ -294,11 +295,18 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));  // per-cluster counts + the chained-scan cells
     mark("k_match");
     k_match<true><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+    const bool fuse_place = !e->no_fuse && (uint64_t)n.n_clusters + 2 + ntiles <= kFusedMaxCounters;
+    if (fuse_place) {
+      mark("k_place_fused");
+      size_t smem = 4 * ((size_t)n.n_clusters + 2 + ntiles);
+      k_place_fused<<<e->sm_count * 2, 1024, smem, M>>>(sc.keys[0], sc.keys[1], sc.ccount, sc.cstart, sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters, ntiles, r.totals);
+    } else {
     mark("k_scan_counts");
     const uint32_t nch_c = (n.n_clusters + 1 + kScanChunk - 1) / kScanChunk, nch_t = (ntiles + kScanChunk - 1) / kScanChunk;
     k_scan_counts<<<nch_c + nch_t, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, nch_c, sc.tile_orph, ntiles, sc.chain, r.totals);
     mark("k_place");
     k_place<<<(n.n_pods + 1023) / 1024, 256, 0, M>>>(sc.keys[0], sc.keys[1], sc.cstart, sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters);
+    }
   } else if (n.n_pods) {
     uint32_t bits = 1;
     while ((1ull << bits) <= n.n_clusters) bits++;  // keys are in [0, n_clusters]
@@ -347,7 +355,10 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     mark("k_decide_phase1");
     k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
   }
-  if (n.n_groups) {
+  if (n.n_groups && !e->no_fuse && n.n_groups <= kFusedMaxCounters) {
+    mark("k_creates_fused");
+    k_creates_fused<<<e->sm_count, 1024, 4 * (size_t)n.n_groups, M>>>(s, sc, r, z, f, e->cfg.max_creates);
+  } else if (n.n_groups) {
     mark("k_scan_creates");
     const uint32_t nch_g = (n.n_groups + kScanChunk - 1) / kScanChunk;
     uint32_t *gchain = sc.chain + 2 * ((size_t)(n.n_clusters + 1 + kScanChunk - 1) / kScanChunk + (e->sl.ntiles + kScanChunk - 1) / kScanChunk);
@@ -477,8 +488,11 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaMalloc((void **)&e->d_in, e->in_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_scratch, e->scratch_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
+  cudaFuncSetAttribute(k_place_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
+  cudaFuncSetAttribute(k_creates_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
   if (const char *g = getenv("KR_FORCE_RADIX")) e->env_radix = (g[0] == '1');
+  if (const char *g = getenv("KR_NO_FUSE")) e->no_fuse = (g[0] == '1');
   e->force_radix = e->env_radix;
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   *out = e;

@@ -1261,16 +1261,13 @@ __global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, const uint32_t 
 
 // Lowest free ray.io/worker-group-replica-index values for the pods to create (raycluster_controller.go:854-881).
 // One warp per group; candidate indices are swept in windows of 1024 bits held in shared memory.
-__global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, ResDev r, Sizes n, kr_flags f, uint32_t create_cap) {
-  __shared__ uint32_t s_bits[4][32];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t g = blockIdx.x * 4 + warp;
-  if (g >= n.n_groups) return;
+__device__ __forceinline__ void create_fill_group(const SnapDev &s, const ScratchDev &sc, const ResDev &r, const kr_flags &f, uint32_t g,
+                                                  uint32_t create_off, uint32_t create_cap, uint32_t *s_bits /* [32] per warp */, uint32_t lane) {
   const kr_group_result gr = r.groups[g];
   if (gr.n_create == 0) return;
   const bool mh = (gr.flags & KR_GR_MULTIHOST) != 0;  // multi-host: in-use indices = label of the first pod of every valid replica (:1067-1077)
-  if ((uint64_t)gr.create_off + gr.n_create > create_cap) return;  // host reports KR_E_CAPACITY from totals[0]
-  int32_t *out = r.create_idx + gr.create_off;
+  if ((uint64_t)create_off + gr.n_create > create_cap) return;  // host reports KR_E_CAPACITY from totals[0]
+  int32_t *out = r.create_idx + create_off;
   if (!f.gate_multihost_indexing) {  // createWorkerPod without an index (:884-889)
     for (uint32_t k = lane; k < gr.n_create; k += 32) out[k] = -1;
     return;
@@ -1282,7 +1279,7 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
   const uint64_t bound = (uint64_t)gr.n_running + gr.n_create;  // the n_create lowest free indices all lie below this
   uint32_t written = 0;
   for (uint64_t w0 = 0; w0 < bound && written < gr.n_create; w0 += 1024) {
-    s_bits[warp][lane] = 0;
+    s_bits[lane] = 0;
     __syncwarp();
     for (uint32_t b = seg0; b < seg1; b += 32) {
       uint32_t i = b + lane;
@@ -1291,12 +1288,12 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
         if ((row.w >> 16) == slot && (row.w & KR_PP_HAS_REPLICA_IDX)) {
           int32_t idx = (int32_t)row.z;
           if (idx >= 0 && (uint64_t)idx >= w0 && (uint64_t)idx < w0 + 1024 && (uint64_t)idx < bound)
-            atomicOr(&s_bits[warp][(idx - w0) >> 5], 1u << ((idx - w0) & 31));
+            atomicOr(&s_bits[(idx - w0) >> 5], 1u << ((idx - w0) & 31));
         }
       }
     }
     __syncwarp();
-    uint32_t word = s_bits[warp][lane];
+    uint32_t word = s_bits[lane];
     uint64_t wbase = w0 + 32ull * lane;
     uint32_t freeb = ~word;
     if (wbase >= bound) freeb = 0;
@@ -1313,6 +1310,97 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
     written += __shfl_sync(0xFFFFFFFFu, x, 31);
     __syncwarp();
   }
+}
+
+__global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, ResDev r, Sizes n, kr_flags f, uint32_t create_cap) {
+  __shared__ uint32_t s_bits[4][32];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * 4 + warp;
+  if (g >= n.n_groups) return;
+  create_fill_group(s, sc, r, f, g, r.groups[g].create_off, create_cap, s_bits[warp], lane);
+}
+
+// ---- fused variants for snapshots whose per-cluster / per-group counters fit in shared memory: every block scans the counters
+// itself (a few tens of KB out of L2) instead of waiting for a scan kernel, which removes two ~10 us stages from the chain.
+static constexpr uint32_t kFusedMaxCounters = 48 * 1024;  // 192 KB of shared memory
+
+// exclusive scan of in[0..n) into shared memory by the whole block (any block size that is a multiple of 32, <= 1024)
+__device__ __forceinline__ uint32_t block_scan_to_smem(const uint32_t *__restrict__ in, uint32_t n, uint32_t *out_sm, uint32_t big_limit, bool &big,
+                                                       uint32_t *s_warp, uint32_t *s_carry) {
+  const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  if (t == 0) *s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += blockDim.x * 8) {
+    uint32_t i0 = base + t * 8;
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? __ldg(&in[i0 + k]) : 0u;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { sum += v[k]; big |= (i0 + k < big_limit) && v[k] > KR_FAST_MAX_BUCKET; }
+    uint32_t x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t wv = lane < nw ? s_warp[lane] : 0u, wx = wv;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wx, d); if (lane >= d) wx += y; }
+    uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
+    uint32_t run = *s_carry + woff + x - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (i0 + k < n) out_sm[i0 + k] = run; run += v[k]; }
+    __syncthreads();
+    if (t == 0) *s_carry += total;
+    __syncthreads();
+  }
+  return *s_carry;
+}
+
+// bucket starts + placement in one persistent kernel (replaces k_scan_counts + k_place)
+__global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ ccount,
+                                                      uint32_t *__restrict__ cstart, const uint32_t *__restrict__ tile_orph, uint32_t *__restrict__ out,
+                                                      uint32_t n, uint32_t n_clusters, uint32_t ntiles, uint32_t *totals) {
+  extern __shared__ uint32_t sm_dyn[];
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  uint32_t *sm_start = sm_dyn;                    // [n_clusters + 2]
+  uint32_t *sm_orph = sm_dyn + n_clusters + 2;    // [ntiles]
+  const uint32_t nb = n_clusters + 1;
+  bool big = false, dummy = false;
+  uint32_t tot = block_scan_to_smem(ccount, nb, sm_start, nb - 1, big, s_warp, &s_carry);
+  if (threadIdx.x == 0) sm_start[nb] = tot;
+  block_scan_to_smem(tile_orph, ntiles, sm_orph, 0, dummy, s_warp, &s_carry);
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (uint32_t i = threadIdx.x; i <= nb; i += blockDim.x) cstart[i] = sm_start[i];
+    if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
+  }
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    uint32_t c = __ldg(&key[p]);
+    uint32_t pos = sm_start[c] + __ldg(&rank[p]);
+    if (c == n_clusters) pos += sm_orph[p / kSortTile];
+    out[pos] = p;
+  }
+}
+
+// create offsets + replica-index allocation in one persistent kernel (replaces k_scan_creates + k_create_fill)
+__global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc, ResDev r, Sizes n, kr_flags f, uint32_t create_cap) {
+  extern __shared__ uint32_t sm_dyn[];
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_bits[32][32];
+  uint32_t *sm_off = sm_dyn;  // [n_groups]
+  bool dummy = false;
+  uint32_t tot = block_scan_to_smem(sc.gcreate, n.n_groups, sm_off, 0, dummy, s_warp, &s_carry);
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (uint32_t g = threadIdx.x; g < n.n_groups; g += blockDim.x) r.groups[g].create_off = sm_off[g];
+    if (threadIdx.x == 0) r.totals[0] = tot;
+  }
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (uint32_t g = blockIdx.x * nw + warp; g < n.n_groups; g += gridDim.x * nw)
+    if (__ldg(&sc.gcreate[g])) create_fill_group(s, sc, r, f, g, sm_off[g], create_cap, s_bits[warp], lane);
 }
 
 // ------------------------------------------------------------------------------------------------ k_jobs
