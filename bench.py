@@ -30,6 +30,22 @@ METRIC = "reconciles/sec over 10k RayCluster x 100 pods (batched reconcilePods +
 UNIT = "reconciles/s"
 
 
+def _ncu_traffic(kernel: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture of
+    this same command (profiles/r1_ncu_full_c3.json; C3 only) — None when no capture matches."""
+    if workload != "C3":
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_c3.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        return None
+    for name, d in prof.items():
+        if name.startswith(kernel):
+            return int((d["dram_rd_MB"] + d["dram_wr_MB"]) * 1e6)
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -40,51 +56,54 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the GPU legs (B200_PROFILING.md recipe).  Sampled through NVML (same counters as
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`) every 2 ms from a thread, because the timed
+    region lasts tens of milliseconds and nvidia-smi's own loop cannot tick faster than ~100 ms."""
 
     def __init__(self, device: int):
         self.device = device
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[int, int]] = []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.device]) if vis and vis.split(",")[self.device].isdigit() else self.device
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def pump():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self._t = threading.Thread(target=pump, daemon=True)
+            self._t.start()
+        except Exception as ex:  # noqa: BLE001
+            self.err = str(ex)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self._stop.set()
+        self._t.join(timeout=1)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        seen = set()
+        for _, r in self.samples:
+            for name, bit in bits.items():
+                if r & bit:
+                    seen.add(name)
+        mhz = [m for m, _ in self.samples]
+        # "under load" = samples at or above half the maximum clock (idle gaps between legs sit at the idle clock)
+        load = [m for m in mhz if self.max_mhz and m >= 0.5 * self.max_mhz] or mhz
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(seen), "samples": len(mhz)}
 
 
 def build_workload(name: str, rank: int, world: int):
@@ -284,7 +303,7 @@ def main():
         dom_ms = kavg[dom] if dom == "k_hash" else non_hash_ms
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom if dom == "k_hash" else "match->sort->decide pipeline", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_ms": dom_ms,
+                "frac": ach / peak, "traffic": _ncu_traffic("k_hash2" if dom == "k_hash" else dom, args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_ms": dom_ms,
                 "note": "k_hash is INT32-issue/latency bound (SHA-1 is a serial chain per message; 80 rounds per 64 B), HBM is its secondary bound" if dom == "k_hash" else ""}
         kernels = {k: round(v, 5) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
         line = {

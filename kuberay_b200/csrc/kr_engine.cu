@@ -163,6 +163,7 @@ struct kr_engine {
   kr_flags gflags{};
   bool gvalid = false;
   bool use_graph = true;
+  bool use_pdl = true;        // KR_NO_PDL=1 disables programmatic dependent launch
   // pipeline choice: fast = count/place/in-warp sort (every bucket <= 1024 pods); radix = general stable LSD sort.
   bool force_radix = false;   // sticky per layout: set when a pass met a bucket the fast pipeline cannot sort
   bool ran_fast = false;
@@ -241,6 +242,18 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   return s;
 }
 
+// Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait / pdl_trigger in kr_kernels.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // Launches the whole pass.  profile: serialise everything on stream M and bracket each kernel with events.
 int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = false) {
   const kr_sizes &n = e->sizes;
@@ -283,6 +296,10 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   CK(cudaMemsetAsync(e->d_scratch, 0xFF, e->sl.ff_total, M));
   if (n.n_wtd) CK(cudaMemsetAsync(r.wtd_pod_idx, 0xFF, 4 * (size_t)n.n_wtd, M));
   CK(cudaMemsetAsync(r.totals, 0, 32, M));
+  const bool pdl = !profile && e->use_pdl;
+  bool fuse_place_done = false;    // k_decide_small directly follows k_place_fused on stream M
+  bool creates_after_kernel = false;  // k_creates_fused directly follows a kernel on stream M (no event wait in between)
+  if (!e->force_radix) CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));  // per-cluster counts + the chained-scan cells
   {
     uint32_t items = n.n_clusters + n.n_groups + n.n_heads;
     if (items) { mark("k_build_tables"); k_build_tables<<<(items + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
@@ -292,14 +309,15 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   e->ran_fast = fast;
   const uint32_t *sorted_keys = sc.keys[0];
   if (n.n_pods && fast) {
-    CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));  // per-cluster counts + the chained-scan cells
     mark("k_match");
-    k_match<true><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+    CK(launch_pdl(k_match<true>, dim3(ntiles), dim3(kSortThreads), 0, M, pdl, s, sc, r, z, n.n_wtd ? 1 : 0));
     const bool fuse_place = !e->no_fuse && (uint64_t)n.n_clusters + 2 + ntiles <= kFusedMaxCounters;
     if (fuse_place) {
+      fuse_place_done = true;
       mark("k_place_fused");
       size_t smem = 4 * ((size_t)n.n_clusters + 2 + ntiles);
-      k_place_fused<<<e->sm_count * 2, 1024, smem, M>>>(sc.keys[0], sc.keys[1], sc.ccount, sc.cstart, sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters, ntiles, r.totals);
+      CK(launch_pdl(k_place_fused, dim3(e->sm_count * 2), dim3(1024), smem, M, pdl, (const uint32_t *)sc.keys[0], (const uint32_t *)sc.keys[1], (const uint32_t *)sc.ccount, sc.cstart,
+                    (const uint32_t *)sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters, ntiles, r.totals));
     } else {
     mark("k_scan_counts");
     const uint32_t nch_c = (n.n_clusters + 1 + kScanChunk - 1) / kScanChunk, nch_t = (ntiles + kScanChunk - 1) / kScanChunk;
@@ -325,7 +343,6 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     }
     sorted_keys = sc.keys[cur];
   } else if (fast) {
-    CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));
     CK(cudaMemsetAsync(sc.cstart, 0, 4 * ((size_t)n.n_clusters + 2), M));
   }
   DecideArgs da{s, sc, r, z, f, sorted_keys, sc.vals[0], fast ? 1 : 0, 0};
@@ -338,7 +355,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, G2>>>(da);
     if (fast && n.n_clusters) {
       mark("k_decide_small");
-      k_decide_small<<<(n.n_clusters + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
+      CK(launch_pdl(k_decide_small, dim3((n.n_clusters + kDecideWarps - 1) / kDecideWarps), dim3(kDecideWarps * 32), 0, M, pdl && fuse_place_done, da));
     }
     if (fast && !profile) { CK(cudaEventRecord(e->ev_join2, G2)); CK(cudaStreamWaitEvent(M, e->ev_join2, 0)); }
   }
@@ -354,10 +371,11 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     uint32_t warps = e->n_recreate;  // upper bound on the deferred list
     mark("k_decide_phase1");
     k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
+    creates_after_kernel = true;
   }
   if (n.n_groups && !e->no_fuse && n.n_groups <= kFusedMaxCounters) {
     mark("k_creates_fused");
-    k_creates_fused<<<e->sm_count, 1024, 4 * (size_t)n.n_groups, M>>>(s, sc, r, z, f, e->cfg.max_creates);
+    CK(launch_pdl(k_creates_fused, dim3(e->sm_count), dim3(1024), 4 * (size_t)n.n_groups, M, pdl && creates_after_kernel, s, sc, r, z, f, e->cfg.max_creates));
   } else if (n.n_groups) {
     mark("k_scan_creates");
     const uint32_t nch_g = (n.n_groups + kScanChunk - 1) / kScanChunk;
@@ -493,6 +511,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
   if (const char *g = getenv("KR_FORCE_RADIX")) e->env_radix = (g[0] == '1');
   if (const char *g = getenv("KR_NO_FUSE")) e->no_fuse = (g[0] == '1');
+  if (const char *g = getenv("KR_NO_PDL")) e->use_pdl = !(g[0] == '1');
   e->force_radix = e->env_radix;
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   *out = e;

@@ -119,6 +119,12 @@ __device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) { return m
 #define KR_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define KR_EMPTY32 0xFFFFFFFFu
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may be scheduled while
+// its stream predecessor is still running; it must not touch the predecessor's outputs before pdl_wait().  Both are no-ops
+// for ordinary launches.  pdl_trigger() lets the NEXT kernel in the chain be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 __device__ __forceinline__ uint32_t pp_node_type(uint32_t f) { return (f >> KR_PP_NODE_TYPE_SHIFT) & 3u; }
@@ -231,6 +237,7 @@ __device__ __forceinline__ int32_t aux_lookup(const ScratchDev &sc, uint32_t p) 
 template <bool kFast>
 __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc, ResDev r, Sizes n, int has_wtd) {
   __shared__ uint32_t s_hist[kRadix];
+  pdl_wait(); pdl_trigger();
   const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!kFast) { s_hist[threadIdx.x] = 0; __syncthreads(); }
@@ -1200,6 +1207,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_small(DecideArgs a
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t c = blockIdx.x * kDecideWarps + warp;
+  pdl_wait(); pdl_trigger();
   if (c >= a.n.n_clusters) return;
   const uint32_t seg0 = LDG(a.sc.cstart[c]), seg1 = LDG(a.sc.cstart[c + 1]);
   const uint32_t P = seg1 - seg0;
@@ -1364,6 +1372,7 @@ __global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict
   extern __shared__ uint32_t sm_dyn[];
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
+  pdl_wait(); pdl_trigger();
   uint32_t *sm_start = sm_dyn;                    // [n_clusters + 2]
   uint32_t *sm_orph = sm_dyn + n_clusters + 2;    // [ntiles]
   const uint32_t nb = n_clusters + 1;
@@ -1390,6 +1399,7 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_bits[32][32];
+  pdl_wait(); pdl_trigger();
   uint32_t *sm_off = sm_dyn;  // [n_groups]
   bool dummy = false;
   uint32_t tot = block_scan_to_smem(sc.gcreate, n.n_groups, sm_off, 0, dummy, s_warp, &s_carry);
