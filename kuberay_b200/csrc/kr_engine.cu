@@ -91,7 +91,7 @@ struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
   size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
-  uint32_t cl_slots, wt_slots, aux_slots, ntiles;
+  uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
   ScratchLayout L;
@@ -100,6 +100,8 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.aux_slots = pow2_at_least(2ull * n.n_heads);
   L.ntiles = (uint32_t)((n.n_pods + kSortTile - 1) / kSortTile);
   if (L.ntiles == 0) L.ntiles = 1;
+  L.mtiles = (uint32_t)((n.n_pods + kMatchTile - 1) / kMatchTile);
+  if (L.mtiles == 0) L.mtiles = 1;
   size_t o = 0;
   L.cl_slots_off = o; o = align_up(o + 16 * (size_t)L.cl_slots);
   L.wt_keys = o; o = align_up(o + 8 * (size_t)L.wt_slots);
@@ -121,9 +123,9 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.chain = o;  // directly after ccount: one memset clears both
-  o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.ntiles / 8192 + (size_t)n.n_groups / 8192 + 8));
+  o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.mtiles / 8192 + (size_t)n.n_groups / 8192 + 8));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
-  L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.ntiles + 8));
+  L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.mtiles + 8));
   L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.mh_name = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.mh_meta = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -310,18 +312,19 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   const uint32_t *sorted_keys = sc.keys[0];
   if (n.n_pods && fast) {
     mark("k_match");
-    CK(launch_pdl(k_match<true>, dim3(ntiles), dim3(kSortThreads), 0, M, pdl, s, sc, r, z, n.n_wtd ? 1 : 0));
-    const bool fuse_place = !e->no_fuse && (uint64_t)n.n_clusters + 2 + ntiles <= kFusedMaxCounters;
+    const uint32_t mtiles = e->sl.mtiles;
+    CK(launch_pdl(k_match<true, kMatchItems>, dim3(mtiles), dim3(kSortThreads), 0, M, pdl, s, sc, r, z, n.n_wtd ? 1 : 0));
+    const bool fuse_place = !e->no_fuse && (uint64_t)n.n_clusters + 2 + mtiles <= kFusedMaxCounters;
     if (fuse_place) {
       fuse_place_done = true;
       mark("k_place_fused");
-      size_t smem = 4 * ((size_t)n.n_clusters + 2 + ntiles);
+      size_t smem = 4 * ((size_t)n.n_clusters + 2 + mtiles);
       CK(launch_pdl(k_place_fused, dim3(e->sm_count * 2), dim3(1024), smem, M, pdl, (const uint32_t *)sc.keys[0], (const uint32_t *)sc.keys[1], (const uint32_t *)sc.ccount, sc.cstart,
-                    (const uint32_t *)sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters, ntiles, r.totals));
+                    (const uint32_t *)sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters, mtiles, r.totals));
     } else {
     mark("k_scan_counts");
-    const uint32_t nch_c = (n.n_clusters + 1 + kScanChunk - 1) / kScanChunk, nch_t = (ntiles + kScanChunk - 1) / kScanChunk;
-    k_scan_counts<<<nch_c + nch_t, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, nch_c, sc.tile_orph, ntiles, sc.chain, r.totals);
+    const uint32_t nch_c = (n.n_clusters + 1 + kScanChunk - 1) / kScanChunk, nch_t = (mtiles + kScanChunk - 1) / kScanChunk;
+    k_scan_counts<<<nch_c + nch_t, 1024, 0, M>>>(sc.ccount, sc.cstart, n.n_clusters + 1, nch_c, sc.tile_orph, mtiles, sc.chain, r.totals);
     mark("k_place");
     k_place<<<(n.n_pods + 1023) / 1024, 256, 0, M>>>(sc.keys[0], sc.keys[1], sc.cstart, sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters);
     }
@@ -330,7 +333,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     while ((1ull << bits) <= n.n_clusters) bits++;  // keys are in [0, n_clusters]
     const int passes = (int)((bits + kRadixBits - 1) / kRadixBits);
     mark("k_match");
-    k_match<false><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+    k_match<false, kSortItems><<<ntiles, kSortThreads, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
     int cur = 0;
     for (int p = 0; p < passes; p++) {
       if (p > 0) { mark("k_hist"); k_hist<<<ntiles, kSortThreads, 0, M>>>(sc.keys[cur], sc.hist, n.n_pods, p * kRadixBits); }
@@ -379,7 +382,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   } else if (n.n_groups) {
     mark("k_scan_creates");
     const uint32_t nch_g = (n.n_groups + kScanChunk - 1) / kScanChunk;
-    uint32_t *gchain = sc.chain + 2 * ((size_t)(n.n_clusters + 1 + kScanChunk - 1) / kScanChunk + (e->sl.ntiles + kScanChunk - 1) / kScanChunk);
+    uint32_t *gchain = sc.chain + 2 * ((size_t)(n.n_clusters + 1 + kScanChunk - 1) / kScanChunk + (e->sl.mtiles + kScanChunk - 1) / kScanChunk);
     if (e->force_radix) CK(cudaMemsetAsync(gchain, 0, 8 * (size_t)nch_g, M));  // (the fast pipeline cleared the cells together with ccount)
     k_scan_creates<<<nch_g, 1024, 0, M>>>(r, sc.gcreate, n.n_groups, gchain);
     mark("k_create_fill");

@@ -100,6 +100,8 @@ struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
 static constexpr int kSortThreads = 256;
 static constexpr int kSortItems = 8;
 static constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per tile
+static constexpr int kMatchItems = 2;                        // fast pipeline: pods per thread in k_match (tile = 512 pods; occupancy beats per-thread ILP here: 8/4/2/1 items -> 47/40/33/33 us at C3)
+static constexpr int kMatchTile = kSortThreads * kMatchItems;
 static constexpr int kRadixBits = 8;
 static constexpr int kRadix = 1 << kRadixBits;
 
@@ -234,18 +236,18 @@ __device__ __forceinline__ int32_t aux_lookup(const ScratchDev &sc, uint32_t p) 
 // kFast: the count/place/sort-in-warp pipeline (per-cluster arrival rank by a returning atomic, no radix histogram).
 // The loop is phased — all column loads, then all table probes, then all record loads — so that each thread keeps
 // 8 independent memory requests in flight per phase instead of walking one pod's dependent chain at a time.
-template <bool kFast>
+template <bool kFast, int kItems>
 __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc, ResDev r, Sizes n, int has_wtd) {
   __shared__ uint32_t s_hist[kRadix];
   pdl_wait(); pdl_trigger();
   const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!kFast) { s_hist[threadIdx.x] = 0; __syncthreads(); }
-  const uint32_t base = tile * kSortTile + warp * (32 * kSortItems) + lane;
-  uint32_t ns[kSortItems], cn[kSortItems], gn[kSortItems], nm[kSortItems], pk[kSortItems], rn[kSortItems], ri[kSortItems];
+  const uint32_t base = tile * (kSortThreads * kItems) + warp * (32 * kItems) + lane;
+  uint32_t ns[kItems], cn[kItems], gn[kItems], nm[kItems], pk[kItems], rn[kItems], ri[kItems];
   // phase A: 7 coalesced column loads per pod
 #pragma unroll
-  for (int it = 0; it < kSortItems; it++) {
+  for (int it = 0; it < kItems; it++) {
     uint32_t p = base + it * 32;
     bool v = p < n.n_pods;
     ns[it] = v ? __ldg(&s.p_ns_id[p]) : 0u; cn[it] = v ? __ldg(&s.p_cluster_name_id[p]) : 0u;
@@ -254,15 +256,15 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
     rn[it] = v ? __ldg(&s.p_replica_name_id[p]) : 0u;
   }
   // phase B: hash-join probe (namespace, ray.io/cluster) -> cluster idx; first slot of every pod in flight together
-  uint32_t c[kSortItems], pi[kSortItems];
-  uint4 sl[kSortItems];
+  uint32_t c[kItems], pi[kItems];
+  uint4 sl[kItems];
 #pragma unroll
-  for (int it = 0; it < kSortItems; it++) {
+  for (int it = 0; it < kItems; it++) {
     pi[it] = hash_pair(ns[it], cn[it]) & sc.cl_mask;
     sl[it] = __ldg(&sc.cl_slots[pi[it]]);
   }
 #pragma unroll
-  for (int it = 0; it < kSortItems; it++) {
+  for (int it = 0; it < kItems; it++) {
     c[it] = n.n_clusters;
     if (cn[it] != 0) {
       uint4 q = sl[it];
@@ -276,20 +278,20 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
     }
   }
   // phase C: the cluster's group record
-  uint4 rec[kSortItems];
+  uint4 rec[kItems];
 #pragma unroll
-  for (int it = 0; it < kSortItems; it++) rec[it] = (c[it] < n.n_clusters) ? __ldg(&sc.cl_rec[c[it]]) : make_uint4(0, 0, 0, 0);
+  for (int it = 0; it < kItems; it++) rec[it] = (c[it] < n.n_clusters) ? __ldg(&sc.cl_rec[c[it]]) : make_uint4(0, 0, 0, 0);
   // phase C': first probe of the (tiny, cache-resident) workersToDelete-name table for every pod, and the bucket ranks
-  uint32_t wi[kSortItems];
-  uint64_t wk[kSortItems];
+  uint32_t wi[kItems];
+  uint64_t wk[kItems];
   if (has_wtd) {
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) { wi[it] = hash_pair(ns[it], nm[it]) & sc.wt_mask; wk[it] = __ldg(&sc.wt_keys[wi[it]]); }
+    for (int it = 0; it < kItems; it++) { wi[it] = hash_pair(ns[it], nm[it]) & sc.wt_mask; wk[it] = __ldg(&sc.wt_keys[wi[it]]); }
   }
-  uint32_t rank[kSortItems], orank[kSortItems], woff = 0;
+  uint32_t rank[kItems], orank[kItems], woff = 0;
   if (kFast) {
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++)  // arrival rank inside the cluster's bucket; 8 atomics in flight
+    for (int it = 0; it < kItems; it++)  // arrival rank inside the cluster's bucket; 8 atomics in flight
       rank[it] = (base + it * 32 < n.n_pods && c[it] < n.n_clusters) ? atomicAdd(&sc.ccount[c[it]], 1u) : 0u;
     // Orphans (no RayCluster) need no decision, only List order, and their bucket has no size bound: give them a STABLE rank
     // right here — thread order inside a tile is pod order (warp, then item, then lane) — plus the tile's orphan count, which
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
     uint32_t wcount = 0;
     const uint32_t ltm = lanemask_lt();
 #pragma unroll
-    for (int it = 0; it < kSortItems; it++) {  // (kept apart from rank[]: nothing here may wait for the atomics above)
+    for (int it = 0; it < kItems; it++) {  // (kept apart from rank[]: nothing here may wait for the atomics above)
       bool orph = (base + it * 32 < n.n_pods) && c[it] == n.n_clusters;
       uint32_t bal = __ballot_sync(0xFFFFFFFFu, orph);
       orank[it] = wcount + __popc(bal & ltm);
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
   }
   // phase D: ray.io/group against the cluster's worker groups, workersToDelete-name intersection, outputs
 #pragma unroll
-  for (int it = 0; it < kSortItems; it++) {
+  for (int it = 0; it < kItems; it++) {
     uint32_t p = base + it * 32;
     if (p >= n.n_pods) continue;
     uint32_t slot = KR_ROW_NO_GROUP, g0 = rec[it].x;
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(256) k_place(const uint32_t *__restrict__ key,
     if (p < n) {
       uint32_t c = __ldg(&key[p]);
       uint32_t pos = __ldg(&cstart[c]) + __ldg(&rank[p]);
-      if (c == n_clusters) pos += __ldg(&tile_orph[p / kSortTile]);  // orphans: already in List order, bucket of any size
+      if (c == n_clusters) pos += __ldg(&tile_orph[p / kMatchTile]);  // orphans: already in List order, bucket of any size
       out[pos] = p;
     }
 }
@@ -1202,7 +1204,7 @@ __device__ __forceinline__ bool small_path(const DecideArgs &a, uint32_t c, uint
 }
 
 // Common case: one warp per RayCluster with <= 256 pods, everything after the bucket load stays in registers.
-__global__ void __launch_bounds__(kDecideWarps * 32) k_decide_small(DecideArgs a) {
+__global__ void __launch_bounds__(kDecideWarps * 32, 8) k_decide_small(DecideArgs a) {
   __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1388,7 +1390,7 @@ __global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
     uint32_t c = __ldg(&key[p]);
     uint32_t pos = sm_start[c] + __ldg(&rank[p]);
-    if (c == n_clusters) pos += sm_orph[p / kSortTile];
+    if (c == n_clusters) pos += sm_orph[p / kMatchTile];
     out[pos] = p;
   }
 }
