@@ -380,8 +380,15 @@ void kr_engine_destroy(kr_engine *e);
  * r.Get / cached r.List reads (raycluster_controller.go:114,674,761,1583; common/association.go:83-130,184). */
 int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out);
 
-/* Upload the filled snapshot (host -> HBM, async on the engine stream, then synchronised). */
+/* Upload the filled snapshot (host -> HBM).  Asynchronous: the copies are queued on the engine's copy stream and the next
+ * pass waits for them on the device; the arenas must not be rewritten before that pass (or kr_snapshot_begin) returns. */
 int kr_snapshot_commit(kr_engine *e);
+
+/* Upload only some parts of the arenas; the rest keeps what the previous commit of the SAME layout (same kr_sizes, and for
+ * KR_PART_JSON the same c_json_off/c_json_len) put in HBM.  Typical epoch: pod statuses moved but no spec did — commit
+ * KR_PART_COLUMNS and keep the spec-JSON arena resident (the hash is still recomputed from it every pass). */
+enum { KR_PART_COLUMNS = 1, KR_PART_JSON = 2, KR_PART_ALL = 3 };
+int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts);
 
 /* Run the whole decision + status pass over the committed snapshot and copy the results back.
  * Replaces the decision halves of reconcilePods (raycluster_controller.go:619-935), reconcileMultiHostWorkerGroup

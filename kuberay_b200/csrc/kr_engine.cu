@@ -153,6 +153,7 @@ struct kr_engine {
   OutLayout ol{};
   ScratchLayout sl{};
   bool begun = false, committed = false, ran = false;
+  bool committed_full = false;  // every part of the current layout has been uploaded at least once
   uint32_t n_recreate = 0;  // clusters with KR_CF_UPGRADE_RECREATE (decide phase 1 needed)
   kr_profile prof{};
   std::string err;
@@ -557,7 +558,7 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
   CK(cudaSetDevice(c.device));
   CK(cudaStreamSynchronize(e->scopy));
   CK(cudaStreamSynchronize(e->sm));  // previous results are invalidated from here on
-  if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) { e->gvalid = false; e->force_radix = e->env_radix; }  // layout (hence every kernel argument) changes
+  if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) { e->gvalid = false; e->force_radix = e->env_radix; e->committed_full = false; }  // layout (hence every kernel argument) changes
   e->sizes = *sizes;
   e->il = in_layout(*sizes);
   e->ol = out_layout(*sizes, c.max_creates);
@@ -569,7 +570,9 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
   return KR_OK;
 }
 
-int kr_snapshot_commit(kr_engine *e) {
+int kr_snapshot_commit(kr_engine *e) { return kr_snapshot_commit_parts(e, KR_PART_ALL); }
+
+int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   if (!e || !e->begun) return e ? fail(e, KR_E_STATE, "kr_snapshot_commit before kr_snapshot_begin") : KR_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
   // cheap host-side checks of the invariants the kernels rely on
@@ -594,13 +597,20 @@ int kr_snapshot_commit(kr_engine *e) {
   // (and what depends on it) waits for the second part.  Nothing here blocks the host.
   CK(cudaStreamSynchronize(e->sm));  // a pass still reading the previous snapshot must finish before it is overwritten
   const size_t json_off = e->il.off[kNumCols - 1];
+  if ((parts & KR_PART_ALL) != KR_PART_ALL && !e->committed_full)
+    return fail(e, KR_E_STATE, "a partial commit needs a full commit of this layout first");
+  size_t bytes = 0;
   CK(cudaEventRecord(e->ev_h2d0, e->scopy));
-  if (json_off) CK(cudaMemcpyAsync(e->d_in, e->h_in, json_off, cudaMemcpyHostToDevice, e->scopy));
+  if ((parts & KR_PART_COLUMNS) && json_off) { CK(cudaMemcpyAsync(e->d_in, e->h_in, json_off, cudaMemcpyHostToDevice, e->scopy)); bytes += json_off; }
   CK(cudaEventRecord(e->ev_cols, e->scopy));
-  if (e->il.total > json_off) CK(cudaMemcpyAsync(e->d_in + json_off, e->h_in + json_off, e->il.total - json_off, cudaMemcpyHostToDevice, e->scopy));
+  if ((parts & KR_PART_JSON) && e->il.total > json_off) {
+    CK(cudaMemcpyAsync(e->d_in + json_off, e->h_in + json_off, e->il.total - json_off, cudaMemcpyHostToDevice, e->scopy));
+    bytes += e->il.total - json_off;
+  }
   CK(cudaEventRecord(e->ev_json, e->scopy));
+  if ((parts & KR_PART_ALL) == KR_PART_ALL) e->committed_full = true;
   e->h2d_timed = false;
-  e->prof.h2d_bytes = e->il.total;
+  e->prof.h2d_bytes = bytes;
   e->committed = true;
   return KR_OK;
 }

@@ -47,6 +47,7 @@ def lib() -> C.CDLL:
         L.kr_engine_destroy.restype = None
         L.kr_snapshot_begin.argtypes = [C.c_void_p, P(abi.kr_sizes), P(abi.kr_snapshot_bufs)]
         L.kr_snapshot_commit.argtypes = [C.c_void_p]
+        L.kr_snapshot_commit_parts.argtypes = [C.c_void_p, C.c_uint32]
         L.kr_reconcile_batch.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_results_view)]
         L.kr_reconcile_device_only.argtypes = [C.c_void_p, P(abi.kr_flags)]
         L.kr_reconcile_batch_profiled.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_profile)]
@@ -132,8 +133,8 @@ class Engine:
             if views[name].size:
                 np.copyto(views[name], snap.cols[name])
 
-    def commit(self):
-        self._check(self._L.kr_snapshot_commit(self._h))
+    def commit(self, parts: int = abi.PART_ALL):
+        self._check(self._L.kr_snapshot_commit_parts(self._h, parts))
 
     def load(self, snap: Snapshot):
         views = self.begin(snap.sizes())

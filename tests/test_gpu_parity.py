@@ -137,6 +137,29 @@ def test_repeated_passes_are_identical(oracle_mod):
         eng.close()
 
 
+def test_partial_commit_columns_only(oracle_mod):
+    """kr_snapshot_commit_parts(KR_PART_COLUMNS): pod statuses move, the spec-JSON arena stays resident; results must equal
+    a full pass over the mutated snapshot."""
+    snap, flags = synthetic.generate(synthetic.config("C2"))
+    eng = Engine.for_snapshot(snap)
+    try:
+        with pytest.raises(Exception):
+            eng.begin(snap.sizes()); eng.commit(abi.PART_COLUMNS)        # needs a full commit of this layout first
+        views = eng.load(snap)
+        eng.reconcile(flags)
+        rng = np.random.default_rng(3)
+        flip = rng.choice(snap.dims["pods"], 500, replace=False)
+        snap.p_packed[flip] = (snap.p_packed[flip] & ~np.uint32(7 << abi.PP_PHASE_SHIFT)) | np.uint32(abi.PHASE_FAILED << abi.PP_PHASE_SHIFT)
+        np.copyto(views["p_packed"], snap.p_packed)
+        views["json"][:] = 0                                               # host copy of the JSON is NOT re-uploaded ...
+        eng.commit(abi.PART_COLUMNS)
+        got = eng.reconcile(flags)
+    finally:
+        eng.close()
+    want = oracle_mod.run(snap, flags, threads=8)                          # ... so the hashes still match the real specs
+    assert not want.diff(got)
+
+
 def test_hash_batch_matches_hashlib():
     import base64
     import hashlib
