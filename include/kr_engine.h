@@ -226,6 +226,9 @@ typedef struct kr_flags {
   uint8_t  gate_multihost_indexing;  /* features.RayMultiHostIndexing, default 1 */
   uint8_t  env_random_pod_delete;    /* strings.ToLower(os.Getenv("ENABLE_RANDOM_POD_DELETE")) == "true" (:905) */
   uint8_t  skip_hash;                /* 1 => do not run the hash kernel (hash[] zeroed; Recreate gate treats hash as unknown) — test/bench knob only */
+  uint8_t  fetch_pod_lists;          /* 1 => kr_reconcile_batch / kr_results_fetch also copy the full per-cluster pod lists (sorted_pod_idx,
+                                        sorted_action: 5 B/pod) back; 0 => only the compact action list (act_*) comes back */
+  uint8_t  reserved_[3];
   uint32_t id_head_not_found_reason; /* interned id of "HeadPodNotFound" */
   uint32_t id_head_not_found_msg;    /* interned id of "Head Pod not found" */
 } kr_flags;
@@ -346,10 +349,15 @@ typedef struct kr_results_view {
   const char              *hash;       /* [32*n_clusters] base32hex(sha1(json)) (utils/util.go:628-640) */
   const kr_group_result   *groups;     /* [n_groups] */
   const int32_t           *wtd_pod_idx;/* [n_wtd]: pod (same namespace, same name) the Delete call resolves to, -1 = NotFound */
-  const uint32_t          *sorted_pod_idx; /* [n_pods]: pods bucketed by cluster, list order kept; orphans last */
-  const uint8_t           *sorted_action;  /* [n_pods]: KR_ACT_* aligned with sorted_pod_idx */
+  const uint32_t          *sorted_pod_idx; /* [n_pods]: pods bucketed by cluster, list order kept; orphans last.  NULL unless kr_flags.fetch_pod_lists */
+  const uint8_t           *sorted_action;  /* [n_pods]: KR_ACT_* aligned with sorted_pod_idx.  NULL unless kr_flags.fetch_pod_lists */
   const int32_t           *create_idx; /* [n_create_total] replica indices (:869-881,1081-1094) */
   const kr_job_result     *jobs;       /* [n_jobs] */
+  /* compact action list: every pod whose action != KEEP (orphans excluded), grouped by cluster, List order inside a cluster;
+   * cluster c owns entries [act_start[c], act_start[c+1]).  This is all the Go shim needs to issue the Delete calls. */
+  const uint32_t          *act_start;  /* [n_clusters + 1] */
+  const uint32_t          *act_pod_idx;/* [n_actions] */
+  const uint8_t           *act_code;   /* [n_actions] KR_ACT_* */
   uint32_t n_create_total;
   uint32_t n_orphans;
   uint32_t n_actions;              /* pods with action != KEEP (orphans excluded) */
@@ -389,6 +397,11 @@ int kr_snapshot_commit(kr_engine *e);
  * KR_PART_COLUMNS and keep the spec-JSON arena resident (the hash is still recomputed from it every pass). */
 enum { KR_PART_COLUMNS = 1, KR_PART_JSON = 2, KR_PART_ALL = 3 };
 int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts);
+
+/* Incremental epoch: the caller has rewritten the 7 pod columns of `rows[0..n)` in the pinned arenas
+ * (an informer Update event: phase, PodReady, labels ...) and nothing else; upload just those rows.  Rows may repeat.
+ * Pod additions / removals change n_pods and the List order: they need kr_snapshot_begin + a full commit. */
+int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n);
 
 /* Run the whole decision + status pass over the committed snapshot and copy the results back.
  * Replaces the decision halves of reconcilePods (raycluster_controller.go:619-935), reconcileMultiHostWorkerGroup

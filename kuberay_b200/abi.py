@@ -121,7 +121,8 @@ class kr_config(C.Structure):
 
 class kr_flags(C.Structure):
     _fields_ = [("gate_status_conditions", C.c_uint8), ("gate_multihost_indexing", C.c_uint8), ("env_random_pod_delete", C.c_uint8),
-                ("skip_hash", C.c_uint8), ("id_head_not_found_reason", C.c_uint32), ("id_head_not_found_msg", C.c_uint32)]
+                ("skip_hash", C.c_uint8), ("fetch_pod_lists", C.c_uint8), ("reserved_", C.c_uint8 * 3),
+                ("id_head_not_found_reason", C.c_uint32), ("id_head_not_found_msg", C.c_uint32)]
 
 
 class kr_sizes(C.Structure):
@@ -153,6 +154,7 @@ assert cluster_result_dtype.itemsize == 96 and group_result_dtype.itemsize == 32
 class kr_results_view(C.Structure):
     _fields_ = [("clusters", C.c_void_p), ("hash", C.c_void_p), ("groups", C.c_void_p), ("wtd_pod_idx", C.c_void_p),
                 ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
+                ("act_start", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
                 ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32), ("reserved", C.c_uint32)]
 
 
@@ -165,12 +167,13 @@ class kr_profile(C.Structure):
 class kr_oracle_out(C.Structure):  # oracle/kr_oracle.h (test infrastructure; declared here only for layout sharing)
     _fields_ = [("clusters", C.c_void_p), ("hash", C.c_void_p), ("groups", C.c_void_p), ("wtd_pod_idx", C.c_void_p),
                 ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
+                ("act_start", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
                 ("create_cap", C.c_uint32), ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32)]
 
 
 # every symbol include/kr_engine.h declares
 ENGINE_SYMBOLS = [
-    "kr_device_count", "kr_engine_create", "kr_engine_destroy", "kr_snapshot_begin", "kr_snapshot_commit", "kr_snapshot_commit_parts",
+    "kr_device_count", "kr_engine_create", "kr_engine_destroy", "kr_snapshot_begin", "kr_snapshot_commit", "kr_snapshot_commit_parts", "kr_snapshot_commit_pod_rows",
     "kr_reconcile_batch", "kr_reconcile_device_only", "kr_reconcile_batch_profiled", "kr_results_fetch",
     "kr_hash_batch", "kr_last_profile", "kr_group_results_device", "kr_group_results_copy", "kr_last_error", "kr_algorithmic_bytes",
 ]
@@ -183,6 +186,7 @@ def default_flags(**kw) -> kr_flags:
     f.gate_multihost_indexing = 1
     f.env_random_pod_delete = 0
     f.skip_hash = 0
+    f.fetch_pod_lists = 1
     f.id_head_not_found_reason = 0
     f.id_head_not_found_msg = 0
     for k, v in kw.items():
@@ -193,7 +197,8 @@ def default_flags(**kw) -> kr_flags:
 class Results:
     """Owned numpy copy of one pass's results (engine or oracle) — same fields as kr_results_view."""
 
-    FIELDS = ["clusters", "hash", "groups", "wtd_pod_idx", "sorted_pod_idx", "sorted_action", "create_idx", "jobs"]
+    FIELDS = ["clusters", "hash", "groups", "wtd_pod_idx", "sorted_pod_idx", "sorted_action", "create_idx", "jobs",
+              "act_start", "act_pod_idx", "act_code"]
 
     def __init__(self, sizes: kr_sizes, create_cap: int):
         self.clusters = np.zeros(sizes.n_clusters, dtype=cluster_result_dtype)
@@ -204,6 +209,9 @@ class Results:
         self.sorted_action = np.zeros(sizes.n_pods, dtype=np.uint8)
         self.create_idx = np.zeros(max(create_cap, 1), dtype=np.int32)
         self.jobs = np.zeros(sizes.n_jobs, dtype=job_result_dtype)
+        self.act_start = np.zeros(sizes.n_clusters + 1, dtype=np.uint32)
+        self.act_pod_idx = np.zeros(max(sizes.n_pods, 1), dtype=np.uint32)
+        self.act_code = np.zeros(max(sizes.n_pods, 1), dtype=np.uint8)
         self.n_create_total = 0
         self.n_orphans = 0
         self.n_actions = 0
@@ -222,6 +230,11 @@ class Results:
             if name == "create_idx":
                 n = min(self.n_create_total, other.n_create_total)
                 a, b = a[:n], b[:n]
+            if name in ("act_pod_idx", "act_code"):
+                n = min(self.n_actions, other.n_actions)
+                a, b = a[:n], b[:n]
+            if name in ("sorted_pod_idx", "sorted_action") and (a.size == 0 or b.size == 0):
+                continue  # one side did not fetch the full pod lists (kr_flags.fetch_pod_lists == 0)
             if a.shape != b.shape:
                 out.append(f"{name}: shape {a.shape} != {b.shape}")
                 continue

@@ -67,8 +67,8 @@ InLayout in_layout(const kr_sizes &n) {
   return L;
 }
 
-struct OutLayout {  // results arena
-  size_t totals, clusters, hash, groups, wtd, sorted_idx, sorted_act, jobs, fixed_total, create, total;
+struct OutLayout {  // results arena: [small fixed part | full pod lists | variable-length lists]
+  size_t totals, clusters, hash, groups, wtd, jobs, act_start, small_total, sorted_idx, sorted_act, act_idx, act_code, create, total;
 };
 OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
   OutLayout L;
@@ -78,10 +78,13 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
   L.hash = o; o = align_up(o + 32 * (size_t)n.n_clusters);
   L.groups = o; o = align_up(o + sizeof(kr_group_result) * (size_t)n.n_groups);
   L.wtd = o; o = align_up(o + 4 * (size_t)n.n_wtd);
+  L.jobs = o; o = align_up(o + sizeof(kr_job_result) * (size_t)n.n_jobs);
+  L.act_start = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 1));
+  L.small_total = o;  // everything above comes back in ONE copy
   L.sorted_idx = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.sorted_act = o; o = align_up(o + (size_t)n.n_pods);
-  L.jobs = o; o = align_up(o + sizeof(kr_job_result) * (size_t)n.n_jobs);
-  L.fixed_total = o;
+  L.act_idx = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.act_code = o; o = align_up(o + (size_t)n.n_pods);
   L.create = o; o = align_up(o + 4 * (size_t)create_cap);
   L.total = o;
   return L;
@@ -90,7 +93,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
@@ -121,9 +124,10 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.gacc = o; o = align_up(o + 16 * (size_t)n.n_groups);
   L.gcreate = o; o = align_up(o + 4 * (size_t)n.n_groups + 32);
   L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
+  L.cact = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 8));
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.chain = o;  // directly after ccount: one memset clears both
-  o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.mtiles / 8192 + (size_t)n.n_groups / 8192 + 8));
+  o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.mtiles / 8192 + (size_t)n.n_groups / 8192 + (size_t)n.n_clusters / 8192 + 10));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.mtiles + 8));
   L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -142,7 +146,7 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
 struct kr_engine {
   kr_config cfg{};
   cudaStream_t sm = nullptr, sh = nullptr, sg = nullptr, scopy = nullptr;
-  cudaEvent_t ev_h2d0 = nullptr, ev_cols = nullptr, ev_json = nullptr;  // commit: copy start, columns landed, JSON landed
+  cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_cols = nullptr, ev_json = nullptr;  // commit: copy start, columns landed, JSON landed
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   cudaEvent_t ev_k[KR_MAX_KERNEL_TIMES + 1]{};
@@ -153,6 +157,7 @@ struct kr_engine {
   OutLayout ol{};
   ScratchLayout sl{};
   bool begun = false, committed = false, ran = false;
+  kr_flags last_flags{};      // flags of the last pass (kr_results_fetch honours fetch_pod_lists)
   bool committed_full = false;  // every part of the current layout has been uploaded at least once
   uint32_t n_recreate = 0;  // clusters with KR_CF_UPGRADE_RECREATE (decide phase 1 needed)
   kr_profile prof{};
@@ -160,6 +165,9 @@ struct kr_engine {
   // kr_hash_batch staging
   uint8_t *hb_h = nullptr, *hb_d = nullptr;
   size_t hb_cap = 0;
+  uint8_t *h_in_dev = nullptr;               // device-side address of h_in
+  uint8_t *pr_h = nullptr, *pr_d = nullptr;  // kr_snapshot_commit_pod_rows staging
+  size_t pr_cap = 0;
   int sm_count = 148;
   // the whole pass (both streams) captured once per (layout, flags, n_recreate) and replayed
   cudaGraphExec_t gexec = nullptr;
@@ -216,6 +224,9 @@ ResDev bind_out(const OutLayout &L, uint8_t *base) {
   r.sorted_pod_idx = reinterpret_cast<uint32_t *>(base + L.sorted_idx);
   r.sorted_action = base + L.sorted_act;
   r.jobs = reinterpret_cast<kr_job_result *>(base + L.jobs);
+  r.act_start = reinterpret_cast<uint32_t *>(base + L.act_start);
+  r.act_pod_idx = reinterpret_cast<uint32_t *>(base + L.act_idx);
+  r.act_code = base + L.act_code;
   r.create_idx = reinterpret_cast<int32_t *>(base + L.create);
   return r;
 }
@@ -235,6 +246,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.gacc = reinterpret_cast<int32_t *>(b + L.gacc);
   s.gcreate = reinterpret_cast<uint32_t *>(b + L.gcreate);
   s.deferred_list = reinterpret_cast<uint32_t *>(b + L.deferred_list);
+  s.cact = reinterpret_cast<uint32_t *>(b + L.cact);
   s.ccount = reinterpret_cast<uint32_t *>(b + L.ccount);
   s.chain = reinterpret_cast<uint32_t *>(b + L.chain);
   s.cstart = reinterpret_cast<uint32_t *>(b + L.cstart);
@@ -277,7 +289,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   const bool do_hash = !f.skip_hash && n.n_clusters > 0;
   // the committed snapshot: columns gate stream M, the JSON arena gates the hash
   const unsigned wflag = capturing ? cudaEventWaitExternal : cudaEventWaitDefault;
-  CK(cudaStreamWaitEvent(M, e->ev_cols, wflag));
+  // (the fork comes first so the hash can start while the columns are still landing — an incremental pod-row epoch leaves the JSON untouched)
   if (!profile) { CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0)); }
   CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
   auto launch_hash = [&]() {
@@ -303,6 +315,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   bool fuse_place_done = false;    // k_decide_small directly follows k_place_fused on stream M
   bool creates_after_kernel = false;  // k_creates_fused directly follows a kernel on stream M (no event wait in between)
   if (!e->force_radix) CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));  // per-cluster counts + the chained-scan cells
+  CK(cudaStreamWaitEvent(M, e->ev_cols, wflag));  // the scratch clears above overlap the tail of the upload
   {
     uint32_t items = n.n_clusters + n.n_groups + n.n_heads;
     if (items) { mark("k_build_tables"); k_build_tables<<<(items + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
@@ -377,10 +390,21 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
     creates_after_kernel = true;
   }
-  if (n.n_groups && !e->no_fuse && n.n_groups <= kFusedMaxCounters) {
+  if (!e->no_fuse && (uint64_t)n.n_groups + n.n_clusters + 1 <= kFusedMaxCounters) {
     mark("k_creates_fused");
-    CK(launch_pdl(k_creates_fused, dim3(e->sm_count), dim3(1024), 4 * (size_t)n.n_groups, M, pdl && creates_after_kernel, s, sc, r, z, f, e->cfg.max_creates));
-  } else if (n.n_groups) {
+    CK(launch_pdl(k_creates_fused, dim3(e->sm_count), dim3(1024), 4 * ((size_t)n.n_groups + n.n_clusters + 1), M, pdl && creates_after_kernel, s, sc, r, z, f, e->cfg.max_creates));
+  } else {
+    const uint32_t nch_a = (n.n_clusters + kScanChunk - 1) / kScanChunk;
+    uint32_t *achain = sc.chain + 2 * ((size_t)(n.n_clusters + 1 + kScanChunk - 1) / kScanChunk + (e->sl.mtiles + kScanChunk - 1) / kScanChunk + (n.n_groups + kScanChunk - 1) / kScanChunk + 1);
+    if (n.n_clusters) {
+      if (e->force_radix) CK(cudaMemsetAsync(achain, 0, 8 * (size_t)nch_a, M));
+      mark("k_scan_actions");
+      k_scan_actions<<<nch_a, 1024, 0, M>>>(r, sc.cact, n.n_clusters, achain);
+      mark("k_compact_actions");
+      k_compact_actions<<<(n.n_clusters + 3) / 4, 128, 0, M>>>(r, sc.cact, n.n_clusters);
+    } else CK(cudaMemsetAsync(r.act_start, 0, 4, M));
+  }
+  if (e->no_fuse || (uint64_t)n.n_groups + n.n_clusters + 1 > kFusedMaxCounters) if (n.n_groups) {
     mark("k_scan_creates");
     const uint32_t nch_g = (n.n_groups + kScanChunk - 1) / kScanChunk;
     uint32_t *gchain = sc.chain + 2 * ((size_t)(n.n_clusters + 1 + kScanChunk - 1) / kScanChunk + (e->sl.mtiles + kScanChunk - 1) / kScanChunk);
@@ -398,7 +422,9 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
 // Replays the captured CUDA graph of the pass (captures it first when the layout / flags changed).
 int run_pass_once(kr_engine *e, const kr_flags &f) {
   if (!e->use_graph) return launch_pass(e, f, false);
-  if (!e->gvalid || memcmp(&e->gflags, &f, sizeof f) != 0) {
+  kr_flags fk = f;
+  fk.fetch_pod_lists = 0;  // host-side switch: does not change the device work
+  if (!e->gvalid || memcmp(&e->gflags, &fk, sizeof fk) != 0) {
     if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
     e->gvalid = false;
     CK(cudaStreamBeginCapture(e->sm, cudaStreamCaptureModeThreadLocal));
@@ -410,7 +436,7 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
     ce = cudaGraphInstantiate(&e->gexec, g, 0);
     cudaGraphDestroy(g);
     if (ce != cudaSuccess) return fail(e, KR_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-    e->gflags = f;
+    e->gflags = fk;
     e->gvalid = true;
   }
   CK(cudaGraphLaunch(e->gexec, e->sm));
@@ -420,6 +446,7 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
 // Runs the pass; if the fast pipeline met a bucket it cannot sort (> 1024 pods in one RayCluster or among the orphans),
 // switches this layout to the radix pipeline and runs again.  Leaves the stream synchronised.
 int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
+  e->last_flags = f;
   for (int attempt = 0; attempt < 2; attempt++) {
     int rc = run_pass_once(e, f);
     if (rc) return rc;
@@ -428,7 +455,7 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
     CK(cudaStreamSynchronize(e->sm));
     if (!e->h2d_timed) {
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_json) == cudaSuccess) e->prof.h2d_ms = ms;
+      if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
       e->h2d_timed = true;
     }
     if (e->ran_fast && (e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { e->force_radix = true; e->gvalid = false; continue; }
@@ -437,19 +464,34 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
   return fail(e, KR_E_STATE, "internal: radix pipeline flagged a big bucket");
 }
 
+// Results back to the pinned host arena.  run_pass already brought the 32-byte totals over, so every copy is issued with its
+// exact size up front and the host waits once: [small fixed part] (+ the full pod lists when asked for) + the compact action
+// list + the replica-index arena.
 int fetch_results(kr_engine *e, kr_results_view *out) {
   const kr_sizes &n = e->sizes;
+  const uint32_t *tot = e->h_totals;
+  const uint32_t n_create = tot[0], n_actions = tot[2];
+  const bool full = e->last_flags.fetch_pod_lists != 0;
   CK(cudaEventRecord(e->ev_b, e->sm));
-  CK(cudaMemcpyAsync(e->h_out, e->d_out, e->ol.fixed_total, cudaMemcpyDeviceToHost, e->sm));
-  CK(cudaStreamSynchronize(e->sm));
-  const uint32_t *tot = reinterpret_cast<const uint32_t *>(e->h_out + e->ol.totals);
-  uint32_t n_create = tot[0];
   if (n_create > e->cfg.max_creates) {
     CK(cudaEventRecord(e->ev_c, e->sm));
     return fail(e, KR_E_CAPACITY, "pods to create (%u) exceed kr_config.max_creates (%u)", n_create, e->cfg.max_creates);
   }
+  uint64_t bytes = e->ol.small_total;
+  CK(cudaMemcpyAsync(e->h_out, e->d_out, e->ol.small_total, cudaMemcpyDeviceToHost, e->sm));
+  if (full && n.n_pods) {
+    size_t span = e->ol.act_idx - e->ol.sorted_idx;  // sorted_pod_idx + sorted_action, contiguous
+    CK(cudaMemcpyAsync(e->h_out + e->ol.sorted_idx, e->d_out + e->ol.sorted_idx, span, cudaMemcpyDeviceToHost, e->sm));
+    bytes += span;
+  }
+  if (n_actions) {
+    CK(cudaMemcpyAsync(e->h_out + e->ol.act_idx, e->d_out + e->ol.act_idx, 4 * (size_t)n_actions, cudaMemcpyDeviceToHost, e->sm));
+    CK(cudaMemcpyAsync(e->h_out + e->ol.act_code, e->d_out + e->ol.act_code, (size_t)n_actions, cudaMemcpyDeviceToHost, e->sm));
+    bytes += 5ull * n_actions;
+  }
   if (n_create) {
     CK(cudaMemcpyAsync(e->h_out + e->ol.create, e->d_out + e->ol.create, 4 * (size_t)n_create, cudaMemcpyDeviceToHost, e->sm));
+    bytes += 4ull * n_create;
   }
   CK(cudaEventRecord(e->ev_c, e->sm));
   CK(cudaStreamSynchronize(e->sm));
@@ -457,13 +499,14 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
     ResDev hr = bind_out(e->ol, e->h_out);
     out->clusters = hr.clusters; out->hash = hr.hash; out->groups = hr.groups;
     out->wtd_pod_idx = reinterpret_cast<const int32_t *>(hr.wtd_pod_idx);
-    out->sorted_pod_idx = hr.sorted_pod_idx; out->sorted_action = hr.sorted_action; out->create_idx = hr.create_idx; out->jobs = hr.jobs;
-    out->n_create_total = n_create; out->n_orphans = tot[1]; out->n_actions = tot[2]; out->reserved = 0;
-    (void)n;
+    out->sorted_pod_idx = full ? hr.sorted_pod_idx : nullptr; out->sorted_action = full ? hr.sorted_action : nullptr;
+    out->create_idx = hr.create_idx; out->jobs = hr.jobs;
+    out->act_start = hr.act_start; out->act_pod_idx = hr.act_pod_idx; out->act_code = hr.act_code;
+    out->n_create_total = n_create; out->n_orphans = tot[1]; out->n_actions = n_actions; out->reserved = 0;
   }
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_c) == cudaSuccess) e->prof.d2h_ms = ms;
-  e->prof.d2h_bytes = e->ol.fixed_total + 4ull * n_create;
+  e->prof.d2h_bytes = bytes;
   return KR_OK;
 }
 
@@ -498,7 +541,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaStreamCreateWithFlags(&e->sh, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaStreamCreateWithFlags(&e->sg, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaStreamCreateWithFlags(&e->scopy, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
-  cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
+  cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_h2d1); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
   cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
@@ -535,6 +578,8 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->d_out) cudaFree(e->d_out);
   if (e->hb_d) cudaFree(e->hb_d);
+  if (e->pr_h) cudaFreeHost(e->pr_h);
+  if (e->pr_d) cudaFree(e->pr_d);
   if (e->gexec) cudaGraphExecDestroy(e->gexec);
   for (auto ev : {e->ev_fork, e->ev_hash, e->ev_a, e->ev_b, e->ev_c}) if (ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_k) if (ev) cudaEventDestroy(ev);
@@ -542,7 +587,7 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->sh) cudaStreamDestroy(e->sh);
   if (e->sg) cudaStreamDestroy(e->sg);
   if (e->scopy) { cudaStreamSynchronize(e->scopy); cudaStreamDestroy(e->scopy); }
-  for (auto ev : {e->ev_h2d0, e->ev_cols, e->ev_json}) if (ev) cudaEventDestroy(ev);
+  for (auto ev : {e->ev_h2d0, e->ev_h2d1, e->ev_cols, e->ev_json}) if (ev) cudaEventDestroy(ev);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   delete e;
@@ -608,9 +653,54 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     bytes += e->il.total - json_off;
   }
   CK(cudaEventRecord(e->ev_json, e->scopy));
+  CK(cudaEventRecord(e->ev_h2d1, e->scopy));
   if ((parts & KR_PART_ALL) == KR_PART_ALL) e->committed_full = true;
   e->h2d_timed = false;
   e->prof.h2d_bytes = bytes;
+  e->committed = true;
+  return KR_OK;
+}
+
+int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n) {
+  if (!e || (!rows && n)) return KR_E_INVALID;
+  if (!e->committed_full) return fail(e, KR_E_STATE, "kr_snapshot_commit_pod_rows needs a full commit of this layout first");
+  if (n == 0) return KR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t bytes = 4 * (size_t)n;  // only the row list is staged; the kernel pulls the rows from the mapped pinned arena
+  CK(cudaStreamSynchronize(e->scopy));  // a previous patch may still be reading the staging buffer
+  if (bytes > e->pr_cap) {
+    if (e->pr_h) cudaFreeHost(e->pr_h);
+    if (e->pr_d) cudaFree(e->pr_d);
+    e->pr_h = nullptr; e->pr_d = nullptr; e->pr_cap = 0;
+    size_t cap = bytes + bytes / 2 + 4096;
+    CK(cudaHostAlloc((void **)&e->pr_h, cap, cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&e->pr_d, cap));
+    e->pr_cap = cap;
+  }
+  for (uint32_t i = 0; i < n; i++)
+    if (rows[i] >= e->sizes.n_pods) return fail(e, KR_E_INVALID, "pod row %u out of range", rows[i]);
+  memcpy(e->pr_h, rows, bytes);
+  kr_snapshot_bufs hb;
+  bind_in(e->il, e->h_in, &hb);
+  SnapDev s;
+  bind_in(e->il, e->d_in, &s);
+  PodCols hc, dc;
+  const void *hsrc[7] = {hb.p_ns_id, hb.p_cluster_name_id, hb.p_group_name_id, hb.p_name_id, hb.p_packed, hb.p_replica_index, hb.p_replica_name_id};
+  const void *dsrc[7] = {s.p_ns_id, s.p_cluster_name_id, s.p_group_name_id, s.p_name_id, s.p_packed, s.p_replica_index, s.p_replica_name_id};
+  if (!e->h_in_dev) CK(cudaHostGetDevicePointer((void **)&e->h_in_dev, e->h_in, 0));  // device-side address of the pinned arena (mapped under UVA)
+  for (int k = 0; k < 7; k++) {
+    hc.c[k] = reinterpret_cast<uint32_t *>(e->h_in_dev + (static_cast<const uint8_t *>(hsrc[k]) - e->h_in));
+    dc.c[k] = static_cast<uint32_t *>(const_cast<void *>(dsrc[k]));
+  }
+  CK(cudaStreamSynchronize(e->sm));  // a pass still reading the columns must finish first
+  CK(cudaEventRecord(e->ev_h2d0, e->scopy));
+  CK(cudaMemcpyAsync(e->pr_d, e->pr_h, bytes, cudaMemcpyHostToDevice, e->scopy));
+  k_patch_pods<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, hc, dc);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev_h2d1, e->scopy));
+  CK(cudaEventRecord(e->ev_cols, e->scopy));  // ev_json keeps pointing at the last JSON upload: the hash need not wait for the patch
+  e->h2d_timed = false;
+  e->prof.h2d_bytes = bytes + 28 * (size_t)n;  // row list + the 28-B row payload (PCIe moves one 32-B sector per value read)
   e->committed = true;
   return KR_OK;
 }
@@ -645,6 +735,7 @@ int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile 
   if (!e || !flags) return KR_E_INVALID;
   if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
   CK(cudaSetDevice(e->cfg.device));
+  e->last_flags = *flags;
   CK(cudaEventRecord(e->ev_a, e->sm));
   int rc = launch_pass(e, *flags, true);
   if (rc) return rc;

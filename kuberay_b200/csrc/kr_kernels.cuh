@@ -4,14 +4,17 @@
 // shared-memory staging (hash chunks, per-tile digit counters, per-warp group accumulators), warp-ballot /
 // match_any group-by, grids sized in multiples of the SM count.
 //
-// Pipeline of one pass (engine stream M unless noted):
-//   k_build_tables  cluster table (ns,name)->idx, workersToDelete-name table, head-aux table
-//   k_match         per pod: label/selector match -> cluster idx + group slot, 16-byte pod row, radix digit histogram
-//   k_scan_hist / k_scatter / k_hist   stable LSD radix sort of pod indices by cluster idx (list order kept)
-//   k_decide        one warp per RayCluster: head decision, per-group diff, ordered deletes, status roll-up
-//   k_scan_creates / k_create_fill     replica-index allocation for pods to create
-//   k_jobs          RayJob -> RayCluster status roll-up join
-//   k_hash          (stream H, concurrent) SHA-1 + base32hex of every muted-spec JSON
+// Pipeline of one pass (engine stream M unless noted); one CUDA graph, programmatic dependent launch along the chain:
+//   k_build_tables   cluster table (ns,name)->idx (+ per-cluster group record), workersToDelete-name table, head-aux table
+//   k_match          per pod: label/selector match -> cluster idx + group slot, 16-byte pod row, bucket rank
+//   k_place_fused    bucket starts (scan in shared memory) + pod -> slot of its cluster's bucket   [large: k_scan_counts + k_place]
+//   k_decide_small   one warp per RayCluster (<= 256 pods): in-register bitonic sort (List order), warp-ballot group-by,
+//                    head / group decisions, ordered deletes, status roll-up        | k_decide: general path, side stream
+//   k_hash2          (stream H, concurrent) SHA-1 + base32hex of every muted-spec JSON
+//   k_decide phase 1 clusters whose Recreate gate needs the hash
+//   k_creates_fused  create offsets + lowest free replica indices + compact action list   [large: k_scan_* + k_create_fill ...]
+//   k_jobs           RayJob -> RayCluster status roll-up join
+//   radix pipeline   (k_match<radix>, k_hist, k_scan_rows, k_scatter): stable LSD sort, taken when a RayCluster has > 1024 pods
 //
 // Reference semantics restated here are cited per function (paths relative to
 // ray-operator/controllers/ray/ in ray-project/kuberay).
@@ -64,6 +67,9 @@ struct ResDev {  // device results arena
   uint8_t *sorted_action;
   int32_t *create_idx;
   kr_job_result *jobs;
+  uint32_t *act_start;    // [n_clusters + 1]
+  uint32_t *act_pod_idx;  // [n_pods] capacity; n_actions used
+  uint8_t *act_code;
   uint32_t *totals;  // [0]=n_create_total [1]=n_orphans [2]=n_actions [3]=error flags [4]=clusters deferred to decide phase 1
 };
 
@@ -77,6 +83,7 @@ struct ScratchDev {
   uint32_t *hist;                                              // [256 * ntiles] digit-major
   uint32_t *row_total;                                         // [256] per-digit totals of the current pass
   uint32_t *gcreate;                                           // [n_groups] dense n_create (input of the creates scan)
+  uint32_t *cact;                                              // [n_clusters] pods with an action per cluster (input of the action-list scan)
   uint32_t *mh_rep, *mh_name, *mh_meta, *mh_cnt, *mh_flg;      // multi-host scratch, indexed by sorted position
   uint8_t *mh_act, *mh_head;                                   // per position: action of a multi-host pod / first pod of a valid replica
   uint32_t *tile_orph;                                         // fast pipeline: orphans per k_match tile -> exclusive prefix
@@ -91,11 +98,8 @@ struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
 // row.w layout: low 16 bits = p_packed low bits (+ KR_ROW_WTD_OWN), high 16 bits = group slot inside the cluster
 #define KR_ROW_WTD_OWN (1u << 11)   // named by its own group's scaleStrategy.workersToDelete
 #define KR_ROW_NO_GROUP 0xFFFFu
-#define KR_TOTALS_ERR_MH_UNSUPPORTED 1u
 #define KR_TOTALS_BIG_BUCKET 2u        // fast pipeline only: some cluster (or the orphan bucket) holds more pods than the in-warp sort takes
 
-// error bits in totals[3]
-#define KR_DEVERR_TABLE_FULL 2u
 
 static constexpr int kSortThreads = 256;
 static constexpr int kSortItems = 8;
@@ -1173,6 +1177,7 @@ __device__ __forceinline__ void decide_cluster(const DecideArgs &a, const uint32
     if (!(cf & KR_CF_SKIP))
       status_rollup(a, c, cr, P, (uint32_t)n_heads, head_pod, head_name, ready, available, all_running);
     a.r.clusters[c] = cr;
+    a.sc.cact[c] = n_act;
     if (n_act) atomicAdd(&a.r.totals[2], n_act);
   }
 }
@@ -1330,6 +1335,42 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
   create_fill_group(s, sc, r, f, g, r.groups[g].create_off, create_cap, s_bits[warp], lane);
 }
 
+// Compact action list of one cluster: (pod idx, action) of every pod whose action != KEEP, List order kept (one warp).
+__device__ __forceinline__ void compact_cluster_actions(const ResDev &r, uint32_t c, uint32_t dst, uint32_t lane) {
+  const kr_cluster_result *cr = &r.clusters[c];
+  const uint32_t seg0 = cr->pod_start;
+  // n_pods is only filled when calculateStatus ran; a cluster with actions always has it
+  const uint32_t seg1 = seg0 + (uint32_t)cr->n_pods;
+  const uint32_t lt = lanemask_lt();
+  for (uint32_t b = seg0; b < seg1; b += 32) {
+    uint32_t i = b + lane;
+    uint8_t act = i < seg1 ? r.sorted_action[i] : (uint8_t)KR_ACT_KEEP;
+    uint32_t bal = __ballot_sync(0xFFFFFFFFu, act != KR_ACT_KEEP);
+    if (act != KR_ACT_KEEP) { uint32_t o = dst + __popc(bal & lt); r.act_pod_idx[o] = r.sorted_pod_idx[i]; r.act_code[o] = act; }
+    dst += __popc(bal);
+  }
+}
+
+// unfused path: starts of the per-cluster action lists (chained scan) ...
+__global__ void __launch_bounds__(1024) k_scan_actions(ResDev r, const uint32_t *__restrict__ cact, uint32_t n_clusters, uint32_t *chain) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_prefix;
+  uint32_t excl[8];
+  bool big = false;
+  const uint32_t chunk = blockIdx.x;
+  uint32_t carry = chained_scan_chunk(cact, n_clusters, chunk, chain, 0, big, excl, s_warp, &s_prefix);
+  const uint32_t i0 = chunk * kScanChunk + threadIdx.x * 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) if (i0 + k < n_clusters) r.act_start[i0 + k] = excl[k];
+  if (chunk == gridDim.x - 1 && threadIdx.x == 0) r.act_start[n_clusters] = carry;
+}
+// ... and the lists themselves, one warp per cluster
+__global__ void __launch_bounds__(128) k_compact_actions(ResDev r, const uint32_t *__restrict__ cact, uint32_t n_clusters) {
+  const uint32_t c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= n_clusters || cact[c] == 0) return;
+  compact_cluster_actions(r, c, r.act_start[c], threadIdx.x & 31);
+}
+
 // ---- fused variants for snapshots whose per-cluster / per-group counters fit in shared memory: every block scans the counters
 // itself (a few tens of KB out of L2) instead of waiting for a scan kernel, which removes two ~10 us stages from the chain.
 static constexpr uint32_t kFusedMaxCounters = 48 * 1024;  // 192 KB of shared memory
@@ -1402,17 +1443,38 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_bits[32][32];
   pdl_wait(); pdl_trigger();
-  uint32_t *sm_off = sm_dyn;  // [n_groups]
+  uint32_t *sm_off = sm_dyn;               // [n_groups] create offsets
+  uint32_t *sm_act = sm_dyn + n.n_groups;  // [n_clusters + 1] action-list starts
   bool dummy = false;
   uint32_t tot = block_scan_to_smem(sc.gcreate, n.n_groups, sm_off, 0, dummy, s_warp, &s_carry);
+  uint32_t tot_act = block_scan_to_smem(sc.cact, n.n_clusters, sm_act, 0, dummy, s_warp, &s_carry);
+  if (threadIdx.x == 0) sm_act[n.n_clusters] = tot_act;
   __syncthreads();
   if (blockIdx.x == 0) {
     for (uint32_t g = threadIdx.x; g < n.n_groups; g += blockDim.x) r.groups[g].create_off = sm_off[g];
+    for (uint32_t c = threadIdx.x; c <= n.n_clusters; c += blockDim.x) r.act_start[c] = sm_act[c];
     if (threadIdx.x == 0) r.totals[0] = tot;
   }
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (uint32_t g = blockIdx.x * nw + warp; g < n.n_groups; g += gridDim.x * nw)
     if (__ldg(&sc.gcreate[g])) create_fill_group(s, sc, r, f, g, sm_off[g], create_cap, s_bits[warp], lane);
+  for (uint32_t c = blockIdx.x * nw + warp; c < n.n_clusters; c += gridDim.x * nw)
+    if (sm_act[c + 1] != sm_act[c]) compact_cluster_actions(r, c, sm_act[c], lane);
+}
+
+// ------------------------------------------------------------------------------------------------ k_patch_pods
+// Incremental epoch: copy n updated pod rows from the pinned host arena (mapped, read over PCIe in 32-B sectors — the host never
+// gathers them) into the resident columns.  Only the row list is staged.
+struct PodCols { uint32_t *c[7]; };
+__global__ void __launch_bounds__(256) k_patch_pods(const uint32_t *__restrict__ rows, uint32_t n, PodCols host, PodCols dev) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = rows[i];
+  uint32_t v[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) v[k] = __ldcv(host.c[k] + p);  // volatile-cached: never served from a stale L2 line
+#pragma unroll
+  for (int k = 0; k < 7; k++) dev.c[k][p] = v[k];
 }
 
 // ------------------------------------------------------------------------------------------------ k_jobs
@@ -1438,121 +1500,6 @@ __global__ void __launch_bounds__(256) k_jobs(SnapDev s, ScratchDev sc, ResDev r
 
 __device__ __forceinline__ uint32_t rol(uint32_t x, int k) { return __funnelshift_l(x, x, k); }
 __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-
-__device__ __forceinline__ void sha1_rounds(uint32_t (&w)[16], uint32_t (&h)[5]) {
-  uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
-#pragma unroll
-  for (int i = 0; i < 80; i++) {
-    uint32_t wi;
-    if (i < 16) wi = w[i];
-    else { wi = rol(w[(i - 3) & 15] ^ w[(i - 8) & 15] ^ w[(i - 14) & 15] ^ w[i & 15], 1); w[i & 15] = wi; }
-    uint32_t f, k;
-    if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999u; }
-    else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
-    else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
-    else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
-    uint32_t t = rol(a, 5) + f + e + k + wi;
-    e = d; d = c; c = rol(b, 30); b = a; a = t;
-  }
-  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
-}
-
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_hash(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ off,
-                                                     const uint32_t *__restrict__ len32, const uint64_t *__restrict__ off_end,
-                                                     uint32_t n, char *__restrict__ out) {
-  // tile[warp][message lane][8 x 16-byte pieces], piece index XOR (lane & 7)
-  __shared__ uint4 s_tile[WARPS][32][8];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t m = (blockIdx.x * WARPS + warp) * 32 + lane;
-  const bool have = m < n;
-  uint64_t moff = 0, mlen = 0;
-  if (have) { moff = off[m]; mlen = len32 ? (uint64_t)len32[m] : (off_end[m] - moff); }
-  const uint32_t nblocks = have ? (uint32_t)((mlen + 8) / 64 + 1) : 0;
-  uint32_t max_blocks = nblocks;
-#pragma unroll
-  for (int d = 16; d; d >>= 1) max_blocks = max(max_blocks, __shfl_xor_sync(0xFFFFFFFFu, max_blocks, d));
-  uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
-  const uint64_t mlen16 = (mlen + 15) & ~15ull;  // arena is padded to 16 bytes per message
-  const uint32_t sub = lane & 7, grp = lane >> 3;
-
-  uint4 pre[8];
-  auto fetch = [&](uint32_t chunk) {
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      uint32_t src_lane = 4 * r + grp;  // message whose piece this lane fetches
-      uint64_t o = __shfl_sync(0xFFFFFFFFu, moff, src_lane);
-      uint64_t l16 = __shfl_sync(0xFFFFFFFFu, mlen16, src_lane);
-      uint64_t pos = (uint64_t)chunk * 128 + sub * 16;
-      pre[r] = (pos < l16) ? __ldg(reinterpret_cast<const uint4 *>(bytes + o + pos)) : make_uint4(0, 0, 0, 0);
-    }
-  };
-  const uint32_t nchunks = (max_blocks + 1) / 2;
-  if (nchunks) fetch(0);
-  for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      uint32_t src_lane = 4 * r + grp;
-      s_tile[warp][src_lane][sub ^ (src_lane & 7)] = pre[r];
-    }
-    __syncwarp();
-    if (chunk + 1 < nchunks) fetch(chunk + 1);  // software prefetch: loads in flight during the 160 rounds below
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-      uint32_t blk = chunk * 2 + half;
-      if (blk >= nblocks) continue;
-      uint32_t w[16];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint4 v = s_tile[warp][lane][(half * 4 + q) ^ (lane & 7)];
-        w[4 * q] = bswap(v.x); w[4 * q + 1] = bswap(v.y); w[4 * q + 2] = bswap(v.z); w[4 * q + 3] = bswap(v.w);
-      }
-      uint64_t bstart = (uint64_t)blk * 64;
-      if (bstart + 64 > mlen) {  // tail block(s): 0x80 terminator, zero fill, 64-bit big-endian bit length (FIPS 180-4 §5.1.1)
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-          uint64_t wpos = bstart + 4 * q;
-          uint32_t v = w[q];
-          if (wpos >= mlen) v = (wpos == mlen) ? 0x80000000u : 0u;
-          else if (wpos + 4 > mlen) {
-            uint32_t keep = (uint32_t)(mlen - wpos);  // 1..3 bytes of message in this word
-            uint32_t mask = 0xFFFFFFFFu << (8 * (4 - keep));
-            v = (v & mask) | (0x80u << (8 * (3 - keep)));
-          }
-          w[q] = v;
-        }
-        if (blk == nblocks - 1) { uint64_t bits = mlen * 8; w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
-      }
-      sha1_rounds(w, h);
-    }
-  }
-  if (!have) return;
-  // base32hex: 4 groups of 40 bits -> 8 chars each
-  uint32_t o32[8];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    // 40-bit group j = bits [40j, 40j+40) of h0||h1||h2||h3||h4
-    uint64_t v;
-    switch (j) {
-      case 0: v = ((uint64_t)h[0] << 8) | (h[1] >> 24); break;
-      case 1: v = ((uint64_t)(h[1] & 0xFFFFFFu) << 16) | (h[2] >> 16); break;
-      case 2: v = ((uint64_t)(h[2] & 0xFFFFu) << 24) | (h[3] >> 8); break;
-      default: v = ((uint64_t)(h[3] & 0xFFu) << 32) | h[4]; break;
-    }
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      uint32_t cc = (uint32_t)(v >> (35 - 5 * k)) & 31u;
-      uint32_t ch = cc < 10 ? ('0' + cc) : ('A' + cc - 10);
-      if (k < 4) lo |= ch << (8 * k); else hi |= ch << (8 * (k - 4));
-    }
-    o32[2 * j] = lo; o32[2 * j + 1] = hi;
-  }
-  uint4 *dst = reinterpret_cast<uint4 *>(out + 32 * (size_t)m);
-  dst[0] = make_uint4(o32[0], o32[1], o32[2], o32[3]);
-  dst[1] = make_uint4(o32[4], o32[5], o32[6], o32[7]);
-}
 
 // ------------------------------------------------------------------------------------------------ k_hash2
 // Second-generation hash kernel.  Same one-lane-per-message mapping, but

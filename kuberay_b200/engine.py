@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         L.kr_snapshot_begin.argtypes = [C.c_void_p, P(abi.kr_sizes), P(abi.kr_snapshot_bufs)]
         L.kr_snapshot_commit.argtypes = [C.c_void_p]
         L.kr_snapshot_commit_parts.argtypes = [C.c_void_p, C.c_uint32]
+        L.kr_snapshot_commit_pod_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.kr_reconcile_batch.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_results_view)]
         L.kr_reconcile_device_only.argtypes = [C.c_void_p, P(abi.kr_flags)]
         L.kr_reconcile_batch_profiled.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_profile)]
@@ -136,6 +137,11 @@ class Engine:
     def commit(self, parts: int = abi.PART_ALL):
         self._check(self._L.kr_snapshot_commit_parts(self._h, parts))
 
+    def commit_pod_rows(self, rows: np.ndarray):
+        """Incremental epoch: upload only the pod rows the caller rewrote in the pinned arenas."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        self._check(self._L.kr_snapshot_commit_pod_rows(self._h, rows.ctypes.data, rows.size))
+
     def load(self, snap: Snapshot):
         views = self.begin(snap.sizes())
         self.fill(views, snap)
@@ -206,8 +212,11 @@ class Engine:
         res.hash = _np_view(view.hash, np.uint8, 32 * s.n_clusters).reshape(s.n_clusters, 32)
         res.groups = _np_view(view.groups, abi.group_result_dtype, s.n_groups)
         res.wtd_pod_idx = _np_view(view.wtd_pod_idx, np.int32, s.n_wtd)
-        res.sorted_pod_idx = _np_view(view.sorted_pod_idx, np.uint32, s.n_pods)
-        res.sorted_action = _np_view(view.sorted_action, np.uint8, s.n_pods)
+        res.sorted_pod_idx = _np_view(view.sorted_pod_idx, np.uint32, s.n_pods if view.sorted_pod_idx else 0)
+        res.sorted_action = _np_view(view.sorted_action, np.uint8, s.n_pods if view.sorted_action else 0)
+        res.act_start = _np_view(view.act_start, np.uint32, s.n_clusters + 1)
+        res.act_pod_idx = _np_view(view.act_pod_idx, np.uint32, view.n_actions)
+        res.act_code = _np_view(view.act_code, np.uint8, view.n_actions)
         res.create_idx = _np_view(view.create_idx, np.int32, view.n_create_total)
         res.jobs = _np_view(view.jobs, abi.job_result_dtype, s.n_jobs)
         res.n_create_total, res.n_orphans, res.n_actions = view.n_create_total, view.n_orphans, view.n_actions

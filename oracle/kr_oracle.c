@@ -820,6 +820,16 @@ static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags
       if (a != KR_ACT_KEEP && a != KR_ACT_ORPHAN) n_actions++;
     }
     for (uint32_t c = 0; c < Nc; c++) out->clusters[c].pod_start = x.cl_start[c];
+    /* compact action list, cluster-major, list order inside a cluster */
+    uint32_t na = 0;
+    for (uint32_t c = 0; c < Nc; c++) {
+      out->act_start[c] = na;
+      for (uint32_t i = x.cl_start[c]; i < x.cl_start[c + 1]; i++) {
+        uint8_t a = x.act[x.cl_pods[i]];
+        if (a != KR_ACT_KEEP) { out->act_pod_idx[na] = x.cl_pods[i]; out->act_code[na] = a; na++; }
+      }
+    }
+    out->act_start[Nc] = na;
     out->n_orphans = x.cl_start[Nc + 1] - x.cl_start[Nc];
     out->n_actions = n_actions;
   }

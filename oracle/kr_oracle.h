@@ -40,6 +40,9 @@ typedef struct kr_oracle_out {
   uint8_t           *sorted_action;  /* [n_pods] */
   int32_t           *create_idx; /* [create_cap] */
   kr_job_result     *jobs;       /* [n_jobs] */
+  uint32_t          *act_start;  /* [n_clusters + 1] */
+  uint32_t          *act_pod_idx;/* [n_pods] capacity */
+  uint8_t           *act_code;   /* [n_pods] capacity */
   uint32_t create_cap;
   uint32_t n_create_total, n_orphans, n_actions;
 } kr_oracle_out;

@@ -160,6 +160,48 @@ def test_partial_commit_columns_only(oracle_mod):
     assert not want.diff(got)
 
 
+def test_incremental_pod_rows(oracle_mod):
+    """kr_snapshot_commit_pod_rows: only rewritten pod rows cross PCIe; results equal a full pass over the mutated snapshot."""
+    snap, flags = synthetic.generate(synthetic.config("C2", groups=2))
+    eng = Engine.for_snapshot(snap)
+    try:
+        views = eng.load(snap)
+        eng.reconcile(flags)
+        rng = np.random.default_rng(11)
+        for epoch in range(3):
+            rows = rng.choice(snap.dims["pods"], 300, replace=False).astype(np.uint32)
+            snap.p_packed[rows] ^= np.uint32(abi.PHASE_RUNNING << abi.PP_PHASE_SHIFT) ^ np.uint32(abi.PHASE_FAILED << abi.PP_PHASE_SHIFT)
+            snap.p_group_name_id[rows[:20]] = snap.p_group_name_id[rows[20:40]]          # relabelled pods move between groups
+            for name in ("p_packed", "p_group_name_id"):
+                np.copyto(views[name], snap.cols[name])
+            eng.commit_pod_rows(np.concatenate([rows, rows[:5]]))                      # duplicates are fine
+            got = eng.reconcile(flags)
+            want = oracle_mod.run(snap, flags, threads=8)
+            assert not want.diff(got), epoch
+    finally:
+        eng.close()
+
+
+def test_compact_action_list_without_pod_lists(oracle_mod):
+    """kr_flags.fetch_pod_lists = 0: only the compact action list comes back; it must equal the oracle's."""
+    snap, flags = synthetic.generate(synthetic.config("C2", groups=2))
+    flags.fetch_pod_lists = 0
+    eng = Engine.for_snapshot(snap)
+    try:
+        eng.load(snap)
+        got = eng.reconcile(flags)
+    finally:
+        eng.close()
+    want = oracle_mod.run(snap, flags, threads=8)
+    assert got.sorted_pod_idx.size == 0 and got.n_actions == want.n_actions > 0
+    assert not want.diff(got)
+    # the list is exactly the non-KEEP entries of the full lists, cluster by cluster
+    keep = (want.sorted_action != abi.ACT_KEEP) & (want.sorted_action != abi.ACT_ORPHAN)
+    assert np.array_equal(got.act_pod_idx, want.sorted_pod_idx[keep]) and np.array_equal(got.act_code, want.sorted_action[keep])
+    assert np.array_equal(np.diff(got.act_start.astype(np.int64)), np.add.reduceat(keep.astype(np.int64), want.clusters["pod_start"].astype(np.int64))
+                          if snap.dims["clusters"] else [])
+
+
 def test_hash_batch_matches_hashlib():
     import base64
     import hashlib

@@ -63,8 +63,6 @@ int main(int argc, char **argv) {
   };
   printf("n=%u messages, %.1f MB\n", n, total / 1e6);
 #define RUN(NAME, ...) { float us = time_it([&]() { __VA_ARGS__; }, flush, flush_bytes, 20); CKC(cudaGetLastError()); check(NAME, us); }
-  RUN("k_hash<1> (1 warp/block)", (k_hash<1><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
-  RUN("k_hash<4> (4 warps/block)", (k_hash<4><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<1,0> cpasync", (k_hash2<1, 0><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<1,1> cpasync+mad", (k_hash2<1, 1><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<4,0> cpasync", (k_hash2<4, 0><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
