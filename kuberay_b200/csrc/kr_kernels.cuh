@@ -1524,14 +1524,34 @@ __device__ __forceinline__ uint32_t mad1(uint32_t a, uint32_t one, uint32_t c) {
   return d;
 }
 
+// rol(x, n) on the FMA pipe: x * 2^n as a 64-bit product puts x << n in the low word and x >> (32 - n) in the high word; the
+// two halves have no bit in common, so lo * 1 + hi is the rotation.  `pow2` and `one` are opaque (derived from a kernel
+// parameter), otherwise ptxas strength-reduces both back to ALU-pipe shifts.
+__device__ __forceinline__ uint32_t rol_fma(uint32_t x, uint32_t pow2, uint32_t one) {
+  uint32_t r;
+  asm("{\n\t.reg .u64 t;\n\t.reg .u32 lo, hi;\n\tmul.wide.u32 t, %1, %2;\n\tmov.b64 {lo, hi}, t;\n\tmad.lo.u32 %0, lo, %3, hi;\n\t}" : "=r"(r) : "r"(x), "r"(pow2), "r"(one));
+  return r;
+}
+
+// VARIANT: 0 = every round operation on the ALU pipe; 1 = s formed by two IMADs; 2..5 = experiments that move off-chain work
+// to the FMA pipe (5: w+K; 2: w+K and rol30(b); 3: w+K and the schedule's rol1; 4: all three) hoping a lone warp would
+// alternate pipes.  It does not pay: at 10k messages 0 -> 82 us, 5 -> 96, 2 -> 121, 3 -> 125, 4 -> 143 us; at 100k messages
+// only VARIANT 1 beats 0 (345 vs 375 us).  The engine uses 0 (latency regime) and 1 (throughput regime); 2..5 stay for
+// tools/hash_bench.cu, which reproduces the table (profiles/r1_hash_variants.txt).
 template <int VARIANT>
 __device__ __forceinline__ void sha1_rounds2(uint32_t (&w)[16], uint32_t (&h)[5], uint32_t one) {
   uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+  const uint32_t two = one << 1, two30 = one << 30;
+  constexpr bool kFmaRol30 = VARIANT == 2 || VARIANT == 4, kFmaRol1 = VARIANT == 3 || VARIANT == 4;
 #pragma unroll
   for (int i = 0; i < 80; i++) {
     uint32_t wi;
     if (i < 16) wi = w[i];
-    else { wi = rol(w[(i - 3) & 15] ^ w[(i - 8) & 15] ^ w[(i - 14) & 15] ^ w[i & 15], 1); w[i & 15] = wi; }
+    else {
+      const uint32_t x = w[(i - 3) & 15] ^ w[(i - 8) & 15] ^ w[(i - 14) & 15] ^ w[i & 15];
+      wi = kFmaRol1 ? rol_fma(x, two, one) : rol(x, 1);
+      w[i & 15] = wi;
+    }
     const uint32_t k = i < 20 ? 0x5A827999u : (i < 40 ? 0x6ED9EBA1u : (i < 60 ? 0x8F1BBCDCu : 0xCA62C1D6u));
     uint32_t f;
     if (i < 20) f = (b & c) | (~b & d);
@@ -1540,10 +1560,11 @@ __device__ __forceinline__ void sha1_rounds2(uint32_t (&w)[16], uint32_t (&h)[5]
     else f = b ^ c ^ d;
     uint32_t s;
     if (VARIANT == 0) s = f + e + (wi + k);            // lone warp per scheduler (latency regime): fewest instructions wins
-    else s = mad1(f, one, mad1(e, one, wi + k));        // many warps per scheduler (throughput regime): adds on the FMA pipe
+    else if (VARIANT == 1) s = mad1(f, one, mad1(e, one, wi + k));  // many warps per scheduler (throughput regime): adds on the FMA pipe
+    else s = f + e + mad1(wi, one, k);                  // w + K is far off the chain: FMA pipe
     asm volatile("" : "+r"(s));  // keep s a value of its own: the a->a chain below is then a single rol5(a)+s
     uint32_t t = rol(a, 5) + s;
-    e = d; d = c; c = rol(b, 30); b = a; a = t;
+    e = d; d = c; c = kFmaRol30 ? rol_fma(b, two30, one) : rol(b, 30); b = a; a = t;
   }
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
 }

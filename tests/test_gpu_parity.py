@@ -215,3 +215,34 @@ def test_hash_batch_matches_hashlib():
         eng.close()
     want = [base64.b32hexencode(hashlib.sha1(m).digest()).decode() for m in msgs]
     assert got == want
+
+
+@pytest.mark.parametrize("seed0", [0, 100, 200, 300])
+def test_fuzz_adversarial_snapshots(seed0, oracle_mod, monkeypatch):
+    """Differential fuzz: tiny snapshots drawn from the whole input domain (tests/fuzz_objects.py), packed like the golden
+    scenarios, engine vs oracle byte for byte.  Every fourth seed also runs the radix / unfused pipeline."""
+    import fuzz_objects
+    for seed in range(seed0, seed0 + 100):
+        snap, flags = fuzz_objects.snapshot(seed, big=(seed % 10 == 0))
+        want = oracle_mod.run(snap, flags, threads=1)
+        eng = Engine.for_snapshot(snap)
+        try:
+            eng.load(snap)
+            got = eng.reconcile(flags)
+        finally:
+            eng.close()
+        d = want.diff(got)
+        assert not d, (seed, d[:8])
+    monkeypatch.setenv("KR_FORCE_RADIX", "1")
+    monkeypatch.setenv("KR_NO_FUSE", "1")
+    for seed in range(seed0, seed0 + 100, 4):
+        snap, flags = fuzz_objects.snapshot(seed)
+        want = oracle_mod.run(snap, flags, threads=1)
+        eng = Engine.for_snapshot(snap)
+        try:
+            eng.load(snap)
+            got = eng.reconcile(flags)
+        finally:
+            eng.close()
+        d = want.diff(got)
+        assert not d, ("radix", seed, d[:8])

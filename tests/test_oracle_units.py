@@ -194,3 +194,16 @@ def test_atoi_semantics_of_replica_index_label():
         return (bool(pk & abi.PP_HAS_REPLICA_IDX), r)
     assert idx("7") == (True, 7) and idx("+7") == (True, 7) and idx("-3") == (True, -3) and idx("007") == (True, 7)
     assert idx(" 7")[0] is False and idx("7a")[0] is False and idx("")[0] is False and idx("1_0")[0] is False
+
+
+@pytest.mark.parametrize("seed0", [0, 100, 200])
+def test_fuzz_list_modes_agree(seed0, oracle_mod):
+    """Adversarial snapshots (tests/fuzz_objects.py): the indexed checker and the namespace-scan List mode (the CPU
+    baseline's cost structure) must produce byte-identical records, single- and multi-threaded."""
+    import fuzz_objects
+    for seed in range(seed0, seed0 + 100):
+        snap, flags = fuzz_objects.snapshot(seed)
+        a = oracle_mod.run(snap, flags, list_mode=oracle_mod.INDEXED, threads=1)
+        b = oracle_mod.run(snap, flags, list_mode=oracle_mod.NS_SCAN, threads=3)
+        d = a.diff(b)
+        assert not d, (seed, d[:5])

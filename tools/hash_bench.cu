@@ -65,6 +65,12 @@ int main(int argc, char **argv) {
 #define RUN(NAME, ...) { float us = time_it([&]() { __VA_ARGS__; }, flush, flush_bytes, 20); CKC(cudaGetLastError()); check(NAME, us); }
   RUN("k_hash2<1,0> cpasync", (k_hash2<1, 0><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<1,1> cpasync+mad", (k_hash2<1, 1><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  RUN("k_hash2<1,5> fma: w+K", (k_hash2<1, 5><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  RUN("k_hash2<1,2> fma: w+K rol30", (k_hash2<1, 2><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  RUN("k_hash2<1,3> fma: w+K rol1", (k_hash2<1, 3><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  RUN("k_hash2<1,4> fma: all three", (k_hash2<1, 4><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  RUN("k_hash2<4,2> fma: w+K rol30", (k_hash2<4, 2><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  RUN("k_hash2<4,4> fma: all three", (k_hash2<4, 4><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<4,0> cpasync", (k_hash2<4, 0><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<4,1> cpasync+mad", (k_hash2<4, 1><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   return 0;
