@@ -246,3 +246,26 @@ def test_fuzz_adversarial_snapshots(seed0, oracle_mod, monkeypatch):
             eng.close()
         d = want.diff(got)
         assert not d, ("radix", seed, d[:8])
+
+
+def test_double_buffered_epochs_two_engines(oracle_mod):
+    """Two engines on one GPU used alternately (bench.py's e2e loop): the asynchronous commit of epoch k+1 is issued before the
+    blocking reconcile of epoch k.  Each epoch carries a different snapshot; every result must match the oracle."""
+    snaps = [synthetic.generate(synthetic.config("C2", seed=synthetic.SEED + i)) for i in range(4)]
+    big = max((s for s, _ in snaps), key=lambda s: s.nbytes())
+    engines = [Engine.for_snapshot(big, slack=1.3), Engine.for_snapshot(big, slack=1.3)]
+    try:
+        def stage(i):
+            eng, (snap, _f) = engines[i & 1], snaps[i]
+            eng.fill(eng.begin(snap.sizes()), snap)
+            eng.commit()
+        stage(0)
+        for i in range(len(snaps)):
+            if i + 1 < len(snaps):
+                stage(i + 1)
+            got = engines[i & 1].reconcile(snaps[i][1])
+            want = oracle_mod.run(snaps[i][0], snaps[i][1], threads=8)
+            assert not want.diff(got), i
+    finally:
+        for eng in engines:
+            eng.close()
