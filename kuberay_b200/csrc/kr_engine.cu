@@ -308,13 +308,18 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   }
 
   // --- stream M
-  CK(cudaMemsetAsync(e->d_scratch, 0xFF, e->sl.ff_total, M));
-  if (n.n_wtd) CK(cudaMemsetAsync(r.wtd_pod_idx, 0xFF, 4 * (size_t)n.n_wtd, M));
-  CK(cudaMemsetAsync(r.totals, 0, 32, M));
   const bool pdl = !profile && e->use_pdl;
   bool fuse_place_done = false;    // k_decide_small directly follows k_place_fused on stream M
   bool creates_after_kernel = false;  // k_creates_fused directly follows a kernel on stream M (no event wait in between)
-  if (!e->force_radix) CK(cudaMemsetAsync(sc.ccount, 0, e->sl.cstart - e->sl.ccount, M));  // per-cluster counts + the chained-scan cells
+  {
+    ClearArgs ca{};
+    ca.ptr[0] = reinterpret_cast<uint32_t *>(e->d_scratch); ca.words[0] = (uint32_t)(e->sl.ff_total / 4); ca.value[0] = 0xFFFFFFFFu;
+    ca.ptr[1] = r.wtd_pod_idx; ca.words[1] = n.n_wtd; ca.value[1] = 0xFFFFFFFFu;
+    ca.ptr[2] = r.totals; ca.words[2] = 8; ca.value[2] = 0;
+    ca.ptr[3] = sc.ccount; ca.words[3] = e->force_radix ? 0u : (uint32_t)((e->sl.cstart - e->sl.ccount) / 4); ca.value[3] = 0;  // per-cluster counts + the chained-scan cells
+    mark("k_clear");
+    k_clear<<<e->sm_count * 2, 256, 0, M>>>(ca);
+  }
   CK(cudaStreamWaitEvent(M, e->ev_cols, wflag));  // the scratch clears above overlap the tail of the upload
   {
     uint32_t items = n.n_clusters + n.n_groups + n.n_heads;
@@ -439,6 +444,13 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
     e->gflags = fk;
     e->gvalid = true;
   }
+#ifdef KR_TIMELINE
+  {
+    unsigned long long init[64];
+    for (int i = 0; i < 64; i++) init[i] = (i & 1) ? 0ull : ~0ull;
+    CK(cudaMemcpyToSymbolAsync(g_tl, init, sizeof init, 0, cudaMemcpyHostToDevice, e->sm));
+  }
+#endif
   CK(cudaGraphLaunch(e->gexec, e->sm));
   return KR_OK;
 }
@@ -516,6 +528,15 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
 
 extern "C" {
 
+#ifdef KR_TIMELINE
+// development aid: (first block start, last block end) in ns of %globaltimer for kernel ids 0..31 of the last graph replay
+int kr_debug_timeline(kr_engine *e, unsigned long long *out64) {
+  CK(cudaStreamSynchronize(e->sm));
+  CK(cudaMemcpyFromSymbol(out64, g_tl, 64 * sizeof(unsigned long long)));
+  return KR_OK;
+}
+#endif
+
 int kr_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return KR_E_NO_DEVICE; }
@@ -555,6 +576,12 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
   cudaFuncSetAttribute(k_place_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   cudaFuncSetAttribute(k_creates_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
+  if (const char *g = getenv("KR_CARVEOUT")) {  // experiment: one shared-memory carveout (percent) for every kernel of the pass
+    int pct = atoi(g);
+    const void *ks[] = {(const void *)k_build_tables, (const void *)k_match<true, kMatchItems>, (const void *)k_place_fused, (const void *)k_decide_small,
+                        (const void *)k_decide, (const void *)k_creates_fused, (const void *)k_jobs, (const void *)k_hash2<1, 0>, (const void *)k_hash2<4, 1>};
+    for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
   if (const char *g = getenv("KR_FORCE_RADIX")) e->env_radix = (g[0] == '1');
   if (const char *g = getenv("KR_NO_FUSE")) e->no_fuse = (g[0] == '1');

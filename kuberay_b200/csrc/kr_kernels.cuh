@@ -110,6 +110,20 @@ static constexpr int kRadixBits = 8;
 static constexpr int kRadix = 1 << kRadixBits;
 
 // ------------------------------------------------------------------------------------------------ small helpers
+#ifdef KR_TIMELINE
+// Development aid (tools/timeline.py, built with -DKR_TIMELINE into a separate library): every kernel stamps the earliest
+// block start and the latest block end it sees (%globaltimer, ns) so the gaps between the kernels of one graph replay show.
+__device__ unsigned long long g_tl[64];
+struct TlScope {
+  int id;
+  __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+  __device__ __forceinline__ explicit TlScope(int i) : id(i) { if (threadIdx.x == 0) atomicMin(&g_tl[2 * id], now()); }
+  __device__ __forceinline__ ~TlScope() { if (threadIdx.x == 0) atomicMax(&g_tl[2 * id + 1], now()); }
+};
+#define KR_TL(id) TlScope tl_scope_(id)
+#else
+#define KR_TL(id)
+#endif
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
@@ -167,10 +181,28 @@ __device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uin
   }
 }
 
+// ------------------------------------------------------------------------------------------------ k_clear
+// One launch for the per-pass clears (hash tables to 0xFF, workersToDelete resolutions to -1, totals and bucket counters
+// to 0) instead of four memset nodes at the head of the graph.
+struct ClearArgs { uint32_t *ptr[4]; uint32_t words[4]; uint32_t value[4]; };
+__global__ void __launch_bounds__(256) k_clear(ClearArgs a) {
+  KR_TL(9);
+  const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    uint32_t *p = a.ptr[r];
+    const uint32_t v = a.value[r], nw = a.words[r];
+    uint4 *p4 = reinterpret_cast<uint4 *>(p);  // every region starts 256-byte aligned
+    for (uint32_t i = t0; i < nw / 4; i += stride) p4[i] = make_uint4(v, v, v, v);
+    for (uint32_t i = (nw & ~3u) + t0; i < nw; i += stride) p[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ k_build_tables
 // One thread per cluster / workersToDelete entry / head-aux row.  Tables were memset to 0xFF.
 
 __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {
+  KR_TL(0);
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n.n_clusters) {
     uint32_t ns = s.c_ns_id[t], name = s.c_name_id[t];
@@ -242,6 +274,7 @@ __device__ __forceinline__ int32_t aux_lookup(const ScratchDev &sc, uint32_t p) 
 // 8 independent memory requests in flight per phase instead of walking one pod's dependent chain at a time.
 template <bool kFast, int kItems>
 __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc, ResDev r, Sizes n, int has_wtd) {
+  KR_TL(1);
   __shared__ uint32_t s_hist[kRadix];
   pdl_wait(); pdl_trigger();
   const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
@@ -1210,6 +1243,7 @@ __device__ __forceinline__ bool small_path(const DecideArgs &a, uint32_t c, uint
 
 // Common case: one warp per RayCluster with <= 256 pods, everything after the bucket load stays in registers.
 __global__ void __launch_bounds__(kDecideWarps * 32, 8) k_decide_small(DecideArgs a) {
+  KR_TL(3);
   __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1225,6 +1259,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32, 8) k_decide_small(DecideArg
 
 // General case: radix pipeline (all clusters), big buckets, clusters with multi-host groups, phase 1, the orphan bucket.
 __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
+  KR_TL(4 + a.phase);
   __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1412,6 +1447,7 @@ __device__ __forceinline__ uint32_t block_scan_to_smem(const uint32_t *__restric
 __global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank, const uint32_t *__restrict__ ccount,
                                                       uint32_t *__restrict__ cstart, const uint32_t *__restrict__ tile_orph, uint32_t *__restrict__ out,
                                                       uint32_t n, uint32_t n_clusters, uint32_t ntiles, uint32_t *totals) {
+  KR_TL(2);
   extern __shared__ uint32_t sm_dyn[];
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
@@ -1438,6 +1474,7 @@ __global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict
 
 // create offsets + replica-index allocation in one persistent kernel (replaces k_scan_creates + k_create_fill)
 __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc, ResDev r, Sizes n, kr_flags f, uint32_t create_cap) {
+  KR_TL(6);
   extern __shared__ uint32_t sm_dyn[];
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
@@ -1480,6 +1517,7 @@ __global__ void __launch_bounds__(256) k_patch_pods(const uint32_t *__restrict__
 // ------------------------------------------------------------------------------------------------ k_jobs
 // RayJob roll-up (rayjob_controller.go:203-216, 343, 885): join by (namespace, status.rayClusterName).
 __global__ void __launch_bounds__(256) k_jobs(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {
+  KR_TL(8);
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n.n_jobs) return;
   kr_job_result jr; jr.cluster_idx = -1; jr.cluster_state = 0; jr.not_ready = 0; jr.status_changed = 0; jr.reserved = 0;
@@ -1573,6 +1611,7 @@ template <int WARPS, int VARIANT>
 __global__ void __launch_bounds__(WARPS * 32) k_hash2(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ off,
                                                       const uint32_t *__restrict__ len32, const uint64_t *__restrict__ off_end,
                                                       uint32_t n, char *__restrict__ out, uint32_t one = 1) {
+  KR_TL(7);
   __shared__ uint4 s_tile[2][WARPS][32][8];  // [buffer][warp][message lane][16-byte piece ^ (lane & 7)]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t m = (blockIdx.x * WARPS + warp) * 32 + lane;

@@ -14,7 +14,7 @@ from . import abi
 from .snapshot import Snapshot
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkrengine.so")
+LIB_PATH = os.environ.get("KR_ENGINE_LIB") or os.path.join(_HERE, "libkrengine.so")  # KR_ENGINE_LIB: development builds (tools/)
 _LIB = None
 
 

@@ -114,6 +114,7 @@ class RayClusterReconciler:
         f.gate_status_conditions = 1 if self.env.status_conditions_gate else 0
         f.gate_multihost_indexing = 1 if self.env.multihost_indexing_gate else 0
         f.env_random_pod_delete = 1 if self.env.enable_random_pod_delete else 0
+        f.fetch_pod_lists = 0  # the side effects below only need the compact action list
         res = self.backend.run(snap, f)
         return PassResult(snap, meta, res, pods)
 
@@ -134,9 +135,9 @@ class RayClusterReconciler:
         cr = res.clusters[ci]
         ns, cname = meta.cluster_keys[ci]
         cluster = cl.clusters[(ns, cname)]
-        seg = range(int(cr["pod_start"]), int(cr["pod_start"]) + int(cr["n_pods"])) if cr["path"] != abi.PATH_SKIPPED or cr["n_pods"] else range(0)
-        # pods of this cluster in list order with their actions (n_pods is 0 for CF_SKIP clusters)
-        listed = [(int(res.sorted_pod_idx[i]), int(res.sorted_action[i])) for i in seg]
+        # the compact action list: only the pods this cluster must act on, in List order (what a shim running with
+        # kr_flags.fetch_pod_lists = 0 downloads; the full sorted_pod_idx / sorted_action lists are not needed here)
+        listed = [(int(res.act_pod_idx[i]), int(res.act_code[i])) for i in range(int(res.act_start[ci]), int(res.act_start[ci + 1]))]
         ev = cl.events.append
         path = int(cr["path"])
         if path == abi.PATH_SKIPPED:
@@ -171,7 +172,7 @@ class RayClusterReconciler:
         if ha == abi.HEAD_SKIP_RESTART:
             return None
         if ha == abi.HEAD_MULTIPLE:                 # :738-747
-            names = [pr.pods[pi]["name"] for pi, _ in listed if (pr.pods[pi].get("labels") or {}).get(snapmod.RAY_NODE_TYPE_LABEL) == "head"]
+            names = [p["name"] for p in cl.pods_of(ns, cname, **{snapmod.RAY_NODE_TYPE_LABEL: "head"})]  # the head List of :674
             return f"{int(cr['err_arg'])} head pods found {names}. Please delete extra head pods"
         if ha == abi.HEAD_CREATE:                   # :735, createHeadPod :1307-1337
             pod = self._build_pod(cluster, "head", "headgroup", f"{cname}-head-{cl.gen_suffix()}")
