@@ -576,10 +576,20 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
   cudaFuncSetAttribute(k_place_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   cudaFuncSetAttribute(k_creates_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
-  if (const char *g = getenv("KR_CARVEOUT")) {  // experiment: one shared-memory carveout (percent) for every kernel of the pass
-    int pct = atoi(g);
+  {
+    // One shared-memory carveout for every kernel of the pass.  An SM can only change its L1 / shared-memory split while it is
+    // idle, and the hash kernel keeps every SM busy for the first half of the pass: with per-kernel defaults the main chain
+    // either inherits whatever split the previous pass left behind (k_match then runs with a minimal L1: 60 us instead of
+    // 38 us) or waits for the hash to drain (split 0 / 25: k_place_fused starts 40-150 us late).  50 % holds the largest
+    // shared-memory user (k_creates_fused, 80 KB) and leaves 114 KB of L1 for the table probes.  Measured with
+    // tools/timeline.py at C3: pass 190 us (default) -> 166 us (50); KR_CARVEOUT=<percent> overrides.
+    int pct = 50;
+    if (const char *g = getenv("KR_CARVEOUT")) pct = atoi(g);
     const void *ks[] = {(const void *)k_build_tables, (const void *)k_match<true, kMatchItems>, (const void *)k_place_fused, (const void *)k_decide_small,
-                        (const void *)k_decide, (const void *)k_creates_fused, (const void *)k_jobs, (const void *)k_hash2<1, 0>, (const void *)k_hash2<4, 1>};
+                        (const void *)k_decide, (const void *)k_creates_fused, (const void *)k_jobs, (const void *)k_hash2<1, 0>, (const void *)k_hash2<4, 1>,
+                        (const void *)k_clear, (const void *)k_match<false, kSortItems>, (const void *)k_hist, (const void *)k_scan_rows, (const void *)k_scatter,
+                        (const void *)k_scan_counts, (const void *)k_place, (const void *)k_scan_creates, (const void *)k_create_fill, (const void *)k_scan_actions,
+                        (const void *)k_compact_actions};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
