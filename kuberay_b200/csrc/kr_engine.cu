@@ -558,9 +558,14 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   e->in_cap = in_layout(cap).total;
   e->scratch_cap = scratch_layout(cap).total;
   e->out_cap = out_layout(cap, cfg->max_creates).total;
-  if (cudaStreamCreateWithFlags(&e->sm, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
-  if (cudaStreamCreateWithFlags(&e->sh, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
-  if (cudaStreamCreateWithFlags(&e->sg, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
+  // Block-scheduling priorities (kept by the captured graph nodes): the short general-decide kernel on G goes ahead of the
+  // k_decide_small blocks still queued on M, and both go ahead of the hash, which is never on the critical path of the chain.
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  const int prio_m = prio_greatest < prio_least ? prio_greatest + 1 : prio_greatest;
+  if (cudaStreamCreateWithPriority(&e->sm, cudaStreamNonBlocking, prio_m) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaStreamCreateWithPriority(&e->sh, cudaStreamNonBlocking, prio_least) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaStreamCreateWithPriority(&e->sg, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaStreamCreateWithFlags(&e->scopy, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
   cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_h2d1); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
   cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming);

@@ -1464,11 +1464,24 @@ __global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict
     for (uint32_t i = threadIdx.x; i <= nb; i += blockDim.x) cstart[i] = sm_start[i];
     if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
   }
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    uint32_t c = __ldg(&key[p]);
-    uint32_t pos = sm_start[c] + __ldg(&rank[p]);
-    if (c == n_clusters) pos += sm_orph[p / kMatchTile];
-    out[pos] = p;
+  // four pods per thread per trip: all eight loads are in flight before the first dependent shared-memory lookup
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < n; p0 += 4 * stride) {
+    uint32_t c[4], rk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t p = p0 + k * stride;
+      c[k] = p < n ? __ldg(&key[p]) : 0u;
+      rk[k] = p < n ? __ldg(&rank[p]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t p = p0 + k * stride;
+      if (p >= n) break;
+      uint32_t pos = sm_start[c[k]] + rk[k];
+      if (c[k] == n_clusters) pos += sm_orph[p / kMatchTile];
+      out[pos] = p;
+    }
   }
 }
 

@@ -269,3 +269,25 @@ def test_double_buffered_epochs_two_engines(oracle_mod):
     finally:
         for eng in engines:
             eng.close()
+
+
+def test_parity_c5_autoscaling_sharded_over_8(oracle_mod):
+    """C5 (BASELINE.json configs[4]): 1 000 autoscaling RayClusters x 100 pods, UID-hash sharded 8 ways.
+    Every shard goes through the engine; its records must equal the global CPU pass restricted to the shard's clusters —
+    the path needs no exchange between GPUs."""
+    snap, flags = synthetic.generate(synthetic.config("C5", wtd_group_frac=0.3))
+    glob = oracle_mod.run(snap, flags, threads=8)
+    world, seen = 8, 0
+    for rank in range(world):
+        sh = synthetic.shard_by_uid(snap, rank, world)
+        got = _parity(sh, flags, oracle_mod)
+        keep = (snap.c_uid_hash % np.uint64(world)) == np.uint64(rank)
+        for fld in ("path", "head_action", "err_kind", "err_arg", "n_pods", "new_state", "needs_status_write", "counts", "cond_status"):
+            assert np.array_equal(got.clusters[fld], glob.clusters[keep][fld]), (rank, fld)
+        assert np.array_equal(got.hash, glob.hash[keep])
+        gkeep = keep[snap.g_cluster_idx]
+        for fld in ("expected", "n_running", "diff", "n_create", "flags"):
+            assert np.array_equal(got.groups[fld], glob.groups[gkeep][fld]), (rank, fld)
+        seen += sh.dims["clusters"]
+    assert seen == snap.dims["clusters"]
+    assert (glob.groups["flags"] & abi.GR_WTD_EXECUTED).any()
