@@ -293,7 +293,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   if (!profile) { CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0)); }
   CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
   auto launch_hash = [&]() {
-    if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {
+    if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {  // (CTAs of 2 or 4 warps confine the hash to fewer SMs; measured: no gain for the chain)
       uint32_t blocks = (n.n_clusters + 31) / 32;
       k_hash2<1, 0><<<blocks, 32, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
     } else {
@@ -594,7 +594,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
                         (const void *)k_decide, (const void *)k_creates_fused, (const void *)k_jobs, (const void *)k_hash2<1, 0>, (const void *)k_hash2<4, 1>,
                         (const void *)k_clear, (const void *)k_match<false, kSortItems>, (const void *)k_hist, (const void *)k_scan_rows, (const void *)k_scatter,
                         (const void *)k_scan_counts, (const void *)k_place, (const void *)k_scan_creates, (const void *)k_create_fill, (const void *)k_scan_actions,
-                        (const void *)k_compact_actions};
+                        (const void *)k_compact_actions, (const void *)k_patch_pods};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
