@@ -175,6 +175,7 @@ struct kr_engine {
   bool gvalid = false;
   bool use_graph = true;
   bool use_pdl = true;        // KR_NO_PDL=1 disables programmatic dependent launch
+  int place_ctas = 1;         // k_place_fused CTAs per SM (KR_PLACE_CTAS; measured at C3: 1 -> 25 us, 2 -> 35 us next to the hash)
   // pipeline choice: fast = count/place/in-warp sort (every bucket <= 1024 pods); radix = general stable LSD sort.
   bool force_radix = false;   // sticky per layout: set when a pass met a bucket the fast pipeline cannot sort
   bool ran_fast = false;
@@ -290,8 +291,6 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   // the committed snapshot: columns gate stream M, the JSON arena gates the hash
   const unsigned wflag = capturing ? cudaEventWaitExternal : cudaEventWaitDefault;
   // (the fork comes first so the hash can start while the columns are still landing — an incremental pod-row epoch leaves the JSON untouched)
-  if (!profile) { CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0)); }
-  CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
   auto launch_hash = [&]() {
     if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {  // (CTAs of 2 or 4 warps confine the hash to fewer SMs; measured: no gain for the chain)
       uint32_t blocks = (n.n_clusters + 31) / 32;
@@ -301,11 +300,18 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       k_hash2<4, 1><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
     }
   };
-  if (!profile) {
+  auto start_hash_stream = [&]() -> int {
+    if (profile) return KR_OK;
+    CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0));
+    CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
     if (do_hash) launch_hash();
     else if (n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, H));
     CK(cudaEventRecord(e->ev_hash, H));
-  }
+    return KR_OK;
+  };
+  // The hash goes first: its 313 one-warp CTAs must be resident before the main chain fills the SMs (launched after
+  // k_build_tables instead, they queue behind the chain's blocks and the hash takes 250 us instead of 100).
+  { int rc = start_hash_stream(); if (rc) return rc; }
 
   // --- stream M
   const bool pdl = !profile && e->use_pdl;
@@ -338,7 +344,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       fuse_place_done = true;
       mark("k_place_fused");
       size_t smem = 4 * ((size_t)n.n_clusters + 2 + mtiles);
-      CK(launch_pdl(k_place_fused, dim3(e->sm_count * 2), dim3(1024), smem, M, pdl, (const uint32_t *)sc.keys[0], (const uint32_t *)sc.keys[1], (const uint32_t *)sc.ccount, sc.cstart,
+      CK(launch_pdl(k_place_fused, dim3(e->sm_count * e->place_ctas), dim3(1024), smem, M, pdl, (const uint32_t *)sc.keys[0], (const uint32_t *)sc.keys[1], (const uint32_t *)sc.ccount, sc.cstart,
                     (const uint32_t *)sc.tile_orph, sc.vals[0], n.n_pods, n.n_clusters, mtiles, r.totals));
     } else {
     mark("k_scan_counts");
@@ -601,6 +607,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (const char *g = getenv("KR_FORCE_RADIX")) e->env_radix = (g[0] == '1');
   if (const char *g = getenv("KR_NO_FUSE")) e->no_fuse = (g[0] == '1');
   if (const char *g = getenv("KR_NO_PDL")) e->use_pdl = !(g[0] == '1');
+  if (const char *g = getenv("KR_PLACE_CTAS")) e->place_ctas = atoi(g) > 0 ? atoi(g) : 1;
   e->force_radix = e->env_radix;
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   *out = e;
