@@ -301,20 +301,38 @@ def main():
         cols_s += time.perf_counter() - t0
     cols_bytes = eng.last_profile()["h2d_bytes"]
     barrier()
-    # additional figure: an incremental epoch — 1 % of the pods changed status (informer Update events); only their rows are
-    # uploaded (kr_snapshot_commit_pod_rows).  Rewriting the rows in the arenas is host packing and is not timed.
+    # additional figure: an incremental epoch — informer events touched 1 % of the pods: 0.8 % status
+    # updates, 0.1 % deletions (their rows become KR_PP_TOMBSTONE rows), 0.1 % additions (into the rows freed one step earlier).
+    # Uploaded: those rows (kr_snapshot_commit_pod_rows) + every RayCluster / group / head / RayJob row (KR_PART_OBJECTS).
+    # Rewriting the rows in the arenas is host packing and is not timed.
     rng_c = np.random.default_rng(5)
-    churn = max(1, snap.dims["pods"] // 100)
+    npods = snap.dims["pods"]
+    pod_cols = [name for name, _dt, _m, dim in _abi.COLUMNS if dim == "pods"]
+    workers = np.nonzero(((snap.p_packed >> _abi.PP_NODE_TYPE_SHIFT) & 3) != _abi.NT_HEAD)[0].astype(np.uint32)
+    n_upd, n_del = max(1, npods * 8 // 1000), max(1, npods // 1000)
+    freed = np.zeros(0, dtype=np.uint32)
     inc_s, inc_bytes = 0.0, 0
     for _ in range(args.steps):
-        rows = rng_c.choice(snap.dims["pods"], churn, replace=False).astype(np.uint32)
-        views["p_packed"][rows] ^= np.uint32(1 << 5)  # PodReady True <-> absent
+        for c in pod_cols:  # Pods created since the last epoch take the rows freed one step earlier
+            views[c][freed] = snap.cols[c][freed]
+        gone = rng_c.choice(workers, n_del, replace=False)
+        gone = gone[~np.isin(gone, freed)]
+        for c in pod_cols:
+            views[c][gone] = 0
+        views["p_packed"][gone] = np.uint32(_abi.PP_TOMBSTONE)
+        upd = rng_c.choice(npods, n_upd, replace=False).astype(np.uint32)
+        upd = upd[~np.isin(upd, gone)]
+        views["p_packed"][upd] ^= np.uint32(1 << 5)  # PodReady True <-> absent
+        rows = np.concatenate([freed, gone, upd])
         t0 = time.perf_counter()
+        eng.commit(_abi.PART_OBJECTS)
+        obj_bytes = eng.last_profile()["h2d_bytes"]
         eng.commit_pod_rows(rows)
         eng.reconcile(flags, copy=False)
         inc_s += time.perf_counter() - t0
         inc_prof = eng.last_profile()
-        inc_bytes = inc_prof["h2d_bytes"]
+        inc_bytes = inc_prof["h2d_bytes"] + obj_bytes
+        freed = gone
     barrier()
     # host packing stand-in (not in e2e): copying pre-packed columns into the pinned arenas
     t0 = time.perf_counter()
@@ -373,7 +391,8 @@ def main():
             "e2e_spec_json_resident": {"value": nc_total * args.steps / (cols_ms / 1e3), "unit": UNIT, "ms_per_step": cols_ms / args.steps, "h2d_bytes_per_step": int(cols_bytes),
                                        "note": "extra, not the headline: columns re-uploaded every step, spec-JSON arena kept in HBM from the previous epoch (no spec changed)"},
             "e2e_incremental_1pct_pod_churn": {"value": nc_total * args.steps / (inc_ms / 1e3), "unit": UNIT, "ms_per_step": inc_ms / args.steps, "h2d_bytes_per_step": int(inc_bytes), "patch_ms": inc_prof["h2d_ms"], "kernels_ms": inc_prof["kernels_ms"], "d2h_ms": inc_prof["d2h_ms"],
-                                               "note": "extra, not the headline: per step 1 % of the pods changed status and only their rows are uploaded (kr_snapshot_commit_pod_rows)"},
+                                               "note": "extra, not the headline: per step informer events touched 1 % of the pods (0.8 % status updates, 0.1 % deletions -> tombstone rows, 0.1 % additions into freed rows); "
+                                                       "uploaded: those rows (kr_snapshot_commit_pod_rows) + all RayCluster/group/head/RayJob rows (KR_PART_OBJECTS)"},
             "gpu_launches": int(n_kernels) * args.steps,
             "clocks": clocks,
             "roofline": roof,

@@ -107,6 +107,9 @@ enum {
 #define KR_PP_RAY_TERMINATED  (1u << 8)   /* getRayContainerStateTerminated(pod) != nil (:1237-1248) */
 #define KR_PP_HAS_DELETION_TS (1u << 9)
 #define KR_PP_HAS_REPLICA_IDX (1u << 10)  /* label ray.io/worker-group-replica-index present AND strconv.Atoi succeeded (:857-860) */
+#define KR_PP_TOMBSTONE       (1u << 12)  /* free row of an incrementally maintained arena (a Pod that left the informer cache, or spare
+                                             capacity): the shim writes ns_id = cluster_name_id = 0 with this bit; the row matches no
+                                             RayCluster, is reported as KR_ACT_TOMBSTONE after the orphans' segment and is not counted */
 enum { KR_NT_NONE = 0, KR_NT_HEAD = 1, KR_NT_WORKER = 2, KR_NT_REDIS = 3 };
 enum { KR_PHASE_EMPTY = 0, KR_PHASE_PENDING = 1, KR_PHASE_RUNNING = 2, KR_PHASE_SUCCEEDED = 3, KR_PHASE_FAILED = 4, KR_PHASE_UNKNOWN = 5 };
 
@@ -124,6 +127,7 @@ enum {
   KR_ACT_DELETE_MH_UNHEALTHY = 9,    /* multi-host: unhealthy replica (:999) */
   KR_ACT_DELETE_MH_WTD = 10,         /* multi-host: autoscaler scale-down request (:1030) */
   KR_ACT_DELETE_MH_SCALE_DOWN = 11,  /* multi-host: scaling down (:1114) */
+  KR_ACT_TOMBSTONE = 254,            /* free row (KR_PP_TOMBSTONE) — listed among the orphans, not counted in n_orphans */
   KR_ACT_ORPHAN = 255                /* pod matched no RayCluster in the snapshot */
 };
 
@@ -395,7 +399,13 @@ int kr_snapshot_commit(kr_engine *e);
 /* Upload only some parts of the arenas; the rest keeps what the previous commit of the SAME layout (same kr_sizes, and for
  * KR_PART_JSON the same c_json_off/c_json_len) put in HBM.  Typical epoch: pod statuses moved but no spec did — commit
  * KR_PART_COLUMNS and keep the spec-JSON arena resident (the hash is still recomputed from it every pass). */
-enum { KR_PART_COLUMNS = 1, KR_PART_JSON = 2, KR_PART_ALL = 3 };
+enum {
+  KR_PART_COLUMNS = 1,  /* every column */
+  KR_PART_JSON = 2,     /* the muted-spec JSON arena */
+  KR_PART_ALL = 3,
+  KR_PART_OBJECTS = 4   /* every column except the seven per-pod ones: RayCluster / group / workersToDelete / head-aux / RayJob
+                           rows (about 2 MB at C3).  Together with kr_snapshot_commit_pod_rows this is an incremental epoch. */
+};
 int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts);
 
 /* Incremental epoch: the caller has rewritten the 7 pod columns of `rows[0..n)` in the pinned arenas

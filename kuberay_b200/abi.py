@@ -48,12 +48,14 @@ PP_RESTART_NEVER = 1 << 7
 PP_RAY_TERMINATED = 1 << 8
 PP_HAS_DELETION_TS = 1 << 9
 PP_HAS_REPLICA_IDX = 1 << 10
+PP_TOMBSTONE = 1 << 12
 NT_NONE, NT_HEAD, NT_WORKER, NT_REDIS = range(4)
 PHASE_EMPTY, PHASE_PENDING, PHASE_RUNNING, PHASE_SUCCEEDED, PHASE_FAILED, PHASE_UNKNOWN = range(6)
 
 (ACT_KEEP, ACT_DELETE_ALL_SUSPEND, ACT_DELETE_ALL_RECREATE, ACT_DELETE_HEAD, ACT_DELETE_GROUP_SUSPEND,
  ACT_DELETE_UNHEALTHY, ACT_DELETE_WTD, ACT_DELETE_RANDOM, ACT_DELETE_MH_INCOMPLETE, ACT_DELETE_MH_UNHEALTHY,
  ACT_DELETE_MH_WTD, ACT_DELETE_MH_SCALE_DOWN) = range(12)
+ACT_TOMBSTONE = 254
 ACT_ORPHAN = 255
 
 PATH_NORMAL, PATH_SKIPPED, PATH_SUSPENDING_DELETE_ALL, PATH_SUSPENDED_NOOP, PATH_RECREATE_DELETE_ALL = range(5)
@@ -77,7 +79,7 @@ ANNOT_EMPTY, ANNOT_HASH32, ANNOT_OTHER = 0, 1, 2
 VER_EMPTY, VER_CURRENT, VER_DIFFERENT = 0, 1, 2
 SVCIP_NORMAL, SVCIP_EMPTY, SVCIP_NONE = 0, 1, 2
 
-PART_COLUMNS, PART_JSON, PART_ALL = 1, 2, 3
+PART_COLUMNS, PART_JSON, PART_ALL, PART_OBJECTS = 1, 2, 3, 4
 KR_OK, KR_E_INVALID, KR_E_CAPACITY, KR_E_CUDA, KR_E_STATE, KR_E_NO_DEVICE = 0, -1, -2, -3, -4, -5
 MAX_KERNEL_TIMES = 24
 

@@ -31,7 +31,7 @@ struct InLayout {  // offsets of every input column inside the snapshot arena
 // (element size, per-row multiplicity, dimension index) in the order of kr_snapshot_bufs
 enum { D_CLUSTERS, D_GROUPS, D_WTD, D_PODS, D_HEADS, D_JOBS, D_JSON };
 struct ColDesc { uint8_t elem, mult, dim; };
-const ColDesc kCols[] = {
+constexpr ColDesc kCols[] = {
     {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {8, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {1, 1, D_CLUSTERS}, {1, 1, D_CLUSTERS},
     {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {8, 1, D_CLUSTERS}, {4, 1, D_CLUSTERS},
     {1, 1, D_CLUSTERS}, {4, 5, D_CLUSTERS}, {1, 5, D_CLUSTERS}, {1, 5, D_CLUSTERS}, {4, 1, D_CLUSTERS}, {4, 2, D_CLUSTERS},
@@ -45,6 +45,9 @@ const ColDesc kCols[] = {
     {1, 1, D_JSON},
 };
 constexpr int kNumCols = sizeof(kCols) / sizeof(kCols[0]);
+constexpr int kFirstPodCol = 32;  // p_ns_id ... p_replica_name_id are columns 32..38
+static_assert(kCols[kFirstPodCol].dim == D_PODS && kCols[kFirstPodCol - 1].dim != D_PODS && kCols[kFirstPodCol + 6].dim == D_PODS && kCols[kFirstPodCol + 7].dim != D_PODS,
+              "kFirstPodCol must point at the seven per-pod columns");
 static_assert(sizeof(kr_snapshot_bufs) == kNumCols * sizeof(void *), "kCols must mirror kr_snapshot_bufs");
 static_assert(sizeof(SnapDev) == kNumCols * sizeof(void *), "SnapDev must mirror kr_snapshot_bufs");
 static_assert(sizeof(kr_cluster_result) == 96 && sizeof(kr_group_result) == 32 && sizeof(kr_job_result) == 8, "result record sizes");
@@ -696,6 +699,11 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   size_t bytes = 0;
   CK(cudaEventRecord(e->ev_h2d0, e->scopy));
   if ((parts & KR_PART_COLUMNS) && json_off) { CK(cudaMemcpyAsync(e->d_in, e->h_in, json_off, cudaMemcpyHostToDevice, e->scopy)); bytes += json_off; }
+  else if (parts & KR_PART_OBJECTS) {  // the columns on either side of the seven per-pod ones
+    const size_t a1 = e->il.off[kFirstPodCol], b0 = e->il.off[kFirstPodCol + 7];
+    if (a1) { CK(cudaMemcpyAsync(e->d_in, e->h_in, a1, cudaMemcpyHostToDevice, e->scopy)); bytes += a1; }
+    if (json_off > b0) { CK(cudaMemcpyAsync(e->d_in + b0, e->h_in + b0, json_off - b0, cudaMemcpyHostToDevice, e->scopy)); bytes += json_off - b0; }
+  }
   CK(cudaEventRecord(e->ev_cols, e->scopy));
   if ((parts & KR_PART_JSON) && e->il.total > json_off) {
     CK(cudaMemcpyAsync(e->d_in + json_off, e->h_in + json_off, e->il.total - json_off, cudaMemcpyHostToDevice, e->scopy));

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
         for (uint32_t gi = 1; gi < rec[it].y; gi++)
           if (__ldg(&s.g_name_id[g0 + gi]) == gn[it]) { slot = gi; break; }  // group names are unique (pkg/webhooks/v1/raycluster_webhook.go:74)
     }
-    uint32_t flags = pk[it] & 0x7FFu;
+    uint32_t flags = pk[it] & (0x7FFu | KR_PP_TOMBSTONE);  // bit 11 of the row word is KR_ROW_WTD_OWN
     if (has_wtd) {
       const uint64_t k = key2(ns[it], nm[it]);
       uint32_t i = wi[it];
@@ -1277,15 +1277,23 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
     seg1 = (c == Nc) ? Np : warp_lower_bound(a.sorted_keys, Np, c + 1, lane);
   }
   const uint32_t P = seg1 - seg0;
-  if (c == Nc) {  // the orphan bucket: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot
-    if (a.phase != 0) return;
-    for (uint32_t i = seg0 + lane; i < seg1; i += 32) {
-      if (a.fast) a.r.sorted_pod_idx[i] = LDG(a.unsorted[i]);  // k_match/k_place put the orphans in List order already
-      a.r.sorted_action[i] = KR_ACT_ORPHAN;
+  if (a.phase == 0) {
+    // The orphans' segment: pods whose (namespace, ray.io/cluster) names no RayCluster in the snapshot, and the free rows of an
+    // incrementally maintained arena (KR_PP_TOMBSTONE; there can be many).  Every warp of the grid labels a strided share.
+    const uint32_t o0 = a.fast ? LDG(a.sc.cstart[Nc]) : warp_lower_bound(a.sorted_keys, Np, Nc, lane);
+    const uint32_t gw = blockIdx.x * kDecideWarps + warp, nw = gridDim.x * kDecideWarps;
+    uint32_t real = 0;
+    for (uint32_t i = o0 + gw * 32 + lane; i < Np; i += nw * 32) {
+      const uint32_t pod = a.fast ? LDG(a.unsorted[i]) : a.r.sorted_pod_idx[i];  // k_match/k_place put this segment in List order already
+      if (a.fast) a.r.sorted_pod_idx[i] = pod;
+      const bool tomb = reinterpret_cast<const uint32_t *>(a.sc.rows)[4 * (size_t)pod + 3] & KR_PP_TOMBSTONE;
+      a.r.sorted_action[i] = tomb ? KR_ACT_TOMBSTONE : KR_ACT_ORPHAN;
+      real += tomb ? 0u : 1u;
     }
-    if (lane == 0) a.r.totals[1] = P;
-    return;
+    real = __reduce_add_sync(0xFFFFFFFFu, real);
+    if (lane == 0 && real) atomicAdd(&a.r.totals[1], real);
   }
+  if (c == Nc) return;
   if (small_path(a, c, P)) return;  // k_decide_small owns it
   // fast pipeline, phase 0: informer List order inside the bucket = ascending pod index (phase 1 finds it already sorted)
   if (a.fast && a.phase == 0 && P <= KR_FAST_MAX_BUCKET) { warp_sort_dispatch(a.unsorted + seg0, a.r.sorted_pod_idx + seg0, P, lane); __syncwarp(); }

@@ -247,6 +247,9 @@ def compute_endpoints(old: dict | None, svc: dict | None) -> dict | None:
     return out
 
 
+TOMBSTONE = {"tombstone": True}  # the pod "object" of a free arena row
+
+
 @dataclass
 class PackMeta:
     interner: Interner
@@ -389,6 +392,10 @@ def pack_objects(clusters: list[dict], pods: list[dict], jobs: list[dict] | None
                 w += 1
             g += 1
     for pi, p in enumerate(pods):
+        if p.get("tombstone"):  # free row of an incrementally maintained arena (KR_PP_TOMBSTONE): all ids 0, matches nothing
+            meta.pod_keys.append((None, None))
+            s.p_packed[pi] = abi.PP_TOMBSTONE
+            continue
         labels = p.get("labels") or {}
         ns = p.get("namespace", "default")
         meta.pod_keys.append((ns, p["name"]))

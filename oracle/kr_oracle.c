@@ -811,13 +811,14 @@ static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags
     uint32_t run = 0;
     for (uint32_t g = 0; g < n->n_groups; g++) { out->groups[g].create_off = run; run += out->groups[g].n_create; }
     /* pods bucketed by cluster, list order; orphans last */
-    uint32_t Nc = n->n_clusters, n_actions = 0;
+    uint32_t Nc = n->n_clusters, n_actions = 0, n_tomb = 0;
     for (uint32_t i = 0; i < n->n_pods; i++) {
       uint32_t p = x.cl_pods[i];
       out->sorted_pod_idx[i] = p;
-      uint8_t a = x.pod_cluster[p] == Nc ? KR_ACT_ORPHAN : x.act[p];
+      uint8_t a = x.pod_cluster[p] == Nc ? ((s->p_packed[p] & KR_PP_TOMBSTONE) ? KR_ACT_TOMBSTONE : KR_ACT_ORPHAN) : x.act[p];
       out->sorted_action[i] = a;
-      if (a != KR_ACT_KEEP && a != KR_ACT_ORPHAN) n_actions++;
+      if (a == KR_ACT_TOMBSTONE) n_tomb++;
+      if (a != KR_ACT_KEEP && a != KR_ACT_ORPHAN && a != KR_ACT_TOMBSTONE) n_actions++;
     }
     for (uint32_t c = 0; c < Nc; c++) out->clusters[c].pod_start = x.cl_start[c];
     /* compact action list, cluster-major, list order inside a cluster */
@@ -830,7 +831,7 @@ static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags
       }
     }
     out->act_start[Nc] = na;
-    out->n_orphans = x.cl_start[Nc + 1] - x.cl_start[Nc];
+    out->n_orphans = x.cl_start[Nc + 1] - x.cl_start[Nc] - n_tomb;  /* free rows sit in the orphans' segment but are not orphans */
     out->n_actions = n_actions;
   }
   for (int t = 0; t < threads; t++) free(args[t].creates.v);
