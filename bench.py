@@ -120,20 +120,21 @@ def build_workload(name: str, rank: int, world: int):
     return snap, flags, params
 
 
-def cpu_arm(snap, flags, budget_s: float, threads: int):
+def cpu_arm(snap, flags, budget_s: float, threads: int, list_mode=None):
     """Time the CPU restatement (oracle port, namespace-scan Lists like controller-runtime's CacheReader) on a bounded sample."""
     from oracle import oracle
+    mode = oracle.NS_SCAN if list_mode is None else list_mode
     nc = snap.dims["clusters"]
     probe = min(nc, max(threads * 4, 32))
     t0 = time.perf_counter()
-    oracle.run_range(snap, flags, 0, probe, list_mode=oracle.NS_SCAN, threads=threads)
+    oracle.run_range(snap, flags, 0, probe, list_mode=mode, threads=threads)
     dt = time.perf_counter() - t0
     rate = probe / max(dt, 1e-9)
     sample = int(min(nc, max(probe, rate * budget_s)))
     # a bounded sample of the workload; when the whole snapshot takes less than the budget it is repeated instead
     done, t0 = 0, time.perf_counter()
     while True:
-        oracle.run_range(snap, flags, 0, sample, list_mode=oracle.NS_SCAN, threads=threads)
+        oracle.run_range(snap, flags, 0, sample, list_mode=mode, threads=threads)
         done += sample
         dt = time.perf_counter() - t0
         if sample < nc or dt >= budget_s:
@@ -412,6 +413,14 @@ def main():
             v, sample, dt = cpu_arm(snap, flags, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{sample} reconciles over the {nc_local}-cluster snapshot in {dt:.1f} s (CPU restatement in C, namespace-scan Lists; not the Go controller)"}
+            # the same port on one thread (the reference's default ReconcileConcurrency = 1, apis/config/v1alpha1/defaults.go:11)
+            # and with pods pre-bucketed by cluster, so the GPU/CPU ratio is not credited to removing the namespace scan alone
+            from oracle import oracle as _o
+            v1, s1, d1 = cpu_arm(snap, flags, args.cpu_seconds / 4, 1)
+            vi, si, di = cpu_arm(snap, flags, args.cpu_seconds / 4, threads, list_mode=_o.INDEXED)
+            line["cpu_baseline_variants"] = {
+                "one_thread_namespace_scan": {"value": v1, "unit": UNIT, "cores": 1, "sample": f"{s1} reconciles in {d1:.1f} s"},
+                "all_threads_indexed_lists": {"value": vi, "unit": UNIT, "cores": threads, "sample": f"{si} reconciles in {di:.1f} s (pods pre-bucketed by cluster: no namespace scan)"}}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:

@@ -291,3 +291,55 @@ def test_parity_c5_autoscaling_sharded_over_8(oracle_mod):
         seen += sh.dims["clusters"]
     assert seen == snap.dims["clusters"]
     assert (glob.groups["flags"] & abi.GR_WTD_EXECUTED).any()
+
+
+def test_error_paths_return_codes_not_crashes(oracle_mod):
+    """The C ABI never throws across the boundary: misuse and capacity overruns come back as KR_E_* codes with a message
+    (kr_last_error), and the engine stays usable afterwards — the Go side falls back to the per-object path for that epoch."""
+    from kuberay_b200.engine import EngineError
+    snap, flags = synthetic.generate(synthetic.config("C1"))
+    eng = Engine.for_snapshot(snap, max_creates=1024)
+    try:
+        # a snapshot larger than the capacities given to kr_engine_create
+        big, _ = synthetic.generate(synthetic.config("C2"))
+        with pytest.raises(EngineError) as ei:
+            eng.begin(big.sizes())
+        assert ei.value.code == abi.KR_E_CAPACITY
+        # partial / incremental commits before this layout was ever fully uploaded
+        views = eng.begin(snap.sizes())
+        eng.fill(views, snap)
+        for call in (lambda: eng.commit(abi.PART_COLUMNS), lambda: eng.commit(abi.PART_OBJECTS), lambda: eng.commit_pod_rows(np.array([0], dtype=np.uint32))):
+            with pytest.raises(EngineError) as ei:
+                call()
+            assert ei.value.code == abi.KR_E_STATE
+        # broken invariants are caught on the host at commit: misaligned JSON offset, groups out of cluster order
+        views["c_json_off"][1] += 1
+        with pytest.raises(EngineError) as ei:
+            eng.commit()
+        assert ei.value.code == abi.KR_E_INVALID and "16-byte" in str(ei.value)
+        views["c_json_off"][1] -= 1
+        views["c_group_off"][2] += 1
+        with pytest.raises(EngineError) as ei:
+            eng.commit()
+        assert ei.value.code == abi.KR_E_INVALID
+        views["c_group_off"][2] -= 1
+        eng.commit()
+        # a pod row outside the arena
+        with pytest.raises(EngineError) as ei:
+            eng.commit_pod_rows(np.array([snap.dims["pods"]], dtype=np.uint32))
+        assert ei.value.code == abi.KR_E_INVALID
+        # more pods to create than kr_config.max_creates: the pass runs, the fetch reports the overrun
+        views["g_replicas"][:] = 500
+        views["g_max"][:] = 2 ** 31 - 1
+        views["g_flags"][:] &= ~np.uint32(abi.GF_REPLICAS_NIL | abi.GF_MAX_NIL)
+        eng.commit()
+        with pytest.raises(EngineError) as ei:
+            eng.reconcile(flags)
+        assert ei.value.code == abi.KR_E_CAPACITY and "max_creates" in str(ei.value)
+        # ... and the engine is still usable
+        eng.fill(views, snap)
+        eng.commit()
+        got = eng.reconcile(flags)
+        assert not oracle_mod.run(snap, flags).diff(got)
+    finally:
+        eng.close()
