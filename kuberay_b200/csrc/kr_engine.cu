@@ -1,9 +1,11 @@
 // kr_engine.cu — C ABI (include/kr_engine.h) of the batched reconcile engine: arenas, streams, kernel schedule.
 //
-// One engine = one device, two streams: M (match -> sort -> decide -> creates) and H (hash), joined by events.
+// One engine = one device and four streams: M (clear -> tables -> match -> place -> decide -> creates), H (hash),
+// G (general decide kernel beside the small one) and a copy stream; the pass is one CUDA graph joined by events.
 // Inputs live in ONE pinned host arena and ONE device arena with identical layouts computed per snapshot from
-// kr_sizes, so kr_snapshot_commit is a single contiguous H2D copy; results likewise come back in one D2H copy
-// (+ one for the replica-index arena when pods are to be created).
+// kr_sizes: a full commit is two contiguous asynchronous H2D copies (columns, then the spec-JSON arena), partial and
+// per-row commits upload less (kr_snapshot_commit_parts / kr_snapshot_commit_pod_rows).  Results come back with the
+// exact sizes read from a 32-byte totals record and a single host wait (fetch_results).
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -129,7 +131,7 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.deferred_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.cact = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 8));
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
-  L.chain = o;  // directly after ccount: one memset clears both
+  L.chain = o;  // directly after ccount: k_clear zeroes both as one region
   o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.mtiles / 8192 + (size_t)n.n_groups / 8192 + (size_t)n.n_clusters / 8192 + 10));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.mtiles + 8));
