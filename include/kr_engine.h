@@ -408,9 +408,14 @@ enum {
 };
 int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts);
 
-/* Incremental epoch: the caller has rewritten the 7 pod columns of `rows[0..n)` in the pinned arenas
- * (an informer Update event: phase, PodReady, labels ...) and nothing else; upload just those rows.  Rows may repeat.
- * Pod additions / removals change n_pods and the List order: they need kr_snapshot_begin + a full commit. */
+/* Incremental epoch: the caller has rewritten the 7 pod columns of `rows[0..n)` in the pinned arenas;
+ * upload just those rows (rows may repeat; `rows` itself is copied before the call returns).  Informer events map to rows:
+ * Update -> the Pod's row rewritten; Delete -> the row becomes a free row (every id 0, p_packed = KR_PP_TOMBSTONE);
+ * Add -> a free row filled in (an arena is created with spare free rows; List order = row order, which is as arbitrary as the
+ * informer cache's own order).  Combine with kr_snapshot_commit_parts(KR_PART_OBJECTS) for the RayCluster / group / head /
+ * RayJob rows.  The rows are read from the arenas asynchronously (the device pulls them over PCIe): like after
+ * kr_snapshot_commit, do not rewrite the arenas until the next pass has returned.  A change that moves a table's row
+ * count (kr_sizes) needs kr_snapshot_begin + a full commit. */
 int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n);
 
 /* Run the whole decision + status pass over the committed snapshot and copy the results back.
