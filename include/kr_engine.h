@@ -418,6 +418,15 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts);
  * count (kr_sizes) needs kr_snapshot_begin + a full commit. */
 int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n);
 
+/* The same epoch, journal style: the caller hands over the new rows themselves instead of writing them into the arenas —
+ * values[7*i + k] is column k (p_ns_id, p_cluster_name_id, p_group_name_id, p_name_id, p_packed, p_replica_index,
+ * p_replica_name_id) of pod row rows[i]; the rows[] entries must be distinct.  One contiguous upload of 32 bytes per row
+ * (both arrays are copied before the call returns); the device scatters the values into the resident columns.  The pinned
+ * arenas are NOT touched: a caller that may later take the full-commit path writes the row there as well (its handler has the
+ * values in hand either way).  Faster than kr_snapshot_commit_pod_rows, whose rows the device pulls over PCIe one 32-byte
+ * sector at a time. */
+int kr_snapshot_commit_pod_values(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n);
+
 /* Run the whole decision + status pass over the committed snapshot and copy the results back.
  * Replaces the decision halves of reconcilePods (raycluster_controller.go:619-935), reconcileMultiHostWorkerGroup
  * (:963-1125), shouldRecreatePodsForUpgrade (:1132-1171), shouldDeletePod (:1181-1231), calculateStatus (:1552-1719),

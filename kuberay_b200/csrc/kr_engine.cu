@@ -171,7 +171,9 @@ struct kr_engine {
   uint8_t *hb_h = nullptr, *hb_d = nullptr;
   size_t hb_cap = 0;
   uint8_t *h_in_dev = nullptr;               // device-side address of h_in
-  uint8_t *pr_h = nullptr, *pr_d = nullptr;  // kr_snapshot_commit_pod_rows staging
+  uint8_t *pr_h = nullptr, *pr_d = nullptr;  // incremental pod commits: staging
+  cudaEvent_t ev_pr = nullptr;               // staging buffer consumed by the copy stream
+  bool pr_busy = false;
   size_t pr_cap = 0;
   int sm_count = 148;
   // the whole pass (both streams) captured once per (layout, flags, n_recreate) and replayed
@@ -578,7 +580,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaStreamCreateWithPriority(&e->sh, cudaStreamNonBlocking, prio_least) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaStreamCreateWithPriority(&e->sg, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaStreamCreateWithFlags(&e->scopy, cudaStreamNonBlocking) != cudaSuccess) return bail(KR_E_CUDA);
-  cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_h2d1); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
+  cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_h2d1); cudaEventCreateWithFlags(&e->ev_pr, cudaEventDisableTiming); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
   cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
@@ -605,7 +607,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
                         (const void *)k_decide, (const void *)k_creates_fused, (const void *)k_jobs, (const void *)k_hash2<1, 0>, (const void *)k_hash2<4, 1>,
                         (const void *)k_clear, (const void *)k_match<false, kSortItems>, (const void *)k_hist, (const void *)k_scan_rows, (const void *)k_scatter,
                         (const void *)k_scan_counts, (const void *)k_place, (const void *)k_scan_creates, (const void *)k_create_fill, (const void *)k_scan_actions,
-                        (const void *)k_compact_actions, (const void *)k_patch_pods};
+                        (const void *)k_compact_actions, (const void *)k_patch_pods, (const void *)k_patch_pod_values};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
@@ -641,7 +643,7 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->sh) cudaStreamDestroy(e->sh);
   if (e->sg) cudaStreamDestroy(e->sg);
   if (e->scopy) { cudaStreamSynchronize(e->scopy); cudaStreamDestroy(e->scopy); }
-  for (auto ev : {e->ev_h2d0, e->ev_h2d1, e->ev_cols, e->ev_json}) if (ev) cudaEventDestroy(ev);
+  for (auto ev : {e->ev_h2d0, e->ev_h2d1, e->ev_cols, e->ev_json, e->ev_pr}) if (ev) cudaEventDestroy(ev);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   delete e;
@@ -720,13 +722,14 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   return KR_OK;
 }
 
-int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n) {
+// Shared by the two incremental pod commits: stage the row list (and, journal style, the 7 values per row), upload, scatter.
+static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n) {
   if (!e || (!rows && n)) return KR_E_INVALID;
-  if (!e->committed_full) return fail(e, KR_E_STATE, "kr_snapshot_commit_pod_rows needs a full commit of this layout first");
+  if (!e->committed_full) return fail(e, KR_E_STATE, "an incremental pod commit needs a full commit of this layout first");
   if (n == 0) return KR_OK;
   CK(cudaSetDevice(e->cfg.device));
-  const size_t bytes = 4 * (size_t)n;  // only the row list is staged; the kernel pulls the rows from the mapped pinned arena
-  CK(cudaStreamSynchronize(e->scopy));  // a previous patch may still be reading the staging buffer
+  const size_t bytes = (values ? 32 : 4) * (size_t)n;  // row list (+ 7 values per row); kr_snapshot_commit_pod_rows lets the device pull the rows
+  if (e->pr_busy) { CK(cudaEventSynchronize(e->ev_pr)); e->pr_busy = false; }  // a previous patch may still be reading the staging buffer
   if (bytes > e->pr_cap) {
     if (e->pr_h) cudaFreeHost(e->pr_h);
     if (e->pr_d) cudaFree(e->pr_d);
@@ -738,7 +741,8 @@ int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n) 
   }
   for (uint32_t i = 0; i < n; i++)
     if (rows[i] >= e->sizes.n_pods) return fail(e, KR_E_INVALID, "pod row %u out of range", rows[i]);
-  memcpy(e->pr_h, rows, bytes);
+  memcpy(e->pr_h, rows, 4 * (size_t)n);
+  if (values) memcpy(e->pr_h + 4 * (size_t)n, values, 28 * (size_t)n);
   kr_snapshot_bufs hb;
   bind_in(e->il, e->h_in, &hb);
   SnapDev s;
@@ -754,14 +758,24 @@ int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n) 
   CK(cudaStreamSynchronize(e->sm));  // a pass still reading the columns must finish first
   CK(cudaEventRecord(e->ev_h2d0, e->scopy));
   CK(cudaMemcpyAsync(e->pr_d, e->pr_h, bytes, cudaMemcpyHostToDevice, e->scopy));
-  k_patch_pods<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, hc, dc);
+  CK(cudaEventRecord(e->ev_pr, e->scopy));
+  e->pr_busy = true;
+  if (values) k_patch_pod_values<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, dc);
+  else k_patch_pods<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, hc, dc);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));
   CK(cudaEventRecord(e->ev_cols, e->scopy));  // ev_json keeps pointing at the last JSON upload: the hash need not wait for the patch
   e->h2d_timed = false;
-  e->prof.h2d_bytes = bytes + 28 * (size_t)n;  // row list + the 28-B row payload (PCIe moves one 32-B sector per value read)
+  e->prof.h2d_bytes = 32 * (size_t)n;  // row list + the 28-byte row payload (pulled one 32-byte sector per value in the rows-only variant)
   e->committed = true;
   return KR_OK;
+}
+
+int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n) { return commit_pod_patch(e, rows, nullptr, n); }
+
+int kr_snapshot_commit_pod_values(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n) {
+  if (!values && n) return KR_E_INVALID;
+  return commit_pod_patch(e, rows, values, n);
 }
 
 int kr_reconcile_device_only(kr_engine *e, const kr_flags *flags) {

@@ -1537,6 +1537,18 @@ __global__ void __launch_bounds__(256) k_patch_pods(const uint32_t *__restrict__
   for (int k = 0; k < 7; k++) dev.c[k][p] = v[k];
 }
 
+// Journal-style incremental epoch: the rows arrive in one contiguous staging buffer ([n row indices][n x 7 values]); scatter them
+// into the resident columns.  (Writing them through to the mapped pinned arena as well was measured: 70 k four-byte PCIe
+// writes cost as much as the sector pulls of k_patch_pods, ~180 us — the caller keeps its arenas current itself.)
+__global__ void __launch_bounds__(256) k_patch_pod_values(const uint32_t *__restrict__ stage, uint32_t n, PodCols dev) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = stage[i];
+  const uint32_t *v = stage + n + 7 * (size_t)i;
+#pragma unroll
+  for (int k = 0; k < 7; k++) dev.c[k][p] = v[k];
+}
+
 // ------------------------------------------------------------------------------------------------ k_jobs
 // RayJob roll-up (rayjob_controller.go:203-216, 343, 885): join by (namespace, status.rayClusterName).
 __global__ void __launch_bounds__(256) k_jobs(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {

@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
         L.kr_snapshot_commit.argtypes = [C.c_void_p]
         L.kr_snapshot_commit_parts.argtypes = [C.c_void_p, C.c_uint32]
         L.kr_snapshot_commit_pod_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.kr_snapshot_commit_pod_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.kr_reconcile_batch.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_results_view)]
         L.kr_reconcile_device_only.argtypes = [C.c_void_p, P(abi.kr_flags)]
         L.kr_reconcile_batch_profiled.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_profile)]
@@ -141,6 +142,13 @@ class Engine:
         """Incremental epoch: upload only the pod rows the caller rewrote in the pinned arenas."""
         rows = np.ascontiguousarray(rows, dtype=np.uint32)
         self._check(self._L.kr_snapshot_commit_pod_rows(self._h, rows.ctypes.data, rows.size))
+
+    def commit_pod_values(self, rows: np.ndarray, values: np.ndarray):
+        """Incremental epoch, journal style: hand over the new rows themselves (values[i] = the 7 pod columns of rows[i])."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.uint32).reshape(-1, 7)
+        assert values.shape[0] == rows.size
+        self._check(self._L.kr_snapshot_commit_pod_values(self._h, rows.ctypes.data, values.ctypes.data, rows.size))
 
     def load(self, snap: Snapshot):
         views = self.begin(snap.sizes())

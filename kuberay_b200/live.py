@@ -124,12 +124,20 @@ class LiveArena:
             if parts:
                 self.engine.commit(parts)
             rows = np.array(sorted(self._dirty), dtype=np.uint32)
-            for c in _POD_COLS:
-                self.views[c][rows] = snap.cols[c][rows]
-            for c in _POD_COLS:  # every row that was not reported dirty must already be identical
-                assert np.array_equal(self.views[c], snap.cols[c]), c
-            if rows.size:
-                self.engine.commit_pod_rows(rows)
+            self._epoch = getattr(self, "_epoch", 0) + 1
+            if self._epoch % 2 and rows.size:
+                # journal style: hand the rows over (and keep the pinned arenas current for a later full commit)
+                vals = np.stack([snap.cols[c][rows].view(np.uint32) for c in _POD_COLS], axis=1)
+                for c in _POD_COLS:
+                    self.views[c][rows] = snap.cols[c][rows]
+                self.engine.commit_pod_values(rows, vals)
+            else:
+                for c in _POD_COLS:
+                    self.views[c][rows] = snap.cols[c][rows]
+                for c in _POD_COLS:  # every row that was not reported dirty must already be identical
+                    assert np.array_equal(self.views[c], snap.cols[c]), c
+                if rows.size:
+                    self.engine.commit_pod_rows(rows)
             self.stats["rows"] += int(rows.size)
             mode = "incremental"
         self.snap, self.meta = snap, meta
