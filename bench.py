@@ -48,6 +48,21 @@ def _ncu_traffic(kernel: str, workload: str):
     return None
 
 
+def _ncu_inst(kernel: str, workload: str):
+    """Warp instructions executed by one launch of `kernel` in the committed ncu capture (C3 only)."""
+    if workload != "C3":
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_c3.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        return None
+    for name, d in prof.items():
+        if name.startswith(kernel):
+            return int(d["inst"])
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -376,6 +391,19 @@ def main():
                 "frac": ach / peak, "traffic": _ncu_traffic("k_hash2" if dom == "k_hash" else dom, args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_ms": dom_ms,
                 "note": "k_hash is INT32-issue/latency bound (SHA-1 is a serial chain per message; 80 rounds per 64 B), HBM is its secondary bound" if dom == "k_hash" else ""}
         kernels = {k: round(v, 5) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
+        # The hash against the bound that actually holds it ("report ... and the ALU-bound ceiling"): warp instructions
+        # of one launch (committed ncu capture) over its duration, against the ALU pipe's issue rate (one warp instruction per
+        # 2 cycles per scheduler; ~all of SHA-1 is LOP3/SHF/IADD3/LEA on that pipe) — over all 4 x SMs schedulers, and over the
+        # ceil(n/32) schedulers that have a warp at all when there are fewer one-lane-per-message warps than schedulers.
+        hash_alu = None
+        h_inst = _ncu_inst("k_hash2", args.workload)
+        if h_inst and kavg.get("k_hash") and clocks.get("sm_mhz"):
+            n_sched = 4 * torch.cuda.get_device_properties(local_rank).multi_processor_count
+            rate = h_inst / (kavg["k_hash"] / 1e3)  # warp instr / s
+            per_sched_peak = clocks["sm_mhz"] * 1e6 / 2
+            busy = min(n_sched, (nc_local + 31) // 32)
+            hash_alu = {"warp_instr_per_launch": h_inst, "achieved_gwarp_instr_s": rate / 1e9, "alu_pipe_peak_gwarp_instr_s": n_sched * per_sched_peak / 1e9,
+                        "frac_of_chip": rate / (n_sched * per_sched_peak), "schedulers_with_a_warp": busy, "frac_of_busy_schedulers": rate / (busy * per_sched_peak)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -406,6 +434,7 @@ def main():
                                   "kernels": "clear+build_tables+match+place+decide+creates, each timed alone (serialised, event-bracketed)", "avg_ms": non_hash_ms},
             "hash_roofline": {"achieved": alg["hash"] / (kavg.get("k_hash", float("nan")) / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": alg["hash"] / (kavg.get("k_hash", float("nan")) / 1e3) / 1e9 / peak, "avg_ms": kavg.get("k_hash")},
+            "hash_alu_view": hash_alu,
             "wall_ms_timed_region": wall_ms,
             "results_check": {"n_actions": int(res.n_actions), "n_create_total": int(res.n_create_total), "n_orphans": int(res.n_orphans)},
         }
