@@ -452,6 +452,15 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
 /* Timings of the last batch. */
 int kr_last_profile(kr_engine *e, kr_profile *prof);
 
+/* Engine options (call before the first kr_snapshot_begin).
+ * KR_OPT_FIXED_LAYOUT = 1: lay the arenas out once, for the capacities given to kr_engine_create, instead of per snapshot.
+ *   Column addresses then never move: kr_snapshot_begin(sizes) only sets the live row counts (<= capacities) and returns the
+ *   same pointers, what is resident in HBM stays valid across begins, and an informer event that changes a table's row count
+ *   (a RayCluster or head Pod appears, workersToDelete lists grow, a Pod is appended after the last row) is still an
+ *   incremental epoch: kr_snapshot_begin(new counts) + KR_PART_OBJECTS + kr_snapshot_commit_pod_rows/_values. */
+enum { KR_OPT_FIXED_LAYOUT = 1 };
+int kr_engine_set_option(kr_engine *e, uint32_t option, uint64_t value);
+
 /* Device pointer + byte size of the per-group delta records (kr_group_result[n_groups]) of the last pass:
  * the payload of the optional cross-GPU all-gather; the caller owns the collective. */
 int kr_group_results_device(kr_engine *e, const void **dev_ptr, uint64_t *bytes);

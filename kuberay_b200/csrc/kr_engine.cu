@@ -164,6 +164,7 @@ struct kr_engine {
   bool begun = false, committed = false, ran = false;
   kr_flags last_flags{};      // flags of the last pass (kr_results_fetch honours fetch_pod_lists)
   bool committed_full = false;  // every part of the current layout has been uploaded at least once
+  bool fixed_layout = false;    // KR_OPT_FIXED_LAYOUT: arenas laid out for the capacities, live counts in `sizes`
   uint32_t n_recreate = 0;  // clusters with KR_CF_UPGRADE_RECREATE (decide phase 1 needed)
   kr_profile prof{};
   std::string err;
@@ -443,7 +444,6 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
   kr_flags fk = f;
   fk.fetch_pod_lists = 0;  // host-side switch: does not change the device work
   if (!e->gvalid || memcmp(&e->gflags, &fk, sizeof fk) != 0) {
-    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
     e->gvalid = false;
     CK(cudaStreamBeginCapture(e->sm, cudaStreamCaptureModeThreadLocal));
     int rc = launch_pass(e, f, false, true);
@@ -451,7 +451,15 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
     cudaError_t ce = cudaStreamEndCapture(e->sm, &g);
     if (rc != KR_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
     if (ce != cudaSuccess) return fail(e, KR_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&e->gexec, g, 0);
+    // New row counts / pointers with the same kernel chain are a parameter update of the instantiated graph (cheap);
+    // a different chain (fast <-> radix, fused <-> unfused, phase 1 or RayJobs appearing) is instantiated afresh.
+    bool updated = false;
+    if (e->gexec) {
+      cudaGraphExecUpdateResultInfo info;
+      updated = cudaGraphExecUpdate(e->gexec, g, &info) == cudaSuccess;
+      if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+    }
+    if (!updated) ce = cudaGraphInstantiate(&e->gexec, g, 0);
     cudaGraphDestroy(g);
     if (ce != cudaSuccess) return fail(e, KR_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
     e->gflags = fk;
@@ -505,9 +513,15 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
   uint64_t bytes = e->ol.small_total;
   CK(cudaMemcpyAsync(e->h_out, e->d_out, e->ol.small_total, cudaMemcpyDeviceToHost, e->sm));
   if (full && n.n_pods) {
-    size_t span = e->ol.act_idx - e->ol.sorted_idx;  // sorted_pod_idx + sorted_action, contiguous
-    CK(cudaMemcpyAsync(e->h_out + e->ol.sorted_idx, e->d_out + e->ol.sorted_idx, span, cudaMemcpyDeviceToHost, e->sm));
-    bytes += span;
+    if (!e->fixed_layout) {
+      size_t span = e->ol.act_idx - e->ol.sorted_idx;  // sorted_pod_idx + sorted_action, contiguous
+      CK(cudaMemcpyAsync(e->h_out + e->ol.sorted_idx, e->d_out + e->ol.sorted_idx, span, cudaMemcpyDeviceToHost, e->sm));
+      bytes += span;
+    } else {  // capacity slack between the two arrays: copy the live prefixes
+      CK(cudaMemcpyAsync(e->h_out + e->ol.sorted_idx, e->d_out + e->ol.sorted_idx, 4 * (size_t)n.n_pods, cudaMemcpyDeviceToHost, e->sm));
+      CK(cudaMemcpyAsync(e->h_out + e->ol.sorted_act, e->d_out + e->ol.sorted_act, (size_t)n.n_pods, cudaMemcpyDeviceToHost, e->sm));
+      bytes += 5 * (size_t)n.n_pods;
+    }
   }
   if (n_actions) {
     CK(cudaMemcpyAsync(e->h_out + e->ol.act_idx, e->d_out + e->ol.act_idx, 4 * (size_t)n_actions, cudaMemcpyDeviceToHost, e->sm));
@@ -549,6 +563,16 @@ int kr_debug_timeline(kr_engine *e, unsigned long long *out64) {
   return KR_OK;
 }
 #endif
+
+int kr_engine_set_option(kr_engine *e, uint32_t option, uint64_t value) {
+  if (!e) return KR_E_INVALID;
+  if (option == KR_OPT_FIXED_LAYOUT) {
+    if (e->begun) return fail(e, KR_E_STATE, "KR_OPT_FIXED_LAYOUT must be set before the first kr_snapshot_begin");
+    e->fixed_layout = value != 0;
+    return KR_OK;
+  }
+  return fail(e, KR_E_INVALID, "unknown option %u", option);
+}
 
 int kr_device_count(void) {
   int n = 0;
@@ -659,11 +683,19 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
   CK(cudaSetDevice(c.device));
   CK(cudaStreamSynchronize(e->scopy));
   CK(cudaStreamSynchronize(e->sm));  // previous results are invalidated from here on
-  if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) { e->gvalid = false; e->force_radix = e->env_radix; e->committed_full = false; }  // layout (hence every kernel argument) changes
+  if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) {  // row counts (and, without KR_OPT_FIXED_LAYOUT, every column address) change
+    e->gvalid = false; e->force_radix = e->env_radix;
+    if (!e->fixed_layout) e->committed_full = false;
+  }
   e->sizes = *sizes;
-  e->il = in_layout(*sizes);
-  e->ol = out_layout(*sizes, c.max_creates);
-  e->sl = scratch_layout(*sizes);
+  const kr_sizes lay = e->fixed_layout ? cap_sizes(c) : *sizes;
+  e->il = in_layout(lay);
+  e->ol = out_layout(lay, c.max_creates);
+  e->sl = scratch_layout(lay);
+  if (e->fixed_layout) {  // offsets and table sizes from the capacities, tile counts (grid sizes) from the live pod count
+    const ScratchLayout live = scratch_layout(*sizes);
+    e->sl.ntiles = live.ntiles; e->sl.mtiles = live.mtiles;
+  }
   if (e->il.total > e->in_cap || e->ol.total > e->out_cap || e->sl.total > e->scratch_cap)
     return fail(e, KR_E_CAPACITY, "internal: layout exceeds arena");
   bind_in(e->il, e->h_in, out);
@@ -702,17 +734,23 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     return fail(e, KR_E_STATE, "a partial commit needs a full commit of this layout first");
   size_t bytes = 0;
   CK(cudaEventRecord(e->ev_h2d0, e->scopy));
-  if ((parts & KR_PART_COLUMNS) && json_off) { CK(cudaMemcpyAsync(e->d_in, e->h_in, json_off, cudaMemcpyHostToDevice, e->scopy)); bytes += json_off; }
-  else if (parts & KR_PART_OBJECTS) {  // the columns on either side of the seven per-pod ones
-    const size_t a1 = e->il.off[kFirstPodCol], b0 = e->il.off[kFirstPodCol + 7];
-    if (a1) { CK(cudaMemcpyAsync(e->d_in, e->h_in, a1, cudaMemcpyHostToDevice, e->scopy)); bytes += a1; }
-    if (json_off > b0) { CK(cudaMemcpyAsync(e->d_in + b0, e->h_in + b0, json_off - b0, cudaMemcpyHostToDevice, e->scopy)); bytes += json_off - b0; }
+  auto up = [&](size_t off, size_t len) -> int {
+    if (len) { CK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, len, cudaMemcpyHostToDevice, e->scopy)); bytes += len; }
+    return KR_OK;
+  };
+  const size_t a1 = e->il.off[kFirstPodCol], b0 = e->il.off[kFirstPodCol + 7];
+  if ((parts & KR_PART_COLUMNS) && !e->fixed_layout) { if (int rc = up(0, json_off)) return rc; }
+  else if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) {
+    // the (small) columns on either side of the seven per-pod ones; then, for KR_PART_COLUMNS under a fixed layout, the live
+    // prefix of each per-pod column (the capacity slack between the columns is not worth moving)
+    if (int rc = up(0, a1)) return rc;
+    if (int rc = up(b0, json_off - b0)) return rc;
+    if (parts & KR_PART_COLUMNS)
+      for (int k = 0; k < 7; k++)
+        if (int rc = up(e->il.off[kFirstPodCol + k], 4 * (size_t)n.n_pods)) return rc;
   }
   CK(cudaEventRecord(e->ev_cols, e->scopy));
-  if ((parts & KR_PART_JSON) && e->il.total > json_off) {
-    CK(cudaMemcpyAsync(e->d_in + json_off, e->h_in + json_off, e->il.total - json_off, cudaMemcpyHostToDevice, e->scopy));
-    bytes += e->il.total - json_off;
-  }
+  if (parts & KR_PART_JSON) { if (int rc = up(json_off, e->fixed_layout ? (size_t)n.json_bytes : e->il.total - json_off)) return rc; }
   CK(cudaEventRecord(e->ev_json, e->scopy));
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));
   if ((parts & KR_PART_ALL) == KR_PART_ALL) e->committed_full = true;

@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         L.kr_snapshot_commit_parts.argtypes = [C.c_void_p, C.c_uint32]
         L.kr_snapshot_commit_pod_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.kr_snapshot_commit_pod_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.kr_engine_set_option.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         L.kr_reconcile_batch.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_results_view)]
         L.kr_reconcile_device_only.argtypes = [C.c_void_p, P(abi.kr_flags)]
         L.kr_reconcile_batch_profiled.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_profile)]
@@ -116,6 +117,10 @@ class Engine:
             pass
 
     # -- snapshot
+    def set_fixed_layout(self, on: bool = True):
+        """KR_OPT_FIXED_LAYOUT: lay the arenas out for the capacities once; begin() then only sets the live row counts."""
+        self._check(self._L.kr_engine_set_option(self._h, abi.OPT_FIXED_LAYOUT, 1 if on else 0))
+
     def begin(self, sizes: abi.kr_sizes) -> dict[str, np.ndarray]:
         """kr_snapshot_begin: returns numpy views over the engine-owned pinned arenas, keyed by column name."""
         bufs = abi.kr_snapshot_bufs()

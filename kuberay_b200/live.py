@@ -5,8 +5,10 @@ SURVEY §8(f) rank 1.  The device keeps the last snapshot; an epoch uploads only
     KR_PP_TOMBSTONE row, an added Pod takes the lowest free row) -> kr_snapshot_commit_pod_rows(rows);
   * RayCluster / worker-group / workersToDelete / head-aux / RayJob rows are small -> kr_snapshot_commit_parts(KR_PART_OBJECTS);
   * spec changes -> KR_PART_JSON as well.
-A change that moves a table's row count (a RayCluster or a head Pod appears / disappears, the workersToDelete lists change
-length, the arena runs out of free rows) changes the column layout and takes the full begin + commit path ("rebase").
+The engine runs with KR_OPT_FIXED_LAYOUT (arenas laid out for the capacities), so a change that moves a table's row count —
+a RayCluster or a head Pod appears / disappears, the workersToDelete lists change length, a Pod is appended after the last
+row — is still incremental: kr_snapshot_begin(new live counts) keeps every column where it is.  Only outgrowing a capacity
+takes the full path ("rebase": a larger engine, everything uploaded).
 
 This class re-packs the objects on the host with the ordinary packer and diffs the columns: it is the executable
 statement of the protocol for the tests, not a fast packer (that is the Go shim's job).
@@ -54,15 +56,11 @@ class LiveArena:
         key = (pod.get("namespace", "default"), pod["name"])
         row = self.row_of.get(key)
         if row is None:
-            if _is_head(pod) or not self.free:
-                if not self.free:
-                    self.rows.extend([None] * max(64, len(self.rows) // 8))  # grow the arena: layout change
-                    self._index()
-                self._need_rebase = True  # a new head-aux row (n_heads) or new capacity (n_pods)
+            if not self.free:  # no free row: append after the last one (a new live count, still no layout change)
+                self.rows.append(None)
+                heapq.heappush(self.free, len(self.rows) - 1)
             row = heapq.heappop(self.free)
             self.row_of[key] = row
-        elif _is_head(pod) != _is_head(self.rows[row]):
-            self._need_rebase = True
         self.rows[row] = pod
         self._dirty.add(row)
 
@@ -70,8 +68,6 @@ class LiveArena:
         row = self.row_of.pop((namespace, name), None)
         if row is None:
             return False
-        if _is_head(self.rows[row]):
-            self._need_rebase = True
         self.rows[row] = None
         heapq.heappush(self.free, row)
         self._dirty.add(row)
@@ -79,13 +75,10 @@ class LiveArena:
 
     def upsert_cluster(self, cluster: dict):
         key = (cluster.get("namespace", "default"), cluster["name"])
-        if key not in self.clusters:
-            self._need_rebase = True
         self.clusters[key] = cluster
 
     def delete_cluster(self, namespace: str, name: str):
-        if self.clusters.pop((namespace, name), None) is not None:
-            self._need_rebase = True
+        self.clusters.pop((namespace, name), None)
 
     # ------------------------------------------------------------------ epoch
     def pack(self) -> tuple[snp.Snapshot, snp.PackMeta]:
@@ -100,19 +93,24 @@ class LiveArena:
     def flush(self) -> str:
         """Bring the device copy up to date; returns "rebase" or "incremental"."""
         snap, meta = self.pack()
-        same_layout = (not self._need_rebase) and getattr(self, "snap", None) is not None and bytes(snap.sizes()) == bytes(self.snap.sizes())
         if not self.use_engine:
-            mode = "incremental" if same_layout else "rebase"
-        elif not same_layout:
-            if self.engine is None or not self._fits(snap):
-                if self.engine is not None:
-                    self.engine.close()
-                self.engine = Engine.for_snapshot(snap, device=self.device, slack=1.5)
+            mode = "incremental" if (not self._need_rebase and getattr(self, "snap", None) is not None) else "rebase"
+        elif self._need_rebase or self.engine is None or not self._fits(snap):
+            # first epoch, or a table outgrew the capacities: new engine sized with slack, fixed layout, full upload
+            if self.engine is not None:
+                self.engine.close()
+            self.engine = Engine.for_snapshot(snap, device=self.device, slack=1.5)
+            self.engine.set_fixed_layout(True)
             self.views = self.engine.begin(snap.sizes())
             self.engine.fill(self.views, snap)
             self.engine.commit()
             mode = "rebase"
         else:
+            # Under the fixed layout every column keeps its address, so any event is incremental: new live counts, the small
+            # object columns, the spec JSON if it moved, and the pod rows the events touched (appended rows included).
+            old_pods = self.snap.dims["pods"]
+            if bytes(snap.sizes()) != bytes(self.snap.sizes()):
+                self.views = self.engine.begin(snap.sizes())
             parts = 0
             if any(not np.array_equal(self.views[c], snap.cols[c]) for c in _OBJ_COLS):
                 for c in _OBJ_COLS:
@@ -123,21 +121,17 @@ class LiveArena:
                 parts |= abi.PART_JSON
             if parts:
                 self.engine.commit(parts)
-            rows = np.array(sorted(self._dirty), dtype=np.uint32)
+            self._dirty.update(range(old_pods, snap.dims["pods"]))  # rows appended past the old end of the arena
+            rows = np.array(sorted(r for r in self._dirty if r < snap.dims["pods"]), dtype=np.uint32)
+            for c in _POD_COLS:
+                self.views[c][rows] = snap.cols[c][rows]
+            for c in _POD_COLS:  # every row that was not reported dirty must already be identical
+                assert np.array_equal(self.views[c], snap.cols[c]), c
             self._epoch = getattr(self, "_epoch", 0) + 1
-            if self._epoch % 2 and rows.size:
-                # journal style: hand the rows over (and keep the pinned arenas current for a later full commit)
-                vals = np.stack([snap.cols[c][rows].view(np.uint32) for c in _POD_COLS], axis=1)
-                for c in _POD_COLS:
-                    self.views[c][rows] = snap.cols[c][rows]
-                self.engine.commit_pod_values(rows, vals)
-            else:
-                for c in _POD_COLS:
-                    self.views[c][rows] = snap.cols[c][rows]
-                for c in _POD_COLS:  # every row that was not reported dirty must already be identical
-                    assert np.array_equal(self.views[c], snap.cols[c]), c
-                if rows.size:
-                    self.engine.commit_pod_rows(rows)
+            if rows.size and self._epoch % 2:  # journal style: hand the rows over
+                self.engine.commit_pod_values(rows, np.stack([snap.cols[c][rows].view(np.uint32) for c in _POD_COLS], axis=1))
+            elif rows.size:                     # or let the device pull them from the arenas
+                self.engine.commit_pod_rows(rows)
             self.stats["rows"] += int(rows.size)
             mode = "incremental"
         self.snap, self.meta = snap, meta

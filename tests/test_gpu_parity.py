@@ -343,3 +343,28 @@ def test_error_paths_return_codes_not_crashes(oracle_mod):
         assert not oracle_mod.run(snap, flags).diff(got)
     finally:
         eng.close()
+
+
+def test_fixed_layout_keeps_addresses_and_resident_data(oracle_mod):
+    """KR_OPT_FIXED_LAYOUT: arenas laid out for the capacities.  begin() with other row counts returns the same pointers, the
+    spec-JSON arena stays resident across it, and the pass (graph parameters updated in place) matches the oracle."""
+    snaps = [synthetic.generate(synthetic.config("C2", seed=synthetic.SEED + i)) for i in range(3)]
+    eng = Engine.for_snapshot(snaps[0][0], slack=1.3)
+    eng.set_fixed_layout(True)
+    try:
+        addr = None
+        for i, (snap, flags) in enumerate(snaps):
+            views = eng.begin(snap.sizes())
+            here = {k: v.ctypes.data for k, v in views.items() if v.size}
+            assert addr is None or all(addr[k] == p for k, p in here.items() if k in addr), "a column moved"
+            addr = here if addr is None else addr
+            eng.fill(views, snap)
+            # the JSON arena is the same for every seed of this config: after the first epoch only the columns travel
+            eng.commit(abi.PART_ALL if i == 0 else abi.PART_COLUMNS)
+            assert i == 0 or eng.last_profile()["h2d_bytes"] < 1.35 * (snap.nbytes() - snap.dims["json"])  # (small columns travel capacity-long)
+            got = eng.reconcile(flags)
+            assert not oracle_mod.run(snap, flags, threads=8).diff(got), i
+        with pytest.raises(Exception):
+            eng.set_fixed_layout(False)  # only before the first begin
+    finally:
+        eng.close()
