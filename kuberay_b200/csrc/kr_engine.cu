@@ -8,6 +8,7 @@
 // exact sizes read from a 32-byte totals record and a single host wait (fetch_results).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -183,6 +184,7 @@ struct kr_engine {
   bool gvalid = false;
   bool use_graph = true;
   bool use_pdl = true;        // KR_NO_PDL=1 disables programmatic dependent launch
+  int hash_ctas_per_sm = 2;   // KR_HASH_CTAS: resident hash CTAs per SM in the throughput regime
   int place_ctas = 1;         // k_place_fused CTAs per SM (KR_PLACE_CTAS; measured at C3: 1 -> 25 us, 2 -> 35 us next to the hash)
   // pipeline choice: fast = count/place/in-warp sort (every bucket <= 1024 pods); radix = general stable LSD sort.
   bool force_radix = false;   // sticky per layout: set when a pass met a bucket the fast pipeline cannot sort
@@ -304,7 +306,9 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       uint32_t blocks = (n.n_clusters + 31) / 32;
       k_hash2<1, 0><<<blocks, 32, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
     } else {
-      uint32_t blocks = (n.n_clusters + 127) / 128;
+      // throughput regime: two resident CTAs per SM walk the message groups, so the hash never fills the SMs' shared memory and
+      // the main chain starts at once (with one CTA per group, 3 per SM, k_clear waited ~140 us at C3x10 for the first to retire)
+      uint32_t blocks = std::min<uint32_t>((n.n_clusters + 127) / 128, (uint32_t)e->sm_count * e->hash_ctas_per_sm);
       k_hash2<4, 1><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
     }
   };
@@ -638,6 +642,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (const char *g = getenv("KR_FORCE_RADIX")) e->env_radix = (g[0] == '1');
   if (const char *g = getenv("KR_NO_FUSE")) e->no_fuse = (g[0] == '1');
   if (const char *g = getenv("KR_NO_PDL")) e->use_pdl = !(g[0] == '1');
+  if (const char *g = getenv("KR_HASH_CTAS")) e->hash_ctas_per_sm = atoi(g) > 0 ? atoi(g) : 2;
   if (const char *g = getenv("KR_PLACE_CTAS")) e->place_ctas = atoi(g) > 0 ? atoi(g) : 1;
   e->force_radix = e->env_radix;
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);

@@ -1649,7 +1649,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_hash2(const uint8_t *__restrict_
   KR_TL(7);
   __shared__ uint4 s_tile[2][WARPS][32][8];  // [buffer][warp][message lane][16-byte piece ^ (lane & 7)]
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t m = (blockIdx.x * WARPS + warp) * 32 + lane;
+  // grid-stride over groups of WARPS*32 messages: the engine caps the grid for large n so that the hash leaves room on every
+  // SM for the main chain's blocks (each warp owns its shared tile, so the trips need no block-wide barrier)
+  for (uint32_t grp_i = blockIdx.x; (uint64_t)grp_i * (WARPS * 32) < n; grp_i += gridDim.x) {
+  const uint32_t m = (grp_i * WARPS + warp) * 32 + lane;
   const bool have = m < n;
   uint64_t moff = 0;
   uint32_t mlen = 0;
@@ -1717,7 +1720,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_hash2(const uint8_t *__restrict_
     }
     __syncwarp();  // every lane is done reading this buffer before the fetch two iterations ahead overwrites it
   }
-  if (!have) return;
+  if (have) {
   uint32_t o32[8];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -1740,6 +1743,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_hash2(const uint8_t *__restrict_
   uint4 *dst = reinterpret_cast<uint4 *>(out + 32 * (size_t)m);
   dst[0] = make_uint4(o32[0], o32[1], o32[2], o32[3]);
   dst[1] = make_uint4(o32[4], o32[5], o32[6], o32[7]);
+  }
+  __syncwarp();
+  }  // next group of messages
 }
 
 }  // namespace kr
