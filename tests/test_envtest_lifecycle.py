@@ -1,0 +1,175 @@
+"""The reference's envtest suites for the RayCluster controller (raycluster_controller_test.go), restated as closed loops on
+the host-side reconciler mirror: reconcile -> side effects on the fake client -> next reconcile sees them.  envtest's
+`Eventually(...)` becomes "reconcile until the predicate holds" (a handful of passes); there is no kubelet, so — as in the
+Go suites — the test flips Pods to Running itself.
+
+Every scenario runs against the CPU oracle (`-m "not gpu"`) and against the CUDA engine through the C ABI (`-m gpu`).
+"""
+import pytest
+
+from kuberay_b200.reconciler import Env, EngineBackend, FakeClient, RayClusterReconciler
+
+NS = "default"
+GROUP = "small-group"
+
+
+class OracleBackend:
+    def run(self, snap, flags):
+        from oracle import oracle
+        return oracle.run(snap, flags)
+
+
+@pytest.fixture(params=["oracle", pytest.param("engine", marks=pytest.mark.gpu)])
+def backend(request):
+    return OracleBackend() if request.param == "oracle" else EngineBackend(0)
+
+
+def cluster_template(name, autoscaling=None):
+    """rayClusterTemplate (raycluster_controller_test.go:44-120): one worker group, replicas 3, minReplicas 0, maxReplicas 4."""
+    spec = {"headGroupSpec": {"rayStartParams": {}, "template": {"spec": {"containers": [{"name": "ray-head"}]}}},
+            "workerGroupSpecs": [{"groupName": GROUP, "replicas": 3, "minReplicas": 0, "maxReplicas": 4, "numOfHosts": 1, "workersToDelete": [],
+                                  "template": {"spec": {"containers": [{"name": "ray-worker"}]}}}]}
+    if autoscaling is not None:
+        spec["enableInTreeAutoscaling"] = autoscaling
+    return {"namespace": NS, "name": name, "uid": f"uid-{name}", "spec": spec, "status": {}}
+
+
+def workers(client, name):
+    return client.pods_of(NS, name, **{"ray.io/group": GROUP})
+
+
+def heads(client, name):
+    return client.pods_of(NS, name, **{"ray.io/node-type": "head"})
+
+
+def everything(client, name):
+    return client.pods_of(NS, name)
+
+
+def set_running(pods):
+    # envtest marks PodReady true when a test sets Status.Phase = Running (raycluster_controller_test.go:197-199)
+    for p in pods:
+        p["phase"] = "Running"
+        p["conditions"] = [{"type": "Ready", "status": "True"}]
+        p.setdefault("podIP", "10.0.0.7")
+
+
+def eventually(r, name, pred, passes=8):
+    for _ in range(passes):
+        if pred():
+            return True
+        r.reconcile(NS, name)
+    return pred()
+
+
+def consistently(r, name, pred, passes=4):
+    for _ in range(passes):
+        r.reconcile(NS, name)
+        if not pred():
+            return False
+    return True
+
+
+def status(client, name):
+    return client.clusters[(NS, name)].get("status") or {}
+
+
+def cond_true(client, name, ctype):
+    return any(c.get("type") == ctype and c.get("status") == "True" for c in status(client, name).get("conditions") or [])
+
+
+def test_basic_lifecycle(backend):
+    """raycluster_controller_test.go:132-249: 1 head + 3 workers appear; all Running -> state ready with its transition time;
+    a deleted worker is replaced; replicas above maxReplicas is clamped to maxReplicas and stays there."""
+    name = "raycluster-basic"
+    client = FakeClient([cluster_template(name)], [])
+    r = RayClusterReconciler(client, backend)
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3)                       # :154-159
+    assert len(heads(client, name)) == 1                                                      # :161-169
+    set_running(everything(client, name))                                                     # :171-195
+    assert eventually(r, name, lambda: status(client, name).get("state") == "ready")          # :197-205
+    assert status(client, name)["stateTransitionTimes"].get("ready")                          # :206-212
+    assert status(client, name)["readyWorkerReplicas"] == 3 and status(client, name)["availableWorkerReplicas"] == 3
+
+    victim = workers(client, name)[0]                                                         # :215-228
+    assert client.delete_pod(NS, victim["name"])
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3)
+    assert victim["name"] not in {p["name"] for p in workers(client, name)}
+
+    client.clusters[(NS, name)]["spec"]["workerGroupSpecs"][0]["replicas"] = 5                # :230-249 (maxReplicas is 4)
+    assert eventually(r, name, lambda: len(workers(client, name)) == 4)
+    assert consistently(r, name, lambda: len(workers(client, name)) == 4)
+    assert len(heads(client, name)) == 1
+
+
+def test_autoscaler_scale_down_then_up(backend):
+    """raycluster_controller_test.go:426-530: with in-tree autoscaling the autoscaler names its victim in workersToDelete and
+    lowers replicas; exactly that Pod goes; after it clears the list a higher replicas count adds Pods back."""
+    name = "raycluster-autoscaler"
+    client = FakeClient([cluster_template(name, autoscaling=True)], [])
+    r = RayClusterReconciler(client, backend)
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3)                       # :491-496
+    set_running(everything(client, name))
+    grp = client.clusters[(NS, name)]["spec"]["workerGroupSpecs"][0]
+    victim = workers(client, name)[0]["name"]
+    grp["replicas"], grp["workersToDelete"] = 2, [victim]                                     # :498-509
+    assert eventually(r, name, lambda: len(workers(client, name)) == 2)                       # :511-514
+    assert victim not in {p["name"] for p in workers(client, name)}
+    assert consistently(r, name, lambda: len(workers(client, name)) == 2)                     # no random deletes under autoscaling
+    grp["workersToDelete"] = []                                                               # cleanUpWorkersToDelete :516-518
+    grp["replicas"] = 4                                                                       # :521-534
+    assert eventually(r, name, lambda: len(workers(client, name)) == 4)
+    assert len(heads(client, name)) == 1
+
+
+@pytest.mark.parametrize("conditions_gate", [True, False])
+def test_suspend_and_resume(backend, conditions_gate):
+    """raycluster_controller_test.go:565-735 (testSuspendRayCluster, with and without the RayClusterStatusConditions gate)."""
+    name = "raycluster-suspend"
+    client = FakeClient([cluster_template(name)], [])
+    r = RayClusterReconciler(client, backend, Env(status_conditions_gate=conditions_gate))
+    spec = client.clusters[(NS, name)]["spec"]
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3)                       # :603-608
+
+    spec["suspend"] = True                                                                    # :610-626
+    assert eventually(r, name, lambda: len(everything(client, name)) == 0)
+    assert eventually(r, name, lambda: status(client, name).get("state") == "suspended")      # :628-641
+    if conditions_gate:
+        assert eventually(r, name, lambda: cond_true(client, name, "RayClusterSuspended") and not cond_true(client, name, "RayClusterSuspending"))
+        assert not cond_true(client, name, "RayClusterProvisioned")
+        assert (status(client, name).get("head") or {}).get("podName", "") == ""
+
+    spec["suspend"] = False                                                                   # :643-680: resume, then suspend again
+    assert eventually(r, name, lambda: len(heads(client, name)) == 1 and len(workers(client, name)) == 3)
+    set_running(workers(client, name))                                                        # head stays Pending
+    spec["suspend"] = True
+    assert eventually(r, name, lambda: len(everything(client, name)) == 0)
+    assert eventually(r, name, lambda: status(client, name).get("state") == "suspended")
+    if conditions_gate:  # (the Go suite waits for the condition with its own Eventually: the deprecated state field never left "suspended")
+        assert eventually(r, name, lambda: cond_true(client, name, "RayClusterSuspended") and not cond_true(client, name, "RayClusterSuspending"))
+
+    spec["suspend"] = False                                                                   # :682-704
+    assert eventually(r, name, lambda: len(heads(client, name)) == 1 and len(workers(client, name)) == 3)
+    set_running(everything(client, name))
+    assert eventually(r, name, lambda: status(client, name).get("state") == "ready")          # :706-718
+    if conditions_gate:
+        assert eventually(r, name, lambda: not cond_true(client, name, "RayClusterSuspended") and not cond_true(client, name, "RayClusterSuspending"))
+        assert cond_true(client, name, "RayClusterProvisioned")
+        assert (status(client, name).get("head") or {}).get("podName", "") != ""
+
+
+def test_worker_group_suspend(backend):
+    """raycluster_controller_test.go:737-800 (worker-group suspend): the group's Pods go, the head stays; un-suspending brings
+    the three workers back."""
+    name = "raycluster-group-suspend"
+    client = FakeClient([cluster_template(name)], [])
+    r = RayClusterReconciler(client, backend)
+    grp = client.clusters[(NS, name)]["spec"]["workerGroupSpecs"][0]
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3)
+    set_running(everything(client, name))
+    grp["suspend"] = True
+    assert eventually(r, name, lambda: len(workers(client, name)) == 0)
+    assert consistently(r, name, lambda: len(workers(client, name)) == 0 and len(heads(client, name)) == 1)
+    grp["suspend"] = False
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3)
+    assert len(heads(client, name)) == 1
