@@ -159,7 +159,7 @@ def test_suspend_and_resume(backend, conditions_gate):
 
 
 def test_worker_group_suspend(backend):
-    """raycluster_controller_test.go:737-800 (worker-group suspend): the group's Pods go, the head stays; un-suspending brings
+    """raycluster_controller_test.go:838-878 (worker-group suspend): the group's Pods go, the head stays; un-suspending brings
     the three workers back."""
     name = "raycluster-group-suspend"
     client = FakeClient([cluster_template(name)], [])
@@ -173,3 +173,71 @@ def test_worker_group_suspend(backend):
     grp["suspend"] = False
     assert eventually(r, name, lambda: len(workers(client, name)) == 3)
     assert len(heads(client, name)) == 1
+
+
+class FinalizerClient(FakeClient):
+    """Pods that carry a finalizer are not removed by Delete: they get a deletionTimestamp and stay listed until the finalizer is
+    removed — what the apiserver does in the "atomically with Condition" suite (raycluster_controller_test.go:760-768)."""
+
+    def delete_pod(self, ns, name):
+        pod = self.pods.get((ns, name))
+        if pod is not None and pod.get("finalizers"):
+            pod["deletionTimestamp"] = "2026-01-01T00:00:00Z"
+            return True
+        return super().delete_pod(ns, name)
+
+    def remove_finalizers(self):
+        for key in list(self.pods):
+            self.pods[key].pop("finalizers", None)
+            if self.pods[key].get("deletionTimestamp"):
+                del self.pods[key]
+
+
+def suspend_status(client, name):
+    suspending, suspended = cond_true(client, name, "RayClusterSuspending"), cond_true(client, name, "RayClusterSuspended")
+    assert not (suspending and suspended)
+    return "RayClusterSuspending" if suspending else ("RayClusterSuspended" if suspended else "")
+
+
+def test_suspend_is_atomic_with_the_condition(backend):
+    """raycluster_controller_test.go:741-836: once RayClusterSuspending is on, flipping spec.suspend back to false does not stop
+    the suspension; only after the blocked Pods are really gone do both conditions clear and fresh Pods get created."""
+    name = "raycluster-suspend-atomically"
+    client = FinalizerClient([cluster_template(name)], [])
+    r = RayClusterReconciler(client, backend)
+    spec = client.clusters[(NS, name)]["spec"]
+    assert eventually(r, name, lambda: len(everything(client, name)) == 4)                    # :757-768
+    for p in everything(client, name):
+        p["finalizers"] = ["ray.io/deletion-blocker"]
+    old_names = {p["name"] for p in everything(client, name)}
+
+    spec["suspend"] = True                                                                    # :770-777
+    assert eventually(r, name, lambda: suspend_status(client, name) == "RayClusterSuspending")
+    spec["suspend"] = False                                                                   # :779-785
+    assert consistently(r, name, lambda: suspend_status(client, name) == "RayClusterSuspending")
+    assert {p["name"] for p in everything(client, name)} == old_names                         # still there, all terminating
+    assert all(p.get("deletionTimestamp") for p in everything(client, name))
+
+    client.remove_finalizers()                                                                # :787-817
+    assert eventually(r, name, lambda: suspend_status(client, name) == "")
+    assert consistently(r, name, lambda: suspend_status(client, name) == "")
+    assert eventually(r, name, lambda: len(everything(client, name)) == 4)
+    assert not ({p["name"] for p in everything(client, name)} & old_names)
+
+    spec["suspend"] = True                                                                    # :819-830
+    assert eventually(r, name, lambda: len(everything(client, name)) == 0)
+    assert eventually(r, name, lambda: suspend_status(client, name) == "RayClusterSuspended")
+    assert consistently(r, name, lambda: suspend_status(client, name) == "RayClusterSuspended")
+
+
+def test_group_suspend_with_autoscaler_is_stopped_by_validation(backend):
+    """raycluster_controller_test.go:880-920: worker-group suspend together with in-tree autoscaling fails ValidateRayClusterSpec
+    (utils/validation.go stays in the Go prelude, raycluster_controller.go:159-185), so reconcilePods never runs for the object.
+    The shim hands such an object to the engine with KR_CF_SKIP: no decision is produced and no Pod is touched."""
+    name = "raycluster-suspend-workergroup-autoscaler"
+    client = FakeClient([cluster_template(name, autoscaling=True)], [])
+    r = RayClusterReconciler(client, backend)
+    assert eventually(r, name, lambda: len(everything(client, name)) == 4)
+    client.clusters[(NS, name)]["spec"]["workerGroupSpecs"][0]["suspend"] = True
+    client.clusters[(NS, name)]["skip"] = True  # what the prelude's validation error amounts to for the batch
+    assert consistently(r, name, lambda: len(workers(client, name)) == 3 and len(heads(client, name)) == 1)
