@@ -383,3 +383,61 @@ def test_multihost_random_scale_down_only_without_autoscaler(backend):
         client.clusters[(NS, CN)]["spec"]["workerGroupSpecs"][0]["replicas"] = 2
         assert r.reconcile_pods(NS, CN) is None
         assert len(workers(client)) == want and all(len(g) == 4 for g in replica_groups(client).values())
+
+
+# ------------------------------------------------------------------ head info of calculateStatus (:1344-1513, :1319-1342)
+def _status_client(pods=None, svc=None):
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    if svc is not None:
+        cluster["headService"] = svc
+    return FakeClient([cluster], copy.deepcopy(SC["base"]["pods"]) if pods is None else pods)
+
+
+def test_head_pod_ip_and_name_table(backend):
+    """TestGetHeadPodIPAndNameFromGetRayClusterHeadPod (raycluster_controller_unit_test.go:1344-1415): one head -> its IP and
+    name; none -> both empty, no error; two -> error; head without an IP yet -> name only."""
+    base = copy.deepcopy(SC["base"]["pods"])
+    head = next(p for p in base if (p.get("labels") or {}).get("ray.io/node-type") == "head")
+    head["podIP"] = "1.2.3.4"
+    new, err = RayClusterReconciler(_status_client(base), backend).calculate_status(NS, CN)
+    assert err is None and (new["head"]["podIP"], new["head"]["podName"]) == ("1.2.3.4", head["name"])
+
+    new, err = RayClusterReconciler(_status_client([]), backend).calculate_status(NS, CN)
+    assert err is None and (new["head"]["podIP"], new["head"]["podName"]) == ("", "")
+
+    extra = {"namespace": NS, "name": "unexpectedExtraHeadNode", "labels": {"ray.io/cluster": CN, "ray.io/node-type": "head", "ray.io/group": "headgroup"}}
+    new, err = RayClusterReconciler(_status_client(base + [extra]), backend).calculate_status(NS, CN)
+    assert new is None and err == "found multiple heads"
+
+    no_ip = copy.deepcopy(base)
+    next(p for p in no_ip if p["name"] == head["name"]).pop("podIP")
+    new, err = RayClusterReconciler(_status_client(no_ip), backend).calculate_status(NS, CN)
+    assert err is None and (new["head"]["podIP"], new["head"]["podName"]) == ("", head["name"])
+
+
+def test_head_service_ip_and_name_table(backend):
+    """TestGetHeadServiceIPAndName / ...OnHeadlessService (:1417-1513): one head Service -> its ClusterIP and name; none or two
+    -> error; a headless Service (ClusterIP None) -> the head Pod's IP."""
+    svc_name = f"{CN}-head-svc"
+    new, err = RayClusterReconciler(_status_client(svc={"count": 1, "clusterIP": "1.2.3.4", "name": svc_name}), backend).calculate_status(NS, CN)
+    assert err is None and (new["head"]["serviceIP"], new["head"]["serviceName"]) == ("1.2.3.4", svc_name)
+    new, err = RayClusterReconciler(_status_client(svc={"count": 0}), backend).calculate_status(NS, CN)
+    assert new is None and err == "unable to find head service"
+    new, err = RayClusterReconciler(_status_client(svc={"count": 2, "clusterIP": "1.2.3.4", "name": svc_name}), backend).calculate_status(NS, CN)
+    assert new is None and err == "found multiple head services"
+    pods = copy.deepcopy(SC["base"]["pods"])
+    head = next(p for p in pods if (p.get("labels") or {}).get("ray.io/node-type") == "head")
+    head["podIP"] = "10.9.8.7"
+    new, err = RayClusterReconciler(_status_client(pods, svc={"count": 1, "clusterIP": "None", "name": svc_name}), backend).calculate_status(NS, CN)
+    assert err is None and (new["head"]["serviceIP"], new["head"]["serviceName"]) == ("10.9.8.7", svc_name)
+
+
+def test_update_endpoints_from_the_head_service_ports(backend):
+    """TestUpdateEndpoints (:1319-1342): status.endpoints maps every head Service port name to its (node or target) port."""
+    ports = [{"name": "client", "targetPort": 10001}, {"name": "dashboard", "targetPort": 8265}, {"name": "metrics", "targetPort": 8080},
+             {"name": "gcs-server", "targetPort": 6379}, {"name": "serve", "targetPort": 8000}]
+    client = _status_client(svc={"count": 1, "clusterIP": "10.0.0.1", "name": f"{CN}-head-svc", "ports": ports})
+    new, err = RayClusterReconciler(client, backend).calculate_status(NS, CN)
+    assert err is None
+    assert new["endpoints"] == {"client": "10001", "dashboard": "8265", "metrics": "8080", "gcs-server": "6379", "serve": "8000"}
+    assert new["_needs_write"]  # the endpoints differ from the (empty) stored status
