@@ -1,0 +1,166 @@
+// kr_common.cuh — device views of the arenas, layout constants and the small device helpers shared by every kernel.
+// Part of the sm_100a kernel set of the batched reconcile engine; see kr_kernels.cuh for the pipeline overview.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kr_engine.h"
+
+namespace kr {
+
+// ------------------------------------------------------------------------------------------------ device views
+
+struct SnapDev {  // device mirror of kr_snapshot_bufs
+  const uint32_t *c_ns_id, *c_name_id;
+  const uint64_t *c_uid_hash;
+  const uint32_t *c_flags;
+  const uint8_t *c_suspend_status, *c_ext_err_kind;
+  const uint32_t *c_ext_err_msg_id, *c_group_off, *c_group_cnt;
+  const uint64_t *c_json_off;
+  const uint32_t *c_json_len;
+  const uint8_t *c_old_state;
+  const int32_t *c_old_counts;
+  const uint8_t *c_old_cond_status, *c_old_cond_variant;
+  const uint32_t *c_old_cond_reason_id, *c_old_cond_msg_id, *c_old_head_ids;
+  const uint8_t *c_svc_count, *c_svc_ip_kind;
+  const uint32_t *c_svc_ip_id, *c_svc_name_id;
+  const uint32_t *g_cluster_idx, *g_name_id;
+  const int32_t *g_replicas, *g_min, *g_max, *g_num_hosts;
+  const uint32_t *g_flags, *g_wtd_off, *g_wtd_cnt;
+  const uint32_t *w_name_id;
+  const uint32_t *p_ns_id, *p_cluster_name_id, *p_group_name_id, *p_name_id, *p_packed;
+  const int32_t *p_replica_index;
+  const uint32_t *p_replica_name_id;
+  const uint32_t *h_pod_idx;
+  const uint8_t *h_ready_status;
+  const uint32_t *h_ready_reason_id, *h_ready_msg_id, *h_pod_ip_id;
+  const uint8_t *h_annot_state, *h_version_state, *h_annot_hash;
+  const uint32_t *j_ns_id, *j_cluster_name_id, *j_summary_id, *c_summary_id;
+  const uint8_t *json;
+};
+
+struct ResDev {  // device results arena
+  kr_cluster_result *clusters;
+  char *hash;
+  kr_group_result *groups;
+  uint32_t *wtd_pod_idx;  // unsigned for atomicMin; 0xFFFFFFFF == -1 == NotFound
+  uint32_t *sorted_pod_idx;
+  uint8_t *sorted_action;
+  int32_t *create_idx;
+  kr_job_result *jobs;
+  uint32_t *act_start;    // [n_clusters + 1]
+  uint32_t *act_pod_idx;  // [n_pods] capacity; n_actions used
+  uint8_t *act_code;
+  uint32_t *totals;  // [0]=n_create_total [1]=n_orphans [2]=n_actions [3]=error flags [4]=clusters deferred to decide phase 1
+};
+
+struct ScratchDev {
+  uint4 *cl_slots; uint32_t cl_mask;                           // cluster table: {key lo, key hi, cluster idx, -} per 16-byte slot
+  uint4 *cl_rec;                                               // [n_clusters] {group_off, group_cnt, name id of group 0, bit0 = has a multi-host group}
+  uint64_t *wt_keys; uint32_t *wt_head; uint32_t *wt_next; uint32_t wt_mask;  // workersToDelete-name table
+  uint32_t *aux_keys; uint32_t *aux_vals; uint32_t aux_mask;   // pod idx -> head-aux row
+  uint4 *rows;                                                 // 16-byte pod rows, original order
+  uint32_t *keys[2]; uint32_t *vals[2];                        // radix ping-pong
+  uint32_t *hist;                                              // [256 * ntiles] digit-major
+  uint32_t *row_total;                                         // [256] per-digit totals of the current pass
+  uint32_t *gcreate;                                           // [n_groups] dense n_create (input of the creates scan)
+  uint32_t *cact;                                              // [n_clusters] pods with an action per cluster (input of the action-list scan)
+  uint32_t *mh_rep, *mh_name, *mh_meta, *mh_cnt, *mh_flg;      // multi-host scratch, indexed by sorted position
+  uint8_t *mh_act, *mh_head;                                   // per position: action of a multi-host pod / first pod of a valid replica
+  uint32_t *tile_orph;                                         // fast pipeline: orphans per k_match tile -> exclusive prefix
+  uint32_t *chain;                                             // chained-scan hand-off cells {ready, carry} (zeroed with ccount)
+  uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]
+  uint32_t *deferred_list;                                     // clusters left for decide phase 1 (count in totals[4])
+  int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
+};
+
+struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
+
+// row.w layout: low 16 bits = p_packed low bits (+ KR_ROW_WTD_OWN), high 16 bits = group slot inside the cluster
+#define KR_ROW_WTD_OWN (1u << 11)   // named by its own group's scaleStrategy.workersToDelete
+#define KR_ROW_NO_GROUP 0xFFFFu
+#define KR_TOTALS_BIG_BUCKET 2u        // fast pipeline only: some cluster (or the orphan bucket) holds more pods than the in-warp sort takes
+
+
+static constexpr int kSortThreads = 256;
+static constexpr int kSortItems = 8;
+static constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per tile
+static constexpr int kMatchItems = 2;                        // fast pipeline: pods per thread in k_match (tile = 512 pods; occupancy beats per-thread ILP here: 8/4/2/1 items -> 47/40/33/33 us at C3)
+static constexpr int kMatchTile = kSortThreads * kMatchItems;
+static constexpr int kRadixBits = 8;
+static constexpr int kRadix = 1 << kRadixBits;
+
+// ------------------------------------------------------------------------------------------------ small helpers
+#ifdef KR_TIMELINE
+// Development aid (tools/timeline.py, built with -DKR_TIMELINE into a separate library): every kernel stamps the earliest
+// block start and the latest block end it sees (%globaltimer, ns) so the gaps between the kernels of one graph replay show.
+__device__ unsigned long long g_tl[64];
+struct TlScope {
+  int id;
+  __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+  __device__ __forceinline__ explicit TlScope(int i) : id(i) { if (threadIdx.x == 0) atomicMin(&g_tl[2 * id], now()); }
+  __device__ __forceinline__ ~TlScope() { if (threadIdx.x == 0) atomicMax(&g_tl[2 * id + 1], now()); }
+};
+#define KR_TL(id) TlScope tl_scope_(id)
+#else
+#define KR_TL(id)
+#endif
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint64_t key2(uint32_t a, uint32_t b) { return ((uint64_t)a << 32) | b; }
+// slot hash of an (a, b) id pair: two 32-bit multiplies + one finalizer (the tables are small and 2x over-provisioned)
+__device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) { return mix32(a * 0x9E3779B1u ^ (b * 0x85EBCA77u + 0x165667B1u)); }
+#define KR_EMPTY64 0xFFFFFFFFFFFFFFFFull
+#define KR_EMPTY32 0xFFFFFFFFu
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may be scheduled while
+// its stream predecessor is still running; it must not touch the predecessor's outputs before pdl_wait().  Both are no-ops
+// for ordinary launches.  pdl_trigger() lets the NEXT kernel in the chain be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__device__ __forceinline__ uint32_t pp_node_type(uint32_t f) { return (f >> KR_PP_NODE_TYPE_SHIFT) & 3u; }
+__device__ __forceinline__ uint32_t pp_phase(uint32_t f) { return (f >> KR_PP_PHASE_SHIFT) & 7u; }
+__device__ __forceinline__ uint32_t pp_ready(uint32_t f) { return (f >> KR_PP_READY_SHIFT) & 3u; }
+
+// shouldDeletePod (raycluster_controller.go:1181-1231)
+__device__ __forceinline__ bool should_delete(uint32_t f) {
+  uint32_t ph = pp_phase(f);
+  return ph == KR_PHASE_FAILED || ph == KR_PHASE_SUCCEEDED ||
+         (ph == KR_PHASE_RUNNING && (f & KR_PP_RAY_TERMINATED) && (f & KR_PP_RESTART_NEVER));
+}
+
+// utils.GetWorkerGroupDesiredReplicas (utils/util.go:386-404); int32 multiply wraps like Go's
+__device__ __forceinline__ int32_t desired_replicas(int32_t replicas, int32_t mn, int32_t mx, int32_t hosts, uint32_t gf) {
+  int32_t minr = (gf & KR_GF_MIN_NIL) ? 0 : mn;
+  int32_t maxr = (gf & KR_GF_MAX_NIL) ? INT32_MAX : mx;
+  if (gf & KR_GF_SUSPEND) return 0;
+  int32_t w;
+  if ((gf & KR_GF_REPLICAS_NIL) || replicas < minr) w = minr;
+  else if (replicas > maxr) w = maxr;
+  else w = replicas;
+  return (int32_t)((uint32_t)w * (uint32_t)hosts);
+}
+
+__device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uint32_t name, uint32_t &out) {
+  if (name == 0) return false;
+  uint32_t i = hash_pair(ns, name) & sc.cl_mask;
+  while (true) {
+    uint4 sl = __ldg(&sc.cl_slots[i]);  // one 16-byte load: key and value together
+    if (sl.x == name && sl.y == ns) { out = sl.z; return true; }
+    if (sl.x == KR_EMPTY32 && sl.y == KR_EMPTY32) return false;
+    i = (i + 1) & sc.cl_mask;
+  }
+}
+
+}  // namespace kr

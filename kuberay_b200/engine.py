@@ -27,7 +27,7 @@ class EngineError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile libkrengine.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc")
-    deps = [os.path.join(src, f) for f in ("kr_engine.cu", "kr_kernels.cuh")] + [os.path.join(_HERE, "..", "include", "kr_engine.h")]
+    deps = [os.path.join(src, f) for f in os.listdir(src) if f.endswith((".cu", ".cuh"))] + [os.path.join(_HERE, "..", "include", "kr_engine.h")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if stale:
         subprocess.check_call(["make", "-s", "-C", src, "-B", "NVCCFLAGS=-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC"])
