@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t *__restrict
 #pragma unroll
     for (int k = 0; k < 8; k++) if (i0 + k < nb) cstart[i0 + k] = excl[k];
     if (chunk == nchunks_c - 1 && threadIdx.x == 0) cstart[nb] = carry;
-    if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
+    if (big) KR_MARK_ATTEMPT_VOID(totals);
   } else {
     const uint32_t chunk = blockIdx.x - nchunks_c;
     chained_scan_chunk(tile_orph, ntiles, chunk, chain + 2 * (size_t)nchunks_c, 0, big, excl, s_warp, &s_prefix);

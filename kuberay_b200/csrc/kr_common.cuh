@@ -80,6 +80,18 @@ struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
 // row.w layout: low 16 bits = p_packed low bits (+ KR_ROW_WTD_OWN), high 16 bits = group slot inside the cluster
 #define KR_ROW_WTD_OWN (1u << 11)   // named by its own group's scaleStrategy.workersToDelete
 #define KR_ROW_NO_GROUP 0xFFFFu
+// Fast pipeline only: once a bucket too large for the in-warp sort was met (k_place_fused / k_scan_counts set the flag), the
+// rest of this attempt is void — its buckets are not in List order and sorted_pod_idx is not written for the big ones — and the
+// engine reruns the pass on the radix pipeline.  Every later kernel of the attempt leaves at once instead of chasing
+// uninitialised indices.
+// (load the word early with KR_ATTEMPT_WORD so it travels with the kernel's first real loads, test it with KR_WORD_VOID)
+// The word read here sits 128 bytes into the totals block, away from the counters the decide warps update with atomics (reading
+// totals[3] itself from every warp serialised on that hot sector: +7 us on k_decide_small).
+#define KR_TOTALS_VOID_WORD 32
+#define KR_ATTEMPT_WORD(totals) __ldcg(&(totals)[KR_TOTALS_VOID_WORD])
+#define KR_WORD_VOID(w) ((w) != 0)
+#define KR_MARK_ATTEMPT_VOID(totals) do { atomicOr(&(totals)[3], KR_TOTALS_BIG_BUCKET); (totals)[KR_TOTALS_VOID_WORD] = 1u; } while (0)
+#define KR_ATTEMPT_VOID(totals) KR_WORD_VOID(KR_ATTEMPT_WORD(totals))
 #define KR_TOTALS_BIG_BUCKET 2u        // fast pipeline only: some cluster (or the orphan bucket) holds more pods than the in-warp sort takes
 
 

@@ -614,7 +614,9 @@ __global__ void __launch_bounds__(kDecideWarps * 32, 8) k_decide_small(DecideArg
   const uint32_t c = blockIdx.x * kDecideWarps + warp;
   pdl_wait(); pdl_trigger();
   if (c >= a.n.n_clusters) return;
+  const uint32_t attempt = KR_ATTEMPT_WORD(a.r.totals);
   const uint32_t seg0 = LDG(a.sc.cstart[c]), seg1 = LDG(a.sc.cstart[c + 1]);
+  if (KR_WORD_VOID(attempt)) return;
   const uint32_t P = seg1 - seg0;
   if (!small_path(a, c, P)) return;
   if (P <= 128) decide_cluster_regs<4>(a, c, seg0, seg1, s_acc[warp], s_mode[warp], lane);
@@ -628,6 +630,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide(DecideArgs a) {
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t Nc = a.n.n_clusters, Np = a.n.n_pods;
+  if (a.fast && KR_ATTEMPT_VOID(a.r.totals)) return;
   uint32_t c = blockIdx.x * kDecideWarps + warp;
   if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
     if (c >= a.r.totals[4]) return;

@@ -10,6 +10,7 @@ namespace kr {
 
 // exclusive scan of the dense n_create array -> groups[].create_off, total in totals[0] (chained multi-block scan).
 __global__ void __launch_bounds__(1024) k_scan_creates(ResDev r, const uint32_t *__restrict__ gcreate, uint32_t n_groups, uint32_t *chain) {
+  if (KR_ATTEMPT_VOID(r.totals)) return;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_prefix;
   uint32_t excl[8];
@@ -46,9 +47,10 @@ __device__ __forceinline__ void create_fill_group(const SnapDev &s, const Scratc
     __syncwarp();
     for (uint32_t b = seg0; b < seg1; b += 32) {
       uint32_t i = b + lane;
-      if (i < seg1 && (mh ? sc.mh_head[i] != 0 : r.sorted_action[i] == KR_ACT_KEEP)) {  // runningPods: listed and not deleted by name
-        uint4 row = sc.rows[r.sorted_pod_idx[i]];
-        if ((row.w >> 16) == slot && (row.w & KR_PP_HAS_REPLICA_IDX)) {
+      if (i < seg1) {
+        const uint4 row = sc.rows[r.sorted_pod_idx[i]];
+        // this group's pods first (mh_head is only written for them), then runningPods: listed and not deleted by name
+        if ((row.w >> 16) == slot && (row.w & KR_PP_HAS_REPLICA_IDX) && (mh ? sc.mh_head[i] != 0 : r.sorted_action[i] == KR_ACT_KEEP)) {
           int32_t idx = (int32_t)row.z;
           if (idx >= 0 && (uint64_t)idx >= w0 && (uint64_t)idx < w0 + 1024 && (uint64_t)idx < bound)
             atomicOr(&s_bits[(idx - w0) >> 5], 1u << ((idx - w0) & 31));
@@ -76,6 +78,7 @@ __device__ __forceinline__ void create_fill_group(const SnapDev &s, const Scratc
 }
 
 __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, ResDev r, Sizes n, kr_flags f, uint32_t create_cap) {
+  if (KR_ATTEMPT_VOID(r.totals)) return;
   __shared__ uint32_t s_bits[4][32];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t g = blockIdx.x * 4 + warp;
@@ -101,6 +104,7 @@ __device__ __forceinline__ void compact_cluster_actions(const ResDev &r, uint32_
 
 // unfused path: starts of the per-cluster action lists (chained scan) ...
 __global__ void __launch_bounds__(1024) k_scan_actions(ResDev r, const uint32_t *__restrict__ cact, uint32_t n_clusters, uint32_t *chain) {
+  if (KR_ATTEMPT_VOID(r.totals)) return;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_prefix;
   uint32_t excl[8];
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(1024) k_scan_actions(ResDev r, const uint32_t 
 }
 // ... and the lists themselves, one warp per cluster
 __global__ void __launch_bounds__(128) k_compact_actions(ResDev r, const uint32_t *__restrict__ cact, uint32_t n_clusters) {
+  if (KR_ATTEMPT_VOID(r.totals)) return;
   const uint32_t c = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (c >= n_clusters || cact[c] == 0) return;
   compact_cluster_actions(r, c, r.act_start[c], threadIdx.x & 31);
@@ -153,7 +158,9 @@ __device__ __forceinline__ uint32_t block_scan_to_smem(const uint32_t *__restric
     if (t == 0) *s_carry += total;
     __syncthreads();
   }
-  return *s_carry;
+  const uint32_t grand_total = *s_carry;
+  __syncthreads();  // every thread has read the total before a following call resets the carry
+  return grand_total;
 }
 
 // bucket starts + placement in one persistent kernel (replaces k_scan_counts + k_place)
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(1024) k_place_fused(const uint32_t *__restrict
   __syncthreads();
   if (blockIdx.x == 0) {
     for (uint32_t i = threadIdx.x; i <= nb; i += blockDim.x) cstart[i] = sm_start[i];
-    if (big) atomicOr(&totals[3], KR_TOTALS_BIG_BUCKET);
+    if (big) KR_MARK_ATTEMPT_VOID(totals);
   }
   // four pods per thread per trip: all eight loads are in flight before the first dependent shared-memory lookup
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_bits[32][32];
   pdl_wait(); pdl_trigger();
+  const uint32_t attempt = KR_ATTEMPT_WORD(r.totals);
   uint32_t *sm_off = sm_dyn;               // [n_groups] create offsets
   uint32_t *sm_act = sm_dyn + n.n_groups;  // [n_clusters + 1] action-list starts
   bool dummy = false;
@@ -213,6 +221,7 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   uint32_t tot_act = block_scan_to_smem(sc.cact, n.n_clusters, sm_act, 0, dummy, s_warp, &s_carry);
   if (threadIdx.x == 0) sm_act[n.n_clusters] = tot_act;
   __syncthreads();
+  if (KR_WORD_VOID(attempt)) return;  // (the scans above only touch counters; what follows would chase unwritten pod lists)
   if (blockIdx.x == 0) {
     for (uint32_t g = threadIdx.x; g < n.n_groups; g += blockDim.x) r.groups[g].create_off = sm_off[g];
     for (uint32_t c = threadIdx.x; c <= n.n_clusters; c += blockDim.x) r.act_start[c] = sm_act[c];

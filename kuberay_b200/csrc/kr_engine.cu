@@ -79,7 +79,7 @@ struct OutLayout {  // results arena: [small fixed part | full pod lists | varia
 OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
   OutLayout L;
   size_t o = 0;
-  L.totals = o; o = align_up(o + 32);
+  L.totals = o; o = align_up(o + 256);  // 8 counters + (128 bytes in) the void-attempt word
   L.clusters = o; o = align_up(o + sizeof(kr_cluster_result) * (size_t)n.n_clusters);
   L.hash = o; o = align_up(o + 32 * (size_t)n.n_clusters);
   L.groups = o; o = align_up(o + sizeof(kr_group_result) * (size_t)n.n_groups);
@@ -333,7 +333,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     ClearArgs ca{};
     ca.ptr[0] = reinterpret_cast<uint32_t *>(e->d_scratch); ca.words[0] = (uint32_t)(e->sl.ff_total / 4); ca.value[0] = 0xFFFFFFFFu;
     ca.ptr[1] = r.wtd_pod_idx; ca.words[1] = n.n_wtd; ca.value[1] = 0xFFFFFFFFu;
-    ca.ptr[2] = r.totals; ca.words[2] = 8; ca.value[2] = 0;
+    ca.ptr[2] = r.totals; ca.words[2] = 64; ca.value[2] = 0;  // the 8 counters and, 128 bytes in, the void-attempt word (the block is 256 bytes)
     ca.ptr[3] = sc.ccount; ca.words[3] = e->force_radix ? 0u : (uint32_t)((e->sl.cstart - e->sl.ccount) / 4); ca.value[3] = 0;  // per-cluster counts + the chained-scan cells
     mark("k_clear");
     k_clear<<<e->sm_count * 2, 256, 0, M>>>(ca);
@@ -620,6 +620,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaMalloc((void **)&e->d_in, e->in_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_scratch, e->scratch_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
+  cudaMemset(e->d_out, 0, e->out_cap);  // the alignment padding between the result arrays travels with the single D2H copy
   cudaFuncSetAttribute(k_place_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   cudaFuncSetAttribute(k_creates_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   {
@@ -900,7 +901,6 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
   size_t o_off = 0, o_len = align_up(8 * (size_t)n), o_data = align_up(o_len + 4 * (size_t)n), o_out = align_up(o_data + data + 16), total = o_out + 32 * (size_t)n;
   if (total > e->hb_cap) {
     if (e->hb_h) cudaFreeHost(e->hb_h);
-  if (e->h_totals) cudaFreeHost(e->h_totals);
     if (e->hb_d) cudaFree(e->hb_d);
     e->hb_h = nullptr; e->hb_d = nullptr; e->hb_cap = 0;
     size_t cap = total + total / 4;

@@ -217,6 +217,24 @@ def test_hash_batch_matches_hashlib():
     assert got == want
 
 
+def test_hash_batch_and_passes_share_an_engine(oracle_mod):
+    """kr_hash_batch (the RayService callers' entry point) between passes of the same engine: its staging buffers grow
+    without disturbing the pass's own pinned buffers (a stray free there once corrupted the totals record)."""
+    import base64
+    import hashlib
+    snap, flags = synthetic.generate(synthetic.config("C2"))
+    eng = Engine.for_snapshot(snap)
+    try:
+        eng.load(snap)
+        want = oracle_mod.run(snap, flags, threads=8)
+        for size in (10, 1000, 40000):
+            msgs = [bytes([i % 251]) * (i % 700) for i in range(size // 10)]
+            assert eng.hash_batch(msgs) == [base64.b32hexencode(hashlib.sha1(m).digest()).decode() for m in msgs]
+            assert not want.diff(eng.reconcile(flags)), size
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("seed0", [0, 100, 200, 300])
 def test_fuzz_adversarial_snapshots(seed0, oracle_mod, monkeypatch):
     """Differential fuzz: tiny snapshots drawn from the whole input domain (tests/fuzz_objects.py), packed like the golden
