@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_bits[32][32];
   pdl_wait(); pdl_trigger();
-  const uint32_t attempt = KR_ATTEMPT_WORD(r.totals);
+  if (KR_ATTEMPT_VOID(r.totals)) return;  // (a void attempt never wrote the counters scanned below)
   uint32_t *sm_off = sm_dyn;               // [n_groups] create offsets
   uint32_t *sm_act = sm_dyn + n.n_groups;  // [n_clusters + 1] action-list starts
   bool dummy = false;
@@ -221,7 +221,6 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   uint32_t tot_act = block_scan_to_smem(sc.cact, n.n_clusters, sm_act, 0, dummy, s_warp, &s_carry);
   if (threadIdx.x == 0) sm_act[n.n_clusters] = tot_act;
   __syncthreads();
-  if (KR_WORD_VOID(attempt)) return;  // (the scans above only touch counters; what follows would chase unwritten pod lists)
   if (blockIdx.x == 0) {
     for (uint32_t g = threadIdx.x; g < n.n_groups; g += blockDim.x) r.groups[g].create_off = sm_off[g];
     for (uint32_t c = threadIdx.x; c <= n.n_clusters; c += blockDim.x) r.act_start[c] = sm_act[c];
