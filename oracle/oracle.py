@@ -30,7 +30,7 @@ def build(force: bool = False) -> str:
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(os.environ.get("KR_ORACLE_LIB") or build())  # KR_ORACLE_LIB: e.g. the ASan/UBSan build (make -C oracle asan)
         L.kr_oracle_run.argtypes = [C.POINTER(abi.kr_snapshot_bufs), C.POINTER(abi.kr_sizes), C.POINTER(abi.kr_flags),
                                     C.POINTER(abi.kr_oracle_out), C.c_int, C.c_int]
         L.kr_oracle_run.restype = C.c_int
