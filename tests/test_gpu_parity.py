@@ -386,3 +386,23 @@ def test_fixed_layout_keeps_addresses_and_resident_data(oracle_mod):
             eng.set_fixed_layout(False)  # only before the first begin
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_parity_stressed_distributions(seed, oracle_mod, monkeypatch):
+    """Medium snapshots with the rare branches made common: a third of the clusters suspended / on the Recreate gate (large
+    phase-1 list) / waiting on expectations, half of the groups multi-host or carrying workersToDelete, many orphans."""
+    rng = np.random.default_rng(seed)
+    params = synthetic.SynthParams(
+        n_clusters=int(rng.integers(500, 3000)), pods_per_cluster=int(rng.integers(5, 130)), groups=int(rng.integers(1, 5)),
+        clusters_per_namespace=int(rng.integers(1, 200)), autoscaling_frac=float(rng.random()), suspended_frac=float(rng.random() * 0.3),
+        recreate_frac=float(rng.random() * 0.4), expect_pending_frac=float(rng.random() * 0.3), wtd_group_frac=float(rng.random() * 0.6),
+        orphan_frac=float(rng.random() * 0.1), multihost_frac=float(rng.random() * 0.6), steady_frac=float(rng.random()), jobs=bool(seed % 2),
+        seed=synthetic.SEED + seed)
+    snap, flags = synthetic.generate(params)
+    flags.env_random_pod_delete = seed % 2
+    got = _parity(snap, flags, oracle_mod)
+    assert got.n_actions > 0
+    if seed % 3 == 0:
+        monkeypatch.setenv("KR_FORCE_RADIX", "1")
+        _parity(snap, flags, oracle_mod)
