@@ -16,7 +16,9 @@
  * Pinning: the Go reference cannot be built here (no Go toolchain; k8s deps un-vendored), so this
  * restatement is pinned against the reference's own known-answer tests, transcribed to
  * tests/golden (JSON) (utils/util_test.go:408-475,555-894; raycluster_controller_unit_test.go:
- * 417-1010,1611-2221,2380-2503,2873-3137,3680-3814; utils/consistency_test.go:16-146).
+ * 417-1010,1319-1513,1611-2221,2380-2503,2873-3137,3680-3814; utils/consistency_test.go:16-146)
+ * and the envtest suites restated as closed loops (raycluster_controller_test.go:132-249,426-530,
+ * 565-920,925-1123; tests/test_envtest_lifecycle.py, tests/test_golden.py).
  * SHA-1/base32hex are pinned by FIPS 180 / RFC 4648 vectors and python hashlib.  Literal spec-hash
  * digests vs Go are UNPINNED in the reference itself (no golden digest exists in its tree): the
  * hash input bytes are produced by Go's json.Marshal in production and passed through verbatim.
