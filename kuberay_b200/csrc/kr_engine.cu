@@ -268,7 +268,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   return s;
 }
 
-// Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait / pdl_trigger in kr_kernels.cuh).
+// Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait / pdl_trigger in kr_common.cuh).
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg{};
