@@ -68,6 +68,7 @@ struct ScratchDev {
   uint32_t *cact;                                              // [n_clusters] pods with an action per cluster (input of the action-list scan)
   uint32_t *mh_rep, *mh_name, *mh_meta, *mh_cnt, *mh_flg;      // multi-host scratch, indexed by sorted position
   uint8_t *mh_act, *mh_head;                                   // per position: action of a multi-host pod / first pod of a valid replica
+  uint32_t *act_tmp_idx; uint8_t *act_tmp_code;                // per cluster, from its pod_start: the pods it acts on (compacted by the decide warp)
   uint32_t *tile_orph;                                         // fast pipeline: orphans per k_match tile -> exclusive prefix
   uint32_t *chain;                                             // chained-scan hand-off cells {ready, carry} (zeroed with ccount)
   uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]

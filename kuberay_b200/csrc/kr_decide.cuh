@@ -566,7 +566,13 @@ __device__ __forceinline__ void decide_cluster(const DecideArgs &a, const uint32
     }
     __syncwarp();
     if (valid) a.r.sorted_action[i] = act;
-    n_act += __popc(__ballot_sync(0xFFFFFFFFu, valid && act != KR_ACT_KEEP));
+    // the cluster's action list, compacted while the pods are still in registers (k_creates_fused / k_compact_actions only move it)
+    const uint32_t abal = __ballot_sync(0xFFFFFFFFu, valid && act != KR_ACT_KEEP);
+    if (valid && act != KR_ACT_KEEP) {
+      const size_t o = (size_t)seg0 + n_act + __popc(abal & lt);
+      a.sc.act_tmp_idx[o] = pod; a.sc.act_tmp_code[o] = act;
+    }
+    n_act += __popc(abal);
   }
 
   // ---------------- status roll-up + record

@@ -87,19 +87,10 @@ __global__ void __launch_bounds__(128) k_create_fill(SnapDev s, ScratchDev sc, R
 }
 
 // Compact action list of one cluster: (pod idx, action) of every pod whose action != KEEP, List order kept (one warp).
-__device__ __forceinline__ void compact_cluster_actions(const ResDev &r, uint32_t c, uint32_t dst, uint32_t lane) {
-  const kr_cluster_result *cr = &r.clusters[c];
-  const uint32_t seg0 = cr->pod_start;
-  // n_pods is only filled when calculateStatus ran; a cluster with actions always has it
-  const uint32_t seg1 = seg0 + (uint32_t)cr->n_pods;
-  const uint32_t lt = lanemask_lt();
-  for (uint32_t b = seg0; b < seg1; b += 32) {
-    uint32_t i = b + lane;
-    uint8_t act = i < seg1 ? r.sorted_action[i] : (uint8_t)KR_ACT_KEEP;
-    uint32_t bal = __ballot_sync(0xFFFFFFFFu, act != KR_ACT_KEEP);
-    if (act != KR_ACT_KEEP) { uint32_t o = dst + __popc(bal & lt); r.act_pod_idx[o] = r.sorted_pod_idx[i]; r.act_code[o] = act; }
-    dst += __popc(bal);
-  }
+__device__ __forceinline__ void compact_cluster_actions(const ResDev &r, const ScratchDev &sc, uint32_t c, uint32_t dst, uint32_t cnt, uint32_t lane) {
+  // the decide warp left the cluster's cnt actions compacted at its pod_start (List order): move them to their place in the list
+  const size_t src = r.clusters[c].pod_start;
+  for (uint32_t k = lane; k < cnt; k += 32) { r.act_pod_idx[dst + k] = sc.act_tmp_idx[src + k]; r.act_code[dst + k] = sc.act_tmp_code[src + k]; }
 }
 
 // unfused path: starts of the per-cluster action lists (chained scan) ...
@@ -117,31 +108,36 @@ __global__ void __launch_bounds__(1024) k_scan_actions(ResDev r, const uint32_t 
   if (chunk == gridDim.x - 1 && threadIdx.x == 0) r.act_start[n_clusters] = carry;
 }
 // ... and the lists themselves, one warp per cluster
-__global__ void __launch_bounds__(128) k_compact_actions(ResDev r, const uint32_t *__restrict__ cact, uint32_t n_clusters) {
+__global__ void __launch_bounds__(128) k_compact_actions(ResDev r, ScratchDev sc, uint32_t n_clusters) {
   if (KR_ATTEMPT_VOID(r.totals)) return;
-  const uint32_t c = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (c >= n_clusters || cact[c] == 0) return;
-  compact_cluster_actions(r, c, r.act_start[c], threadIdx.x & 31);
+  uint32_t c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= n_clusters) return;
+  const uint32_t cnt = sc.cact[c];
+  if (cnt == 0) return;
+  compact_cluster_actions(r, sc, c, r.act_start[c], cnt, threadIdx.x & 31);
 }
 
 // ---- fused variants for snapshots whose per-cluster / per-group counters fit in shared memory: every block scans the counters
 // itself (a few tens of KB out of L2) instead of waiting for a scan kernel, which removes two ~10 us stages from the chain.
 static constexpr uint32_t kFusedMaxCounters = 48 * 1024;  // 192 KB of shared memory
 
-// exclusive scan of in[0..n) into shared memory by the whole block (any block size that is a multiple of 32, <= 1024)
+// exclusive scan of in[0..n) into shared memory by the whole block (any block size that is a multiple of 32, <= 1024).
+// 8 counters per thread per trip keeps the 1024-thread CTAs at 32 registers: with 16 the CTA no longer fits beside the blocks
+// of the previous kernel and the programmatic early launch turns into a wait (k_place_fused started 25 us late)
 __device__ __forceinline__ uint32_t block_scan_to_smem(const uint32_t *__restrict__ in, uint32_t n, uint32_t *out_sm, uint32_t big_limit, bool &big,
                                                        uint32_t *s_warp, uint32_t *s_carry) {
   const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
   if (t == 0) *s_carry = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < n; base += blockDim.x * 8) {
-    uint32_t i0 = base + t * 8;
-    uint32_t v[8];
+  constexpr int V = 8;
+  for (uint32_t base = 0; base < n; base += blockDim.x * V) {
+    uint32_t i0 = base + t * V;
+    uint32_t v[V];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (i0 + k < n) ? __ldg(&in[i0 + k]) : 0u;
+    for (int k = 0; k < V; k++) v[k] = (i0 + k < n) ? __ldg(&in[i0 + k]) : 0u;
     uint32_t sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { sum += v[k]; big |= (i0 + k < big_limit) && v[k] > KR_FAST_MAX_BUCKET; }
+    for (int k = 0; k < V; k++) { sum += v[k]; big |= (i0 + k < big_limit) && v[k] > KR_FAST_MAX_BUCKET; }
     uint32_t x = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
@@ -153,7 +149,7 @@ __device__ __forceinline__ uint32_t block_scan_to_smem(const uint32_t *__restric
     uint32_t woff = __shfl_sync(0xFFFFFFFFu, wx - wv, w), total = __shfl_sync(0xFFFFFFFFu, wx, 31);
     uint32_t run = *s_carry + woff + x - sum;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { if (i0 + k < n) out_sm[i0 + k] = run; run += v[k]; }
+    for (int k = 0; k < V; k++) { if (i0 + k < n) out_sm[i0 + k] = run; run += v[k]; }
     __syncthreads();
     if (t == 0) *s_carry += total;
     __syncthreads();
@@ -230,7 +226,7 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   for (uint32_t g = blockIdx.x * nw + warp; g < n.n_groups; g += gridDim.x * nw)
     if (__ldg(&sc.gcreate[g])) create_fill_group(s, sc, r, f, g, sm_off[g], create_cap, s_bits[warp], lane);
   for (uint32_t c = blockIdx.x * nw + warp; c < n.n_clusters; c += gridDim.x * nw)
-    if (sm_act[c + 1] != sm_act[c]) compact_cluster_actions(r, c, sm_act[c], lane);
+    if (sm_act[c + 1] != sm_act[c]) compact_cluster_actions(r, sc, c, sm_act[c], sm_act[c + 1] - sm_act[c], lane);
 }
 
 // ------------------------------------------------------------------------------------------------ k_patch_pods

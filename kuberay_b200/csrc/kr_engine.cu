@@ -99,7 +99,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
@@ -143,6 +143,8 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.mh_flg = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.mh_act = o; o = align_up(o + (size_t)n.n_pods);
   L.mh_head = o; o = align_up(o + (size_t)n.n_pods);
+  L.act_tmp_idx = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.act_tmp_code = o; o = align_up(o + (size_t)n.n_pods);
   L.total = o;
   return L;
 }
@@ -265,6 +267,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.mh_rep = reinterpret_cast<uint32_t *>(b + L.mh_rep); s.mh_name = reinterpret_cast<uint32_t *>(b + L.mh_name);
   s.mh_meta = reinterpret_cast<uint32_t *>(b + L.mh_meta); s.mh_cnt = reinterpret_cast<uint32_t *>(b + L.mh_cnt);
   s.mh_flg = reinterpret_cast<uint32_t *>(b + L.mh_flg); s.mh_act = b + L.mh_act; s.mh_head = b + L.mh_head;
+  s.act_tmp_idx = reinterpret_cast<uint32_t *>(b + L.act_tmp_idx); s.act_tmp_code = b + L.act_tmp_code;
   return s;
 }
 
@@ -424,7 +427,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       mark("k_scan_actions");
       k_scan_actions<<<nch_a, 1024, 0, M>>>(r, sc.cact, n.n_clusters, achain);
       mark("k_compact_actions");
-      k_compact_actions<<<(n.n_clusters + 3) / 4, 128, 0, M>>>(r, sc.cact, n.n_clusters);
+      k_compact_actions<<<(n.n_clusters + 3) / 4, 128, 0, M>>>(r, sc, n.n_clusters);
     } else CK(cudaMemsetAsync(r.act_start, 0, 4, M));
   }
   if (e->no_fuse || (uint64_t)n.n_groups + n.n_clusters + 1 > kFusedMaxCounters) if (n.n_groups) {
