@@ -116,8 +116,10 @@ struct TlScope {
   __device__ __forceinline__ ~TlScope() { if (threadIdx.x == 0) atomicMax(&g_tl[2 * id + 1], now()); }
 };
 #define KR_TL(id) TlScope tl_scope_(id)
+#define KR_TL_POINT(id) do { if (threadIdx.x == 0) { unsigned long long t_ = TlScope::now(); atomicMin(&g_tl[2 * (id)], t_); atomicMax(&g_tl[2 * (id) + 1], t_); } } while (0)
 #else
 #define KR_TL(id)
+#define KR_TL_POINT(id)
 #endif
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
