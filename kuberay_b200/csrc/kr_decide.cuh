@@ -591,35 +591,44 @@ __device__ __forceinline__ void decide_cluster_regs(const DecideArgs &a, uint32_
                                                     int32_t (&s_acc)[4][KR_SMEM_GROUPS], int32_t (&s_mode)[2][KR_SMEM_GROUPS], uint32_t lane) {
   uint32_t pidx[K], pw[K];
   const uint32_t P = seg1 - seg0;
+  if (a.phase == 0) {
 #pragma unroll
-  for (int k = 0; k < K; k++) { uint32_t g = k * 32 + lane; pidx[k] = g < P ? LDG(a.unsorted[seg0 + g]) : 0xFFFFFFFFu; }
-  warp_bitonic_sort_striped<K>(pidx, lane);
+    for (int k = 0; k < K; k++) { uint32_t g = k * 32 + lane; pidx[k] = g < P ? LDG(a.unsorted[seg0 + g]) : 0xFFFFFFFFu; }
+    warp_bitonic_sort_striped<K>(pidx, lane);
+  } else {  // phase 1: phase 0 sorted and published this bucket before it deferred the cluster
+#pragma unroll
+    for (int k = 0; k < K; k++) { uint32_t g = k * 32 + lane; pidx[k] = g < P ? a.r.sorted_pod_idx[seg0 + g] : 0xFFFFFFFFu; }
+  }
 #pragma unroll
   for (int k = 0; k < K; k++) {
     uint32_t g = k * 32 + lane;
     pw[k] = 0;
-    if (g < P) { a.r.sorted_pod_idx[seg0 + g] = pidx[k]; pw[k] = reinterpret_cast<const uint32_t *>(a.sc.rows)[4 * (size_t)pidx[k] + 3]; }
+    if (g < P) { if (a.phase == 0) a.r.sorted_pod_idx[seg0 + g] = pidx[k]; pw[k] = reinterpret_cast<const uint32_t *>(a.sc.rows)[4 * (size_t)pidx[k] + 3]; }
     else pidx[k] = 0;
   }
   __syncwarp();  // sorted_pod_idx of this bucket is visible to the whole warp (decide_multihost re-reads it)
   decide_cluster<K, false>(a, c, seg0, seg1, pidx, pw, s_acc, s_mode, lane);
 }
 
-// Is this cluster decided by k_decide_small (bucket sorted and kept in registers)?  Fast pipeline, phase 0, at most 256
-// pods, no multi-host worker group (those need the memory-resident sweeps of decide_multihost).
+// Is this cluster decided by k_decide_small (bucket sorted and kept in registers)?  Fast pipeline, at most 256 pods, no
+// multi-host worker group (those need the memory-resident sweeps of decide_multihost).  Both phases: the clusters phase 0
+// deferred (Recreate gate waiting for the hash) keep their shape, so phase 1 splits them between the same two kernels.
 __device__ __forceinline__ bool small_path(const DecideArgs &a, uint32_t c, uint32_t P) {
-  return a.fast && a.phase == 0 && P <= 256 && !(a.f.gate_multihost_indexing && (__ldg(&a.sc.cl_rec[c]).w & 1u));
+  return a.fast && P <= 256 && !(a.f.gate_multihost_indexing && (__ldg(&a.sc.cl_rec[c]).w & 1u));
 }
 
 // Common case: one warp per RayCluster with <= 256 pods, everything after the bucket load stays in registers.
 __global__ void __launch_bounds__(kDecideWarps * 32, 8) k_decide_small(DecideArgs a) {
-  KR_TL(3);
+  KR_TL(a.phase ? 12 : 3);
   __shared__ int32_t s_acc[kDecideWarps][4][KR_SMEM_GROUPS];  // n_list, n_unhealthy, n_wtd_own, running-rank cursor
   __shared__ int32_t s_mode[kDecideWarps][2][KR_SMEM_GROUPS]; // mode, delete-prefix length
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t c = blockIdx.x * kDecideWarps + warp;
+  uint32_t c = blockIdx.x * kDecideWarps + warp;
   pdl_wait(); pdl_trigger();
-  if (c >= a.n.n_clusters) return;
+  if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
+    if (c >= a.r.totals[4]) return;
+    c = a.sc.deferred_list[c];
+  } else if (c >= a.n.n_clusters) return;
   const uint32_t attempt = KR_ATTEMPT_WORD(a.r.totals);
   const uint32_t seg0 = LDG(a.sc.cstart[c]), seg1 = LDG(a.sc.cstart[c + 1]);
   if (KR_WORD_VOID(attempt)) return;

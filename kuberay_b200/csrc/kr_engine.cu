@@ -155,7 +155,7 @@ struct kr_engine {
   kr_config cfg{};
   cudaStream_t sm = nullptr, sh = nullptr, sg = nullptr, scopy = nullptr;
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_cols = nullptr, ev_json = nullptr;  // commit: copy start, columns landed, JSON landed
-  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   cudaEvent_t ev_k[KR_MAX_KERNEL_TIMES + 1]{};
   uint8_t *h_in = nullptr, *d_in = nullptr, *d_scratch = nullptr, *d_out = nullptr, *h_out = nullptr;
@@ -412,9 +412,15 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   if (e->n_recreate > 0 && do_hash) {
     da.phase = 1;
     uint32_t warps = e->n_recreate;  // upper bound on the deferred list
+    const dim3 grid1((warps + kDecideWarps - 1) / kDecideWarps), block1(kDecideWarps * 32);
+    // like phase 0: the register-resident kernel on M for the small clusters, the general one beside it on G for the rest
+    cudaStream_t G1 = (fast && !profile) ? e->sg : M;
+    if (fast && !profile) { CK(cudaEventRecord(e->ev_fork3, M)); CK(cudaStreamWaitEvent(G1, e->ev_fork3, 0)); }
     mark("k_decide_phase1");
-    k_decide<<<(warps + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, M>>>(da);
-    creates_after_kernel = true;
+    k_decide<<<grid1, block1, 0, G1>>>(da);
+    if (fast) { mark("k_decide_small_phase1"); k_decide_small<<<grid1, block1, 0, M>>>(da); }
+    if (fast && !profile) { CK(cudaEventRecord(e->ev_join3, G1)); CK(cudaStreamWaitEvent(M, e->ev_join3, 0)); }
+    creates_after_kernel = !(fast && !profile);
   }
   if (!e->no_fuse && (uint64_t)n.n_groups + n.n_clusters + 1 <= kFusedMaxCounters) {
     mark("k_creates_fused");
@@ -614,6 +620,8 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   cudaEventCreate(&e->ev_h2d0); cudaEventCreate(&e->ev_h2d1); cudaEventCreateWithFlags(&e->ev_pr, cudaEventDisableTiming); cudaEventCreate(&e->ev_cols); cudaEventCreate(&e->ev_json);
   cudaEventCreateWithFlags(&e->ev_fork2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_fork3, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_join3, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_hash, cudaEventDisableTiming);
   cudaEventCreate(&e->ev_a); cudaEventCreate(&e->ev_b); cudaEventCreate(&e->ev_c);
@@ -679,6 +687,8 @@ void kr_engine_destroy(kr_engine *e) {
   for (auto ev : {e->ev_h2d0, e->ev_h2d1, e->ev_cols, e->ev_json, e->ev_pr}) if (ev) cudaEventDestroy(ev);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
+  if (e->ev_fork3) cudaEventDestroy(e->ev_fork3);
+  if (e->ev_join3) cudaEventDestroy(e->ev_join3);
   delete e;
 }
 

@@ -19,7 +19,7 @@ import torch  # noqa: E402
 from kuberay_b200 import synthetic  # noqa: E402
 from kuberay_b200.engine import Engine, lib  # noqa: E402
 
-NAMES = {10: "  creates: scans done", 11: "  creates: fills done", 9: "k_clear", 0: "k_build_tables", 1: "k_match", 2: "k_place_fused", 3: "k_decide_small", 4: "k_decide<general>", 5: "k_decide<phase 1>",
+NAMES = {10: "  creates: scans done", 11: "  creates: fills done", 9: "k_clear", 0: "k_build_tables", 1: "k_match", 2: "k_place_fused", 3: "k_decide_small", 4: "k_decide<general>", 5: "k_decide<phase 1>", 12: "k_decide_small<ph 1>",
          6: "k_creates_fused", 7: "k_hash2", 8: "k_jobs"}
 
 
