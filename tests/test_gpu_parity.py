@@ -406,3 +406,38 @@ def test_parity_stressed_distributions(seed, oracle_mod, monkeypatch):
     if seed % 3 == 0:
         monkeypatch.setenv("KR_FORCE_RADIX", "1")
         _parity(snap, flags, oracle_mod)
+
+
+def test_remaining_entry_points(oracle_mod):
+    """kr_reconcile_device_only + kr_results_fetch (the split the benchmark's value leg uses), kr_reconcile_batch_profiled,
+    kr_group_results_device / _copy (the multi-GPU all-gather's source) and kr_algorithmic_bytes."""
+    import torch
+    snap, flags = synthetic.generate(synthetic.config("C2", groups=2, jobs=True))
+    want = oracle_mod.run(snap, flags, threads=8)
+    eng = Engine.for_snapshot(snap)
+    try:
+        eng.load(snap)
+        with pytest.raises(Exception):
+            eng.fetch()                                   # nothing has run on this snapshot yet
+        eng.reconcile_device_only(flags)                  # kernels only, results stay in HBM
+        assert eng.last_profile()["kernels_ms"] > 0
+        assert not want.diff(eng.fetch())                 # ... until they are asked for
+        prof = eng.reconcile_profiled(flags)              # serialised, one event pair per kernel
+        names = [k for k, _ in prof["kernels"]]
+        assert {"k_clear", "k_build_tables", "k_match", "k_decide_small", "k_hash", "k_jobs"} <= set(names) and all(ms > 0 for _, ms in prof["kernels"])
+        assert not want.diff(eng.fetch())
+        ptr, nbytes = eng.group_results_device()
+        assert ptr and nbytes == 32 * snap.dims["groups"]
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        eng.group_results_copy(buf.data_ptr(), buf.numel())
+        assert np.array_equal(buf.cpu().numpy().view(abi.group_result_dtype), want.groups)
+        with pytest.raises(Exception):
+            eng.group_results_copy(buf.data_ptr(), nbytes - 1)   # destination too small: KR_E_CAPACITY, no partial copy
+        alg = eng.algorithmic_bytes()
+        d = snap.dims
+        # SURVEY §8(d): 144 B/cluster (32 of them the digest, counted with the hash) + 56 B/group + 4 B/workersToDelete name + 33 B/pod + L
+        assert alg["hash"] == int(snap.c_json_len.sum()) + 32 * d["clusters"]
+        assert alg["match"] == 112 * d["clusters"] + 56 * d["groups"] + 4 * d["wtd"] + 33 * d["pods"]
+        assert alg["pass"] == alg["hash"] + alg["match"]
+    finally:
+        eng.close()
