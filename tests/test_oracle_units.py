@@ -207,3 +207,46 @@ def test_fuzz_list_modes_agree(seed0, oracle_mod):
         b = oracle_mod.run(snap, flags, list_mode=oracle_mod.NS_SCAN, threads=3)
         d = a.diff(b)
         assert not d, (seed, d[:5])
+
+
+def _i32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+def _desired_replicas_model(replicas, min_, max_, hosts, suspend):
+    """GetWorkerGroupDesiredReplicas (utils/util.go:386-404) in Go's int32 arithmetic, written out independently."""
+    mn = 0 if min_ is None else min_
+    mx = 2 ** 31 - 1 if max_ is None else max_
+    if suspend:
+        return 0
+    if replicas is None or replicas < mn:
+        w = mn
+    elif replicas > mx:
+        w = mx
+    else:
+        w = replicas
+    return _i32(w * hosts)
+
+
+def test_desired_replicas_property(oracle_mod):
+    """Property test over the whole int32 domain (nil / extreme / wrapping values included) against the independent model."""
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+    i32 = st.one_of(st.none(), st.integers(-2 ** 31, 2 ** 31 - 1), st.sampled_from([0, 1, -1, 2 ** 31 - 1, -2 ** 31, 2 ** 30, 65536]))
+    hosts = st.one_of(st.integers(-2 ** 31, 2 ** 31 - 1), st.sampled_from([0, 1, 2, 4, -1, 65536, 2 ** 31 - 1]))
+
+    @hyp.settings(max_examples=3000, deadline=None)
+    @hyp.given(i32, i32, i32, hosts, st.booleans())
+    def check(replicas, mn, mx, h, suspend):
+        assert oracle_mod.desired_replicas(replicas, mn, mx, h, suspend) == _desired_replicas_model(replicas, mn, mx, h, suspend)
+
+    check()
+
+
+def test_sha1_random_lengths_against_hashlib(oracle_mod):
+    rng = np.random.default_rng(7)
+    for n in list(range(0, 200)) + [int(x) for x in rng.integers(200, 20000, 40)]:
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert oracle_mod.sha1(m) == hashlib.sha1(m).digest()
+        assert oracle_mod.hash32(m) == base64.b32hexencode(hashlib.sha1(m).digest()).decode()
