@@ -135,26 +135,41 @@ def build_workload(name: str, rank: int, world: int):
     return snap, flags, params
 
 
-def cpu_arm(snap, flags, budget_s: float, threads: int, list_mode=None):
-    """Time the CPU restatement (oracle port, namespace-scan Lists like controller-runtime's CacheReader) on a bounded sample."""
-    from oracle import oracle
-    mode = oracle.NS_SCAN if list_mode is None else list_mode
-    nc = snap.dims["clusters"]
-    probe = min(nc, max(threads * 4, 32))
-    t0 = time.perf_counter()
-    oracle.run_range(snap, flags, 0, probe, list_mode=mode, threads=threads)
-    dt = time.perf_counter() - t0
-    rate = probe / max(dt, 1e-9)
-    sample = int(min(nc, max(probe, rate * budget_s)))
-    # a bounded sample of the workload; when the whole snapshot takes less than the budget it is repeated instead
-    done, t0 = 0, time.perf_counter()
-    while True:
-        oracle.run_range(snap, flags, 0, sample, list_mode=mode, threads=threads)
-        done += sample
+class CpuArm:
+    """The CPU restatement (oracle port) as the reference arm: built here with -O3 -march=native (SHA-NI SHA-1 where the host
+    has it, like Go's crypto/sha1), ONE shared index per snapshot (controller-runtime's informer cache keeps its namespace
+    index between reconciles — building it is reported separately, never inside a timed reconcile), one preallocated result set,
+    worker threads looping over a bounded sample of clusters."""
+
+    def __init__(self, snap):
+        from oracle import oracle
+        self.oracle = oracle
+        self.L = oracle.load(oracle.build_native())
+        t0 = time.perf_counter()
+        self.cx = oracle.Context(snap, self.L)
+        self.ctx_build_ms = 1e3 * (time.perf_counter() - t0)
+        self.nc = snap.dims["clusters"]
+        self.sha = "SHA-NI" if self.L.kr_oracle_sha1_impl() else "portable C"
+
+    def run(self, flags, budget_s: float, threads: int, list_mode=None):
+        """-> (reconciles/s, reconciles done, seconds).  A bounded sample: `sample` clusters x `reps` repetitions inside the
+        worker threads (thread start-up amortised), sized from a probe so that the leg takes about budget_s."""
+        o = self.oracle
+        mode = o.NS_SCAN if list_mode is None else list_mode
+        probe = min(self.nc, max(threads * 4, 32))
+        self.cx.run_range(flags, 0, probe, list_mode=mode, threads=threads)  # first touch
+        t0 = time.perf_counter()
+        self.cx.run_range(flags, 0, probe, list_mode=mode, threads=threads)
+        rate = probe / max(time.perf_counter() - t0, 1e-9)
+        sample = int(min(self.nc, max(probe, rate * budget_s)))
+        reps = max(1, int(rate * budget_s / sample))
+        t0 = time.perf_counter()
+        self.cx.run_range(flags, 0, sample, list_mode=mode, threads=threads, reps=reps)
         dt = time.perf_counter() - t0
-        if sample < nc or dt >= budget_s:
-            break
-    return done / dt, done, dt
+        return sample * reps / dt, sample * reps, dt
+
+    def close(self):
+        self.cx.close()
 
 
 def run_reference(args, rank: int, world: int):
@@ -162,12 +177,13 @@ def run_reference(args, rank: int, world: int):
         return
     snap, flags, params = build_workload(args.workload, 0, 1)
     threads = os.cpu_count() or 1
-    per_step = max(0.5, min(10.0, 120.0 / max(args.steps + args.warmup, 1)))
+    arm = CpuArm(snap)
+    per_step = max(0.25, min(5.0, 100.0 / max(args.steps + args.warmup, 1)))
     for _ in range(args.warmup):
-        cpu_arm(snap, flags, per_step / 4, threads)
+        arm.run(flags, per_step / 4, threads)
     tot_c, tot_t, sample = 0, 0.0, 0
     for _ in range(args.steps):
-        _, sample, dt = cpu_arm(snap, flags, per_step, threads)
+        _, sample, dt = arm.run(flags, per_step, threads)
         tot_c += sample; tot_t += dt
     v = tot_c / tot_t
     line = {
@@ -175,12 +191,14 @@ def run_reference(args, rank: int, world: int):
         "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {params.n_clusters} RayClusters x {params.pods_per_cluster} pods, {params.groups} worker group(s), 100 clusters/namespace",
-                   "note": "CPU restatement (C), NOT the Go controller: no Go toolchain in this image; namespace-scan cached List per selector as in controller-runtime"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "note": "CPU restatement (C, -O3 -march=native, " + arm.sha + " SHA-1), NOT the Go controller: no Go toolchain in this image; namespace-scan cached List per "
+                           "selector as in controller-runtime; the cache's namespace index is built once outside the timed region (" + f"{arm.ctx_build_ms:.1f} ms)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "index_build_ms_not_timed": arm.ctx_build_ms,
                          "sample": f"{sample} reconciles per step over the {snap.dims['clusters']}-cluster snapshot (each = G+4 namespace-scan Lists + SHA-1 of its spec JSON)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    arm.close()
     print(json.dumps(line), flush=True)
 
 
@@ -440,17 +458,20 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, sample, dt = cpu_arm(snap, flags, args.cpu_seconds, threads)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample} reconciles over the {nc_local}-cluster snapshot in {dt:.1f} s (CPU restatement in C, namespace-scan Lists; not the Go controller)"}
+            arm = CpuArm(snap)
+            v, sample, dt = arm.run(flags, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "index_build_ms_not_timed": arm.ctx_build_ms,
+                                    "sample": f"{sample} reconciles over the {nc_local}-cluster snapshot in {dt:.1f} s (CPU restatement in C, -O3 -march=native, {arm.sha} SHA-1, "
+                                              "namespace-scan Lists against one prebuilt cache index; not the Go controller)"}
             # the same port on one thread (the reference's default ReconcileConcurrency = 1, apis/config/v1alpha1/defaults.go:11)
             # and with pods pre-bucketed by cluster, so the GPU/CPU ratio is not credited to removing the namespace scan alone
             from oracle import oracle as _o
-            v1, s1, d1 = cpu_arm(snap, flags, args.cpu_seconds / 4, 1)
-            vi, si, di = cpu_arm(snap, flags, args.cpu_seconds / 4, threads, list_mode=_o.INDEXED)
+            v1, s1, d1 = arm.run(flags, args.cpu_seconds / 4, 1)
+            vi, si, di = arm.run(flags, args.cpu_seconds / 4, threads, list_mode=_o.INDEXED)
             line["cpu_baseline_variants"] = {
                 "one_thread_namespace_scan": {"value": v1, "unit": UNIT, "cores": 1, "sample": f"{s1} reconciles in {d1:.1f} s"},
                 "all_threads_indexed_lists": {"value": vi, "unit": UNIT, "cores": threads, "sample": f"{si} reconciles in {di:.1f} s (pods pre-bucketed by cluster: no namespace scan)"}}
+            arm.close()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:

@@ -38,10 +38,17 @@ class Env:
     enable_random_pod_delete: bool = False   # ENABLE_RANDOM_POD_DELETE == "true"
 
 
+class ApiError(Exception):
+    """A Create/Delete call that failed at the API server (anything but NotFound)."""
+
+
 class FakeClient:
-    """Minimal object store: RayClusters by (ns,name), Pods by (ns,name)."""
+    """Minimal object store: RayClusters by (ns,name), Pods by (ns,name).  `fail_delete` / `fail_create` inject API-server
+    failures (names / node types) the way the reference's tests do with interceptor funcs."""
 
     def __init__(self, clusters=(), pods=(), jobs=()):
+        self.fail_delete: set[tuple[str, str]] = set()   # (ns, name) whose Delete returns an error
+        self.fail_create: set[str] = set()               # node types ("head" / "worker") whose Create returns an error
         self.clusters = {(c.get("namespace", "default"), c["name"]): copy.deepcopy(c) for c in clusters}
         self.pods = {(p.get("namespace", "default"), p["name"]): copy.deepcopy(p) for p in pods}
         self.jobs = [copy.deepcopy(j) for j in jobs]
@@ -52,9 +59,14 @@ class FakeClient:
         return [self.pods[k] for k in sorted(self.pods)]  # fake client Lists come back name-ordered
 
     def delete_pod(self, ns: str, name: str) -> bool:
+        """-> True if deleted, False if NotFound; raises ApiError on an injected failure."""
+        if (ns, name) in self.fail_delete:
+            raise ApiError(f"delete {ns}/{name}: injected failure")
         return self.pods.pop((ns, name), None) is not None
 
     def create_pod(self, pod: dict):
+        if (pod.get("labels") or {}).get(snapmod.RAY_NODE_TYPE_LABEL) in self.fail_create:
+            raise ApiError(f"create {pod.get('namespace', 'default')}/{pod['name']}: injected failure")
         self.pods[(pod.get("namespace", "default"), pod["name"])] = pod
 
     def gen_suffix(self) -> str:
@@ -129,7 +141,17 @@ class RayClusterReconciler:
         ci = self._cluster_index(pr, ns, name)
         return self._apply_decisions(pr, ci)
 
-    def _apply_decisions(self, pr: PassResult, ci: int) -> str | None:
+    def _apply_decisions(self, pr: PassResult, ci: int):
+        """-> None, the plain error string reconcilePods returns, or ("Failed<Verb><Kind>Pod", message) when an API call
+        failed: the reference joins one of the five ErrFailed* markers (utils/constant.go:322-334) onto that error, and only
+        those set the ReplicaFailure condition (raycluster_controller.go:1563-1571)."""
+        self._stage = "FailedDeleteAllPods"
+        try:
+            return self._apply_decisions_inner(pr, ci)
+        except ApiError as ex:
+            return (self._stage, str(ex))
+
+    def _apply_decisions_inner(self, pr: PassResult, ci: int) -> str | None:
         cl = self.client
         res, snap, meta = pr.res, pr.snap, pr.meta
         cr = res.clusters[ci]
@@ -162,6 +184,7 @@ class RayClusterReconciler:
                 hp.setdefault("annotations", {})[snapmod.RECREATE_HASH_ANNOT] = bytes(res.hash[ci]).decode()
                 hp["annotations"][snapmod.KUBERAY_VERSION_ANNOT] = snapmod.KUBERAY_VERSION
         ha = int(cr["head_action"])
+        self._stage = "FailedDeleteHeadPod"         # :705
         if ha == abi.HEAD_DELETE:                   # :700-711
             pi = next(pi for pi, act in listed if act == abi.ACT_DELETE_HEAD)
             pod = pr.pods[pi]
@@ -174,6 +197,7 @@ class RayClusterReconciler:
         if ha == abi.HEAD_MULTIPLE:                 # :738-747
             names = [p["name"] for p in cl.pods_of(ns, cname, **{snapmod.RAY_NODE_TYPE_LABEL: "head"})]  # the head List of :674
             return f"{int(cr['err_arg'])} head pods found {names}. Please delete extra head pods"
+        self._stage = "FailedCreateHeadPod"         # :736
         if ha == abi.HEAD_CREATE:                   # :735, createHeadPod :1307-1337
             pod = self._build_pod(cluster, "head", "headgroup", f"{cname}-head-{cl.gen_suffix()}")
             pod.setdefault("annotations", {})[snapmod.RECREATE_HASH_ANNOT] = bytes(res.hash[ci]).decode()
@@ -189,6 +213,7 @@ class RayClusterReconciler:
             if not fl & abi.GR_PROCESSED:
                 break
             gname = grp["groupName"]
+            self._stage = "FailedDeleteWorkerPod"   # :770,800,826,922,949
             in_group = [(pi, act) for pi, act in listed if (pr.pods[pi].get("labels") or {}).get(snapmod.RAY_NODE_GROUP_LABEL) == gname]
             if fl & abi.GR_EXPECT_PENDING:
                 continue
@@ -215,11 +240,15 @@ class RayClusterReconciler:
                 w0 = int(snap.g_wtd_off[g0 + gi])
                 names = grp.get("workersToDelete") or (grp.get("scaleStrategy") or {}).get("workersToDelete") or []
                 for k, nm in enumerate(names):
-                    pi = int(res.wtd_pod_idx[w0 + k])
-                    if pi >= 0 and cl.delete_pod(*meta.pod_keys[pi]):
+                    # Delete(ns, name) goes to the API server for EVERY name (:817-822): a Pod the informer snapshot does not
+                    # hold yet (wtd_pod_idx == -1: not in the cache, or owned by another shard) is still deleted there;
+                    # wtd_pod_idx only told the engine which listed pods leave runningPods (:837-842)
+                    assert int(res.wtd_pod_idx[w0 + k]) < 0 or meta.pod_keys[int(res.wtd_pod_idx[w0 + k])] == (ns, nm)
+                    if cl.delete_pod(ns, nm):
                         ev(("Normal", EV_DELETED_WORKER_POD, f"Deleted pod {ns}/{nm}"))
                 # (:835 clears worker.ScaleStrategy.WorkersToDelete on the loop's COPY of the group spec only — the CR keeps
                 #  the names until the autoscaler removes them; later passes see NotFound and move on)
+            self._stage = "FailedCreateWorkerPod"   # :879,887
             for k in range(int(gr["n_create"])):    # :865-890
                 idx = int(res.create_idx[int(gr["create_off"]) + k])
                 pod = self._build_pod(cluster, "worker", gname, f"{cname}-{gname}-worker-{cl.gen_suffix()}")
@@ -227,6 +256,7 @@ class RayClusterReconciler:
                     pod["labels"][snapmod.REPLICA_INDEX_LABEL] = str(idx)
                 cl.create_pod(pod)
                 ev(("Normal", EV_CREATED_WORKER_POD, f"Created worker Pod {ns}/{pod['name']}"))
+            self._stage = "FailedDeleteWorkerPod"   # :922
             for pi, act in in_group:                # :916-928
                 if act == abi.ACT_DELETE_RANDOM:
                     cl.delete_pod(*meta.pod_keys[pi])
@@ -260,6 +290,7 @@ class RayClusterReconciler:
             if ek == abi.ERR_MH_NOT_MULTIPLE:
                 return f"desired worker pods ({int(gr['expected'])}) is not a multiple of NumOfHosts ({grp.get('numOfHosts', 1)}) for group {gname}"
         hosts = int(grp.get("numOfHosts", 1))
+        self._stage = "FailedCreateWorkerPod"       # :1091
         for k in range(int(gr["n_create"])):        # one entry per replica group (:1082-1094)
             idx = int(res.create_idx[int(gr["create_off"]) + k])
             rname = f"{gname}-{cl.gen_suffix()}"
@@ -376,11 +407,18 @@ class RayClusterReconciler:
 
     # ------------------------------------------------------------------ the full Reconcile body for one key (:296-355)
     def reconcile(self, ns: str, name: str, now: str = "now") -> tuple[float, str | None]:
-        """-> (requeue seconds, error).  One pass feeds both the decisions and the status, as the engine produces them."""
+        """-> (requeue seconds, error).  One pass feeds both the decisions and the status, as the engine produces them —
+        unless a side-effect call failed at the API server: the record's status was computed for reconcileErr == nil, so it
+        is discarded and the status is re-evaluated (status-only pass, c_ext_err_kind = the ErrFailed* kind), which is what
+        calculateStatus(ctx, instance, reconcileErr) sees in the reference (:308-316, 1563-1577, 1599)."""
         pr = self._pass()
         ci = self._cluster_index(pr, ns, name)
         err = self._apply_decisions(pr, ci)
-        new, cerr = self.status_from_record(pr, ci)
+        if isinstance(err, tuple):
+            new, cerr = self.calculate_status(ns, name, err)
+            err = f"{err[0]}: {err[1]}"
+        else:
+            new, cerr = self.status_from_record(pr, ci)
         inconsistent = False
         if cerr is None:
             inconsistent = self.update_status(ns, name, new, now)

@@ -20,7 +20,7 @@
 
 static inline uint32_t rol32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
 
-static void sha1_block(uint32_t h[5], const uint8_t *p) {
+static void __attribute__((unused)) sha1_block(uint32_t h[5], const uint8_t *p) {
   uint32_t w[80];
   for (int i = 0; i < 16; i++)
     w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
@@ -38,10 +38,77 @@ static void sha1_block(uint32_t h[5], const uint8_t *p) {
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
 }
 
+#if defined(__SHA__) && defined(__SSE4_1__)
+/* SHA-NI block function (only in the -march=native build bench.py makes for the CPU arm on a host that has the extension):
+ * Go's crypto/sha1 uses the same instructions on amd64, so the timed CPU baseline is not handicapped by a portable-C SHA-1.
+ * Same FIPS 180-4 compression function as sha1_block; tests/test_oracle_units.py checks both against hashlib. */
+#include <immintrin.h>
+static void sha1_blocks_ni(uint32_t h[5], const uint8_t *p, uint64_t nblk) {
+  const __m128i flip = _mm_set_epi64x(0x0001020304050607ULL, 0x08090a0b0c0d0e0fULL);
+  __m128i abcd = _mm_shuffle_epi32(_mm_loadu_si128((const __m128i *)h), 0x1B);
+  __m128i e0 = _mm_set_epi32((int)h[4], 0, 0, 0), e1;
+  while (nblk--) {
+    const __m128i abcd_save = abcd, e_save = e0;
+    __m128i m0 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 0)), flip);
+    __m128i m1 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 16)), flip);
+    __m128i m2 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 32)), flip);
+    __m128i m3 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 48)), flip);
+    /* rounds 0-3 */
+    e0 = _mm_add_epi32(e0, m0); e1 = abcd; abcd = _mm_sha1rnds4_epu32(abcd, e0, 0);
+    /* 4-7 */
+    e1 = _mm_sha1nexte_epu32(e1, m1); e0 = abcd; abcd = _mm_sha1rnds4_epu32(abcd, e1, 0); m0 = _mm_sha1msg1_epu32(m0, m1);
+    /* 8-11 */
+    e0 = _mm_sha1nexte_epu32(e0, m2); e1 = abcd; abcd = _mm_sha1rnds4_epu32(abcd, e0, 0); m1 = _mm_sha1msg1_epu32(m1, m2); m0 = _mm_xor_si128(m0, m2);
+    /* 12-15 */
+    e1 = _mm_sha1nexte_epu32(e1, m3); e0 = abcd; m0 = _mm_sha1msg2_epu32(m0, m3); abcd = _mm_sha1rnds4_epu32(abcd, e1, 0); m2 = _mm_sha1msg1_epu32(m2, m3); m1 = _mm_xor_si128(m1, m3);
+    /* 16-19 */
+    e0 = _mm_sha1nexte_epu32(e0, m0); e1 = abcd; m1 = _mm_sha1msg2_epu32(m1, m0); abcd = _mm_sha1rnds4_epu32(abcd, e0, 0); m3 = _mm_sha1msg1_epu32(m3, m0); m2 = _mm_xor_si128(m2, m0);
+    /* 20-23 */
+    e1 = _mm_sha1nexte_epu32(e1, m1); e0 = abcd; m2 = _mm_sha1msg2_epu32(m2, m1); abcd = _mm_sha1rnds4_epu32(abcd, e1, 1); m0 = _mm_sha1msg1_epu32(m0, m1); m3 = _mm_xor_si128(m3, m1);
+    /* 24-27 */
+    e0 = _mm_sha1nexte_epu32(e0, m2); e1 = abcd; m3 = _mm_sha1msg2_epu32(m3, m2); abcd = _mm_sha1rnds4_epu32(abcd, e0, 1); m1 = _mm_sha1msg1_epu32(m1, m2); m0 = _mm_xor_si128(m0, m2);
+    /* 28-31 */
+    e1 = _mm_sha1nexte_epu32(e1, m3); e0 = abcd; m0 = _mm_sha1msg2_epu32(m0, m3); abcd = _mm_sha1rnds4_epu32(abcd, e1, 1); m2 = _mm_sha1msg1_epu32(m2, m3); m1 = _mm_xor_si128(m1, m3);
+    /* 32-35 */
+    e0 = _mm_sha1nexte_epu32(e0, m0); e1 = abcd; m1 = _mm_sha1msg2_epu32(m1, m0); abcd = _mm_sha1rnds4_epu32(abcd, e0, 1); m3 = _mm_sha1msg1_epu32(m3, m0); m2 = _mm_xor_si128(m2, m0);
+    /* 36-39 */
+    e1 = _mm_sha1nexte_epu32(e1, m1); e0 = abcd; m2 = _mm_sha1msg2_epu32(m2, m1); abcd = _mm_sha1rnds4_epu32(abcd, e1, 1); m0 = _mm_sha1msg1_epu32(m0, m1); m3 = _mm_xor_si128(m3, m1);
+    /* 40-43 */
+    e0 = _mm_sha1nexte_epu32(e0, m2); e1 = abcd; m3 = _mm_sha1msg2_epu32(m3, m2); abcd = _mm_sha1rnds4_epu32(abcd, e0, 2); m1 = _mm_sha1msg1_epu32(m1, m2); m0 = _mm_xor_si128(m0, m2);
+    /* 44-47 */
+    e1 = _mm_sha1nexte_epu32(e1, m3); e0 = abcd; m0 = _mm_sha1msg2_epu32(m0, m3); abcd = _mm_sha1rnds4_epu32(abcd, e1, 2); m2 = _mm_sha1msg1_epu32(m2, m3); m1 = _mm_xor_si128(m1, m3);
+    /* 48-51 */
+    e0 = _mm_sha1nexte_epu32(e0, m0); e1 = abcd; m1 = _mm_sha1msg2_epu32(m1, m0); abcd = _mm_sha1rnds4_epu32(abcd, e0, 2); m3 = _mm_sha1msg1_epu32(m3, m0); m2 = _mm_xor_si128(m2, m0);
+    /* 52-55 */
+    e1 = _mm_sha1nexte_epu32(e1, m1); e0 = abcd; m2 = _mm_sha1msg2_epu32(m2, m1); abcd = _mm_sha1rnds4_epu32(abcd, e1, 2); m0 = _mm_sha1msg1_epu32(m0, m1); m3 = _mm_xor_si128(m3, m1);
+    /* 56-59 */
+    e0 = _mm_sha1nexte_epu32(e0, m2); e1 = abcd; m3 = _mm_sha1msg2_epu32(m3, m2); abcd = _mm_sha1rnds4_epu32(abcd, e0, 2); m1 = _mm_sha1msg1_epu32(m1, m2); m0 = _mm_xor_si128(m0, m2);
+    /* 60-63 */
+    e1 = _mm_sha1nexte_epu32(e1, m3); e0 = abcd; m0 = _mm_sha1msg2_epu32(m0, m3); abcd = _mm_sha1rnds4_epu32(abcd, e1, 3); m2 = _mm_sha1msg1_epu32(m2, m3); m1 = _mm_xor_si128(m1, m3);
+    /* 64-67 */
+    e0 = _mm_sha1nexte_epu32(e0, m0); e1 = abcd; m1 = _mm_sha1msg2_epu32(m1, m0); abcd = _mm_sha1rnds4_epu32(abcd, e0, 3); m3 = _mm_sha1msg1_epu32(m3, m0); m2 = _mm_xor_si128(m2, m0);
+    /* 68-71 */
+    e1 = _mm_sha1nexte_epu32(e1, m1); e0 = abcd; m2 = _mm_sha1msg2_epu32(m2, m1); abcd = _mm_sha1rnds4_epu32(abcd, e1, 3); m3 = _mm_xor_si128(m3, m1);
+    /* 72-75 */
+    e0 = _mm_sha1nexte_epu32(e0, m2); e1 = abcd; m3 = _mm_sha1msg2_epu32(m3, m2); abcd = _mm_sha1rnds4_epu32(abcd, e0, 3);
+    /* 76-79 */
+    e1 = _mm_sha1nexte_epu32(e1, m3); e0 = abcd; abcd = _mm_sha1rnds4_epu32(abcd, e1, 3);
+    e0 = _mm_sha1nexte_epu32(e0, e_save);
+    abcd = _mm_add_epi32(abcd, abcd_save);
+    p += 64;
+  }
+  _mm_storeu_si128((__m128i *)h, _mm_shuffle_epi32(abcd, 0x1B));
+  h[4] = (uint32_t)_mm_extract_epi32(e0, 3);
+}
+#define KR_SHA1_BLOCKS(h, p, n) sha1_blocks_ni(h, p, n)
+#else
+#define KR_SHA1_BLOCKS(h, p, n) do { for (uint64_t i_ = 0; i_ < (n); i_++) sha1_block(h, (p) + 64 * i_); } while (0)
+#endif
+
 void kr_oracle_sha1(const uint8_t *msg, uint64_t len, uint8_t digest[20]) {
   uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
   uint64_t full = len / 64;
-  for (uint64_t i = 0; i < full; i++) sha1_block(h, msg + 64 * i);
+  KR_SHA1_BLOCKS(h, msg, full);
   uint8_t tail[128];
   uint64_t rem = len - 64 * full;
   memset(tail, 0, sizeof tail);
@@ -50,11 +117,19 @@ void kr_oracle_sha1(const uint8_t *msg, uint64_t len, uint8_t digest[20]) {
   int nb = (rem >= 56) ? 2 : 1;
   uint64_t bits = len * 8;
   for (int i = 0; i < 8; i++) tail[64 * nb - 1 - i] = (uint8_t)(bits >> (8 * i));
-  for (int i = 0; i < nb; i++) sha1_block(h, tail + 64 * i);
+  KR_SHA1_BLOCKS(h, tail, (uint64_t)nb);
   for (int i = 0; i < 5; i++) {
     digest[4 * i] = (uint8_t)(h[i] >> 24); digest[4 * i + 1] = (uint8_t)(h[i] >> 16);
     digest[4 * i + 2] = (uint8_t)(h[i] >> 8); digest[4 * i + 3] = (uint8_t)h[i];
   }
+}
+
+int kr_oracle_sha1_impl(void) {
+#if defined(__SHA__) && defined(__SSE4_1__)
+  return 1; /* SHA-NI */
+#else
+  return 0; /* portable C */
+#endif
 }
 
 void kr_oracle_hash32(const uint8_t *msg, uint64_t len, char out32[32]) {
@@ -145,6 +220,7 @@ typedef struct {
   uint32_t *ns_start;      /* [Nns+1] */
   uint32_t *ns_pods;       /* [Np] pods bucketed by namespace, list order */
   int32_t  *pod_head_aux;  /* [Np] head-aux row or -1 */
+  int32_t  *wtd;           /* [Nw] pod a workersToDelete name resolves to (same namespace + same name), -1 = NotFound */
   uint8_t  *act;           /* [Np] action by original pod index */
 } octx;
 
@@ -463,7 +539,7 @@ static void reconcile_pods(const octx *x, oscratch *t, uint32_t c, const char *h
     /* :814-835 WorkersToDelete: r.Delete(ns, name); success => deletedWorkers[name] */
     gr->flags |= KR_GR_WTD_EXECUTED;
     for (uint32_t w = 0; w < s->g_wtd_cnt[g]; w++) {
-      int32_t j = x->out->wtd_pod_idx[s->g_wtd_off[g] + w]; /* resolved up front: same namespace + same name */
+      int32_t j = x->wtd[s->g_wtd_off[g] + w]; /* resolved up front: same namespace + same name */
       if (j < 0) continue;                                    /* NotFound: tolerated (:823-828) */
       uint32_t name = s->p_name_id[j];
       for (uint32_t i = 0; i < L->n; i++)
@@ -674,6 +750,7 @@ static void calculate_status(const octx *x, oscratch *t, uint32_t c, kr_cluster_
 typedef struct {
   octx *x;
   uint32_t c0, c1;
+  int reps;
   ivec creates;
   int rc;
 } worker_arg;
@@ -685,6 +762,8 @@ static void reconcile_cluster(octx *x, oscratch *t, uint32_t c, ivec *creates) {
   cr->head_pod_idx = -1;
   cr->stop_after_group = -1;
   for (uint32_t gi = 0; gi < s->c_group_cnt[c]; gi++) memset(&x->out->groups[s->c_group_off[c] + gi], 0, sizeof(kr_group_result));
+  /* a context is reused across runs: this cluster's pods start without an action */
+  for (uint32_t i = x->cl_start[c]; i < x->cl_start[c + 1]; i++) x->act[x->cl_pods[i]] = KR_ACT_KEEP;
   char *h = x->out->hash + 32 * (size_t)c;
   /* :623 — computed every reconcile */
   if (x->f->skip_hash) memset(h, 0, 32);
@@ -703,7 +782,10 @@ static void reconcile_cluster(octx *x, oscratch *t, uint32_t c, ivec *creates) {
 static void *worker_main(void *p) {
   worker_arg *a = (worker_arg *)p;
   oscratch t; memset(&t, 0, sizeof t);
-  for (uint32_t c = a->c0; c < a->c1; c++) reconcile_cluster(a->x, &t, c, &a->creates);
+  for (int r = 0; r < a->reps; r++) {
+    a->creates.n = 0;
+    for (uint32_t c = a->c0; c < a->c1; c++) reconcile_cluster(a->x, &t, c, &a->creates);
+  }
   scratch_free(&t);
   return NULL;
 }
@@ -746,11 +828,12 @@ static int build_context(octx *x) {
     if (p < Np && x->pod_head_aux[p] < 0) x->pod_head_aux[p] = (int32_t)h;
   }
   /* resolve WorkersToDelete names: Delete(ns of the cluster, name) (:818-822) */
+  x->wtd = (int32_t *)malloc(((size_t)n->n_wtd + 1) * 4);
   for (uint32_t g = 0; g < n->n_groups; g++) {
     uint32_t c = s->g_cluster_idx[g];
     for (uint32_t w = 0; w < s->g_wtd_cnt[g]; w++) {
       uint32_t e = s->g_wtd_off[g] + w, v;
-      x->out->wtd_pod_idx[e] = kmap_get(&x->podname_map, key2(s->c_ns_id[c], s->w_name_id[e]), &v) ? (int32_t)v : -1;
+      x->wtd[e] = kmap_get(&x->podname_map, key2(s->c_ns_id[c], s->w_name_id[e]), &v) ? (int32_t)v : -1;
     }
   }
   return 0;
@@ -758,23 +841,46 @@ static int build_context(octx *x) {
 
 static void free_context(octx *x) {
   kmap_free(&x->cluster_map); kmap_free(&x->podname_map); kmap_free(&x->ns_map);
-  free(x->pod_cluster); free(x->cl_start); free(x->cl_pods); free(x->ns_start); free(x->ns_pods); free(x->pod_head_aux); free(x->act);
+  free(x->pod_cluster); free(x->cl_start); free(x->cl_pods); free(x->ns_start); free(x->ns_pods); free(x->pod_head_aux); free(x->wtd); free(x->act);
 }
 
-static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags *f, kr_oracle_out *out,
-                    int list_mode, int threads, uint32_t c0, uint32_t c1, int full) {
-  octx x; memset(&x, 0, sizeof x);
-  x.s = s; x.n = n; x.f = f; x.out = out; x.list_mode = list_mode;
+/* The shared index of one snapshot: what controller-runtime's informer cache holds between reconciles (its namespace index is
+ * maintained incrementally from watch events, never rebuilt per List).  Built once per snapshot, reused by every run. */
+struct kr_oracle_ctx { octx x; kr_sizes n; };
+
+int kr_oracle_ctx_create(const kr_snapshot_bufs *s, const kr_sizes *n, kr_oracle_ctx **out) {
+  if (!s || !n || !out) return KR_E_INVALID;
+  kr_oracle_ctx *cx = (kr_oracle_ctx *)calloc(1, sizeof *cx);
+  if (!cx) return KR_E_CAPACITY;
+  cx->n = *n;
+  cx->x.s = s; cx->x.n = &cx->n;
+  int rc = build_context(&cx->x);
+  if (rc) { free_context(&cx->x); free(cx); return rc; }
+  *out = cx;
+  return 0;
+}
+
+void kr_oracle_ctx_destroy(kr_oracle_ctx *cx) {
+  if (!cx) return;
+  free_context(&cx->x);
+  free(cx);
+}
+
+static int ctx_run(kr_oracle_ctx *cx, const kr_flags *f, kr_oracle_out *out, int list_mode, int threads, uint32_t c0, uint32_t c1, int reps, int full) {
+  octx *x = &cx->x;
+  const kr_snapshot_bufs *s = x->s; const kr_sizes *n = x->n;
+  x->f = f; x->out = out; x->list_mode = list_mode;
   if (c1 > n->n_clusters) c1 = n->n_clusters;
-  int rc = build_context(&x);
-  if (rc) { free_context(&x); return rc; }
+  if (reps < 1) reps = 1;
+  int rc = 0;
+  if (n->n_wtd) memcpy(out->wtd_pod_idx, x->wtd, (size_t)n->n_wtd * 4);
   if (threads < 1) threads = 1;
   uint32_t span = c1 > c0 ? c1 - c0 : 0;
   if ((uint32_t)threads > span) threads = span ? (int)span : 1;
   worker_arg *args = (worker_arg *)calloc((size_t)threads, sizeof(worker_arg));
   pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
   for (int t = 0; t < threads; t++) {
-    args[t].x = &x;
+    args[t].x = x; args[t].reps = reps;
     args[t].c0 = c0 + (uint32_t)(((uint64_t)span * t) / threads);
     args[t].c1 = c0 + (uint32_t)(((uint64_t)span * (t + 1)) / threads);
     if (threads == 1) worker_main(&args[t]);
@@ -788,7 +894,7 @@ static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags
       kr_job_result *jr = &out->jobs[j];
       memset(jr, 0, sizeof *jr);
       uint32_t c;
-      if (s->j_cluster_name_id[j] == 0 || !kmap_get(&x.cluster_map, key2(s->j_ns_id[j], s->j_cluster_name_id[j]), &c)) { jr->cluster_idx = -1; continue; }
+      if (s->j_cluster_name_id[j] == 0 || !kmap_get(&x->cluster_map, key2(s->j_ns_id[j], s->j_cluster_name_id[j]), &c)) { jr->cluster_idx = -1; continue; }
       jr->cluster_idx = (int32_t)c;
       jr->cluster_state = s->c_old_state[c];
       jr->not_ready = s->c_old_state[c] != KR_STATE_READY;
@@ -799,8 +905,7 @@ static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags
     for (int t = 0; t < threads && rc == 0; t++) {
       ivec *cv = &args[t].creates;
       for (uint32_t i = 0; i < cv->n;) {
-        uint32_t g = (uint32_t)cv->v[i], cnt = (uint32_t)cv->v[i + 1];
-        (void)g;
+        uint32_t cnt = (uint32_t)cv->v[i + 1];
         if ((uint64_t)total + cnt > out->create_cap) { rc = KR_E_CAPACITY; break; }
         memcpy(out->create_idx + total, cv->v + i + 2, cnt * sizeof(int32_t));
         total += cnt; i += 2 + cnt;
@@ -813,38 +918,58 @@ static int run_impl(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags
     /* pods bucketed by cluster, list order; orphans last */
     uint32_t Nc = n->n_clusters, n_actions = 0, n_tomb = 0;
     for (uint32_t i = 0; i < n->n_pods; i++) {
-      uint32_t p = x.cl_pods[i];
+      uint32_t p = x->cl_pods[i];
       out->sorted_pod_idx[i] = p;
-      uint8_t a = x.pod_cluster[p] == Nc ? ((s->p_packed[p] & KR_PP_TOMBSTONE) ? KR_ACT_TOMBSTONE : KR_ACT_ORPHAN) : x.act[p];
+      uint8_t a = x->pod_cluster[p] == Nc ? ((s->p_packed[p] & KR_PP_TOMBSTONE) ? KR_ACT_TOMBSTONE : KR_ACT_ORPHAN) : x->act[p];
       out->sorted_action[i] = a;
       if (a == KR_ACT_TOMBSTONE) n_tomb++;
       if (a != KR_ACT_KEEP && a != KR_ACT_ORPHAN && a != KR_ACT_TOMBSTONE) n_actions++;
     }
-    for (uint32_t c = 0; c < Nc; c++) out->clusters[c].pod_start = x.cl_start[c];
+    for (uint32_t c = 0; c < Nc; c++) out->clusters[c].pod_start = x->cl_start[c];
     /* compact action list, cluster-major, list order inside a cluster */
     uint32_t na = 0;
     for (uint32_t c = 0; c < Nc; c++) {
       out->act_start[c] = na;
-      for (uint32_t i = x.cl_start[c]; i < x.cl_start[c + 1]; i++) {
-        uint8_t a = x.act[x.cl_pods[i]];
-        if (a != KR_ACT_KEEP) { out->act_pod_idx[na] = x.cl_pods[i]; out->act_code[na] = a; na++; }
+      for (uint32_t i = x->cl_start[c]; i < x->cl_start[c + 1]; i++) {
+        uint8_t a = x->act[x->cl_pods[i]];
+        if (a != KR_ACT_KEEP) { out->act_pod_idx[na] = x->cl_pods[i]; out->act_code[na] = a; na++; }
       }
     }
     out->act_start[Nc] = na;
-    out->n_orphans = x.cl_start[Nc + 1] - x.cl_start[Nc] - n_tomb;  /* free rows sit in the orphans' segment but are not orphans */
+    out->n_orphans = x->cl_start[Nc + 1] - x->cl_start[Nc] - n_tomb;  /* free rows sit in the orphans' segment but are not orphans */
     out->n_actions = n_actions;
   }
   for (int t = 0; t < threads; t++) free(args[t].creates.v);
   free(args); free(tids);
-  free_context(&x);
   return rc;
 }
 
+int kr_oracle_ctx_run(kr_oracle_ctx *cx, const kr_flags *f, kr_oracle_out *out, int list_mode, int threads) {
+  if (!cx || !f || !out) return KR_E_INVALID;
+  return ctx_run(cx, f, out, list_mode, threads, 0, cx->n.n_clusters, 1, 1);
+}
+
+int kr_oracle_ctx_run_range(kr_oracle_ctx *cx, const kr_flags *f, kr_oracle_out *out, int list_mode, int threads,
+                            uint32_t c0, uint32_t c1, int reps) {
+  if (!cx || !f || !out) return KR_E_INVALID;
+  return ctx_run(cx, f, out, list_mode, threads, c0, c1, reps, 0);
+}
+
 int kr_oracle_run(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags *f, kr_oracle_out *out, int list_mode, int threads) {
-  return run_impl(s, n, f, out, list_mode, threads, 0, n->n_clusters, 1);
+  kr_oracle_ctx *cx = NULL;
+  int rc = kr_oracle_ctx_create(s, n, &cx);
+  if (rc) return rc;
+  rc = kr_oracle_ctx_run(cx, f, out, list_mode, threads);
+  kr_oracle_ctx_destroy(cx);
+  return rc;
 }
 
 int kr_oracle_run_range(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags *f, kr_oracle_out *out,
                         int list_mode, int threads, uint32_t c0, uint32_t c1) {
-  return run_impl(s, n, f, out, list_mode, threads, c0, c1, 0);
+  kr_oracle_ctx *cx = NULL;
+  int rc = kr_oracle_ctx_create(s, n, &cx);
+  if (rc) return rc;
+  rc = kr_oracle_ctx_run_range(cx, f, out, list_mode, threads, c0, c1, 1);
+  kr_oracle_ctx_destroy(cx);
+  return rc;
 }

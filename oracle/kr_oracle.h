@@ -65,6 +65,20 @@ int kr_oracle_run(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags *
 int kr_oracle_run_range(const kr_snapshot_bufs *s, const kr_sizes *n, const kr_flags *f,
                         kr_oracle_out *out, int list_mode, int threads, uint32_t c0, uint32_t c1);
 
+/* The shared index of one snapshot (what controller-runtime's informer cache keeps between reconciles: its namespace and
+ * label indexes are maintained incrementally from watch events, never rebuilt per reconcile).  Build it once per snapshot,
+ * then run any number of passes / ranges against it; `s` must stay valid and unchanged for the context's lifetime.
+ * `reps` repeats the range inside the worker threads (bench.py: amortises thread start-up over a bounded sample). */
+typedef struct kr_oracle_ctx kr_oracle_ctx;
+int  kr_oracle_ctx_create(const kr_snapshot_bufs *s, const kr_sizes *n, kr_oracle_ctx **out);
+int  kr_oracle_ctx_run(kr_oracle_ctx *cx, const kr_flags *f, kr_oracle_out *out, int list_mode, int threads);
+int  kr_oracle_ctx_run_range(kr_oracle_ctx *cx, const kr_flags *f, kr_oracle_out *out, int list_mode, int threads,
+                             uint32_t c0, uint32_t c1, int reps);
+void kr_oracle_ctx_destroy(kr_oracle_ctx *cx);
+
+/* 1 when this build's SHA-1 uses the x86 SHA extensions (the -march=native build of the CPU arm), 0 for portable C. */
+int kr_oracle_sha1_impl(void);
+
 /* base32hex(sha1(msg)) -> 32 chars (utils/util.go:628-640). */
 void kr_oracle_hash32(const uint8_t *msg, uint64_t len, char out32[32]);
 /* raw SHA-1 (FIPS 180-4) */

@@ -27,21 +27,86 @@ def build(force: bool = False) -> str:
     return so
 
 
+def build_native() -> str:
+    """The CPU arm's build: same source, -O3 -march=native for the host it runs on (bench.py only; never shipped)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libkroracle_native.so"])
+    return os.path.join(_HERE, "libkroracle_native.so")
+
+
+def _bind(L: C.CDLL) -> C.CDLL:
+    L.kr_oracle_run.argtypes = [C.POINTER(abi.kr_snapshot_bufs), C.POINTER(abi.kr_sizes), C.POINTER(abi.kr_flags),
+                                C.POINTER(abi.kr_oracle_out), C.c_int, C.c_int]
+    L.kr_oracle_run.restype = C.c_int
+    L.kr_oracle_run_range.argtypes = L.kr_oracle_run.argtypes + [C.c_uint32, C.c_uint32]
+    L.kr_oracle_run_range.restype = C.c_int
+    L.kr_oracle_ctx_create.argtypes = [C.POINTER(abi.kr_snapshot_bufs), C.POINTER(abi.kr_sizes), C.POINTER(C.c_void_p)]
+    L.kr_oracle_ctx_create.restype = C.c_int
+    L.kr_oracle_ctx_run.argtypes = [C.c_void_p, C.POINTER(abi.kr_flags), C.POINTER(abi.kr_oracle_out), C.c_int, C.c_int]
+    L.kr_oracle_ctx_run.restype = C.c_int
+    L.kr_oracle_ctx_run_range.argtypes = L.kr_oracle_ctx_run.argtypes + [C.c_uint32, C.c_uint32, C.c_int]
+    L.kr_oracle_ctx_run_range.restype = C.c_int
+    L.kr_oracle_ctx_destroy.argtypes = [C.c_void_p]
+    L.kr_oracle_ctx_destroy.restype = None
+    L.kr_oracle_sha1_impl.restype = C.c_int
+    L.kr_oracle_hash32.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.kr_oracle_sha1.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.kr_oracle_desired_replicas.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]
+    L.kr_oracle_desired_replicas.restype = C.c_int32
+    L.kr_oracle_should_delete.argtypes = [C.c_uint32]
+    L.kr_oracle_should_delete.restype = C.c_int
+    return L
+
+
+def load(path: str) -> C.CDLL:
+    """Load another build of the oracle (bench.py: the -march=native CPU arm)."""
+    return _bind(C.CDLL(path))
+
+
+class Context:
+    """One snapshot's shared index (kr_oracle_ctx): built once, reused by every run — as controller-runtime's informer cache
+    is between reconciles.  Keeps the snapshot's arrays and one preallocated result set alive."""
+
+    def __init__(self, snap, L: C.CDLL | None = None, create_cap: int = 1 << 20):
+        self.L = L or lib()
+        self.snap = snap
+        self.sizes = snap.sizes()
+        self.bufs = snap.bufs()
+        self.res = abi.Results(self.sizes, create_cap)
+        self.out = _out_struct(self.res)
+        self.h = C.c_void_p()
+        rc = self.L.kr_oracle_ctx_create(C.byref(self.bufs), C.byref(self.sizes), C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError(f"kr_oracle_ctx_create failed: {rc}")
+
+    def run_range(self, flags: abi.kr_flags, c0: int, c1: int, list_mode: int = NS_SCAN, threads: int = 1, reps: int = 1) -> abi.Results:
+        rc = self.L.kr_oracle_ctx_run_range(self.h, C.byref(flags), C.byref(self.out), list_mode, threads, c0, c1, reps)
+        if rc != 0:
+            raise RuntimeError(f"kr_oracle_ctx_run_range failed: {rc}")
+        return self.res
+
+    def run(self, flags: abi.kr_flags, list_mode: int = INDEXED, threads: int = 1) -> abi.Results:
+        rc = self.L.kr_oracle_ctx_run(self.h, C.byref(flags), C.byref(self.out), list_mode, threads)
+        if rc != 0:
+            raise RuntimeError(f"kr_oracle_ctx_run failed: {rc}")
+        self.res.n_create_total, self.res.n_orphans, self.res.n_actions = self.out.n_create_total, self.out.n_orphans, self.out.n_actions
+        return self.res
+
+    def close(self):
+        if self.h:
+            self.L.kr_oracle_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        L = C.CDLL(os.environ.get("KR_ORACLE_LIB") or build())  # KR_ORACLE_LIB: e.g. the ASan/UBSan build (make -C oracle asan)
-        L.kr_oracle_run.argtypes = [C.POINTER(abi.kr_snapshot_bufs), C.POINTER(abi.kr_sizes), C.POINTER(abi.kr_flags),
-                                    C.POINTER(abi.kr_oracle_out), C.c_int, C.c_int]
-        L.kr_oracle_run.restype = C.c_int
-        L.kr_oracle_run_range.argtypes = L.kr_oracle_run.argtypes + [C.c_uint32, C.c_uint32]
-        L.kr_oracle_run_range.restype = C.c_int
-        L.kr_oracle_hash32.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
-        L.kr_oracle_sha1.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
-        L.kr_oracle_desired_replicas.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]
-        L.kr_oracle_desired_replicas.restype = C.c_int32
-        L.kr_oracle_should_delete.argtypes = [C.c_uint32]
-        L.kr_oracle_should_delete.restype = C.c_int
+        L = _bind(C.CDLL(os.environ.get("KR_ORACLE_LIB") or build()))  # KR_ORACLE_LIB: e.g. the ASan/UBSan build (make -C oracle asan)
         _LIB = L
     return _LIB
 

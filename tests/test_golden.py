@@ -441,3 +441,78 @@ def test_update_endpoints_from_the_head_service_ports(backend):
     assert err is None
     assert new["endpoints"] == {"client": "10001", "dashboard": "8265", "metrics": "8080", "gcs-server": "6379", "serve": "8000"}
     assert new["_needs_write"]  # the endpoints differ from the (empty) stored status
+
+
+# ---------------------------------------------------------------------------------------------- API-call failures
+# reconcilePods joins one of the five ErrFailed* markers onto the error of a failing Create/Delete
+# (raycluster_controller.go:637,663,705,736,770,800,826,879,887,922); calculateStatus receives that error and only then sets
+# ReplicaFailure (:1563-1571) and refuses State=ready (:1599).  The engine's record was computed for reconcileErr == nil, so
+# the mirror (like the Go shim) discards its status half and re-evaluates status-only with the error kind.
+
+def _ready_fixture():
+    cluster = copy.deepcopy(SC["base"]["cluster"])
+    cluster["spec"]["enableInTreeAutoscaling"] = False
+    cluster["spec"]["workerGroupSpecs"][0].update({"replicas": 5, "workersToDelete": []})
+    pods = copy.deepcopy(SC["base"]["pods"])
+    for p in pods:
+        p["conditions"] = [{"type": "Ready", "status": "True"}]
+        if p["name"] != "headNode":
+            p.setdefault("labels", {})["ray.io/node-type"] = "worker"
+    return cluster, pods
+
+
+def _cond(status, t):
+    return next((c for c in status.get("conditions") or [] if c["type"] == t), None)
+
+
+def test_failed_create_head_sets_replica_failure(backend):
+    cluster, pods = _ready_fixture()
+    client = FakeClient([cluster], [p for p in pods if p["name"] != "headNode"])
+    client.fail_create.add("head")
+    r = RayClusterReconciler(client, backend)
+    requeue, err = r.reconcile(NS, CN)
+    assert requeue == 2.0 and err.startswith("FailedCreateHeadPod")
+    st = client.clusters[(NS, CN)]["status"]
+    rf = _cond(st, "ReplicaFailure")
+    assert rf and rf["status"] == "True" and rf["reason"] == "FailedCreateHeadPod" and "injected failure" in rf["message"]
+    assert st.get("state", "") != "ready"
+    assert len(heads(client)) == 0 and len(workers(client)) == 5  # reconcilePods returned at :736: workers untouched
+    # the failure clears: next pass creates the head and removes the condition (:1572-1574)
+    client.fail_create.clear()
+    r.reconcile(NS, CN)
+    assert len(heads(client)) == 1
+    assert _cond(client.clusters[(NS, CN)]["status"], "ReplicaFailure") is None
+
+
+def test_failed_delete_worker_blocks_ready_state(backend):
+    """All pods Running+Ready and |pods| == desired+1, so a pass WITHOUT the failure would set State=ready; the random
+    delete of one surplus... (here: a workersToDelete name) fails at the API server => ReplicaFailure, no ready."""
+    cluster, pods = _ready_fixture()
+    cluster["spec"]["workerGroupSpecs"][0].update({"replicas": 5, "workersToDelete": ["pod3"]})
+    client = FakeClient([cluster], pods)
+    client.fail_delete.add((NS, "pod3"))
+    r = RayClusterReconciler(client, backend)
+    _, err = r.reconcile(NS, CN)
+    assert err.startswith("FailedDeleteWorkerPod")
+    st = client.clusters[(NS, CN)]["status"]
+    assert _cond(st, "ReplicaFailure")["reason"] == "FailedDeleteWorkerPod"
+    assert st.get("state", "") != "ready"
+    assert len(workers(client)) == 5
+
+
+def test_workers_to_delete_name_outside_the_snapshot_is_still_deleted(backend):
+    """:817-822 issues Delete(ns, name) for every name; a Pod the packed snapshot does not list (not yet in the informer
+    cache / another shard) resolves to wtd_pod_idx = -1 in the engine but is deleted at the API server all the same."""
+    cluster, pods = _ready_fixture()
+    cluster["spec"]["enableInTreeAutoscaling"] = True
+    cluster["spec"]["workerGroupSpecs"][0].update({"replicas": 5, "workersToDelete": ["late-pod"]})
+    client = FakeClient([cluster], pods)
+    r = RayClusterReconciler(client, backend)
+    pr = r._pass()
+    late = copy.deepcopy(pods[1]); late["name"] = "late-pod"
+    client.create_pod(late)  # arrives after the snapshot was packed
+    ci = r._cluster_index(pr, NS, CN)
+    assert int(pr.res.wtd_pod_idx[int(pr.snap.g_wtd_off[int(pr.snap.c_group_off[ci])])]) == -1
+    assert r._apply_decisions(pr, ci) is None
+    assert (NS, "late-pod") not in client.pods
+    assert ("Normal", "DeletedWorkerPod", f"Deleted pod {NS}/late-pod") in client.events
