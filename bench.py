@@ -236,6 +236,9 @@ def main():
     from kuberay_b200.engine import Engine
 
     snap, flags, params = build_workload(args.workload, rank, world)
+    # the production configuration in every leg: the shim consumes the records + the compact action list + the replica indices,
+    # not the full per-cluster pod lists (kr_flags.fetch_pod_lists = 0; they are a verification / debugging output)
+    flags.fetch_pod_lists = 0
     nc_local = snap.dims["clusters"]
     eng = Engine.for_snapshot(snap, device=local_rank)
     views = eng.load(snap)
@@ -289,8 +292,7 @@ def main():
 
     # ---------------- e2e: host buffers through the C ABI (commit = H2D, reconcile_batch = kernels + D2H)
     # D2H = every cluster / group / RayJob record, the hashes, the workersToDelete resolutions, the compact action list and the
-    # replica indices; the full per-cluster pod lists (5 B/pod) stay on the device (kr_flags.fetch_pod_lists = 0)
-    flags.fetch_pod_lists = 0
+    # replica indices (kr_flags.fetch_pod_lists = 0, as in the value leg)
     for _ in range(2):
         eng.commit(); eng.reconcile(flags, copy=False)
     barrier()

@@ -230,8 +230,11 @@ typedef struct kr_flags {
   uint8_t  gate_multihost_indexing;  /* features.RayMultiHostIndexing, default 1 */
   uint8_t  env_random_pod_delete;    /* strings.ToLower(os.Getenv("ENABLE_RANDOM_POD_DELETE")) == "true" (:905) */
   uint8_t  skip_hash;                /* 1 => do not run the hash kernel (hash[] zeroed; Recreate gate treats hash as unknown) — test/bench knob only */
-  uint8_t  fetch_pod_lists;          /* 1 => kr_reconcile_batch / kr_results_fetch also copy the full per-cluster pod lists (sorted_pod_idx,
-                                        sorted_action: 5 B/pod) back; 0 => only the compact action list (act_*) comes back */
+  uint8_t  fetch_pod_lists;          /* 1 => the pass also builds every RayCluster's full pod list in List order (sorted_pod_idx,
+                                        sorted_action: 5 B/pod; cluster_result.pod_start) and kr_reconcile_batch / kr_results_fetch copy
+                                        it back — verification and debugging; 0 => only the compact action list (act_*) is produced,
+                                        which is all the shim consumes, and the pass takes the bucket pipeline (no per-cluster sort;
+                                        pod_start is then 0) */
   uint8_t  reserved_[3];
   uint32_t id_head_not_found_reason; /* interned id of "HeadPodNotFound" */
   uint32_t id_head_not_found_msg;    /* interned id of "Head Pod not found" */
@@ -357,14 +360,20 @@ typedef struct kr_results_view {
   const uint8_t           *sorted_action;  /* [n_pods]: KR_ACT_* aligned with sorted_pod_idx.  NULL unless kr_flags.fetch_pod_lists */
   const int32_t           *create_idx; /* [n_create_total] replica indices (:869-881,1081-1094) */
   const kr_job_result     *jobs;       /* [n_jobs] */
-  /* compact action list: every pod whose action != KEEP (orphans excluded), grouped by cluster, List order inside a cluster;
-   * cluster c owns entries [act_start[c], act_start[c+1]).  This is all the Go shim needs to issue the Delete calls. */
+  /* compact action list: every pod whose action != KEEP (orphans excluded), grouped by cluster in cluster order, List order
+   * inside a cluster; cluster c owns entries [act_start[c], act_start[c] + act_cnt[c]).  This is all the Go shim needs to issue
+   * the Delete calls.  act_start is non-decreasing and act_start[n_clusters] == act_extent; a cluster may own fewer entries than
+   * the gap to its successor (the engine reserves a whole bucket for a RayCluster whose Recreate gate was still waiting for the
+   * digest when the list was laid out).  The same holds for create_idx: group g owns [create_off, create_off + n_create). */
   const uint32_t          *act_start;  /* [n_clusters + 1] */
-  const uint32_t          *act_pod_idx;/* [n_actions] */
-  const uint8_t           *act_code;   /* [n_actions] KR_ACT_* */
-  uint32_t n_create_total;
+  const uint32_t          *act_cnt;    /* [n_clusters] */
+  const uint32_t          *act_pod_idx;/* [act_extent] */
+  const uint8_t           *act_code;   /* [act_extent] KR_ACT_* */
+  uint32_t n_create_total;         /* pods to create = sum of group_results.n_create */
   uint32_t n_orphans;
-  uint32_t n_actions;              /* pods with action != KEEP (orphans excluded) */
+  uint32_t n_actions;              /* pods with action != KEEP (orphans excluded) = sum of act_cnt */
+  uint32_t create_extent;          /* entries of create_idx in use (>= n_create_total) */
+  uint32_t act_extent;             /* entries of act_pod_idx / act_code in use (>= n_actions) */
   uint32_t reserved;
 } kr_results_view;
 

@@ -157,8 +157,9 @@ assert cluster_result_dtype.itemsize == 96 and group_result_dtype.itemsize == 32
 class kr_results_view(C.Structure):
     _fields_ = [("clusters", C.c_void_p), ("hash", C.c_void_p), ("groups", C.c_void_p), ("wtd_pod_idx", C.c_void_p),
                 ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
-                ("act_start", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
-                ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32), ("reserved", C.c_uint32)]
+                ("act_start", C.c_void_p), ("act_cnt", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
+                ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32),
+                ("create_extent", C.c_uint32), ("act_extent", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class kr_profile(C.Structure):
@@ -170,7 +171,7 @@ class kr_profile(C.Structure):
 class kr_oracle_out(C.Structure):  # oracle/kr_oracle.h (test infrastructure; declared here only for layout sharing)
     _fields_ = [("clusters", C.c_void_p), ("hash", C.c_void_p), ("groups", C.c_void_p), ("wtd_pod_idx", C.c_void_p),
                 ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
-                ("act_start", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
+                ("act_start", C.c_void_p), ("act_cnt", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
                 ("create_cap", C.c_uint32), ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32)]
 
 
@@ -201,7 +202,7 @@ class Results:
     """Owned numpy copy of one pass's results (engine or oracle) — same fields as kr_results_view."""
 
     FIELDS = ["clusters", "hash", "groups", "wtd_pod_idx", "sorted_pod_idx", "sorted_action", "create_idx", "jobs",
-              "act_start", "act_pod_idx", "act_code"]
+              "act_start", "act_cnt", "act_pod_idx", "act_code"]
 
     def __init__(self, sizes: kr_sizes, create_cap: int):
         self.clusters = np.zeros(sizes.n_clusters, dtype=cluster_result_dtype)
@@ -213,6 +214,7 @@ class Results:
         self.create_idx = np.zeros(max(create_cap, 1), dtype=np.int32)
         self.jobs = np.zeros(sizes.n_jobs, dtype=job_result_dtype)
         self.act_start = np.zeros(sizes.n_clusters + 1, dtype=np.uint32)
+        self.act_cnt = np.zeros(sizes.n_clusters, dtype=np.uint32)
         self.act_pod_idx = np.zeros(max(sizes.n_pods, 1), dtype=np.uint32)
         self.act_code = np.zeros(max(sizes.n_pods, 1), dtype=np.uint8)
         self.n_create_total = 0
@@ -222,28 +224,38 @@ class Results:
     def hash_strings(self):
         return [bytes(r).decode("ascii", "replace") for r in self.hash]
 
+    def actions_of(self, c: int):
+        """(pod idx, action) pairs of cluster c, List order."""
+        a, n = int(self.act_start[c]), int(self.act_cnt[c])
+        return self.act_pod_idx[a:a + n], self.act_code[a:a + n]
+
+    def creates_of(self, g: int):
+        a, n = int(self.groups["create_off"][g]), int(self.groups["n_create"][g])
+        return self.create_idx[a:a + n]
+
     def diff(self, other: "Results") -> list[str]:
-        """Field-by-field byte comparison; returns human-readable mismatches (empty == bit-exact parity)."""
+        """Field-by-field comparison; returns human-readable mismatches (empty == bit-exact parity).
+
+        The two variable-length arenas (action list, replica indices) are compared owner by owner through their
+        (offset, count) pairs: the engine may leave reserved-but-unused places in them (kr_results_view docs), so raw offsets
+        are layout, not results.  pod_start / sorted_* only mean something when the full pod lists were fetched."""
         out = []
         for k in ("n_create_total", "n_orphans", "n_actions"):
             if getattr(self, k) != getattr(other, k):
                 out.append(f"{k}: {getattr(self, k)} != {getattr(other, k)}")
+        lists = self.sorted_pod_idx.size != 0 and other.sorted_pod_idx.size != 0
         for name in self.FIELDS:
             a, b = getattr(self, name), getattr(other, name)
-            if name == "create_idx":
-                n = min(self.n_create_total, other.n_create_total)
-                a, b = a[:n], b[:n]
-            if name in ("act_pod_idx", "act_code"):
-                n = min(self.n_actions, other.n_actions)
-                a, b = a[:n], b[:n]
-            if name in ("sorted_pod_idx", "sorted_action") and (a.size == 0 or b.size == 0):
+            if name in ("create_idx", "act_pod_idx", "act_code", "act_start"):
+                continue  # compared through their owners below
+            if name in ("sorted_pod_idx", "sorted_action") and not lists:
                 continue  # one side did not fetch the full pod lists (kr_flags.fetch_pod_lists == 0)
             if a.shape != b.shape:
                 out.append(f"{name}: shape {a.shape} != {b.shape}")
                 continue
             if a.dtype.names:
                 for fld in a.dtype.names:
-                    if fld == "reserved":
+                    if fld == "reserved" or fld == "create_off" or (fld == "pod_start" and not lists):
                         continue
                     neq = a[fld] != b[fld]
                     if neq.ndim > 1:
@@ -258,4 +270,31 @@ class Results:
                 if neq.any():
                     i = int(np.flatnonzero(neq)[0])
                     out.append(f"{name}: {int(neq.sum())} entries differ, first at [{i}]: {a[i]} != {b[i]}")
+        if self.act_cnt.shape == other.act_cnt.shape and not (self.act_cnt != other.act_cnt).any():
+            for res in (self, other):
+                if (np.diff(res.act_start.astype(np.int64)) < res.act_cnt.astype(np.int64)).any():
+                    out.append("act_start: a cluster's entries run into its successor's")
+            sa, sb = _gather_owned(self.act_start[:-1], self.act_cnt), _gather_owned(other.act_start[:-1], other.act_cnt)
+            for name in ("act_pod_idx", "act_code"):
+                neq = getattr(self, name)[sa] != getattr(other, name)[sb]
+                if neq.any():
+                    i = int(np.flatnonzero(neq)[0])
+                    out.append(f"{name}: {int(neq.sum())} entries differ, first at action #{i}: {getattr(self, name)[sa][i]} != {getattr(other, name)[sb][i]}")
+        if self.groups.shape == other.groups.shape and not (self.groups["n_create"] != other.groups["n_create"]).any():
+            sa, sb = _gather_owned(self.groups["create_off"], self.groups["n_create"]), _gather_owned(other.groups["create_off"], other.groups["n_create"])
+            neq = self.create_idx[sa] != other.create_idx[sb]
+            if neq.any():
+                i = int(np.flatnonzero(neq)[0])
+                out.append(f"create_idx: {int(neq.sum())} entries differ, first at create #{i}: {self.create_idx[sa][i]} != {other.create_idx[sb][i]}")
         return out
+
+
+def _gather_owned(start: np.ndarray, cnt: np.ndarray) -> np.ndarray:
+    """Indices [start[i], start[i] + cnt[i]) of every owner i, concatenated in owner order."""
+    cnt = cnt.astype(np.int64)
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, dtype=np.int64)
+    owner = np.repeat(np.arange(cnt.size), cnt)
+    first = np.cumsum(cnt) - cnt
+    return start.astype(np.int64)[owner] + (np.arange(tot) - first[owner])

@@ -1,0 +1,597 @@
+// kr_bucket2.cuh — the bucket pipeline: k_match2 + k_decide2, the production path of a pass whose caller does not ask for the
+// full per-cluster pod lists (kr_flags.fetch_pod_lists == 0).
+// Part of the sm_100a kernel set of the batched reconcile engine; see kr_kernels.cuh for the pipeline overview.
+//
+// The sort pipeline (k_match -> k_place_fused -> k_decide_small -> k_creates_fused) spends most of its time restoring informer
+// List order inside every RayCluster's bucket — a scan + placement kernel, a 16-byte row gather and an in-register bitonic sort
+// per cluster — although the reference only looks at that order in three places: the head pod is the FIRST head listed
+// (common/association.go:184-196), a scale-down deletes the first -diff running pods (raycluster_controller.go:916-919), and
+// the Delete calls are issued in List order.  Everything else (selectors, counts, the unhealthy / workersToDelete sets, the
+// lowest free replica indices, the status roll-up) is a set computation.  So here
+//   k_match2   drops each pod's 16-byte record {pod idx, group slot | flags, replica index, name id} straight into its
+//              cluster's fixed-stride bucket at the arrival rank a returning atomic hands out: no scan, no placement pass, no
+//              row array — three scattered accesses per pod (table probe, atomic, record store) instead of four plus a gather;
+//   k_decide2  (one warp per RayCluster, bucket in registers, ARRIVAL order) takes the first head as a warp minimum over pod
+//              indices, the ordered delete prefix by extracting the -diff smallest indices (warp min-reduce per victim; a
+//              counting rank for long prefixes) and orders only the handful of pods that carry an action; it also allocates the
+//              replica indices from the registers and places the action list / create arena with a decoupled look-back over the
+//              CTAs, so nothing follows it: no creates kernel, no compaction kernel.
+// A bucket stride too small for some cluster voids the attempt (the engine widens the stride or falls back to the sort
+// pipeline); clusters with multi-host groups or more than KR_SMEM_GROUPS worker groups are routed to the sort pipeline by the
+// host before the pass.
+#pragma once
+
+#include "kr_decide.cuh"
+
+namespace kr {
+
+static constexpr int kD2Warps = 8;  // RayClusters per k_decide2 CTA
+
+// ------------------------------------------------------------------------------------------------ k_match2
+// The selector match (common/association.go:83-130) + bucketing.  7 coalesced column loads per pod (issued before the
+// programmatic-launch wait: they do not depend on the table build), one 16-byte probe of the cluster table (which also
+// carries the name of worker group 0, so a single-group RayCluster needs no second lookup), a shared-memory Bloom test
+// for the workersToDelete names, one returning atomic and one 16-byte record store.
+template <int kItems>
+__global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev sc, ResDev r, Sizes n, int has_wtd) {
+  KR_TL(1);
+  extern __shared__ uint32_t sm_bits[];  // copy of the workersToDelete Bloom bitmap
+  __shared__ uint32_t s_orph[kSortThreads / 32];
+  const uint32_t tile = blockIdx.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = tile * (kSortThreads * kItems) + warp * (32 * kItems) + lane;
+  uint32_t ns[kItems], cn[kItems], gn[kItems], nm[kItems], pk[kItems], ri[kItems];
+#pragma unroll
+  for (int it = 0; it < kItems; it++) {
+    const uint32_t p = base + it * 32;
+    const bool v = p < n.n_pods;
+    ns[it] = v ? __ldg(&s.p_ns_id[p]) : 0u; cn[it] = v ? __ldg(&s.p_cluster_name_id[p]) : 0u;
+    gn[it] = v ? __ldg(&s.p_group_name_id[p]) : 0u; nm[it] = v ? __ldg(&s.p_name_id[p]) : 0u;
+    pk[it] = v ? __ldg(&s.p_packed[p]) : 0u; ri[it] = v ? (uint32_t)__ldg(&s.p_replica_index[p]) : 0u;
+  }
+  pdl_wait(); pdl_trigger();
+  if (has_wtd) {
+    const uint32_t words = (sc.wt_bits_mask + 1) >> 5;
+    for (uint32_t i = threadIdx.x; i < words; i += kSortThreads) sm_bits[i] = __ldcg(&sc.wt_bits[i]);
+    __syncthreads();
+  }
+  // hash-join probe (namespace, ray.io/cluster) -> slot; the first probe of every pod in flight together
+  uint32_t pi[kItems];
+  uint4 sl[kItems];
+#pragma unroll
+  for (int it = 0; it < kItems; it++) {
+    pi[it] = hash_pair(ns[it], cn[it]) & sc.cl_mask;
+    sl[it] = __ldg(&sc.cl_slots[pi[it]]);
+  }
+  uint32_t orphans = 0;
+#pragma unroll
+  for (int it = 0; it < kItems; it++) {
+    const uint32_t p = base + it * 32;
+    const bool v = p < n.n_pods;
+    uint32_t c = n.n_clusters, cflags = 0, gname0 = 0;
+    if (cn[it] != 0) {
+      uint4 q = sl[it];
+      uint32_t i = pi[it];
+      while (true) {
+        if (q.x == cn[it] && q.y == ns[it]) { c = q.w >> 2; cflags = q.w & 3u; gname0 = q.z; break; }
+        if (q.x == KR_EMPTY32 && q.y == KR_EMPTY32) break;
+        i = (i + 1) & sc.cl_mask;
+        q = __ldg(&sc.cl_slots[i]);
+      }
+    }
+    const bool matched = v && c < n.n_clusters;
+    // ray.io/group against the cluster's worker groups (group names are unique: pkg/webhooks/v1/raycluster_webhook.go:74)
+    uint32_t slot = KR_ROW_NO_GROUP, g0 = 0xFFFFFFFFu;
+    if (matched && gn[it] != 0) {
+      if (gname0 == gn[it]) slot = 0;
+      else if (cflags & KR_CL_MULTI) {
+        const uint4 rec = __ldg(&sc.cl_rec[c]);
+        g0 = rec.x;
+        for (uint32_t gi = 1; gi < rec.y; gi++)
+          if (__ldg(&s.g_name_id[g0 + gi]) == gn[it]) { slot = gi; break; }
+      }
+    }
+    uint32_t flags = pk[it] & (0x7FFu | KR_PP_TOMBSTONE);  // bit 11 of the record word is KR_ROW_WTD_OWN
+    if (has_wtd && v) {  // scaleStrategy.workersToDelete: Delete(ns, name) (raycluster_controller.go:817-822)
+      const uint32_t hk = hash_pair(ns[it], nm[it]);
+      if (sm_bits[(hk & sc.wt_bits_mask) >> 5] & (1u << (hk & 31))) {
+        const uint64_t k = key2(ns[it], nm[it]);
+        uint32_t i = hk & sc.wt_mask;
+        uint64_t kk = __ldg(&sc.wt_keys[i]);
+        while (kk != KR_EMPTY64) {
+          if (kk == k) {
+            for (uint32_t e = sc.wt_head[i]; e != KR_EMPTY32; e = sc.wt_next[e]) {
+              atomicMin(&r.wtd_pod_idx[e], p);
+              if (slot != KR_ROW_NO_GROUP) {  // is e one of this pod's own group's names?
+                if (g0 == 0xFFFFFFFFu) g0 = __ldg(&s.c_group_off[c]);
+                const uint32_t g = g0 + slot, off = __ldg(&s.g_wtd_off[g]);
+                if (e >= off && e < off + __ldg(&s.g_wtd_cnt[g])) flags |= KR_ROW_WTD_OWN;
+              }
+            }
+            break;
+          }
+          i = (i + 1) & sc.wt_mask;
+          kk = __ldg(&sc.wt_keys[i]);
+        }
+      }
+    }
+    if (matched) {
+      const uint32_t rank = atomicAdd(&sc.ccount[c], 1u);  // arrival rank inside the cluster's bucket
+      if (rank < sc.bucket_stride) sc.bucket[(size_t)c * sc.bucket_stride + rank] = make_uint4(p, (slot << 16) | flags, ri[it], nm[it]);
+      else KR_MARK_ATTEMPT_VOID(r.totals);  // the engine reruns the pass with a wider stride / on the sort pipeline
+    }
+    orphans += __popc(__ballot_sync(0xFFFFFFFFu, v && !matched && !(pk[it] & KR_PP_TOMBSTONE)));
+  }
+  // pods that match no RayCluster of the snapshot (free rows of an incrementally maintained arena are not orphans)
+  if (lane == 0) s_orph[warp] = orphans;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; w++) t += s_orph[w];
+    if (t) atomicAdd(&r.totals[1], t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_decide2
+
+struct Decide2Args {
+  SnapDev s; ScratchDev sc; ResDev r; Sizes n; kr_flags f;
+  uint32_t create_cap;
+  int phase;  // 0: every RayCluster; 1: only the clusters phase 0 deferred (Recreate gate waiting for the hash kernel)
+};
+
+// look-back cell: [63:62] status (0 none, 1 aggregate of this CTA, 2 inclusive prefix), [61:31] pods to create, [30:0] action slots
+#define KR_LB_AGG (1ull << 62)
+#define KR_LB_INC (2ull << 62)
+__device__ __forceinline__ unsigned long long lb_pack(uint32_t creates, uint32_t acts) { return ((unsigned long long)creates << 31) | acts; }
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of (creates, action slots) over the CTAs before this one (decoupled look-back; executed by warp 0).  CTAs
+// are dispatched in index order, so every predecessor a CTA spins on is resident or done.  The cell carries its own payload:
+// no other memory has to be ordered with it.
+__device__ __forceinline__ unsigned long long cta_lookback(unsigned long long *state, uint32_t b, unsigned long long agg, uint32_t lane) {
+  if (b == 0) { if (lane == 0) lb_store(&state[0], KR_LB_INC | agg); return 0; }
+  if (lane == 0) lb_store(&state[b], KR_LB_AGG | agg);
+  unsigned long long excl = 0;
+  int32_t top = (int32_t)b - 1;  // lane l looks at CTA top - l
+  while (true) {
+    const int32_t idx = top - (int32_t)lane;
+    unsigned long long v;
+    uint32_t inc_mask, none_mask;
+    do {
+      v = idx >= 0 ? lb_load(&state[idx]) : KR_LB_INC;  // before CTA 0: an inclusive prefix of zero
+      inc_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+      none_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 0);
+      // cells below the nearest inclusive one do not matter
+      if (inc_mask) none_mask &= (2u << (__ffs(inc_mask) - 1)) - 1;
+    } while (none_mask);
+    const uint32_t take = inc_mask ? ((2u << (__ffs(inc_mask) - 1)) - 1) : 0xFFFFFFFFu;  // lanes 0 .. nearest inclusive
+    unsigned long long part = (take >> lane) & 1u ? (v & ~(3ull << 62)) : 0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);  // the two 31-bit fields cannot carry into each other (< 2^31 each in total)
+    excl += part;
+    if (inc_mask) break;
+    top -= 32;
+  }
+  if (lane == 0) lb_store(&state[b], KR_LB_INC | (excl + agg));
+  return excl;
+}
+
+// reconcilePods (raycluster_controller.go:619-935) + calculateStatus (:1552-1719) for one RayCluster whose bucket (<= 32*K pods,
+// arrival order) sits in registers.  Multi-host groups never reach this kernel.
+template <int K>
+__global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
+  KR_TL(a.phase ? 12 : 3);
+  __shared__ int32_t s_acc[kD2Warps][3][KR_SMEM_GROUPS];   // n_list, n_unhealthy, n_wtd_own per group
+  __shared__ int32_t s_mode[kD2Warps][3][KR_SMEM_GROUPS];  // mode, delete-prefix length, n_create
+  __shared__ uint32_t s_list[kD2Warps][32 * K];            // pod indices being ranked (delete candidates / acted pods)
+  __shared__ uint32_t s_bits[kD2Warps][32];                // 1024-bit window of replica indices in use
+  __shared__ uint32_t s_cta[kD2Warps][3];                  // per cluster: action slots reserved, pods to create, pods acted on
+  __shared__ unsigned long long s_base;
+  const SnapDev &s = a.s;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt = lanemask_lt();
+  const uint32_t S = a.sc.bucket_stride;
+  uint32_t c = blockIdx.x * kD2Warps + warp;
+  // cluster scalars do not depend on the previous kernel
+  bool mine = a.phase == 0 && c < a.n.n_clusters;
+  uint32_t cf = 0, G = 0, g0 = 0;
+  uint8_t suspend_status = 0, ext_err = 0, old_prov = 0;
+  if (mine) {
+    cf = LDG(s.c_flags[c]); G = LDG(s.c_group_cnt[c]); g0 = LDG(s.c_group_off[c]);
+    suspend_status = LDG(s.c_suspend_status[c]); ext_err = LDG(s.c_ext_err_kind[c]);
+    old_prov = LDG(s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED]);
+  }
+  pdl_wait(); pdl_trigger();
+  if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
+    mine = c < a.r.totals[4];
+    if (mine) {
+      c = a.sc.deferred_list[c];
+      cf = LDG(s.c_flags[c]); G = LDG(s.c_group_cnt[c]); g0 = LDG(s.c_group_off[c]);
+      suspend_status = LDG(s.c_suspend_status[c]); ext_err = LDG(s.c_ext_err_kind[c]);
+      old_prov = LDG(s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED]);
+    }
+  }
+  if (KR_ATTEMPT_VOID(a.r.totals)) mine = false;  // (every warp still walks through the CTA barriers below)
+  const bool gate = a.f.gate_status_conditions != 0;
+
+  uint32_t P = 0;
+  if (mine) { P = __ldcg(&a.sc.ccount[c]); if (P > S) { mine = false; P = 0; } }  // k_match2 voided the attempt
+  const uint4 *bucket = a.sc.bucket + (size_t)c * S;
+  uint32_t pidx[K], pw[K], ridx[K], act[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const uint32_t i = k * 32 + lane;
+    uint4 rec = make_uint4(0xFFFFFFFFu, KR_ROW_NO_GROUP << 16, 0, 0);
+    if (i < P) rec = __ldcg(&bucket[i]);
+    pidx[k] = rec.x; pw[k] = rec.y; ridx[k] = rec.z; act[k] = KR_ACT_KEEP;
+  }
+  int32_t *acc_list = s_acc[warp][0], *acc_unh = s_acc[warp][1], *acc_wtd = s_acc[warp][2];
+  int32_t *g_mode = s_mode[warp][0], *g_prefix = s_mode[warp][1], *g_ncreate = s_mode[warp][2];
+  if (lane < KR_SMEM_GROUPS) { acc_list[lane] = 0; acc_unh[lane] = 0; acc_wtd[lane] = 0; g_mode[lane] = GM_UNPROCESSED; g_prefix[lane] = 0; g_ncreate[lane] = 0; }
+  __syncwarp();
+
+  // ---------------- scan 1: counts over the cluster's pods (order-free)
+  int32_t ready = 0, available = 0, n_heads = 0;
+  bool all_running = P > 0;       // CheckAllPodsRunning (utils/util.go:584-603)
+  uint32_t head_pod = 0xFFFFFFFFu;  // first head in List order = the smallest pod index among the heads
+  uint32_t head_pos = 0;
+  const uint32_t nchunks = (P + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if ((uint32_t)k >= nchunks) break;
+    const bool valid = (uint32_t)(k * 32) + lane < P;
+    const uint32_t w = pw[k], fl = w & 0xFFFFu, slot = valid ? (w >> 16) : KR_ROW_NO_GROUP;
+    const uint32_t nt = pp_node_type(fl), ph = pp_phase(fl), rd = pp_ready(fl);
+    const bool w_run = valid && nt == KR_NT_WORKER && ph == KR_PHASE_RUNNING;
+    available += __popc(__ballot_sync(0xFFFFFFFFu, w_run));
+    ready += __popc(__ballot_sync(0xFFFFFFFFu, w_run && rd == KR_COND_TRUE));
+    const bool not_ok = valid && (ph != KR_PHASE_RUNNING || rd == KR_COND_FALSE || rd == KR_COND_UNKNOWN);
+    if (__any_sync(0xFFFFFFFFu, not_ok)) all_running = false;
+    const bool is_head = valid && nt == KR_NT_HEAD;
+    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, is_head);
+    if (hb) {
+      n_heads += __popc(hb);
+      const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, is_head ? pidx[k] : 0xFFFFFFFFu);
+      if (m < head_pod) { head_pod = m; head_pos = k * 32 + (__ffs(__ballot_sync(0xFFFFFFFFu, is_head && pidx[k] == m)) - 1); }
+    }
+    const uint32_t gkey = (slot < G) ? slot : KR_ROW_NO_GROUP;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, gkey);
+    if (gkey != KR_ROW_NO_GROUP) {
+      const uint32_t ub = __ballot_sync(peers, should_delete(fl));
+      const uint32_t wb = __ballot_sync(peers, (fl & KR_ROW_WTD_OWN) != 0);
+      if ((peers & lt) == 0) {  // leader of its group in this chunk
+        acc_list[gkey] += __popc(peers);
+        acc_unh[gkey] += __popc(ub & peers);
+        acc_wtd[gkey] += __popc(wb & peers);
+      }
+    }
+    __syncwarp();
+  }
+  uint32_t head_flags = 0, head_name = 0;
+  if (n_heads > 0) { const uint4 hrec = __ldcg(&bucket[head_pos]); head_flags = hrec.y & 0xFFFFu; head_name = hrec.w; }
+
+  // ---------------- scalar decisions (uniform across the warp) — same order as decide_cluster / the reference
+  kr_cluster_result cr;
+  {
+    uint32_t *z = reinterpret_cast<uint32_t *>(&cr);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(cr) / 4); k++) z[k] = 0;
+  }
+  cr.head_pod_idx = -1; cr.stop_after_group = -1;
+  uint8_t all_action = KR_ACT_KEEP;
+  bool head_delete = false, run_groups = false, deferred = false, any_prefix = false;
+  uint32_t n_create_cluster = 0;
+  if (mine) {
+    if (cf & KR_CF_SKIP) {
+      cr.path = KR_PATH_SKIPPED;
+    } else if (ext_err != KR_EXT_ERR_NONE) {
+      cr.path = KR_PATH_SKIPPED;  // :308-314
+      cr.err_kind = ext_err == KR_EXT_ERR_STATUS_ONLY_NIL ? KR_ERR_NONE : KR_ERR_EXTERNAL;
+    } else if (suspend_status == KR_SUSPEND_SUSPENDING || (!gate && (cf & KR_CF_SUSPEND))) {
+      cr.path = KR_PATH_SUSPENDING_DELETE_ALL; all_action = KR_ACT_DELETE_ALL_SUSPEND;  // :629-644
+    } else if (gate && (suspend_status == KR_SUSPEND_SUSPENDED || (cf & KR_CF_SUSPEND))) {
+      cr.path = KR_PATH_SUSPENDED_NOOP;  // :646-654
+    } else {
+      bool recreate = false;
+      if ((cf & KR_CF_UPGRADE_RECREATE) && n_heads > 0) {  // shouldRecreatePodsForUpgrade :1132-1171
+        const int32_t aux = aux_lookup(a.sc, head_pod);
+        const uint8_t ver = aux >= 0 ? s.h_version_state[aux] : (uint8_t)KR_VER_EMPTY;
+        const uint8_t ast = aux >= 0 ? s.h_annot_state[aux] : (uint8_t)KR_ANNOT_EMPTY;
+        if (ver == KR_VER_DIFFERENT) cr.head_update_annotations = 1;
+        else if (ast == KR_ANNOT_OTHER) recreate = true;
+        else if (ast == KR_ANNOT_HASH32 && !a.f.skip_hash) {
+          if (a.phase == 0) {
+            // The hash kernel is still running on its own stream.  Decide the cluster as if the digests matched, reserve the
+            // whole bucket in the action list (a Recreate deletes every pod) and let phase 1 redo it once the digest is there.
+            deferred = true;
+            if (lane == 0) a.sc.deferred_list[atomicAdd(&a.r.totals[4], 1u)] = c;
+          } else {
+            const uint8_t *ah = s.h_annot_hash + 32 * (size_t)aux;
+            const char *hh = a.r.hash + 32 * (size_t)c;
+            recreate = __any_sync(0xFFFFFFFFu, ah[lane] != (uint8_t)hh[lane]);
+          }
+        }
+      }
+      if (recreate) {
+        cr.path = KR_PATH_RECREATE_DELETE_ALL; all_action = KR_ACT_DELETE_ALL_RECREATE;  // :657-670
+      } else {
+        cr.path = KR_PATH_NORMAL;
+        if (!(cf & KR_CF_HEAD_EXPECT_OK)) { cr.head_action = KR_HEAD_EXPECT_PENDING; run_groups = true; }  // head (:673-748)
+        else if (n_heads == 1) {
+          if (should_delete(head_flags)) { cr.head_action = KR_HEAD_DELETE; cr.err_kind = KR_ERR_HEAD_DELETED; head_delete = true; }
+          else run_groups = true;
+        } else if (n_heads == 0) {
+          if (old_prov == KR_COND_TRUE && (cf & KR_CF_SKIP_HEAD_RESTART)) cr.head_action = KR_HEAD_SKIP_RESTART;
+          else { cr.head_action = KR_HEAD_CREATE; run_groups = true; }
+        } else {
+          cr.head_action = KR_HEAD_MULTIPLE; cr.err_kind = KR_ERR_MULTIPLE_HEADS; cr.err_arg = n_heads;
+        }
+      }
+    }
+    // worker groups in spec order (:751-933): O(1) per group from the scan-1 counters
+    if (run_groups) {
+      const bool autoscaling = (cf & KR_CF_AUTOSCALING) != 0;
+      cr.stop_after_group = (int32_t)G;
+      for (uint32_t gi = 0; gi < G; gi++) {
+        const uint32_t g = g0 + gi, gf = LDG(s.g_flags[g]);
+        const int32_t hosts = LDG(s.g_num_hosts[g]), g_rep = LDG(s.g_replicas[g]), g_mn = LDG(s.g_min[g]), g_mx = LDG(s.g_max[g]);
+        kr_group_result gr;
+        gr.expected = 0; gr.n_list = 0; gr.n_unhealthy = 0; gr.n_running = 0; gr.diff = 0; gr.n_create = 0; gr.create_off = 0;
+        gr.flags = KR_GR_PROCESSED;
+        int32_t mode = GM_SKIP, prefix = 0;
+        bool abort_here = false;
+        if (!(gf & KR_GF_EXPECT_OK)) {
+          gr.flags |= KR_GR_EXPECT_PENDING;
+        } else {
+          const int32_t expected = desired_replicas(g_rep, g_mn, g_mx, hosts, gf);
+          const int32_t n_list = acc_list[gi], n_unh = acc_unh[gi], n_wtd = acc_wtd[gi];
+          gr.expected = expected; gr.n_list = n_list;
+          if (gf & KR_GF_SUSPEND) { gr.flags |= KR_GR_SUSPENDED; mode = GM_SUSPENDED; }
+          else if (n_unh > 0) {  // :786-812
+            gr.n_unhealthy = n_unh; gr.flags |= KR_GR_ABORTED; mode = GM_UNHEALTHY;
+            cr.err_kind = KR_ERR_UNHEALTHY_WORKERS; cr.err_arg = n_unh; abort_here = true;
+          } else {
+            gr.flags |= KR_GR_WTD_EXECUTED; mode = GM_NORMAL;  // :814-849
+            const int32_t running = n_list - n_wtd;
+            const int32_t diff = expected - running;
+            gr.n_running = running; gr.diff = diff;
+            if (diff > 0) gr.n_create = (uint32_t)diff;
+            else if (diff < 0) {
+              if (!autoscaling || a.f.env_random_pod_delete) {  // :898-928
+                const long long remove = -(long long)diff;
+                if (remove > running) {  // expected < 0: the Go loop would index past runningPods (:917)
+                  prefix = running; gr.flags |= KR_GR_ABORTED;
+                  cr.err_kind = KR_ERR_NEGATIVE_EXPECTED; cr.err_arg = expected; abort_here = true;
+                } else prefix = (int32_t)remove;
+              } else gr.flags |= KR_GR_RANDOM_DELETE_OFF;
+            }
+          }
+        }
+        any_prefix |= prefix > 0;
+        n_create_cluster += gr.n_create;
+        __syncwarp();
+        if (lane == 0) {
+          g_mode[gi] = mode; g_prefix[gi] = prefix; g_ncreate[gi] = (int32_t)gr.n_create;
+          a.r.groups[g] = gr;  // create_off follows once the look-back has placed this cluster
+        }
+        if (abort_here) { cr.stop_after_group = (int32_t)gi; break; }
+      }
+    }
+    // groups never reached keep an all-zero record
+    {
+      const int32_t reached = ((cf & KR_CF_SKIP) || !run_groups) ? 0 : (cr.stop_after_group == (int32_t)G ? (int32_t)G : cr.stop_after_group + 1);
+      for (uint32_t gi = reached + lane; gi < G; gi += 32) {
+        kr_group_result z; z.expected = 0; z.n_list = 0; z.n_unhealthy = 0; z.n_running = 0; z.diff = 0; z.n_create = 0; z.create_off = 0; z.flags = 0;
+        a.r.groups[g0 + gi] = z;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---------------- scan 2: per-pod actions (set computations first, then the two ordered pieces)
+  uint32_t cand = 0;  // bit k: this lane's pod of chunk k is a running pod of a group in normal mode (subject to the ordered delete prefix)
+  if (mine) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if ((uint32_t)k >= nchunks) break;
+      const bool valid = (uint32_t)(k * 32) + lane < P;
+      const uint32_t w = pw[k], fl = w & 0xFFFFu;
+      const uint32_t gkey = (valid && run_groups && (w >> 16) < G) ? (w >> 16) : KR_ROW_NO_GROUP;
+      const int32_t mode = (gkey != KR_ROW_NO_GROUP) ? g_mode[gkey] : GM_UNPROCESSED;
+      uint32_t ac = KR_ACT_KEEP;
+      if (all_action != KR_ACT_KEEP) ac = valid ? all_action : (uint32_t)KR_ACT_KEEP;
+      else if (head_delete) { if (valid && pidx[k] == head_pod) ac = KR_ACT_DELETE_HEAD; }
+      else if (mode == GM_SUSPENDED) ac = KR_ACT_DELETE_GROUP_SUSPEND;
+      else if (mode == GM_UNHEALTHY) { if (should_delete(fl)) ac = KR_ACT_DELETE_UNHEALTHY; }
+      else if (mode == GM_NORMAL) {
+        if (fl & KR_ROW_WTD_OWN) ac = KR_ACT_DELETE_WTD;
+        else cand |= 1u << k;
+      }
+      act[k] = ac;
+    }
+    // runningPods.Items[0 .. -diff) (:916-919): the -diff smallest pod indices among the group's running pods
+    if (any_prefix) {
+      for (uint32_t gi = 0; gi < G; gi++) {
+        const int32_t pre = g_prefix[gi];
+        if (pre <= 0) continue;
+        if (pre <= 8) {  // a few victims: extract the minimum pre times
+          for (int32_t it = 0; it < pre; it++) {
+            uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < K; k++)
+              if (((cand >> k) & 1u) && (pw[k] >> 16) == gi && act[k] == KR_ACT_KEEP) m = min(m, pidx[k]);
+            const uint32_t wm = __reduce_min_sync(0xFFFFFFFFu, m);
+            if (wm == 0xFFFFFFFFu) break;
+#pragma unroll
+            for (int k = 0; k < K; k++)
+              if (((cand >> k) & 1u) && pidx[k] == wm) act[k] = KR_ACT_DELETE_RANDOM;
+          }
+        } else {  // a long prefix: rank every candidate among the group's candidates by counting
+          uint32_t nc = 0;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const bool isc = ((cand >> k) & 1u) && (pw[k] >> 16) == gi;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, isc);
+            if (isc) s_list[warp][nc + __popc(bal & lt)] = pidx[k];
+            nc += __popc(bal);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const bool isc = ((cand >> k) & 1u) && (pw[k] >> 16) == gi;
+            if (!__any_sync(0xFFFFFFFFu, isc)) continue;
+            uint32_t rank = 0;
+            for (uint32_t i = 0; i < nc; i++) rank += s_list[warp][i] < pidx[k] ? 1u : 0u;
+            if (isc && (int32_t)rank < pre) act[k] = KR_ACT_DELETE_RANDOM;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  // the cluster's action list in List order: stage the acted pods, rank each by counting the smaller pod indices
+  uint32_t n_act = 0;
+  uint32_t arank[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    arank[k] = 0;
+    const bool isa = act[k] != KR_ACT_KEEP;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, isa);
+    if (isa) s_list[warp][n_act + __popc(bal & lt)] = pidx[k];
+    n_act += __popc(bal);
+  }
+  __syncwarp();
+  if (n_act > 1) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const bool isa = act[k] != KR_ACT_KEEP;
+      if (!__any_sync(0xFFFFFFFFu, isa)) continue;
+      uint32_t rank = 0;
+      for (uint32_t i = 0; i < n_act; i++) rank += s_list[warp][i] < pidx[k] ? 1u : 0u;
+      arank[k] = rank;
+    }
+  }
+
+  // ---------------- status roll-up + record (needs nothing from the placement below)
+  if (mine && lane == 0) {
+    if (!(cf & KR_CF_SKIP))
+      status_rollup(a.s, a.sc, a.f, c, cr, P, (uint32_t)n_heads, n_heads > 0 ? (int32_t)head_pod : -1, head_name, ready, available, all_running);
+    a.r.clusters[c] = cr;
+  }
+
+  // ---------------- placement: where this cluster's action list and replica indices go
+  const uint32_t slots = deferred ? P : n_act;  // a deferred cluster may still turn into "delete every pod"
+  uint32_t act_off = 0, create_off = 0;
+  if (a.phase == 0) {
+    if (lane == 0) { s_cta[warp][0] = mine ? slots : 0u; s_cta[warp][1] = mine ? n_create_cluster : 0u; s_cta[warp][2] = mine ? n_act : 0u; }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t ta = 0, tc = 0, tn = 0;
+#pragma unroll
+      for (int w = 0; w < kD2Warps; w++) { ta += s_cta[w][0]; tc += s_cta[w][1]; tn += s_cta[w][2]; }
+      const unsigned long long agg = lb_pack(tc, ta);
+      const unsigned long long excl = cta_lookback(a.sc.lb_state, blockIdx.x, agg, lane);
+      if (lane == 0) {
+        s_base = excl;
+        if (tn) atomicAdd(&a.r.totals[2], tn);  // pods acted on (the extent of the list, totals[5], also counts reserved slots)
+        if (blockIdx.x == gridDim.x - 1) {       // extents of the two arenas
+          const unsigned long long tot = excl + agg;
+          a.r.totals[0] = (uint32_t)(tot >> 31); a.r.totals[6] = (uint32_t)(tot >> 31);
+          a.r.totals[5] = (uint32_t)(tot & 0x7FFFFFFFu);
+          a.r.act_start[a.n.n_clusters] = (uint32_t)(tot & 0x7FFFFFFFu);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    act_off = (uint32_t)(base & 0x7FFFFFFFu); create_off = (uint32_t)(base >> 31);
+#pragma unroll
+    for (int w = 0; w < kD2Warps; w++)
+      if (w < (int)warp) { act_off += s_cta[w][0]; create_off += s_cta[w][1]; }
+    if (mine && lane == 0) {
+      a.r.act_start[c] = act_off; a.r.act_cnt[c] = n_act;
+      if (deferred) a.sc.cact[c] = n_create_cluster;  // phase 1 corrects the count of pods to create if the cluster turns into a Recreate
+    }
+  } else if (mine) {  // phase 1: the places phase 0 reserved
+    act_off = a.r.act_start[c];
+    if (lane == 0) {
+      const uint32_t old_act = a.r.act_cnt[c], old_create = a.sc.cact[c];
+      a.r.act_cnt[c] = n_act;
+      if (n_act != old_act) atomicAdd(&a.r.totals[2], n_act - old_act);
+      if (n_create_cluster != old_create) atomicAdd(&a.r.totals[6], n_create_cluster - old_create);
+    }
+  }
+  if (!mine) return;
+  // action list, List order
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    if (act[k] != KR_ACT_KEEP) { a.r.act_pod_idx[act_off + arank[k]] = pidx[k]; a.r.act_code[act_off + arank[k]] = (uint8_t)act[k]; }
+  // create offsets + lowest free ray.io/worker-group-replica-index values (:854-881), from the registers
+  if (a.phase == 1 || n_create_cluster) {
+    uint32_t off = create_off;
+    for (uint32_t gi = 0; gi < G; gi++) {
+      const uint32_t g = g0 + gi;
+      const uint32_t want = (uint32_t)g_ncreate[gi];
+      if (a.phase == 1) {
+        // keep the arena position phase 0 gave this group (a Recreate leaves a gap: n_create is now 0)
+        off = a.sc.gcreate[g];
+      }
+      if (lane == 0) { a.r.groups[g].create_off = off; if (a.phase == 0) a.sc.gcreate[g] = off; }
+      if (want == 0) continue;
+      if ((uint64_t)off + want > a.create_cap) { off += want; continue; }  // the host reports KR_E_CAPACITY from totals[0]
+      int32_t *out = a.r.create_idx + off;
+      if (!a.f.gate_multihost_indexing) {  // createWorkerPod without an index (:884-889)
+        for (uint32_t k2 = lane; k2 < want; k2 += 32) out[k2] = -1;
+      } else {
+        const uint64_t bound = (uint64_t)(acc_list[gi] - acc_wtd[gi]) + want;  // the `want` lowest free indices all lie below n_running + want
+        uint32_t written = 0;
+        for (uint64_t w0 = 0; w0 < bound && written < want; w0 += 1024) {
+          s_bits[warp][lane] = 0;
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            // runningPods of this group: listed, not deleted by name, label present and numeric
+            if ((pw[k] >> 16) == gi && (pw[k] & KR_PP_HAS_REPLICA_IDX) && act[k] == KR_ACT_KEEP && pidx[k] != 0xFFFFFFFFu) {
+              const int32_t idx = (int32_t)ridx[k];
+              if (idx >= 0 && (uint64_t)idx >= w0 && (uint64_t)idx < w0 + 1024 && (uint64_t)idx < bound)
+                atomicOr(&s_bits[warp][(idx - w0) >> 5], 1u << ((idx - w0) & 31));
+            }
+          }
+          __syncwarp();
+          const uint32_t word = s_bits[warp][lane];
+          const uint64_t wbase = w0 + 32ull * lane;
+          uint32_t freeb = ~word;
+          if (wbase >= bound) freeb = 0;
+          else if (bound - wbase < 32) freeb &= (1u << (uint32_t)(bound - wbase)) - 1;
+          const uint32_t cnt = __popc(freeb);
+          uint32_t x = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d) x += y; }
+          uint32_t pos = written + x - cnt;
+          while (freeb && pos < want) {
+            const uint32_t bit = __ffs(freeb) - 1;
+            freeb &= freeb - 1;
+            out[pos++] = (int32_t)(wbase + bit);
+          }
+          written += __shfl_sync(0xFFFFFFFFu, x, 31);
+          __syncwarp();
+        }
+      }
+      off += want;
+    }
+  } else if (G) {
+    // no pod to create: every group of the cluster still gets its (empty) place in the arena
+    for (uint32_t gi = lane; gi < G; gi += 32) { a.r.groups[g0 + gi].create_off = create_off; a.sc.gcreate[g0 + gi] = create_off; }
+  }
+}
+
+}  // namespace kr

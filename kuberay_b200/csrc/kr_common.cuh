@@ -50,13 +50,19 @@ struct ResDev {  // device results arena
   int32_t *create_idx;
   kr_job_result *jobs;
   uint32_t *act_start;    // [n_clusters + 1]
+  uint32_t *act_cnt;      // [n_clusters]
   uint32_t *act_pod_idx;  // [n_pods] capacity; n_actions used
   uint8_t *act_code;
-  uint32_t *totals;  // [0]=n_create_total [1]=n_orphans [2]=n_actions [3]=error flags [4]=clusters deferred to decide phase 1
+  // [0]=extent of create_idx [1]=n_orphans [2]=n_actions [3]=error flags [4]=clusters deferred to decide phase 1
+  // [5]=extent of the action list (bucket pipeline: >= [2], deferred clusters reserve their whole bucket) [6]=pods to create (bucket pipeline)
+  uint32_t *totals;
 };
 
 struct ScratchDev {
-  uint4 *cl_slots; uint32_t cl_mask;                           // cluster table: {key lo, key hi, cluster idx, -} per 16-byte slot
+  // cluster table, one 16-byte slot per entry: {name id, ns id, name id of worker group 0, cluster idx << 2 | flags}
+  // (flags: bit 0 = some worker group has numOfHosts > 1, bit 1 = more than one worker group).  The common case — one worker
+  // group — resolves pod -> cluster -> group slot with this single load.
+  uint4 *cl_slots; uint32_t cl_mask;
   uint4 *cl_rec;                                               // [n_clusters] {group_off, group_cnt, name id of group 0, bit0 = has a multi-host group}
   uint64_t *wt_keys; uint32_t *wt_head; uint32_t *wt_next; uint32_t wt_mask;  // workersToDelete-name table
   uint32_t *aux_keys; uint32_t *aux_vals; uint32_t aux_mask;   // pod idx -> head-aux row
@@ -74,7 +80,13 @@ struct ScratchDev {
   uint32_t *ccount, *cstart;                                   // fast pipeline: pods per cluster bucket [n_clusters+1], bucket starts [n_clusters+2]
   uint32_t *deferred_list;                                     // clusters left for decide phase 1 (count in totals[4])
   int32_t *gacc;                                               // [4 * n_groups] spill accumulators (clusters with > KR_SMEM_GROUPS groups)
+  // bucket pipeline (kr_bucket2.cuh)
+  uint4 *bucket; uint32_t bucket_stride;                       // [n_clusters * stride] {pod idx, slot << 16 | flags, replica index, name id}, arrival order
+  uint32_t *wt_bits; uint32_t wt_bits_mask;                    // Bloom bitmap over the workersToDelete (ns, name) keys (power-of-two bit count)
+  unsigned long long *lb_state;                                // decoupled look-back cells of k_decide2 (one per CTA), zeroed every pass
 };
+#define KR_CL_MH 1u      // cl_slots[].w flag bits
+#define KR_CL_MULTI 2u
 
 struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
 
@@ -172,7 +184,7 @@ __device__ __forceinline__ bool cl_lookup(const ScratchDev &sc, uint32_t ns, uin
   uint32_t i = hash_pair(ns, name) & sc.cl_mask;
   while (true) {
     uint4 sl = __ldg(&sc.cl_slots[i]);  // one 16-byte load: key and value together
-    if (sl.x == name && sl.y == ns) { out = sl.z; return true; }
+    if (sl.x == name && sl.y == ns) { out = sl.w >> 2; return true; }
     if (sl.x == KR_EMPTY32 && sl.y == KR_EMPTY32) return false;
     i = (i + 1) & sc.cl_mask;
   }

@@ -43,11 +43,10 @@ struct DecideArgs {
 
 // calculateStatus (raycluster_controller.go:1552-1719) + InconsistentRayClusterStatus (utils/consistency.go:16-34).
 // Scalar code, executed by lane 0 only.
-__device__ void status_rollup(const DecideArgs &a, uint32_t c, kr_cluster_result &cr, uint32_t P, uint32_t n_heads, int32_t head_pod,
-                              uint32_t head_name_id, int32_t ready, int32_t available, bool all_running) {
-  const SnapDev &s = a.s;
+__device__ void status_rollup(const SnapDev &s, const ScratchDev &sc, const kr_flags &f, uint32_t c, kr_cluster_result &cr, uint32_t P, uint32_t n_heads,
+                              int32_t head_pod, uint32_t head_name_id, int32_t ready, int32_t available, bool all_running) {
   const uint32_t cf = s.c_flags[c];
-  const bool gate = a.f.gate_status_conditions != 0;
+  const bool gate = f.gate_status_conditions != 0;
   const bool reconcile_err = cr.err_kind != KR_ERR_NONE;
   const uint8_t ek = s.c_ext_err_kind[c];
   uint8_t cst[KR_NUM_CONDS], cvr[KR_NUM_CONDS];
@@ -94,14 +93,14 @@ __device__ void status_rollup(const DecideArgs &a, uint32_t c, kr_cluster_result
   uint32_t head_pod_ip = 0, head_pod_name = 0;
   int32_t aux = -1;
   if (n_heads == 1) {
-    aux = aux_lookup(a.sc, (uint32_t)head_pod);
+    aux = aux_lookup(sc, (uint32_t)head_pod);
     head_pod_ip = aux >= 0 ? s.h_pod_ip_id[aux] : 0;
     head_pod_name = head_name_id;
   }
   if (gate) {
     if (n_heads == 0) {  // :1613-1619
       cst[KR_COND_HEAD_POD_READY] = KR_COND_FALSE; cvr[KR_COND_HEAD_POD_READY] = KR_CV_HEAD_NOT_FOUND;
-      hpr_reason = a.f.id_head_not_found_reason; hpr_msg = a.f.id_head_not_found_msg;
+      hpr_reason = f.id_head_not_found_reason; hpr_msg = f.id_head_not_found_msg;
     } else {             // :1621-1622
       cst[KR_COND_HEAD_POD_READY] = aux >= 0 ? s.h_ready_status[aux] : (uint8_t)KR_COND_FALSE;
       cvr[KR_COND_HEAD_POD_READY] = KR_CV_HEAD_FROM_POD;
@@ -578,7 +577,7 @@ __device__ __forceinline__ void decide_cluster(const DecideArgs &a, const uint32
   // ---------------- status roll-up + record
   if (lane == 0) {
     if (!(cf & KR_CF_SKIP))
-      status_rollup(a, c, cr, P, (uint32_t)n_heads, head_pod, head_name, ready, available, all_running);
+      status_rollup(a.s, a.sc, a.f, c, cr, P, (uint32_t)n_heads, head_pod, head_name, ready, available, all_running);
     a.r.clusters[c] = cr;
     a.sc.cact[c] = n_act;
     if (n_act) atomicAdd(&a.r.totals[2], n_act);

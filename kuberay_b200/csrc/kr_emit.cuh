@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(1024) k_scan_actions(ResDev r, const uint32_t 
   uint32_t carry = chained_scan_chunk(cact, n_clusters, chunk, chain, 0, big, excl, s_warp, &s_prefix);
   const uint32_t i0 = chunk * kScanChunk + threadIdx.x * 8;
 #pragma unroll
-  for (int k = 0; k < 8; k++) if (i0 + k < n_clusters) r.act_start[i0 + k] = excl[k];
+  for (int k = 0; k < 8; k++) if (i0 + k < n_clusters) { r.act_start[i0 + k] = excl[k]; r.act_cnt[i0 + k] = cact[i0 + k]; }
   if (chunk == gridDim.x - 1 && threadIdx.x == 0) r.act_start[n_clusters] = carry;
 }
 // ... and the lists themselves, one warp per cluster
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(1024) k_creates_fused(SnapDev s, ScratchDev sc
   KR_TL_POINT(10);
   if (blockIdx.x == 0) {
     for (uint32_t g = threadIdx.x; g < n.n_groups; g += blockDim.x) r.groups[g].create_off = sm_off[g];
-    for (uint32_t c = threadIdx.x; c <= n.n_clusters; c += blockDim.x) r.act_start[c] = sm_act[c];
+    for (uint32_t c = threadIdx.x; c <= n.n_clusters; c += blockDim.x) { r.act_start[c] = sm_act[c]; if (c < n.n_clusters) r.act_cnt[c] = sm_act[c + 1] - sm_act[c]; }
     if (threadIdx.x == 0) r.totals[0] = tot;
   }
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;

@@ -74,7 +74,7 @@ InLayout in_layout(const kr_sizes &n) {
 }
 
 struct OutLayout {  // results arena: [small fixed part | full pod lists | variable-length lists]
-  size_t totals, clusters, hash, groups, wtd, jobs, act_start, small_total, sorted_idx, sorted_act, act_idx, act_code, create, total;
+  size_t totals, clusters, hash, groups, wtd, jobs, act_start, act_cnt, small_total, sorted_idx, sorted_act, act_idx, act_code, create, total;
 };
 OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
   OutLayout L;
@@ -86,6 +86,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
   L.wtd = o; o = align_up(o + 4 * (size_t)n.n_wtd);
   L.jobs = o; o = align_up(o + sizeof(kr_job_result) * (size_t)n.n_jobs);
   L.act_start = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 1));
+  L.act_cnt = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.small_total = o;  // everything above comes back in ONE copy
   L.sorted_idx = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.sorted_act = o; o = align_up(o + (size_t)n.n_pods);
@@ -99,8 +100,10 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, lb_state, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, bucket, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
+  uint32_t wt_bits_n;      // bits of the workersToDelete Bloom bitmap
+  size_t bucket_entries;   // capacity of the bucket arena of the bucket pipeline (0: that pipeline is off for this engine)
 };
 ScratchLayout scratch_layout(const kr_sizes &n) {
   ScratchLayout L;
@@ -134,6 +137,13 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.ccount = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.chain = o;  // directly after ccount: k_clear zeroes both as one region
   o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.mtiles / 8192 + (size_t)n.n_groups / 8192 + (size_t)n.n_clusters / 8192 + 10));
+  {
+    uint64_t bits = 1024;
+    while (bits < 64ull * n.n_wtd && bits < (1ull << 17)) bits <<= 1;  // 64 bits per name up to 16 KB (shared-memory copy per k_match2 CTA)
+    L.wt_bits_n = (uint32_t)bits;
+  }
+  L.wt_bits = o; o = align_up(o + L.wt_bits_n / 8);   // zeroed with ccount and chain (one region up to cstart)
+  L.lb_state = o; o = align_up(o + 8 * ((size_t)n.n_clusters / 8 + 2));
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.mtiles + 8));
   L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -145,6 +155,11 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.mh_head = o; o = align_up(o + (size_t)n.n_pods);
   L.act_tmp_idx = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.act_tmp_code = o; o = align_up(o + (size_t)n.n_pods);
+  // bucket pipeline: fixed-stride buckets of 16-byte records.  Room for a stride of >= 4x the mean cluster size, at least 64
+  // records per cluster; snapshots of very many tiny clusters (64 records per cluster would dwarf the pods) do without.
+  L.bucket_entries = std::max<size_t>(4 * (size_t)n.n_pods, 64 * (size_t)n.n_clusters);
+  if (64 * (size_t)n.n_clusters > 8 * (size_t)n.n_pods + (1u << 20)) L.bucket_entries = 0;
+  L.bucket = o; o = align_up(o + 16 * L.bucket_entries);
   L.total = o;
   return L;
 }
@@ -195,6 +210,18 @@ struct kr_engine {
   bool no_fuse = false;       // KR_NO_FUSE=1: always take the separate scan kernels (tests; large snapshots take them anyway)
   bool env_radix = false;     // KR_FORCE_RADIX=1: always take the general pipeline (tests)
   uint32_t *h_totals = nullptr;  // pinned copy of the device totals (pipeline fallback check)
+  // bucket pipeline (kr_bucket2.cuh): taken when the caller does not fetch the full pod lists and the snapshot qualifies
+  bool no_bucket = false;       // KR_NO_BUCKET=1: never take it (tests of the sort pipeline)
+  uint32_t bstride = 0;         // bucket stride of this layout (64 / 128 / 256); 0 = the layout does not qualify (a cluster outgrew 256 pods, ...)
+  bool snap_has_mh = false;     // some worker group has numOfHosts > 1
+  uint32_t snap_max_groups = 0; // most worker groups in one RayCluster
+  bool ran_bucket = false;
+  // hash order: message ids by descending SHA-1 block count, rebuilt at every commit from c_json_len
+  uint32_t *h_order = nullptr, *d_order = nullptr;
+  cudaEvent_t ev_order = nullptr;  // the upload of h_order has left the pinned buffer
+  bool order_pending = false;
+  std::vector<uint32_t> row_stamp;  // kr_snapshot_commit_pod_values: duplicate-row detection (epoch-stamped)
+  uint32_t row_epoch = 0;
 };
 
 namespace {
@@ -238,6 +265,7 @@ ResDev bind_out(const OutLayout &L, uint8_t *base) {
   r.sorted_action = base + L.sorted_act;
   r.jobs = reinterpret_cast<kr_job_result *>(base + L.jobs);
   r.act_start = reinterpret_cast<uint32_t *>(base + L.act_start);
+  r.act_cnt = reinterpret_cast<uint32_t *>(base + L.act_cnt);
   r.act_pod_idx = reinterpret_cast<uint32_t *>(base + L.act_idx);
   r.act_code = base + L.act_code;
   r.create_idx = reinterpret_cast<int32_t *>(base + L.create);
@@ -268,6 +296,9 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.mh_meta = reinterpret_cast<uint32_t *>(b + L.mh_meta); s.mh_cnt = reinterpret_cast<uint32_t *>(b + L.mh_cnt);
   s.mh_flg = reinterpret_cast<uint32_t *>(b + L.mh_flg); s.mh_act = b + L.mh_act; s.mh_head = b + L.mh_head;
   s.act_tmp_idx = reinterpret_cast<uint32_t *>(b + L.act_tmp_idx); s.act_tmp_code = b + L.act_tmp_code;
+  s.bucket = reinterpret_cast<uint4 *>(b + L.bucket); s.bucket_stride = 0;
+  s.wt_bits = reinterpret_cast<uint32_t *>(b + L.wt_bits); s.wt_bits_mask = L.wt_bits_n - 1;
+  s.lb_state = reinterpret_cast<unsigned long long *>(b + L.lb_state);
   return s;
 }
 
@@ -305,14 +336,18 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   const unsigned wflag = capturing ? cudaEventWaitExternal : cudaEventWaitDefault;
   // (the fork comes first so the hash can start while the columns are still landing — an incremental pod-row epoch leaves the JSON untouched)
   auto launch_hash = [&]() {
-    if (n.n_clusters <= (uint32_t)e->sm_count * 4 * 32) {  // (CTAs of 2 or 4 warps confine the hash to fewer SMs; measured: no gain for the chain)
-      uint32_t blocks = (n.n_clusters + 31) / 32;
-      k_hash2<1, 0><<<blocks, 32, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
+    // messages are taken in e->d_order (descending SHA-1 block count, built at commit): length-homogeneous warps, longest first
+    const uint32_t ngroups = (n.n_clusters + 31) / 32;
+    if (ngroups <= (uint32_t)e->sm_count * 4) {
+      // latency regime (C3: 313 groups): the pass waits for the longest message's serial chain — warp-specialised pairs,
+      // two per SM so that every hash warp has a scheduler to itself
+      const uint32_t G = std::min<uint32_t>(ngroups, (uint32_t)e->sm_count * 2);
+      k_hash3<1, 0><<<G, 64, sizeof(H3Smem), H>>>(s.json, s.c_json_off, s.c_json_len, e->d_order, n.n_clusters, r.hash);
     } else {
-      // throughput regime: two resident CTAs per SM walk the message groups, so the hash never fills the SMs' shared memory and
-      // the main chain starts at once (with one CTA per group, 3 per SM, k_clear waited ~140 us at C3x10 for the first to retire)
+      // throughput regime: resident CTAs of four one-lane-per-message warps walk the groups, round adds on the FMA pipe
+      // (tools/hash_bench, 100 k messages: 1.58 TB/s against 1.40 TB/s for the pairs)
       uint32_t blocks = std::min<uint32_t>((n.n_clusters + 127) / 128, (uint32_t)e->sm_count * e->hash_ctas_per_sm);
-      k_hash2<4, 1><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, nullptr, n.n_clusters, r.hash, 1u);
+      k_hash2<4, 1><<<blocks, 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, e->d_order, n.n_clusters, r.hash, 1u);
     }
   };
   auto start_hash_stream = [&]() -> int {
@@ -329,6 +364,12 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   { int rc = start_hash_stream(); if (rc) return rc; }
 
   // --- stream M
+  // bucket pipeline (kr_bucket2.cuh): the caller does not fetch the full pod lists, no multi-host group is in play, every
+  // RayCluster has few worker groups and (checked on the device) at most `bstride` pods
+  const bool bucket = !e->no_bucket && !f.fetch_pod_lists && e->bstride != 0 && !e->force_radix && e->snap_max_groups <= KR_SMEM_GROUPS &&
+                      !(e->snap_has_mh && f.gate_multihost_indexing) && (size_t)n.n_clusters * e->bstride <= e->sl.bucket_entries;
+  e->ran_bucket = bucket;
+  sc.bucket_stride = e->bstride;
   const bool pdl = !profile && e->use_pdl;
   bool fuse_place_done = false;    // k_decide_small directly follows k_place_fused on stream M
   bool creates_after_kernel = false;  // k_creates_fused directly follows a kernel on stream M (no event wait in between)
@@ -337,7 +378,8 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     ca.ptr[0] = reinterpret_cast<uint32_t *>(e->d_scratch); ca.words[0] = (uint32_t)(e->sl.ff_total / 4); ca.value[0] = 0xFFFFFFFFu;
     ca.ptr[1] = r.wtd_pod_idx; ca.words[1] = n.n_wtd; ca.value[1] = 0xFFFFFFFFu;
     ca.ptr[2] = r.totals; ca.words[2] = 64; ca.value[2] = 0;  // the 8 counters and, 128 bytes in, the void-attempt word (the block is 256 bytes)
-    ca.ptr[3] = sc.ccount; ca.words[3] = e->force_radix ? 0u : (uint32_t)((e->sl.cstart - e->sl.ccount) / 4); ca.value[3] = 0;  // per-cluster counts + the chained-scan cells
+    // per-cluster counts + the chained-scan cells + the workersToDelete Bloom bitmap + the look-back cells (one region)
+    ca.ptr[3] = sc.ccount; ca.words[3] = (uint32_t)((e->sl.cstart - e->sl.ccount) / 4); ca.value[3] = 0;
     mark("k_clear");
     k_clear<<<e->sm_count * 2, 256, 0, M>>>(ca);
   }
@@ -346,6 +388,36 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     uint32_t items = n.n_clusters + n.n_groups + n.n_heads;
     if (items) { mark("k_build_tables"); k_build_tables<<<(items + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
   }
+  if (bucket) {
+    e->ran_fast = false;
+    const uint32_t mtiles = e->sl.mtiles;
+    if (n.n_pods) {
+      mark("k_match2");
+      CK(launch_pdl(k_match2<kMatchItems>, dim3(mtiles), dim3(kSortThreads), n.n_wtd ? e->sl.wt_bits_n / 8 : 0, M, pdl, s, sc, r, z, n.n_wtd ? 1 : 0));
+    }
+    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 0};
+    auto launch_decide2 = [&](dim3 grid, bool with_pdl) -> cudaError_t {
+      if (e->bstride <= 64) return launch_pdl(k_decide2<2>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
+      if (e->bstride <= 128) return launch_pdl(k_decide2<4>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
+      return launch_pdl(k_decide2<8>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
+    };
+    if (n.n_clusters) {
+      mark("k_decide2");
+      CK(launch_decide2(dim3((n.n_clusters + kD2Warps - 1) / kD2Warps), pdl && n.n_pods != 0));
+    } else CK(cudaMemsetAsync(r.act_start, 0, 4, M));
+    if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
+    if (profile) {
+      if (do_hash) { mark("k_hash"); launch_hash(); }
+      else if (n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, M));
+    } else {
+      CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
+    }
+    if (e->n_recreate > 0 && do_hash) {  // clusters whose Recreate gate needs the digest: decided again, in the places phase 0 reserved
+      da.phase = 1;
+      mark("k_decide2_phase1");
+      CK(launch_decide2(dim3((e->n_recreate + kD2Warps - 1) / kD2Warps), false));
+    }
+  } else {
   const uint32_t ntiles = e->sl.ntiles;
   const bool fast = !e->force_radix;
   e->ran_fast = fast;
@@ -445,6 +517,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     mark("k_create_fill");
     k_create_fill<<<(n.n_groups + 3) / 4, 128, 0, M>>>(s, sc, r, z, f, e->cfg.max_creates);
   }
+  }  // sort / radix pipelines
   if (profile && k <= KR_MAX_KERNEL_TIMES) cudaEventRecord(e->ev_k[k < KR_MAX_KERNEL_TIMES ? k : KR_MAX_KERNEL_TIMES], M);
   e->prof.n_kernels = (uint32_t)k;
   CK(cudaGetLastError());
@@ -454,8 +527,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
 // Replays the captured CUDA graph of the pass (captures it first when the layout / flags changed).
 int run_pass_once(kr_engine *e, const kr_flags &f) {
   if (!e->use_graph) return launch_pass(e, f, false);
-  kr_flags fk = f;
-  fk.fetch_pod_lists = 0;  // host-side switch: does not change the device work
+  kr_flags fk = f;  // (fetch_pod_lists selects the pipeline: part of the key)
   if (!e->gvalid || memcmp(&e->gflags, &fk, sizeof fk) != 0) {
     e->gvalid = false;
     CK(cudaStreamBeginCapture(e->sm, cudaStreamCaptureModeThreadLocal));
@@ -493,19 +565,26 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
 // switches this layout to the radix pipeline and runs again.  Leaves the stream synchronised.
 int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
   e->last_flags = f;
-  for (int attempt = 0; attempt < 2; attempt++) {
+  for (int attempt = 0; attempt < 5; attempt++) {
     int rc = run_pass_once(e, f);
     if (rc) return rc;
     if (done) CK(cudaEventRecord(done, e->sm));
     CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
+    e->order_pending = false;
     if (!e->h2d_timed) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
       e->h2d_timed = true;
     }
-    if (e->ran_fast && (e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { e->force_radix = true; e->gvalid = false; continue; }
-    return KR_OK;
+    if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) return KR_OK;
+    // some RayCluster outgrew what this pipeline holds per bucket: bucket pipeline -> wider stride -> sort pipeline -> radix pipeline
+    if (e->ran_bucket) {
+      const uint32_t wider = e->bstride * 2;
+      e->bstride = (wider <= 256 && (size_t)e->sizes.n_clusters * wider <= e->sl.bucket_entries) ? wider : 0;
+    } else if (e->ran_fast) e->force_radix = true;
+    else break;
+    e->gvalid = false;
   }
   return fail(e, KR_E_STATE, "internal: radix pipeline flagged a big bucket");
 }
@@ -516,7 +595,8 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
 int fetch_results(kr_engine *e, kr_results_view *out) {
   const kr_sizes &n = e->sizes;
   const uint32_t *tot = e->h_totals;
-  const uint32_t n_create = tot[0], n_actions = tot[2];
+  // bucket pipeline: the two arenas can hold reserved-but-unused places (totals[5] / totals[0] are their extents, [2] / [6] the counts)
+  const uint32_t n_create = tot[0], n_actions = e->ran_bucket ? tot[5] : tot[2];
   const bool full = e->last_flags.fetch_pod_lists != 0;
   CK(cudaEventRecord(e->ev_b, e->sm));
   if (n_create > e->cfg.max_creates) {
@@ -553,8 +633,9 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
     out->wtd_pod_idx = reinterpret_cast<const int32_t *>(hr.wtd_pod_idx);
     out->sorted_pod_idx = full ? hr.sorted_pod_idx : nullptr; out->sorted_action = full ? hr.sorted_action : nullptr;
     out->create_idx = hr.create_idx; out->jobs = hr.jobs;
-    out->act_start = hr.act_start; out->act_pod_idx = hr.act_pod_idx; out->act_code = hr.act_code;
-    out->n_create_total = n_create; out->n_orphans = tot[1]; out->n_actions = n_actions; out->reserved = 0;
+    out->act_start = hr.act_start; out->act_cnt = hr.act_cnt; out->act_pod_idx = hr.act_pod_idx; out->act_code = hr.act_code;
+    out->n_create_total = e->ran_bucket ? tot[6] : n_create; out->n_orphans = tot[1]; out->n_actions = tot[2];
+    out->create_extent = n_create; out->act_extent = n_actions;
   }
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_c) == cudaSuccess) e->prof.d2h_ms = ms;
@@ -647,7 +728,8 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
                         (const void *)k_decide, (const void *)k_creates_fused, (const void *)k_jobs, (const void *)k_hash2<1, 0>, (const void *)k_hash2<4, 1>,
                         (const void *)k_clear, (const void *)k_match<false, kSortItems>, (const void *)k_hist, (const void *)k_scan_rows, (const void *)k_scatter,
                         (const void *)k_scan_counts, (const void *)k_place, (const void *)k_scan_creates, (const void *)k_create_fill, (const void *)k_scan_actions,
-                        (const void *)k_compact_actions, (const void *)k_patch_pods, (const void *)k_patch_pod_values};
+                        (const void *)k_compact_actions, (const void *)k_patch_pods, (const void *)k_patch_pod_values,
+                        (const void *)k_match2<kMatchItems>, (const void *)k_decide2<2>, (const void *)k_decide2<4>, (const void *)k_decide2<8>, (const void *)k_hash3<1, 0>};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
@@ -658,6 +740,11 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (const char *g = getenv("KR_PLACE_CTAS")) e->place_ctas = atoi(g) > 0 ? atoi(g) : 1;
   e->force_radix = e->env_radix;
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+  if (const char *g = getenv("KR_NO_BUCKET")) e->no_bucket = (g[0] == '1');
+  if (cudaHostAlloc((void **)&e->h_order, 4 * ((size_t)cfg->max_clusters + 1), cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+  if (cudaMalloc((void **)&e->d_order, 4 * ((size_t)cfg->max_clusters + 1)) != cudaSuccess) return bail(KR_E_CUDA);
+  cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming);
+  cudaFuncSetAttribute(k_hash3<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(H3Smem));
   *out = e;
   return KR_OK;
 }
@@ -671,6 +758,9 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->h_out) cudaFreeHost(e->h_out);
   if (e->hb_h) cudaFreeHost(e->hb_h);
   if (e->h_totals) cudaFreeHost(e->h_totals);
+  if (e->h_order) cudaFreeHost(e->h_order);
+  if (e->d_order) cudaFree(e->d_order);
+  if (e->ev_order) cudaEventDestroy(e->ev_order);
   if (e->d_in) cudaFree(e->d_in);
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->d_out) cudaFree(e->d_out);
@@ -705,6 +795,12 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
   if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) {  // row counts (and, without KR_OPT_FIXED_LAYOUT, every column address) change
     e->gvalid = false; e->force_radix = e->env_radix;
     if (!e->fixed_layout) e->committed_full = false;
+    // bucket stride: a power of two with 25 % head room over the mean cluster size (a cluster that outgrows it voids the
+    // attempt; the pass then widens the stride, up to 256, or leaves the bucket pipeline for this layout)
+    uint32_t st = 64;
+    const uint64_t want = sizes->n_clusters ? ((uint64_t)sizes->n_pods * 5 / 4 + sizes->n_clusters - 1) / sizes->n_clusters : 0;
+    while (st < want && st < 512) st <<= 1;
+    e->bstride = st <= 256 ? st : 0;
   }
   e->sizes = *sizes;
   const kr_sizes lay = e->fixed_layout ? cap_sizes(c) : *sizes;
@@ -731,19 +827,48 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   kr_snapshot_bufs hb;
   bind_in(e->il, e->h_in, &hb);
   const kr_sizes &n = e->sizes;
-  uint32_t n_recreate = 0;
-  uint64_t goff = 0;
+  uint32_t n_recreate = 0, max_groups = 0;
+  bool has_mh = false;
+  uint64_t goff = 0, woff = 0;
   for (uint32_t c = 0; c < n.n_clusters; c++) {
     if (hb.c_group_off[c] != goff) return fail(e, KR_E_INVALID, "cluster %u: groups must be stored in cluster order (group_off %u != %llu)", c, hb.c_group_off[c], (unsigned long long)goff);
     if (hb.c_group_cnt[c] >= 0xFFFFu) return fail(e, KR_E_CAPACITY, "cluster %u has %u worker groups (limit 65534)", c, hb.c_group_cnt[c]);
+    if (goff + hb.c_group_cnt[c] > n.n_groups) return fail(e, KR_E_INVALID, "cluster %u: groups run past n_groups", c);
+    // the kernels trust these indices: a shim bug must come back as KR_E_INVALID, not as out-of-bounds device writes
+    for (uint64_t g = goff; g < goff + hb.c_group_cnt[c]; g++) {
+      if (hb.g_cluster_idx[g] != c) return fail(e, KR_E_INVALID, "group %llu: g_cluster_idx %u != owning cluster %u", (unsigned long long)g, hb.g_cluster_idx[g], c);
+      if (hb.g_wtd_off[g] != woff) return fail(e, KR_E_INVALID, "group %llu: workersToDelete names must be stored in group order (wtd_off %u != %llu)", (unsigned long long)g, hb.g_wtd_off[g], (unsigned long long)woff);
+      woff += hb.g_wtd_cnt[g];
+      if (woff > n.n_wtd) return fail(e, KR_E_INVALID, "group %llu: workersToDelete names run past n_wtd", (unsigned long long)g);
+      has_mh |= hb.g_num_hosts[g] > 1;
+    }
+    max_groups = std::max(max_groups, hb.c_group_cnt[c]);
     goff += hb.c_group_cnt[c];
     if (hb.c_json_off[c] & 15) return fail(e, KR_E_INVALID, "cluster %u: json offset not 16-byte aligned", c);
     if (hb.c_json_off[c] + hb.c_json_len[c] > n.json_bytes) return fail(e, KR_E_INVALID, "cluster %u: json range outside arena", c);
     if (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) n_recreate++;
   }
   if (goff != n.n_groups) return fail(e, KR_E_INVALID, "sum of group_cnt (%llu) != n_groups (%u)", (unsigned long long)goff, n.n_groups);
-  if (n_recreate != e->n_recreate) e->gvalid = false;  // decide phase 1 launch shape depends on it
-  e->n_recreate = n_recreate;
+  if (woff != n.n_wtd) return fail(e, KR_E_INVALID, "sum of g_wtd_cnt (%llu) != n_wtd (%u)", (unsigned long long)woff, n.n_wtd);
+  for (uint32_t h = 0; h < n.n_heads; h++)
+    if (hb.h_pod_idx[h] >= n.n_pods) return fail(e, KR_E_INVALID, "head-aux row %u: h_pod_idx %u >= n_pods %u", h, hb.h_pod_idx[h], n.n_pods);
+  if (n_recreate != e->n_recreate || has_mh != e->snap_has_mh || (max_groups > KR_SMEM_GROUPS) != (e->snap_max_groups > KR_SMEM_GROUPS)) e->gvalid = false;  // launch shape / pipeline depend on them
+  e->n_recreate = n_recreate; e->snap_has_mh = has_mh; e->snap_max_groups = max_groups;
+  // hash order: message ids by descending SHA-1 block count (counting sort; the kernels run length-homogeneous warps, longest first)
+  if (e->order_pending) { CK(cudaEventSynchronize(e->ev_order)); e->order_pending = false; }  // a previous upload may still be reading h_order
+  {
+    uint32_t maxb = 0;
+    for (uint32_t c = 0; c < n.n_clusters; c++) maxb = std::max(maxb, (hb.c_json_len[c] + 8) / 64 + 1);
+    if (maxb <= (1u << 20)) {
+      std::vector<uint32_t> start((size_t)maxb + 2, 0);
+      for (uint32_t c = 0; c < n.n_clusters; c++) start[maxb - ((hb.c_json_len[c] + 8) / 64 + 1) + 1]++;  // bucket 0 = longest
+      for (uint32_t b = 0; b <= maxb; b++) start[b + 1] += start[b];
+      for (uint32_t c = 0; c < n.n_clusters; c++) e->h_order[start[maxb - ((hb.c_json_len[c] + 8) / 64 + 1)]++] = c;
+    } else {
+      for (uint32_t c = 0; c < n.n_clusters; c++) e->h_order[c] = c;
+      std::stable_sort(e->h_order, e->h_order + n.n_clusters, [&](uint32_t a, uint32_t b) { return hb.c_json_len[a] / 64 > hb.c_json_len[b] / 64; });
+    }
+  }
   // Asynchronous, in two parts on the copy stream: every column first, the spec-JSON arena (the larger half) second.
   // The pass waits on the two events, so match/place/decide run while the JSON is still crossing PCIe and only the hash
   // (and what depends on it) waits for the second part.  Nothing here blocks the host.
@@ -769,6 +894,9 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
         if (int rc = up(e->il.off[kFirstPodCol + k], 4 * (size_t)n.n_pods)) return rc;
   }
   CK(cudaEventRecord(e->ev_cols, e->scopy));
+  if (n.n_clusters) { CK(cudaMemcpyAsync(e->d_order, e->h_order, 4 * (size_t)n.n_clusters, cudaMemcpyHostToDevice, e->scopy)); bytes += 4 * (size_t)n.n_clusters; }
+  CK(cudaEventRecord(e->ev_order, e->scopy));
+  e->order_pending = true;
   if (parts & KR_PART_JSON) { if (int rc = up(json_off, e->fixed_layout ? (size_t)n.json_bytes : e->il.total - json_off)) return rc; }
   CK(cudaEventRecord(e->ev_json, e->scopy));
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));
@@ -798,6 +926,14 @@ static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *
   }
   for (uint32_t i = 0; i < n; i++)
     if (rows[i] >= e->sizes.n_pods) return fail(e, KR_E_INVALID, "pod row %u out of range", rows[i]);
+  if (values) {  // the scatter kernel writes one thread per entry: two entries for one row would race
+    if (e->row_stamp.size() < e->sizes.n_pods) e->row_stamp.assign(e->sizes.n_pods, 0);
+    if (++e->row_epoch == 0) { std::fill(e->row_stamp.begin(), e->row_stamp.end(), 0u); e->row_epoch = 1; }
+    for (uint32_t i = 0; i < n; i++) {
+      if (e->row_stamp[rows[i]] == e->row_epoch) return fail(e, KR_E_INVALID, "kr_snapshot_commit_pod_values: pod row %u appears twice", rows[i]);
+      e->row_stamp[rows[i]] = e->row_epoch;
+    }
+  }
   memcpy(e->pr_h, rows, 4 * (size_t)n);
   if (values) memcpy(e->pr_h + 4 * (size_t)n, values, 28 * (size_t)n);
   kr_snapshot_bufs hb;
@@ -866,19 +1002,21 @@ int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile 
   if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
   CK(cudaSetDevice(e->cfg.device));
   e->last_flags = *flags;
-  CK(cudaEventRecord(e->ev_a, e->sm));
-  int rc = launch_pass(e, *flags, true);
-  if (rc) return rc;
-  CK(cudaEventRecord(e->ev_b, e->sm));
-  CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
-  CK(cudaStreamSynchronize(e->sm));
-  if (e->ran_fast && (e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) {
-    e->force_radix = true; e->gvalid = false;
+  for (int attempt = 0;; attempt++) {  // same fallback ladder as run_pass
     CK(cudaEventRecord(e->ev_a, e->sm));
-    rc = launch_pass(e, *flags, true);
+    int rc = launch_pass(e, *flags, true);
     if (rc) return rc;
     CK(cudaEventRecord(e->ev_b, e->sm));
+    CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
+    e->order_pending = false;
+    if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) break;
+    if (attempt >= 4) return fail(e, KR_E_STATE, "internal: radix pipeline flagged a big bucket");
+    if (e->ran_bucket) {
+      const uint32_t wider = e->bstride * 2;
+      e->bstride = (wider <= 256 && (size_t)e->sizes.n_clusters * wider <= e->sl.bucket_entries) ? wider : 0;
+    } else if (e->ran_fast) e->force_radix = true;
+    e->gvalid = false;
   }
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->prof.kernels_ms = ms;
@@ -911,7 +1049,7 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
     if (offsets[i + 1] - offsets[i] > 0xFFFFFFFFull) return fail(e, KR_E_CAPACITY, "message %u longer than 4 GiB", i);
     data += align_up(offsets[i + 1] - offsets[i], 16);
   }
-  size_t o_off = 0, o_len = align_up(8 * (size_t)n), o_data = align_up(o_len + 4 * (size_t)n), o_out = align_up(o_data + data + 16), total = o_out + 32 * (size_t)n;
+  size_t o_off = 0, o_len = align_up(8 * (size_t)n), o_ord = align_up(o_len + 4 * (size_t)n), o_data = align_up(o_ord + 4 * (size_t)n), o_out = align_up(o_data + data + 16), total = o_out + 32 * (size_t)n;
   if (total > e->hb_cap) {
     if (e->hb_h) cudaFreeHost(e->hb_h);
     if (e->hb_d) cudaFree(e->hb_d);
@@ -932,13 +1070,19 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
     if (pad) memset(e->hb_h + o_data + cur + len, 0, pad);
     cur += len + pad;
   }
+  // message ids by descending block count, staged behind the lengths
+  uint32_t *ord = reinterpret_cast<uint32_t *>(e->hb_h + o_ord);
+  for (uint32_t i = 0; i < n; i++) ord[i] = i;
+  std::stable_sort(ord, ord + n, [&](uint32_t a, uint32_t b) { return (sl[a] + 8) / 64 > (sl[b] + 8) / 64; });
   CK(cudaMemcpyAsync(e->hb_d, e->hb_h, o_data + data, cudaMemcpyHostToDevice, e->sh));
   const uint8_t *db = e->hb_d + o_data;
   const uint64_t *doff = reinterpret_cast<const uint64_t *>(e->hb_d + o_off);
   const uint32_t *dlen = reinterpret_cast<const uint32_t *>(e->hb_d + o_len);
+  const uint32_t *dord = reinterpret_cast<const uint32_t *>(e->hb_d + o_ord);
   char *dout = reinterpret_cast<char *>(e->hb_d + o_out);
-  if (n <= (uint32_t)e->sm_count * 4 * 32) k_hash2<1, 0><<<(n + 31) / 32, 32, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout, 1u);
-  else k_hash2<4, 1><<<(n + 127) / 128, 128, 0, e->sh>>>(db, doff, dlen, nullptr, n, dout, 1u);
+  const uint32_t ngroups = (n + 31) / 32;
+  if (ngroups <= (uint32_t)e->sm_count * 4) k_hash3<1, 0><<<std::min<uint32_t>(ngroups, (uint32_t)e->sm_count * 2), 64, sizeof(H3Smem), e->sh>>>(db, doff, dlen, dord, n, dout);
+  else k_hash2<4, 1><<<std::min<uint32_t>((n + 127) / 128, (uint32_t)e->sm_count * 4), 128, 0, e->sh>>>(db, doff, dlen, dord, n, dout, 1u);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->hb_h + o_out, dout, 32 * (size_t)n, cudaMemcpyDeviceToHost, e->sh));
   CK(cudaStreamSynchronize(e->sh));

@@ -27,4 +27,5 @@
 #include "kr_bucket.cuh"
 #include "kr_decide.cuh"
 #include "kr_emit.cuh"
+#include "kr_bucket2.cuh"
 #include "kr_hash.cuh"

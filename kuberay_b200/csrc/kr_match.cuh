@@ -28,20 +28,24 @@ __global__ void __launch_bounds__(256) k_clear(ClearArgs a) {
 
 __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, ResDev r, Sizes n) {
   KR_TL(0);
+  pdl_trigger();  // the match kernel's CTAs may be scheduled now: they load their pod columns, then wait for this grid to finish
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n.n_clusters) {
     uint32_t ns = s.c_ns_id[t], name = s.c_name_id[t];
     uint32_t i = hash_pair(ns, name) & sc.cl_mask;
-    unsigned long long *slots = reinterpret_cast<unsigned long long *>(sc.cl_slots);  // [2*i] = key (x = name, y = ns), [2*i+1] low word = idx
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(sc.cl_slots);  // [2*i] = key (x = name, y = ns), [2*i+1] = payload
     const unsigned long long kk = ((unsigned long long)ns << 32) | name;
-    while (true) {
-      unsigned long long prev = atomicCAS(&slots[2 * (size_t)i], KR_EMPTY64, kk);
-      if (prev == KR_EMPTY64 || prev == kk) { atomicMin(reinterpret_cast<uint32_t *>(&slots[2 * (size_t)i + 1]), t); break; }  // duplicate (ns,name): lowest index wins
-      i = (i + 1) & sc.cl_mask;
-    }
     uint32_t g0 = s.c_group_off[t], G = s.c_group_cnt[t], mh = 0;
     for (uint32_t gi = 0; gi < G; gi++) mh |= (s.g_num_hosts[g0 + gi] > 1) ? 1u : 0u;
-    sc.cl_rec[t] = make_uint4(g0, G, G ? s.g_name_id[g0] : 0u, mh);  // .w bit 0: some worker group has numOfHosts > 1
+    const uint32_t gname0 = G ? s.g_name_id[g0] : 0u;
+    // payload = {z: name id of group 0, w: idx << 2 | flags} as one 64-bit word whose high half orders by cluster index
+    const unsigned long long payload = ((unsigned long long)((t << 2) | (G > 1 ? KR_CL_MULTI : 0u) | mh) << 32) | gname0;
+    while (true) {
+      unsigned long long prev = atomicCAS(&slots[2 * (size_t)i], KR_EMPTY64, kk);
+      if (prev == KR_EMPTY64 || prev == kk) { atomicMin(&slots[2 * (size_t)i + 1], payload); break; }  // duplicate (ns,name): lowest index wins, with its own payload
+      i = (i + 1) & sc.cl_mask;
+    }
+    sc.cl_rec[t] = make_uint4(g0, G, gname0, mh);  // .w bit 0: some worker group has numOfHosts > 1
     return;
   }
   t -= n.n_clusters;
@@ -53,7 +57,9 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
     for (uint32_t w = 0; w < cnt; w++) {
       uint32_t e = off + w;
       uint64_t k = key2(ns, s.w_name_id[e]);
-      uint32_t i = hash_pair(ns, s.w_name_id[e]) & sc.wt_mask;
+      const uint32_t hk = hash_pair(ns, s.w_name_id[e]);
+      atomicOr(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5], 1u << (hk & 31));  // Bloom bit: k_match2 probes the table only for pods whose bit is set
+      uint32_t i = hk & sc.wt_mask;
       while (true) {
         unsigned long long prev = atomicCAS((unsigned long long *)&sc.wt_keys[i], KR_EMPTY64, k);
         if (prev == KR_EMPTY64 || prev == k) {
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match(SnapDev s, ScratchDev sc
       uint4 q = sl[it];
       uint32_t i = pi[it];
       while (true) {
-        if (q.x == cn[it] && q.y == ns[it]) { c[it] = q.z; break; }
+        if (q.x == cn[it] && q.y == ns[it]) { c[it] = q.w >> 2; break; }
         if (q.x == KR_EMPTY32 && q.y == KR_EMPTY32) break;
         i = (i + 1) & sc.cl_mask;
         q = __ldg(&sc.cl_slots[i]);

@@ -228,9 +228,10 @@ class Engine:
         res.sorted_pod_idx = _np_view(view.sorted_pod_idx, np.uint32, s.n_pods if view.sorted_pod_idx else 0)
         res.sorted_action = _np_view(view.sorted_action, np.uint8, s.n_pods if view.sorted_action else 0)
         res.act_start = _np_view(view.act_start, np.uint32, s.n_clusters + 1)
-        res.act_pod_idx = _np_view(view.act_pod_idx, np.uint32, view.n_actions)
-        res.act_code = _np_view(view.act_code, np.uint8, view.n_actions)
-        res.create_idx = _np_view(view.create_idx, np.int32, view.n_create_total)
+        res.act_cnt = _np_view(view.act_cnt, np.uint32, s.n_clusters)
+        res.act_pod_idx = _np_view(view.act_pod_idx, np.uint32, view.act_extent)
+        res.act_code = _np_view(view.act_code, np.uint8, view.act_extent)
+        res.create_idx = _np_view(view.create_idx, np.int32, view.create_extent)
         res.jobs = _np_view(view.jobs, abi.job_result_dtype, s.n_jobs)
         res.n_create_total, res.n_orphans, res.n_actions = view.n_create_total, view.n_orphans, view.n_actions
         if copy:

@@ -159,7 +159,7 @@ class RayClusterReconciler:
         cluster = cl.clusters[(ns, cname)]
         # the compact action list: only the pods this cluster must act on, in List order (what a shim running with
         # kr_flags.fetch_pod_lists = 0 downloads; the full sorted_pod_idx / sorted_action lists are not needed here)
-        listed = [(int(res.act_pod_idx[i]), int(res.act_code[i])) for i in range(int(res.act_start[ci]), int(res.act_start[ci + 1]))]
+        listed = [(int(res.act_pod_idx[i]), int(res.act_code[i])) for i in range(int(res.act_start[ci]), int(res.act_start[ci]) + int(res.act_cnt[ci]))]
         ev = cl.events.append
         path = int(cr["path"])
         if path == abi.PATH_SKIPPED:

@@ -936,6 +936,7 @@ static int ctx_run(kr_oracle_ctx *cx, const kr_flags *f, kr_oracle_out *out, int
       }
     }
     out->act_start[Nc] = na;
+    for (uint32_t c = 0; c < Nc; c++) out->act_cnt[c] = out->act_start[c + 1] - out->act_start[c];
     out->n_orphans = x->cl_start[Nc + 1] - x->cl_start[Nc] - n_tomb;  /* free rows sit in the orphans' segment but are not orphans */
     out->n_actions = n_actions;
   }

@@ -43,6 +43,7 @@ typedef struct kr_oracle_out {
   int32_t           *create_idx; /* [create_cap] */
   kr_job_result     *jobs;       /* [n_jobs] */
   uint32_t          *act_start;  /* [n_clusters + 1] */
+  uint32_t          *act_cnt;    /* [n_clusters] */
   uint32_t          *act_pod_idx;/* [n_pods] capacity */
   uint8_t           *act_code;   /* [n_pods] capacity */
   uint32_t create_cap;

@@ -8,17 +8,39 @@ from kuberay_b200.engine import Engine
 pytestmark = pytest.mark.gpu
 
 
+def _compact(flags):
+    """The same switches with kr_flags.fetch_pod_lists = 0: the pass takes the bucket pipeline (kr_bucket2.cuh) when the snapshot
+    qualifies and the sort / radix pipeline otherwise; only the compact results come back."""
+    f = abi.kr_flags.from_buffer_copy(flags)
+    f.fetch_pod_lists = 0
+    return f
+
+
 def _parity(snap, flags, oracle_mod, **kw):
+    """Engine vs oracle, twice: with the full pod lists (sort / radix pipeline) and without (bucket pipeline)."""
     eng = Engine.for_snapshot(snap, **kw)
     try:
         eng.load(snap)
         got = eng.reconcile(flags)
+        lean = eng.reconcile(_compact(flags))
     finally:
         eng.close()
     want = oracle_mod.run(snap, flags, threads=8)
     d = want.diff(got)
     assert not d, "\n".join(d[:20])
+    d = want.diff(lean)
+    assert not d, "compact results (fetch_pod_lists = 0):\n" + "\n".join(d[:20])
+    assert lean.sorted_pod_idx.size == 0
     return got
+
+
+def _kernels(snap, flags):
+    eng = Engine.for_snapshot(snap)
+    try:
+        eng.load(snap)
+        return [k for k, _ in eng.reconcile_profiled(flags)["kernels"]]
+    finally:
+        eng.close()
 
 
 @pytest.mark.parametrize("cfg", ["C1", "C2"])
@@ -197,9 +219,48 @@ def test_compact_action_list_without_pod_lists(oracle_mod):
     assert not want.diff(got)
     # the list is exactly the non-KEEP entries of the full lists, cluster by cluster
     keep = (want.sorted_action != abi.ACT_KEEP) & (want.sorted_action != abi.ACT_ORPHAN)
-    assert np.array_equal(got.act_pod_idx, want.sorted_pod_idx[keep]) and np.array_equal(got.act_code, want.sorted_action[keep])
-    assert np.array_equal(np.diff(got.act_start.astype(np.int64)), np.add.reduceat(keep.astype(np.int64), want.clusters["pod_start"].astype(np.int64))
+    own = abi._gather_owned(got.act_start[:-1], got.act_cnt)  # cluster c owns [act_start[c], act_start[c] + act_cnt[c])
+    assert np.array_equal(got.act_pod_idx[own], want.sorted_pod_idx[keep]) and np.array_equal(got.act_code[own], want.sorted_action[keep])
+    assert np.array_equal(got.act_cnt.astype(np.int64), np.add.reduceat(keep.astype(np.int64), want.clusters["pod_start"].astype(np.int64))
                           if snap.dims["clusters"] else [])
+    # RayClusters whose Recreate gate waited for the digest reserved their whole bucket: the list's extent is at least the count
+    assert got.act_start[-1] >= got.n_actions and (np.diff(got.act_start.astype(np.int64)) >= got.act_cnt).all()
+
+
+def test_bucket_pipeline_is_taken_and_widens_its_stride(oracle_mod):
+    """fetch_pod_lists = 0 on a qualifying snapshot runs k_match2 + k_decide2 and nothing of the sort pipeline.  A RayCluster
+    larger than the first stride voids the attempt: the engine widens the stride (64 -> 128 -> 256), then leaves for the sort
+    pipeline (here: a 300-pod cluster), every time bit-exact."""
+    snap, flags = synthetic.generate(synthetic.config("C3"))
+    names = _kernels(snap, _compact(flags))
+    assert {"k_match2", "k_decide2", "k_hash"} <= set(names) and not any(k.startswith(("k_place", "k_creates", "k_decide_small")) for k in names)
+    names = _kernels(snap, flags)
+    assert "k_match2" not in names and "k_decide_small" in names
+    for big in (100, 200, 300):
+        # 300 RayClusters x 20 pods; the pods of clusters 1 .. k are relabelled into cluster 0 (same namespace), which then
+        # lists `big` pods (and several heads), while clusters 1 .. k list none
+        both, f = synthetic.generate(synthetic.SynthParams(n_clusters=300, pods_per_cluster=20, groups=1))
+        k = big // 20 - 1
+        moved = np.isin(both.p_cluster_name_id, both.c_name_id[1:k + 1])
+        both.p_cluster_name_id[moved] = both.c_name_id[0]
+        _parity(both, f, oracle_mod)
+        names = _kernels(both, _compact(f))   # (a fresh engine starts at the narrow stride again and ends where the ladder ends)
+        assert ("k_match2" in names) == (big <= 256), (big, names)
+
+
+def test_bucket_pipeline_long_delete_prefix_and_delete_all(oracle_mod):
+    """The ordered pieces of k_decide2 off their common path: scale-downs by tens of pods (counting rank instead of the
+    min-extraction), whole-cluster deletions (suspension, Recreate: action list = the sorted bucket), three worker groups."""
+    params = synthetic.SynthParams(n_clusters=600, pods_per_cluster=90, groups=3, suspended_frac=0.1, recreate_frac=0.3, autoscaling_frac=0.2)
+    snap, flags = synthetic.generate(params)
+    rng = np.random.default_rng(5)
+    shrink = rng.random(snap.dims["groups"]) < 0.5
+    snap.g_replicas[shrink] = rng.integers(0, 8, int(shrink.sum()))
+    snap.g_min[shrink] = 0
+    snap.g_flags[shrink] &= ~np.uint32(abi.GF_REPLICAS_NIL | abi.GF_MIN_NIL)
+    flags.env_random_pod_delete = 1
+    got = _parity(snap, flags, oracle_mod)
+    assert (got.groups["diff"] < -8).sum() > 50 and (got.clusters["path"] == abi.PATH_RECREATE_DELETE_ALL).sum() > 5
 
 
 def test_hash_batch_matches_hashlib():
@@ -247,10 +308,13 @@ def test_fuzz_adversarial_snapshots(seed0, oracle_mod, monkeypatch):
         try:
             eng.load(snap)
             got = eng.reconcile(flags)
+            lean = eng.reconcile(_compact(flags))
         finally:
             eng.close()
         d = want.diff(got)
         assert not d, (seed, d[:8])
+        d = want.diff(lean)
+        assert not d, ("compact", seed, d[:8])
     monkeypatch.setenv("KR_FORCE_RADIX", "1")
     monkeypatch.setenv("KR_NO_FUSE", "1")
     for seed in range(seed0, seed0 + 100, 4):

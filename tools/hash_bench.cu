@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../kuberay_b200/csrc/kr_kernels.cuh"
@@ -47,6 +48,16 @@ int main(int argc, char **argv) {
   std::vector<char> want(32 * (size_t)n), got(32 * (size_t)n);
   for (uint32_t i = 0; i < n; i++) kr_oracle_hash32(bytes.data() + off[i], len[i], &want[32 * (size_t)i]);
 
+  // message ids by descending block count (what the engine's commit builds from c_json_len)
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (len[a] + 8) / 64 > (len[b] + 8) / 64; });
+  uint32_t *d_order;
+  CKC(cudaMalloc(&d_order, 4 * (size_t)n));
+  CKC(cudaMemcpy(d_order, order.data(), 4 * (size_t)n, cudaMemcpyHostToDevice));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const uint32_t ngroups = (n + 31) / 32;
   uint8_t *d_bytes; uint64_t *d_off; uint32_t *d_len; char *d_out; void *flush;
   size_t flush_bytes = 512ull << 20;
   CKC(cudaMalloc(&d_bytes, bytes.size())); CKC(cudaMalloc(&d_off, 8 * (n + 1))); CKC(cudaMalloc(&d_len, 4 * n)); CKC(cudaMalloc(&d_out, 32 * (size_t)n));
@@ -62,7 +73,38 @@ int main(int argc, char **argv) {
     CKC(cudaMemset(d_out, 0, 32 * (size_t)n));
   };
   printf("n=%u messages, %.1f MB\n", n, total / 1e6);
+  CKC(cudaFuncSetAttribute(k_hash3<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(H3Smem)));
 #define RUN(NAME, ...) { float us = time_it([&]() { __VA_ARGS__; }, flush, flush_bytes, 20); CKC(cudaGetLastError()); check(NAME, us); }
+  for (int per_sm : {1, 2, 4, 6}) {
+    const uint32_t G = std::min<uint32_t>(ngroups, (uint32_t)(sms * per_sm));
+    char nm[64];
+    snprintf(nm, sizeof nm, "k_hash3<1> sorted %d CTA/SM", per_sm);
+    RUN(nm, (k_hash3<1, 0><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    snprintf(nm, sizeof nm, "k_hash3<1> unsorted %d CTA/SM", per_sm);
+    RUN(nm, (k_hash3<1, 0><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
+  }
+  for (int per_sm : {1, 2, 3}) {
+    const uint32_t G = std::min<uint32_t>((ngroups + 1) / 2, (uint32_t)(sms * per_sm));
+    char nm[64];
+    snprintf(nm, sizeof nm, "k_hash3<2> sorted %d CTA/SM", per_sm);
+    RUN(nm, (k_hash3<2, 0><<<G, 128, 2 * sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+  }
+  {  // each side alone (results are wrong by construction): which warp bounds a block?
+    const uint32_t G = std::min<uint32_t>(ngroups, (uint32_t)sms);
+    RUN("k_hash3<1> 1/SM producer only", (k_hash3<1, 1><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 1/SM consumer only", (k_hash3<1, 2><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 1/SM both", (k_hash3<1, 0><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 1/SM hand-offs only", (k_hash3<1, 3><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 1/SM no hand-offs", (k_hash3<1, 4><<<G, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    const uint32_t G2 = std::min<uint32_t>(ngroups, (uint32_t)sms * 2);
+    RUN("k_hash3<1> 2/SM hand-offs only", (k_hash3<1, 3><<<G2, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 2/SM no hand-offs", (k_hash3<1, 4><<<G2, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 2/SM producer only", (k_hash3<1, 1><<<G2, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+    RUN("k_hash3<1> 2/SM consumer only", (k_hash3<1, 2><<<G2, 64, sizeof(H3Smem)>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+  }
+  RUN("k_hash2<1,0> sorted", (k_hash2<1, 0><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+  RUN("k_hash2<4,1> sorted", (k_hash2<4, 1><<<(n + 127) / 128, 128>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
+  RUN("k_hash2<4,1> sorted 2CTA/SM", (k_hash2<4, 1><<<std::min<uint32_t>((n + 127) / 128, sms * 2), 128>>>(d_bytes, d_off, d_len, d_order, n, d_out)));
   RUN("k_hash2<1,0> cpasync", (k_hash2<1, 0><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<1,1> cpasync+mad", (k_hash2<1, 1><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
   RUN("k_hash2<1,5> fma: w+K", (k_hash2<1, 5><<<(n + 31) / 32, 32>>>(d_bytes, d_off, d_len, nullptr, n, d_out)));
