@@ -478,6 +478,28 @@ int kr_group_results_device(kr_engine *e, const void **dev_ptr, uint64_t *bytes)
  * torch.distributed.all_gather over NCCL); synchronises the engine stream before returning. */
 int kr_group_results_copy(kr_engine *e, void *dst_device, uint64_t dst_capacity_bytes);
 
+/* ---- spec JSON: the step BEFORE the hash, host code (no device needed).
+ * Canonical bytes of json.Marshal(mute(RayClusterSpec)) — what utils.GenerateHashWithoutReplicasAndWorkersToDelete hashes
+ * (ray-operator/controllers/ray/utils/util.go:642-665, types apis/ray/v1/raycluster_types.go:13-225) — from the spec as JSON
+ * text in any key order (e.g. `.spec` of the watch event, whose keys the API server sorts alphabetically).  Replaces the
+ * per-reconcile DeepCopy + reflective json.Marshal of the reference: the shim calls it once per metadata.generation.
+ * flags: KR_SPEC_JSON_UNMUTED = plain json.Marshal(spec) without the muting (utils.GenerateJsonHash callers).
+ * Returns KR_E_INVALID on malformed input, KR_E_CAPACITY (with *out_len = the size needed) when out is too small. */
+enum { KR_SPEC_JSON_UNMUTED = 1 };
+int kr_spec_json_emit(const uint8_t *spec_json, uint64_t len, uint32_t flags, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
+/* Same, written straight into a JSON arena (kr_snapshot_bufs.json): the bytes go to the next 16-byte aligned offset at or after
+ * *cursor, zero-padded to 16 bytes; *off_out / *len_out are the values for c_json_off / c_json_len; *cursor moves past them. */
+int kr_spec_json_emit_arena(const uint8_t *spec_json, uint64_t len, uint8_t *arena, uint64_t arena_cap, uint64_t *cursor,
+                            uint64_t *off_out, uint32_t *len_out);
+
+/* resource.Quantity's canonical string ("1000m" -> "1", "1.5Gi" -> "1536Mi", "0.5" -> "500m"; k8s.io/apimachinery
+ * pkg/api/resource Quantity.String), NUL-terminated into out.  Used by the emitter for ResourceList values. */
+int kr_quantity_canonical(const char *text, char *out, uint64_t out_cap);
+
+/* Error text of the last failing kr_spec_json_* / kr_quantity_canonical call on this thread (never NULL). */
+const char *kr_spec_json_last_error(void);
+
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);
 

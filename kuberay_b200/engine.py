@@ -27,7 +27,7 @@ class EngineError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile libkrengine.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc")
-    deps = [os.path.join(src, f) for f in os.listdir(src) if f.endswith((".cu", ".cuh"))] + [os.path.join(_HERE, "..", "include", "kr_engine.h")]
+    deps = [os.path.join(src, f) for f in os.listdir(src) if f.endswith((".cu", ".cuh", ".cpp"))] + [os.path.join(_HERE, "..", "include", "kr_engine.h")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if stale:
         subprocess.check_call(["make", "-s", "-C", src, "-B", "NVCCFLAGS=-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC"])
@@ -62,10 +62,40 @@ def lib() -> C.CDLL:
         L.kr_last_error.argtypes = [C.c_void_p]
         L.kr_last_error.restype = C.c_char_p
         L.kr_algorithmic_bytes.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
+        L.kr_spec_json_emit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, P(C.c_uint64)]
+        L.kr_spec_json_emit_arena.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_uint64), P(C.c_uint32)]
+        L.kr_quantity_canonical.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
+        L.kr_spec_json_last_error.restype = C.c_char_p
         for name in abi.ENGINE_SYMBOLS:
             getattr(L, name)  # raises AttributeError if the header and the library drifted apart
         _LIB = L
     return _LIB
+
+
+def spec_json_emit(spec_json: bytes, muted: bool = True) -> bytes:
+    """kr_spec_json_emit: canonical json.Marshal(mute(spec)) bytes of a RayClusterSpec given as JSON text (host code, no GPU)."""
+    L = lib()
+    need = C.c_uint64()
+    cap = 2 * len(spec_json) + 256
+    for _ in range(2):
+        out = C.create_string_buffer(cap)
+        rc = L.kr_spec_json_emit(spec_json, len(spec_json), 0 if muted else abi.SPEC_JSON_UNMUTED, out, cap, C.byref(need))
+        if rc == abi.KR_E_CAPACITY:
+            cap = need.value
+            continue
+        if rc != 0:
+            raise EngineError(rc, L.kr_spec_json_last_error().decode())
+        return out.raw[:need.value]
+    raise EngineError(abi.KR_E_CAPACITY, "kr_spec_json_emit: output does not fit")
+
+
+def quantity_canonical(text: str) -> str:
+    L = lib()
+    out = C.create_string_buffer(128)
+    rc = L.kr_quantity_canonical(text.encode(), out, 128)
+    if rc != 0:
+        raise EngineError(rc, L.kr_spec_json_last_error().decode())
+    return out.value.decode()
 
 
 def _np_view(ptr: int, dtype, count: int) -> np.ndarray:

@@ -259,15 +259,22 @@ class PackMeta:
     flags: abi.kr_flags | None = None
 
 
+def spec_hash_input(spec: dict) -> bytes:
+    """The bytes GenerateHashWithoutReplicasAndWorkersToDelete hashes (utils/util.go:642-665): json.Marshal(mute(spec)), from
+    the native emitter behind the C ABI (kr_spec_json_emit; host code of libkrengine.so, no device needed)."""
+    import json
+
+    from . import engine
+    return engine.spec_json_emit(json.dumps(spec or {}).encode("utf-8"))
+
+
 def pack_objects(clusters: list[dict], pods: list[dict], jobs: list[dict] | None = None, interner: Interner | None = None,
                  kuberay_version: str = KUBERAY_VERSION, spec_json=None) -> tuple[Snapshot, PackMeta]:
     """Pack object-level RayClusters / Pods / RayJobs (plain dicts, see tests/golden/README.md) into a Snapshot.
 
-    `spec_json(cluster) -> bytes` supplies the muted-spec JSON (production: Go json.Marshal). Default: cluster["specJson"]
-    if present else the test canonicalizer kuberay_b200.specjson.muted_spec_json(cluster["spec"]).
+    `spec_json(cluster) -> bytes` supplies the muted-spec JSON. Default: cluster["specJson"] if present (bytes marshalled by
+    the Go side), else the native emitter (spec_hash_input: kr_spec_json_emit over cluster["spec"]).
     """
-    from . import specjson
-
     it = interner or Interner()
     jobs = jobs or []
     n_groups = sum(len((c.get("spec") or {}).get("workerGroupSpecs") or []) for c in clusters)
@@ -281,7 +288,7 @@ def pack_objects(clusters: list[dict], pods: list[dict], jobs: list[dict] | None
         elif "specJson" in c:
             b = c["specJson"].encode() if isinstance(c["specJson"], str) else bytes(c["specJson"])
         else:
-            b = specjson.muted_spec_json(c.get("spec") or {})
+            b = spec_hash_input(c.get("spec") or {})
         blobs.append(b)
     json_bytes = sum(_align16(len(b)) for b in blobs)
     s = Snapshot(len(clusters), n_groups, n_wtd, len(pods), len(head_rows), len(jobs), json_bytes)

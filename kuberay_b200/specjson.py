@@ -1,8 +1,8 @@
-"""Muted-spec JSON for the RayCluster spec hash — TEST/HARNESS canonicalizer.
+"""Muted-spec JSON for the RayCluster spec hash — TEST canonicalizer (an independent restatement used to cross-check the
+native emitter kuberay_b200/csrc/kr_specjson.cpp, which is what the product path calls: include/kr_engine.h kr_spec_json_emit).
 
-In production the hash input is produced by Go: json.Marshal of the muted RayClusterSpec
-(ray-operator/controllers/ray/utils/util.go:629,642-661) and handed to the engine as bytes; the GPU does
-SHA-1 + base32hex only.  This module restates the muting (util.go:645-661) and the Go encoding/json rules of
+The hash input is json.Marshal of the muted RayClusterSpec (ray-operator/controllers/ray/utils/util.go:629,642-661); the GPU
+does SHA-1 + base32hex.  This module restates the muting (util.go:645-661) and the Go encoding/json rules of
 SURVEY.md Appendix B for the subset of fields the fixtures / synthetic generator emit, so that the reference's
 *relational* hash tests (rayservice_controller_unit_test.go:39-97) can be replayed.  Literal digest parity with Go
 is unpinned in the reference (no golden digest exists in its tree); nested corev1 structs are emitted in the
@@ -81,11 +81,15 @@ def _enc(v, key: str | None = None) -> str:
     raise TypeError(type(v))
 
 
+# pointer-typed fields (*bool / *int32 / *string): omitempty drops them only when nil — `"suspend":false` stays
+_POINTER_FIELDS = {"suspend", "managedBy", "enableInTreeAutoscaling", "enableIngress", "idleTimeoutSeconds", "replicas"}
+
+
 def _struct(obj: dict, fields, enc_field) -> str:
     parts = []
     for name, omitempty in fields:
         v = obj.get(name)
-        if omitempty and _is_empty(v):
+        if omitempty and (v is None if name in _POINTER_FIELDS else _is_empty(v)):
             continue
         parts.append(_enc_str(name) + ":" + enc_field(name, v))
     return "{" + ",".join(parts) + "}"

@@ -122,13 +122,12 @@ def test_terminated_head_restart_policy(backend):
 @pytest.mark.parametrize("case", load("recreate_upgrade")["cases"], ids=lambda c: c["name"])
 def test_should_recreate_pods_for_upgrade(case, backend):
     """TestShouldRecreatePodsForUpgrade raycluster_controller_unit_test.go:3680-3814"""
-    from kuberay_b200 import specjson
     import base64
     import hashlib
     cluster = copy.deepcopy(SC["base"]["cluster"])
     cluster["spec"]["upgradeStrategy"] = case["upgradeStrategy"]
     cluster["spec"]["workerGroupSpecs"][0]["workersToDelete"] = []
-    current = base64.b32hexencode(hashlib.sha1(specjson.muted_spec_json(cluster["spec"])).digest()).decode()
+    current = base64.b32hexencode(hashlib.sha1(snapmod.spec_hash_input(cluster["spec"])).digest()).decode()
     pods = []
     if case["head"] is not None:
         hp = copy.deepcopy(SC["base"]["pods"][0])

@@ -19,13 +19,14 @@ import torch  # noqa: E402
 from kuberay_b200 import synthetic  # noqa: E402
 from kuberay_b200.engine import Engine, lib  # noqa: E402
 
-NAMES = {10: "  creates: scans done", 11: "  creates: fills done", 9: "k_clear", 0: "k_build_tables", 1: "k_match", 2: "k_place_fused", 3: "k_decide_small", 4: "k_decide<general>", 5: "k_decide<phase 1>", 12: "k_decide_small<ph 1>",
-         6: "k_creates_fused", 7: "k_hash2", 8: "k_jobs"}
+NAMES = {10: "  creates: scans done", 11: "  creates: fills done", 9: "k_clear", 0: "k_build_tables", 1: "k_match / k_match2", 2: "k_place_fused", 3: "k_decide_small / k_decide2", 4: "k_decide<general>", 5: "k_decide<phase 1>",
+         12: "decide phase 1 (small / k_decide2)", 6: "k_creates_fused", 7: "k_hash", 8: "k_jobs"}
 
 
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "C3"
     snap, flags = synthetic.generate(synthetic.config(wl))
+    flags.fetch_pod_lists = int(os.environ.get("TL_POD_LISTS", "0"))  # 0: production configuration (bucket pipeline)
     flags.skip_hash = int(os.environ.get("TL_SKIP_HASH", "0"))
     eng = Engine.for_snapshot(snap)
     eng.load(snap)
@@ -49,7 +50,7 @@ def main():
     print(f"{wl}: pass {tot / reps:.1f} us (CUDA events)")
     for k in sorted(NAMES, key=lambda k: acc[k, 0] if acc[k, 1] else 1e18):
         if acc[k, 1]:
-            print(f"  {NAMES[k]:20s} start {acc[k, 0]:7.1f} us   end {acc[k, 1]:7.1f} us   ({acc[k, 1] - acc[k, 0]:6.1f} us)")
+            print(f"  {NAMES[k]:36s} start {acc[k, 0]:7.1f} us   end {acc[k, 1]:7.1f} us   ({acc[k, 1] - acc[k, 0]:6.1f} us)")
     eng.close()
 
 
