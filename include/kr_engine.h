@@ -458,6 +458,26 @@ int kr_results_fetch(kr_engine *e, kr_results_view *out);
  * also used by rayservice_controller.go:1130-1157,1244 callers.  Host buffers; copies included. */
 int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, uint32_t n, char *out32xN);
 
+/* Batched isClusterSpecHashEqual (rayservice_controller.go:1130-1157; callers :1121-1127, :1179-1186 and the rollback check
+ * :2064-2094): for every row, does the RayCluster's ray.io/hash-without-replicas-and-workers-to-delete annotation equal the hash
+ * of the RayService's goal spec?  The goal specs are canonicalised on the host (kr_spec_json_emit) and hashed in ONE GPU batch.
+ *   partial == 0: goal hash = hash(mute(goal spec)); a goal spec that does not parse hashes to "" (the reference drops the error).
+ *   partial != 0: n = strconv.Atoi(num-worker-groups annotation); failure => equal (the reference returns true); with at least n
+ *                 goal worker groups the hash is taken over the first n only, with fewer the goal hash stays "" (:1143-1153).
+ *                 (A negative n panics in the reference — slice bounds; here it counts as an Atoi failure.)
+ * equal_out[i] = 1 / 0; goal_hash_out32xN (optional) receives the 32 characters of every goal hash, zero bytes when it is "". */
+typedef struct kr_hash_compare_row {
+  const uint8_t *goal_spec_json;      /* RayService .spec.rayClusterSpec as JSON text, any key order */
+  uint64_t       goal_spec_len;
+  const char    *cluster_hash;        /* the annotation's value; NULL / len 0 when absent */
+  uint32_t       cluster_hash_len;
+  const char    *num_worker_groups;   /* annotation ray.io/num-worker-groups (only read when partial) */
+  uint32_t       num_worker_groups_len;
+  uint8_t        partial;
+  uint8_t        reserved_[7];
+} kr_hash_compare_row;
+int kr_hash_compare_batch(kr_engine *e, const kr_hash_compare_row *rows, uint32_t n, uint8_t *equal_out, char *goal_hash_out32xN);
+
 /* Timings of the last batch. */
 int kr_last_profile(kr_engine *e, kr_profile *prof);
 

@@ -163,6 +163,11 @@ class kr_results_view(C.Structure):
                 ("create_extent", C.c_uint32), ("act_extent", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class kr_hash_compare_row(C.Structure):
+    _fields_ = [("goal_spec_json", C.c_char_p), ("goal_spec_len", C.c_uint64), ("cluster_hash", C.c_char_p), ("cluster_hash_len", C.c_uint32),
+                ("num_worker_groups", C.c_char_p), ("num_worker_groups_len", C.c_uint32), ("partial", C.c_uint8), ("reserved_", C.c_uint8 * 7)]
+
+
 class kr_profile(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernels_ms", C.c_float), ("d2h_ms", C.c_float), ("n_kernels", C.c_uint32),
                 ("kernel_ms", C.c_float * MAX_KERNEL_TIMES), ("kernel_name", C.c_char_p * MAX_KERNEL_TIMES),
@@ -181,7 +186,7 @@ ENGINE_SYMBOLS = [
     "kr_device_count", "kr_engine_create", "kr_engine_destroy", "kr_snapshot_begin", "kr_snapshot_commit", "kr_snapshot_commit_parts", "kr_snapshot_commit_pod_rows", "kr_snapshot_commit_pod_values", "kr_engine_set_option",
     "kr_reconcile_batch", "kr_reconcile_device_only", "kr_reconcile_batch_profiled", "kr_results_fetch",
     "kr_hash_batch", "kr_last_profile", "kr_group_results_device", "kr_group_results_copy", "kr_last_error", "kr_algorithmic_bytes",
-    "kr_spec_json_emit", "kr_spec_json_emit_arena", "kr_quantity_canonical", "kr_spec_json_last_error",
+    "kr_spec_json_emit", "kr_spec_json_emit_arena", "kr_quantity_canonical", "kr_spec_json_last_error", "kr_hash_compare_batch",
 ]
 
 

@@ -20,6 +20,9 @@
 
 using namespace kr;
 
+// kr_specjson.cpp
+int kr_specjson_emit_string(const uint8_t *spec_json, uint64_t len, bool muted, long max_groups, std::string &out, long *n_groups);
+
 namespace {
 
 constexpr size_t kAlign = 256;
@@ -1087,6 +1090,63 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
   CK(cudaMemcpyAsync(e->hb_h + o_out, dout, 32 * (size_t)n, cudaMemcpyDeviceToHost, e->sh));
   CK(cudaStreamSynchronize(e->sh));
   memcpy(out32xN, e->hb_h + o_out, 32 * (size_t)n);
+  return KR_OK;
+}
+
+// strconv.Atoi: optional sign, decimal digits only, no spaces / underscores, must fit an int
+static bool go_atoi(const char *t, uint32_t len, long long &v) {
+  if (!t || len == 0 || len > 19) return false;
+  uint32_t i = 0;
+  bool neg = false;
+  if (t[0] == '+' || t[0] == '-') { neg = t[0] == '-'; i = 1; }
+  if (i >= len) return false;
+  v = 0;
+  for (; i < len; i++) { if (t[i] < '0' || t[i] > '9') return false; v = v * 10 + (t[i] - '0'); }
+  if (neg) v = -v;
+  return true;
+}
+
+int kr_hash_compare_batch(kr_engine *e, const kr_hash_compare_row *rows, uint32_t n, uint8_t *equal_out, char *goal_hash_out32xN) {
+  if (!e || (!rows && n) || (!equal_out && n)) return KR_E_INVALID;
+  if (goal_hash_out32xN) memset(goal_hash_out32xN, 0, 32 * (size_t)n);
+  // 1. goal specs -> canonical muted JSON (host), rows that need no hash are settled here
+  std::vector<int32_t> msg_of(n, -1);  // row -> message index, -1 = goal hash is ""
+  std::string blob;
+  std::vector<uint64_t> offs{0};
+  for (uint32_t i = 0; i < n; i++) {
+    const kr_hash_compare_row &r = rows[i];
+    equal_out[i] = 2;  // undecided
+    long max_groups = -1;
+    if (r.partial) {
+      long long ng = 0;
+      if (!go_atoi(r.num_worker_groups, r.num_worker_groups_len, ng) || ng < 0 || ng > 0x7FFFFFFF) { equal_out[i] = 1; continue; }  // :1140-1142
+      max_groups = (long)ng;
+    }
+    std::string js;
+    const int rc = kr_specjson_emit_string(r.goal_spec_json, r.goal_spec_len, true, max_groups, js, nullptr);
+    if (rc == KR_E_STATE) continue;                                   // fewer goal groups than the cluster has: goal hash stays ""
+    if (rc != KR_OK) { if (r.partial) equal_out[i] = 1; continue; }   // :1151-1153 / the dropped error of :1135
+    msg_of[i] = (int32_t)(offs.size() - 1);
+    blob += js;
+    offs.push_back(blob.size());
+  }
+  // 2. one GPU batch for every digest
+  const uint32_t nmsg = (uint32_t)(offs.size() - 1);
+  std::vector<char> digests(32 * (size_t)nmsg);
+  if (nmsg) {
+    int rc = kr_hash_batch(e, reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), nmsg, digests.data());
+    if (rc) return rc;
+  }
+  // 3. compare with the annotation
+  for (uint32_t i = 0; i < n; i++) {
+    if (equal_out[i] != 2) continue;
+    const kr_hash_compare_row &r = rows[i];
+    const uint32_t clen = r.cluster_hash ? r.cluster_hash_len : 0;
+    if (msg_of[i] < 0) { equal_out[i] = clen == 0; continue; }
+    const char *d = &digests[32 * (size_t)msg_of[i]];
+    if (goal_hash_out32xN) memcpy(goal_hash_out32xN + 32 * (size_t)i, d, 32);
+    equal_out[i] = clen == 32 && memcmp(r.cluster_hash, d, 32) == 0;
+  }
   return KR_OK;
 }
 

@@ -546,13 +546,24 @@ void mute(Node &spec) {
 
 thread_local std::string g_err;
 
-int emit_impl(const uint8_t *spec_json, uint64_t len, bool muted, std::string &out) {
+// max_groups >= 0: keep only the first max_groups worker groups (rayservice_controller.go:1146-1147) — when the spec has fewer, nothing
+// is emitted and KR_E_STATE comes back with *n_groups set.
+int emit_impl(const uint8_t *spec_json, uint64_t len, bool muted, std::string &out, long max_groups = -1, long *n_groups = nullptr) {
   Parser ps{reinterpret_cast<const char *>(spec_json), reinterpret_cast<const char *>(spec_json) + len, {}};
   Node root;
   if (!ps.value(root, 0)) { g_err = "kr_spec_json: parse error: " + ps.err; return KR_E_INVALID; }
   ps.ws();
   if (ps.p != ps.end) { g_err = "kr_spec_json: trailing characters after the JSON value"; return KR_E_INVALID; }
   if (root.t != N_OBJ) { g_err = "kr_spec_json: the spec must be a JSON object"; return KR_E_INVALID; }
+  {
+    Node *ws = root.get("workerGroupSpecs");
+    const long have = (ws && ws->t == N_ARR) ? (long)ws->a.size() : 0;
+    if (n_groups) *n_groups = have;
+    if (max_groups >= 0) {
+      if (have < max_groups) return KR_E_STATE;
+      if (ws && ws->t == N_ARR) ws->a.resize((size_t)max_groups);
+    }
+  }
   if (muted) mute(root);
   Emitter em;
   em.strct("RayClusterSpec", &root);
@@ -562,6 +573,11 @@ int emit_impl(const uint8_t *spec_json, uint64_t len, bool muted, std::string &o
 }
 
 }  // namespace
+
+// for kr_engine.cu (kr_hash_compare_batch): same emitter, optional truncation of the worker groups
+int kr_specjson_emit_string(const uint8_t *spec_json, uint64_t len, bool muted, long max_groups, std::string &out, long *n_groups) {
+  return emit_impl(spec_json, len, muted, out, max_groups, n_groups);
+}
 
 extern "C" {
 

@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
         L.kr_spec_json_emit_arena.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_uint64), P(C.c_uint32)]
         L.kr_quantity_canonical.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
         L.kr_spec_json_last_error.restype = C.c_char_p
+        L.kr_hash_compare_batch.argtypes = [C.c_void_p, P(abi.kr_hash_compare_row), C.c_uint32, C.c_void_p, C.c_void_p]
         for name in abi.ENGINE_SYMBOLS:
             getattr(L, name)  # raises AttributeError if the header and the library drifted apart
         _LIB = L
@@ -247,6 +248,26 @@ class Engine:
         out = np.zeros(32 * n, dtype=np.uint8)
         self._check(self._L.kr_hash_batch(self._h, blob.ctypes.data, offs.ctypes.data, n, out.ctypes.data))
         return [bytes(out[32 * i:32 * i + 32]).decode("ascii") for i in range(n)]
+
+    def hash_compare_batch(self, rows: list[tuple[bytes, str | None, str | None, bool]]) -> tuple[list[bool], list[str]]:
+        """kr_hash_compare_batch — batched isClusterSpecHashEqual (rayservice_controller.go:1130-1157).
+        rows: (goal .spec.rayClusterSpec as JSON text, cluster hash annotation, num-worker-groups annotation, partial).
+        -> (equal flags, goal hashes ("" where the reference leaves the goal hash empty))."""
+        n = len(rows)
+        arr = (abi.kr_hash_compare_row * max(n, 1))()
+        keep = []
+        for i, (spec, chash, nwg, partial) in enumerate(rows):
+            cb = chash.encode() if chash is not None else None
+            nb = nwg.encode() if nwg is not None else None
+            keep += [spec, cb, nb]
+            arr[i].goal_spec_json, arr[i].goal_spec_len = spec, len(spec)
+            arr[i].cluster_hash, arr[i].cluster_hash_len = cb, len(cb) if cb is not None else 0
+            arr[i].num_worker_groups, arr[i].num_worker_groups_len = nb, len(nb) if nb is not None else 0
+            arr[i].partial = 1 if partial else 0
+        eq = np.zeros(max(n, 1), dtype=np.uint8)
+        hs = np.zeros(32 * max(n, 1), dtype=np.uint8)
+        self._check(self._L.kr_hash_compare_batch(self._h, arr, n, eq.ctypes.data, hs.ctypes.data))
+        return [bool(x) for x in eq[:n]], [bytes(hs[32 * i:32 * i + 32]).rstrip(b"\0").decode("ascii") for i in range(n)]
 
     def _results(self, view: abi.kr_results_view, copy: bool) -> abi.Results:
         s = self.sizes

@@ -194,3 +194,61 @@ def test_emit_into_the_json_arena():
     small = np.zeros(64, dtype=np.uint8)
     cursor = C.c_uint64(0)
     assert L.kr_spec_json_emit_arena(spec, len(spec), small.ctypes.data, small.size, C.byref(cursor), C.byref(off), C.byref(ln)) == abi.KR_E_CAPACITY
+
+
+# ---------------------------------------------------------------------------------------------- f4: RayService hash comparison
+# TestIsClusterSpecHashEqual, rayservice_controller_unit_test.go:1057-1148 (table transcribed: partial, diffReplicas,
+# addNewWorkerGroup, updateClusterSpec -> expected) + the branches of isClusterSpecHashEqual the table does not reach
+# (rayservice_controller.go:1139-1153: Atoi failure => true, fewer goal groups => goal hash "").
+IS_EQUAL_TABLE = [
+    ("[full] diff replicas", False, True, False, False, True),
+    ("[full] completely identical", False, False, False, False, True),
+    ("[full] update cluster spec", False, False, False, True, False),
+    ("[partial] new worker group", True, False, True, False, True),
+    ("[partial] diff replicas + new worker group", True, True, True, False, True),
+    ("[partial] diff replicas", True, True, False, False, True),
+    ("[partial] update cluster spec", True, False, False, True, False),
+]
+
+
+@pytest.mark.gpu
+def test_hash_compare_batch_is_cluster_spec_hash_equal():
+    from kuberay_b200.engine import Engine
+    sc = json.load(open(__file__.rsplit("/", 1)[0] + "/golden/reconcile_scenarios.json"))["base"]["cluster"]["spec"]
+    sc = copy.deepcopy(sc)
+    sc["workerGroupSpecs"][0].pop("workersToDelete", None)
+    base_hash = base64.b32hexencode(hashlib.sha1(engine.spec_json_emit(json.dumps(sc).encode())).digest()).decode()
+    nwg = str(len(sc["workerGroupSpecs"]))
+    rows, want = [], []
+    for _name, partial, diff_replicas, add_group, update_spec, expected in IS_EQUAL_TABLE:
+        svc = copy.deepcopy(sc)
+        if diff_replicas:
+            svc["workerGroupSpecs"][0]["replicas"] += 1
+        if add_group:
+            svc["workerGroupSpecs"].append({"groupName": "worker-group-2", "replicas": 1})
+        if update_spec:
+            svc["rayVersion"] = "new-version"
+        rows.append((json.dumps(svc).encode(), base_hash, nwg, partial))
+        want.append(expected)
+    two = copy.deepcopy(sc); two["workerGroupSpecs"].append({"groupName": "g2"})
+    extra = [
+        ((json.dumps(sc).encode(), base_hash, "one", True), True),        # Atoi fails: the reference returns true (:1140-1142)
+        ((json.dumps(sc).encode(), base_hash, " 1", True), True),         # strconv.Atoi takes no spaces
+        ((json.dumps(sc).encode(), base_hash, "+1", True), True),         # ... but a sign
+        ((json.dumps(sc).encode(), base_hash, "2", True), False),         # fewer goal groups than the cluster: goal hash "" != annotation
+        ((json.dumps(sc).encode(), None, "2", True), True),               # ... "" == "" (no annotation)
+        ((json.dumps(sc).encode(), None, nwg, False), False),             # full compare against a missing annotation
+        ((b"{not json", "", nwg, False), True),                           # the error of :1135 is dropped: "" == ""
+        ((b"{not json", base_hash, nwg, True), True),                     # :1151-1153
+        ((json.dumps(two).encode(), base_hash, "0", True), False),        # the first 0 groups: a different spec
+        ((json.dumps(sc).encode(), base_hash.lower(), nwg, False), False),
+    ]
+    rows += [r for r, _ in extra]; want += [w for _, w in extra]
+    eng = Engine(0, max_clusters=1)
+    try:
+        got, hashes = eng.hash_compare_batch(rows)
+        assert eng.hash_compare_batch([]) == ([], [])
+    finally:
+        eng.close()
+    assert got == want, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert hashes[1] == base_hash and hashes[3] == base_hash and hashes[2] != base_hash and hashes[len(IS_EQUAL_TABLE) + 3] == ""
