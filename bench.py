@@ -357,7 +357,7 @@ def main():
             views[c][gone] = 0
         views["p_packed"][gone] = np.uint32(_abi.PP_TOMBSTONE)
         upd = rng_c.choice(npods, n_upd, replace=False).astype(np.uint32)
-        upd = upd[~np.isin(upd, gone)]
+        upd = upd[~np.isin(upd, gone) & ~np.isin(upd, freed)]  # (kr_snapshot_commit_pod_values takes every row once)
         views["p_packed"][upd] ^= np.uint32(1 << 5)  # PodReady True <-> absent
         rows = np.concatenate([freed, gone, upd])
         vals = np.stack([views[c][rows].view(np.uint32) for c in pod_cols], axis=1)  # the handlers have the new rows in hand

@@ -360,11 +360,12 @@ typedef struct kr_results_view {
   const uint8_t           *sorted_action;  /* [n_pods]: KR_ACT_* aligned with sorted_pod_idx.  NULL unless kr_flags.fetch_pod_lists */
   const int32_t           *create_idx; /* [n_create_total] replica indices (:869-881,1081-1094) */
   const kr_job_result     *jobs;       /* [n_jobs] */
-  /* compact action list: every pod whose action != KEEP (orphans excluded), grouped by cluster in cluster order, List order
-   * inside a cluster; cluster c owns entries [act_start[c], act_start[c] + act_cnt[c]).  This is all the Go shim needs to issue
-   * the Delete calls.  act_start is non-decreasing and act_start[n_clusters] == act_extent; a cluster may own fewer entries than
-   * the gap to its successor (the engine reserves a whole bucket for a RayCluster whose Recreate gate was still waiting for the
-   * digest when the list was laid out).  The same holds for create_idx: group g owns [create_off, create_off + n_create). */
+  /* compact action list: every pod whose action != KEEP (orphans excluded), one contiguous run per cluster, List order inside
+   * a run; cluster c owns entries [act_start[c], act_start[c] + act_cnt[c]).  This is all the Go shim needs to issue the Delete
+   * calls.  The ORDER of the runs inside the list is unspecified when kr_flags.fetch_pod_lists == 0 (each RayCluster reserves
+   * its run with one atomic; a RayCluster whose Recreate gate was still waiting for the digest reserves its whole bucket and
+   * may use less), and is cluster order with act_start[c + 1] == act_start[c] + act_cnt[c] when it is 1.  The same holds for
+   * create_idx: group g owns [create_off, create_off + n_create).  act_start[n_clusters] is only meaningful in the second case. */
   const uint32_t          *act_start;  /* [n_clusters + 1] */
   const uint32_t          *act_cnt;    /* [n_clusters] */
   const uint32_t          *act_pod_idx;/* [act_extent] */

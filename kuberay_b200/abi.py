@@ -278,10 +278,10 @@ class Results:
                     i = int(np.flatnonzero(neq)[0])
                     out.append(f"{name}: {int(neq.sum())} entries differ, first at [{i}]: {a[i]} != {b[i]}")
         if self.act_cnt.shape == other.act_cnt.shape and not (self.act_cnt != other.act_cnt).any():
-            for res in (self, other):
-                if (np.diff(res.act_start.astype(np.int64)) < res.act_cnt.astype(np.int64)).any():
-                    out.append("act_start: a cluster's entries run into its successor's")
             sa, sb = _gather_owned(self.act_start[:-1], self.act_cnt), _gather_owned(other.act_start[:-1], other.act_cnt)
+            for res, idx in ((self, sa), (other, sb)):
+                if np.unique(idx).size != idx.size or (idx.size and int(idx.max()) >= res.act_pod_idx.size):
+                    out.append("act_start / act_cnt: two clusters' runs overlap or leave the list")
             for name in ("act_pod_idx", "act_code"):
                 neq = getattr(self, name)[sa] != getattr(other, name)[sb]
                 if neq.any():

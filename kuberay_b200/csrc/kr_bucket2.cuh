@@ -14,8 +14,8 @@
 //   k_decide2  (one warp per RayCluster, bucket in registers, ARRIVAL order) takes the first head as a warp minimum over pod
 //              indices, the ordered delete prefix by extracting the -diff smallest indices (warp min-reduce per victim; a
 //              counting rank for long prefixes) and orders only the handful of pods that carry an action; it also allocates the
-//              replica indices from the registers and places the action list / create arena with a decoupled look-back over the
-//              CTAs, so nothing follows it: no creates kernel, no compaction kernel.
+//              replica indices from the registers and reserves its places in the action list / create arena with one returning
+//              atomic, so nothing follows it: no scan, no creates kernel, no compaction kernel.
 // A bucket stride too small for some cluster voids the attempt (the engine widens the stride or falls back to the sort
 // pipeline); clusters with multi-host groups or more than KR_SMEM_GROUPS worker groups are routed to the sort pipeline by the
 // host before the pass.
@@ -26,6 +26,7 @@
 namespace kr {
 
 static constexpr int kD2Warps = 8;  // RayClusters per k_decide2 CTA
+#define KR_ROW_UNHEALTHY (1u << 13)  // bucket record word: shouldDeletePod(pod) (k_match2 evaluates it once per pod)
 
 // ------------------------------------------------------------------------------------------------ k_match2
 // The selector match (common/association.go:83-130) + bucketing.  7 coalesced column loads per pod (issued before the
@@ -50,12 +51,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
     pk[it] = v ? __ldg(&s.p_packed[p]) : 0u; ri[it] = v ? (uint32_t)__ldg(&s.p_replica_index[p]) : 0u;
   }
   pdl_wait(); pdl_trigger();
-  if (has_wtd) {
-    const uint32_t words = (sc.wt_bits_mask + 1) >> 5;
-    for (uint32_t i = threadIdx.x; i < words; i += kSortThreads) sm_bits[i] = __ldcg(&sc.wt_bits[i]);
-    __syncthreads();
-  }
-  // hash-join probe (namespace, ray.io/cluster) -> slot; the first probe of every pod in flight together
+  // hash-join probe (namespace, ray.io/cluster) -> slot; the first probe of every pod goes out before anything waits
   uint32_t pi[kItems];
   uint4 sl[kItems];
 #pragma unroll
@@ -63,7 +59,13 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
     pi[it] = hash_pair(ns[it], cn[it]) & sc.cl_mask;
     sl[it] = __ldg(&sc.cl_slots[pi[it]]);
   }
+  if (has_wtd) {
+    const uint32_t words = (sc.wt_bits_mask + 1) >> 5;
+    for (uint32_t i = threadIdx.x; i < words; i += kSortThreads) sm_bits[i] = __ldcg(&sc.wt_bits[i]);
+    __syncthreads();
+  }
   uint32_t orphans = 0;
+  uint32_t cidx[kItems], roww[kItems];  // cluster idx (n_clusters: none) and the record word (slot << 16 | flags) of every pod
 #pragma unroll
   for (int it = 0; it < kItems; it++) {
     const uint32_t p = base + it * 32;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
       }
     }
     uint32_t flags = pk[it] & (0x7FFu | KR_PP_TOMBSTONE);  // bit 11 of the record word is KR_ROW_WTD_OWN
+    if (should_delete(pk[it])) flags |= KR_ROW_UNHEALTHY;  // shouldDeletePod (raycluster_controller.go:1181-1231), once per pod, here
     if (has_wtd && v) {  // scaleStrategy.workersToDelete: Delete(ns, name) (raycluster_controller.go:817-822)
       const uint32_t hk = hash_pair(ns[it], nm[it]);
       if (sm_bits[(hk & sc.wt_bits_mask) >> 5] & (1u << (hk & 31))) {
@@ -115,12 +118,26 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
         }
       }
     }
-    if (matched) {
-      const uint32_t rank = atomicAdd(&sc.ccount[c], 1u);  // arrival rank inside the cluster's bucket
-      if (rank < sc.bucket_stride) sc.bucket[(size_t)c * sc.bucket_stride + rank] = make_uint4(p, (slot << 16) | flags, ri[it], nm[it]);
-      else KR_MARK_ATTEMPT_VOID(r.totals);  // the engine reruns the pass with a wider stride / on the sort pipeline
+    if (matched && pp_node_type(pk[it]) == KR_NT_HEAD) {
+      // the cluster's FIRST head in List order (common/association.go:184-196) and its head-aux row, as one 64-bit maximum of
+      // ~(pod idx << 32 | row + 1): the decide warp reads it together with the pod count
+      const int32_t aux = aux_lookup(sc, p);
+      const unsigned long long key = ((unsigned long long)p << 32) | (uint32_t)(aux + 1);
+      atomicMax(reinterpret_cast<unsigned long long *>(&sc.cl_dyn[c].z), ~key);
     }
+    cidx[it] = matched ? c : n.n_clusters;
+    roww[it] = (slot << 16) | flags;
     orphans += __popc(__ballot_sync(0xFFFFFFFFu, v && !matched && !(pk[it] & KR_PP_TOMBSTONE)));
+  }
+  // arrival rank inside the cluster's bucket: every atomic of the thread in flight before the first record store needs its rank
+  uint32_t rank[kItems];
+#pragma unroll
+  for (int it = 0; it < kItems; it++) rank[it] = cidx[it] < n.n_clusters ? atomicAdd(&sc.cl_dyn[cidx[it]].x, 1u) : 0u;
+#pragma unroll
+  for (int it = 0; it < kItems; it++) {
+    if (cidx[it] >= n.n_clusters) continue;
+    if (rank[it] < sc.bucket_stride) sc.bucket[(size_t)cidx[it] * sc.bucket_stride + rank[it]] = make_uint4(base + it * 32, roww[it], ri[it], nm[it]);
+    else KR_MARK_ATTEMPT_VOID(r.totals);  // the engine reruns the pass with a wider stride / on the sort pipeline
   }
   // pods that match no RayCluster of the snapshot (free rows of an incrementally maintained arena are not orphans)
   if (lane == 0) s_orph[warp] = orphans;
@@ -141,109 +158,76 @@ struct Decide2Args {
   int phase;  // 0: every RayCluster; 1: only the clusters phase 0 deferred (Recreate gate waiting for the hash kernel)
 };
 
-// look-back cell: [63:62] status (0 none, 1 aggregate of this CTA, 2 inclusive prefix), [61:31] pods to create, [30:0] action slots
-#define KR_LB_AGG (1ull << 62)
-#define KR_LB_INC (2ull << 62)
-__device__ __forceinline__ unsigned long long lb_pack(uint32_t creates, uint32_t acts) { return ((unsigned long long)creates << 31) | acts; }
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Exclusive prefix of (creates, action slots) over the CTAs before this one (decoupled look-back; executed by warp 0).  CTAs
-// are dispatched in index order, so every predecessor a CTA spins on is resident or done.  The cell carries its own payload:
-// no other memory has to be ordered with it.
-__device__ __forceinline__ unsigned long long cta_lookback(unsigned long long *state, uint32_t b, unsigned long long agg, uint32_t lane) {
-  if (b == 0) { if (lane == 0) lb_store(&state[0], KR_LB_INC | agg); return 0; }
-  if (lane == 0) lb_store(&state[b], KR_LB_AGG | agg);
-  unsigned long long excl = 0;
-  int32_t top = (int32_t)b - 1;  // lane l looks at CTA top - l
-  while (true) {
-    const int32_t idx = top - (int32_t)lane;
-    unsigned long long v;
-    uint32_t inc_mask, none_mask;
-    do {
-      v = idx >= 0 ? lb_load(&state[idx]) : KR_LB_INC;  // before CTA 0: an inclusive prefix of zero
-      inc_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-      none_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 0);
-      // cells below the nearest inclusive one do not matter
-      if (inc_mask) none_mask &= (2u << (__ffs(inc_mask) - 1)) - 1;
-    } while (none_mask);
-    const uint32_t take = inc_mask ? ((2u << (__ffs(inc_mask) - 1)) - 1) : 0xFFFFFFFFu;  // lanes 0 .. nearest inclusive
-    unsigned long long part = (take >> lane) & 1u ? (v & ~(3ull << 62)) : 0ull;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);  // the two 31-bit fields cannot carry into each other (< 2^31 each in total)
-    excl += part;
-    if (inc_mask) break;
-    top -= 32;
-  }
-  if (lane == 0) lb_store(&state[b], KR_LB_INC | (excl + agg));
-  return excl;
-}
-
 // reconcilePods (raycluster_controller.go:619-935) + calculateStatus (:1552-1719) for one RayCluster whose bucket (<= 32*K pods,
 // arrival order) sits in registers.  Multi-host groups never reach this kernel.
 template <int K>
-__global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
+__global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decide2Args a) {
   KR_TL(a.phase ? 12 : 3);
   __shared__ int32_t s_acc[kD2Warps][3][KR_SMEM_GROUPS];   // n_list, n_unhealthy, n_wtd_own per group
   __shared__ int32_t s_mode[kD2Warps][3][KR_SMEM_GROUPS];  // mode, delete-prefix length, n_create
   __shared__ uint32_t s_list[kD2Warps][32 * K];            // pod indices being ranked (delete candidates / acted pods)
   __shared__ uint32_t s_bits[kD2Warps][32];                // 1024-bit window of replica indices in use
-  __shared__ uint32_t s_cta[kD2Warps][3];                  // per cluster: action slots reserved, pods to create, pods acted on
-  __shared__ unsigned long long s_base;
   const SnapDev &s = a.s;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt = lanemask_lt();
   const uint32_t S = a.sc.bucket_stride;
   uint32_t c = blockIdx.x * kD2Warps + warp;
-  // cluster scalars do not depend on the previous kernel
+  // the cluster's inputs: one 128-byte record (lane i = word i), written by k_build_tables — not by the kernel this one waits for
   bool mine = a.phase == 0 && c < a.n.n_clusters;
-  uint32_t cf = 0, G = 0, g0 = 0;
-  uint8_t suspend_status = 0, ext_err = 0, old_prov = 0;
-  if (mine) {
-    cf = LDG(s.c_flags[c]); G = LDG(s.c_group_cnt[c]); g0 = LDG(s.c_group_off[c]);
-    suspend_status = LDG(s.c_suspend_status[c]); ext_err = LDG(s.c_ext_err_kind[c]);
-    old_prov = LDG(s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED]);
-  }
+  RecordCI ci{mine ? __ldg(&a.sc.cl_in[32 * (size_t)c + lane]) : 0u};
   pdl_wait(); pdl_trigger();
   if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
     mine = c < a.r.totals[4];
-    if (mine) {
-      c = a.sc.deferred_list[c];
-      cf = LDG(s.c_flags[c]); G = LDG(s.c_group_cnt[c]); g0 = LDG(s.c_group_off[c]);
-      suspend_status = LDG(s.c_suspend_status[c]); ext_err = LDG(s.c_ext_err_kind[c]);
-      old_prov = LDG(s.c_old_cond_status[5 * (size_t)c + KR_COND_PROVISIONED]);
-    }
+    if (mine) { c = a.sc.deferred_list[c]; ci.word = __ldg(&a.sc.cl_in[32 * (size_t)c + lane]); }
   }
   if (KR_ATTEMPT_VOID(a.r.totals)) mine = false;  // (every warp still walks through the CTA barriers below)
+  // pod count + first head, and the whole bucket beside them (stale records past the count are masked once it is here)
+  const uint4 *bucket = a.sc.bucket + (size_t)(mine ? c : 0) * S;
+  uint4 dyn = make_uint4(0, 0, 0, 0);
+  uint4 recs[K] = {};
+  if (mine) {
+    dyn = __ldcg(&a.sc.cl_dyn[c]);
+#pragma unroll
+    for (int k = 0; k < K; k++) if ((uint32_t)(k * 32) + lane < S) recs[k] = __ldcg(&bucket[k * 32 + lane]);
+  }
+  uint32_t P = dyn.x;
+  if (P > S) { mine = false; P = 0; }  // k_match2 voided the attempt
+  const uint32_t cf = ci.flags(), G = ci.group_cnt(), g0 = ci.group_off();
+  const uint8_t suspend_status = ci.suspend_status(), ext_err = ci.ext_err_kind(), old_prov = ci.cond_status(KR_COND_PROVISIONED);
   const bool gate = a.f.gate_status_conditions != 0;
-
-  uint32_t P = 0;
-  if (mine) { P = __ldcg(&a.sc.ccount[c]); if (P > S) { mine = false; P = 0; } }  // k_match2 voided the attempt
-  const uint4 *bucket = a.sc.bucket + (size_t)c * S;
+  // first head in List order = the smallest pod index among the heads (k_match2), with its head-aux row
+  uint32_t head_pod = 0xFFFFFFFFu;
+  int32_t head_aux = -1;
+  {
+    const unsigned long long raw = ((unsigned long long)dyn.w << 32) | dyn.z;
+    if (mine && raw != 0) { const unsigned long long key = ~raw; head_pod = (uint32_t)(key >> 32); head_aux = (int32_t)(uint32_t)key - 1; }
+  }
+  // what the decisions need from the head-aux table goes out now, beside the bucket
+  uint8_t h_ver = KR_VER_EMPTY, h_ast = KR_ANNOT_EMPTY;
+  if (head_aux >= 0 && (cf & KR_CF_UPGRADE_RECREATE)) { h_ver = s.h_version_state[head_aux]; h_ast = s.h_annot_state[head_aux]; }
   uint32_t pidx[K], pw[K], ridx[K], act[K];
+  uint32_t head_pos = 0xFFFFFFFFu, head_name = 0, head_flags = 0;
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const uint32_t i = k * 32 + lane;
-    uint4 rec = make_uint4(0xFFFFFFFFu, KR_ROW_NO_GROUP << 16, 0, 0);
-    if (i < P) rec = __ldcg(&bucket[i]);
-    pidx[k] = rec.x; pw[k] = rec.y; ridx[k] = rec.z; act[k] = KR_ACT_KEEP;
+    const bool valid = i < P;
+    pidx[k] = valid ? recs[k].x : 0xFFFFFFFFu; pw[k] = valid ? recs[k].y : (KR_ROW_NO_GROUP << 16); ridx[k] = valid ? recs[k].z : 0u; act[k] = KR_ACT_KEEP;
+    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, valid && recs[k].x == head_pod);
+    if (hit) {
+      const int src = __ffs(hit) - 1;
+      head_pos = k * 32 + src;
+      head_name = __shfl_sync(0xFFFFFFFFu, recs[k].w, src); head_flags = __shfl_sync(0xFFFFFFFFu, recs[k].y, src) & 0xFFFFu;
+    }
   }
+  (void)head_pos;
   int32_t *acc_list = s_acc[warp][0], *acc_unh = s_acc[warp][1], *acc_wtd = s_acc[warp][2];
   int32_t *g_mode = s_mode[warp][0], *g_prefix = s_mode[warp][1], *g_ncreate = s_mode[warp][2];
   if (lane < KR_SMEM_GROUPS) { acc_list[lane] = 0; acc_unh[lane] = 0; acc_wtd[lane] = 0; g_mode[lane] = GM_UNPROCESSED; g_prefix[lane] = 0; g_ncreate[lane] = 0; }
   __syncwarp();
 
   // ---------------- scan 1: counts over the cluster's pods (order-free)
-  int32_t ready = 0, available = 0, n_heads = 0;
+  int32_t ready = 0, available = 0, n_heads = 0, n0_list = 0, n0_unh = 0, n0_wtd = 0;
   bool all_running = P > 0;       // CheckAllPodsRunning (utils/util.go:584-603)
-  uint32_t head_pod = 0xFFFFFFFFu;  // first head in List order = the smallest pod index among the heads
-  uint32_t head_pos = 0;
   const uint32_t nchunks = (P + 31) / 32;
 #pragma unroll
   for (int k = 0; k < K; k++) {
@@ -256,17 +240,18 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
     ready += __popc(__ballot_sync(0xFFFFFFFFu, w_run && rd == KR_COND_TRUE));
     const bool not_ok = valid && (ph != KR_PHASE_RUNNING || rd == KR_COND_FALSE || rd == KR_COND_UNKNOWN);
     if (__any_sync(0xFFFFFFFFu, not_ok)) all_running = false;
-    const bool is_head = valid && nt == KR_NT_HEAD;
-    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, is_head);
-    if (hb) {
-      n_heads += __popc(hb);
-      const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, is_head ? pidx[k] : 0xFFFFFFFFu);
-      if (m < head_pod) { head_pod = m; head_pos = k * 32 + (__ffs(__ballot_sync(0xFFFFFFFFu, is_head && pidx[k] == m)) - 1); }
+    n_heads += __popc(__ballot_sync(0xFFFFFFFFu, valid && nt == KR_NT_HEAD));
+    if (G == 1) {  // the common case: one worker group — three ballots instead of the match_any group-by
+      const bool in0 = slot == 0;
+      n0_list += __popc(__ballot_sync(0xFFFFFFFFu, in0));
+      n0_unh += __popc(__ballot_sync(0xFFFFFFFFu, in0 && (fl & KR_ROW_UNHEALTHY)));
+      n0_wtd += __popc(__ballot_sync(0xFFFFFFFFu, in0 && (fl & KR_ROW_WTD_OWN)));
+      continue;
     }
     const uint32_t gkey = (slot < G) ? slot : KR_ROW_NO_GROUP;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, gkey);
     if (gkey != KR_ROW_NO_GROUP) {
-      const uint32_t ub = __ballot_sync(peers, should_delete(fl));
+      const uint32_t ub = __ballot_sync(peers, (fl & KR_ROW_UNHEALTHY) != 0);
       const uint32_t wb = __ballot_sync(peers, (fl & KR_ROW_WTD_OWN) != 0);
       if ((peers & lt) == 0) {  // leader of its group in this chunk
         acc_list[gkey] += __popc(peers);
@@ -276,8 +261,7 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
     }
     __syncwarp();
   }
-  uint32_t head_flags = 0, head_name = 0;
-  if (n_heads > 0) { const uint4 hrec = __ldcg(&bucket[head_pos]); head_flags = hrec.y & 0xFFFFu; head_name = hrec.w; }
+  if (G == 1) { if (lane == 0) { acc_list[0] = n0_list; acc_unh[0] = n0_unh; acc_wtd[0] = n0_wtd; } __syncwarp(); }
 
   // ---------------- scalar decisions (uniform across the warp) — same order as decide_cluster / the reference
   kr_cluster_result cr;
@@ -303,9 +287,8 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
     } else {
       bool recreate = false;
       if ((cf & KR_CF_UPGRADE_RECREATE) && n_heads > 0) {  // shouldRecreatePodsForUpgrade :1132-1171
-        const int32_t aux = aux_lookup(a.sc, head_pod);
-        const uint8_t ver = aux >= 0 ? s.h_version_state[aux] : (uint8_t)KR_VER_EMPTY;
-        const uint8_t ast = aux >= 0 ? s.h_annot_state[aux] : (uint8_t)KR_ANNOT_EMPTY;
+        const int32_t aux = head_aux;
+        const uint8_t ver = h_ver, ast = h_ast;
         if (ver == KR_VER_DIFFERENT) cr.head_update_annotations = 1;
         else if (ast == KR_ANNOT_OTHER) recreate = true;
         else if (ast == KR_ANNOT_HASH32 && !a.f.skip_hash) {
@@ -327,7 +310,7 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
         cr.path = KR_PATH_NORMAL;
         if (!(cf & KR_CF_HEAD_EXPECT_OK)) { cr.head_action = KR_HEAD_EXPECT_PENDING; run_groups = true; }  // head (:673-748)
         else if (n_heads == 1) {
-          if (should_delete(head_flags)) { cr.head_action = KR_HEAD_DELETE; cr.err_kind = KR_ERR_HEAD_DELETED; head_delete = true; }
+          if (head_flags & KR_ROW_UNHEALTHY) { cr.head_action = KR_HEAD_DELETE; cr.err_kind = KR_ERR_HEAD_DELETED; head_delete = true; }
           else run_groups = true;
         } else if (n_heads == 0) {
           if (old_prov == KR_COND_TRUE && (cf & KR_CF_SKIP_HEAD_RESTART)) cr.head_action = KR_HEAD_SKIP_RESTART;
@@ -342,8 +325,11 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
       const bool autoscaling = (cf & KR_CF_AUTOSCALING) != 0;
       cr.stop_after_group = (int32_t)G;
       for (uint32_t gi = 0; gi < G; gi++) {
-        const uint32_t g = g0 + gi, gf = LDG(s.g_flags[g]);
-        const int32_t hosts = LDG(s.g_num_hosts[g]), g_rep = LDG(s.g_replicas[g]), g_mn = LDG(s.g_min[g]), g_mx = LDG(s.g_max[g]);
+        const uint32_t g = g0 + gi;
+        const bool rec0 = gi == 0;  // worker group 0 came with the cluster's record
+        const uint32_t gf = rec0 ? ci.g0_flags() : LDG(s.g_flags[g]);
+        const int32_t hosts = rec0 ? ci.g0_hosts() : LDG(s.g_num_hosts[g]), g_rep = rec0 ? ci.g0_rep() : LDG(s.g_replicas[g]);
+        const int32_t g_mn = rec0 ? ci.g0_min() : LDG(s.g_min[g]), g_mx = rec0 ? ci.g0_max() : LDG(s.g_max[g]);
         kr_group_result gr;
         gr.expected = 0; gr.n_list = 0; gr.n_unhealthy = 0; gr.n_running = 0; gr.diff = 0; gr.n_create = 0; gr.create_off = 0;
         gr.flags = KR_GR_PROCESSED;
@@ -411,7 +397,7 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
       if (all_action != KR_ACT_KEEP) ac = valid ? all_action : (uint32_t)KR_ACT_KEEP;
       else if (head_delete) { if (valid && pidx[k] == head_pod) ac = KR_ACT_DELETE_HEAD; }
       else if (mode == GM_SUSPENDED) ac = KR_ACT_DELETE_GROUP_SUSPEND;
-      else if (mode == GM_UNHEALTHY) { if (should_delete(fl)) ac = KR_ACT_DELETE_UNHEALTHY; }
+      else if (mode == GM_UNHEALTHY) { if (fl & KR_ROW_UNHEALTHY) ac = KR_ACT_DELETE_UNHEALTHY; }
       else if (mode == GM_NORMAL) {
         if (fl & KR_ROW_WTD_OWN) ac = KR_ACT_DELETE_WTD;
         else cand |= 1u << k;
@@ -482,41 +468,27 @@ __global__ void __launch_bounds__(kD2Warps * 32) k_decide2(Decide2Args a) {
   }
 
   // ---------------- status roll-up + record (needs nothing from the placement below)
-  if (mine && lane == 0) {
-    if (!(cf & KR_CF_SKIP))
-      status_rollup(a.s, a.sc, a.f, c, cr, P, (uint32_t)n_heads, n_heads > 0 ? (int32_t)head_pod : -1, head_name, ready, available, all_running);
-    a.r.clusters[c] = cr;
-  }
+  if (!(cf & KR_CF_SKIP))  // (every lane runs it, uniformly: the inputs are one shuffle away in the record)
+    status_rollup(a.s, a.f, ci, cr, P, (uint32_t)n_heads, n_heads > 0 ? (int32_t)head_pod : -1, head_aux, head_name, ready, available, all_running);
+  if (mine && lane == 0) a.r.clusters[c] = cr;
 
-  // ---------------- placement: where this cluster's action list and replica indices go
+  // ---------------- placement: where this cluster's action list and replica indices go.  One returning 64-bit atomic per
+  // RayCluster on the two arena cursors (pods to create << 32 | action slots), issued by lane 0 and needed only for the stores
+  // below.  (A decoupled look-back over the CTAs was built first: placement in cluster order, but the prefix crosses the grid in
+  // 32-CTA hops — 39 hops x ~1 us on the critical path of a 10 k-cluster pass, 41 % of the kernel's stall samples at the barrier
+  // in front of it; profiles/r2_ncu_bucket_a.json.  The owners' ORDER inside the arenas is therefore unspecified; every owner
+  // finds its place through (act_start, act_cnt) / (create_off, n_create), which is what the shim reads anyway.)
   const uint32_t slots = deferred ? P : n_act;  // a deferred cluster may still turn into "delete every pod"
   uint32_t act_off = 0, create_off = 0;
   if (a.phase == 0) {
-    if (lane == 0) { s_cta[warp][0] = mine ? slots : 0u; s_cta[warp][1] = mine ? n_create_cluster : 0u; s_cta[warp][2] = mine ? n_act : 0u; }
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t ta = 0, tc = 0, tn = 0;
-#pragma unroll
-      for (int w = 0; w < kD2Warps; w++) { ta += s_cta[w][0]; tc += s_cta[w][1]; tn += s_cta[w][2]; }
-      const unsigned long long agg = lb_pack(tc, ta);
-      const unsigned long long excl = cta_lookback(a.sc.lb_state, blockIdx.x, agg, lane);
-      if (lane == 0) {
-        s_base = excl;
-        if (tn) atomicAdd(&a.r.totals[2], tn);  // pods acted on (the extent of the list, totals[5], also counts reserved slots)
-        if (blockIdx.x == gridDim.x - 1) {       // extents of the two arenas
-          const unsigned long long tot = excl + agg;
-          a.r.totals[0] = (uint32_t)(tot >> 31); a.r.totals[6] = (uint32_t)(tot >> 31);
-          a.r.totals[5] = (uint32_t)(tot & 0x7FFFFFFFu);
-          a.r.act_start[a.n.n_clusters] = (uint32_t)(tot & 0x7FFFFFFFu);
-        }
-      }
+    unsigned long long base = 0;
+    if (mine && lane == 0) {
+      if (slots | n_create_cluster) base = atomicAdd(reinterpret_cast<unsigned long long *>(&a.r.totals[8]), ((unsigned long long)n_create_cluster << 32) | slots);
+      if (n_act) atomicAdd(&a.r.totals[2], n_act);  // pods acted on (the extent of the list also counts reserved slots)
+      if (n_create_cluster) atomicAdd(&a.r.totals[6], n_create_cluster);
     }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    act_off = (uint32_t)(base & 0x7FFFFFFFu); create_off = (uint32_t)(base >> 31);
-#pragma unroll
-    for (int w = 0; w < kD2Warps; w++)
-      if (w < (int)warp) { act_off += s_cta[w][0]; create_off += s_cta[w][1]; }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    act_off = (uint32_t)base; create_off = (uint32_t)(base >> 32);
     if (mine && lane == 0) {
       a.r.act_start[c] = act_off; a.r.act_cnt[c] = n_act;
       if (deferred) a.sc.cact[c] = n_create_cluster;  // phase 1 corrects the count of pods to create if the cluster turns into a Recreate

@@ -54,7 +54,8 @@ struct ResDev {  // device results arena
   uint32_t *act_pod_idx;  // [n_pods] capacity; n_actions used
   uint8_t *act_code;
   // [0]=extent of create_idx [1]=n_orphans [2]=n_actions [3]=error flags [4]=clusters deferred to decide phase 1
-  // [5]=extent of the action list (bucket pipeline: >= [2], deferred clusters reserve their whole bucket) [6]=pods to create (bucket pipeline)
+  // bucket pipeline: [6]=pods to create, [8]/[9]=the two arena cursors as ONE 64-bit word (low: extent of the action list, >= [2]
+  // because deferred clusters reserve their whole bucket; high: extent of create_idx)
   uint32_t *totals;
 };
 
@@ -83,7 +84,19 @@ struct ScratchDev {
   // bucket pipeline (kr_bucket2.cuh)
   uint4 *bucket; uint32_t bucket_stride;                       // [n_clusters * stride] {pod idx, slot << 16 | flags, replica index, name id}, arrival order
   uint32_t *wt_bits; uint32_t wt_bits_mask;                    // Bloom bitmap over the workersToDelete (ns, name) keys (power-of-two bit count)
-  unsigned long long *lb_state;                                // decoupled look-back cells of k_decide2 (one per CTA), zeroed every pass
+  uint32_t *cl_in;                                             // [32 * n_clusters] every per-cluster input of the decide kernel as ONE 128-byte record (KR_CI_*)
+  uint4 *cl_dyn;                                               // [n_clusters] {pods bucketed so far, -, ~(first head's pod idx << 32 | head-aux row + 1)}, zeroed every pass
+};
+// words of a cl_in record (built by k_build_tables; k_decide2 loads it with one coalesced 128-byte access, lane i = word i)
+enum {
+  KR_CI_FLAGS = 0, KR_CI_GOFF = 1, KR_CI_GCNT = 2,
+  KR_CI_B0 = 3,   // bytes: suspend_status, ext_err_kind, old_state, svc_count
+  KR_CI_B1 = 4,   // bytes: svc_ip_kind, old_cond_status[0..2]
+  KR_CI_B2 = 5,   // bytes: old_cond_status[3..4], old_cond_variant[0..1]
+  KR_CI_B3 = 6,   // bytes: old_cond_variant[2..4], -
+  KR_CI_EXT_MSG = 7, KR_CI_CNT = 8 /* ..12 */, KR_CI_REASON = 13, KR_CI_MSG = 14 /* ..15 */, KR_CI_HEAD = 16 /* ..19 */,
+  KR_CI_SVC_IP = 20, KR_CI_SVC_NAME = 21,
+  KR_CI_G0_FLAGS = 22, KR_CI_G0_REP = 23, KR_CI_G0_MIN = 24, KR_CI_G0_MAX = 25, KR_CI_G0_HOSTS = 26  // worker group 0 (when group_cnt >= 1)
 };
 #define KR_CL_MH 1u      // cl_slots[].w flag bits
 #define KR_CL_MULTI 2u

@@ -41,36 +41,102 @@ struct DecideArgs {
   int phase;                    // 0: everything that does not need the hash; 1: only clusters deferred by phase 0
 };
 
+// Where status_rollup finds a RayCluster's inputs: straight in the snapshot columns (sort / radix pipelines: scalar code on
+// lane 0) ...
+struct ColumnsCI {
+  const SnapDev &s; uint32_t c;
+  __device__ __forceinline__ uint32_t flags() const { return s.c_flags[c]; }
+  __device__ __forceinline__ uint8_t ext_err_kind() const { return s.c_ext_err_kind[c]; }
+  __device__ __forceinline__ uint32_t ext_err_msg() const { return s.c_ext_err_msg_id[c]; }
+  __device__ __forceinline__ uint8_t cond_status(int k) const { return s.c_old_cond_status[5 * (size_t)c + k]; }
+  __device__ __forceinline__ uint8_t cond_variant(int k) const { return s.c_old_cond_variant[5 * (size_t)c + k]; }
+  __device__ __forceinline__ uint32_t reason() const { return s.c_old_cond_reason_id[c]; }
+  __device__ __forceinline__ uint32_t msg(int k) const { return s.c_old_cond_msg_id[2 * (size_t)c + k]; }
+  __device__ __forceinline__ uint32_t group_cnt() const { return s.c_group_cnt[c]; }
+  __device__ __forceinline__ uint32_t group_off() const { return s.c_group_off[c]; }
+  __device__ __forceinline__ uint8_t svc_count() const { return s.c_svc_count[c]; }
+  __device__ __forceinline__ uint8_t svc_ip_kind() const { return s.c_svc_ip_kind[c]; }
+  __device__ __forceinline__ uint32_t svc_ip() const { return s.c_svc_ip_id[c]; }
+  __device__ __forceinline__ uint32_t svc_name() const { return s.c_svc_name_id[c]; }
+  __device__ __forceinline__ uint8_t old_state() const { return s.c_old_state[c]; }
+  __device__ __forceinline__ uint8_t suspend_status() const { return s.c_suspend_status[c]; }
+  __device__ __forceinline__ int32_t old_count(int k) const { return s.c_old_counts[5 * (size_t)c + k]; }
+  __device__ __forceinline__ uint32_t old_head(int k) const { return s.c_old_head_ids[4 * (size_t)c + k]; }
+  // worker group 0's scalars may come with the cluster's record; here every group is read from the columns
+  __device__ __forceinline__ bool has_group0() const { return false; }
+  __device__ __forceinline__ uint32_t g0_flags() const { return 0; }
+  __device__ __forceinline__ int32_t g0_rep() const { return 0; }
+  __device__ __forceinline__ int32_t g0_min() const { return 0; }
+  __device__ __forceinline__ int32_t g0_max() const { return 0; }
+  __device__ __forceinline__ int32_t g0_hosts() const { return 0; }
+};
+// ... or in the 128-byte cl_in record the warp loaded with one access, lane i holding word i (bucket pipeline: every lane runs
+// the roll-up, uniformly, and each field is one shuffle away).
+struct RecordCI {
+  uint32_t word;  // this lane's word of the record
+  __device__ __forceinline__ uint32_t w(int i) const { return __shfl_sync(0xFFFFFFFFu, word, i); }
+  __device__ __forceinline__ uint8_t byte(int i, int b) const { return (uint8_t)(w(i) >> (8 * b)); }
+  __device__ __forceinline__ uint32_t flags() const { return w(KR_CI_FLAGS); }
+  __device__ __forceinline__ uint8_t ext_err_kind() const { return byte(KR_CI_B0, 1); }
+  __device__ __forceinline__ uint32_t ext_err_msg() const { return w(KR_CI_EXT_MSG); }
+  __device__ __forceinline__ uint8_t cond_status(int k) const { return k < 3 ? byte(KR_CI_B1, 1 + k) : byte(KR_CI_B2, k - 3); }
+  __device__ __forceinline__ uint8_t cond_variant(int k) const { return k < 2 ? byte(KR_CI_B2, 2 + k) : byte(KR_CI_B3, k - 2); }
+  __device__ __forceinline__ uint32_t reason() const { return w(KR_CI_REASON); }
+  __device__ __forceinline__ uint32_t msg(int k) const { return w(KR_CI_MSG + k); }
+  __device__ __forceinline__ uint32_t group_cnt() const { return w(KR_CI_GCNT); }
+  __device__ __forceinline__ uint32_t group_off() const { return w(KR_CI_GOFF); }
+  __device__ __forceinline__ uint8_t svc_count() const { return byte(KR_CI_B0, 3); }
+  __device__ __forceinline__ uint8_t svc_ip_kind() const { return byte(KR_CI_B1, 0); }
+  __device__ __forceinline__ uint32_t svc_ip() const { return w(KR_CI_SVC_IP); }
+  __device__ __forceinline__ uint32_t svc_name() const { return w(KR_CI_SVC_NAME); }
+  __device__ __forceinline__ uint8_t old_state() const { return byte(KR_CI_B0, 2); }
+  __device__ __forceinline__ uint8_t suspend_status() const { return byte(KR_CI_B0, 0); }
+  __device__ __forceinline__ int32_t old_count(int k) const { return (int32_t)w(KR_CI_CNT + k); }
+  __device__ __forceinline__ uint32_t old_head(int k) const { return w(KR_CI_HEAD + k); }
+  __device__ __forceinline__ bool has_group0() const { return true; }
+  __device__ __forceinline__ uint32_t g0_flags() const { return w(KR_CI_G0_FLAGS); }
+  __device__ __forceinline__ int32_t g0_rep() const { return (int32_t)w(KR_CI_G0_REP); }
+  __device__ __forceinline__ int32_t g0_min() const { return (int32_t)w(KR_CI_G0_MIN); }
+  __device__ __forceinline__ int32_t g0_max() const { return (int32_t)w(KR_CI_G0_MAX); }
+  __device__ __forceinline__ int32_t g0_hosts() const { return (int32_t)w(KR_CI_G0_HOSTS); }
+};
+
 // calculateStatus (raycluster_controller.go:1552-1719) + InconsistentRayClusterStatus (utils/consistency.go:16-34).
-// Scalar code, executed by lane 0 only.
-__device__ void status_rollup(const SnapDev &s, const ScratchDev &sc, const kr_flags &f, uint32_t c, kr_cluster_result &cr, uint32_t P, uint32_t n_heads,
-                              int32_t head_pod, uint32_t head_name_id, int32_t ready, int32_t available, bool all_running) {
-  const uint32_t cf = s.c_flags[c];
+// Scalar code: executed by lane 0 only (ColumnsCI) or by every lane uniformly (RecordCI).  aux = head-aux row of the first head
+// pod (-1: none / not in the table).
+template <class CI>
+__device__ __forceinline__ void status_rollup(const SnapDev &s, const kr_flags &f, const CI &ci, kr_cluster_result &cr, uint32_t P, uint32_t n_heads,
+                                              int32_t head_pod, int32_t aux, uint32_t head_name_id, int32_t ready, int32_t available, bool all_running) {
+  const uint32_t cf = ci.flags();
   const bool gate = f.gate_status_conditions != 0;
   const bool reconcile_err = cr.err_kind != KR_ERR_NONE;
-  const uint8_t ek = s.c_ext_err_kind[c];
-  uint8_t cst[KR_NUM_CONDS], cvr[KR_NUM_CONDS];
+  const uint8_t ek = ci.ext_err_kind();
+  uint8_t cst[KR_NUM_CONDS], cvr[KR_NUM_CONDS], ocst[KR_NUM_CONDS], ocvr[KR_NUM_CONDS];
 #pragma unroll
-  for (int k = 0; k < KR_NUM_CONDS; k++) { cst[k] = s.c_old_cond_status[5 * (size_t)c + k]; cvr[k] = s.c_old_cond_variant[5 * (size_t)c + k]; }
-  uint32_t hpr_reason = s.c_old_cond_reason_id[c], hpr_msg = s.c_old_cond_msg_id[2 * (size_t)c], rf_msg = s.c_old_cond_msg_id[2 * (size_t)c + 1];
+  for (int k = 0; k < KR_NUM_CONDS; k++) { ocst[k] = cst[k] = ci.cond_status(k); ocvr[k] = cvr[k] = ci.cond_variant(k); }
+  const uint32_t old_reason = ci.reason(), old_msg0 = ci.msg(0), old_msg1 = ci.msg(1);
+  uint32_t hpr_reason = old_reason, hpr_msg = old_msg0, rf_msg = old_msg1;
   if (gate) {  // :1563-1577
     if (reconcile_err) {
       if (ek >= KR_EXT_ERR_FAILED_DELETE_ALL_PODS && ek <= KR_EXT_ERR_FAILED_CREATE_WORKER_POD) {
-        cst[KR_COND_REPLICA_FAILURE] = KR_COND_TRUE; cvr[KR_COND_REPLICA_FAILURE] = ek; rf_msg = s.c_ext_err_msg_id[c];
+        cst[KR_COND_REPLICA_FAILURE] = KR_COND_TRUE; cvr[KR_COND_REPLICA_FAILURE] = ek; rf_msg = ci.ext_err_msg();
       }
     } else {
       cst[KR_COND_REPLICA_FAILURE] = KR_COND_ABSENT; cvr[KR_COND_REPLICA_FAILURE] = KR_CV_NONE; rf_msg = 0;
     }
   }
   int32_t desired = 0, minr = 0; long long maxr = 0;  // utils/util.go:407-442
-  const uint32_t G = s.c_group_cnt[c], g0 = s.c_group_off[c];
+  const uint32_t G = ci.group_cnt(), g0 = ci.group_off();
   for (uint32_t gi = 0; gi < G; gi++) {
-    uint32_t g = g0 + gi, gf = s.g_flags[g];
-    int32_t hosts = s.g_num_hosts[g];
-    desired = (int32_t)((uint32_t)desired + (uint32_t)desired_replicas(s.g_replicas[g], s.g_min[g], s.g_max[g], hosts, gf));
+    const uint32_t g = g0 + gi;
+    const bool rec = gi == 0 && ci.has_group0();
+    const uint32_t gf = rec ? ci.g0_flags() : s.g_flags[g];
+    const int32_t hosts = rec ? ci.g0_hosts() : s.g_num_hosts[g], g_rep = rec ? ci.g0_rep() : s.g_replicas[g];
+    const int32_t g_mn = rec ? ci.g0_min() : s.g_min[g], g_mx = rec ? ci.g0_max() : s.g_max[g];
+    desired = (int32_t)((uint32_t)desired + (uint32_t)desired_replicas(g_rep, g_mn, g_mx, hosts, gf));
     if (gf & KR_GF_SUSPEND) continue;
-    int32_t mn = (gf & KR_GF_MIN_NIL) ? 0 : s.g_min[g];
-    int32_t mx = (gf & KR_GF_MAX_NIL) ? INT32_MAX : s.g_max[g];
+    int32_t mn = (gf & KR_GF_MIN_NIL) ? 0 : g_mn;
+    int32_t mx = (gf & KR_GF_MAX_NIL) ? INT32_MAX : g_mx;
     minr = (int32_t)((uint32_t)minr + (uint32_t)mn * (uint32_t)hosts);
     maxr += (long long)mx * (long long)hosts;
   }
@@ -78,22 +144,22 @@ __device__ void status_rollup(const SnapDev &s, const ScratchDev &sc, const kr_f
 
   cr.n_pods = (int32_t)P; cr.n_heads = (int32_t)n_heads; cr.head_pod_idx = head_pod;
   uint8_t serr = KR_SERR_NONE;  // :1608-1611, :1785-1806, :1721-1745
+  const uint8_t svc_count = ci.svc_count(), svc_ip_kind = ci.svc_ip_kind();
   if (n_heads > 1) serr = KR_SERR_MULTIPLE_HEADS;
-  else if (s.c_svc_count[c] == 0) serr = KR_SERR_NO_HEAD_SERVICE;
-  else if (s.c_svc_count[c] > 1) serr = KR_SERR_MULTIPLE_HEAD_SERVICES;
-  else if (s.c_svc_ip_kind[c] == KR_SVCIP_EMPTY) serr = KR_SERR_EMPTY_SERVICE_IP;
+  else if (svc_count == 0) serr = KR_SERR_NO_HEAD_SERVICE;
+  else if (svc_count > 1) serr = KR_SERR_MULTIPLE_HEAD_SERVICES;
+  else if (svc_ip_kind == KR_SVCIP_EMPTY) serr = KR_SERR_EMPTY_SERVICE_IP;
   cr.status_err = serr;
   if (serr != KR_SERR_NONE) return;
 
-  const uint8_t old_state = s.c_old_state[c];
+  const uint8_t old_state = ci.old_state();
   uint8_t new_state = old_state;
   bool reason_cleared = false;
   if (!reconcile_err && (long long)P == (long long)desired + 1 && all_running) { new_state = KR_STATE_READY; reason_cleared = true; }  // :1599-1604
 
   uint32_t head_pod_ip = 0, head_pod_name = 0;
-  int32_t aux = -1;
+  if (n_heads != 1) aux = -1;
   if (n_heads == 1) {
-    aux = aux_lookup(sc, (uint32_t)head_pod);
     head_pod_ip = aux >= 0 ? s.h_pod_ip_id[aux] : 0;
     head_pod_name = head_name_id;
   }
@@ -106,7 +172,7 @@ __device__ void status_rollup(const SnapDev &s, const ScratchDev &sc, const kr_f
       cvr[KR_COND_HEAD_POD_READY] = KR_CV_HEAD_FROM_POD;
       hpr_reason = aux >= 0 ? s.h_ready_reason_id[aux] : 0; hpr_msg = aux >= 0 ? s.h_ready_msg_id[aux] : 0;
     }
-    const uint8_t ss = s.c_suspend_status[c];
+    const uint8_t ss = ci.suspend_status();
     if (cst[KR_COND_PROVISIONED] != KR_COND_TRUE && ss != KR_SUSPEND_SUSPENDED) {  // :1625-1644
       if (all_running) { cst[KR_COND_PROVISIONED] = KR_COND_TRUE; cvr[KR_COND_PROVISIONED] = KR_CV_PROV_ALL_READY; }
       else { cst[KR_COND_PROVISIONED] = KR_COND_FALSE; cvr[KR_COND_PROVISIONED] = KR_CV_PROV_PROVISIONING; }
@@ -126,9 +192,9 @@ __device__ void status_rollup(const SnapDev &s, const ScratchDev &sc, const kr_f
   }
   if ((cf & KR_CF_SUSPEND) && P == 0) new_state = KR_STATE_SUSPENDED;  // :1696-1698
 
-  uint32_t svc_ip = s.c_svc_ip_id[c];
-  if (s.c_svc_ip_kind[c] == KR_SVCIP_NONE) svc_ip = (n_heads == 1) ? head_pod_ip : 0;  // :1732-1742
-  uint32_t head_ids[4] = {head_pod_ip, svc_ip, head_pod_name, s.c_svc_name_id[c]};
+  uint32_t svc_ip = ci.svc_ip();
+  if (svc_ip_kind == KR_SVCIP_NONE) svc_ip = (n_heads == 1) ? head_pod_ip : 0;  // :1732-1742
+  uint32_t head_ids[4] = {head_pod_ip, svc_ip, head_pod_name, ci.svc_name()};
 
   cr.new_state = new_state;
   cr.state_changed = new_state != old_state;
@@ -143,20 +209,19 @@ __device__ void status_rollup(const SnapDev &s, const ScratchDev &sc, const kr_f
   bool inc = new_state != old_state;  // utils/consistency.go:16-34
   if (reason_cleared && (cf & KR_CF_OLD_REASON_NONEMPTY)) inc = true;
 #pragma unroll
-  for (int k = 0; k < 5; k++) if (s.c_old_counts[5 * (size_t)c + k] != cr.counts[k]) inc = true;
+  for (int k = 0; k < 5; k++) if (ci.old_count(k) != cr.counts[k]) inc = true;
   if (cf & KR_CF_ENDPOINTS_CHANGED) inc = true;
 #pragma unroll
-  for (int k = 0; k < 4; k++) if (s.c_old_head_ids[4 * (size_t)c + k] != head_ids[k]) inc = true;
+  for (int k = 0; k < 4; k++) if (ci.old_head(k) != head_ids[k]) inc = true;
 #pragma unroll
   for (int k = 0; k < KR_NUM_CONDS; k++) {
-    uint8_t os = s.c_old_cond_status[5 * (size_t)c + k], ov = s.c_old_cond_variant[5 * (size_t)c + k];
-    if (os != cst[k]) { inc = true; continue; }
+    if (ocst[k] != cst[k]) { inc = true; continue; }
     if (cst[k] == KR_COND_ABSENT) continue;
     if (k == KR_COND_HEAD_POD_READY) {
-      if (s.c_old_cond_reason_id[c] != hpr_reason || s.c_old_cond_msg_id[2 * (size_t)c] != hpr_msg) inc = true;
+      if (old_reason != hpr_reason || old_msg0 != hpr_msg) inc = true;
     } else if (k == KR_COND_REPLICA_FAILURE) {
-      if (ov != cvr[k] || s.c_old_cond_msg_id[2 * (size_t)c + 1] != rf_msg) inc = true;
-    } else if (ov != cvr[k]) inc = true;
+      if (ocvr[k] != cvr[k] || old_msg1 != rf_msg) inc = true;
+    } else if (ocvr[k] != cvr[k]) inc = true;
   }
   cr.needs_status_write = inc ? 1 : 0;
 }
@@ -577,7 +642,7 @@ __device__ __forceinline__ void decide_cluster(const DecideArgs &a, const uint32
   // ---------------- status roll-up + record
   if (lane == 0) {
     if (!(cf & KR_CF_SKIP))
-      status_rollup(a.s, a.sc, a.f, c, cr, P, (uint32_t)n_heads, head_pod, head_name, ready, available, all_running);
+      status_rollup(a.s, a.f, ColumnsCI{a.s, c}, cr, P, (uint32_t)n_heads, head_pod, n_heads == 1 ? aux_lookup(a.sc, (uint32_t)head_pod) : -1, head_name, ready, available, all_running);
     a.r.clusters[c] = cr;
     a.sc.cact[c] = n_act;
     if (n_act) atomicAdd(&a.r.totals[2], n_act);

@@ -103,7 +103,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, lb_state, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, bucket, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
   uint32_t wt_bits_n;      // bits of the workersToDelete Bloom bitmap
   size_t bucket_entries;   // capacity of the bucket arena of the bucket pipeline (0: that pipeline is off for this engine)
@@ -146,7 +146,7 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
     L.wt_bits_n = (uint32_t)bits;
   }
   L.wt_bits = o; o = align_up(o + L.wt_bits_n / 8);   // zeroed with ccount and chain (one region up to cstart)
-  L.lb_state = o; o = align_up(o + 8 * ((size_t)n.n_clusters / 8 + 2));
+  L.cl_dyn = o; o = align_up(o + 16 * (size_t)n.n_clusters);
   L.cstart = o; o = align_up(o + 4 * ((size_t)n.n_clusters + 2));
   L.tile_orph = o; o = align_up(o + 4 * ((size_t)L.mtiles + 8));
   L.mh_rep = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -161,7 +161,9 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   // bucket pipeline: fixed-stride buckets of 16-byte records.  Room for a stride of >= 4x the mean cluster size, at least 64
   // records per cluster; snapshots of very many tiny clusters (64 records per cluster would dwarf the pods) do without.
   L.bucket_entries = std::max<size_t>(4 * (size_t)n.n_pods, 64 * (size_t)n.n_clusters);
-  if (64 * (size_t)n.n_clusters > 8 * (size_t)n.n_pods + (1u << 20)) L.bucket_entries = 0;
+  L.bucket_entries = std::max<size_t>(L.bucket_entries, std::min<size_t>(256 * (size_t)n.n_clusters, (size_t)4 << 20));  // small snapshots: room for the widest stride
+  if (64 * (size_t)n.n_clusters > 8 * (size_t)n.n_pods + (4u << 20)) L.bucket_entries = 0;
+  L.cl_in = o; o = align_up(o + 128 * (size_t)n.n_clusters);
   L.bucket = o; o = align_up(o + 16 * L.bucket_entries);
   L.total = o;
   return L;
@@ -301,7 +303,8 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.act_tmp_idx = reinterpret_cast<uint32_t *>(b + L.act_tmp_idx); s.act_tmp_code = b + L.act_tmp_code;
   s.bucket = reinterpret_cast<uint4 *>(b + L.bucket); s.bucket_stride = 0;
   s.wt_bits = reinterpret_cast<uint32_t *>(b + L.wt_bits); s.wt_bits_mask = L.wt_bits_n - 1;
-  s.lb_state = reinterpret_cast<unsigned long long *>(b + L.lb_state);
+  s.cl_in = reinterpret_cast<uint32_t *>(b + L.cl_in);
+  s.cl_dyn = reinterpret_cast<uint4 *>(b + L.cl_dyn);
   return s;
 }
 
@@ -381,7 +384,8 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     ca.ptr[0] = reinterpret_cast<uint32_t *>(e->d_scratch); ca.words[0] = (uint32_t)(e->sl.ff_total / 4); ca.value[0] = 0xFFFFFFFFu;
     ca.ptr[1] = r.wtd_pod_idx; ca.words[1] = n.n_wtd; ca.value[1] = 0xFFFFFFFFu;
     ca.ptr[2] = r.totals; ca.words[2] = 64; ca.value[2] = 0;  // the 8 counters and, 128 bytes in, the void-attempt word (the block is 256 bytes)
-    // per-cluster counts + the chained-scan cells + the workersToDelete Bloom bitmap + the look-back cells (one region)
+    // per-cluster counts + the chained-scan cells + the workersToDelete Bloom bitmap + the bucket fill counters / first-head
+    // cells (one region)
     ca.ptr[3] = sc.ccount; ca.words[3] = (uint32_t)((e->sl.cstart - e->sl.ccount) / 4); ca.value[3] = 0;
     mark("k_clear");
     k_clear<<<e->sm_count * 2, 256, 0, M>>>(ca);
@@ -572,7 +576,7 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
     int rc = run_pass_once(e, f);
     if (rc) return rc;
     if (done) CK(cudaEventRecord(done, e->sm));
-    CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
+    CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 48, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
     e->order_pending = false;
     if (!e->h2d_timed) {
@@ -598,8 +602,8 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
 int fetch_results(kr_engine *e, kr_results_view *out) {
   const kr_sizes &n = e->sizes;
   const uint32_t *tot = e->h_totals;
-  // bucket pipeline: the two arenas can hold reserved-but-unused places (totals[5] / totals[0] are their extents, [2] / [6] the counts)
-  const uint32_t n_create = tot[0], n_actions = e->ran_bucket ? tot[5] : tot[2];
+  // bucket pipeline: the two arenas can hold reserved-but-unused places (totals[9] / totals[8] are their extents, [6] / [2] the counts)
+  const uint32_t n_create = e->ran_bucket ? tot[9] : tot[0], n_actions = e->ran_bucket ? tot[8] : tot[2];
   const bool full = e->last_flags.fetch_pod_lists != 0;
   CK(cudaEventRecord(e->ev_b, e->sm));
   if (n_create > e->cfg.max_creates) {
@@ -1010,7 +1014,7 @@ int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile 
     int rc = launch_pass(e, *flags, true);
     if (rc) return rc;
     CK(cudaEventRecord(e->ev_b, e->sm));
-    CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 32, cudaMemcpyDeviceToHost, e->sm));
+    CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 48, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
     e->order_pending = false;
     if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) break;

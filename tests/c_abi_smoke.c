@@ -62,8 +62,8 @@ int main(void) {
   printf("path %d head_action %d err_kind %d err_arg %d n_pods %d | group expected %d unhealthy %d n_create %u | actions %u hash %.32s\n",
          c->path, c->head_action, c->err_kind, c->err_arg, c->n_pods, g->expected, g->n_unhealthy, g->n_create, r.n_actions, r.hash);
   int ok = c->err_kind == KR_ERR_UNHEALTHY_WORKERS && c->err_arg == 1 && c->n_pods == 3 && g->expected == 2 && g->n_unhealthy == 1 &&
-           g->n_create == 0 && r.n_actions == 1 && r.act_start[0] == 0 && r.act_start[1] == 1 && r.act_pod_idx[0] == 2 &&
-           r.act_code[0] == KR_ACT_DELETE_UNHEALTHY && r.n_orphans == 0;
+           g->n_create == 0 && r.n_actions == 1 && r.act_cnt[0] == 1 && r.act_pod_idx[r.act_start[0]] == 2 &&
+           r.act_code[r.act_start[0]] == KR_ACT_DELETE_UNHEALTHY && r.n_orphans == 0;
   /* the same digest through the RayService entry point */
   char h[32];
   const uint64_t offs[2] = {0, sizeof spec - 1};

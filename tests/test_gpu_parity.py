@@ -223,8 +223,9 @@ def test_compact_action_list_without_pod_lists(oracle_mod):
     assert np.array_equal(got.act_pod_idx[own], want.sorted_pod_idx[keep]) and np.array_equal(got.act_code[own], want.sorted_action[keep])
     assert np.array_equal(got.act_cnt.astype(np.int64), np.add.reduceat(keep.astype(np.int64), want.clusters["pod_start"].astype(np.int64))
                           if snap.dims["clusters"] else [])
-    # RayClusters whose Recreate gate waited for the digest reserved their whole bucket: the list's extent is at least the count
-    assert got.act_start[-1] >= got.n_actions and (np.diff(got.act_start.astype(np.int64)) >= got.act_cnt).all()
+    # one run per cluster, anywhere in the list, never overlapping (RayClusters whose Recreate gate waited for the digest reserved
+    # their whole bucket: the list's extent is at least the count)
+    assert got.act_pod_idx.size >= got.n_actions and np.unique(own).size == own.size
 
 
 def test_bucket_pipeline_is_taken_and_widens_its_stride(oracle_mod):
