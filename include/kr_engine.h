@@ -521,6 +521,36 @@ int kr_quantity_canonical(const char *text, char *out, uint64_t out_cap);
 /* Error text of the last failing kr_spec_json_* / kr_quantity_canonical call on this thread (never NULL). */
 const char *kr_spec_json_last_error(void);
 
+/* ---- multi-GPU coordinator (SURVEY §8(b) "one engine per device + a coordinator", §8(e)).  One process, one engine per shard,
+ * each driven by its own host thread bound to its GPU's NUMA node (the thread also creates the engine: node-local pinned arenas).
+ * A RayCluster's decisions depend only on its own objects (common/association.go:83-130), so the snapshot shards by
+ * uid_hash64 % n with no data-path collective; the only exchange is the optional all-gather of the per-group delta records.
+ * devices[i] = CUDA ordinal of shard i (NULL: i % device count; a device may repeat — several shards on one GPU).
+ * The group's calls are made from ONE coordinator thread; the engines stay reachable (kr_group_engine) for the per-shard calls
+ * (kr_snapshot_commit_pod_rows, kr_results_fetch, ...), which the caller may issue from any one thread at a time per engine. */
+typedef struct kr_group kr_group;
+int       kr_group_create(const kr_config *per_shard_capacities, const int32_t *devices, uint32_t n, kr_group **out);
+void      kr_group_destroy(kr_group *g);
+uint32_t  kr_group_size(kr_group *g);
+kr_engine *kr_group_engine(kr_group *g, uint32_t shard);
+int       kr_group_device(kr_group *g, uint32_t shard);
+uint32_t  kr_group_shard_of_uid(kr_group *g, uint64_t uid_hash);   /* uid_hash64 % n */
+/* Route a GLOBAL snapshot (host columns in `global`, row counts in `n`) into the shards' pinned arenas — kr_snapshot_begin +
+ * fill of every engine, natively: clusters by UID hash, pods through the (namespace, ray.io/cluster) -> cluster table (orphans by
+ * a hash of that key), head-aux rows after their pod, RayJobs after their RayCluster; List order is kept inside every shard and
+ * every index column is rewritten.  The optional outputs say where each global cluster / pod row went ([n_clusters] / [n_pods]):
+ * the shim maps the shards' result rows back through them.  Follow with kr_group_commit. */
+int       kr_group_route(kr_group *g, const kr_snapshot_bufs *global, const kr_sizes *n, kr_sizes *shard_sizes_out,
+                         uint32_t *cluster_shard_out, uint32_t *cluster_row_out, uint32_t *pod_shard_out, uint32_t *pod_row_out);
+int       kr_group_commit(kr_group *g, uint32_t parts);                                           /* kr_snapshot_commit_parts on every shard, in parallel */
+int       kr_group_reconcile(kr_group *g, const kr_flags *flags, kr_results_view *views /* [n] */); /* kr_reconcile_batch on every shard, in parallel */
+/* The optional exchange step: every device receives every shard's kr_group_result records.  *slot_bytes_out = bytes per shard
+ * slot (32 * the largest shard's n_groups, rounded up to 256; shorter shards are zero padded); host_out (optional, >= n slots)
+ * receives device 0's gathered copy.  NCCL (ncclAllGather from the coordinator thread) when every shard has its own device and
+ * libnccl is loadable, peer copies otherwise; *used_nccl_out says which. */
+int       kr_group_allgather_group_results(kr_group *g, void *host_out, uint64_t host_cap, uint64_t *slot_bytes_out, int *used_nccl_out);
+const char *kr_group_last_error(kr_group *g);
+
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);
 

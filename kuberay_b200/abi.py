@@ -187,6 +187,8 @@ ENGINE_SYMBOLS = [
     "kr_reconcile_batch", "kr_reconcile_device_only", "kr_reconcile_batch_profiled", "kr_results_fetch",
     "kr_hash_batch", "kr_last_profile", "kr_group_results_device", "kr_group_results_copy", "kr_last_error", "kr_algorithmic_bytes",
     "kr_spec_json_emit", "kr_spec_json_emit_arena", "kr_quantity_canonical", "kr_spec_json_last_error", "kr_hash_compare_batch",
+    "kr_group_create", "kr_group_destroy", "kr_group_size", "kr_group_engine", "kr_group_device", "kr_group_shard_of_uid", "kr_group_route",
+    "kr_group_commit", "kr_group_reconcile", "kr_group_allgather_group_results", "kr_group_last_error",
 ]
 
 

@@ -67,6 +67,22 @@ def lib() -> C.CDLL:
         L.kr_quantity_canonical.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
         L.kr_spec_json_last_error.restype = C.c_char_p
         L.kr_hash_compare_batch.argtypes = [C.c_void_p, P(abi.kr_hash_compare_row), C.c_uint32, C.c_void_p, C.c_void_p]
+        L.kr_group_create.argtypes = [P(abi.kr_config), C.c_void_p, C.c_uint32, P(C.c_void_p)]
+        L.kr_group_destroy.argtypes = [C.c_void_p]
+        L.kr_group_destroy.restype = None
+        L.kr_group_size.argtypes = [C.c_void_p]
+        L.kr_group_size.restype = C.c_uint32
+        L.kr_group_engine.argtypes = [C.c_void_p, C.c_uint32]
+        L.kr_group_engine.restype = C.c_void_p
+        L.kr_group_device.argtypes = [C.c_void_p, C.c_uint32]
+        L.kr_group_shard_of_uid.argtypes = [C.c_void_p, C.c_uint64]
+        L.kr_group_shard_of_uid.restype = C.c_uint32
+        L.kr_group_route.argtypes = [C.c_void_p, P(abi.kr_snapshot_bufs), P(abi.kr_sizes), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kr_group_commit.argtypes = [C.c_void_p, C.c_uint32]
+        L.kr_group_reconcile.argtypes = [C.c_void_p, P(abi.kr_flags), C.c_void_p]
+        L.kr_group_allgather_group_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_int)]
+        L.kr_group_last_error.argtypes = [C.c_void_p]
+        L.kr_group_last_error.restype = C.c_char_p
         for name in abi.ENGINE_SYMBOLS:
             getattr(L, name)  # raises AttributeError if the header and the library drifted apart
         _LIB = L
@@ -105,6 +121,65 @@ def _np_view(ptr: int, dtype, count: int) -> np.ndarray:
     dt = np.dtype(dtype)
     buf = (C.c_uint8 * (dt.itemsize * count)).from_address(ptr)
     return np.frombuffer(buf, dtype=dt, count=count)
+
+
+class Group:
+    """kr_group: one engine per shard behind the multi-GPU coordinator of the C ABI (UID-hash sharding)."""
+
+    def __init__(self, per_shard: abi.kr_config, devices: list[int]):
+        self._L = lib()
+        if self._L.kr_device_count() <= 0:
+            raise EngineError(abi.KR_E_NO_DEVICE, "no CUDA device visible (this engine has no CPU fallback)")
+        self.n = len(devices)
+        dv = (C.c_int32 * self.n)(*devices)
+        self._h = C.c_void_p()
+        rc = self._L.kr_group_create(C.byref(per_shard), dv, self.n, C.byref(self._h))
+        if rc != 0:
+            raise EngineError(rc, "kr_group_create failed")
+        self.engines = []
+        for i in range(self.n):  # Engine views over the group's engines (not owned: close() is the group's)
+            e = Engine.__new__(Engine)
+            e._L, e._h, e.sizes, e.cfg = self._L, C.c_void_p(self._L.kr_group_engine(self._h, i)), None, per_shard
+            self.engines.append(e)
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, self._L.kr_group_last_error(self._h).decode())
+
+    def route(self, snap: Snapshot):
+        """kr_group_route: -> (shard sizes, cluster shard, cluster row, pod shard, pod row)."""
+        d = snap.dims
+        sizes, bufs = snap.sizes(), snap.bufs()
+        ss = (abi.kr_sizes * self.n)()
+        cs, cr = np.zeros(d["clusters"], np.uint32), np.zeros(d["clusters"], np.uint32)
+        ps, pr = np.zeros(d["pods"], np.uint32), np.zeros(d["pods"], np.uint32)
+        self._check(self._L.kr_group_route(self._h, C.byref(bufs), C.byref(sizes), ss, cs.ctypes.data, cr.ctypes.data, ps.ctypes.data, pr.ctypes.data))
+        for i, e in enumerate(self.engines):
+            e.sizes = abi.kr_sizes.from_buffer_copy(ss[i])
+        return [abi.kr_sizes.from_buffer_copy(s) for s in ss], cs, cr, ps, pr
+
+    def commit(self, parts: int = abi.PART_ALL):
+        self._check(self._L.kr_group_commit(self._h, parts))
+
+    def reconcile(self, flags: abi.kr_flags, copy: bool = True) -> list[abi.Results]:
+        views = (abi.kr_results_view * self.n)()
+        self._check(self._L.kr_group_reconcile(self._h, C.byref(flags), views))
+        return [e._results(views[i], copy) for i, e in enumerate(self.engines)]
+
+    def allgather_group_results(self) -> tuple[np.ndarray, int, bool]:
+        """-> (device 0's gathered records [n_shards, slot/32] of group_result_dtype, slot bytes, used NCCL)."""
+        slot, used = C.c_uint64(), C.c_int()
+        self._check(self._L.kr_group_allgather_group_results(self._h, None, 0, C.byref(slot), C.byref(used)))
+        out = np.zeros(max(slot.value * self.n, 32), dtype=np.uint8)
+        self._check(self._L.kr_group_allgather_group_results(self._h, out.ctypes.data, out.size, C.byref(slot), C.byref(used)))
+        return out[:slot.value * self.n].view(abi.group_result_dtype).reshape(self.n, -1), slot.value, bool(used.value)
+
+    def close(self):
+        if self._h:
+            for e in self.engines:
+                e._h = C.c_void_p()
+            self._L.kr_group_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 class Engine:
