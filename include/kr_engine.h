@@ -551,6 +551,72 @@ int       kr_group_reconcile(kr_group *g, const kr_flags *flags, kr_results_view
 int       kr_group_allgather_group_results(kr_group *g, void *host_out, uint64_t host_cap, uint64_t *slot_bytes_out, int *used_nccl_out);
 const char *kr_group_last_error(kr_group *g);
 
+/* ---- native event-driven packer / interner (the step BEFORE the path; host code).
+ * The shim's informer handlers (watch set raycluster_controller.go:1525-1533, cache universe internal/managercache/cache.go:16-36)
+ * call the upsert / delete entry points as events arrive; kr_packer_flush brings the device copy up to date before an epoch:
+ * only the pod rows the events touched, the small RayCluster / group / head / RayJob tables when one of them changed, and the
+ * muted-spec JSON (kr_spec_json_emit, re-emitted only when metadata.generation moved) cross PCIe.  The packer owns an engine
+ * created with KR_OPT_FIXED_LAYOUT for the given capacities; kr_packer_engine() is the handle for kr_reconcile_batch etc.
+ * Strings are interned here (kr_packer_string turns a result's id back into bytes).  One caller thread at a time. */
+typedef struct kr_str { const char *p; uint32_t n; } kr_str;   /* not NUL-terminated; p == NULL: absent (label / annotation / field not there) */
+typedef struct kr_pod_obj {            /* what the path reads of a *corev1.Pod */
+  kr_str ns, name;
+  kr_str cluster, group, replica_name, replica_index;  /* labels ray.io/cluster, ray.io/group, ray.io/worker-group-replica-name / -index (text; strconv.Atoi here) */
+  uint8_t node_type, phase, ready_cond;  /* KR_NT_*, KR_PHASE_*, PodReady condition as KR_COND_* */
+  uint8_t restart_never, ray_terminated, has_deletion_ts;
+  uint8_t head_ready_status, reserved_;  /* the rest is read only for node_type == KR_NT_HEAD */
+  kr_str head_ready_reason, head_ready_msg;  /* FindHeadPodReadyCondition (utils/util.go:81-124) */
+  kr_str pod_ip, recreate_hash, kuberay_version;  /* status.podIP; annotations ray.io/upgrade-strategy-recreate-hash, ray.io/kuberay-version */
+} kr_pod_obj;
+typedef struct kr_group_obj {          /* WorkerGroupSpec (apis/ray/v1/raycluster_types.go:157-207) + its expectation bit */
+  kr_str name;
+  int32_t replicas, min_replicas, max_replicas, num_hosts;
+  uint32_t flags;                      /* KR_GF_* */
+  const kr_str *workers_to_delete; uint32_t n_workers_to_delete;
+} kr_group_obj;
+typedef struct kr_cluster_obj {
+  kr_str ns, name, uid;
+  uint64_t resource_version, generation;  /* epoch keys; the spec JSON is re-emitted only when generation moves */
+  uint32_t flags;                      /* KR_CF_* */
+  uint8_t suspend_status, ext_err_kind, old_state, svc_count, svc_ip_kind;
+  uint8_t spec_json_verbatim;          /* 1: spec_json already IS json.Marshal(mute(spec)) (marshalled by the Go side): stored as is */
+  uint8_t reserved_[2];
+  kr_str ext_err_msg;
+  int32_t old_counts[5];
+  uint8_t old_cond_status[5], old_cond_variant[5], reserved2_[6];
+  kr_str old_head_ready_reason, old_head_ready_msg, old_replica_failure_msg;
+  kr_str old_head[4];                  /* podIP, serviceIP, podName, serviceName */
+  kr_str svc_ip, svc_name, status_summary;
+  const kr_group_obj *groups; uint32_t n_groups;
+  const uint8_t *spec_json; uint64_t spec_json_len;  /* .spec as JSON text, any key order */
+} kr_cluster_obj;
+typedef struct kr_job_obj { kr_str ns, name, cluster_name, status_summary; } kr_job_obj;
+typedef struct kr_packer kr_packer;
+enum { KR_PACK_POD_ROWS = 8, KR_PACK_FULL = 16 };  /* kr_packer_flush mode bits, beside KR_PART_OBJECTS / KR_PART_JSON */
+int        kr_packer_create(const kr_config *capacities, kr_packer **out);
+void       kr_packer_destroy(kr_packer *p);
+kr_engine *kr_packer_engine(kr_packer *p);
+int        kr_packer_set_kuberay_version(kr_packer *p, kr_str version);  /* utils.KUBERAY_VERSION; default "nightly" */
+int        kr_packer_pod_upsert(kr_packer *p, const kr_pod_obj *pod);      /* Add / Update */
+int        kr_packer_pod_delete(kr_packer *p, kr_str ns, kr_str name);
+int        kr_packer_cluster_upsert(kr_packer *p, const kr_cluster_obj *c);
+int        kr_packer_cluster_delete(kr_packer *p, kr_str ns, kr_str name);
+int        kr_packer_job_upsert(kr_packer *p, const kr_job_obj *j);
+int        kr_packer_job_delete(kr_packer *p, kr_str ns, kr_str name);
+int        kr_packer_flush(kr_packer *p, uint32_t *mode_out);
+int        kr_packer_sizes(kr_packer *p, kr_sizes *out);
+int        kr_packer_bufs(kr_packer *p, kr_snapshot_bufs *out);            /* the arenas the packer maintains (read-only for the caller) */
+uint32_t   kr_packer_intern(kr_packer *p, kr_str s);                       /* e.g. kr_flags.id_head_not_found_reason */
+int        kr_packer_string(kr_packer *p, uint32_t id, kr_str *out);
+int64_t    kr_packer_cluster_row(kr_packer *p, kr_str ns, kr_str name);    /* -1: not packed */
+int64_t    kr_packer_pod_row(kr_packer *p, kr_str ns, kr_str name);
+int        kr_packer_pod_key(kr_packer *p, uint32_t row, kr_str *ns, kr_str *name);  /* act_pod_idx -> the Pod to delete */
+/* The epoch a record belongs to: Reconcile(req) trusts the record of `req` only if its own cache read of the RayCluster shows the
+ * resourceVersion packed here and no Pod event arrived since the flush (podset version) — else it takes the per-object Go path. */
+int        kr_packer_epoch(kr_packer *p, uint64_t *epoch, uint64_t *podset_version);
+int        kr_packer_cluster_epoch(kr_packer *p, uint32_t cluster_row, uint64_t *resource_version, uint64_t *generation);
+const char *kr_packer_last_error(kr_packer *p);
+
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);
 

@@ -163,6 +163,38 @@ class kr_results_view(C.Structure):
                 ("create_extent", C.c_uint32), ("act_extent", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class kr_str(C.Structure):
+    _fields_ = [("p", C.c_char_p), ("n", C.c_uint32)]
+
+
+class kr_pod_obj(C.Structure):
+    _fields_ = [("ns", kr_str), ("name", kr_str), ("cluster", kr_str), ("group", kr_str), ("replica_name", kr_str), ("replica_index", kr_str),
+                ("node_type", C.c_uint8), ("phase", C.c_uint8), ("ready_cond", C.c_uint8), ("restart_never", C.c_uint8), ("ray_terminated", C.c_uint8),
+                ("has_deletion_ts", C.c_uint8), ("head_ready_status", C.c_uint8), ("reserved_", C.c_uint8),
+                ("head_ready_reason", kr_str), ("head_ready_msg", kr_str), ("pod_ip", kr_str), ("recreate_hash", kr_str), ("kuberay_version", kr_str)]
+
+
+class kr_group_obj(C.Structure):
+    _fields_ = [("name", kr_str), ("replicas", C.c_int32), ("min_replicas", C.c_int32), ("max_replicas", C.c_int32), ("num_hosts", C.c_int32),
+                ("flags", C.c_uint32), ("workers_to_delete", C.POINTER(kr_str)), ("n_workers_to_delete", C.c_uint32)]
+
+
+class kr_cluster_obj(C.Structure):
+    _fields_ = [("ns", kr_str), ("name", kr_str), ("uid", kr_str), ("resource_version", C.c_uint64), ("generation", C.c_uint64), ("flags", C.c_uint32),
+                ("suspend_status", C.c_uint8), ("ext_err_kind", C.c_uint8), ("old_state", C.c_uint8), ("svc_count", C.c_uint8), ("svc_ip_kind", C.c_uint8),
+                ("spec_json_verbatim", C.c_uint8), ("reserved_", C.c_uint8 * 2), ("ext_err_msg", kr_str), ("old_counts", C.c_int32 * 5), ("old_cond_status", C.c_uint8 * 5),
+                ("old_cond_variant", C.c_uint8 * 5), ("reserved2_", C.c_uint8 * 6), ("old_head_ready_reason", kr_str), ("old_head_ready_msg", kr_str),
+                ("old_replica_failure_msg", kr_str), ("old_head", kr_str * 4), ("svc_ip", kr_str), ("svc_name", kr_str), ("status_summary", kr_str),
+                ("groups", C.POINTER(kr_group_obj)), ("n_groups", C.c_uint32), ("spec_json", C.c_char_p), ("spec_json_len", C.c_uint64)]
+
+
+class kr_job_obj(C.Structure):
+    _fields_ = [("ns", kr_str), ("name", kr_str), ("cluster_name", kr_str), ("status_summary", kr_str)]
+
+
+PACK_POD_ROWS, PACK_FULL = 8, 16
+
+
 class kr_hash_compare_row(C.Structure):
     _fields_ = [("goal_spec_json", C.c_char_p), ("goal_spec_len", C.c_uint64), ("cluster_hash", C.c_char_p), ("cluster_hash_len", C.c_uint32),
                 ("num_worker_groups", C.c_char_p), ("num_worker_groups_len", C.c_uint32), ("partial", C.c_uint8), ("reserved_", C.c_uint8 * 7)]
@@ -189,6 +221,10 @@ ENGINE_SYMBOLS = [
     "kr_spec_json_emit", "kr_spec_json_emit_arena", "kr_quantity_canonical", "kr_spec_json_last_error", "kr_hash_compare_batch",
     "kr_group_create", "kr_group_destroy", "kr_group_size", "kr_group_engine", "kr_group_device", "kr_group_shard_of_uid", "kr_group_route",
     "kr_group_commit", "kr_group_reconcile", "kr_group_allgather_group_results", "kr_group_last_error",
+    "kr_packer_create", "kr_packer_destroy", "kr_packer_engine", "kr_packer_set_kuberay_version", "kr_packer_pod_upsert", "kr_packer_pod_delete",
+    "kr_packer_cluster_upsert", "kr_packer_cluster_delete", "kr_packer_job_upsert", "kr_packer_job_delete", "kr_packer_flush", "kr_packer_sizes", "kr_packer_bufs",
+    "kr_packer_intern", "kr_packer_string", "kr_packer_cluster_row", "kr_packer_pod_row", "kr_packer_pod_key", "kr_packer_epoch",
+    "kr_packer_cluster_epoch", "kr_packer_last_error",
 ]
 
 

@@ -18,7 +18,7 @@ HEADER = os.path.join(ROOT, "include", "kr_engine.h")
 
 def test_library_exports_every_symbol_the_header_declares(engine_lib):
     text = open(HEADER).read()
-    declared = set(re.findall(r"^(?:int|void|uint32_t|kr_engine|const char) *\*? *(kr_[a-z_0-9]+)\s*\(", text, flags=re.M))
+    declared = set(re.findall(r"^(?:int|void|uint32_t|int64_t|kr_engine|const char) *\*? *(kr_[a-z_0-9]+)\s*\(", text, flags=re.M))
     assert declared == set(abi.ENGINE_SYMBOLS), declared ^ set(abi.ENGINE_SYMBOLS)
     for name in declared:
         assert hasattr(engine_lib, name), name
