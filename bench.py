@@ -123,11 +123,42 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(seen), "samples": len(mhz)}
 
 
-def build_workload(name: str, rank: int, world: int):
-    """Global snapshot = world x (workload per GPU), sharded by cluster-UID hash; weak scaling."""
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this rank (and so the engine's pinned arenas, allocated after this call) to the CPUs of its GPU's NUMA node: eight
+    ranks uploading 66 MB each out of remote memory were what bent the round-1 e2e scaling curve (GPUs 0-3 / 4-7 sit on
+    different nodes).  Best effort: a restricted cgroup keeps what it allows."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cpus) & allowed)
+        if use:
+            os.sched_setaffinity(0, use)
+            return f"node {node}: {len(use)} cpus"
+        return f"node {node}: no allowed cpu"
+    except Exception as ex:  # noqa: BLE001
+        return f"not bound ({type(ex).__name__})"
+
+
+def build_workload(name: str, rank: int, world: int, strong: bool = False):
+    """Global snapshot = world x (workload per GPU), sharded by cluster-UID hash; weak scaling — or, with
+    --scaling strong, the fixed workload split over the ranks (the literal BASELINE.json metric: one 10k x 100 snapshot at 1/2/4/8)."""
     from kuberay_b200 import synthetic
     params = synthetic.config(name)
-    if world > 1:
+    if world > 1 and not strong:
         params.n_clusters *= world
     snap, flags = synthetic.generate(params)
     if world > 1:
@@ -212,6 +243,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also all-gather the per-group delta records over NCCL each step (N>1)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: the workload per GPU (default); strong: the workload once, split over the GPUs")
+    ap.add_argument("--no-pack-leg", action="store_true", help="skip the e2e_with_pack leg (tools/pack_bench)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -231,11 +264,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from kuberay_b200.engine import Engine
 
-    snap, flags, params = build_workload(args.workload, rank, world)
+    snap, flags, params = build_workload(args.workload, rank, world, strong=args.scaling == "strong")
     # the production configuration in every leg: the shim consumes the records + the compact action list + the replica indices,
     # not the full per-cluster pod lists (kr_flags.fetch_pod_lists = 0; they are a verification / debugging output)
     flags.fetch_pod_lists = 0
@@ -289,6 +323,18 @@ def main():
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     n_kernels = eng.last_profile()["n_kernels"]
+    # the same graph without the hash kernel: the match -> decide chain on its own (what pipeline_roofline is quoted on)
+    flags.skip_hash = 1
+    for _ in range(3):
+        l2_flush(); step_device()
+    chain_ms = 0.0
+    for _ in range(args.steps):
+        l2_flush()
+        chain_ms += step_device()
+    chain_ms /= args.steps
+    flags.skip_hash = 0
+    for _ in range(2):
+        l2_flush(); step_device()
 
     # ---------------- e2e: host buffers through the C ABI (commit = H2D, reconcile_batch = kernels + D2H)
     # D2H = every cluster / group / RayJob record, the hashes, the workersToDelete resolutions, the compact action list and the
@@ -363,12 +409,11 @@ def main():
         vals = np.stack([views[c][rows].view(np.uint32) for c in pod_cols], axis=1)  # the handlers have the new rows in hand
         t0 = time.perf_counter()
         eng.commit(_abi.PART_OBJECTS)
-        obj_bytes = eng.last_profile()["h2d_bytes"]
         eng.commit_pod_values(rows, vals)
         eng.reconcile(flags, copy=False)
         inc_s += time.perf_counter() - t0
         inc_prof = eng.last_profile()
-        inc_bytes = inc_prof["h2d_bytes"] + obj_bytes
+        inc_bytes = inc_prof["h2d_bytes"]  # both commits of the epoch
         freed = gone
     barrier()
     # host packing stand-in (not in e2e): copying pre-packed columns into the pinned arenas
@@ -426,9 +471,10 @@ def main():
                         "frac_of_chip": rate / (n_sched * per_sched_peak), "schedulers_with_a_warp": busy, "frac_of_busy_schedulers": rate / (busy * per_sched_peak)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {params.n_clusters // world} RayClusters x {params.pods_per_cluster} pods per GPU ({int(nc_total)} clusters total), {params.groups} worker group(s), 100 clusters/namespace, pods in shuffled List order",
                        "sharding": "cluster-UID hash % n_gpus, no data-path collective" + (" + NCCL all-gather of the per-group delta records" if gather is not None else ""),
+                       "numa": numa,
                        "l2": "flushed between timed steps (512 MiB memset, excluded)", "timing": "CUDA events on the engine stream per step, max over ranks",
                        "hash": "SHA-1+base32hex of every spec JSON recomputed every step (as the reference does)"},
             "e2e": {"value": nc_total * args.steps / (pipe_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": pipe_ms / args.steps,
@@ -450,14 +496,34 @@ def main():
             "algorithmic_bytes": alg,
             "pass_roofline": {"achieved": alg["pass"] / (dev_ms / args.steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg["pass"] / (dev_ms / args.steps / 1e3) / 1e9 / peak,
                               "note": "all algorithmic bytes of one pass (hash + match/decide) over the graph replay time of the value leg"},
-            "pipeline_roofline": {"achieved": alg["match"] / (non_hash_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg["match"] / (non_hash_ms / 1e3) / 1e9 / peak,
-                                  "kernels": "clear+build_tables+match+place+decide+creates, each timed alone (serialised, event-bracketed)", "avg_ms": non_hash_ms},
+            "pipeline_roofline": {"achieved": alg["match"] / (chain_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg["match"] / (chain_ms / 1e3) / 1e9 / peak,
+                                  "kernels": "clear+build_tables+match+decide as one graph replay with the hash kernel skipped (kr_flags.skip_hash), CUDA events, L2 flushed", "avg_ms": chain_ms,
+                                  "serialised_sum_ms": non_hash_ms},
             "hash_roofline": {"achieved": alg["hash"] / (kavg.get("k_hash", float("nan")) / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": alg["hash"] / (kavg.get("k_hash", float("nan")) / 1e3) / 1e9 / peak, "avg_ms": kavg.get("k_hash")},
             "hash_alu_view": hash_alu,
             "wall_ms_timed_region": wall_ms,
             "results_check": {"n_actions": int(res.n_actions), "n_create_total": int(res.n_create_total), "n_orphans": int(res.n_orphans)},
         }
+        if world == 1 and not args.no_pack_leg and args.workload in ("C3", "C2"):
+            # e2e THROUGH the native packer (tools/pack_bench.cpp: plain C++ on the C ABI, as the cgo shim would be): per epoch the
+            # informer events of a 1 % pod churn + 2 % RayCluster updates are applied natively (interning, row placement),
+            # kr_packer_flush uploads what changed, kr_reconcile_batch returns every record
+            exe = os.path.join(ROOT, "tools", "pack_bench")
+            try:
+                out = subprocess.run([exe, str(params.n_clusters), str(params.pods_per_cluster), str(args.steps), "3"], capture_output=True, text=True, timeout=600)
+                pb = json.loads(out.stdout.strip().splitlines()[-1])
+                epoch = pb["flush_ms"] + pb["reconcile_ms"]
+                line["e2e_with_pack"] = {
+                    "value": params.n_clusters / (epoch / 1e3), "unit": UNIT, "ms_per_step": epoch, "flush_ms": pb["flush_ms"], "reconcile_ms": pb["reconcile_ms"],
+                    "h2d_bytes_per_step": pb["h2d_bytes_per_epoch"], "d2h_bytes_per_step": pb["d2h_bytes_per_epoch"],
+                    "events_per_step": pb["events_per_epoch"], "event_handling_ms_per_step": pb["events_ms"],
+                    "value_with_event_handling_on_the_critical_path": pb["reconciles_per_s"], "initial_load_pod_upserts_per_s": pb["pod_upserts_per_s"],
+                    "note": "native packer (kr_packer_*): the epoch = kr_packer_flush (changed pod rows + small object tables, filled natively from the event "
+                            "stream) + kr_reconcile_batch; event handlers run as events arrive (off the epoch's critical path in the shim) — their cost is "
+                            "given beside it, and the last figure puts it ON the critical path"}
+            except Exception as ex:  # noqa: BLE001
+                line["e2e_with_pack"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             arm = CpuArm(snap)

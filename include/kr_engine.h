@@ -385,7 +385,7 @@ typedef struct kr_profile {
   uint32_t n_kernels;                       /* kernels launched by the last batch (our own, not library) */
   float    kernel_ms[KR_MAX_KERNEL_TIMES];  /* valid only after kr_reconcile_batch_profiled */
   const char *kernel_name[KR_MAX_KERNEL_TIMES];
-  uint64_t h2d_bytes, d2h_bytes;            /* bytes moved by the last commit / the last results fetch */
+  uint64_t h2d_bytes, d2h_bytes;            /* bytes uploaded by the commits since the previous pass / moved by the last results fetch */
 } kr_profile;
 
 /* --------------------------------------------------------- entry points */

@@ -221,6 +221,7 @@ struct kr_engine {
   bool snap_has_mh = false;     // some worker group has numOfHosts > 1
   uint32_t snap_max_groups = 0; // most worker groups in one RayCluster
   bool ran_bucket = false;
+  uint64_t h2d_accum = 0;       // bytes uploaded by the commits since the last pass (kr_profile.h2d_bytes)
   // hash order: message ids by descending SHA-1 block count, rebuilt at every commit from c_json_len
   uint32_t *h_order = nullptr, *d_order = nullptr;
   cudaEvent_t ev_order = nullptr;  // the upload of h_order has left the pinned buffer
@@ -579,6 +580,7 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
     CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 48, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
     e->order_pending = false;
+    e->h2d_accum = 0;  // (kr_profile.h2d_bytes keeps the sum of the commits that fed this pass)
     if (!e->h2d_timed) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
@@ -909,7 +911,7 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));
   if ((parts & KR_PART_ALL) == KR_PART_ALL) e->committed_full = true;
   e->h2d_timed = false;
-  e->prof.h2d_bytes = bytes;
+  e->prof.h2d_bytes = (e->h2d_accum += bytes);
   e->committed = true;
   return KR_OK;
 }
@@ -966,7 +968,7 @@ static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));
   CK(cudaEventRecord(e->ev_cols, e->scopy));  // ev_json keeps pointing at the last JSON upload: the hash need not wait for the patch
   e->h2d_timed = false;
-  e->prof.h2d_bytes = 32 * (size_t)n;  // row list + the 28-byte row payload (pulled one 32-byte sector per value in the rows-only variant)
+  e->prof.h2d_bytes = (e->h2d_accum += 32 * (size_t)n);  // row list + the 28-byte row payload (pulled one 32-byte sector per value in the rows-only variant)
   e->committed = true;
   return KR_OK;
 }

@@ -18,8 +18,10 @@
 // Everything an epoch needs beyond the changed rows is already resident in HBM: no per-epoch repack, no per-epoch full upload.
 #include <algorithm>
 #include <cstring>
+#include <deque>
 #include <queue>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <vector>
 
@@ -68,8 +70,8 @@ struct kr_packer {
   kr_snapshot_bufs b{};
   std::string err;
   // interner
-  std::unordered_map<std::string, uint32_t> ids;
-  std::vector<std::string> strs;
+  std::unordered_map<std::string_view, uint32_t> ids;   // views into `strs` (a deque: elements never move)
+  std::deque<std::string> strs;
   // pods
   std::unordered_map<Key, uint32_t, KeyHash> pod_row;     // (ns id, name id) -> row
   std::vector<Key> row_key;                                // row -> key ({0,0}: free)
@@ -92,12 +94,11 @@ struct kr_packer {
 
   uint32_t intern(const kr_str &s) {
     if (!s.p) return KR_ID_ABSENT;
-    std::string k(s.p, s.n);
-    auto it = ids.find(k);
+    auto it = ids.find(std::string_view(s.p, s.n));  // no allocation on the hit path
     if (it != ids.end()) return it->second;
     uint32_t id = (uint32_t)strs.size();
-    strs.push_back(k);
-    ids.emplace(std::move(k), id);
+    strs.emplace_back(s.p, s.n);
+    ids.emplace(std::string_view(strs.back()), id);
     return id;
   }
   uint32_t intern0(const kr_str &s) { return (s.p && s.n) ? intern(s) : 0u; }  // HeadInfo-like fields: "" is encoded as 0
@@ -186,8 +187,8 @@ int kr_packer_create(const kr_config *capacities, kr_packer **out) {
   memset(&p->sizes, 0, sizeof p->sizes);
   rc = kr_snapshot_begin(p->e, &p->sizes, &p->b);  // fixed layout: these pointers stay valid for the packer's lifetime
   if (rc) { kr_engine_destroy(p->e); delete p; return rc; }
-  p->strs = {"<absent>", ""};
-  p->ids.emplace("", 1u);
+  p->strs.emplace_back("<absent>"); p->strs.emplace_back("");
+  p->ids.emplace(std::string_view(p->strs[1]), 1u);
   *out = p;
   return KR_OK;
 }
