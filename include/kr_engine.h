@@ -617,6 +617,75 @@ int        kr_packer_epoch(kr_packer *p, uint64_t *epoch, uint64_t *podset_versi
 int        kr_packer_cluster_epoch(kr_packer *p, uint32_t cluster_row, uint64_t *resource_version, uint64_t *generation);
 const char *kr_packer_last_error(kr_packer *p);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Pod metadata builder (first part): what createHeadPod / createWorkerPodWithIndex put into the new Pod's
+ * ObjectMeta — the part of buildHeadPod / buildWorkerPod that depends on the engine's create tuples (group, replica index,
+ * host index).  Host-side; no GPU.  Replaces, for the metadata only:
+ *   utils.PodName            (controllers/ray/utils/util.go:198-215)   kr_pod_name
+ *   utils.CheckName          (util.go:217-240)                          kr_check_name
+ *   utils.CheckLabel         (util.go:247-265)                          kr_check_label
+ *   utils.GenerateRayWorkerReplicaGroupName (util.go:375-379)           kr_pod_creates_expand (names "<group>-<5 chars>")
+ *   mergeLabels + labelPod   (common/pod.go:1276-1283, 775-799)         kr_pod_meta_build
+ *   replica index / name / host index labels (common/pod.go:430-439)    kr_pod_meta_build
+ *   Name | GenerateName, Namespace (common/pod.go:170-178, 353-357)     kr_pod_meta_build
+ *   initTemplateAnnotations, ray.io/ft-enabled, ray.io/external-storage-namespace (common/pod.go:67-75, 85-87, 105-114)
+ *   ray.io/serve label for RayService-owned clusters (common/pod.go:583-588)
+ *   recreate-hash + kuberay-version annotations of the head (raycluster_controller.go:1313-1316)
+ *   the controller ownerReference (raycluster_controller.go:1407, 1429: controllerutil.SetControllerReference)
+ * The container / env / command part of BuildPod (common/pod.go:575-760) is NOT here: it does not depend on the create tuple and
+ * stays in Go. */
+typedef struct kr_kv { kr_str key, value; } kr_kv;
+enum { KR_CRD_RAYCLUSTER = 0, KR_CRD_RAYJOB = 1, KR_CRD_RAYSERVICE = 2 };  /* utils.GetCRDType(instance.Labels[ray.io/originated-from-crd]) */
+typedef struct kr_podmeta_cluster {
+  kr_str name, ns, uid;
+  kr_str cluster_hash;            /* createHeadPod's clusterHash; absent or "": no hash / version stamps (:1313) */
+  kr_str kuberay_version;         /* utils.KUBERAY_VERSION */
+  kr_str storage_ns_annotation;   /* instance.Annotations[ray.io/external-storage-namespace]; p == NULL: not set */
+  kr_str storage_ns_option;       /* spec.gcsFaultToleranceOptions.externalStorageNamespace; absent or "": not set */
+  uint8_t overwrite_container_cmd;  /* isOverwriteRayContainerCmd(instance) (common/pod.go:62-65) */
+  uint8_t ft_enabled;               /* utils.IsGCSFaultToleranceEnabled (util.go:753-756) */
+  uint8_t crd_type;                 /* KR_CRD_* */
+  uint8_t deterministic_head_name;  /* utils.IsDeterministicHeadPodNameEnabled() (util.go:895-897) */
+  uint8_t gate_multihost_indexing;  /* features.RayMultiHostIndexing */
+  uint8_t reserved[3];
+} kr_podmeta_cluster;
+typedef struct kr_podmeta_group {   /* HeadGroupSpec or one WorkerGroupSpec, as far as the metadata reads it */
+  kr_str group_name;                /* ignored for the head ("headgroup") */
+  int32_t num_of_hosts;             /* ignored for the head */
+  uint32_t n_template_labels, n_group_labels, n_template_annotations;
+  const kr_kv *template_labels;     /* spec.template.metadata.labels */
+  const kr_kv *group_labels;        /* the group's top-level `labels` (they win, common/pod.go:1276-1283) */
+  const kr_kv *template_annotations;/* spec.template.metadata.annotations */
+} kr_podmeta_group;
+typedef struct kr_podmeta_create {  /* one Pod to create */
+  int32_t group;                    /* -1: the head; else index into the worker groups */
+  int32_t replica_index, host_index;/* createWorkerPodWithIndex(..., replicaIndex, hostIndex) (:1363) */
+  kr_str replica_name;              /* replicaGrpName; "" for single-host groups */
+} kr_podmeta_create;
+
+/* Each returns the length of the result (which may exceed cap: nothing is written past cap) or a negative KR_E_*; an empty
+ * input to kr_check_name / kr_check_label is KR_E_INVALID (the reference indexes s[0] and panics). */
+int64_t kr_pod_name(kr_str prefix, uint8_t node_type /* KR_NT_HEAD | KR_NT_WORKER */, uint8_t is_generate_name, char *out, uint64_t cap);
+int64_t kr_check_name(kr_str s, char *out, uint64_t cap);
+int64_t kr_check_label(kr_str s, char *out, uint64_t cap);
+
+/* One JSON object per create, written back to back into out[]; create i owns out[off[i] .. off[i+1]).  Each object is the
+ * ObjectMeta patch in Go's field order and map encoding (keys sorted, strings escaped as encoding/json does):
+ *   {"name"|"generateName":…,"namespace":…,"labels":{…},"annotations":{…},"ownerReferences":[{…}]}
+ * *need = bytes required; KR_E_CAPACITY when cap is too small (off[] is still filled in, so the caller can size and retry). */
+int kr_pod_meta_build(const kr_podmeta_cluster *cluster, const kr_podmeta_group *head, const kr_podmeta_group *groups, uint32_t n_groups,
+                      const kr_podmeta_create *creates, uint32_t n_creates, uint8_t *out, uint64_t cap, uint64_t *off, uint64_t *need);
+
+/* Engine results -> create tuples for ONE RayCluster, in the order the reference issues the Create calls: the head first when
+ * head_create != 0 (:692-699), then group by group (:869-889; multi-host :1081-1094: for every new replica index one generated
+ * replica name and hosts 0..NumOfHosts-1).  group_results / groups are the cluster's n_groups rows, create_idx the engine's arena.
+ * Replica names take 5 characters of the apimachinery rand.String alphabet from a splitmix64 stream seeded with `seed`; they live
+ * in name_buf.  *n_out = tuples required; KR_E_CAPACITY when cap or name_cap is too small. */
+int kr_pod_creates_expand(const kr_group_result *group_results, const kr_podmeta_group *groups, uint32_t n_groups, const int32_t *create_idx,
+                          uint8_t head_create, uint8_t gate_multihost_indexing, uint64_t seed, kr_podmeta_create *out, uint32_t cap,
+                          char *name_buf, uint64_t name_cap, uint32_t *n_out);
+const char *kr_pod_meta_last_error(void);
+
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);
 

@@ -195,6 +195,29 @@ class kr_job_obj(C.Structure):
 PACK_POD_ROWS, PACK_FULL = 8, 16
 
 
+class kr_kv(C.Structure):
+    _fields_ = [("key", kr_str), ("value", kr_str)]
+
+
+CRD_RAYCLUSTER, CRD_RAYJOB, CRD_RAYSERVICE = 0, 1, 2
+
+
+class kr_podmeta_cluster(C.Structure):
+    _fields_ = [("name", kr_str), ("ns", kr_str), ("uid", kr_str), ("cluster_hash", kr_str), ("kuberay_version", kr_str),
+                ("storage_ns_annotation", kr_str), ("storage_ns_option", kr_str), ("overwrite_container_cmd", C.c_uint8), ("ft_enabled", C.c_uint8),
+                ("crd_type", C.c_uint8), ("deterministic_head_name", C.c_uint8), ("gate_multihost_indexing", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+
+
+class kr_podmeta_group(C.Structure):
+    _fields_ = [("group_name", kr_str), ("num_of_hosts", C.c_int32), ("n_template_labels", C.c_uint32), ("n_group_labels", C.c_uint32),
+                ("n_template_annotations", C.c_uint32), ("template_labels", C.POINTER(kr_kv)), ("group_labels", C.POINTER(kr_kv)),
+                ("template_annotations", C.POINTER(kr_kv))]
+
+
+class kr_podmeta_create(C.Structure):
+    _fields_ = [("group", C.c_int32), ("replica_index", C.c_int32), ("host_index", C.c_int32), ("replica_name", kr_str)]
+
+
 class kr_hash_compare_row(C.Structure):
     _fields_ = [("goal_spec_json", C.c_char_p), ("goal_spec_len", C.c_uint64), ("cluster_hash", C.c_char_p), ("cluster_hash_len", C.c_uint32),
                 ("num_worker_groups", C.c_char_p), ("num_worker_groups_len", C.c_uint32), ("partial", C.c_uint8), ("reserved_", C.c_uint8 * 7)]
@@ -225,6 +248,7 @@ ENGINE_SYMBOLS = [
     "kr_packer_cluster_upsert", "kr_packer_cluster_delete", "kr_packer_job_upsert", "kr_packer_job_delete", "kr_packer_flush", "kr_packer_sizes", "kr_packer_bufs",
     "kr_packer_intern", "kr_packer_string", "kr_packer_cluster_row", "kr_packer_pod_row", "kr_packer_pod_key", "kr_packer_epoch",
     "kr_packer_cluster_epoch", "kr_packer_last_error",
+    "kr_pod_name", "kr_check_name", "kr_check_label", "kr_pod_meta_build", "kr_pod_creates_expand", "kr_pod_meta_last_error",
 ]
 
 

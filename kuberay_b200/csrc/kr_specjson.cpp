@@ -574,6 +574,9 @@ int emit_impl(const uint8_t *spec_json, uint64_t len, bool muted, std::string &o
 
 }  // namespace
 
+// for kr_podmeta.cpp: the same Go string encoder
+void kr_go_string_append(std::string &out, const std::string &s) { go_string(out, s); }
+
 // for kr_engine.cu (kr_hash_compare_batch): same emitter, optional truncation of the worker groups
 int kr_specjson_emit_string(const uint8_t *spec_json, uint64_t len, bool muted, long max_groups, std::string &out, long *n_groups) {
   return emit_impl(spec_json, len, muted, out, max_groups, n_groups);

@@ -1,0 +1,195 @@
+"""Pod metadata builder over the C ABI (kr_pod_* in include/kr_engine.h; kuberay_b200/csrc/kr_podmeta.cpp) — SURVEY §8 f3.
+
+Host-side mirror of the reference's names for this step:
+  pod_name / check_name / check_label      utils.PodName / CheckName / CheckLabel (controllers/ray/utils/util.go:198-265)
+  build_pod_meta(cluster, creates, env)    the ObjectMeta of buildHeadPod / buildWorkerPod (raycluster_controller.go:1387-1433) for the
+                                           engine's create tuples: one dict per Pod to create
+  expand_creates(...)                      engine results -> (group, replicaIndex, hostIndex, replicaGrpName) tuples in Create order
+
+Everything is computed by the native library; this file only marshals dicts into the C structs.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+from .engine import EngineError, lib
+
+OVERWRITE_CMD_ANNOT = "ray.io/overwrite-container-cmd"
+FT_ENABLED_ANNOT = "ray.io/ft-enabled"
+STORAGE_NS_ANNOT = "ray.io/external-storage-namespace"
+ORIGINATED_FROM_CRD_LABEL = "ray.io/originated-from-crd"
+CRD_TYPES = {"RayJob": abi.CRD_RAYJOB, "RayService": abi.CRD_RAYSERVICE}  # utils.GetCRDType (util.go:59-64): anything else is RayCluster
+
+
+@dataclass
+class PodMetaEnv:
+    """Process-level inputs of the builder (env vars / feature gates / build constants of the operator)."""
+    kuberay_version: str = "v1.5.0"
+    deterministic_head_name: bool = False    # ENABLE_DETERMINISTIC_HEAD_POD_NAME
+    multihost_indexing_gate: bool = True     # features.RayMultiHostIndexing
+
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = lib()
+    if not _bound:
+        P = C.POINTER
+        for f in (L.kr_check_name, L.kr_check_label):
+            f.argtypes = [abi.kr_str, C.c_char_p, C.c_uint64]
+            f.restype = C.c_int64
+        L.kr_pod_name.argtypes = [abi.kr_str, C.c_uint8, C.c_uint8, C.c_char_p, C.c_uint64]
+        L.kr_pod_name.restype = C.c_int64
+        L.kr_pod_meta_build.argtypes = [P(abi.kr_podmeta_cluster), P(abi.kr_podmeta_group), P(abi.kr_podmeta_group), C.c_uint32,
+                                        P(abi.kr_podmeta_create), C.c_uint32, C.c_void_p, C.c_uint64, P(C.c_uint64), P(C.c_uint64)]
+        L.kr_pod_creates_expand.argtypes = [C.c_void_p, P(abi.kr_podmeta_group), C.c_uint32, C.c_void_p, C.c_uint8, C.c_uint8, C.c_uint64,
+                                            P(abi.kr_podmeta_create), C.c_uint32, C.c_char_p, C.c_uint64, P(C.c_uint32)]
+        L.kr_pod_meta_last_error.restype = C.c_char_p
+        _bound = True
+    return L
+
+
+class _Keep:
+    """Owns the byte strings / arrays the C structs point into for the duration of one call."""
+
+    def __init__(self):
+        self.refs = []
+
+    def s(self, v) -> abi.kr_str:
+        if v is None:
+            return abi.kr_str(None, 0)
+        b = v if isinstance(v, bytes) else str(v).encode("utf-8", "surrogateescape")
+        self.refs.append(b)
+        return abi.kr_str(b, len(b))
+
+    def kvs(self, m: dict | None):
+        items = list((m or {}).items())
+        arr = (abi.kr_kv * max(len(items), 1))()
+        for i, (k, v) in enumerate(items):
+            arr[i].key, arr[i].value = self.s(k), self.s(v)
+        self.refs.append(arr)
+        return arr, len(items)
+
+
+def _err(L, rc):
+    return EngineError(int(rc), (L.kr_pod_meta_last_error() or b"").decode())
+
+
+def _text(fn, s: str, *extra) -> str:
+    L = _lib()
+    b = s.encode("utf-8", "surrogateescape")
+    buf = C.create_string_buffer(len(b) + 16)
+    n = fn(abi.kr_str(b, len(b)), *extra, buf, len(buf))
+    if n < 0:
+        raise _err(L, n)
+    return buf.raw[:n].decode("utf-8", "surrogateescape")
+
+
+def check_name(s: str) -> str:
+    return _text(_lib().kr_check_name, s)
+
+
+def check_label(s: str) -> str:
+    return _text(_lib().kr_check_label, s)
+
+
+def pod_name(prefix: str, node_type: str, is_generate_name: bool) -> str:
+    nt = abi.NT_HEAD if node_type == "head" else abi.NT_WORKER
+    return _text(_lib().kr_pod_name, prefix, nt, 1 if is_generate_name else 0)
+
+
+def _group_struct(keep: _Keep, grp: dict, head: bool) -> abi.kr_podmeta_group:
+    g = abi.kr_podmeta_group()
+    tmeta = ((grp.get("template") or {}).get("metadata") or {})
+    g.group_name = keep.s("headgroup" if head else grp.get("groupName", ""))
+    g.num_of_hosts = 1 if head else int(grp.get("numOfHosts", 1))
+    tl, g.n_template_labels = keep.kvs(tmeta.get("labels"))
+    gl, g.n_group_labels = keep.kvs(grp.get("labels"))
+    ta, g.n_template_annotations = keep.kvs(tmeta.get("annotations"))
+    g.template_labels, g.group_labels, g.template_annotations = tl, gl, ta
+    return g
+
+
+def _cluster_struct(keep: _Keep, cluster: dict, env: PodMetaEnv, cluster_hash: str | None) -> abi.kr_podmeta_cluster:
+    spec = cluster.get("spec") or {}
+    annots = cluster.get("annotations") or {}
+    c = abi.kr_podmeta_cluster()
+    c.name, c.ns, c.uid = keep.s(cluster["name"]), keep.s(cluster.get("namespace", "default")), keep.s(cluster.get("uid", ""))
+    c.cluster_hash = keep.s(cluster_hash or None)
+    c.kuberay_version = keep.s(env.kuberay_version)
+    c.storage_ns_annotation = keep.s(annots.get(STORAGE_NS_ANNOT))
+    ft = spec.get("gcsFaultToleranceOptions")
+    c.storage_ns_option = keep.s((ft or {}).get("externalStorageNamespace") or None)
+    c.overwrite_container_cmd = 1 if str(annots.get(OVERWRITE_CMD_ANNOT, "")).lower() == "true" and OVERWRITE_CMD_ANNOT in annots else 0
+    c.ft_enabled = 1 if (FT_ENABLED_ANNOT in annots and str(annots[FT_ENABLED_ANNOT]).lower() == "true") or ft is not None else 0
+    c.crd_type = CRD_TYPES.get((cluster.get("labels") or {}).get(ORIGINATED_FROM_CRD_LABEL), abi.CRD_RAYCLUSTER)
+    c.deterministic_head_name = 1 if env.deterministic_head_name else 0
+    c.gate_multihost_indexing = 1 if env.multihost_indexing_gate else 0
+    return c
+
+
+def build_pod_meta(cluster: dict, creates: list[tuple[int, int, int, str]], env: PodMetaEnv | None = None, cluster_hash: str | None = None,
+                   raw: bool = False) -> list:
+    """ObjectMeta of every Pod to create.  creates: (group index or -1 for the head, replicaIndex, hostIndex, replicaGrpName).
+
+    raw=True returns the JSON bytes per create exactly as the library wrote them (Go map/field order)."""
+    L = _lib()
+    env = env or PodMetaEnv()
+    keep = _Keep()
+    spec = cluster.get("spec") or {}
+    c = _cluster_struct(keep, cluster, env, cluster_hash)
+    head = _group_struct(keep, spec.get("headGroupSpec") or {}, True)
+    wgs = spec.get("workerGroupSpecs") or []
+    groups = (abi.kr_podmeta_group * max(len(wgs), 1))(*[_group_struct(keep, g, False) for g in wgs])
+    tuples = (abi.kr_podmeta_create * max(len(creates), 1))()
+    for i, (g, ri, hi, rn) in enumerate(creates):
+        tuples[i].group, tuples[i].replica_index, tuples[i].host_index = int(g), int(ri), int(hi)
+        tuples[i].replica_name = keep.s(rn or "")
+    off = (C.c_uint64 * (len(creates) + 1))()
+    need = C.c_uint64()
+    rc = L.kr_pod_meta_build(C.byref(c), C.byref(head), groups, len(wgs), tuples, len(creates), None, 0, off, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise _err(L, rc)
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = L.kr_pod_meta_build(C.byref(c), C.byref(head), groups, len(wgs), tuples, len(creates), buf, need.value, off, C.byref(need))
+    if rc:
+        raise _err(L, rc)
+    b = bytes(buf)
+    parts = [b[off[i]:off[i + 1]] for i in range(len(creates))]
+    return parts if raw else [json.loads(p) for p in parts]
+
+
+def expand_creates(group_results: np.ndarray, create_idx: np.ndarray, groups: list[dict], head_create: bool, env: PodMetaEnv | None = None,
+                   seed: int = 0) -> list[tuple[int, int, int, str]]:
+    """The cluster's create tuples in the order the reference issues the Create calls (kr_pod_creates_expand).
+    group_results: the cluster's rows of Results.groups; create_idx: Results.create_idx (the whole arena)."""
+    L = _lib()
+    env = env or PodMetaEnv()
+    keep = _Keep()
+    gr = np.ascontiguousarray(group_results)
+    ci = np.ascontiguousarray(create_idx, dtype=np.int32)
+    gs = (abi.kr_podmeta_group * max(len(groups), 1))(*[_group_struct(keep, g, False) for g in groups])
+    n = C.c_uint32()
+    args = (gr.ctypes.data if len(gr) else None, gs, len(groups), ci.ctypes.data if len(ci) else None, 1 if head_create else 0,
+            1 if env.multihost_indexing_gate else 0, seed & (2 ** 64 - 1))
+    rc = L.kr_pod_creates_expand(*args, None, 0, None, 0, C.byref(n))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise _err(L, rc)
+    out = (abi.kr_podmeta_create * max(n.value, 1))()
+    name_cap = sum((len(str(g.get("groupName", "")).encode()) + 6) * int(r["n_create"]) for g, r in zip(groups, gr)) + 8
+    names = C.create_string_buffer(name_cap)
+    rc = L.kr_pod_creates_expand(*args, out, n.value, names, name_cap, C.byref(n))
+    if rc:
+        raise _err(L, rc)
+    res = []
+    for i in range(n.value):
+        t = out[i]
+        rn = t.replica_name.p[:t.replica_name.n].decode() if t.replica_name.n else ""
+        res.append((t.group, t.replica_index, t.host_index, rn))
+    return res

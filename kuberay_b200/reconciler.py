@@ -20,6 +20,7 @@ import copy
 from dataclasses import dataclass, field
 
 from . import abi
+from . import podmeta
 from . import snapshot as snapmod
 
 # event reasons (utils/constant.go:337-438)
@@ -199,9 +200,7 @@ class RayClusterReconciler:
             return f"{int(cr['err_arg'])} head pods found {names}. Please delete extra head pods"
         self._stage = "FailedCreateHeadPod"         # :736
         if ha == abi.HEAD_CREATE:                   # :735, createHeadPod :1307-1337
-            pod = self._build_pod(cluster, "head", "headgroup", f"{cname}-head-{cl.gen_suffix()}")
-            pod.setdefault("annotations", {})[snapmod.RECREATE_HASH_ANNOT] = bytes(res.hash[ci]).decode()
-            pod["annotations"][snapmod.KUBERAY_VERSION_ANNOT] = snapmod.KUBERAY_VERSION
+            pod = self._build_pod(cluster, (-1, 0, 0, ""), cluster_hash=bytes(res.hash[ci]).decode())
             cl.create_pod(pod)
             ev(("Normal", EV_CREATED_HEAD_POD, f"Created head Pod {ns}/{pod['name']}"))
         # worker groups in spec order (:751-933)
@@ -251,9 +250,7 @@ class RayClusterReconciler:
             self._stage = "FailedCreateWorkerPod"   # :879,887
             for k in range(int(gr["n_create"])):    # :865-890
                 idx = int(res.create_idx[int(gr["create_off"]) + k])
-                pod = self._build_pod(cluster, "worker", gname, f"{cname}-{gname}-worker-{cl.gen_suffix()}")
-                if self.env.multihost_indexing_gate:
-                    pod["labels"][snapmod.REPLICA_INDEX_LABEL] = str(idx)
+                pod = self._build_pod(cluster, (gi, idx if self.env.multihost_indexing_gate else 0, 0, ""))   # :878 / :887
                 cl.create_pod(pod)
                 ev(("Normal", EV_CREATED_WORKER_POD, f"Created worker Pod {ns}/{pod['name']}"))
             self._stage = "FailedDeleteWorkerPod"   # :922
@@ -295,22 +292,19 @@ class RayClusterReconciler:
             idx = int(res.create_idx[int(gr["create_off"]) + k])
             rname = f"{gname}-{cl.gen_suffix()}"
             for j in range(hosts):
-                pod = self._build_pod(cluster, "worker", gname, f"{cname}-{gname}-worker-{cl.gen_suffix()}")
-                pod["labels"][snapmod.REPLICA_INDEX_LABEL] = str(idx)
-                pod["labels"][snapmod.REPLICA_NAME_LABEL] = rname
-                pod["labels"]["ray.io/replica-host-index"] = str(j)
+                pod = self._build_pod(cluster, (gi, idx, j, rname))   # :1090
                 cl.create_pod(pod)
                 cl.events.append(("Normal", EV_CREATED_WORKER_POD, f"Created worker Pod {ns}/{pod['name']}"))
         return None
 
-    @staticmethod
-    def _build_pod(cluster: dict, node_type: str, group: str, name: str) -> dict:
-        """labelPod (common/pod.go:775-799) — only the labels the selectors read matter to the path."""
-        cname = cluster["name"]
-        return {"namespace": cluster.get("namespace", "default"), "name": name, "phase": "", "restartPolicy": "Always",
-                "labels": {"ray.io/is-ray-node": "yes", snapmod.RAY_CLUSTER_LABEL: cname, snapmod.RAY_NODE_TYPE_LABEL: node_type,
-                           snapmod.RAY_NODE_GROUP_LABEL: group, "ray.io/identifier": f"{cname}-{node_type}"},
-                "annotations": {}}
+    def _build_pod(self, cluster: dict, create: tuple, cluster_hash: str | None = None) -> dict:
+        """The new Pod's ObjectMeta from the native builder (kr_pod_meta_build: buildHeadPod / buildWorkerPod metadata,
+        raycluster_controller.go:1387-1433); the fake API server then turns generateName into a name (5 generated characters)."""
+        env = podmeta.PodMetaEnv(kuberay_version=snapmod.KUBERAY_VERSION, multihost_indexing_gate=bool(self.env.multihost_indexing_gate))
+        meta = podmeta.build_pod_meta(cluster, [create], env, cluster_hash=cluster_hash)[0]
+        name = meta.get("name") or meta["generateName"] + self.client.gen_suffix()
+        return {"namespace": meta["namespace"], "name": name, "phase": "", "restartPolicy": "Always", "labels": meta["labels"],
+                "annotations": meta["annotations"], "ownerReferences": meta["ownerReferences"]}
 
     @staticmethod
     def _should_delete_reason(pod: dict, node_type: str) -> str:
