@@ -375,7 +375,17 @@ typedef struct kr_results_view {
   uint32_t n_actions;              /* pods with action != KEEP (orphans excluded) = sum of act_cnt */
   uint32_t create_extent;          /* entries of create_idx in use (>= n_create_total) */
   uint32_t act_extent;             /* entries of act_pod_idx / act_code in use (>= n_actions) */
-  uint32_t reserved;
+  /* Incremental epochs: after a full pass on the bucket pipeline (kr_flags.fetch_pod_lists == 0) the engine keeps its join tables,
+   * per-cluster pod buckets, digests and results resident on the device.  While the commits that follow are
+   * kr_snapshot_commit_pod_rows / _values and kr_snapshot_commit_parts(KR_PART_OBJECTS and/or KR_PART_JSON) — the informer's Pod and
+   * RayCluster events — and the flags stay the same, the next pass re-matches only the touched pod rows, re-decides only the
+   * RayClusters they (or changed object rows) belong to and returns only those records; every array of this view is still
+   * complete and bit-identical to what a full pass would return.  n_changed / changed_clusters name the records that were
+   * recomputed: n_changed == n_clusters and changed_clusters == NULL after a full pass.  Anything the resident state cannot
+   * absorb (a changed table key or CSR offset, wholesale column commits, different flags, an overflowing bucket) silently
+   * takes the full pass.  KR_NO_INCR=1 in the environment turns the incremental path off. */
+  uint32_t n_changed;
+  const uint32_t          *changed_clusters; /* [n_changed] cluster rows, unordered */
 } kr_results_view;
 
 /* Per-kernel device times of the last kr_reconcile_batch (CUDA events on the engine's streams). */

@@ -160,7 +160,7 @@ class kr_results_view(C.Structure):
                 ("sorted_pod_idx", C.c_void_p), ("sorted_action", C.c_void_p), ("create_idx", C.c_void_p), ("jobs", C.c_void_p),
                 ("act_start", C.c_void_p), ("act_cnt", C.c_void_p), ("act_pod_idx", C.c_void_p), ("act_code", C.c_void_p),
                 ("n_create_total", C.c_uint32), ("n_orphans", C.c_uint32), ("n_actions", C.c_uint32),
-                ("create_extent", C.c_uint32), ("act_extent", C.c_uint32), ("reserved", C.c_uint32)]
+                ("create_extent", C.c_uint32), ("act_extent", C.c_uint32), ("n_changed", C.c_uint32), ("changed_clusters", C.c_void_p)]
 
 
 class kr_str(C.Structure):
@@ -289,6 +289,8 @@ class Results:
         self.n_create_total = 0
         self.n_orphans = 0
         self.n_actions = 0
+        self.n_changed = sizes.n_clusters   # records recomputed by the pass (engine: fewer after an incremental epoch)
+        self.changed_clusters = None
 
     def hash_strings(self):
         return [bytes(r).decode("ascii", "replace") for r in self.hash]

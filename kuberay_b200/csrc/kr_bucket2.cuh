@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
 struct Decide2Args {
   SnapDev s; ScratchDev sc; ResDev r; Sizes n; kr_flags f;
   uint32_t create_cap;
-  int phase;  // 0: every RayCluster; 1: only the clusters phase 0 deferred (Recreate gate waiting for the hash kernel)
+  int phase;  // 0: every RayCluster; 1: only the clusters phase 0 deferred (Recreate gate waiting for the hash kernel);
+              // 2: only the clusters an incremental epoch marked dirty (kr_incr.cuh) — digests resident, places reused while they suffice
 };
 
 // reconcilePods (raycluster_controller.go:619-935) + calculateStatus (:1552-1719) for one RayCluster whose bucket (<= 32*K pods,
@@ -179,6 +180,9 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
     mine = c < a.r.totals[4];
     if (mine) { c = a.sc.deferred_list[c]; ci.word = __ldg(&a.sc.cl_in[32 * (size_t)c + lane]); }
+  } else if (a.phase == 2) {  // the dirty list of an incremental epoch (input records rewritten by k_inc_prepare: no read-only path)
+    mine = c < __ldcg(&a.sc.inc[KR_INC_DIRTY]) && !__ldcg(&a.sc.inc[KR_INC_VOID]) && !__ldcg(&a.sc.inc[KR_INC_STRUCTURAL]);
+    if (mine) { c = a.sc.dirty_list[c]; ci.word = __ldcg(&a.sc.cl_in[32 * (size_t)c + lane]); }
   }
   if (KR_ATTEMPT_VOID(a.r.totals)) mine = false;  // (every warp still walks through the CTA barriers below)
   // pod count + first head, and the whole bucket beside them (stale records past the count are masked once it is here)
@@ -195,6 +199,11 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   const uint32_t cf = ci.flags(), G = ci.group_cnt(), g0 = ci.group_off();
   const uint8_t suspend_status = ci.suspend_status(), ext_err = ci.ext_err_kind(), old_prov = ci.cond_status(KR_COND_PROVISIONED);
   const bool gate = a.f.gate_status_conditions != 0;
+  uint32_t old_create = 0;  // phase 2: pods this cluster asked for in the resident results (they leave the running total)
+  if (a.phase == 2 && mine) {
+    for (uint32_t gi = lane; gi < G; gi += 32) old_create += a.r.groups[g0 + gi].n_create;
+    old_create = __reduce_add_sync(0xFFFFFFFFu, old_create);
+  }
   // first head in List order = the smallest pod index among the heads (k_match2), with its head-aux row
   uint32_t head_pod = 0xFFFFFFFFu;
   int32_t head_aux = -1;
@@ -492,6 +501,31 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
     if (mine && lane == 0) {
       a.r.act_start[c] = act_off; a.r.act_cnt[c] = n_act;
       if (deferred) a.sc.cact[c] = n_create_cluster;  // phase 1 corrects the count of pods to create if the cluster turns into a Recreate
+      a.sc.act_res[c] = slots; a.sc.cre_res[c] = n_create_cluster;  // what an incremental epoch may reuse
+    }
+  } else if (a.phase == 2) {  // incremental epoch: keep the cluster's places while they suffice, else take new ones at the cursors
+    unsigned long long base = 0;
+    uint32_t need = 0;  // bit 0: new action slots, bit 1: new create slots
+    if (mine && lane == 0) {
+      const uint32_t old_act = a.r.act_cnt[c];
+      need = (n_act > a.sc.act_res[c] ? 1u : 0u) | (n_create_cluster > a.sc.cre_res[c] ? 2u : 0u);
+      if (need) base = atomicAdd(reinterpret_cast<unsigned long long *>(&a.r.totals[8]), ((unsigned long long)((need & 2u) ? n_create_cluster : 0u) << 32) | ((need & 1u) ? n_act : 0u));
+      if ((need & 1u) && (uint64_t)(uint32_t)base + n_act > a.n.n_pods) a.sc.inc[KR_INC_VOID] = 1u;          // the action list is full of abandoned runs:
+      if ((need & 2u) && (uint64_t)(uint32_t)(base >> 32) + n_create_cluster > a.create_cap) a.sc.inc[KR_INC_VOID] = 1u;  // a full pass packs it again
+      if (n_act != old_act) atomicAdd(&a.r.totals[2], n_act - old_act);
+      if (n_create_cluster != old_create) atomicAdd(&a.r.totals[6], n_create_cluster - old_create);
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0); need = __shfl_sync(0xFFFFFFFFu, need, 0);
+    if (mine) {
+      act_off = (need & 1u) ? (uint32_t)base : a.r.act_start[c];
+      create_off = (need & 2u) ? (uint32_t)(base >> 32) : (G ? a.sc.gcreate[g0] : 0u);
+      if ((need & 1u) && (uint64_t)act_off + n_act > a.n.n_pods) mine = false;
+      if ((need & 2u) && (uint64_t)create_off + n_create_cluster > a.create_cap) mine = false;
+      if (mine && lane == 0) {
+        a.r.act_start[c] = act_off; a.r.act_cnt[c] = n_act;
+        if (need & 1u) a.sc.act_res[c] = n_act;
+        if (need & 2u) a.sc.cre_res[c] = n_create_cluster;
+      }
     }
   } else if (mine) {  // phase 1: the places phase 0 reserved
     act_off = a.r.act_start[c];
@@ -517,7 +551,7 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
         // keep the arena position phase 0 gave this group (a Recreate leaves a gap: n_create is now 0)
         off = a.sc.gcreate[g];
       }
-      if (lane == 0) { a.r.groups[g].create_off = off; if (a.phase == 0) a.sc.gcreate[g] = off; }
+      if (lane == 0) { a.r.groups[g].create_off = off; if (a.phase != 1) a.sc.gcreate[g] = off; }
       if (want == 0) continue;
       if ((uint64_t)off + want > a.create_cap) { off += want; continue; }  // the host reports KR_E_CAPACITY from totals[0]
       int32_t *out = a.r.create_idx + off;

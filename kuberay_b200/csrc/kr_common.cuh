@@ -85,7 +85,22 @@ struct ScratchDev {
   uint4 *bucket; uint32_t bucket_stride;                       // [n_clusters * stride] {pod idx, slot << 16 | flags, replica index, name id}, arrival order
   uint32_t *wt_bits; uint32_t wt_bits_mask;                    // Bloom bitmap over the workersToDelete (ns, name) keys (power-of-two bit count)
   uint32_t *cl_in;                                             // [32 * n_clusters] every per-cluster input of the decide kernel as ONE 128-byte record (KR_CI_*)
-  uint4 *cl_dyn;                                               // [n_clusters] {pods bucketed so far, -, ~(first head's pod idx << 32 | head-aux row + 1)}, zeroed every pass
+  uint4 *cl_dyn;                                               // [n_clusters] {pods bucketed so far, -, ~(first head's pod idx << 32 | head-aux row + 1)}, zeroed every full pass
+  // device-side incremental epochs (kr_incr.cuh): the buckets, cl_dyn, cl_in, the tables and the results stay resident between passes
+  uint32_t *stamp;                                             // [n_pods] epoch in which the row was last touched (retired) by a pod commit
+  uint32_t *touched;                                           // [n_pods] rows touched since the last pass (each once), count in inc[KR_INC_TOUCHED]
+  uint32_t *dirty_flag;                                        // [n_clusters] epoch in which the RayCluster was last marked dirty
+  uint32_t *dirty_list;                                        // [n_clusters] RayClusters to decide again, count in inc[KR_INC_DIRTY]
+  uint32_t *act_res, *cre_res;                                 // [n_clusters] places the cluster holds in the action list / create arena (reused while they suffice)
+  uint32_t *inc;                                               // [16] counters / flags of the running epoch (KR_INC_*)
+};
+enum {
+  KR_INC_TOUCHED = 0, KR_INC_DIRTY = 1,
+  KR_INC_STRUCTURAL = 2,   // an object commit changed a table key / CSR offset: the resident tables are stale, take a full pass
+  KR_INC_EPOCH = 3,        // epochs completed; stamps / dirty flags of the running epoch carry this + 1
+  KR_INC_HEADS = 4,        // the pod idx -> head-aux row table must be rebuilt
+  KR_INC_VOID = 5,         // the incremental attempt is void (a bucket or an arena overflowed): take a full pass
+  KR_INC_GROUPS = 6,       // gather: group records staged so far
 };
 // words of a cl_in record (built by k_build_tables; k_decide2 loads it with one coalesced 128-byte access, lane i = word i)
 enum {

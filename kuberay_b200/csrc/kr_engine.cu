@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kr_kernels.cuh"
+#include "kr_incr.cuh"
 
 using namespace kr;
 
@@ -103,7 +104,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, inc_zero, stamp, dirty_flag, inc, inc_zero_end, touched, dirty_list, act_res, cre_res, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
   uint32_t wt_bits_n;      // bits of the workersToDelete Bloom bitmap
   size_t bucket_entries;   // capacity of the bucket arena of the bucket pipeline (0: that pipeline is off for this engine)
@@ -165,6 +166,16 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   if (64 * (size_t)n.n_clusters > 8 * (size_t)n.n_pods + (4u << 20)) L.bucket_entries = 0;
   L.cl_in = o; o = align_up(o + 128 * (size_t)n.n_clusters);
   L.bucket = o; o = align_up(o + 16 * L.bucket_entries);
+  // incremental epochs (kr_incr.cuh): [stamps | dirty flags | counters] start out zero (one memset when the layout moves)
+  L.inc_zero = o;
+  L.stamp = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.dirty_flag = o; o = align_up(o + 4 * (size_t)n.n_clusters);
+  L.inc = o; o = align_up(o + 64);
+  L.inc_zero_end = o;
+  L.touched = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.dirty_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
+  L.act_res = o; o = align_up(o + 4 * (size_t)n.n_clusters);
+  L.cre_res = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.total = o;
   return L;
 }
@@ -228,6 +239,25 @@ struct kr_engine {
   bool order_pending = false;
   std::vector<uint32_t> row_stamp;  // kr_snapshot_commit_pod_values: duplicate-row detection (epoch-stamped)
   uint32_t row_epoch = 0;
+  // device-side incremental epochs (kr_incr.cuh)
+  bool no_incr = false;          // KR_NO_INCR=1: every pass is a full pass (tests)
+  bool inc_valid = false;        // the resident buckets / tables / results describe the committed snapshot up to the commits since the last pass
+  bool inc_zero_needed = true;   // the stamp / dirty-flag / counter region of this layout has not been zeroed yet
+  kr_flags inc_flags{};          // flags of the pass that left the resident state
+  uint32_t inc_n_pods = 0, inc_n_heads = 0;  // rows resident at the last pass
+  uint32_t res_n_heads = 0;                  // head-aux rows the resident device columns hold (object commits move it)
+  bool hash_dirty = false;       // spec JSON (or a JSON range) committed since the digests were computed
+  bool ran_inc = false;          // the last pass was an incremental one
+  bool host_results_stale = false;  // an incremental pass went unfetched: the host copy misses its records, the next fetch copies everything
+  bool fetched = true;              // the last pass's results have been copied to the host arena
+  uint32_t inc_n_dirty = 0;      // changed RayClusters of the last incremental pass
+  bool inc_gathered = false;     // ... and their records sit packed in the staging buffer
+  bool inc_hash_ran = false;
+  std::vector<uint64_t> prev_json_off; std::vector<uint32_t> prev_json_len;  // JSON ranges the digests were computed from
+  uint8_t *d_obj_stage = nullptr; size_t obj_stage_cap = 0;   // KR_PART_OBJECTS uploads land here while the state is resident
+  uint8_t *d_inc_stage = nullptr, *h_inc_stage = nullptr; size_t inc_stage_cap = 0; uint32_t inc_stage_clusters = 0, inc_stage_groups = 0;
+  uint32_t *h_inc = nullptr;     // pinned copy of the epoch counters (16 words) + the changed-cluster list
+  uint32_t *h_changed = nullptr; size_t h_changed_cap = 0;
 };
 
 namespace {
@@ -306,6 +336,10 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.wt_bits = reinterpret_cast<uint32_t *>(b + L.wt_bits); s.wt_bits_mask = L.wt_bits_n - 1;
   s.cl_in = reinterpret_cast<uint32_t *>(b + L.cl_in);
   s.cl_dyn = reinterpret_cast<uint4 *>(b + L.cl_dyn);
+  s.stamp = reinterpret_cast<uint32_t *>(b + L.stamp); s.touched = reinterpret_cast<uint32_t *>(b + L.touched);
+  s.dirty_flag = reinterpret_cast<uint32_t *>(b + L.dirty_flag); s.dirty_list = reinterpret_cast<uint32_t *>(b + L.dirty_list);
+  s.act_res = reinterpret_cast<uint32_t *>(b + L.act_res); s.cre_res = reinterpret_cast<uint32_t *>(b + L.cre_res);
+  s.inc = reinterpret_cast<uint32_t *>(b + L.inc);
   return s;
 }
 
@@ -425,6 +459,8 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       mark("k_decide2_phase1");
       CK(launch_decide2(dim3((e->n_recreate + kD2Warps - 1) / kD2Warps), false));
     }
+    mark("k_inc_finish");
+    k_inc_finish<<<1, 32, 0, M>>>(sc);  // closes the epoch: whatever the commits queued for an incremental pass is void now
   } else {
   const uint32_t ntiles = e->sl.ntiles;
   const bool fast = !e->force_radix;
@@ -569,10 +605,131 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
   return KR_OK;
 }
 
+
+// a bucket-pipeline pass leaves everything an incremental epoch needs on the device
+void after_full_pass(kr_engine *e, const kr_flags &f) {
+  e->inc_valid = e->ran_bucket && !e->no_incr;
+  e->inc_flags = f; e->inc_n_pods = e->sizes.n_pods; e->inc_n_heads = e->sizes.n_heads;
+  e->host_results_stale = false; e->inc_n_dirty = 0; e->fetched = false; e->ran_inc = false;
+  if (!f.skip_hash) e->hash_dirty = false;
+}
+
+// One incremental pass over the resident state (kr_incr.cuh).  Returns KR_OK with *done_inc = true when its results stand;
+// *done_inc = false means the attempt was void (structural object change, bucket / arena overflow) and a full pass must follow.
+int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile, bool *done_inc) {
+  *done_inc = false;
+  const kr_sizes &n = e->sizes;
+  SnapDev s;
+  bind_in(e->il, e->d_in, &s);
+  ResDev r = bind_out(e->ol, e->d_out);
+  ScratchDev sc = bind_scratch(e->sl, e->d_scratch);
+  sc.bucket_stride = e->bstride;
+  Sizes z{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
+  cudaStream_t M = e->sm, H = profile ? e->sm : e->sh;
+  int k = 0;
+  auto mark = [&](const char *name) {
+    if (profile && k < KR_MAX_KERNEL_TIMES) { e->prof.kernel_name[k] = name; cudaEventRecord(e->ev_k[k], M); }
+    k++;
+  };
+  e->prof.n_kernels = 0;
+  CK(cudaStreamWaitEvent(M, e->ev_cols, 0));
+  const bool do_hash = e->hash_dirty && !f.skip_hash && n.n_clusters > 0;
+  if (do_hash) {  // the spec JSON was committed again: every digest is recomputed (on its own stream), every Recreate gate re-read
+    if (!profile) { CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0)); }
+    CK(cudaStreamWaitEvent(H, e->ev_json, 0));
+    if (profile) mark("k_hash");
+    const uint32_t ngroups = (n.n_clusters + 31) / 32;
+    if (ngroups <= (uint32_t)e->sm_count * 4)
+      k_hash3<1, 0><<<std::min<uint32_t>(ngroups, (uint32_t)e->sm_count * 2), 64, sizeof(H3Smem), H>>>(s.json, s.c_json_off, s.c_json_len, e->d_order, n.n_clusters, r.hash);
+    else
+      k_hash2<4, 1><<<std::min<uint32_t>((n.n_clusters + 127) / 128, (uint32_t)e->sm_count * e->hash_ctas_per_sm), 128, 0, H>>>(s.json, s.c_json_off, s.c_json_len, e->d_order, n.n_clusters, r.hash, 1u);
+    if (!profile) CK(cudaEventRecord(e->ev_hash, H));
+    if (e->n_recreate) { mark("k_inc_mark_recreate"); k_inc_mark_recreate<<<(n.n_clusters + 255) / 256, 256, 0, M>>>(s, sc, z); }
+  }
+  const int grid = e->sm_count * 2;
+  if (n.n_heads || e->inc_n_heads) {
+    mark("k_inc_aux_rebuild");
+    k_inc_aux_clear<<<std::min<uint32_t>(grid, (e->sl.aux_slots + 255) / 256), 256, 0, M>>>(sc);
+    k_inc_aux_insert<<<std::min<uint32_t>(grid, (n.n_heads + 255) / 256 + 1), 256, 0, M>>>(s, sc, z);
+  }
+  mark("k_inc_prepare");
+  if (e->bstride <= 64) k_inc_prepare<2><<<grid, kD2Warps * 32, 0, M>>>(s, sc, z);
+  else if (e->bstride <= 128) k_inc_prepare<4><<<grid, kD2Warps * 32, 0, M>>>(s, sc, z);
+  else k_inc_prepare<8><<<grid, kD2Warps * 32, 0, M>>>(s, sc, z);
+  mark("k_inc_admit");
+  k_inc_admit<<<grid, 256, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
+  if (do_hash && !profile) CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
+  if (n.n_clusters) {
+    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 2};
+    const dim3 dgrid((n.n_clusters + kD2Warps - 1) / kD2Warps), dblock(kD2Warps * 32);
+    mark("k_decide2_dirty");
+    if (e->bstride <= 64) k_decide2<2><<<dgrid, dblock, 0, M>>>(da);
+    else if (e->bstride <= 128) k_decide2<4><<<dgrid, dblock, 0, M>>>(da);
+    else k_decide2<8><<<dgrid, dblock, 0, M>>>(da);
+  }
+  if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
+  // staging for the changed records: up to a quarter of the RayClusters (beyond that the whole record arrays are as cheap to move)
+  {
+    const uint32_t capc = std::max<uint32_t>(64, n.n_clusters / 4), capg = capc * KR_SMEM_GROUPS;
+    const size_t need = 32 * (size_t)capc + sizeof(kr_cluster_result) * (size_t)capc + sizeof(kr_group_result) * (size_t)capg + 1024;
+    if (need > e->inc_stage_cap) {
+      if (e->d_inc_stage) cudaFree(e->d_inc_stage);
+      if (e->h_inc_stage) cudaFreeHost(e->h_inc_stage);
+      e->d_inc_stage = nullptr; e->h_inc_stage = nullptr; e->inc_stage_cap = 0;
+      CK(cudaMalloc((void **)&e->d_inc_stage, need));
+      CK(cudaHostAlloc((void **)&e->h_inc_stage, need, cudaHostAllocDefault));
+      e->inc_stage_cap = need;
+    }
+    e->inc_stage_clusters = capc; e->inc_stage_groups = capg;
+    IncStage st;
+    st.meta = reinterpret_cast<uint32_t *>(e->d_inc_stage);
+    st.clusters = reinterpret_cast<kr_cluster_result *>(e->d_inc_stage + align_up(32 * (size_t)capc));
+    st.groups = reinterpret_cast<kr_group_result *>(e->d_inc_stage + align_up(32 * (size_t)capc) + align_up(sizeof(kr_cluster_result) * (size_t)capc));
+    st.cap_clusters = capc; st.cap_groups = capg;
+    mark("k_inc_gather");
+    k_inc_gather<<<std::min<uint32_t>(grid, (capc + 255) / 256), 256, 0, M>>>(s, sc, r, st);
+  }
+  if (profile && k <= KR_MAX_KERNEL_TIMES) cudaEventRecord(e->ev_k[k < KR_MAX_KERNEL_TIMES ? k : KR_MAX_KERNEL_TIMES], M);
+  e->prof.n_kernels = (uint32_t)k;
+  if (done) CK(cudaEventRecord(done, M));
+  CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 48, cudaMemcpyDeviceToHost, M));
+  CK(cudaMemcpyAsync(e->h_inc, sc.inc, 64, cudaMemcpyDeviceToHost, M));
+  k_inc_finish<<<1, 32, 0, M>>>(sc);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(M));
+  e->order_pending = false;
+  e->h2d_accum = 0;
+  if (!e->h2d_timed) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
+    e->h2d_timed = true;
+  }
+  if (e->h_inc[KR_INC_VOID] || e->h_inc[KR_INC_STRUCTURAL]) return KR_OK;  // the caller takes the full pass
+  if (!e->fetched) e->host_results_stale = true;  // the previous pass's records never reached the host copy
+  e->fetched = false;
+  e->inc_n_dirty = e->h_inc[KR_INC_DIRTY];
+  e->inc_gathered = e->inc_n_dirty <= e->inc_stage_clusters && e->h_inc[KR_INC_GROUPS] <= e->inc_stage_groups;
+  e->inc_hash_ran = do_hash;
+  if (do_hash) e->hash_dirty = false;
+  e->ran_inc = true;
+  *done_inc = true;
+  return KR_OK;
+}
+
 // Runs the pass; if the fast pipeline met a bucket it cannot sort (> 1024 pods in one RayCluster or among the orphans),
 // switches this layout to the radix pipeline and runs again.  Leaves the stream synchronised.
 int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
   e->last_flags = f;
+  if (e->inc_valid && !e->no_incr && memcmp(&e->inc_flags, &f, sizeof f) == 0) {
+    bool ok = false;
+    if (int rc = run_pass_inc(e, f, done, false, &ok)) return rc;
+    if (ok) { e->inc_n_pods = e->sizes.n_pods; e->inc_n_heads = e->sizes.n_heads; return KR_OK; }
+  }
+  e->inc_valid = false; e->ran_inc = false;
+  if (e->inc_zero_needed) {  // first pass on this layout: stamps, dirty flags and epoch counters start from zero
+    CK(cudaMemsetAsync(e->d_scratch + e->sl.inc_zero, 0, e->sl.inc_zero_end - e->sl.inc_zero, e->sm));
+    e->inc_zero_needed = false;
+  }
   for (int attempt = 0; attempt < 5; attempt++) {
     int rc = run_pass_once(e, f);
     if (rc) return rc;
@@ -586,7 +743,7 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
       if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
       e->h2d_timed = true;
     }
-    if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) return KR_OK;
+    if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { after_full_pass(e, f); return KR_OK; }
     // some RayCluster outgrew what this pipeline holds per bucket: bucket pipeline -> wider stride -> sort pipeline -> radix pipeline
     if (e->ran_bucket) {
       const uint32_t wider = e->bstride * 2;
@@ -612,8 +769,40 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
     CK(cudaEventRecord(e->ev_c, e->sm));
     return fail(e, KR_E_CAPACITY, "pods to create (%u) exceed kr_config.max_creates (%u)", n_create, e->cfg.max_creates);
   }
-  uint64_t bytes = e->ol.small_total;
-  CK(cudaMemcpyAsync(e->h_out, e->d_out, e->ol.small_total, cudaMemcpyDeviceToHost, e->sm));
+  const bool inc = e->ran_inc && !e->host_results_stale;
+  const bool packed = inc && e->inc_gathered;
+  uint64_t bytes = 0;
+  const uint32_t nd = e->inc_n_dirty, ngr = inc ? e->h_inc[KR_INC_GROUPS] : 0;
+  const size_t st_cl = align_up(32 * (size_t)e->inc_stage_clusters), st_gr = st_cl + align_up(sizeof(kr_cluster_result) * (size_t)e->inc_stage_clusters);
+  if (packed) {
+    // incremental pass: the changed cluster / group records come back packed (k_inc_gather) and are scattered into the host
+    // arena below; the flat arrays an epoch can touch anywhere (name resolutions, RayJob rows, digests when they were
+    // recomputed) are small and come back whole
+    if (nd) {
+      CK(cudaMemcpyAsync(e->h_inc_stage, e->d_inc_stage, 32 * (size_t)nd, cudaMemcpyDeviceToHost, e->sm));
+      CK(cudaMemcpyAsync(e->h_inc_stage + st_cl, e->d_inc_stage + st_cl, sizeof(kr_cluster_result) * (size_t)nd, cudaMemcpyDeviceToHost, e->sm));
+      if (ngr) CK(cudaMemcpyAsync(e->h_inc_stage + st_gr, e->d_inc_stage + st_gr, sizeof(kr_group_result) * (size_t)ngr, cudaMemcpyDeviceToHost, e->sm));
+      bytes += (32 + sizeof(kr_cluster_result)) * (uint64_t)nd + sizeof(kr_group_result) * (uint64_t)ngr;
+    }
+    CK(cudaMemcpyAsync(e->h_out + e->ol.totals, e->d_out + e->ol.totals, 256, cudaMemcpyDeviceToHost, e->sm));
+    if (n.n_wtd) { CK(cudaMemcpyAsync(e->h_out + e->ol.wtd, e->d_out + e->ol.wtd, 4 * (size_t)n.n_wtd, cudaMemcpyDeviceToHost, e->sm)); bytes += 4ull * n.n_wtd; }
+    if (n.n_jobs) { CK(cudaMemcpyAsync(e->h_out + e->ol.jobs, e->d_out + e->ol.jobs, sizeof(kr_job_result) * (size_t)n.n_jobs, cudaMemcpyDeviceToHost, e->sm)); bytes += sizeof(kr_job_result) * (uint64_t)n.n_jobs; }
+    if (e->inc_hash_ran && n.n_clusters) { CK(cudaMemcpyAsync(e->h_out + e->ol.hash, e->d_out + e->ol.hash, 32 * (size_t)n.n_clusters, cudaMemcpyDeviceToHost, e->sm)); bytes += 32ull * n.n_clusters; }
+  } else {
+    bytes = e->ol.small_total;
+    CK(cudaMemcpyAsync(e->h_out, e->d_out, e->ol.small_total, cudaMemcpyDeviceToHost, e->sm));
+  }
+  if (inc && nd) {  // the changed-cluster list itself
+    if ((size_t)nd > e->h_changed_cap) {
+      if (e->h_changed) cudaFreeHost(e->h_changed);
+      e->h_changed = nullptr; e->h_changed_cap = 0;
+      const size_t cap = std::max<size_t>(1024, (size_t)e->cfg.max_clusters);
+      CK(cudaHostAlloc((void **)&e->h_changed, 4 * cap, cudaHostAllocDefault));
+      e->h_changed_cap = cap;
+    }
+    CK(cudaMemcpyAsync(e->h_changed, e->d_scratch + e->sl.dirty_list, 4 * (size_t)nd, cudaMemcpyDeviceToHost, e->sm));
+    bytes += 4ull * nd;
+  }
   if (full && n.n_pods) {
     if (!e->fixed_layout) {
       size_t span = e->ol.act_idx - e->ol.sorted_idx;  // sorted_pod_idx + sorted_action, contiguous
@@ -636,6 +825,19 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
   }
   CK(cudaEventRecord(e->ev_c, e->sm));
   CK(cudaStreamSynchronize(e->sm));
+  if (packed && nd) {  // scatter the packed records into the host arena
+    ResDev hr = bind_out(e->ol, e->h_out);
+    const uint32_t *meta = reinterpret_cast<const uint32_t *>(e->h_inc_stage);
+    const kr_cluster_result *scl = reinterpret_cast<const kr_cluster_result *>(e->h_inc_stage + st_cl);
+    const kr_group_result *sgr = reinterpret_cast<const kr_group_result *>(e->h_inc_stage + st_gr);
+    for (uint32_t i = 0; i < nd; i++) {
+      const uint32_t *m = meta + 8 * (size_t)i;
+      const uint32_t c = m[0];
+      hr.clusters[c] = scl[i]; hr.act_start[c] = m[1]; hr.act_cnt[c] = m[2];
+      if (m[4]) memcpy(&hr.groups[m[3]], &sgr[m[5]], sizeof(kr_group_result) * (size_t)m[4]);
+    }
+  }
+  e->fetched = true; e->host_results_stale = false;
   if (out) {
     ResDev hr = bind_out(e->ol, e->h_out);
     out->clusters = hr.clusters; out->hash = hr.hash; out->groups = hr.groups;
@@ -645,6 +847,8 @@ int fetch_results(kr_engine *e, kr_results_view *out) {
     out->act_start = hr.act_start; out->act_cnt = hr.act_cnt; out->act_pod_idx = hr.act_pod_idx; out->act_code = hr.act_code;
     out->n_create_total = e->ran_bucket ? tot[6] : n_create; out->n_orphans = tot[1]; out->n_actions = tot[2];
     out->create_extent = n_create; out->act_extent = n_actions;
+    out->n_changed = inc ? nd : n.n_clusters;
+    out->changed_clusters = (inc && nd) ? e->h_changed : nullptr;
   }
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_c) == cudaSuccess) e->prof.d2h_ms = ms;
@@ -738,7 +942,10 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
                         (const void *)k_clear, (const void *)k_match<false, kSortItems>, (const void *)k_hist, (const void *)k_scan_rows, (const void *)k_scatter,
                         (const void *)k_scan_counts, (const void *)k_place, (const void *)k_scan_creates, (const void *)k_create_fill, (const void *)k_scan_actions,
                         (const void *)k_compact_actions, (const void *)k_patch_pods, (const void *)k_patch_pod_values,
-                        (const void *)k_match2<kMatchItems>, (const void *)k_decide2<2>, (const void *)k_decide2<4>, (const void *)k_decide2<8>, (const void *)k_hash3<1, 0>};
+                        (const void *)k_match2<kMatchItems>, (const void *)k_decide2<2>, (const void *)k_decide2<4>, (const void *)k_decide2<8>, (const void *)k_hash3<1, 0>,
+                        (const void *)k_inc_retire, (const void *)k_inc_objects, (const void *)k_inc_objects_keys, (const void *)k_inc_aux_clear, (const void *)k_inc_aux_insert,
+                        (const void *)k_inc_mark_recreate, (const void *)k_inc_prepare<2>, (const void *)k_inc_prepare<4>, (const void *)k_inc_prepare<8>, (const void *)k_inc_admit,
+                        (const void *)k_inc_gather, (const void *)k_inc_finish};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
@@ -750,6 +957,8 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   e->force_radix = e->env_radix;
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   if (const char *g = getenv("KR_NO_BUCKET")) e->no_bucket = (g[0] == '1');
+  if (const char *g = getenv("KR_NO_INCR")) e->no_incr = (g[0] == '1');
+  if (cudaHostAlloc((void **)&e->h_inc, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaHostAlloc((void **)&e->h_order, 4 * ((size_t)cfg->max_clusters + 1), cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_order, 4 * ((size_t)cfg->max_clusters + 1)) != cudaSuccess) return bail(KR_E_CUDA);
   cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming);
@@ -768,6 +977,11 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->hb_h) cudaFreeHost(e->hb_h);
   if (e->h_totals) cudaFreeHost(e->h_totals);
   if (e->h_order) cudaFreeHost(e->h_order);
+  if (e->h_inc) cudaFreeHost(e->h_inc);
+  if (e->h_changed) cudaFreeHost(e->h_changed);
+  if (e->h_inc_stage) cudaFreeHost(e->h_inc_stage);
+  if (e->d_inc_stage) cudaFree(e->d_inc_stage);
+  if (e->d_obj_stage) cudaFree(e->d_obj_stage);
   if (e->d_order) cudaFree(e->d_order);
   if (e->ev_order) cudaEventDestroy(e->ev_order);
   if (e->d_in) cudaFree(e->d_in);
@@ -802,14 +1016,22 @@ int kr_snapshot_begin(kr_engine *e, const kr_sizes *sizes, kr_snapshot_bufs *out
   CK(cudaStreamSynchronize(e->scopy));
   CK(cudaStreamSynchronize(e->sm));  // previous results are invalidated from here on
   if (memcmp(&e->sizes, sizes, sizeof *sizes) != 0) {  // row counts (and, without KR_OPT_FIXED_LAYOUT, every column address) change
-    e->gvalid = false; e->force_radix = e->env_radix;
-    if (!e->fixed_layout) e->committed_full = false;
-    // bucket stride: a power of two with 25 % head room over the mean cluster size (a cluster that outgrows it voids the
-    // attempt; the pass then widens the stride, up to 256, or leaves the bucket pipeline for this layout)
-    uint32_t st = 64;
-    const uint64_t want = sizes->n_clusters ? ((uint64_t)sizes->n_pods * 5 / 4 + sizes->n_clusters - 1) / sizes->n_clusters : 0;
-    while (st < want && st < 512) st <<= 1;
-    e->bstride = st <= 256 ? st : 0;
+    e->gvalid = false;
+    // The resident state of the incremental path survives new live counts under a fixed layout as long as the object tables keep
+    // their shape: pod rows appended (they arrive as committed rows), head-aux rows come and go, the JSON arena grows.
+    const bool keep = e->inc_valid && e->fixed_layout && sizes->n_clusters == e->sizes.n_clusters && sizes->n_groups == e->sizes.n_groups &&
+                      sizes->n_wtd == e->sizes.n_wtd && sizes->n_jobs == e->sizes.n_jobs && sizes->n_pods >= e->sizes.n_pods;
+    if (!e->fixed_layout) { e->committed_full = false; e->inc_zero_needed = true; }
+    if (!keep) {
+      e->inc_valid = false;
+      e->force_radix = e->env_radix;
+      // bucket stride: a power of two with 25 % head room over the mean cluster size (a cluster that outgrows it voids the
+      // attempt; the pass then widens the stride, up to 256, or leaves the bucket pipeline for this layout)
+      uint32_t st = 64;
+      const uint64_t want = sizes->n_clusters ? ((uint64_t)sizes->n_pods * 5 / 4 + sizes->n_clusters - 1) / sizes->n_clusters : 0;
+      while (st < want && st < 512) st <<= 1;
+      e->bstride = st <= 256 ? st : 0;
+    }
   }
   e->sizes = *sizes;
   const kr_sizes lay = e->fixed_layout ? cap_sizes(c) : *sizes;
@@ -857,6 +1079,11 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     if (hb.c_json_off[c] + hb.c_json_len[c] > n.json_bytes) return fail(e, KR_E_INVALID, "cluster %u: json range outside arena", c);
     if (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) n_recreate++;
   }
+  if (parts & KR_PART_COLUMNS) e->inc_valid = false;  // pod columns uploaded wholesale: the resident buckets no longer describe them
+  if (parts & KR_PART_JSON) e->hash_dirty = true;
+  if (e->prev_json_off.size() != n.n_clusters) { e->prev_json_off.assign(n.n_clusters, ~0ull); e->prev_json_len.assign(n.n_clusters, ~0u); e->hash_dirty = true; }
+  for (uint32_t c = 0; c < n.n_clusters; c++)
+    if (e->prev_json_off[c] != hb.c_json_off[c] || e->prev_json_len[c] != hb.c_json_len[c]) { e->hash_dirty = true; e->prev_json_off[c] = hb.c_json_off[c]; e->prev_json_len[c] = hb.c_json_len[c]; }
   if (goff != n.n_groups) return fail(e, KR_E_INVALID, "sum of group_cnt (%llu) != n_groups (%u)", (unsigned long long)goff, n.n_groups);
   if (woff != n.n_wtd) return fail(e, KR_E_INVALID, "sum of g_wtd_cnt (%llu) != n_wtd (%u)", (unsigned long long)woff, n.n_wtd);
   for (uint32_t h = 0; h < n.n_heads; h++)
@@ -887,11 +1114,24 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     return fail(e, KR_E_STATE, "a partial commit needs a full commit of this layout first");
   size_t bytes = 0;
   CK(cudaEventRecord(e->ev_h2d0, e->scopy));
+  const size_t a1 = e->il.off[kFirstPodCol], b0 = e->il.off[kFirstPodCol + 7];
+  // While the incremental state is resident, an object commit lands beside the resident tables and is diffed against them on
+  // the device (k_inc_objects): changed rows mark their RayCluster dirty, a changed key makes the next pass a full one.
+  const bool stage_objects = e->inc_valid && !e->no_incr && (parts & KR_PART_OBJECTS) && !(parts & KR_PART_COLUMNS);
+  if (stage_objects && a1 + (json_off - b0) > e->obj_stage_cap) {
+    if (e->d_obj_stage) cudaFree(e->d_obj_stage);
+    e->d_obj_stage = nullptr; e->obj_stage_cap = 0;
+    CK(cudaMalloc((void **)&e->d_obj_stage, a1 + (json_off - b0)));
+    e->obj_stage_cap = a1 + (json_off - b0);
+  }
+  auto stage_of = [&](size_t off) { return off < a1 ? off : a1 + (off - b0); };
   auto up = [&](size_t off, size_t len) -> int {
-    if (len) { CK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, len, cudaMemcpyHostToDevice, e->scopy)); bytes += len; }
+    if (!len) return KR_OK;
+    uint8_t *dst = (stage_objects && off < json_off) ? e->d_obj_stage + stage_of(off) : e->d_in + off;
+    CK(cudaMemcpyAsync(dst, e->h_in + off, len, cudaMemcpyHostToDevice, e->scopy));
+    bytes += len;
     return KR_OK;
   };
-  const size_t a1 = e->il.off[kFirstPodCol], b0 = e->il.off[kFirstPodCol + 7];
   if ((parts & KR_PART_COLUMNS) && !e->fixed_layout) { if (int rc = up(0, json_off)) return rc; }
   else if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) {
     // the (small) columns on either side of the seven per-pod ones; then, for KR_PART_COLUMNS under a fixed layout, the live
@@ -902,6 +1142,49 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
       for (int k = 0; k < 7; k++)
         if (int rc = up(e->il.off[kFirstPodCol + k], 4 * (size_t)n.n_pods)) return rc;
   }
+  if (stage_objects) {
+    static const uint8_t kObjClass[kNumCols] = {
+        KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_COPY, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_COPY, KR_OC_COPY,
+        KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER,
+        KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_GROUP, KR_OC_GROUP, KR_OC_GROUP, KR_OC_STRUCT, KR_OC_GROUP, KR_OC_STRUCT, KR_OC_STRUCT,
+        KR_OC_STRUCT,
+        0, 0, 0, 0, 0, 0, 0,
+        KR_OC_HEADKEY, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD,
+        KR_OC_COPY, KR_OC_COPY, KR_OC_COPY, KR_OC_COPY,
+        0};
+    uint64_t dn[7];
+    dims_of(n, dn);
+    ObjDiffArgs oa{};
+    int nc = 0;
+    uint32_t first = 0;
+    constexpr int kHeadKeyCol = 39, kGroupClusterCol = 22;
+    static_assert(kCols[kHeadKeyCol].dim == D_HEADS && kCols[kHeadKeyCol - 1].dim == D_PODS && kCols[kGroupClusterCol].dim == D_GROUPS && kCols[kGroupClusterCol - 1].dim == D_CLUSTERS, "column indices of the object diff");
+    for (int i = 0; i < kNumCols - 1; i++) {
+      if (kCols[i].dim == D_PODS) continue;
+      oa.src[nc] = e->d_obj_stage + stage_of(e->il.off[i]);
+      oa.dst[nc] = e->d_in + e->il.off[i];
+      oa.first[nc] = first;
+      oa.rows_old[nc] = kCols[i].dim == D_HEADS ? e->res_n_heads : (uint32_t)dn[kCols[i].dim];
+      oa.row_bytes[nc] = (uint16_t)(kCols[i].elem * kCols[i].mult);
+      oa.cls[nc] = kObjClass[i];
+      first += (uint32_t)dn[kCols[i].dim];
+      nc++;
+    }
+    oa.first[nc] = first; oa.n_cols = nc;
+    oa.g_cluster_idx_new = reinterpret_cast<const uint32_t *>(e->d_obj_stage + stage_of(e->il.off[kGroupClusterCol]));
+    oa.h_pod_idx_new = reinterpret_cast<const uint32_t *>(e->d_obj_stage + stage_of(e->il.off[kHeadKeyCol]));
+    oa.h_pod_idx_old = reinterpret_cast<const uint32_t *>(e->d_in + e->il.off[kHeadKeyCol]);
+    oa.n_heads_old = e->res_n_heads;
+    SnapDev sd;
+    bind_in(e->il, e->d_in, &sd);
+    ScratchDev scd = bind_scratch(e->sl, e->d_scratch);
+    Sizes zz{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
+    if (first) k_inc_objects<<<(first + 255) / 256, 256, 0, e->scopy>>>(oa, sd, scd, zz);
+    if (n.n_heads) k_inc_objects_keys<<<(n.n_heads + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n.n_heads);
+    if (n.n_heads != e->res_n_heads) CK(cudaMemsetAsync(scd.inc + KR_INC_HEADS, 1, 1, e->scopy));  // rows came or went: the pod -> row table is rebuilt
+    CK(cudaGetLastError());
+  }
+  if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) e->res_n_heads = n.n_heads;
   CK(cudaEventRecord(e->ev_cols, e->scopy));
   if (n.n_clusters) { CK(cudaMemcpyAsync(e->d_order, e->h_order, 4 * (size_t)n.n_clusters, cudaMemcpyHostToDevice, e->scopy)); bytes += 4 * (size_t)n.n_clusters; }
   CK(cudaEventRecord(e->ev_order, e->scopy));
@@ -962,6 +1245,12 @@ static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *
   CK(cudaMemcpyAsync(e->pr_d, e->pr_h, bytes, cudaMemcpyHostToDevice, e->scopy));
   CK(cudaEventRecord(e->ev_pr, e->scopy));
   e->pr_busy = true;
+  if (e->inc_valid && !e->no_incr) {  // the rows' previous values leave the resident state before the new ones land
+    ScratchDev scd = bind_scratch(e->sl, e->d_scratch);
+    ResDev rd = bind_out(e->ol, e->d_out);
+    Sizes zz{e->sizes.n_clusters, e->sizes.n_groups, e->sizes.n_wtd, e->sizes.n_pods, e->sizes.n_heads, e->sizes.n_jobs};
+    k_inc_retire<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, s, scd, rd, zz, e->inc_n_pods, e->sizes.n_wtd ? 1 : 0);
+  }
   if (values) k_patch_pod_values<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, dc);
   else k_patch_pods<<<(n + 255) / 256, 256, 0, e->scopy>>>(reinterpret_cast<const uint32_t *>(e->pr_d), n, hc, dc);
   CK(cudaGetLastError());
@@ -1011,7 +1300,20 @@ int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile 
   if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
   CK(cudaSetDevice(e->cfg.device));
   e->last_flags = *flags;
-  for (int attempt = 0;; attempt++) {  // same fallback ladder as run_pass
+  bool inc_done = false;
+  if (e->inc_valid && !e->no_incr && memcmp(&e->inc_flags, flags, sizeof *flags) == 0) {
+    CK(cudaEventRecord(e->ev_a, e->sm));
+    if (int rc = run_pass_inc(e, *flags, e->ev_b, true, &inc_done)) return rc;
+    if (inc_done) { e->inc_n_pods = e->sizes.n_pods; e->inc_n_heads = e->sizes.n_heads; }
+  }
+  if (!inc_done) {
+    e->inc_valid = false; e->ran_inc = false;
+    if (e->inc_zero_needed) {
+      CK(cudaMemsetAsync(e->d_scratch + e->sl.inc_zero, 0, e->sl.inc_zero_end - e->sl.inc_zero, e->sm));
+      e->inc_zero_needed = false;
+    }
+  }
+  for (int attempt = 0; !inc_done; attempt++) {  // same fallback ladder as run_pass
     CK(cudaEventRecord(e->ev_a, e->sm));
     int rc = launch_pass(e, *flags, true);
     if (rc) return rc;
@@ -1019,7 +1321,7 @@ int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile 
     CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 48, cudaMemcpyDeviceToHost, e->sm));
     CK(cudaStreamSynchronize(e->sm));
     e->order_pending = false;
-    if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) break;
+    if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { after_full_pass(e, *flags); break; }
     if (attempt >= 4) return fail(e, KR_E_STATE, "internal: radix pipeline flagged a big bucket");
     if (e->ran_bucket) {
       const uint32_t wider = e->bstride * 2;

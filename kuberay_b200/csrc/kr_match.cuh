@@ -23,6 +23,30 @@ __global__ void __launch_bounds__(256) k_clear(ClearArgs a) {
   }
 }
 
+// The decide kernel's per-cluster inputs, gathered from ~25 columns into one 128-byte record (KR_CI_*).  Written by k_build_tables
+// in a full pass and again by k_inc_prepare for the RayClusters an incremental epoch found changed.
+__device__ __forceinline__ void write_cl_in(const SnapDev &s, const ScratchDev &sc, uint32_t t, uint32_t g0, uint32_t G) {
+  uint32_t *ci = sc.cl_in + 32 * (size_t)t;
+  const uint8_t *cs = s.c_old_cond_status + 5 * (size_t)t, *cv = s.c_old_cond_variant + 5 * (size_t)t;
+  uint4 w0, w1;
+  w0.x = s.c_flags[t]; w0.y = g0; w0.z = G;
+  w0.w = s.c_suspend_status[t] | ((uint32_t)s.c_ext_err_kind[t] << 8) | ((uint32_t)s.c_old_state[t] << 16) | ((uint32_t)s.c_svc_count[t] << 24);
+  w1.x = s.c_svc_ip_kind[t] | ((uint32_t)cs[0] << 8) | ((uint32_t)cs[1] << 16) | ((uint32_t)cs[2] << 24);
+  w1.y = cs[3] | ((uint32_t)cs[4] << 8) | ((uint32_t)cv[0] << 16) | ((uint32_t)cv[1] << 24);
+  w1.z = cv[2] | ((uint32_t)cv[3] << 8) | ((uint32_t)cv[4] << 16);
+  w1.w = s.c_ext_err_msg_id[t];
+  uint4 *o = reinterpret_cast<uint4 *>(ci);
+  o[0] = w0; o[1] = w1;
+  const int32_t *oc = s.c_old_counts + 5 * (size_t)t;
+  o[2] = make_uint4((uint32_t)oc[0], (uint32_t)oc[1], (uint32_t)oc[2], (uint32_t)oc[3]);
+  o[3] = make_uint4((uint32_t)oc[4], s.c_old_cond_reason_id[t], s.c_old_cond_msg_id[2 * (size_t)t], s.c_old_cond_msg_id[2 * (size_t)t + 1]);
+  const uint32_t *oh = s.c_old_head_ids + 4 * (size_t)t;
+  o[4] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+  uint4 w5 = make_uint4(s.c_svc_ip_id[t], s.c_svc_name_id[t], 0, 0), w6 = make_uint4(0, 0, 0, 0);
+  if (G) { w5.z = s.g_flags[g0]; w5.w = (uint32_t)s.g_replicas[g0]; w6.x = (uint32_t)s.g_min[g0]; w6.y = (uint32_t)s.g_max[g0]; w6.z = (uint32_t)s.g_num_hosts[g0]; }
+  o[5] = w5; o[6] = w6; o[7] = make_uint4(0, 0, 0, 0);
+}
+
 // ------------------------------------------------------------------------------------------------ k_build_tables
 // One thread per cluster / workersToDelete entry / head-aux row.  Tables were memset to 0xFF.
 
@@ -46,27 +70,7 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
       i = (i + 1) & sc.cl_mask;
     }
     sc.cl_rec[t] = make_uint4(g0, G, gname0, mh);  // .w bit 0: some worker group has numOfHosts > 1
-    {  // the decide kernel's per-cluster inputs, gathered from ~25 columns into one 128-byte record
-      uint32_t *ci = sc.cl_in + 32 * (size_t)t;
-      const uint8_t *cs = s.c_old_cond_status + 5 * (size_t)t, *cv = s.c_old_cond_variant + 5 * (size_t)t;
-      uint4 w0, w1;
-      w0.x = s.c_flags[t]; w0.y = g0; w0.z = G;
-      w0.w = s.c_suspend_status[t] | ((uint32_t)s.c_ext_err_kind[t] << 8) | ((uint32_t)s.c_old_state[t] << 16) | ((uint32_t)s.c_svc_count[t] << 24);
-      w1.x = s.c_svc_ip_kind[t] | ((uint32_t)cs[0] << 8) | ((uint32_t)cs[1] << 16) | ((uint32_t)cs[2] << 24);
-      w1.y = cs[3] | ((uint32_t)cs[4] << 8) | ((uint32_t)cv[0] << 16) | ((uint32_t)cv[1] << 24);
-      w1.z = cv[2] | ((uint32_t)cv[3] << 8) | ((uint32_t)cv[4] << 16);
-      w1.w = s.c_ext_err_msg_id[t];
-      uint4 *o = reinterpret_cast<uint4 *>(ci);
-      o[0] = w0; o[1] = w1;
-      const int32_t *oc = s.c_old_counts + 5 * (size_t)t;
-      o[2] = make_uint4((uint32_t)oc[0], (uint32_t)oc[1], (uint32_t)oc[2], (uint32_t)oc[3]);
-      o[3] = make_uint4((uint32_t)oc[4], s.c_old_cond_reason_id[t], s.c_old_cond_msg_id[2 * (size_t)t], s.c_old_cond_msg_id[2 * (size_t)t + 1]);
-      const uint32_t *oh = s.c_old_head_ids + 4 * (size_t)t;
-      o[4] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-      uint4 w5 = make_uint4(s.c_svc_ip_id[t], s.c_svc_name_id[t], 0, 0), w6 = make_uint4(0, 0, 0, 0);
-      if (G) { w5.z = s.g_flags[g0]; w5.w = (uint32_t)s.g_replicas[g0]; w6.x = (uint32_t)s.g_min[g0]; w6.y = (uint32_t)s.g_max[g0]; w6.z = (uint32_t)s.g_num_hosts[g0]; }
-      o[5] = w5; o[6] = w6; o[7] = make_uint4(0, 0, 0, 0);
-    }
+    write_cl_in(s, sc, t, g0, G);
     return;
   }
   t -= n.n_clusters;

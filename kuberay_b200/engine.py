@@ -360,6 +360,9 @@ class Engine:
         res.create_idx = _np_view(view.create_idx, np.int32, view.create_extent)
         res.jobs = _np_view(view.jobs, abi.job_result_dtype, s.n_jobs)
         res.n_create_total, res.n_orphans, res.n_actions = view.n_create_total, view.n_orphans, view.n_actions
+        # incremental epochs: the records the pass recomputed (None: a full pass, every record)
+        res.n_changed = view.n_changed
+        res.changed_clusters = _np_view(view.changed_clusters, np.uint32, view.n_changed).copy() if view.changed_clusters else None
         if copy:
             for name in abi.Results.FIELDS:
                 setattr(res, name, getattr(res, name).copy())

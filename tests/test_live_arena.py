@@ -100,20 +100,33 @@ def test_arena_with_free_rows_decides_like_a_fresh_pack(seed, oracle_mod):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lean", [False, True])
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
-def test_incremental_epochs_match_the_oracle(seed, oracle_mod):
+def test_incremental_epochs_match_the_oracle(seed, lean, oracle_mod):
+    """lean (kr_flags.fetch_pod_lists = 0) is the production configuration: the bucket pipeline, and after its first pass the
+    device-side incremental epochs (kr_incr.cuh) — every epoch must still equal a from-scratch oracle run over the arena, and most
+    epochs must really have been incremental on the device (the pass names the records it recomputed)."""
     rng = np.random.default_rng(seed)
     clusters, pods, jobs = fuzz_objects.generate(seed, big=True)
     live = LiveArena(clusters, pods, jobs, spare_rows=16)
     counter = [0]
+    device_incremental = 0
     try:
         for epoch in range(25):
             _events(rng, live, counter, structural=(epoch % 8 == 7))
             live.flush()
-            got = live.reconcile()
-            want = oracle_mod.run(live.snap, live.meta.flags)
+            flags = live.meta.flags
+            flags.fetch_pod_lists = 0 if lean else 1
+            got = live.reconcile(flags)
+            want = oracle_mod.run(live.snap, flags)
             d = want.diff(got)
-            assert not d, (epoch, d[:6])
+            assert not d, (epoch, d[:6], got.n_changed)
+            if got.changed_clusters is not None or (got.n_changed == 0 and live.snap.dims["clusters"]):
+                device_incremental += 1
+                assert got.n_changed <= live.snap.dims["clusters"] and len(set(got.changed_clusters.tolist() if got.changed_clusters is not None else [])) == got.n_changed
         assert live.stats["incremental"] >= 12 and live.stats["rebase"] >= 1 and live.stats["rows"] > 0, live.stats
+        # (a snapshot with a multi-host group is decided by the sort pipeline: no resident buckets, no device-side incremental epochs)
+        eligible = lean and not (live.snap.g_num_hosts > 1).any() and int(live.snap.c_group_cnt.max(initial=0)) <= 32
+        assert device_incremental >= (10 if eligible else 0) and (lean or device_incremental == 0), (device_incremental, live.stats)
     finally:
         live.close()
