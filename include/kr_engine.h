@@ -498,7 +498,12 @@ int kr_last_profile(kr_engine *e, kr_profile *prof);
  *   same pointers, what is resident in HBM stays valid across begins, and an informer event that changes a table's row count
  *   (a RayCluster or head Pod appears, workersToDelete lists grow, a Pod is appended after the last row) is still an
  *   incremental epoch: kr_snapshot_begin(new counts) + KR_PART_OBJECTS + kr_snapshot_commit_pod_rows/_values. */
-enum { KR_OPT_FIXED_LAYOUT = 1 };
+enum {
+  KR_OPT_FIXED_LAYOUT = 1,
+  KR_OPT_INCREMENTAL = 2   /* 1 (default): passes after a full bucket-pipeline pass are incremental on the device whenever the commits in
+                              between allow it (kr_results_view docs); 0: every pass is a full pass (benchmarks of the full pass, tests).
+                              May be changed at any time. */
+};
 int kr_engine_set_option(kr_engine *e, uint32_t option, uint64_t value);
 
 /* Device pointer + byte size of the per-group delta records (kr_group_result[n_groups]) of the last pass:

@@ -81,6 +81,7 @@ SVCIP_NORMAL, SVCIP_EMPTY, SVCIP_NONE = 0, 1, 2
 
 PART_COLUMNS, PART_JSON, PART_ALL, PART_OBJECTS = 1, 2, 3, 4
 OPT_FIXED_LAYOUT = 1
+OPT_INCREMENTAL = 2
 SPEC_JSON_UNMUTED = 1
 KR_OK, KR_E_INVALID, KR_E_CAPACITY, KR_E_CUDA, KR_E_STATE, KR_E_NO_DEVICE = 0, -1, -2, -3, -4, -5
 MAX_KERNEL_TIMES = 24

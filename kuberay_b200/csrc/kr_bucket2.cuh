@@ -25,8 +25,12 @@
 
 namespace kr {
 
+__device__ __forceinline__ uint32_t inc_epoch_of(const ScratchDev &sc) { return __ldcg(&sc.inc[KR_INC_EPOCH]) + 1u; }  // stamp value of the running incremental epoch (kr_incr.cuh)
+
 static constexpr int kD2Warps = 8;  // RayClusters per k_decide2 CTA
 #define KR_ROW_UNHEALTHY (1u << 13)  // bucket record word: shouldDeletePod(pod) (k_match2 evaluates it once per pod)
+#define KR_ROW_FRESH (1u << 14)      // bucket record word: appended by k_inc_admit in the running incremental epoch (cleared by the decide warp)
+
 
 // ------------------------------------------------------------------------------------------------ k_match2
 // The selector match (common/association.go:83-130) + bucketing.  7 coalesced column loads per pod (issued before the
@@ -161,9 +165,11 @@ struct Decide2Args {
 
 // reconcilePods (raycluster_controller.go:619-935) + calculateStatus (:1552-1719) for one RayCluster whose bucket (<= 32*K pods,
 // arrival order) sits in registers.  Multi-host groups never reach this kernel.
-template <int K>
+// kInc: the instantiation an incremental epoch launches (phase 2 only); the instantiation of the full pass carries none of its code.
+template <int K, bool kInc = false>
 __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decide2Args a) {
-  KR_TL(a.phase ? 12 : 3);
+  const int phase = kInc ? 2 : a.phase;
+  KR_TL(phase ? 12 : 3);
   __shared__ int32_t s_acc[kD2Warps][3][KR_SMEM_GROUPS];   // n_list, n_unhealthy, n_wtd_own per group
   __shared__ int32_t s_mode[kD2Warps][3][KR_SMEM_GROUPS];  // mode, delete-prefix length, n_create
   __shared__ uint32_t s_list[kD2Warps][32 * K];            // pod indices being ranked (delete candidates / acted pods)
@@ -174,19 +180,22 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   const uint32_t S = a.sc.bucket_stride;
   uint32_t c = blockIdx.x * kD2Warps + warp;
   // the cluster's inputs: one 128-byte record (lane i = word i), written by k_build_tables — not by the kernel this one waits for
-  bool mine = a.phase == 0 && c < a.n.n_clusters;
+  bool mine = phase == 0 && c < a.n.n_clusters;
   RecordCI ci{mine ? __ldg(&a.sc.cl_in[32 * (size_t)c + lane]) : 0u};
   pdl_wait(); pdl_trigger();
-  if (a.phase == 1) {  // compact list of the clusters phase 0 deferred
+  if (phase == 1) {  // compact list of the clusters phase 0 deferred
     mine = c < a.r.totals[4];
     if (mine) { c = a.sc.deferred_list[c]; ci.word = __ldg(&a.sc.cl_in[32 * (size_t)c + lane]); }
-  } else if (a.phase == 2) {  // the dirty list of an incremental epoch (input records rewritten by k_inc_prepare: no read-only path)
+  } else if (kInc) {  // the dirty list of an incremental epoch (input records rewritten by k_inc_prepare: no read-only path)
     mine = c < __ldcg(&a.sc.inc[KR_INC_DIRTY]) && !__ldcg(&a.sc.inc[KR_INC_VOID]) && !__ldcg(&a.sc.inc[KR_INC_STRUCTURAL]);
-    if (mine) { c = a.sc.dirty_list[c]; ci.word = __ldcg(&a.sc.cl_in[32 * (size_t)c + lane]); }
+    if (mine) {
+      c = a.sc.dirty_list[c];
+      ci.word = __ldcg(&a.sc.cl_in[32 * (size_t)c + lane]);  // (rewritten by k_inc_refresh if an object row of the cluster changed)
+    }
   }
   if (KR_ATTEMPT_VOID(a.r.totals)) mine = false;  // (every warp still walks through the CTA barriers below)
   // pod count + first head, and the whole bucket beside them (stale records past the count are masked once it is here)
-  const uint4 *bucket = a.sc.bucket + (size_t)(mine ? c : 0) * S;
+  uint4 *bucket = a.sc.bucket + (size_t)(mine ? c : 0) * S;
   uint4 dyn = make_uint4(0, 0, 0, 0);
   uint4 recs[K] = {};
   if (mine) {
@@ -196,11 +205,44 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   }
   uint32_t P = dyn.x;
   if (P > S) { mine = false; P = 0; }  // k_match2 voided the attempt
+  if (kInc) {
+    // Incremental epoch: the bucket holds the records of the last pass plus the ones k_inc_admit appended (KR_ROW_FRESH).  Records
+    // of rows the epoch touched are stale (k_inc_retire stamped the row): drop them, store the bucket back compacted (arrival
+    // order kept) and take the cluster's first head from what is left.
+    const uint32_t epoch = inc_epoch_of(a.sc);
+    uint32_t kept = 0, head_min = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint32_t j = k * 32 + lane;
+      bool keep = mine && j < P;
+      if (keep && !(recs[k].y & KR_ROW_FRESH)) keep = __ldcg(&a.sc.stamp[recs[k].x]) != epoch;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) {
+        uint4 rec = recs[k];
+        rec.y &= ~KR_ROW_FRESH;
+        bucket[kept + __popc(bal & lt)] = rec;
+        if (pp_node_type(rec.y & 0xFFFFu) == KR_NT_HEAD) head_min = min(head_min, rec.x);
+      }
+      kept += __popc(bal);
+    }
+    head_min = __reduce_min_sync(0xFFFFFFFFu, head_min);
+    __syncwarp();
+    unsigned long long raw = 0;
+    if (mine) {
+      if (lane == 0 && head_min != 0xFFFFFFFFu) raw = ~(((unsigned long long)head_min << 32) | (uint32_t)(aux_lookup(a.sc, head_min) + 1));
+      raw = __shfl_sync(0xFFFFFFFFu, raw, 0);
+      P = kept;
+      dyn = make_uint4(kept, 0u, (uint32_t)raw, (uint32_t)(raw >> 32));
+      if (lane == 0) a.sc.cl_dyn[c] = dyn;
+#pragma unroll
+      for (int k = 0; k < K; k++) if ((uint32_t)(k * 32) + lane < kept) recs[k] = __ldcg(&bucket[k * 32 + lane]);
+    }
+  }
   const uint32_t cf = ci.flags(), G = ci.group_cnt(), g0 = ci.group_off();
   const uint8_t suspend_status = ci.suspend_status(), ext_err = ci.ext_err_kind(), old_prov = ci.cond_status(KR_COND_PROVISIONED);
   const bool gate = a.f.gate_status_conditions != 0;
   uint32_t old_create = 0;  // phase 2: pods this cluster asked for in the resident results (they leave the running total)
-  if (a.phase == 2 && mine) {
+  if (kInc && mine) {
     for (uint32_t gi = lane; gi < G; gi += 32) old_create += a.r.groups[g0 + gi].n_create;
     old_create = __reduce_add_sync(0xFFFFFFFFu, old_create);
   }
@@ -301,7 +343,7 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
         if (ver == KR_VER_DIFFERENT) cr.head_update_annotations = 1;
         else if (ast == KR_ANNOT_OTHER) recreate = true;
         else if (ast == KR_ANNOT_HASH32 && !a.f.skip_hash) {
-          if (a.phase == 0) {
+          if (phase == 0) {
             // The hash kernel is still running on its own stream.  Decide the cluster as if the digests matched, reserve the
             // whole bucket in the action list (a Recreate deletes every pod) and let phase 1 redo it once the digest is there.
             deferred = true;
@@ -489,7 +531,7 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   // finds its place through (act_start, act_cnt) / (create_off, n_create), which is what the shim reads anyway.)
   const uint32_t slots = deferred ? P : n_act;  // a deferred cluster may still turn into "delete every pod"
   uint32_t act_off = 0, create_off = 0;
-  if (a.phase == 0) {
+  if (phase == 0) {
     unsigned long long base = 0;
     if (mine && lane == 0) {
       if (slots | n_create_cluster) base = atomicAdd(reinterpret_cast<unsigned long long *>(&a.r.totals[8]), ((unsigned long long)n_create_cluster << 32) | slots);
@@ -503,7 +545,7 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
       if (deferred) a.sc.cact[c] = n_create_cluster;  // phase 1 corrects the count of pods to create if the cluster turns into a Recreate
       a.sc.act_res[c] = slots; a.sc.cre_res[c] = n_create_cluster;  // what an incremental epoch may reuse
     }
-  } else if (a.phase == 2) {  // incremental epoch: keep the cluster's places while they suffice, else take new ones at the cursors
+  } else if (kInc) {  // incremental epoch: keep the cluster's places while they suffice, else take new ones at the cursors
     unsigned long long base = 0;
     uint32_t need = 0;  // bit 0: new action slots, bit 1: new create slots
     if (mine && lane == 0) {
@@ -542,16 +584,16 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   for (int k = 0; k < K; k++)
     if (act[k] != KR_ACT_KEEP) { a.r.act_pod_idx[act_off + arank[k]] = pidx[k]; a.r.act_code[act_off + arank[k]] = (uint8_t)act[k]; }
   // create offsets + lowest free ray.io/worker-group-replica-index values (:854-881), from the registers
-  if (a.phase == 1 || n_create_cluster) {
+  if (phase == 1 || n_create_cluster) {
     uint32_t off = create_off;
     for (uint32_t gi = 0; gi < G; gi++) {
       const uint32_t g = g0 + gi;
       const uint32_t want = (uint32_t)g_ncreate[gi];
-      if (a.phase == 1) {
+      if (phase == 1) {
         // keep the arena position phase 0 gave this group (a Recreate leaves a gap: n_create is now 0)
         off = a.sc.gcreate[g];
       }
-      if (lane == 0) { a.r.groups[g].create_off = off; if (a.phase != 1) a.sc.gcreate[g] = off; }
+      if (lane == 0) { a.r.groups[g].create_off = off; if (phase != 1) a.sc.gcreate[g] = off; }
       if (want == 0) continue;
       if ((uint64_t)off + want > a.create_cap) { off += want; continue; }  // the host reports KR_E_CAPACITY from totals[0]
       int32_t *out = a.r.create_idx + off;

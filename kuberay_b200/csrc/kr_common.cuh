@@ -90,6 +90,7 @@ struct ScratchDev {
   uint32_t *stamp;                                             // [n_pods] epoch in which the row was last touched (retired) by a pod commit
   uint32_t *touched;                                           // [n_pods] rows touched since the last pass (each once), count in inc[KR_INC_TOUCHED]
   uint32_t *dirty_flag;                                        // [n_clusters] epoch in which the RayCluster was last marked dirty
+  uint32_t *obj_flag;                                          // [n_clusters] epoch in which an object commit changed one of its rows (its input record is rewritten)
   uint32_t *dirty_list;                                        // [n_clusters] RayClusters to decide again, count in inc[KR_INC_DIRTY]
   uint32_t *act_res, *cre_res;                                 // [n_clusters] places the cluster holds in the action list / create arena (reused while they suffice)
   uint32_t *inc;                                               // [16] counters / flags of the running epoch (KR_INC_*)

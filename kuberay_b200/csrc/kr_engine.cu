@@ -104,7 +104,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, inc_zero, stamp, dirty_flag, inc, inc_zero_end, touched, dirty_list, act_res, cre_res, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, inc_zero, stamp, dirty_flag, obj_flag, inc, inc_zero_end, touched, dirty_list, act_res, cre_res, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
   uint32_t wt_bits_n;      // bits of the workersToDelete Bloom bitmap
   size_t bucket_entries;   // capacity of the bucket arena of the bucket pipeline (0: that pipeline is off for this engine)
@@ -170,6 +170,7 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.inc_zero = o;
   L.stamp = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.dirty_flag = o; o = align_up(o + 4 * (size_t)n.n_clusters);
+  L.obj_flag = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.inc = o; o = align_up(o + 64);
   L.inc_zero_end = o;
   L.touched = o; o = align_up(o + 4 * (size_t)n.n_pods);
@@ -246,6 +247,8 @@ struct kr_engine {
   kr_flags inc_flags{};          // flags of the pass that left the resident state
   uint32_t inc_n_pods = 0, inc_n_heads = 0;  // rows resident at the last pass
   uint32_t res_n_heads = 0;                  // head-aux rows the resident device columns hold (object commits move it)
+  std::vector<uint32_t> prev_h_pod_idx;      // ... and their keys: a change means the pod -> head-aux row table must be rebuilt
+  bool heads_rebuild = false;
   bool hash_dirty = false;       // spec JSON (or a JSON range) committed since the digests were computed
   bool ran_inc = false;          // the last pass was an incremental one
   bool host_results_stale = false;  // an incremental pass went unfetched: the host copy misses its records, the next fetch copies everything
@@ -337,6 +340,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.cl_in = reinterpret_cast<uint32_t *>(b + L.cl_in);
   s.cl_dyn = reinterpret_cast<uint4 *>(b + L.cl_dyn);
   s.stamp = reinterpret_cast<uint32_t *>(b + L.stamp); s.touched = reinterpret_cast<uint32_t *>(b + L.touched);
+  s.obj_flag = reinterpret_cast<uint32_t *>(b + L.obj_flag);
   s.dirty_flag = reinterpret_cast<uint32_t *>(b + L.dirty_flag); s.dirty_list = reinterpret_cast<uint32_t *>(b + L.dirty_list);
   s.act_res = reinterpret_cast<uint32_t *>(b + L.act_res); s.cre_res = reinterpret_cast<uint32_t *>(b + L.cre_res);
   s.inc = reinterpret_cast<uint32_t *>(b + L.inc);
@@ -459,8 +463,6 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       mark("k_decide2_phase1");
       CK(launch_decide2(dim3((e->n_recreate + kD2Warps - 1) / kD2Warps), false));
     }
-    mark("k_inc_finish");
-    k_inc_finish<<<1, 32, 0, M>>>(sc);  // closes the epoch: whatever the commits queued for an incremental pass is void now
   } else {
   const uint32_t ntiles = e->sl.ntiles;
   const bool fast = !e->force_radix;
@@ -610,7 +612,7 @@ int run_pass_once(kr_engine *e, const kr_flags &f) {
 void after_full_pass(kr_engine *e, const kr_flags &f) {
   e->inc_valid = e->ran_bucket && !e->no_incr;
   e->inc_flags = f; e->inc_n_pods = e->sizes.n_pods; e->inc_n_heads = e->sizes.n_heads;
-  e->host_results_stale = false; e->inc_n_dirty = 0; e->fetched = false; e->ran_inc = false;
+  e->host_results_stale = false; e->inc_n_dirty = 0; e->fetched = false; e->ran_inc = false; e->heads_rebuild = false;
   if (!f.skip_hash) e->hash_dirty = false;
 }
 
@@ -647,15 +649,13 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
     if (e->n_recreate) { mark("k_inc_mark_recreate"); k_inc_mark_recreate<<<(n.n_clusters + 255) / 256, 256, 0, M>>>(s, sc, z); }
   }
   const int grid = e->sm_count * 2;
-  if (n.n_heads || e->inc_n_heads) {
+  if (e->heads_rebuild) {  // a head Pod came or went since the table was built (the commit compared the keys on the host)
     mark("k_inc_aux_rebuild");
     k_inc_aux_clear<<<std::min<uint32_t>(grid, (e->sl.aux_slots + 255) / 256), 256, 0, M>>>(sc);
     k_inc_aux_insert<<<std::min<uint32_t>(grid, (n.n_heads + 255) / 256 + 1), 256, 0, M>>>(s, sc, z);
   }
-  mark("k_inc_prepare");
-  if (e->bstride <= 64) k_inc_prepare<2><<<grid, kD2Warps * 32, 0, M>>>(s, sc, z);
-  else if (e->bstride <= 128) k_inc_prepare<4><<<grid, kD2Warps * 32, 0, M>>>(s, sc, z);
-  else k_inc_prepare<8><<<grid, kD2Warps * 32, 0, M>>>(s, sc, z);
+  mark("k_inc_refresh");
+  k_inc_refresh<<<std::min<uint32_t>(grid, (n.n_clusters + 255) / 256 + 1), 256, 0, M>>>(s, sc);
   mark("k_inc_admit");
   k_inc_admit<<<grid, 256, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
   if (do_hash && !profile) CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
@@ -663,15 +663,15 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
     Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 2};
     const dim3 dgrid((n.n_clusters + kD2Warps - 1) / kD2Warps), dblock(kD2Warps * 32);
     mark("k_decide2_dirty");
-    if (e->bstride <= 64) k_decide2<2><<<dgrid, dblock, 0, M>>>(da);
-    else if (e->bstride <= 128) k_decide2<4><<<dgrid, dblock, 0, M>>>(da);
-    else k_decide2<8><<<dgrid, dblock, 0, M>>>(da);
+    if (e->bstride <= 64) k_decide2<2, true><<<dgrid, dblock, 0, M>>>(da);
+    else if (e->bstride <= 128) k_decide2<4, true><<<dgrid, dblock, 0, M>>>(da);
+    else k_decide2<8, true><<<dgrid, dblock, 0, M>>>(da);
   }
   if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
   // staging for the changed records: up to a quarter of the RayClusters (beyond that the whole record arrays are as cheap to move)
   {
-    const uint32_t capc = std::max<uint32_t>(64, n.n_clusters / 4), capg = capc * KR_SMEM_GROUPS;
-    const size_t need = 32 * (size_t)capc + sizeof(kr_cluster_result) * (size_t)capc + sizeof(kr_group_result) * (size_t)capg + 1024;
+    const uint32_t capc = std::max<uint32_t>(64, n.n_clusters / 4), capg = (uint32_t)std::min<uint64_t>((uint64_t)capc * KR_SMEM_GROUPS, (uint64_t)n.n_groups + 1);
+    const size_t need = align_up(32 * (size_t)capc) + align_up(sizeof(kr_cluster_result) * (size_t)capc) + sizeof(kr_group_result) * (size_t)capg + 1024;
     if (need > e->inc_stage_cap) {
       if (e->d_inc_stage) cudaFree(e->d_inc_stage);
       if (e->h_inc_stage) cudaFreeHost(e->h_inc_stage);
@@ -704,6 +704,7 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
     if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
     e->h2d_timed = true;
   }
+  e->heads_rebuild = false;  // (rebuilt here, or about to be rebuilt by the full pass)
   if (e->h_inc[KR_INC_VOID] || e->h_inc[KR_INC_STRUCTURAL]) return KR_OK;  // the caller takes the full pass
   if (!e->fetched) e->host_results_stale = true;  // the previous pass's records never reached the host copy
   e->fetched = false;
@@ -878,6 +879,11 @@ int kr_engine_set_option(kr_engine *e, uint32_t option, uint64_t value) {
     e->fixed_layout = value != 0;
     return KR_OK;
   }
+  if (option == KR_OPT_INCREMENTAL) {
+    e->no_incr = value == 0;
+    if (e->no_incr) e->inc_valid = false;
+    return KR_OK;
+  }
   return fail(e, KR_E_INVALID, "unknown option %u", option);
 }
 
@@ -944,7 +950,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
                         (const void *)k_compact_actions, (const void *)k_patch_pods, (const void *)k_patch_pod_values,
                         (const void *)k_match2<kMatchItems>, (const void *)k_decide2<2>, (const void *)k_decide2<4>, (const void *)k_decide2<8>, (const void *)k_hash3<1, 0>,
                         (const void *)k_inc_retire, (const void *)k_inc_objects, (const void *)k_inc_objects_keys, (const void *)k_inc_aux_clear, (const void *)k_inc_aux_insert,
-                        (const void *)k_inc_mark_recreate, (const void *)k_inc_prepare<2>, (const void *)k_inc_prepare<4>, (const void *)k_inc_prepare<8>, (const void *)k_inc_admit,
+                        (const void *)k_inc_mark_recreate, (const void *)k_decide2<2, true>, (const void *)k_decide2<4, true>, (const void *)k_decide2<8, true>, (const void *)k_inc_refresh, (const void *)k_inc_admit,
                         (const void *)k_inc_gather, (const void *)k_inc_finish};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
@@ -959,6 +965,20 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (const char *g = getenv("KR_NO_BUCKET")) e->no_bucket = (g[0] == '1');
   if (const char *g = getenv("KR_NO_INCR")) e->no_incr = (g[0] == '1');
   if (cudaHostAlloc((void **)&e->h_inc, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+  {  // buffers of the incremental path, sized for the capacities up front (a pinned allocation inside an epoch costs milliseconds)
+    const InLayout capl = in_layout(cap);
+    const size_t objs = capl.off[kFirstPodCol] + (capl.off[kNumCols - 1] - capl.off[kFirstPodCol + 7]);
+    if (cudaMalloc((void **)&e->d_obj_stage, objs) != cudaSuccess) return bail(KR_E_CUDA);
+    e->obj_stage_cap = objs;
+    const uint32_t capc = std::max<uint32_t>(64, cfg->max_clusters / 4), capg = (uint32_t)std::min<uint64_t>((uint64_t)capc * KR_SMEM_GROUPS, (uint64_t)cfg->max_groups + 1);
+    const size_t need = align_up(32 * (size_t)capc) + align_up(sizeof(kr_cluster_result) * (size_t)capc) + sizeof(kr_group_result) * (size_t)capg + 1024;
+    if (cudaMalloc((void **)&e->d_inc_stage, need) != cudaSuccess) return bail(KR_E_CUDA);
+    if (cudaHostAlloc((void **)&e->h_inc_stage, need, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+    e->inc_stage_cap = need;
+    const size_t chg = std::max<size_t>(1024, (size_t)cfg->max_clusters);
+    if (cudaHostAlloc((void **)&e->h_changed, 4 * chg, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
+    e->h_changed_cap = chg;
+  }
   if (cudaHostAlloc((void **)&e->h_order, 4 * ((size_t)cfg->max_clusters + 1), cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_order, 4 * ((size_t)cfg->max_clusters + 1)) != cudaSuccess) return bail(KR_E_CUDA);
   cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming);
@@ -1081,9 +1101,9 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   }
   if (parts & KR_PART_COLUMNS) e->inc_valid = false;  // pod columns uploaded wholesale: the resident buckets no longer describe them
   if (parts & KR_PART_JSON) e->hash_dirty = true;
-  if (e->prev_json_off.size() != n.n_clusters) { e->prev_json_off.assign(n.n_clusters, ~0ull); e->prev_json_len.assign(n.n_clusters, ~0u); e->hash_dirty = true; }
-  for (uint32_t c = 0; c < n.n_clusters; c++)
-    if (e->prev_json_off[c] != hb.c_json_off[c] || e->prev_json_len[c] != hb.c_json_len[c]) { e->hash_dirty = true; e->prev_json_off[c] = hb.c_json_off[c]; e->prev_json_len[c] = hb.c_json_len[c]; }
+  bool ranges_moved = e->prev_json_off.size() != n.n_clusters;  // some RayCluster's JSON range differs from the one the digests / the hash order were computed from
+  for (uint32_t c = 0; c < n.n_clusters && !ranges_moved; c++)
+    ranges_moved = e->prev_json_off[c] != hb.c_json_off[c] || e->prev_json_len[c] != hb.c_json_len[c];
   if (goff != n.n_groups) return fail(e, KR_E_INVALID, "sum of group_cnt (%llu) != n_groups (%u)", (unsigned long long)goff, n.n_groups);
   if (woff != n.n_wtd) return fail(e, KR_E_INVALID, "sum of g_wtd_cnt (%llu) != n_wtd (%u)", (unsigned long long)woff, n.n_wtd);
   for (uint32_t h = 0; h < n.n_heads; h++)
@@ -1092,7 +1112,7 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   e->n_recreate = n_recreate; e->snap_has_mh = has_mh; e->snap_max_groups = max_groups;
   // hash order: message ids by descending SHA-1 block count (counting sort; the kernels run length-homogeneous warps, longest first)
   if (e->order_pending) { CK(cudaEventSynchronize(e->ev_order)); e->order_pending = false; }  // a previous upload may still be reading h_order
-  {
+  if (ranges_moved) {  // (unchanged lengths: the resident order stands — an object / pod epoch does not pay for it)
     uint32_t maxb = 0;
     for (uint32_t c = 0; c < n.n_clusters; c++) maxb = std::max(maxb, (hb.c_json_len[c] + 8) / 64 + 1);
     if (maxb <= (1u << 20)) {
@@ -1181,14 +1201,25 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     Sizes zz{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
     if (first) k_inc_objects<<<(first + 255) / 256, 256, 0, e->scopy>>>(oa, sd, scd, zz);
     if (n.n_heads) k_inc_objects_keys<<<(n.n_heads + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n.n_heads);
-    if (n.n_heads != e->res_n_heads) CK(cudaMemsetAsync(scd.inc + KR_INC_HEADS, 1, 1, e->scopy));  // rows came or went: the pod -> row table is rebuilt
     CK(cudaGetLastError());
   }
-  if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) e->res_n_heads = n.n_heads;
+  if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) {
+    if (e->prev_h_pod_idx.size() != n.n_heads || (n.n_heads && memcmp(e->prev_h_pod_idx.data(), hb.h_pod_idx, 4 * (size_t)n.n_heads) != 0)) {
+      e->heads_rebuild = true;
+      e->prev_h_pod_idx.assign(hb.h_pod_idx, hb.h_pod_idx + n.n_heads);
+    }
+    e->res_n_heads = n.n_heads;
+  }
   CK(cudaEventRecord(e->ev_cols, e->scopy));
-  if (n.n_clusters) { CK(cudaMemcpyAsync(e->d_order, e->h_order, 4 * (size_t)n.n_clusters, cudaMemcpyHostToDevice, e->scopy)); bytes += 4 * (size_t)n.n_clusters; }
-  CK(cudaEventRecord(e->ev_order, e->scopy));
-  e->order_pending = true;
+  if (ranges_moved) {  // the new order travels with this commit: from here on the recorded ranges are the ones it was built from
+    e->hash_dirty = true;
+    e->prev_json_off.assign(hb.c_json_off, hb.c_json_off + n.n_clusters); e->prev_json_len.assign(hb.c_json_len, hb.c_json_len + n.n_clusters);
+    if (n.n_clusters) {
+      CK(cudaMemcpyAsync(e->d_order, e->h_order, 4 * (size_t)n.n_clusters, cudaMemcpyHostToDevice, e->scopy)); bytes += 4 * (size_t)n.n_clusters;
+      CK(cudaEventRecord(e->ev_order, e->scopy));
+      e->order_pending = true;
+    }
+  }
   if (parts & KR_PART_JSON) { if (int rc = up(json_off, e->fixed_layout ? (size_t)n.json_bytes : e->il.total - json_off)) return rc; }
   CK(cudaEventRecord(e->ev_json, e->scopy));
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));

@@ -12,12 +12,12 @@
 //                                                             dirty, a changed table key or CSR offset makes the epoch
 //                                                             "structural" (the next pass is a full one).
 // The pass then touches only what changed:
-//   k_inc_prepare  (one warp per dirty RayCluster) rewrites its input record, drops the stamped rows from its bucket (in place,
-//                  arrival order kept) and recomputes its first head;
 //   k_inc_admit    (one thread per touched row) runs the selector match of k_match2 on the row's NEW values and appends the
-//                  record to its bucket — marking that RayCluster dirty as well;
-//   k_decide2<K>   phase 2: the unchanged decide kernel over the dirty list (digests are resident, so the Recreate gate is
-//                  decided in place); a cluster keeps its places in the action list / create arena while they suffice;
+//                  record (marked KR_ROW_FRESH) to its RayCluster's bucket — marking that RayCluster dirty as well;
+//   k_inc_refresh  rewrites the 128-byte input record of the RayClusters whose RayCluster / group rows changed;
+//   k_decide2<K>   phase 2: the decide kernel over the dirty list.  Each warp first drops the records of stamped rows from its bucket (stored back compacted, arrival order
+//                  kept) and recomputes the first head; then decides as in a full pass (digests are resident, so the Recreate
+//                  gate is decided in place); a cluster keeps its places in the action list / create arena while they suffice;
 //   k_inc_gather   packs the changed cluster / group records for one small D2H copy.
 // Results are bit-identical to a full pass over the same state (tests/test_live_arena.py, tests/test_packer.py run every epoch
 // against the oracle); anything the resident state cannot absorb — structural object changes, a bucket or arena overflow — voids
@@ -28,7 +28,7 @@
 
 namespace kr {
 
-__device__ __forceinline__ uint32_t inc_epoch(const ScratchDev &sc) { return __ldcg(&sc.inc[KR_INC_EPOCH]) + 1u; }
+__device__ __forceinline__ uint32_t inc_epoch(const ScratchDev &sc) { return inc_epoch_of(sc); }
 
 __device__ __forceinline__ void mark_dirty(const ScratchDev &sc, uint32_t c, uint32_t epoch) {
   if (atomicExch(&sc.dirty_flag[c], epoch) != epoch) sc.dirty_list[atomicAdd(&sc.inc[KR_INC_DIRTY], 1u)] = c;
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(256) k_inc_objects(ObjDiffArgs a, SnapDev s, S
   const uint32_t epoch = inc_epoch(sc);
   switch (a.cls[col]) {
     case KR_OC_STRUCT: sc.inc[KR_INC_STRUCTURAL] = 1u; break;
-    case KR_OC_CLUSTER: if (row < n.n_clusters) mark_dirty(sc, row, epoch); break;
-    case KR_OC_GROUP: { const uint32_t c = a.g_cluster_idx_new[row]; if (c < n.n_clusters) mark_dirty(sc, c, epoch); break; }
-    case KR_OC_HEADKEY: sc.inc[KR_INC_HEADS] = 1u;  // fall through: both pods' clusters see a different head-aux row now
+    case KR_OC_CLUSTER: if (row < n.n_clusters) { sc.obj_flag[row] = epoch; mark_dirty(sc, row, epoch); } break;
+    case KR_OC_GROUP: { const uint32_t c = a.g_cluster_idx_new[row]; if (c < n.n_clusters) { sc.obj_flag[c] = epoch; mark_dirty(sc, c, epoch); } break; }
+    case KR_OC_HEADKEY:  // (the host compared the keys as well and rebuilds the pod -> row table); both pods' clusters see a different head-aux row now
     case KR_OC_HEAD:
       mark_pod_cluster_dirty(s, sc, n, a.h_pod_idx_new[row], epoch);
       if (row < a.n_heads_old) mark_pod_cluster_dirty(s, sc, n, a.h_pod_idx_old[row], epoch);
@@ -144,11 +144,9 @@ __global__ void __launch_bounds__(256) k_inc_objects_keys(const uint32_t *src, u
 // ------------------------------------------------------------------------------------------------ head-aux table rebuild
 // pod idx -> head-aux row, when an epoch changed h_pod_idx (a head Pod came or went): clear, then insert (k_build_tables' third part)
 __global__ void __launch_bounds__(256) k_inc_aux_clear(ScratchDev sc) {
-  if (__ldcg(&sc.inc[KR_INC_HEADS]) == 0) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= sc.aux_mask; i += gridDim.x * blockDim.x) { sc.aux_keys[i] = KR_EMPTY32; sc.aux_vals[i] = KR_EMPTY32; }
 }
 __global__ void __launch_bounds__(256) k_inc_aux_insert(SnapDev s, ScratchDev sc, Sizes n) {
-  if (__ldcg(&sc.inc[KR_INC_HEADS]) == 0) return;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n.n_heads; t += gridDim.x * blockDim.x) {
     const uint32_t p = s.h_pod_idx[t];
     uint32_t i = mix32(p) & sc.aux_mask;
@@ -166,44 +164,16 @@ __global__ void __launch_bounds__(256) k_inc_mark_recreate(SnapDev s, ScratchDev
   if (c < n.n_clusters && (s.c_flags[c] & KR_CF_UPGRADE_RECREATE)) mark_dirty(sc, c, inc_epoch(sc));
 }
 
-// ------------------------------------------------------------------------------------------------ k_inc_prepare
-// One warp per RayCluster marked dirty by the commits of this epoch (grid-stride over the list).
-template <int K>
-__global__ void __launch_bounds__(kD2Warps * 32) k_inc_prepare(SnapDev s, ScratchDev sc, Sizes n) {
-  const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
-  const uint32_t S = sc.bucket_stride;
-  const uint32_t epoch = inc_epoch(sc);
+// ------------------------------------------------------------------------------------------------ k_inc_refresh
+// Input records (cl_in) of the RayClusters one of whose RayCluster / group rows an object commit changed (grid-stride over the
+// dirty list as the commits left it; clusters k_inc_admit adds later had no object change).
+__global__ void __launch_bounds__(256) k_inc_refresh(SnapDev s, ScratchDev sc) {
   const uint32_t n_dirty = __ldcg(&sc.inc[KR_INC_DIRTY]);
+  const uint32_t epoch = inc_epoch(sc);
   if (__ldcg(&sc.inc[KR_INC_STRUCTURAL])) return;
-  for (uint32_t i = blockIdx.x * kD2Warps + (threadIdx.x >> 5); i < n_dirty; i += gridDim.x * kD2Warps) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dirty; i += gridDim.x * blockDim.x) {
     const uint32_t c = sc.dirty_list[i];
-    if (lane == 0) write_cl_in(s, sc, c, s.c_group_off[c], s.c_group_cnt[c]);
-    uint4 *bucket = sc.bucket + (size_t)c * S;
-    const uint32_t P = min(__ldcg(&sc.cl_dyn[c].x), S);
-    uint32_t kept = 0, head_min = 0xFFFFFFFFu;
-    uint4 recs[K];
-    bool keep[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      const uint32_t j = k * 32 + lane;
-      keep[k] = false;
-      if (j < P) { recs[k] = __ldcg(&bucket[j]); keep[k] = __ldcg(&sc.stamp[recs[k].x]) != epoch; }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep[k]);
-      if (keep[k]) {
-        bucket[kept + __popc(bal & lt)] = recs[k];  // never past a record not yet read: kept + rank <= k * 32 + lane
-        if (pp_node_type(recs[k].y & 0xFFFFu) == KR_NT_HEAD) head_min = min(head_min, recs[k].x);
-      }
-      kept += __popc(bal);
-    }
-    head_min = __reduce_min_sync(0xFFFFFFFFu, head_min);
-    if (lane == 0) {
-      unsigned long long raw = 0;
-      if (head_min != 0xFFFFFFFFu) raw = ~(((unsigned long long)head_min << 32) | (uint32_t)(aux_lookup(sc, head_min) + 1));
-      sc.cl_dyn[c] = make_uint4(kept, 0u, (uint32_t)raw, (uint32_t)(raw >> 32));
-    }
+    if (__ldcg(&sc.obj_flag[c]) == epoch) write_cl_in(s, sc, c, s.c_group_off[c], s.c_group_cnt[c]);
   }
 }
 
@@ -259,13 +229,9 @@ __global__ void __launch_bounds__(256) k_inc_admit(SnapDev s, ScratchDev sc, Res
       if (!(pk & KR_PP_TOMBSTONE)) atomicAdd(&r.totals[1], 1u);
       continue;
     }
-    mark_dirty(sc, c, epoch);
-    if (pp_node_type(pk) == KR_NT_HEAD) {
-      const unsigned long long key = ((unsigned long long)p << 32) | (uint32_t)(aux_lookup(sc, p) + 1);
-      atomicMax(reinterpret_cast<unsigned long long *>(&sc.cl_dyn[c].z), ~key);
-    }
+    mark_dirty(sc, c, epoch);  // the decide warp drops the row's stale record, takes this one and recomputes the first head
     const uint32_t rank = atomicAdd(&sc.cl_dyn[c].x, 1u);
-    if (rank < sc.bucket_stride) sc.bucket[(size_t)c * sc.bucket_stride + rank] = make_uint4(p, (slot << 16) | flags, ri, nm);
+    if (rank < sc.bucket_stride) sc.bucket[(size_t)c * sc.bucket_stride + rank] = make_uint4(p, (slot << 16) | flags | KR_ROW_FRESH, ri, nm);
     else sc.inc[KR_INC_VOID] = 1u;
   }
 }

@@ -54,6 +54,13 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
   KR_TL(0);
   pdl_trigger();  // the match kernel's CTAs may be scheduled now: they load their pod columns, then wait for this grid to finish
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
+    // A full pass closes the running incremental epoch (kr_incr.cuh): whatever the commits queued for an incremental pass is void,
+    // and the next epoch's stamps must differ from every stamp written so far.  (Every commit kernel of this epoch has finished:
+    // the pass waits for the commit stream before this kernel.)
+    sc.inc[KR_INC_TOUCHED] = 0; sc.inc[KR_INC_DIRTY] = 0; sc.inc[KR_INC_STRUCTURAL] = 0; sc.inc[KR_INC_HEADS] = 0; sc.inc[KR_INC_VOID] = 0; sc.inc[KR_INC_GROUPS] = 0;
+    sc.inc[KR_INC_EPOCH] += 1u;
+  }
   if (t < n.n_clusters) {
     uint32_t ns = s.c_ns_id[t], name = s.c_name_id[t];
     uint32_t i = hash_pair(ns, name) & sc.cl_mask;

@@ -227,6 +227,10 @@ class Engine:
         """KR_OPT_FIXED_LAYOUT: lay the arenas out for the capacities once; begin() then only sets the live row counts."""
         self._check(self._L.kr_engine_set_option(self._h, abi.OPT_FIXED_LAYOUT, 1 if on else 0))
 
+    def set_incremental(self, on: bool = True):
+        """KR_OPT_INCREMENTAL: allow (default) or forbid device-side incremental passes; off = every pass is a full pass."""
+        self._check(self._L.kr_engine_set_option(self._h, abi.OPT_INCREMENTAL, 1 if on else 0))
+
     def begin(self, sizes: abi.kr_sizes) -> dict[str, np.ndarray]:
         """kr_snapshot_begin: returns numpy views over the engine-owned pinned arenas, keyed by column name."""
         bufs = abi.kr_snapshot_bufs()
