@@ -4,19 +4,28 @@
 // shared-memory staging (hash chunks, per-tile digit counters, per-warp group accumulators), warp-ballot /
 // match_any group-by, grids sized in multiples of the SM count.
 //
-// Pipeline of one pass (engine stream M unless noted); one CUDA graph, programmatic dependent launch along the chain:
-//   k_clear          per-pass clears (hash tables, workersToDelete resolutions, totals, bucket counters) in one launch
-//   k_build_tables   cluster table (ns,name)->idx (+ per-cluster group record), workersToDelete-name table, head-aux table
-//   k_match          per pod: label/selector match -> cluster idx + group slot, 16-byte pod row, bucket rank
-//   k_place_fused    bucket starts (scan in shared memory) + pod -> slot of its cluster's bucket   [large: k_scan_counts + k_place]
-//   k_decide_small   one warp per RayCluster (<= 256 pods): in-register bitonic sort (List order), warp-ballot group-by,
-//                    head / group decisions, ordered deletes, status roll-up        | k_decide: general path, side stream
-//   k_hash2          (stream H, concurrent) SHA-1 + base32hex of every muted-spec JSON
-//   k_decide phase 1 clusters whose Recreate gate needs the hash
-//   k_creates_fused  create offsets + lowest free replica indices + compact action list   [large: k_scan_* + k_create_fill ...]
+// A FULL pass is one CUDA graph (stream M unless noted), programmatic dependent launch along the chain.  Production configuration
+// (kr_flags.fetch_pod_lists == 0, no multi-host group, <= KR_SMEM_GROUPS worker groups and <= 256 pods per RayCluster) — the
+// BUCKET pipeline (kr_bucket2.cuh):
+//   k_clear          per-pass clears (hash tables, workersToDelete resolutions, totals, bucket counters / first-head cells) in one launch
+//   k_build_tables   cluster table (ns,name)->{idx, flags, name of worker group 0}, the 128-byte per-cluster input record (cl_in),
+//                    workersToDelete-name table + Bloom bitmap, head-aux table; closes the running incremental epoch
+//   k_match2         per pod: selector match -> its cluster's fixed-stride bucket at an arrival rank (one returning atomic):
+//                    16-byte record {pod idx, group slot | flags, replica index, name id}; first head per cluster by a 64-bit atomicMax
+//   k_decide2        one warp per RayCluster, bucket in registers, ARRIVAL order: order-free counts, the ordered delete prefix by
+//                    min-extraction / counting rank, status roll-up, action list + replica indices placed with one atomic per cluster
+//   k_hash3          (stream H, concurrent) SHA-1 + base32hex of every muted-spec JSON: producer warp (staging, padding, W expansion)
+//                    + consumer warp (the 80-round chain) per 32 messages, messages ordered by block count   [> 19 k messages: k_hash2<4,1>]
+//   k_decide2 ph. 1  the clusters whose Recreate gate needs the digest, in the places phase 0 reserved
 //   k_jobs           RayJob -> RayCluster status roll-up join
-//   k_patch_pods     (copy stream, incremental epochs) rewritten pod rows pulled from the mapped pinned arena
-//   radix pipeline   (k_match<radix>, k_hist, k_scan_rows, k_scatter): stable LSD sort, taken when a RayCluster has > 1024 pods
+// When the caller asks for the full per-cluster pod lists (fetch_pod_lists == 1) or the snapshot does not qualify — the SORT pipeline:
+//   k_match -> k_place_fused -> k_decide_small (+ k_decide on a side stream) -> [phase 1] -> k_creates_fused
+//   (buckets restored to List order by an in-register bitonic sort), and for RayClusters with > 1024 pods the RADIX pipeline
+//   (k_match<radix>, k_hist, k_scan_rows, k_scatter: stable LSD sort) with the unfused scan kernels.
+// INCREMENTAL epochs (kr_incr.cuh, included by kr_engine.cu): after a full bucket pass everything stays resident; pod-row commits
+// run k_inc_retire on the rows' old values, object commits are diffed on the device (k_inc_objects), and the pass is
+//   k_inc_refresh -> k_inc_admit -> k_decide2<K, inc> over the dirty RayClusters -> k_inc_gather.
+//   k_patch_pods / k_patch_pod_values (copy stream): rewritten pod rows pulled from the mapped pinned arena / scattered from a staged copy.
 //
 // Reference semantics restated here are cited per function (paths relative to
 // ray-operator/controllers/ray/ in ray-project/kuberay).

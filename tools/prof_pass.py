@@ -15,6 +15,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "C3"
 snap, flags = synthetic.generate(synthetic.config(wl))
 flags.fetch_pod_lists = int(os.environ.get("TL_POD_LISTS", "0"))
 eng = Engine.for_snapshot(snap)
+eng.set_incremental(False)  # every pass here is the FULL pass
 eng.load(snap)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(int(os.environ.get("PASSES", "4"))):

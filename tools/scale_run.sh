@@ -4,18 +4,17 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python tools/group_check.py C5 > gpurun_out/r2_group_c5_n8.json 2> gpurun_out/r2_group_c5_n8.err
-python tools/group_check.py C3 > gpurun_out/r2_group_c3_n8.json 2> gpurun_out/r2_group_c3_n8.err
 python -m pytest tests/test_group.py -m gpu -q 2>&1 | tail -3 > gpurun_out/r2_group_tests_n8.txt
 P=29511
+NG=$(python -c "import torch; print(torch.cuda.device_count())")
 for N in 2 4 8; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((P+N)) bench.py --gpus $N --steps 20 --warmup 5 \
+  [ $N -le $NG ] || continue
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((P+N)) bench.py --gpus $N --steps 20 --warmup 5 --no-pack-leg \
     > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
 done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $((P+20)) bench.py --gpus 8 --steps 20 --warmup 5 --scaling strong \
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port $((P+20)) bench.py --gpus $NG --steps 20 --warmup 5 --scaling strong \
   > gpurun_out/r2_bench_n8_strong.json 2> gpurun_out/r2_bench_n8_strong.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $((P+21)) bench.py --impl reference --gpus 8 --steps 3 --warmup 1 \
-  > gpurun_out/r2_bench_ref_n8.json 2> gpurun_out/r2_bench_ref_n8.err
-tail -c 600 gpurun_out/r2_group_c5_n8.json gpurun_out/r2_group_c3_n8.json gpurun_out/r2_group_tests_n8.txt
+tail -c 600 gpurun_out/r2_group_c5_n8.json gpurun_out/r2_group_tests_n8.txt
 for f in gpurun_out/r2_bench_n*.json; do echo "== $f"; python - "$f" <<'PY'
 import json, sys
 try:

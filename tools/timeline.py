@@ -29,6 +29,7 @@ def main():
     flags.fetch_pod_lists = int(os.environ.get("TL_POD_LISTS", "0"))  # 0: production configuration (bucket pipeline)
     flags.skip_hash = int(os.environ.get("TL_SKIP_HASH", "0"))
     eng = Engine.for_snapshot(snap)
+    eng.set_incremental(False)  # every pass here is the FULL pass
     eng.load(snap)
     L = lib()
     L.kr_debug_timeline.argtypes = [C.c_void_p, C.c_void_p]
