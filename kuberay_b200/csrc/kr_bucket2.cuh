@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
 struct Decide2Args {
   SnapDev s; ScratchDev sc; ResDev r; Sizes n; kr_flags f;
   uint32_t create_cap;
+  int spin_hash;  // phase 0: a cluster whose Recreate gate reads a digest waits for the concurrently running hash kernel (no phase 1)
   int phase;  // 0: every RayCluster; 1: only the clusters phase 0 deferred (Recreate gate waiting for the hash kernel);
               // 2: only the clusters an incremental epoch marked dirty (kr_incr.cuh) — digests resident, places reused while they suffice
 };
@@ -343,15 +344,30 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
         if (ver == KR_VER_DIFFERENT) cr.head_update_annotations = 1;
         else if (ast == KR_ANNOT_OTHER) recreate = true;
         else if (ast == KR_ANNOT_HASH32 && !a.f.skip_hash) {
-          if (phase == 0) {
+          if (phase == 0 && !a.spin_hash) {
             // The hash kernel is still running on its own stream.  Decide the cluster as if the digests matched, reserve the
             // whole bucket in the action list (a Recreate deletes every pod) and let phase 1 redo it once the digest is there.
             deferred = true;
             if (lane == 0) a.sc.deferred_list[atomicAdd(&a.r.totals[4], 1u)] = c;
           } else {
             const uint8_t *ah = s.h_annot_hash + 32 * (size_t)aux;
-            const char *hh = a.r.hash + 32 * (size_t)c;
-            recreate = __any_sync(0xFFFFFFFFu, ah[lane] != (uint8_t)hh[lane]);
+            const uint32_t *hw = reinterpret_cast<const uint32_t *>(a.r.hash + 32 * (size_t)c);
+            if (phase == 0) {
+              // The hash kernel runs beside this one (its CTAs were resident before the chain started, and it takes the
+              // digests these gates read FIRST: kr_engine.cu builds the hash order that way), so the digest is normally there
+              // already; if not, wait for its last word — zeroed on the hash stream in front of the hash kernel, stored last by the hash lane.  Bounded: a warp that
+              // gives up flags the pass and the engine reruns it on the two-phase schedule.
+              if (lane == 0) {
+                const volatile uint32_t *w7 = hw + 7;
+                uint32_t it = 0;
+                while (*w7 == 0u && it < 40000u) { __nanosleep(100); it++; }
+                if (*w7 == 0u) atomicOr(&a.r.totals[3], KR_TOTALS_HASH_WAIT);
+              }
+              __syncwarp();
+              __threadfence();
+            }
+            const uint32_t word = __ldcg(&hw[lane >> 2]);
+            recreate = __any_sync(0xFFFFFFFFu, ah[lane] != (uint8_t)(word >> (8 * (lane & 3))));
           }
         }
       }

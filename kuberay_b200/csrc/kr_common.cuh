@@ -135,6 +135,8 @@ struct Sizes { uint32_t n_clusters, n_groups, n_wtd, n_pods, n_heads, n_jobs; };
 #define KR_MARK_ATTEMPT_VOID(totals) do { atomicOr(&(totals)[3], KR_TOTALS_BIG_BUCKET); (totals)[KR_TOTALS_VOID_WORD] = 1u; } while (0)
 #define KR_ATTEMPT_VOID(totals) KR_WORD_VOID(KR_ATTEMPT_WORD(totals))
 #define KR_TOTALS_BIG_BUCKET 2u        // fast pipeline only: some cluster (or the orphan bucket) holds more pods than the in-warp sort takes
+#define KR_TOTALS_HASH_WAIT 4u         // bucket pipeline: a decide warp gave up waiting for a digest of the concurrently running hash kernel
+                                       // (the engine reruns the pass with the two-phase schedule)
 
 
 static constexpr int kSortThreads = 256;

@@ -229,6 +229,9 @@ struct kr_engine {
   uint32_t *h_totals = nullptr;  // pinned copy of the device totals (pipeline fallback check)
   // bucket pipeline (kr_bucket2.cuh): taken when the caller does not fetch the full pod lists and the snapshot qualifies
   bool no_bucket = false;       // KR_NO_BUCKET=1: never take it (tests of the sort pipeline)
+  bool hash_spin = true;        // bucket pipeline: Recreate gates wait for their digest inside k_decide2 instead of a second decide phase
+                                // (KR_NO_HASH_SPIN=1, or a pass in which a warp gave up waiting, turns it off)
+  uint64_t recreate_sig = 0;    // which RayClusters carry KR_CF_UPGRADE_RECREATE (their messages lead the hash order)
   uint32_t bstride = 0;         // bucket stride of this layout (64 / 128 / 256); 0 = the layout does not qualify (a cluster outgrew 256 pods, ...)
   bool snap_has_mh = false;     // some worker group has numOfHosts > 1
   uint32_t snap_max_groups = 0; // most worker groups in one RayCluster
@@ -380,6 +383,12 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   // the committed snapshot: columns gate stream M, the JSON arena gates the hash
   const unsigned wflag = capturing ? cudaEventWaitExternal : cudaEventWaitDefault;
   // (the fork comes first so the hash can start while the columns are still landing — an incremental pod-row epoch leaves the JSON untouched)
+  // bucket pipeline (kr_bucket2.cuh): the caller does not fetch the full pod lists, no multi-host group is in play, every
+  // RayCluster has few worker groups and (checked on the device) at most `bstride` pods
+  const bool bucket = !e->no_bucket && !f.fetch_pod_lists && e->bstride != 0 && !e->force_radix && e->snap_max_groups <= KR_SMEM_GROUPS &&
+                      !(e->snap_has_mh && f.gate_multihost_indexing) && (size_t)n.n_clusters * e->bstride <= e->sl.bucket_entries;
+  // ... and there the clusters whose Recreate gate reads a digest wait for it inside the decide kernel (the hash runs beside it)
+  const bool spin = bucket && !profile && do_hash && e->hash_spin && e->n_recreate > 0;
   auto launch_hash = [&]() {
     // messages are taken in e->d_order (descending SHA-1 block count, built at commit): length-homogeneous warps, longest first
     const uint32_t ngroups = (n.n_clusters + 31) / 32;
@@ -399,6 +408,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     if (profile) return KR_OK;
     CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0));
     CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
+    if (do_hash && spin && n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, H));  // the digests' last words are "ready" marks (k_decide2)
     if (do_hash) launch_hash();
     else if (n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, H));
     CK(cudaEventRecord(e->ev_hash, H));
@@ -409,10 +419,6 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
   { int rc = start_hash_stream(); if (rc) return rc; }
 
   // --- stream M
-  // bucket pipeline (kr_bucket2.cuh): the caller does not fetch the full pod lists, no multi-host group is in play, every
-  // RayCluster has few worker groups and (checked on the device) at most `bstride` pods
-  const bool bucket = !e->no_bucket && !f.fetch_pod_lists && e->bstride != 0 && !e->force_radix && e->snap_max_groups <= KR_SMEM_GROUPS &&
-                      !(e->snap_has_mh && f.gate_multihost_indexing) && (size_t)n.n_clusters * e->bstride <= e->sl.bucket_entries;
   e->ran_bucket = bucket;
   sc.bucket_stride = e->bstride;
   const bool pdl = !profile && e->use_pdl;
@@ -441,7 +447,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       mark("k_match2");
       CK(launch_pdl(k_match2<kMatchItems>, dim3(mtiles), dim3(kSortThreads), n.n_wtd ? e->sl.wt_bits_n / 8 : 0, M, pdl, s, sc, r, z, n.n_wtd ? 1 : 0));
     }
-    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 0};
+    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, spin ? 1 : 0, 0};
     auto launch_decide2 = [&](dim3 grid, bool with_pdl) -> cudaError_t {
       if (e->bstride <= 64) return launch_pdl(k_decide2<2>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
       if (e->bstride <= 128) return launch_pdl(k_decide2<4>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
@@ -458,7 +464,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     } else {
       CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
     }
-    if (e->n_recreate > 0 && do_hash) {  // clusters whose Recreate gate needs the digest: decided again, in the places phase 0 reserved
+    if (e->n_recreate > 0 && do_hash && !spin) {  // clusters whose Recreate gate needs the digest: decided again, in the places phase 0 reserved
       da.phase = 1;
       mark("k_decide2_phase1");
       CK(launch_decide2(dim3((e->n_recreate + kD2Warps - 1) / kD2Warps), false));
@@ -660,7 +666,7 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
   k_inc_admit<<<grid, 256, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
   if (do_hash && !profile) CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
   if (n.n_clusters) {
-    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 2};
+    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 0, 2};
     const dim3 dgrid((n.n_clusters + kD2Warps - 1) / kD2Warps), dblock(kD2Warps * 32);
     mark("k_decide2_dirty");
     if (e->bstride <= 64) k_decide2<2, true><<<dgrid, dblock, 0, M>>>(da);
@@ -743,6 +749,10 @@ int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, e->ev_h2d0, e->ev_h2d1) == cudaSuccess) e->prof.h2d_ms = ms;
       e->h2d_timed = true;
+    }
+    if (e->h_totals[3] & KR_TOTALS_HASH_WAIT) {  // a decide warp gave up waiting for its digest: rerun on the two-phase schedule
+      e->hash_spin = false; e->gvalid = false;
+      continue;
     }
     if (!(e->h_totals[3] & KR_TOTALS_BIG_BUCKET)) { after_full_pass(e, f); return KR_OK; }
     // some RayCluster outgrew what this pipeline holds per bucket: bucket pipeline -> wider stride -> sort pipeline -> radix pipeline
@@ -964,6 +974,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaHostAlloc((void **)&e->h_totals, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   if (const char *g = getenv("KR_NO_BUCKET")) e->no_bucket = (g[0] == '1');
   if (const char *g = getenv("KR_NO_INCR")) e->no_incr = (g[0] == '1');
+  if (const char *g = getenv("KR_NO_HASH_SPIN")) e->hash_spin = !(g[0] == '1');
   if (cudaHostAlloc((void **)&e->h_inc, 64, cudaHostAllocDefault) != cudaSuccess) return bail(KR_E_CUDA);
   {  // buffers of the incremental path, sized for the capacities up front (a pinned allocation inside an epoch costs milliseconds)
     const InLayout capl = in_layout(cap);
@@ -1112,17 +1123,25 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
   e->n_recreate = n_recreate; e->snap_has_mh = has_mh; e->snap_max_groups = max_groups;
   // hash order: message ids by descending SHA-1 block count (counting sort; the kernels run length-homogeneous warps, longest first)
   if (e->order_pending) { CK(cudaEventSynchronize(e->ev_order)); e->order_pending = false; }  // a previous upload may still be reading h_order
-  if (ranges_moved) {  // (unchanged lengths: the resident order stands — an object / pod epoch does not pay for it)
+  // The RayClusters whose Recreate gate compares a digest lead the order: their digests are ready when the decide kernel, running
+  // beside the hash, gets to them (k_decide2 waits for a digest's last word otherwise).
+  uint64_t rsig = 0x9E3779B97F4A7C15ull * (n_recreate + 1);
+  for (uint32_t c = 0; c < n.n_clusters; c++) if (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) rsig = (rsig ^ c) * 0x100000001B3ull;
+  const bool order_stale = ranges_moved || rsig != e->recreate_sig;
+  if (order_stale) {  // (unchanged lengths and gates: the resident order stands — an object / pod epoch does not pay for it)
     uint32_t maxb = 0;
     for (uint32_t c = 0; c < n.n_clusters; c++) maxb = std::max(maxb, (hb.c_json_len[c] + 8) / 64 + 1);
-    if (maxb <= (1u << 20)) {
-      std::vector<uint32_t> start((size_t)maxb + 2, 0);
-      for (uint32_t c = 0; c < n.n_clusters; c++) start[maxb - ((hb.c_json_len[c] + 8) / 64 + 1) + 1]++;  // bucket 0 = longest
-      for (uint32_t b = 0; b <= maxb; b++) start[b + 1] += start[b];
-      for (uint32_t c = 0; c < n.n_clusters; c++) e->h_order[start[maxb - ((hb.c_json_len[c] + 8) / 64 + 1)]++] = c;
+    auto blocks_of = [&](uint32_t c) { return (hb.c_json_len[c] + 8) / 64 + 1; };
+    auto lead = [&](uint32_t c) { return (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) ? 0u : 1u; };
+    if (maxb <= (1u << 20)) {  // counting sort on (not Recreate, descending block count): bucket 0 = the longest Recreate message
+      std::vector<uint32_t> start(2 * ((size_t)maxb + 1) + 1, 0);
+      auto key = [&](uint32_t c) { return lead(c) * (maxb + 1) + (maxb - blocks_of(c)); };
+      for (uint32_t c = 0; c < n.n_clusters; c++) start[key(c) + 1]++;
+      for (size_t b = 0; b + 1 < start.size(); b++) start[b + 1] += start[b];
+      for (uint32_t c = 0; c < n.n_clusters; c++) e->h_order[start[key(c)]++] = c;
     } else {
       for (uint32_t c = 0; c < n.n_clusters; c++) e->h_order[c] = c;
-      std::stable_sort(e->h_order, e->h_order + n.n_clusters, [&](uint32_t a, uint32_t b) { return hb.c_json_len[a] / 64 > hb.c_json_len[b] / 64; });
+      std::stable_sort(e->h_order, e->h_order + n.n_clusters, [&](uint32_t a, uint32_t b) { return lead(a) != lead(b) ? lead(a) < lead(b) : blocks_of(a) > blocks_of(b); });
     }
   }
   // Asynchronous, in two parts on the copy stream: every column first, the spec-JSON arena (the larger half) second.
@@ -1211,9 +1230,12 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     e->res_n_heads = n.n_heads;
   }
   CK(cudaEventRecord(e->ev_cols, e->scopy));
-  if (ranges_moved) {  // the new order travels with this commit: from here on the recorded ranges are the ones it was built from
+  if (ranges_moved) {  // digests of moved ranges are stale
     e->hash_dirty = true;
     e->prev_json_off.assign(hb.c_json_off, hb.c_json_off + n.n_clusters); e->prev_json_len.assign(hb.c_json_len, hb.c_json_len + n.n_clusters);
+  }
+  if (order_stale) {  // the new order travels with this commit: from here on the recorded ranges / gates are the ones it was built from
+    e->recreate_sig = rsig;
     if (n.n_clusters) {
       CK(cudaMemcpyAsync(e->d_order, e->h_order, 4 * (size_t)n.n_clusters, cudaMemcpyHostToDevice, e->scopy)); bytes += 4 * (size_t)n.n_clusters;
       CK(cudaEventRecord(e->ev_order, e->scopy));

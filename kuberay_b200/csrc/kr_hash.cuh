@@ -320,9 +320,14 @@ __device__ __forceinline__ void digest_to_base32hex(const uint32_t (&h)[5], char
     }
     o32[2 * j] = lo; o32[2 * j + 1] = hi;
   }
+  // The last word is the digest's "ready" mark: a decide warp of the concurrently running main chain may be polling it
+  // (k_decide2: Recreate gate), so it is stored after a fence, once the other 28 bytes are visible.
   uint4 *dst = reinterpret_cast<uint4 *>(out32);
   dst[0] = make_uint4(o32[0], o32[1], o32[2], o32[3]);
-  dst[1] = make_uint4(o32[4], o32[5], o32[6], o32[7]);
+  reinterpret_cast<uint2 *>(out32)[2] = make_uint2(o32[4], o32[5]);
+  reinterpret_cast<uint32_t *>(out32)[6] = o32[6];
+  __threadfence();
+  reinterpret_cast<volatile uint32_t *>(out32)[7] = o32[7];
 }
 
 // grid: CTAs of PAIRS x 64 threads (even warp = consumer, odd warp = producer); G = total pairs; group g of 32 messages (in
