@@ -34,11 +34,11 @@ UNIT = "reconciles/s"
 
 def _ncu_traffic(kernel: str, workload: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture of
-    this same command (profiles/r1_ncu_full_c3.json; C3 only) — None when no capture matches."""
+    this same command (profiles/r2_ncu_full_c3.json; C3 only) — None when no capture matches."""
     if workload != "C3":
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_c3.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_full_c3.json")) as f:
             prof = json.load(f)
     except Exception:
         return None
@@ -53,7 +53,7 @@ def _ncu_inst(kernel: str, workload: str):
     if workload != "C3":
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_c3.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_full_c3.json")) as f:
             prof = json.load(f)
     except Exception:
         return None
@@ -468,7 +468,7 @@ def main():
         dom_ms = kavg[dom] if dom == "k_hash" else non_hash_ms
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom if dom == "k_hash" else "match->sort->decide pipeline", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": _ncu_traffic("k_hash2" if dom == "k_hash" else dom, args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_ms": dom_ms,
+                "frac": ach / peak, "traffic": _ncu_traffic("k_hash3" if dom == "k_hash" else dom, args.workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_ms": dom_ms,
                 "note": "k_hash is INT32-issue/latency bound (SHA-1 is a serial chain per message; 80 rounds per 64 B), HBM is its secondary bound" if dom == "k_hash" else ""}
         kernels = {k: round(v, 5) for k, v in sorted(kavg.items(), key=lambda kv: -kv[1])}
         # The hash against the bound that actually holds it ("report ... and the ALU-bound ceiling"): warp instructions
@@ -476,12 +476,12 @@ def main():
         # 2 cycles per scheduler; ~all of SHA-1 is LOP3/SHF/IADD3/LEA on that pipe) — over all 4 x SMs schedulers, and over the
         # ceil(n/32) schedulers that have a warp at all when there are fewer one-lane-per-message warps than schedulers.
         hash_alu = None
-        h_inst = _ncu_inst("k_hash2", args.workload)
+        h_inst = _ncu_inst("k_hash3", args.workload)
         if h_inst and kavg.get("k_hash") and clocks.get("sm_mhz"):
             n_sched = 4 * torch.cuda.get_device_properties(local_rank).multi_processor_count
             rate = h_inst / (kavg["k_hash"] / 1e3)  # warp instr / s
             per_sched_peak = clocks["sm_mhz"] * 1e6 / 2
-            busy = min(n_sched, (nc_local + 31) // 32)
+            busy = min(n_sched, 2 * ((nc_local + 31) // 32))  # k_hash3: a consumer and a producer warp per 32 messages
             hash_alu = {"warp_instr_per_launch": h_inst, "achieved_gwarp_instr_s": rate / 1e9, "alu_pipe_peak_gwarp_instr_s": n_sched * per_sched_peak / 1e9,
                         "frac_of_chip": rate / (n_sched * per_sched_peak), "schedulers_with_a_warp": busy, "frac_of_busy_schedulers": rate / (busy * per_sched_peak)}
         line = {

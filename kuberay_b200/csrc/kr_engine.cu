@@ -942,6 +942,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
   if (cudaMalloc((void **)&e->d_scratch, e->scratch_cap) != cudaSuccess) return bail(KR_E_CUDA);
   if (cudaMalloc((void **)&e->d_out, e->out_cap) != cudaSuccess) return bail(KR_E_CUDA);
   cudaMemset(e->d_out, 0, e->out_cap);  // the alignment padding between the result arrays travels with the single D2H copy
+  cudaMemset(e->d_scratch, 0, e->scratch_cap);  // bucket records past a cluster's count are loaded speculatively (and masked): never garbage
   cudaFuncSetAttribute(k_place_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   cudaFuncSetAttribute(k_creates_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)kFusedMaxCounters);
   {

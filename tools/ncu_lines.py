@@ -46,6 +46,7 @@ for ln in dis.splitlines():
     if ln.startswith(".text."):
         sym = ln[6:].rstrip(":")
         dem = subprocess.run(["c++filt", sym], capture_output=True, text=True).stdout.strip()
+        dem = dem.replace("false", "0").replace("true", "1")  # ncu prints bool template arguments as (bool)0 / (bool)1
         on = re.sub(r"\W+", "", dem.split("(")[0].replace("void kr::", "").replace("kr::", "", 1)) == want
         continue
     if not on:
