@@ -250,3 +250,33 @@ def test_sha1_random_lengths_against_hashlib(oracle_mod):
         m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
         assert oracle_mod.sha1(m) == hashlib.sha1(m).digest()
         assert oracle_mod.hash32(m) == base64.b32hexencode(hashlib.sha1(m).digest()).decode()
+
+
+def test_oracle_context_reuse_ranges_and_reps(oracle_mod):
+    """The CPU arm's machinery (bench.py CpuArm): one shared index per snapshot, many runs.  A context must give the same records as
+    the one-shot entry point — whole snapshot, any cluster range, either List mode, any thread count — and `reps` must not leak state
+    from one repetition into the next (the per-pod action scratch is cleared per cluster)."""
+    from kuberay_b200 import synthetic
+    from oracle import oracle
+    snap, flags = synthetic.generate(synthetic.config("C2", n_clusters=120, pods_per_cluster=14, groups=2, jobs=True, wtd_group_frac=0.4, seed=17))
+    want = oracle_mod.run(snap, flags)
+    cx = oracle.Context(snap)
+    try:
+        for mode in (oracle.INDEXED, oracle.NS_SCAN):
+            for threads in (1, 3):
+                got = cx.run(flags, list_mode=mode, threads=threads)
+                assert not want.diff(got), (mode, threads)
+        # ranges: the records of the clusters inside the range equal the full run's (records outside are whatever the last run left)
+        for c0, c1, reps in ((0, 40, 1), (40, 120, 1), (17, 18, 5), (0, 120, 3)):
+            got = cx.run_range(flags, c0, c1, list_mode=oracle.NS_SCAN, threads=2, reps=reps)
+            for f in want.clusters.dtype.names:
+                if f != "pod_start":  # (where the cluster's pods sit in the full per-cluster list: written by whole-snapshot runs only)
+                    assert np.array_equal(got.clusters[f][c0:c1], want.clusters[f][c0:c1]), (f, c0, c1, reps)
+            assert np.array_equal(got.hash[c0:c1], want.hash[c0:c1])
+            g0, g1 = int(snap.c_group_off[c0]), int(snap.c_group_off[c1 - 1] + snap.c_group_cnt[c1 - 1])
+            for f in ("expected", "n_list", "n_unhealthy", "n_running", "diff", "n_create", "flags"):
+                assert np.array_equal(got.groups[f][g0:g1], want.groups[f][g0:g1]), (f, c0, c1)
+        got = cx.run(flags)  # and a full run afterwards is still clean
+        assert not want.diff(got)
+    finally:
+        cx.close()
