@@ -17,6 +17,9 @@
 //     Reconcile(req) compares before it trusts a record ("... epoch matches, else fall back").
 // Everything an epoch needs beyond the changed rows is already resident in HBM: no per-epoch repack, no per-epoch full upload.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <queue>
@@ -44,7 +47,7 @@ struct ClusterRec {
   uint64_t json_off = 0;  // where it sits in the arena
   bool json_placed = false;
 };
-struct HeadRec { uint32_t ready_reason_id, ready_msg_id, pod_ip_id; uint8_t ready_status, annot_state, version_state; char hash[32]; };
+struct HeadRec { uint32_t ready_reason_id, ready_msg_id, pod_ip_id; uint8_t ready_status, annot_state, version_state; char hash[32]; uint32_t slot; /* its head-aux row */ };
 
 bool go_atoi32(const kr_str &t, int32_t &v) {  // strconv.Atoi on the replica-index label (raycluster_controller.go:857-860)
   if (!t.p || t.n == 0 || t.n > 11) return false;
@@ -90,7 +93,10 @@ struct kr_packer {
   uint64_t json_cursor = 0, json_dead = 0;
   uint64_t podset_version = 0, epoch = 0;
   uint32_t last_mode = 0;
-  std::vector<uint32_t> stage_rows, stage_vals;
+  std::vector<uint32_t> stage_vals;   // the epoch's journal: 7 values per entry of dirty_rows
+  std::vector<uint32_t> row_slot;     // pod row -> its journal entry (valid while row_dirty)
+  uint32_t n_heads_live = 0;          // head-aux rows in use (sizes.n_heads follows at flush)
+  kr_sizes engine_sizes{};            // the live counts the engine was last told (kr_snapshot_begin)
 
   uint32_t intern(const kr_str &s) {
     if (!s.p) return KR_ID_ABSENT;
@@ -108,15 +114,46 @@ namespace {
 
 int pfail(kr_packer *p, int code, const std::string &m) { p->err = m; return code; }
 
-void mark_row(kr_packer *p, uint32_t row) {
-  if (row >= p->row_dirty.size()) p->row_dirty.resize((size_t)row + 1024, 0);
-  if (!p->row_dirty[row]) { p->row_dirty[row] = 1; p->dirty_rows.push_back(row); }
+// A touched row gets a slot in the epoch's journal (row list + 7 values per row, what kr_snapshot_commit_pod_values takes): the
+// handler has the values in hand, so the flush gathers nothing from the arenas (70 k scattered reads per 10 k rows: 0.3 ms).
+uint32_t mark_row(kr_packer *p, uint32_t row) {
+  if (row >= p->row_dirty.size()) { p->row_dirty.resize((size_t)row + 1024, 0); p->row_slot.resize(p->row_dirty.size(), 0); }
+  if (!p->row_dirty[row]) {
+    p->row_dirty[row] = 1; p->row_slot[row] = (uint32_t)p->dirty_rows.size();
+    p->dirty_rows.push_back(row); p->stage_vals.resize(7 * p->dirty_rows.size());
+  }
   p->podset_version++;
+  return p->row_slot[row];
 }
 
 void write_pod_row(kr_packer *p, uint32_t row, uint32_t ns, uint32_t cl, uint32_t gr, uint32_t nm, uint32_t packed, int32_t ridx, uint32_t rname) {
   p->b.p_ns_id[row] = ns; p->b.p_cluster_name_id[row] = cl; p->b.p_group_name_id[row] = gr; p->b.p_name_id[row] = nm;
   p->b.p_packed[row] = packed; p->b.p_replica_index[row] = ridx; p->b.p_replica_name_id[row] = rname;
+  uint32_t *v = &p->stage_vals[7 * (size_t)mark_row(p, row)];  // (the last write of an epoch wins)
+  v[0] = ns; v[1] = cl; v[2] = gr; v[3] = nm; v[4] = packed; v[5] = (uint32_t)ridx; v[6] = rname;
+}
+
+// Head-aux rows are dense and STABLE: a head Pod keeps its row while it lives, a new one is appended, a removed one is replaced by
+// the last row.  An update rewrites one row in place — nothing is rebuilt at flush, and the engine's on-device diff of the object
+// tables sees exactly the rows that changed.
+void write_head_row(kr_packer *p, uint32_t h, uint32_t pod_row, const HeadRec &r) {
+  p->b.h_pod_idx[h] = pod_row; p->b.h_ready_status[h] = r.ready_status; p->b.h_ready_reason_id[h] = r.ready_reason_id; p->b.h_ready_msg_id[h] = r.ready_msg_id;
+  p->b.h_pod_ip_id[h] = r.pod_ip_id; p->b.h_annot_state[h] = r.annot_state; p->b.h_version_state[h] = r.version_state;
+  memcpy(p->b.h_annot_hash + 32 * (size_t)h, r.hash, 32);
+}
+void remove_head(kr_packer *p, uint32_t pod_row) {
+  auto it = p->heads.find(pod_row);
+  if (it == p->heads.end()) return;
+  const uint32_t h = it->second.slot, last = p->n_heads_live - 1;
+  p->heads.erase(it);
+  if (h != last) {  // the last row moves into the hole
+    const uint32_t moved_pod = p->b.h_pod_idx[last];
+    HeadRec &m = p->heads[moved_pod];
+    m.slot = h;
+    write_head_row(p, h, moved_pod, m);
+  }
+  p->n_heads_live = last;
+  p->heads_dirty = true;
 }
 
 // group / workersToDelete CSR + per-cluster offsets, from the cluster records (only when an event changed a group or a name list)
@@ -153,18 +190,6 @@ int compact_json(kr_packer *p) {
   p->json_cursor = 0; p->json_dead = 0;
   for (auto &c : p->clusters) if (int rc = place_json(p, c)) return pfail(p, rc, "kr_packer: muted-spec JSON exceeds kr_config.max_json_bytes");
   return KR_OK;
-}
-
-void rebuild_heads(kr_packer *p) {
-  uint32_t h = 0;
-  for (auto &kv : p->heads) {
-    const HeadRec &r = kv.second;
-    p->b.h_pod_idx[h] = kv.first; p->b.h_ready_status[h] = r.ready_status; p->b.h_ready_reason_id[h] = r.ready_reason_id; p->b.h_ready_msg_id[h] = r.ready_msg_id;
-    p->b.h_pod_ip_id[h] = r.pod_ip_id; p->b.h_annot_state[h] = r.annot_state; p->b.h_version_state[h] = r.version_state;
-    memcpy(p->b.h_annot_hash + 32 * (size_t)h, r.hash, 32);
-    h++;
-  }
-  p->sizes.n_heads = h;
 }
 
 void rebuild_jobs(kr_packer *p) {
@@ -228,8 +253,8 @@ int kr_packer_pod_upsert(kr_packer *p, const kr_pod_obj *o) {
   int32_t ridx = 0;
   if (go_atoi32(o->replica_index, ridx)) packed |= KR_PP_HAS_REPLICA_IDX; else ridx = 0;
   write_pod_row(p, row, ns, p->intern(o->cluster), p->intern(o->group), nm, packed, ridx, p->intern(o->replica_name));
-  mark_row(p, row);
-  const bool was_head = p->heads.count(row) != 0;
+  auto hit = p->heads.find(row);
+  const bool was_head = hit != p->heads.end();
   if (o->node_type == KR_NT_HEAD) {
     HeadRec h{};
     h.ready_status = o->head_ready_status; h.ready_reason_id = p->intern(o->head_ready_reason); h.ready_msg_id = p->intern(o->head_ready_msg);
@@ -240,8 +265,12 @@ int kr_packer_pod_upsert(kr_packer *p, const kr_pod_obj *o) {
     if (!o->kuberay_version.p || o->kuberay_version.n == 0) h.version_state = KR_VER_EMPTY;
     else h.version_state = (o->kuberay_version.n == p->kuberay_version.size() && !memcmp(o->kuberay_version.p, p->kuberay_version.data(), o->kuberay_version.n)) ? KR_VER_CURRENT : KR_VER_DIFFERENT;
     if (!was_head && p->heads.size() >= p->cap.max_heads) return pfail(p, KR_E_CAPACITY, "kr_packer: more head Pods than kr_config.max_heads");
-    p->heads[row] = h; p->heads_dirty = true;
-  } else if (was_head) { p->heads.erase(row); p->heads_dirty = true; }
+    if (was_head) h.slot = hit->second.slot;
+    else h.slot = p->n_heads_live++;
+    p->heads[row] = h;
+    write_head_row(p, h.slot, row, h);
+    p->heads_dirty = true;
+  } else if (was_head) remove_head(p, row);
   return KR_OK;
 }
 
@@ -254,8 +283,7 @@ int kr_packer_pod_delete(kr_packer *p, kr_str ns, kr_str name) {
   p->row_key[row] = Key{0, 0};
   write_pod_row(p, row, 0, 0, 0, 0, KR_PP_TOMBSTONE, 0, 0);  // a free row: matches no RayCluster
   p->free_rows.push(row);
-  mark_row(p, row);
-  if (p->heads.erase(row)) p->heads_dirty = true;
+  remove_head(p, row);
   return KR_OK;
 }
 
@@ -388,40 +416,40 @@ int kr_packer_job_delete(kr_packer *p, kr_str ns, kr_str name) {
 int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
   if (!p) return KR_E_INVALID;
   p->err.clear();
+  static const bool trace = getenv("KR_PACKER_TRACE") != nullptr;  // development aid: where a flush spends its time (stderr)
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = trace ? now() : 0;
+  double t1 = 0, t2 = 0, t3 = 0;
   if (p->json_dead * 2 > p->json_cursor && p->json_dead > (1u << 20)) { if (int rc = compact_json(p)) return rc; p->json_dirty = true; }
   if (p->tables_dirty) { if (int rc = rebuild_tables(p)) return rc; p->objects_dirty = true; }
-  if (p->heads_dirty) { rebuild_heads(p); p->objects_dirty = true; }
+  if (p->heads_dirty) { p->sizes.n_heads = p->n_heads_live; p->objects_dirty = true; }  // (rows were written in place by the handlers)
   if (p->jobs_dirty) { rebuild_jobs(p); p->objects_dirty = true; }
+  if (trace) t1 = now();
   kr_sizes want = p->sizes;
   want.n_clusters = (uint32_t)p->clusters.size(); want.n_pods = (uint32_t)p->row_key.size(); want.json_bytes = p->json_cursor;
   kr_snapshot_bufs same;
-  if (memcmp(&want, &p->sizes, sizeof want) != 0 || p->first) {
-    p->sizes = want;
+  p->sizes = want;
+  if (memcmp(&want, &p->engine_sizes, sizeof want) != 0 || p->first) {
     if (int rc = kr_snapshot_begin(p->e, &p->sizes, &same)) return rc;  // fixed layout: new live counts, same addresses, resident data kept
+    p->engine_sizes = want;
   }
   uint32_t mode = 0;
   if (p->first) {
     if (int rc = kr_snapshot_commit(p->e)) return rc;
     mode = KR_PACK_FULL;
   } else {
+    if (trace) t2 = now();
     uint32_t parts = (p->objects_dirty ? KR_PART_OBJECTS : 0u) | (p->json_dirty ? KR_PART_JSON : 0u);
     if (parts) { if (int rc = kr_snapshot_commit_parts(p->e, parts)) return rc; mode |= parts; }
-    if (!p->dirty_rows.empty()) {
-      const size_t n = p->dirty_rows.size();
-      p->stage_rows.assign(p->dirty_rows.begin(), p->dirty_rows.end());
-      p->stage_vals.resize(7 * n);
-      for (size_t i = 0; i < n; i++) {
-        const uint32_t r = p->stage_rows[i];
-        uint32_t *v = &p->stage_vals[7 * i];
-        v[0] = p->b.p_ns_id[r]; v[1] = p->b.p_cluster_name_id[r]; v[2] = p->b.p_group_name_id[r]; v[3] = p->b.p_name_id[r];
-        v[4] = p->b.p_packed[r]; v[5] = (uint32_t)p->b.p_replica_index[r]; v[6] = p->b.p_replica_name_id[r];
-      }
-      if (int rc = kr_snapshot_commit_pod_values(p->e, p->stage_rows.data(), p->stage_vals.data(), (uint32_t)n)) return rc;
+    if (trace) t3 = now();
+    if (!p->dirty_rows.empty()) {  // the epoch's journal, as the handlers wrote it
+      if (int rc = kr_snapshot_commit_pod_values(p->e, p->dirty_rows.data(), p->stage_vals.data(), (uint32_t)p->dirty_rows.size())) return rc;
       mode |= KR_PACK_POD_ROWS;
     }
   }
+  if (trace) fprintf(stderr, "kr_packer_flush: rebuilds %.0f us, begin %.0f us, commit_parts %.0f us, pod rows (%zu) %.0f us\n", t1 - t0, t2 - t1, t3 - t2, p->dirty_rows.size(), now() - t3);
   for (uint32_t r : p->dirty_rows) p->row_dirty[r] = 0;
-  p->dirty_rows.clear();
+  p->dirty_rows.clear(); p->stage_vals.clear();
   p->first = p->objects_dirty = p->tables_dirty = p->heads_dirty = p->jobs_dirty = p->json_dirty = false;
   p->epoch++;
   p->last_mode = mode;
@@ -430,7 +458,7 @@ int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
 }
 
 int kr_packer_bufs(kr_packer *p, kr_snapshot_bufs *out) { if (!p || !out) return KR_E_INVALID; *out = p->b; return KR_OK; }
-int kr_packer_sizes(kr_packer *p, kr_sizes *out) { if (!p || !out) return KR_E_INVALID; *out = p->sizes; out->n_clusters = (uint32_t)p->clusters.size(); out->n_pods = (uint32_t)p->row_key.size(); return KR_OK; }
+int kr_packer_sizes(kr_packer *p, kr_sizes *out) { if (!p || !out) return KR_E_INVALID; *out = p->sizes; out->n_clusters = (uint32_t)p->clusters.size(); out->n_pods = (uint32_t)p->row_key.size(); out->n_heads = p->n_heads_live; return KR_OK; }
 int64_t kr_packer_cluster_row(kr_packer *p, kr_str ns, kr_str name) {
   if (!p || !ns.p || !name.p) return -1;
   auto it = p->cluster_row.find(Key{p->intern(ns), p->intern(name)});
