@@ -429,7 +429,30 @@ def main():
         else:
             inc_kern = {k: round(v, 5) for k, v in eng.reconcile_profiled(flags)["kernels"]}
         freed = gone
+    # second variant: the same number of touched pods, but in 1 % of the RayClusters (a few clusters scaling / restarting — the usual
+    # shape of informer traffic) instead of spread uniformly over all of them.  Object rows are not re-uploaded here (none changed).
+    for c in pod_cols:
+        views[c][:] = snap.cols[c]
+    eng.commit(); eng.reconcile(flags, copy=False)
+    key = snap.p_ns_id.astype(np.uint64) << np.uint64(32) | snap.p_cluster_name_id.astype(np.uint64)
+    ckey = snap.c_ns_id.astype(np.uint64) << np.uint64(32) | snap.c_name_id.astype(np.uint64)
+    n_hot = max(1, nc_local // 100)
+    loc_s, loc_changed, loc_prof = 0.0, [], {"kernels_ms": 0.0, "d2h_ms": 0.0, "h2d_bytes": 0, "d2h_bytes": 0}
+    for step_i in range(args.steps):
+        hot = rng_c.choice(nc_local, n_hot, replace=False)
+        rows = np.nonzero(np.isin(key, ckey[hot]))[0].astype(np.uint32)
+        views["p_packed"][rows] ^= np.uint32(1 << 5)
+        vals = np.stack([views[c][rows].view(np.uint32) for c in pod_cols], axis=1)
+        t0 = time.perf_counter()
+        eng.commit_pod_values(rows, vals)
+        res_i = eng.reconcile(flags, copy=False)
+        loc_s += time.perf_counter() - t0
+        loc_prof = eng.last_profile()
+        loc_changed.append(int(res_i.n_changed) if res_i.changed_clusters is not None or res_i.n_changed < nc_local else -1)
+        loc_rows = int(rows.size)
     eng.set_incremental(False)
+    for c in pod_cols:
+        views[c][:] = snap.cols[c]
     barrier()
     # host packing stand-in (not in e2e): copying pre-packed columns into the pinned arenas
     t0 = time.perf_counter()
@@ -508,6 +531,11 @@ def main():
                                                "note": "extra, not the headline: per step informer events touched 1 % of the pods (0.8 % status updates, 0.1 % deletions -> tombstone rows, 0.1 % additions into freed rows); "
                                                        "uploaded: those rows (kr_snapshot_commit_pod_values, 32 B each) + all RayCluster/group/head/RayJob rows (KR_PART_OBJECTS); the pass is incremental ON THE DEVICE "
                                                        "(kr_incr.cuh: only the touched rows are re-matched, only the RayClusters they belong to re-decided, digests stay resident) and bit-identical to a full pass"},
+            "e2e_incremental_1pct_of_clusters": {"value": nc_local * world * args.steps / loc_s if world == 1 else None, "unit": UNIT, "ms_per_step": 1e3 * loc_s / args.steps,
+                                                 "touched_pods_per_step": loc_rows, "changed_clusters_per_step": (int(np.mean([x for x in loc_changed if x >= 0])) if any(x >= 0 for x in loc_changed) else None),
+                                                 "device_incremental_steps": sum(1 for x in loc_changed if x >= 0), "kernels_ms": loc_prof["kernels_ms"], "d2h_ms": loc_prof["d2h_ms"],
+                                                 "h2d_bytes_per_step": int(loc_prof["h2d_bytes"]), "d2h_bytes_per_step": int(loc_prof["d2h_bytes"]),
+                                                 "note": "extra, rank 0's own figure: every pod of 1 % of the RayClusters changed (kr_snapshot_commit_pod_values only); the pass re-decides just those clusters and returns just their records"},
             "gpu_launches": int(n_kernels) * args.steps,
             "clocks": clocks,
             "roofline": roof,

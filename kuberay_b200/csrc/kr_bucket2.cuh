@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
     if (should_delete(pk[it])) flags |= KR_ROW_UNHEALTHY;  // shouldDeletePod (raycluster_controller.go:1181-1231), once per pod, here
     if (has_wtd && v) {  // scaleStrategy.workersToDelete: Delete(ns, name) (raycluster_controller.go:817-822)
       const uint32_t hk = hash_pair(ns[it], nm[it]);
-      if (sm_bits[(hk & sc.wt_bits_mask) >> 5] & (1u << (hk & 31))) {
+      const uint32_t h2 = bloom2(hk);
+      if ((sm_bits[(hk & sc.wt_bits_mask) >> 5] & (1u << (hk & 31))) && (sm_bits[(h2 & sc.wt_bits_mask) >> 5] & (1u << (h2 & 31)))) {
         const uint64_t k = key2(ns[it], nm[it]);
         uint32_t i = hk & sc.wt_mask;
         uint64_t kk = __ldg(&sc.wt_keys[i]);
@@ -140,8 +141,10 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
 #pragma unroll
   for (int it = 0; it < kItems; it++) {
     if (cidx[it] >= n.n_clusters) continue;
-    if (rank[it] < sc.bucket_stride) sc.bucket[(size_t)cidx[it] * sc.bucket_stride + rank[it]] = make_uint4(base + it * 32, roww[it], ri[it], nm[it]);
-    else KR_MARK_ATTEMPT_VOID(r.totals);  // the engine reruns the pass with a wider stride / on the sort pipeline
+    if (rank[it] < sc.bucket_stride) {
+      sc.bucket[(size_t)cidx[it] * sc.bucket_stride + rank[it]] = make_uint4(base + it * 32, roww[it], ri[it], nm[it]);
+      sc.pos[base + it * 32] = rank[it];  // (coalesced; incremental epochs rewrite a row's record in place)
+    } else KR_MARK_ATTEMPT_VOID(r.totals);  // the engine reruns the pass with a wider stride / on the sort pipeline
   }
   // pods that match no RayCluster of the snapshot (free rows of an incrementally maintained arena are not orphans)
   if (lane == 0) s_orph[warp] = orphans;
@@ -207,21 +210,25 @@ __global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decid
   uint32_t P = dyn.x;
   if (P > S) { mine = false; P = 0; }  // k_match2 voided the attempt
   if (kInc) {
-    // Incremental epoch: the bucket holds the records of the last pass plus the ones k_inc_admit appended (KR_ROW_FRESH).  Records
-    // of rows the epoch touched are stale (k_inc_retire stamped the row): drop them, store the bucket back compacted (arrival
-    // order kept) and take the cluster's first head from what is left.
+    // Incremental epoch: k_inc_admit rewrote the records of rows that stayed in this cluster in place and appended the records of
+    // rows that joined it (KR_ROW_FRESH).  Only if the cluster LOST a row (deleted, or now in another cluster: cl_dyn.y carries the
+    // epoch) some records are stale — the ones whose row is still stamped: drop them and store the bucket back compacted (arrival
+    // order kept, pos[] follows the records that move).  Then take the cluster's first head from what is left.
     const uint32_t epoch = inc_epoch_of(a.sc);
+    const bool lost = dyn.y == epoch;
     uint32_t kept = 0, head_min = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const uint32_t j = k * 32 + lane;
       bool keep = mine && j < P;
-      if (keep && !(recs[k].y & KR_ROW_FRESH)) keep = __ldcg(&a.sc.stamp[recs[k].x]) != epoch;
+      const bool fresh = keep && (recs[k].y & KR_ROW_FRESH);
+      if (keep && lost && !fresh) keep = __ldcg(&a.sc.stamp[recs[k].x]) != epoch;
       const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
       if (keep) {
         uint4 rec = recs[k];
         rec.y &= ~KR_ROW_FRESH;
-        bucket[kept + __popc(bal & lt)] = rec;
+        const uint32_t to = kept + __popc(bal & lt);
+        if (fresh || to != j) { bucket[to] = rec; if (to != j) a.sc.pos[rec.x] = to; }
         if (pp_node_type(rec.y & 0xFFFFu) == KR_NT_HEAD) head_min = min(head_min, rec.x);
       }
       kept += __popc(bal);

@@ -85,10 +85,13 @@ struct ScratchDev {
   uint4 *bucket; uint32_t bucket_stride;                       // [n_clusters * stride] {pod idx, slot << 16 | flags, replica index, name id}, arrival order
   uint32_t *wt_bits; uint32_t wt_bits_mask;                    // Bloom bitmap over the workersToDelete (ns, name) keys (power-of-two bit count)
   uint32_t *cl_in;                                             // [32 * n_clusters] every per-cluster input of the decide kernel as ONE 128-byte record (KR_CI_*)
-  uint4 *cl_dyn;                                               // [n_clusters] {pods bucketed so far, -, ~(first head's pod idx << 32 | head-aux row + 1)}, zeroed every full pass
+  uint4 *cl_dyn;                                               // [n_clusters] {pods bucketed so far, incremental epoch in which the cluster LOST a row (its bucket must be
+                                                               // compacted), ~(first head's pod idx << 32 | head-aux row + 1)}, zeroed every full pass
   // device-side incremental epochs (kr_incr.cuh): the buckets, cl_dyn, cl_in, the tables and the results stay resident between passes
   uint32_t *stamp;                                             // [n_pods] epoch in which the row was last touched (retired) by a pod commit
   uint32_t *touched;                                           // [n_pods] rows touched since the last pass (each once), count in inc[KR_INC_TOUCHED]
+  uint32_t *touched_old;                                       // [n_pods] per touched entry: the RayCluster the row was in before the commit (KR_EMPTY32: none)
+  uint32_t *pos;                                               // [n_pods] where the row's record sits in its RayCluster's bucket (k_match2, k_inc_admit, phase-2 compaction)
   uint32_t *dirty_flag;                                        // [n_clusters] epoch in which the RayCluster was last marked dirty
   uint32_t *obj_flag;                                          // [n_clusters] epoch in which an object commit changed one of its rows (its input record is rewritten)
   uint32_t *dirty_list;                                        // [n_clusters] RayClusters to decide again, count in inc[KR_INC_DIRTY]
@@ -176,6 +179,9 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __device__ __forceinline__ uint64_t key2(uint32_t a, uint32_t b) { return ((uint64_t)a << 32) | b; }
 // slot hash of an (a, b) id pair: two 32-bit multiplies + one finalizer (the tables are small and 2x over-provisioned)
 __device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) { return mix32(a * 0x9E3779B1u ^ (b * 0x85EBCA77u + 0x165667B1u)); }
+// second Bloom position of a workersToDelete key (k = 2: with 64 bits per name the false-positive rate drops from 2.3 % to 0.2 %, and a
+// false positive costs a warp two dependent L2 round trips in the name table)
+__device__ __forceinline__ uint32_t bloom2(uint32_t hk) { return (hk * 0x9E3779B1u) >> 9; }
 #define KR_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define KR_EMPTY32 0xFFFFFFFFu
 

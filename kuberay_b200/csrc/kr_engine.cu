@@ -104,7 +104,7 @@ OutLayout out_layout(const kr_sizes &n, uint32_t create_cap) {
 struct ScratchLayout {
   // 0xFF-initialised region first
   size_t cl_slots_off, wt_keys, wt_head, aux_keys, aux_vals, ff_total;
-  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, inc_zero, stamp, dirty_flag, obj_flag, inc, inc_zero_end, touched, dirty_list, act_res, cre_res, total;
+  size_t cl_rec, wt_next, rows, keys0, keys1, vals0, vals1, hist, row_total, gacc, gcreate, deferred_list, cact, ccount, chain, wt_bits, cl_dyn, cstart, tile_orph, mh_rep, mh_name, mh_meta, mh_cnt, mh_flg, mh_act, mh_head, act_tmp_idx, act_tmp_code, cl_in, bucket, inc_zero, stamp, dirty_flag, obj_flag, inc, inc_zero_end, touched, touched_old, pos, dirty_list, act_res, cre_res, total;
   uint32_t cl_slots, wt_slots, aux_slots, ntiles, mtiles;  // radix tiles (2048 keys) / k_match tiles of the fast pipeline
   uint32_t wt_bits_n;      // bits of the workersToDelete Bloom bitmap
   size_t bucket_entries;   // capacity of the bucket arena of the bucket pipeline (0: that pipeline is off for this engine)
@@ -142,8 +142,9 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.chain = o;  // directly after ccount: k_clear zeroes both as one region
   o = align_up(o + 8 * (((size_t)n.n_clusters + 2) / 8192 + (size_t)L.mtiles / 8192 + (size_t)n.n_groups / 8192 + (size_t)n.n_clusters / 8192 + 10));
   {
+    static const uint64_t per_name = [] { const char *g = getenv("KR_BLOOM_BITS"); return g && atoi(g) > 0 ? (uint64_t)atoi(g) : 64ull; }();
     uint64_t bits = 1024;
-    while (bits < 64ull * n.n_wtd && bits < (1ull << 17)) bits <<= 1;  // 64 bits per name up to 16 KB (shared-memory copy per k_match2 CTA)
+    while (bits < per_name * n.n_wtd && bits < (1ull << 17)) bits <<= 1;  // 64 bits per name up to 16 KB (shared-memory copy per k_match2 CTA)
     L.wt_bits_n = (uint32_t)bits;
   }
   L.wt_bits = o; o = align_up(o + L.wt_bits_n / 8);   // zeroed with ccount and chain (one region up to cstart)
@@ -174,6 +175,8 @@ ScratchLayout scratch_layout(const kr_sizes &n) {
   L.inc = o; o = align_up(o + 64);
   L.inc_zero_end = o;
   L.touched = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.touched_old = o; o = align_up(o + 4 * (size_t)n.n_pods);
+  L.pos = o; o = align_up(o + 4 * (size_t)n.n_pods);
   L.dirty_list = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.act_res = o; o = align_up(o + 4 * (size_t)n.n_clusters);
   L.cre_res = o; o = align_up(o + 4 * (size_t)n.n_clusters);
@@ -343,6 +346,7 @@ ScratchDev bind_scratch(const ScratchLayout &L, uint8_t *b) {
   s.cl_in = reinterpret_cast<uint32_t *>(b + L.cl_in);
   s.cl_dyn = reinterpret_cast<uint4 *>(b + L.cl_dyn);
   s.stamp = reinterpret_cast<uint32_t *>(b + L.stamp); s.touched = reinterpret_cast<uint32_t *>(b + L.touched);
+  s.touched_old = reinterpret_cast<uint32_t *>(b + L.touched_old); s.pos = reinterpret_cast<uint32_t *>(b + L.pos);
   s.obj_flag = reinterpret_cast<uint32_t *>(b + L.obj_flag);
   s.dirty_flag = reinterpret_cast<uint32_t *>(b + L.dirty_flag); s.dirty_list = reinterpret_cast<uint32_t *>(b + L.dirty_list);
   s.act_res = reinterpret_cast<uint32_t *>(b + L.act_res); s.cre_res = reinterpret_cast<uint32_t *>(b + L.cre_res);

@@ -55,15 +55,16 @@ __global__ void __launch_bounds__(256) k_inc_retire(const uint32_t *rows, uint32
   const uint32_t p = rows[i];
   const uint32_t epoch = inc_epoch(sc);
   if (atomicExch(&sc.stamp[p], epoch) == epoch) return;  // committed twice since the last pass: retired already
-  sc.touched[atomicAdd(&sc.inc[KR_INC_TOUCHED], 1u)] = p;
+  const uint32_t ti = atomicAdd(&sc.inc[KR_INC_TOUCHED], 1u);
+  sc.touched[ti] = p; sc.touched_old[ti] = KR_EMPTY32;
   if (p >= n_resident) return;
   const uint32_t ns = s.p_ns_id[p], cn = s.p_cluster_name_id[p], nm = s.p_name_id[p], pk = s.p_packed[p];
   uint32_t c = 0, cflags, gname0;
-  if (cl_probe(sc, ns, cn, c, cflags, gname0)) mark_dirty(sc, c, epoch);
+  if (cl_probe(sc, ns, cn, c, cflags, gname0)) { mark_dirty(sc, c, epoch); sc.touched_old[ti] = c; }  // (k_inc_admit rewrites the record in place if the row stays)
   else if (!(pk & KR_PP_TOMBSTONE)) atomicSub(&r.totals[1], 1u);  // it was an orphan
   if (has_wtd) {  // names that resolved to this row: (namespace, name) is unique among live Pods, so nothing else holds them
     const uint32_t hk = hash_pair(ns, nm);
-    if (__ldcg(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5]) & (1u << (hk & 31))) {
+    if ((__ldcg(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5]) & (1u << (hk & 31))) && (__ldcg(&sc.wt_bits[(bloom2(hk) & sc.wt_bits_mask) >> 5]) & (1u << (bloom2(hk) & 31)))) {
       const uint64_t k = key2(ns, nm);
       uint32_t j = hk & sc.wt_mask;
       uint64_t kk = __ldcg(&sc.wt_keys[j]);
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) k_inc_admit(SnapDev s, ScratchDev sc, Res
   const uint32_t epoch = inc_epoch(sc);
   if (__ldcg(&sc.inc[KR_INC_STRUCTURAL])) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
-    const uint32_t p = sc.touched[i];
+    const uint32_t p = sc.touched[i], c_old = sc.touched_old[i];
     if (p >= n.n_pods) continue;
     const uint32_t ns = s.p_ns_id[p], cn = s.p_cluster_name_id[p], gn = s.p_group_name_id[p], nm = s.p_name_id[p], pk = s.p_packed[p];
     const uint32_t ri = (uint32_t)s.p_replica_index[p];
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) k_inc_admit(SnapDev s, ScratchDev sc, Res
     if (should_delete(pk)) flags |= KR_ROW_UNHEALTHY;
     if (has_wtd) {
       const uint32_t hk = hash_pair(ns, nm);
-      if (__ldcg(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5]) & (1u << (hk & 31))) {
+      if ((__ldcg(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5]) & (1u << (hk & 31))) && (__ldcg(&sc.wt_bits[(bloom2(hk) & sc.wt_bits_mask) >> 5]) & (1u << (bloom2(hk) & 31)))) {
         const uint64_t k = key2(ns, nm);
         uint32_t j = hk & sc.wt_mask;
         uint64_t kk = __ldcg(&sc.wt_keys[j]);
@@ -225,13 +226,21 @@ __global__ void __launch_bounds__(256) k_inc_admit(SnapDev s, ScratchDev sc, Res
         }
       }
     }
+    if (matched && c == c_old) {
+      // the usual event — a status update: the row stays in its RayCluster, its record is rewritten where it sits and the row's
+      // stamp is lifted (nothing of this cluster has to be dropped on its account)
+      sc.bucket[(size_t)c * sc.bucket_stride + sc.pos[p]] = make_uint4(p, (slot << 16) | flags, ri, nm);
+      sc.stamp[p] = 0u;
+      continue;  // (k_inc_retire marked the cluster dirty)
+    }
+    if (c_old != KR_EMPTY32) sc.cl_dyn[c_old].y = epoch;  // the old cluster lost this row: its decide warp drops the stale record (the row stays stamped)
     if (!matched) {
       if (!(pk & KR_PP_TOMBSTONE)) atomicAdd(&r.totals[1], 1u);
       continue;
     }
-    mark_dirty(sc, c, epoch);  // the decide warp drops the row's stale record, takes this one and recomputes the first head
+    mark_dirty(sc, c, epoch);  // the row joined this cluster: a fresh record at the end of its bucket
     const uint32_t rank = atomicAdd(&sc.cl_dyn[c].x, 1u);
-    if (rank < sc.bucket_stride) sc.bucket[(size_t)c * sc.bucket_stride + rank] = make_uint4(p, (slot << 16) | flags | KR_ROW_FRESH, ri, nm);
+    if (rank < sc.bucket_stride) { sc.bucket[(size_t)c * sc.bucket_stride + rank] = make_uint4(p, (slot << 16) | flags | KR_ROW_FRESH, ri, nm); sc.pos[p] = rank; }
     else sc.inc[KR_INC_VOID] = 1u;
   }
 }

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(256) k_build_tables(SnapDev s, ScratchDev sc, 
       uint32_t e = off + w;
       uint64_t k = key2(ns, s.w_name_id[e]);
       const uint32_t hk = hash_pair(ns, s.w_name_id[e]);
-      atomicOr(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5], 1u << (hk & 31));  // Bloom bit: k_match2 probes the table only for pods whose bit is set
+      atomicOr(&sc.wt_bits[(hk & sc.wt_bits_mask) >> 5], 1u << (hk & 31));  // Bloom bits: k_match2 probes the table only for pods whose two bits are set
+      { const uint32_t h2 = bloom2(hk); atomicOr(&sc.wt_bits[(h2 & sc.wt_bits_mask) >> 5], 1u << (h2 & 31)); }
       uint32_t i = hk & sc.wt_mask;
       while (true) {
         unsigned long long prev = atomicCAS((unsigned long long *)&sc.wt_keys[i], KR_EMPTY64, k);
