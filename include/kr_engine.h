@@ -447,6 +447,14 @@ int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n);
  * sector at a time. */
 int kr_snapshot_commit_pod_values(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n);
 
+/* Row-granular object commit: the caller rewrote, in the arenas, the rows of `cluster_rows` (every per-RayCluster column and the rows
+ * of those clusters' worker groups — same group count, same names, same workersToDelete lists as before) and the head-aux rows
+ * `head_rows` (same row count as before).  Only those rows travel (packed) and are applied by the on-device object diff.  It is
+ * purely an optimisation of kr_snapshot_commit_parts(KR_PART_OBJECTS) — the informer's RayCluster status / replica / expectation
+ * updates and head Pod status updates at a few hundred bytes per object instead of the whole object part: whenever the engine has
+ * no resident state, or a Recreate gate, a JSON range or the number of head rows changed, it commits the whole object part itself. */
+int kr_snapshot_commit_object_rows(kr_engine *e, const uint32_t *cluster_rows, uint32_t n_cluster_rows, const uint32_t *head_rows, uint32_t n_head_rows);
+
 /* Run the whole decision + status pass over the committed snapshot and copy the results back.
  * Replaces the decision halves of reconcilePods (raycluster_controller.go:619-935), reconcileMultiHostWorkerGroup
  * (:963-1125), shouldRecreatePodsForUpgrade (:1132-1171), shouldDeletePod (:1181-1231), calculateStatus (:1552-1719),
@@ -607,7 +615,7 @@ typedef struct kr_cluster_obj {
 } kr_cluster_obj;
 typedef struct kr_job_obj { kr_str ns, name, cluster_name, status_summary; } kr_job_obj;
 typedef struct kr_packer kr_packer;
-enum { KR_PACK_POD_ROWS = 8, KR_PACK_FULL = 16 };  /* kr_packer_flush mode bits, beside KR_PART_OBJECTS / KR_PART_JSON */
+enum { KR_PACK_POD_ROWS = 8, KR_PACK_FULL = 16, KR_PACK_OBJECT_ROWS = 32 };  /* kr_packer_flush mode bits, beside KR_PART_OBJECTS / KR_PART_JSON (OBJECT_ROWS: kr_snapshot_commit_object_rows instead of the whole object part) */
 int        kr_packer_create(const kr_config *capacities, kr_packer **out);
 void       kr_packer_destroy(kr_packer *p);
 kr_engine *kr_packer_engine(kr_packer *p);

@@ -59,6 +59,20 @@ static_assert(sizeof(kr_snapshot_bufs) == kNumCols * sizeof(void *), "kCols must
 static_assert(sizeof(SnapDev) == kNumCols * sizeof(void *), "SnapDev must mirror kr_snapshot_bufs");
 static_assert(sizeof(kr_cluster_result) == 96 && sizeof(kr_group_result) == 32 && sizeof(kr_job_result) == 8, "result record sizes");
 
+// how a changed row of each object column is treated by the on-device diff of an object commit (kr_incr.cuh, KR_OC_*)
+static const uint8_t kObjClass[kNumCols] = {
+        KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_COPY, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_COPY, KR_OC_COPY,
+        KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER,
+        KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_GROUP, KR_OC_GROUP, KR_OC_GROUP, KR_OC_STRUCT, KR_OC_GROUP, KR_OC_STRUCT, KR_OC_STRUCT,
+        KR_OC_STRUCT,
+        0, 0, 0, 0, 0, 0, 0,
+        KR_OC_HEADKEY, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD,
+        KR_OC_COPY, KR_OC_COPY, KR_OC_COPY, KR_OC_COPY,
+        0};
+constexpr int kHeadKeyCol = 39, kGroupClusterCol = 22;
+static_assert(kCols[kHeadKeyCol].dim == D_HEADS && kCols[kHeadKeyCol - 1].dim == D_PODS && kCols[kGroupClusterCol].dim == D_GROUPS && kCols[kGroupClusterCol - 1].dim == D_CLUSTERS, "column indices of the object diff");
+
+
 void dims_of(const kr_sizes &n, uint64_t d[7]) {
   d[D_CLUSTERS] = n.n_clusters; d[D_GROUPS] = n.n_groups; d[D_WTD] = n.n_wtd; d[D_PODS] = n.n_pods;
   d[D_HEADS] = n.n_heads; d[D_JOBS] = n.n_jobs; d[D_JSON] = n.json_bytes;
@@ -235,6 +249,9 @@ struct kr_engine {
   bool hash_spin = true;        // bucket pipeline: Recreate gates wait for their digest inside k_decide2 instead of a second decide phase
                                 // (KR_NO_HASH_SPIN=1, or a pass in which a warp gave up waiting, turns it off)
   uint64_t recreate_sig = 0;    // which RayClusters carry KR_CF_UPGRADE_RECREATE (their messages lead the hash order)
+  std::vector<uint8_t> recreate_bit;  // ... per cluster row, as of the last object commit (kr_snapshot_commit_object_rows checks against it)
+  uint8_t *orow_h = nullptr, *orow_d = nullptr; size_t orow_cap = 0;  // kr_snapshot_commit_object_rows staging
+  cudaEvent_t ev_orow = nullptr; bool orow_busy = false;
   uint32_t bstride = 0;         // bucket stride of this layout (64 / 128 / 256); 0 = the layout does not qualify (a cluster outgrew 256 pods, ...)
   bool snap_has_mh = false;     // some worker group has numOfHosts > 1
   uint32_t snap_max_groups = 0; // most worker groups in one RayCluster
@@ -1014,6 +1031,9 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->h_totals) cudaFreeHost(e->h_totals);
   if (e->h_order) cudaFreeHost(e->h_order);
   if (e->h_inc) cudaFreeHost(e->h_inc);
+  if (e->orow_h) cudaFreeHost(e->orow_h);
+  if (e->orow_d) cudaFree(e->orow_d);
+  if (e->ev_orow) cudaEventDestroy(e->ev_orow);
   if (e->h_changed) cudaFreeHost(e->h_changed);
   if (e->h_inc_stage) cudaFreeHost(e->h_inc_stage);
   if (e->d_inc_stage) cudaFree(e->d_inc_stage);
@@ -1187,22 +1207,11 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
         if (int rc = up(e->il.off[kFirstPodCol + k], 4 * (size_t)n.n_pods)) return rc;
   }
   if (stage_objects) {
-    static const uint8_t kObjClass[kNumCols] = {
-        KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_COPY, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_COPY, KR_OC_COPY,
-        KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER, KR_OC_CLUSTER,
-        KR_OC_STRUCT, KR_OC_STRUCT, KR_OC_GROUP, KR_OC_GROUP, KR_OC_GROUP, KR_OC_STRUCT, KR_OC_GROUP, KR_OC_STRUCT, KR_OC_STRUCT,
-        KR_OC_STRUCT,
-        0, 0, 0, 0, 0, 0, 0,
-        KR_OC_HEADKEY, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD, KR_OC_HEAD,
-        KR_OC_COPY, KR_OC_COPY, KR_OC_COPY, KR_OC_COPY,
-        0};
     uint64_t dn[7];
     dims_of(n, dn);
     ObjDiffArgs oa{};
     int nc = 0;
     uint32_t first = 0;
-    constexpr int kHeadKeyCol = 39, kGroupClusterCol = 22;
-    static_assert(kCols[kHeadKeyCol].dim == D_HEADS && kCols[kHeadKeyCol - 1].dim == D_PODS && kCols[kGroupClusterCol].dim == D_GROUPS && kCols[kGroupClusterCol - 1].dim == D_CLUSTERS, "column indices of the object diff");
     for (int i = 0; i < kNumCols - 1; i++) {
       if (kCols[i].dim == D_PODS) continue;
       oa.src[nc] = e->d_obj_stage + stage_of(e->il.off[i]);
@@ -1224,10 +1233,12 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     ScratchDev scd = bind_scratch(e->sl, e->d_scratch);
     Sizes zz{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
     if (first) k_inc_objects<<<(first + 255) / 256, 256, 0, e->scopy>>>(oa, sd, scd, zz);
-    if (n.n_heads) k_inc_objects_keys<<<(n.n_heads + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n.n_heads);
+    if (n.n_heads) k_inc_objects_keys<<<(n.n_heads + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n.n_heads, nullptr);
     CK(cudaGetLastError());
   }
   if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) {
+    e->recreate_bit.resize(n.n_clusters);
+    for (uint32_t c = 0; c < n.n_clusters; c++) e->recreate_bit[c] = (hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) ? 1 : 0;
     if (e->prev_h_pod_idx.size() != n.n_heads || (n.n_heads && memcmp(e->prev_h_pod_idx.data(), hb.h_pod_idx, 4 * (size_t)n.n_heads) != 0)) {
       e->heads_rebuild = true;
       e->prev_h_pod_idx.assign(hb.h_pod_idx, hb.h_pod_idx + n.n_heads);
@@ -1316,6 +1327,105 @@ static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *
   CK(cudaEventRecord(e->ev_cols, e->scopy));  // ev_json keeps pointing at the last JSON upload: the hash need not wait for the patch
   e->h2d_timed = false;
   e->prof.h2d_bytes = (e->h2d_accum += 32 * (size_t)n);  // row list + the 28-byte row payload (pulled one 32-byte sector per value in the rows-only variant)
+  e->committed = true;
+  return KR_OK;
+}
+
+
+int kr_snapshot_commit_object_rows(kr_engine *e, const uint32_t *cluster_rows, uint32_t n_cl, const uint32_t *head_rows, uint32_t n_hd) {
+  if (!e || (!cluster_rows && n_cl) || (!head_rows && n_hd)) return KR_E_INVALID;
+  if (!e->begun) return fail(e, KR_E_STATE, "kr_snapshot_commit_object_rows before kr_snapshot_begin");
+  if (n_cl == 0 && n_hd == 0) return KR_OK;
+  const kr_sizes &n = e->sizes;
+  kr_snapshot_bufs hb;
+  bind_in(e->il, e->h_in, &hb);
+  // Only an optimisation of kr_snapshot_commit_parts(KR_PART_OBJECTS): whenever the resident state cannot take the rows as they
+  // are — no resident state, a Recreate gate or a JSON range that changed (hash order / digests), head rows added or removed —
+  // the whole object part is committed instead.
+  bool whole = !e->inc_valid || e->no_incr || !e->committed_full || e->res_n_heads != n.n_heads || e->recreate_bit.size() != n.n_clusters ||
+               e->prev_json_off.size() != n.n_clusters;
+  for (uint32_t i = 0; i < n_cl && !whole; i++) {
+    const uint32_t c = cluster_rows[i];
+    if (c >= n.n_clusters) return fail(e, KR_E_INVALID, "cluster row %u out of range", c);
+    whole = e->recreate_bit[c] != ((hb.c_flags[c] & KR_CF_UPGRADE_RECREATE) ? 1 : 0) || e->prev_json_off[c] != hb.c_json_off[c] || e->prev_json_len[c] != hb.c_json_len[c] ||
+            (uint64_t)hb.c_group_off[c] + hb.c_group_cnt[c] > n.n_groups;
+  }
+  for (uint32_t i = 0; i < n_hd && !whole; i++) {
+    if (head_rows[i] >= n.n_heads) return fail(e, KR_E_INVALID, "head-aux row %u out of range", head_rows[i]);
+    if (hb.h_pod_idx[head_rows[i]] >= n.n_pods) return fail(e, KR_E_INVALID, "head-aux row %u: h_pod_idx %u >= n_pods %u", head_rows[i], hb.h_pod_idx[head_rows[i]], n.n_pods);
+  }
+  if (whole) return kr_snapshot_commit_parts(e, KR_PART_OBJECTS);
+  CK(cudaSetDevice(e->cfg.device));
+  // group rows of the named clusters
+  std::vector<uint32_t> grows;
+  for (uint32_t i = 0; i < n_cl; i++) for (uint32_t g = 0; g < hb.c_group_cnt[cluster_rows[i]]; g++) grows.push_back(hb.c_group_off[cluster_rows[i]] + g);
+  const uint32_t cnt[7] = {n_cl, (uint32_t)grows.size(), 0, 0, n_hd, 0, 0};
+  const uint32_t *lists[7] = {cluster_rows, grows.data(), nullptr, nullptr, head_rows, nullptr, nullptr};
+  // staging: the three row lists, then every object column's rows packed in list order
+  size_t need = 0, list_off[7] = {0};
+  for (int d = 0; d < 7; d++) { list_off[d] = need; need = align_up(need + 4 * (size_t)cnt[d]); }
+  size_t col_off[kNumCols] = {0};
+  for (int i = 0; i < kNumCols - 1; i++) {
+    const int d = kCols[i].dim;
+    if (d == D_PODS || !cnt[d]) continue;
+    col_off[i] = need; need = align_up(need + (size_t)kCols[i].elem * kCols[i].mult * cnt[d]);
+  }
+  if (e->orow_busy) { CK(cudaEventSynchronize(e->ev_orow)); e->orow_busy = false; }
+  if (need > e->orow_cap) {
+    if (e->orow_h) cudaFreeHost(e->orow_h);
+    if (e->orow_d) cudaFree(e->orow_d);
+    e->orow_h = nullptr; e->orow_d = nullptr; e->orow_cap = 0;
+    const size_t cap = need + need / 2 + 65536;
+    CK(cudaHostAlloc((void **)&e->orow_h, cap, cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&e->orow_d, cap));
+    e->orow_cap = cap;
+  }
+  if (!e->ev_orow) CK(cudaEventCreateWithFlags(&e->ev_orow, cudaEventDisableTiming));
+  for (int d = 0; d < 7; d++) if (cnt[d]) memcpy(e->orow_h + list_off[d], lists[d], 4 * (size_t)cnt[d]);
+  ObjDiffArgs oa{};
+  int nc = 0;
+  uint32_t first = 0;
+  for (int i = 0; i < kNumCols - 1; i++) {
+    const int d = kCols[i].dim;
+    if (d == D_PODS || !cnt[d]) continue;
+    const size_t rb = (size_t)kCols[i].elem * kCols[i].mult;
+    const uint8_t *col = e->h_in + e->il.off[i];
+    uint8_t *dst = e->orow_h + col_off[i];
+    for (uint32_t k = 0; k < cnt[d]; k++) memcpy(dst + k * rb, col + (size_t)lists[d][k] * rb, rb);
+    oa.src[nc] = e->orow_d + col_off[i];
+    oa.rowlist[nc] = reinterpret_cast<const uint32_t *>(e->orow_d + list_off[d]);
+    oa.dst[nc] = e->d_in + e->il.off[i];
+    oa.first[nc] = first;
+    oa.rows_old[nc] = d == D_HEADS ? e->res_n_heads : (d == D_CLUSTERS ? n.n_clusters : n.n_groups);
+    oa.row_bytes[nc] = (uint16_t)rb;
+    oa.cls[nc] = kObjClass[i];
+    if (i == kGroupClusterCol) oa.g_cluster_idx_new = reinterpret_cast<const uint32_t *>(e->orow_d + col_off[i]);
+    if (i == kHeadKeyCol) oa.h_pod_idx_new = reinterpret_cast<const uint32_t *>(e->orow_d + col_off[i]);
+    first += cnt[d];
+    nc++;
+  }
+  oa.first[nc] = first; oa.n_cols = nc;
+  oa.h_pod_idx_old = reinterpret_cast<const uint32_t *>(e->d_in + e->il.off[kHeadKeyCol]);
+  oa.n_heads_old = e->res_n_heads;
+  // the pod -> head-aux row table follows the keys (compared here, on the host shadow)
+  for (uint32_t i = 0; i < n_hd; i++)
+    if (e->prev_h_pod_idx[head_rows[i]] != hb.h_pod_idx[head_rows[i]]) { e->heads_rebuild = true; e->prev_h_pod_idx[head_rows[i]] = hb.h_pod_idx[head_rows[i]]; }
+  CK(cudaStreamSynchronize(e->sm));  // a pass still reading the tables must finish first
+  CK(cudaEventRecord(e->ev_h2d0, e->scopy));
+  CK(cudaMemcpyAsync(e->orow_d, e->orow_h, need, cudaMemcpyHostToDevice, e->scopy));
+  CK(cudaEventRecord(e->ev_orow, e->scopy));
+  e->orow_busy = true;
+  SnapDev sd;
+  bind_in(e->il, e->d_in, &sd);
+  ScratchDev scd = bind_scratch(e->sl, e->d_scratch);
+  Sizes zz{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
+  if (first) k_inc_objects<<<(first + 255) / 256, 256, 0, e->scopy>>>(oa, sd, scd, zz);
+  if (n_hd) k_inc_objects_keys<<<(n_hd + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n_hd, reinterpret_cast<const uint32_t *>(e->orow_d + list_off[D_HEADS]));
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev_h2d1, e->scopy));
+  CK(cudaEventRecord(e->ev_cols, e->scopy));
+  e->h2d_timed = false;
+  e->prof.h2d_bytes = (e->h2d_accum += need);
   e->committed = true;
   return KR_OK;
 }

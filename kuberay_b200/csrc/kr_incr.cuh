@@ -86,6 +86,8 @@ enum { KR_OC_COPY = 0, KR_OC_STRUCT = 1, KR_OC_CLUSTER = 2, KR_OC_GROUP = 3, KR_
 static constexpr int kMaxObjCols = 48;
 struct ObjDiffArgs {
   const uint8_t *src[kMaxObjCols];   // staged (new) column
+  const uint32_t *rowlist[kMaxObjCols];  // NULL: staged row k is resident row k (a whole-table upload); else staged row k is resident row rowlist[k]
+                                         // (kr_snapshot_commit_object_rows: only the rewritten rows travel, packed)
   uint8_t *dst[kMaxObjCols];         // resident column
   uint32_t first[kMaxObjCols + 1];   // flat index of the column's first row (prefix sums of the new row counts)
   uint32_t rows_old[kMaxObjCols];    // rows the resident column held
@@ -110,8 +112,9 @@ __global__ void __launch_bounds__(256) k_inc_objects(ObjDiffArgs a, SnapDev s, S
   int lo = 0, hi = a.n_cols - 1;
   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.first[mid] <= t) lo = mid; else hi = mid - 1; }
   const int col = lo;
-  const uint32_t row = t - a.first[col], rb = a.row_bytes[col];
-  const uint8_t *src = a.src[col] + (size_t)row * rb;
+  const uint32_t k_st = t - a.first[col], rb = a.row_bytes[col];
+  const uint32_t row = a.rowlist[col] ? a.rowlist[col][k_st] : k_st;
+  const uint8_t *src = a.src[col] + (size_t)k_st * rb;
   uint8_t *dst = a.dst[col] + (size_t)row * rb;
   bool differ = row >= a.rows_old[col];
   if (!differ) {
@@ -123,10 +126,10 @@ __global__ void __launch_bounds__(256) k_inc_objects(ObjDiffArgs a, SnapDev s, S
   switch (a.cls[col]) {
     case KR_OC_STRUCT: sc.inc[KR_INC_STRUCTURAL] = 1u; break;
     case KR_OC_CLUSTER: if (row < n.n_clusters) { sc.obj_flag[row] = epoch; mark_dirty(sc, row, epoch); } break;
-    case KR_OC_GROUP: { const uint32_t c = a.g_cluster_idx_new[row]; if (c < n.n_clusters) { sc.obj_flag[c] = epoch; mark_dirty(sc, c, epoch); } break; }
+    case KR_OC_GROUP: { const uint32_t c = a.g_cluster_idx_new[k_st]; if (c < n.n_clusters) { sc.obj_flag[c] = epoch; mark_dirty(sc, c, epoch); } break; }
     case KR_OC_HEADKEY:  // (the host compared the keys as well and rebuilds the pod -> row table); both pods' clusters see a different head-aux row now
     case KR_OC_HEAD:
-      mark_pod_cluster_dirty(s, sc, n, a.h_pod_idx_new[row], epoch);
+      mark_pod_cluster_dirty(s, sc, n, a.h_pod_idx_new[k_st], epoch);
       if (row < a.n_heads_old) mark_pod_cluster_dirty(s, sc, n, a.h_pod_idx_old[row], epoch);
       break;
     default: break;
@@ -137,9 +140,9 @@ __global__ void __launch_bounds__(256) k_inc_objects(ObjDiffArgs a, SnapDev s, S
 }
 
 // second step of the object diff: h_pod_idx into place (every head row of k_inc_objects read the old keys first)
-__global__ void __launch_bounds__(256) k_inc_objects_keys(const uint32_t *src, uint32_t *dst, uint32_t n) {
+__global__ void __launch_bounds__(256) k_inc_objects_keys(const uint32_t *src, uint32_t *dst, uint32_t n, const uint32_t *rowlist) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) dst[t] = src[t];
+  if (t < n) dst[rowlist ? rowlist[t] : t] = src[t];
 }
 
 // ------------------------------------------------------------------------------------------------ head-aux table rebuild

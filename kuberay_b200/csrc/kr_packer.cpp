@@ -97,6 +97,10 @@ struct kr_packer {
   std::vector<uint32_t> row_slot;     // pod row -> its journal entry (valid while row_dirty)
   uint32_t n_heads_live = 0;          // head-aux rows in use (sizes.n_heads follows at flush)
   kr_sizes engine_sizes{};            // the live counts the engine was last told (kr_snapshot_begin)
+  // object rows rewritten in place since the last flush (kr_snapshot_commit_object_rows when no table changed shape)
+  std::vector<uint32_t> dirty_cl, dirty_hd;
+  std::vector<uint8_t> cl_flag, hd_flag;
+  bool wtd_changed = false;           // a workersToDelete name was rewritten in place (same count): the whole object part travels
 
   uint32_t intern(const kr_str &s) {
     if (!s.p) return KR_ID_ABSENT;
@@ -137,6 +141,8 @@ void write_pod_row(kr_packer *p, uint32_t row, uint32_t ns, uint32_t cl, uint32_
 // the last row.  An update rewrites one row in place — nothing is rebuilt at flush, and the engine's on-device diff of the object
 // tables sees exactly the rows that changed.
 void write_head_row(kr_packer *p, uint32_t h, uint32_t pod_row, const HeadRec &r) {
+  if (h >= p->hd_flag.size()) p->hd_flag.resize((size_t)h + 256, 0);
+  if (!p->hd_flag[h]) { p->hd_flag[h] = 1; p->dirty_hd.push_back(h); }
   p->b.h_pod_idx[h] = pod_row; p->b.h_ready_status[h] = r.ready_status; p->b.h_ready_reason_id[h] = r.ready_reason_id; p->b.h_ready_msg_id[h] = r.ready_msg_id;
   p->b.h_pod_ip_id[h] = r.pod_ip_id; p->b.h_annot_state[h] = r.annot_state; p->b.h_version_state[h] = r.version_state;
   memcpy(p->b.h_annot_hash + 32 * (size_t)h, r.hash, 32);
@@ -320,6 +326,8 @@ int kr_packer_cluster_upsert(kr_packer *p, const kr_cluster_obj *o) {
   b.c_summary_id[row] = p->intern(o->status_summary);
   c.resource_version = o->resource_version;
   p->objects_dirty = true;
+  if (row >= p->cl_flag.size()) p->cl_flag.resize((size_t)row + 256, 0);
+  if (!p->cl_flag[row]) { p->cl_flag[row] = 1; p->dirty_cl.push_back(row); }
   // worker groups (replicas / expectations / workersToDelete move every few seconds under the autoscaler)
   bool shape = c.groups.size() != o->n_groups;
   c.groups.resize(o->n_groups);
@@ -338,7 +346,9 @@ int kr_packer_cluster_upsert(kr_packer *p, const kr_cluster_obj *o) {
       const GroupRec &r = c.groups[gi];
       const uint32_t g = g0 + gi;
       b.g_name_id[g] = r.name_id; b.g_replicas[g] = r.replicas; b.g_min[g] = r.mn; b.g_max[g] = r.mx; b.g_num_hosts[g] = r.hosts; b.g_flags[g] = r.flags;
-      for (size_t k = 0; k < r.wtd.size(); k++) b.w_name_id[b.g_wtd_off[g] + k] = r.wtd[k];
+      for (size_t k = 0; k < r.wtd.size(); k++) {
+        if (b.w_name_id[b.g_wtd_off[g] + k] != r.wtd[k]) { b.w_name_id[b.g_wtd_off[g] + k] = r.wtd[k]; p->wtd_changed = true; }
+      }
     }
   }
   // muted-spec JSON: re-emitted only when metadata.generation moved
@@ -421,6 +431,8 @@ int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
   const double t0 = trace ? now() : 0;
   double t1 = 0, t2 = 0, t3 = 0;
   if (p->json_dead * 2 > p->json_cursor && p->json_dead > (1u << 20)) { if (int rc = compact_json(p)) return rc; p->json_dirty = true; }
+  // Row-granular object commit when nothing changed shape: only the rewritten RayCluster / group / head-aux rows travel.
+  bool rows_ok = p->objects_dirty && !p->first && !p->tables_dirty && !p->jobs_dirty && !p->wtd_changed && p->n_heads_live == p->engine_sizes.n_heads;
   if (p->tables_dirty) { if (int rc = rebuild_tables(p)) return rc; p->objects_dirty = true; }
   if (p->heads_dirty) { p->sizes.n_heads = p->n_heads_live; p->objects_dirty = true; }  // (rows were written in place by the handlers)
   if (p->jobs_dirty) { rebuild_jobs(p); p->objects_dirty = true; }
@@ -429,6 +441,7 @@ int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
   want.n_clusters = (uint32_t)p->clusters.size(); want.n_pods = (uint32_t)p->row_key.size(); want.json_bytes = p->json_cursor;
   kr_snapshot_bufs same;
   p->sizes = want;
+  if (want.n_clusters != p->engine_sizes.n_clusters || want.n_groups != p->engine_sizes.n_groups || want.n_wtd != p->engine_sizes.n_wtd || want.n_jobs != p->engine_sizes.n_jobs) rows_ok = false;
   if (memcmp(&want, &p->engine_sizes, sizeof want) != 0 || p->first) {
     if (int rc = kr_snapshot_begin(p->e, &p->sizes, &same)) return rc;  // fixed layout: new live counts, same addresses, resident data kept
     p->engine_sizes = want;
@@ -439,8 +452,12 @@ int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
     mode = KR_PACK_FULL;
   } else {
     if (trace) t2 = now();
-    uint32_t parts = (p->objects_dirty ? KR_PART_OBJECTS : 0u) | (p->json_dirty ? KR_PART_JSON : 0u);
+    uint32_t parts = ((p->objects_dirty && !rows_ok) ? KR_PART_OBJECTS : 0u) | (p->json_dirty ? KR_PART_JSON : 0u);
     if (parts) { if (int rc = kr_snapshot_commit_parts(p->e, parts)) return rc; mode |= parts; }
+    if (rows_ok) {
+      if (int rc = kr_snapshot_commit_object_rows(p->e, p->dirty_cl.data(), (uint32_t)p->dirty_cl.size(), p->dirty_hd.data(), (uint32_t)p->dirty_hd.size())) return rc;
+      mode |= KR_PACK_OBJECT_ROWS;
+    }
     if (trace) t3 = now();
     if (!p->dirty_rows.empty()) {  // the epoch's journal, as the handlers wrote it
       if (int rc = kr_snapshot_commit_pod_values(p->e, p->dirty_rows.data(), p->stage_vals.data(), (uint32_t)p->dirty_rows.size())) return rc;
@@ -450,6 +467,9 @@ int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
   if (trace) fprintf(stderr, "kr_packer_flush: rebuilds %.0f us, begin %.0f us, commit_parts %.0f us, pod rows (%zu) %.0f us\n", t1 - t0, t2 - t1, t3 - t2, p->dirty_rows.size(), now() - t3);
   for (uint32_t r : p->dirty_rows) p->row_dirty[r] = 0;
   p->dirty_rows.clear(); p->stage_vals.clear();
+  for (uint32_t r : p->dirty_cl) p->cl_flag[r] = 0;
+  for (uint32_t r : p->dirty_hd) if (r < p->hd_flag.size()) p->hd_flag[r] = 0;
+  p->dirty_cl.clear(); p->dirty_hd.clear(); p->wtd_changed = false;
   p->first = p->objects_dirty = p->tables_dirty = p->heads_dirty = p->jobs_dirty = p->json_dirty = false;
   p->epoch++;
   p->last_mode = mode;

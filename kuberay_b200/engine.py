@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         L.kr_snapshot_commit_parts.argtypes = [C.c_void_p, C.c_uint32]
         L.kr_snapshot_commit_pod_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.kr_snapshot_commit_pod_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.kr_snapshot_commit_object_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.kr_engine_set_option.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         L.kr_reconcile_batch.argtypes = [C.c_void_p, P(abi.kr_flags), P(abi.kr_results_view)]
         L.kr_reconcile_device_only.argtypes = [C.c_void_p, P(abi.kr_flags)]
@@ -264,6 +265,12 @@ class Engine:
         values = np.ascontiguousarray(values, dtype=np.uint32).reshape(-1, 7)
         assert values.shape[0] == rows.size
         self._check(self._L.kr_snapshot_commit_pod_values(self._h, rows.ctypes.data, values.ctypes.data, rows.size))
+
+    def commit_object_rows(self, cluster_rows=(), head_rows=()):
+        """kr_snapshot_commit_object_rows: only the rewritten RayCluster (+ their groups') and head-aux rows travel."""
+        cr = np.ascontiguousarray(cluster_rows, dtype=np.uint32)
+        hr = np.ascontiguousarray(head_rows, dtype=np.uint32)
+        self._check(self._L.kr_snapshot_commit_object_rows(self._h, cr.ctypes.data if cr.size else None, cr.size, hr.ctypes.data if hr.size else None, hr.size))
 
     def load(self, snap: Snapshot):
         views = self.begin(snap.sizes())

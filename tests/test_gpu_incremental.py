@@ -248,3 +248,47 @@ def test_appended_rows_and_head_rows_come_and_go(oracle_mod):
         assert heads.size
     finally:
         dr.close()
+
+
+def test_object_row_commits_equal_whole_object_commits(oracle_mod):
+    """kr_snapshot_commit_object_rows: only the rewritten RayCluster (+ their groups') and head-aux rows travel.  Same results as the
+    whole object part, incremental on the device; rows whose Recreate bit changes fall back to the whole part by themselves."""
+    rng = np.random.default_rng(8)
+    snap, flags = synthetic.generate(synthetic.config("C2", n_clusters=400, pods_per_cluster=12, groups=2, recreate_frac=0.1, seed=44))
+    dr = Driver(snap, flags)
+    try:
+        dr.check(oracle_mod, expect_incremental=False)
+        nc, nh = snap.dims["clusters"], snap.dims["heads"]
+        for epoch in range(6):
+            cs = rng.choice(nc, 9, replace=False)
+            for c in cs[:5]:
+                g = int(snap.cols["c_group_off"][c]) + int(rng.integers(0, max(1, int(snap.cols["c_group_cnt"][c]))))
+                if snap.cols["c_group_cnt"][c]:
+                    snap.cols["g_replicas"][g] = int(rng.integers(0, 30))
+                    snap.cols["g_flags"][g] ^= np.uint32(abi.GF_EXPECT_OK)
+            snap.cols["c_flags"][cs[5:7]] ^= np.uint32(1 << 5)            # KR_CF_HEAD_EXPECT_OK
+            snap.cols["c_old_counts"][5 * int(cs[7])] = int(rng.integers(0, 9))
+            snap.cols["c_svc_count"][cs[8]] = np.uint8(int(rng.integers(0, 3)))
+            hs = rng.choice(nh, 4, replace=False)
+            snap.cols["h_ready_status"][hs] = np.uint8(int(rng.integers(0, 4)))
+            snap.cols["h_pod_ip_id"][hs[:2]] = snap.cols["h_pod_ip_id"][hs[2:]]
+            if epoch == 4:                                                  # a Recreate gate flips: the engine takes the whole object part itself
+                snap.cols["c_flags"][cs[0]] ^= np.uint32(1 << 3)
+            for c in OBJ_COLS:
+                np.copyto(dr.views[c], snap.cols[c])
+            dr.eng.commit_object_rows(cs, hs)
+            rows = rng.choice(snap.dims["pods"], 15, replace=False).astype(np.uint32)
+            _flip_ready(snap, rows)
+            dr.commit_rows(rows)
+            got, inc = dr.check(oracle_mod, expect_incremental=True)
+            assert got.n_changed <= 9 + 4 + 15 + 1
+            if epoch != 4:
+                assert dr.eng.last_profile()["h2d_bytes"] < 40000, dr.eng.last_profile()   # a few KB, not the 100+ KB object part
+        # rows out of range are refused
+        from kuberay_b200.engine import EngineError
+        with pytest.raises(EngineError):
+            dr.eng.commit_object_rows([nc], [])
+        with pytest.raises(EngineError):
+            dr.eng.commit_object_rows([], [nh])
+    finally:
+        dr.close()
