@@ -430,7 +430,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
     CK(cudaEventRecord(e->ev_fork, M)); CK(cudaStreamWaitEvent(H, e->ev_fork, 0));
     CK(cudaStreamWaitEvent(H, e->ev_json, wflag));
     if (do_hash && spin && n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, H));  // the digests' last words are "ready" marks (k_decide2)
-    if (do_hash) launch_hash();
+    if (do_hash) { launch_hash(); k++; }  // (counted among the pass's kernels: kr_profile.n_kernels)
     else if (n.n_clusters) CK(cudaMemsetAsync(r.hash, 0, 32 * (size_t)n.n_clusters, H));
     CK(cudaEventRecord(e->ev_hash, H));
     return KR_OK;
