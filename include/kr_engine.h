@@ -337,7 +337,8 @@ typedef struct kr_group_result {        /* 32 bytes */
   int32_t  n_unhealthy;          /* :794 */
   int32_t  n_running;            /* len(runningPods.Items) (:837-842); multi-host: valid replica groups (:1055) */
   int32_t  diff;                 /* :849; multi-host: replicasToCreate (:1064) */
-  uint32_t n_create;             /* pods to create */
+  uint32_t n_create;             /* entries of create_idx this group owns: pods to create; for a KR_GR_MULTIHOST group REPLICA GROUPS to create
+                                    (each one is NumOfHosts pods with one generated replica name, raycluster_controller.go:1081-1094) */
   uint32_t create_off;           /* first replica index of this group in create_idx[] (one entry per pod; multi-host: per replica) */
   uint32_t flags;                /* KR_GR_* */
 } kr_group_result;
@@ -370,7 +371,7 @@ typedef struct kr_results_view {
   const uint32_t          *act_cnt;    /* [n_clusters] */
   const uint32_t          *act_pod_idx;/* [act_extent] */
   const uint8_t           *act_code;   /* [act_extent] KR_ACT_* */
-  uint32_t n_create_total;         /* pods to create = sum of group_results.n_create */
+  uint32_t n_create_total;         /* sum of group_results.n_create (= pods to create when no multi-host group is creating) */
   uint32_t n_orphans;
   uint32_t n_actions;              /* pods with action != KEEP (orphans excluded) = sum of act_cnt */
   uint32_t create_extent;          /* entries of create_idx in use (>= n_create_total) */
