@@ -710,6 +710,40 @@ int kr_pod_creates_expand(const kr_group_result *group_results, const kr_podmeta
                           char *name_buf, uint64_t name_cap, uint32_t *n_out);
 const char *kr_pod_meta_last_error(void);
 
+/* `ray start` command builder (second part): what DefaultHeadPodTemplate / DefaultWorkerPodTemplate and BuildPod do to a
+ * group's rayStartParams and to the Ray container's command line — once per group and reconcile, it does not depend on the create
+ * tuple.  Host-side; no GPU.  Replaces:
+ *   updateRayStartParamsResources / updateRayStartParamsLabels   (common/pod.go:1219-1276)    KR_RS_UPDATE_RESOURCES / _LABELS
+ *   setMissingRayStartParams + the head's no-monitor             (common/pod.go:935-978, 196-200)  KR_RS_SET_MISSING
+ *   generateRayStartCommand, addWellKnownAcceleratorResources, convertParamMap (common/pod.go:980-1135)  KR_RS_GENERATE
+ *   the container command / args assembly of BuildPod            (common/pod.go:617-650; utils.GetContainerCommand util.go:884-892)
+ * The env vars, probes, volumes and the autoscaler sidecar of BuildPod stay in Go. */
+enum { KR_RS_UPDATE_RESOURCES = 1, KR_RS_UPDATE_LABELS = 2, KR_RS_SET_MISSING = 4, KR_RS_GENERATE = 8 };
+typedef struct kr_raystart_in {
+  uint8_t node_type;                /* KR_NT_HEAD | KR_NT_WORKER */
+  uint8_t autoscaling_enabled;      /* utils.IsAutoscalingEnabled(&instance.Spec): the head gets no-monitor=true */
+  uint8_t overwrite_container_cmd;  /* podTemplate annotation ray.io/overwrite-container-cmd == "true" (common/pod.go:631-634) */
+  uint8_t login_shell;              /* strings.ToLower(os.Getenv("ENABLE_LOGIN_SHELL")) == "true" */
+  uint32_t steps;                   /* KR_RS_* mask; 0 = all of them, in the reference's order */
+  kr_str head_port;                 /* GetHeadPort(instance.Spec.HeadGroupSpec.RayStartParams); absent: "6379" */
+  kr_str fqdn_ray_ip;               /* utils.GenerateFQDNServiceName(...): the worker's default address is <fqdn>:<head port> */
+  const kr_kv *ray_start_params;    uint32_t n_ray_start_params;   /* the group's rayStartParams */
+  const kr_kv *group_labels;        uint32_t n_group_labels;       /* the group's top-level `labels` */
+  const kr_kv *group_resources;     uint32_t n_group_resources;    /* the group's top-level `resources` (name -> quantity text) */
+  const kr_kv *container_limits;    uint32_t n_container_limits;   /* Ray container resources.limits (name -> quantity text) */
+  const kr_kv *container_requests;  uint32_t n_container_requests; /* Ray container resources.requests */
+  const kr_str *command;            uint32_t n_command;            /* Ray container command / args from the template */
+  const kr_str *args;               uint32_t n_args;
+} kr_raystart_in;
+/* Writes one JSON object (Go map / string encoding):
+ *   {"rayStartParams":{...final params, keys sorted...},"rayStartCommand":"ray start ...","generated":true|false,"command":[...],"args":[...]}
+ * generated == false: the container keeps the template's command / args (overwrite annotation, or they already contain "ray start").
+ * *need = bytes required; KR_E_CAPACITY when cap is too small. */
+int kr_ray_start_command(const kr_raystart_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+/* resource.Quantity as the builder reads it: Value() (rounded up), AsApproximateFloat64(), IsZero(); KR_E_INVALID: not a quantity. */
+int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, uint8_t *is_zero_out);
+const char *kr_ray_start_last_error(void);
+
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);
 

@@ -215,6 +215,18 @@ class kr_podmeta_group(C.Structure):
                 ("template_annotations", C.POINTER(kr_kv))]
 
 
+class kr_raystart_in(C.Structure):
+    _fields_ = [("node_type", C.c_uint8), ("autoscaling_enabled", C.c_uint8), ("overwrite_container_cmd", C.c_uint8), ("login_shell", C.c_uint8),
+                ("steps", C.c_uint32), ("head_port", kr_str), ("fqdn_ray_ip", kr_str),
+                ("ray_start_params", C.POINTER(kr_kv)), ("n_ray_start_params", C.c_uint32), ("group_labels", C.POINTER(kr_kv)), ("n_group_labels", C.c_uint32),
+                ("group_resources", C.POINTER(kr_kv)), ("n_group_resources", C.c_uint32), ("container_limits", C.POINTER(kr_kv)), ("n_container_limits", C.c_uint32),
+                ("container_requests", C.POINTER(kr_kv)), ("n_container_requests", C.c_uint32),
+                ("command", C.POINTER(kr_str)), ("n_command", C.c_uint32), ("args", C.POINTER(kr_str)), ("n_args", C.c_uint32)]
+
+
+RS_UPDATE_RESOURCES, RS_UPDATE_LABELS, RS_SET_MISSING, RS_GENERATE = 1, 2, 4, 8
+
+
 class kr_podmeta_create(C.Structure):
     _fields_ = [("group", C.c_int32), ("replica_index", C.c_int32), ("host_index", C.c_int32), ("replica_name", kr_str)]
 
@@ -250,6 +262,7 @@ ENGINE_SYMBOLS = [
     "kr_packer_intern", "kr_packer_string", "kr_packer_cluster_row", "kr_packer_pod_row", "kr_packer_pod_key", "kr_packer_epoch",
     "kr_packer_cluster_epoch", "kr_packer_last_error",
     "kr_pod_name", "kr_check_name", "kr_check_label", "kr_pod_meta_build", "kr_pod_creates_expand", "kr_pod_meta_last_error",
+    "kr_ray_start_command", "kr_quantity_value", "kr_ray_start_last_error",
 ]
 
 

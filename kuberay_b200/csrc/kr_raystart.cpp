@@ -1,0 +1,361 @@
+// `ray start` command builder (second part) — host side of the C ABI, no GPU.
+//
+// What DefaultHeadPodTemplate / DefaultWorkerPodTemplate and BuildPod do to a group's rayStartParams and to the Ray container's
+// command line, per worker group (it does not depend on the create tuple: the shim calls it once per group and reconcile).
+// Restated from (never copied), paths relative to ray-operator/controllers/ray/:
+//   GetHeadPort                           common/pod.go:54-59
+//   updateRayStartParamsResources         common/pod.go:1238-1276
+//   updateRayStartParamsLabels            common/pod.go:1219-1235
+//   setMissingRayStartParams              common/pod.go:935-978
+//   head: no-monitor with the autoscaler  common/pod.go:196-200
+//   generateRayStartCommand               common/pod.go:980-1020
+//   addWellKnownAcceleratorResources      common/pod.go:1022-1097
+//   convertParamMap                       common/pod.go:1108-1135
+//   the container command / args          common/pod.go:617-650 (BuildPod), utils/util.go:884-892 (GetContainerCommand)
+//   utils.IsGPUResourceKey                utils/resources.go:8-17
+//   resource.Quantity (ParseQuantity, Value, IsZero, AsApproximateFloat64): k8s.io/apimachinery v0.36.0 pkg/api/resource —
+//     third-party, absent from /root/reference; restated from its published behaviour: <sign><digits>[.<digits>][<suffix>] with
+//     suffixes n u m "" k M G T P E (powers of 1000), Ki Mi Gi Ti Pi Ei (powers of 1024) or a decimal exponent e<N> / E<N>;
+//     Value() rounds up to the next integer.
+//   encoding/json float64 formatting (the resources map): shortest representation, 'f' form for 1e-6 <= |x| < 1e21, else 'e' form
+//     with a two-digit exponent reduced to one when it has a leading zero.
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/kr_engine.h"
+
+void kr_go_string_append(std::string &out, const std::string &s);  // kr_specjson.cpp
+
+namespace {
+
+thread_local std::string g_err;
+typedef std::map<std::string, std::string> StrMap;
+
+inline std::string str(kr_str s) { return (s.p && s.n) ? std::string(s.p, s.n) : std::string(); }
+std::string lower(std::string s) { for (char &c : s) if (c >= 'A' && c <= 'Z') c = (char)(c + 32); return s; }
+
+// ---- resource.Quantity: value = mant * 10^e10 * 2^e2 (mant >= 0, sign apart) ------------------------------------------------
+struct Quantity { bool ok = false, neg = false; unsigned __int128 mant = 0; int e10 = 0, e2 = 0; };
+
+Quantity parse_quantity(const std::string &in) {
+  Quantity q;
+  size_t i = 0, n = in.size();
+  if (n == 0) return q;
+  if (in[i] == '+' || in[i] == '-') { q.neg = in[i] == '-'; i++; }
+  int digits = 0, frac = 0;
+  bool dot = false;
+  for (; i < n; i++) {
+    const char c = in[i];
+    if (c >= '0' && c <= '9') {
+      if (q.mant > ((unsigned __int128)1 << 120)) return q;  // far beyond anything a resource field carries
+      q.mant = q.mant * 10 + (unsigned)(c - '0'); digits++;
+      if (dot) frac++;
+    } else if (c == '.' && !dot) dot = true;
+    else break;
+  }
+  if (digits == 0) return q;
+  q.e10 = -frac;
+  const std::string suf = in.substr(i);
+  if (suf.empty()) { q.ok = true; return q; }
+  if (suf == "Ki" || suf == "Mi" || suf == "Gi" || suf == "Ti" || suf == "Pi" || suf == "Ei") {
+    q.e2 = 10 * (int)(std::string("KMGTPE").find(suf[0]) + 1); q.ok = true; return q;
+  }
+  if (suf.size() == 1) {
+    static const char *dec = "numkMGTPE";
+    static const int exp10[] = {-9, -6, -3, 3, 6, 9, 12, 15, 18};
+    const char *p = strchr(dec, suf[0]);
+    if (p && *p) { q.e10 += exp10[p - dec]; q.ok = true; return q; }
+  }
+  if (suf[0] == 'e' || suf[0] == 'E') {
+    size_t k = 1;
+    bool eneg = false;
+    if (k < suf.size() && (suf[k] == '+' || suf[k] == '-')) { eneg = suf[k] == '-'; k++; }
+    if (k >= suf.size()) return q;
+    int ex = 0;
+    for (; k < suf.size(); k++) { if (suf[k] < '0' || suf[k] > '9' || ex > 1000) return q; ex = ex * 10 + (suf[k] - '0'); }
+    q.e10 += eneg ? -ex : ex; q.ok = true; return q;
+  }
+  return q;
+}
+bool q_is_zero(const Quantity &q) { return q.mant == 0; }
+// Value(): the quantity rounded up to an integer, as int64 (saturating)
+long long q_value(const Quantity &q) {
+  unsigned __int128 m = q.mant;
+  bool rem = false;
+  int e10 = q.e10;
+  for (int k = 0; k < q.e2; k++) { if (m > ((unsigned __int128)1 << 125)) return q.neg ? INT64_MIN : INT64_MAX; m <<= 1; }
+  while (e10 > 0) { if (m > ((unsigned __int128)1 << 120)) return q.neg ? INT64_MIN : INT64_MAX; m *= 10; e10--; }
+  while (e10 < 0) { if (m % 10) rem = true; m /= 10; e10++; }
+  if (rem && !q.neg) m += 1;  // round up (towards +inf; a negative value truncates towards zero, which is up)
+  if (m > (unsigned __int128)INT64_MAX) return q.neg ? INT64_MIN : INT64_MAX;
+  return q.neg ? -(long long)m : (long long)m;
+}
+double q_float(const Quantity &q) {
+  double v = (double)q.mant;
+  v *= std::pow(10.0, q.e10);
+  v = std::ldexp(v, q.e2);
+  return q.neg ? -v : v;
+}
+
+// encoding/json's float64 encoder
+std::string go_float(double f) {
+  if (f == 0) return std::signbit(f) ? "-0" : "0";
+  char buf[64];
+  const double a = std::fabs(f);
+  if (a >= 1e-6 && a < 1e21) {
+    auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+  }
+  auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);
+  std::string s(buf, r.ptr);  // d.ddde-07 -> d.ddde-7 (Go cleans a two-digit exponent with a leading zero)
+  const size_t n = s.size();
+  if (n >= 4 && s[n - 4] == 'e' && (s[n - 3] == '-' || s[n - 3] == '+') && s[n - 2] == '0') { s[n - 2] = s[n - 1]; s.pop_back(); }
+  return s;
+}
+
+// json.Unmarshal into map[string]float64: an object whose values are all numbers (null leaves the key out); anything else fails
+bool parse_float_map(const std::string &text, std::map<std::string, double> &out) {
+  size_t i = 0, n = text.size();
+  auto ws = [&] { while (i < n && (text[i] == ' ' || text[i] == '\t' || text[i] == '\n' || text[i] == '\r')) i++; };
+  ws();
+  if (text.compare(i, 4, "null") == 0) { i += 4; ws(); return i == n; }
+  if (i >= n || text[i] != '{') return false;
+  i++; ws();
+  if (i < n && text[i] == '}') { i++; ws(); return i == n; }
+  while (true) {
+    ws();
+    if (i >= n || text[i] != '"') return false;
+    i++;
+    std::string key;
+    while (i < n && text[i] != '"') {
+      if (text[i] == '\\') {
+        if (i + 1 >= n) return false;
+        const char e = text[i + 1];
+        if (e == 'u') return false;  // (resource names are plain ASCII; an escaped key takes the "invalid" path like a syntax error would)
+        key += (e == 'n' ? '\n' : e == 't' ? '\t' : e == 'r' ? '\r' : e == 'b' ? '\b' : e == 'f' ? '\f' : e);
+        i += 2;
+      } else key += text[i++];
+    }
+    if (i >= n) return false;
+    i++; ws();
+    if (i >= n || text[i] != ':') return false;
+    i++; ws();
+    if (text.compare(i, 4, "null") == 0) { i += 4; }
+    else {
+      const size_t s0 = i;
+      if (i < n && text[i] == '-') i++;
+      if (i >= n || text[i] < '0' || text[i] > '9') return false;
+      if (text[i] == '0') i++; else while (i < n && text[i] >= '0' && text[i] <= '9') i++;
+      if (i < n && text[i] == '.') { i++; if (i >= n || text[i] < '0' || text[i] > '9') return false; while (i < n && text[i] >= '0' && text[i] <= '9') i++; }
+      if (i < n && (text[i] == 'e' || text[i] == 'E')) {
+        i++;
+        if (i < n && (text[i] == '+' || text[i] == '-')) i++;
+        if (i >= n || text[i] < '0' || text[i] > '9') return false;
+        while (i < n && text[i] >= '0' && text[i] <= '9') i++;
+      }
+      double v = 0;
+      auto r = std::from_chars(text.data() + s0, text.data() + i, v);
+      if (r.ec != std::errc()) return false;
+      out[key] = v;
+    }
+    ws();
+    if (i < n && text[i] == ',') { i++; continue; }
+    if (i < n && text[i] == '}') { i++; ws(); return i == n; }
+    return false;
+  }
+}
+
+std::string marshal_float_map(const std::map<std::string, double> &m) {  // json.Marshal(map[string]float64): keys sorted
+  std::string out = "{";
+  bool first = true;
+  for (const auto &e : m) {
+    if (!first) out += ',';
+    first = false;
+    kr_go_string_append(out, e.first);
+    out += ':';
+    out += go_float(e.second);
+  }
+  return out + "}";
+}
+
+bool is_gpu_key(const std::string &k) {  // utils/resources.go:8-17
+  if (k.size() >= 3 && k.compare(k.size() - 3, 3, "gpu") == 0) return true;
+  // nvidia\.com/mig-\d+g\.\d+gb$ (unanchored at the front)
+  static const std::string pre = "nvidia.com/mig-";
+  for (size_t s0 = k.find(pre); s0 != std::string::npos; s0 = k.find(pre, s0 + 1)) {
+    size_t i = s0 + pre.size(), d = 0;
+    while (i < k.size() && k[i] >= '0' && k[i] <= '9') { i++; d++; }
+    if (!d || i + 1 >= k.size() || k[i] != 'g' || k[i + 1] != '.') continue;
+    i += 2; d = 0;
+    while (i < k.size() && k[i] >= '0' && k[i] <= '9') { i++; d++; }
+    if (d && k.compare(i, std::string::npos, "gb") == 0) return true;
+  }
+  return false;
+}
+
+const char *custom_accelerator(const std::string &k) {  // common/pod.go:40-49
+  if (k == "aws.amazon.com/neuroncore") return "neuron_cores";
+  if (k == "google.com/tpu") return "TPU";
+  return nullptr;
+}
+
+std::string trim_set(const std::string &s, const char *set) {  // strings.Trim
+  size_t a = 0, b = s.size();
+  while (a < b && strchr(set, s[a])) a++;
+  while (b > a && strchr(set, s[b - 1])) b--;
+  return s.substr(a, b - a);
+}
+
+void put_all(StrMap &m, const kr_kv *kv, uint32_t n) { for (uint32_t i = 0; i < n; i++) m[str(kv[i].key)] = str(kv[i].value); }
+
+// common/pod.go:1238-1276.  The reference ranges over a Go map; two names that normalise to the same key ("CPU" and "cpu") would
+// make its result depend on iteration order — here: byte order of the names, the later one wins.
+void update_resources(StrMap &p, const StrMap &group_resources) {
+  if (group_resources.empty()) return;
+  std::map<std::string, double> custom;
+  for (const auto &e : group_resources) {
+    const Quantity q = parse_quantity(e.second);
+    if (!q.ok) continue;
+    const std::string nm = lower(e.first);
+    if (nm == "cpu") p["num-cpus"] = std::to_string(q_value(q));
+    else if (nm == "memory") p["memory"] = std::to_string(q_value(q));
+    else if (is_gpu_key(nm)) p["num-gpus"] = std::to_string(q_value(q));
+    else custom[e.first] = q_float(q);
+  }
+  if (!custom.empty()) p["resources"] = "'" + marshal_float_map(custom) + "'";
+}
+
+void update_labels(StrMap &p, const StrMap &group_labels) {  // common/pod.go:1219-1235
+  if (group_labels.empty()) return;
+  std::string joined;
+  for (const auto &e : group_labels) { if (!joined.empty()) joined += ','; joined += e.first + "=" + e.second; }
+  p["labels"] = joined;
+}
+
+void add_accelerators(StrMap &p, const StrMap &limits) {  // common/pod.go:1022-1069
+  if (limits.empty()) return;
+  std::map<std::string, double> res;
+  auto it = p.find("resources");
+  if (it != p.end() && !parse_float_map(trim_set(it->second, "'\"` "), res)) return;  // the error is logged and nothing is added
+  bool have_custom = res.count("neuron_cores") || res.count("TPU");
+  for (const auto &e : limits) {  // sorted resource keys
+    const Quantity q = parse_quantity(e.second);
+    const bool zero = !q.ok || q_is_zero(q);
+    if (!p.count("num-gpus") && is_gpu_key(e.first) && !zero) p["num-gpus"] = std::to_string(q_value(q));
+    if (!have_custom) {
+      const char *ray_name = custom_accelerator(e.first);
+      if (ray_name && !zero) {
+        if (!res.count(ray_name)) { res[ray_name] = q_float(q); p["resources"] = "'" + marshal_float_map(res) + "'"; }
+        have_custom = true;
+      }
+    }
+  }
+}
+
+std::string convert_param_map(const StrMap &p) {  // common/pod.go:1108-1135
+  std::string out;
+  for (const auto &e : p) {
+    const std::string lv = lower(e.second);
+    const bool boolean = (lv == "true" || lv == "false") && e.first != "log-color" && e.first != "include-dashboard";
+    if (boolean) { if (lv == "true") out += " --" + e.first + " "; }
+    else out += " --" + e.first + "=" + e.second + " ";
+  }
+  return out;
+}
+
+void json_str_array(std::string &out, const std::vector<std::string> &v) {
+  out += '[';
+  for (size_t i = 0; i < v.size(); i++) { if (i) out += ','; kr_go_string_append(out, v[i]); }
+  out += ']';
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *kr_ray_start_last_error(void) { return g_err.c_str(); }
+
+int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, uint8_t *is_zero_out) {
+  const Quantity q = parse_quantity(str(text));
+  if (!q.ok) { g_err = "kr_quantity_value: not a quantity"; return KR_E_INVALID; }
+  if (value_out) *value_out = q_value(q);
+  if (approx_out) *approx_out = q_float(q);
+  if (is_zero_out) *is_zero_out = q_is_zero(q) ? 1 : 0;
+  return KR_OK;
+}
+
+int kr_ray_start_command(const kr_raystart_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
+  if (!in || !need) { g_err = "kr_ray_start_command: null argument"; return KR_E_INVALID; }
+  if (in->node_type != KR_NT_HEAD && in->node_type != KR_NT_WORKER) { g_err = "kr_ray_start_command: node_type must be KR_NT_HEAD or KR_NT_WORKER"; return KR_E_INVALID; }
+  const bool head = in->node_type == KR_NT_HEAD;
+  StrMap p, labels, resources, limits, requests;
+  put_all(p, in->ray_start_params, in->n_ray_start_params);
+  put_all(labels, in->group_labels, in->n_group_labels);
+  put_all(resources, in->group_resources, in->n_group_resources);
+  put_all(limits, in->container_limits, in->n_container_limits);
+  put_all(requests, in->container_requests, in->n_container_requests);
+  // head port as the workers dial it: GetHeadPort(instance.Spec.HeadGroupSpec.RayStartParams) (raycluster_controller.go:1393,1422)
+  const std::string head_port = (in->head_port.p && in->head_port.n) ? str(in->head_port) : std::string("6379");
+
+  const uint32_t steps = in->steps ? in->steps : 0xFFFFFFFFu;  // (single steps: the reference's unit tests call them one by one)
+  // DefaultHeadPodTemplate / DefaultWorkerPodTemplate (common/pod.go:179-190, 420-440)
+  if (steps & KR_RS_UPDATE_RESOURCES) update_resources(p, resources);
+  if (steps & KR_RS_UPDATE_LABELS) update_labels(p, labels);
+  if (steps & KR_RS_SET_MISSING) {  // setMissingRayStartParams (common/pod.go:935-978)
+    if (!head && !p.count("address")) p["address"] = str(in->fqdn_ray_ip) + ":" + head_port;
+    if (head && !p.count("dashboard-host")) p["dashboard-host"] = "0.0.0.0";
+    if (!p.count("metrics-export-port")) p["metrics-export-port"] = "8080";
+    p["block"] = "true";
+    if (!p.count("dashboard-agent-listen-port")) p["dashboard-agent-listen-port"] = "52365";
+    if (head && in->autoscaling_enabled) p["no-monitor"] = "true";  // common/pod.go:196-200
+  }
+
+  // generateRayStartCommand (common/pod.go:980-1020)
+  auto quantity_of = [](const StrMap &m, const char *k, Quantity &q) { auto it = m.find(k); if (it == m.end()) return false; q = parse_quantity(it->second); return q.ok && !q_is_zero(q); };
+  Quantity q;
+  if (steps & KR_RS_GENERATE) {
+    if (!p.count("num-cpus")) {
+      if (quantity_of(limits, "cpu", q) || quantity_of(requests, "cpu", q)) p["num-cpus"] = std::to_string(q_value(q));
+    }
+    if (!p.count("memory") && quantity_of(limits, "memory", q)) p["memory"] = std::to_string(q_value(q));
+    add_accelerators(p, limits);
+  }
+  const std::string ray_start = std::string(head ? "ray start --head " : "ray start ") + convert_param_map(p);
+
+  // the Ray container's command line (common/pod.go:617-650)
+  std::vector<std::string> command, args;
+  std::string cmd;
+  for (uint32_t i = 0; i < in->n_command; i++) { command.push_back(str(in->command[i])); cmd += " " + command.back() + " "; }
+  for (uint32_t i = 0; i < in->n_args; i++) { args.push_back(str(in->args[i])); cmd += " " + args.back() + " "; }
+  const bool generated = !in->overwrite_container_cmd && cmd.find("ray start") == std::string::npos;
+  if (generated) {
+    command = {"/bin/bash", std::string("-c") + (in->login_shell ? "l" : ""), "--"};  // utils.GetContainerCommand
+    const std::string gen = "ulimit -n 65536; " + ray_start;
+    args = {cmd.empty() ? gen : cmd + " && " + gen};
+  }
+
+  std::string js = "{\"rayStartParams\":{";
+  bool first = true;
+  for (const auto &e : p) { if (!first) js += ','; first = false; kr_go_string_append(js, e.first); js += ':'; kr_go_string_append(js, e.second); }
+  js += "},\"rayStartCommand\":";
+  kr_go_string_append(js, ray_start);
+  js += ",\"generated\":";
+  js += generated ? "true" : "false";
+  js += ",\"command\":";
+  json_str_array(js, command);
+  js += ",\"args\":";
+  json_str_array(js, args);
+  js += '}';
+  *need = js.size();
+  if (js.size() > cap || (!out && !js.empty())) { g_err = "kr_ray_start_command: output buffer too small"; return KR_E_CAPACITY; }
+  memcpy(out, js.data(), js.size());
+  return KR_OK;
+}
+
+}  // extern "C"
