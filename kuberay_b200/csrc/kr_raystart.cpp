@@ -23,6 +23,8 @@
 #include <charconv>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -96,27 +98,55 @@ long long q_value(const Quantity &q) {
   if (m > (unsigned __int128)INT64_MAX) return q.neg ? INT64_MIN : INT64_MAX;
   return q.neg ? -(long long)m : (long long)m;
 }
+// math.Pow10 as Go computes it (tables of literals: exact up to 1e22, correctly rounded beyond; negative powers by one division)
+double go_pow10(int n) {
+  static const double tab[32] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20,
+                                 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31};
+  static const double pos32[10] = {1e0, 1e32, 1e64, 1e96, 1e128, 1e160, 1e192, 1e224, 1e256, 1e288};
+  static const double neg32[11] = {1e-0, 1e-32, 1e-64, 1e-96, 1e-128, 1e-160, 1e-192, 1e-224, 1e-256, 1e-288, 1e-320};
+  if (n >= 0 && n <= 308) return pos32[n / 32] * tab[n % 32];
+  if (n >= -323 && n < 0) return neg32[(-n) / 32] / tab[(-n) % 32];
+  return n > 0 ? INFINITY : 0.0;
+}
+// AsApproximateFloat64(): float64(unscaled) * math.Pow10(-scale), after ParseQuantity rounded anything finer than nano up to nano
 double q_float(const Quantity &q) {
-  double v = (double)q.mant;
-  v *= std::pow(10.0, q.e10);
-  v = std::ldexp(v, q.e2);
+  unsigned __int128 m = q.mant;
+  int e10 = q.e10;
+  for (int k = 0; k < q.e2; k++) { if (m > ((unsigned __int128)1 << 125)) return q.neg ? -INFINITY : INFINITY; m <<= 1; }
+  if (e10 < -9 && m != 0) {
+    bool rem = false;
+    while (e10 < -9) { if (m % 10) rem = true; m /= 10; e10++; }
+    if (rem) m += 1;
+  }
+  const double base = (double)m;
+  const double v = e10 == 0 ? base : base * go_pow10(e10);
   return q.neg ? -v : v;
 }
 
 // encoding/json's float64 encoder
 std::string go_float(double f) {
   if (f == 0) return std::signbit(f) ? "-0" : "0";
+  // shortest round-trip digits and decimal exponent (strconv's 'e' / -1), then encoding/json's layout
   char buf[64];
-  const double a = std::fabs(f);
-  if (a >= 1e-6 && a < 1e21) {
-    auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::fixed);
-    return std::string(buf, r.ptr);
-  }
   auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);
-  std::string s(buf, r.ptr);  // d.ddde-07 -> d.ddde-7 (Go cleans a two-digit exponent with a leading zero)
-  const size_t n = s.size();
-  if (n >= 4 && s[n - 4] == 'e' && (s[n - 3] == '-' || s[n - 3] == '+') && s[n - 2] == '0') { s[n - 2] = s[n - 1]; s.pop_back(); }
-  return s;
+  std::string sci(buf, r.ptr), digits;
+  const size_t epos = sci.find('e');
+  for (size_t i = 0; i < epos; i++) if (sci[i] >= '0' && sci[i] <= '9') digits += sci[i];
+  const int e10 = atoi(sci.c_str() + epos + 1);
+  const std::string sign = f < 0 ? "-" : "";
+  const double a = std::fabs(f);
+  const int nd = (int)digits.size();
+  if (a >= 1e-6 && a < 1e21) {  // 'f' form: the digits, padded with zeros up to the decimal point
+    if (e10 >= nd - 1) return sign + digits + std::string((size_t)(e10 - nd + 1), '0');
+    if (e10 >= 0) return sign + digits.substr(0, (size_t)e10 + 1) + "." + digits.substr((size_t)e10 + 1);
+    return sign + "0." + std::string((size_t)(-e10 - 1), '0') + digits;
+  }
+  std::string out = sign + digits.substr(0, 1) + (nd > 1 ? "." + digits.substr(1) : "");
+  char eb[16];
+  snprintf(eb, sizeof eb, "e%c%02d", e10 < 0 ? '-' : '+', e10 < 0 ? -e10 : e10);
+  std::string es(eb);  // e-07 -> e-7 (Go cleans a two-digit exponent with a leading zero)
+  if (es.size() == 4 && es[2] == '0') es = es.substr(0, 2) + es.substr(3);
+  return out + es;
 }
 
 // json.Unmarshal into map[string]float64: an object whose values are all numbers (null leaves the key out); anything else fails
@@ -137,10 +167,35 @@ bool parse_float_map(const std::string &text, std::map<std::string, double> &out
       if (text[i] == '\\') {
         if (i + 1 >= n) return false;
         const char e = text[i + 1];
-        if (e == 'u') return false;  // (resource names are plain ASCII; an escaped key takes the "invalid" path like a syntax error would)
+        if (e == 'u') {  // \uXXXX (json.Marshal writes <, >, & of a resource name this way), surrogate pairs included
+          auto hex4 = [&](size_t at, uint32_t &v) {
+            if (at + 4 > n) return false;
+            v = 0;
+            for (size_t k = 0; k < 4; k++) {
+              const char c = text[at + k];
+              const int d = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : -1;
+              if (d < 0) return false;
+              v = v * 16 + (uint32_t)d;
+            }
+            return true;
+          };
+          uint32_t cp = 0, lo = 0;
+          if (!hex4(i + 2, cp)) return false;
+          i += 6;
+          if (cp >= 0xD800 && cp < 0xDC00 && i + 1 < n && text[i] == '\\' && text[i + 1] == 'u' && hex4(i + 2, lo) && lo >= 0xDC00 && lo < 0xE000) {
+            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00); i += 6;
+          } else if (cp >= 0xD800 && cp < 0xE000) cp = 0xFFFD;  // lone surrogate
+          if (cp < 0x80) key += (char)cp;
+          else if (cp < 0x800) { key += (char)(0xC0 | (cp >> 6)); key += (char)(0x80 | (cp & 63)); }
+          else if (cp < 0x10000) { key += (char)(0xE0 | (cp >> 12)); key += (char)(0x80 | ((cp >> 6) & 63)); key += (char)(0x80 | (cp & 63)); }
+          else { key += (char)(0xF0 | (cp >> 18)); key += (char)(0x80 | ((cp >> 12) & 63)); key += (char)(0x80 | ((cp >> 6) & 63)); key += (char)(0x80 | (cp & 63)); }
+          continue;
+        }
+        if (e != '"' && e != '\\' && e != '/' && e != 'n' && e != 't' && e != 'r' && e != 'b' && e != 'f') return false;
         key += (e == 'n' ? '\n' : e == 't' ? '\t' : e == 'r' ? '\r' : e == 'b' ? '\b' : e == 'f' ? '\f' : e);
         i += 2;
-      } else key += text[i++];
+      } else if ((unsigned char)text[i] < 0x20) return false;  // raw control characters are not JSON
+      else key += text[i++];
     }
     if (i >= n) return false;
     i++; ws();

@@ -193,3 +193,61 @@ def expand_creates(group_results: np.ndarray, create_idx: np.ndarray, groups: li
         rn = t.replica_name.p[:t.replica_name.n].decode() if t.replica_name.n else ""
         res.append((t.group, t.replica_index, t.host_index, rn))
     return res
+
+
+# ------------------------------------------------------------------------------------------------ `ray start` command (kr_raystart.cpp)
+def _bind_raystart():
+    L = _lib()
+    if not getattr(L, "_kr_rs_bound", False):
+        P = C.POINTER
+        L.kr_ray_start_command.argtypes = [P(abi.kr_raystart_in), C.c_void_p, C.c_uint64, P(C.c_uint64)]
+        L.kr_quantity_value.argtypes = [abi.kr_str, P(C.c_int64), P(C.c_double), P(C.c_uint8)]
+        L.kr_quantity_value.restype = C.c_int64
+        L.kr_ray_start_last_error.restype = C.c_char_p
+        L._kr_rs_bound = True
+    return L
+
+
+def quantity_value(text: str) -> tuple[int, float, bool]:
+    """resource.Quantity as the builder reads it: (Value() rounded up, AsApproximateFloat64(), IsZero())."""
+    L = _bind_raystart()
+    b = text.encode()
+    v, f, z = C.c_int64(), C.c_double(), C.c_uint8()
+    rc = L.kr_quantity_value(abi.kr_str(b, len(b)), C.byref(v), C.byref(f), C.byref(z))
+    if rc:
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    return v.value, f.value, bool(z.value)
+
+
+def ray_start_command(node_type: str, ray_start_params: dict | None = None, *, group_labels: dict | None = None, group_resources: dict | None = None,
+                      limits: dict | None = None, requests: dict | None = None, command: list[str] | None = None, args: list[str] | None = None,
+                      head_port: str | None = None, fqdn_ray_ip: str = "", autoscaling: bool = False, overwrite_cmd: bool = False, login_shell: bool = False,
+                      steps: int = 0) -> dict:
+    """kr_ray_start_command: the group's final rayStartParams, the `ray start` line and the Ray container's command / args
+    (DefaultHeadPodTemplate / DefaultWorkerPodTemplate + BuildPod, common/pod.go:179-200, 420-440, 617-650, 935-1135)."""
+    L = _bind_raystart()
+    keep = _Keep()
+    a = abi.kr_raystart_in()
+    a.node_type = abi.NT_HEAD if node_type == "head" else abi.NT_WORKER if node_type == "worker" else abi.NT_NONE
+    a.autoscaling_enabled, a.overwrite_container_cmd, a.login_shell, a.steps = int(autoscaling), int(overwrite_cmd), int(login_shell), steps
+    a.head_port, a.fqdn_ray_ip = keep.s(head_port), keep.s(fqdn_ray_ip)
+    for field, m in (("ray_start_params", ray_start_params), ("group_labels", group_labels), ("group_resources", group_resources),
+                     ("container_limits", limits), ("container_requests", requests)):
+        arr, n = keep.kvs(m)
+        setattr(a, field, arr)
+        setattr(a, "n_" + field, n)
+    for field, lst in (("command", command), ("args", args)):
+        lst = lst or []
+        arr = (abi.kr_str * max(len(lst), 1))(*[keep.s(x) for x in lst])
+        keep.refs.append(arr)
+        setattr(a, field, arr)
+        setattr(a, "n_" + field, len(lst))
+    need = C.c_uint64()
+    rc = L.kr_ray_start_command(C.byref(a), None, 0, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = L.kr_ray_start_command(C.byref(a), buf, need.value, C.byref(need))
+    if rc:
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    return json.loads(bytes(buf)[:need.value])

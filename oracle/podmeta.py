@@ -170,3 +170,213 @@ def expand_creates(group_results, create_idx, groups: list[dict], head_create: b
             else:
                 out.append((g, idx, 0))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ `ray start` command (second part of f3)
+# Restated from common/pod.go:935-1135, 1219-1276, 617-650 and utils/resources.go:8-17; resource.Quantity and encoding/json float
+# formatting from their published behaviour (k8s.io/apimachinery v0.36.0 is not vendored under /root/reference).
+import math
+import re
+from fractions import Fraction
+
+_QTY = re.compile(r"^([+-]?)(\d+\.?\d*|\.\d+)(Ki|Mi|Gi|Ti|Pi|Ei|[numkMGTPE]|[eE][+-]?\d+)?$")
+_DEC = {"n": -9, "u": -6, "m": -3, "k": 3, "M": 6, "G": 9, "T": 12, "P": 15, "E": 18}
+
+
+def parse_quantity(text: str):
+    """-> exact Fraction, or None when the text is not a quantity."""
+    m = _QTY.match(text)
+    if not m:
+        return None
+    sign, num, suf = m.groups()
+    v = Fraction(num if not num.endswith(".") else num + "0") if not num.startswith(".") else Fraction("0" + num)
+    if suf:
+        if suf in ("Ki", "Mi", "Gi", "Ti", "Pi", "Ei"):
+            v *= 2 ** (10 * ("KMGTPE".index(suf[0]) + 1))
+        elif suf in _DEC:
+            v *= Fraction(10) ** _DEC[suf]
+        else:
+            v *= Fraction(10) ** int(suf[1:])
+    return -v if sign == "-" else v
+
+
+def quantity_value(v: Fraction) -> int:
+    return math.ceil(v)
+
+
+def go_pow10(n: int) -> float:
+    """math.Pow10: literal tables, negative powers by one division."""
+    if 0 <= n <= 308:
+        return float(f"1e{32 * (n // 32)}") * float(f"1e{n % 32}")
+    if -323 <= n < 0:
+        return float(f"1e-{32 * ((-n) // 32)}") / float(f"1e{(-n) % 32}")
+    return math.inf if n > 0 else 0.0
+
+
+def quantity_float(text: str) -> float:
+    """AsApproximateFloat64 on the parsed text: float64(unscaled) * math.Pow10(-scale); finer than nano is rounded up to nano first."""
+    m = _QTY.match(text)
+    sign, num, suf = m.groups()
+    ip, _, fp = num.partition(".")
+    mant, e10, e2 = int((ip + fp) or "0"), -len(fp), 0
+    if suf in ("Ki", "Mi", "Gi", "Ti", "Pi", "Ei"):
+        e2 = 10 * ("KMGTPE".index(suf[0]) + 1)
+    elif suf in _DEC:
+        e10 += _DEC[suf]
+    elif suf:
+        e10 += int(suf[1:])
+    mant <<= e2
+    if e10 < -9 and mant:
+        mant = -(-mant // 10 ** (-9 - e10))
+        e10 = -9
+    v = float(mant) if e10 == 0 else float(mant) * go_pow10(e10)
+    return -v if sign == "-" else v
+
+
+def go_float(f: float) -> str:
+    """encoding/json float64: shortest repr, 'f' form in [1e-6, 1e21), else 'e' form with Go's exponent clean-up."""
+    if f == 0:
+        return "-0" if math.copysign(1, f) < 0 else "0"
+    r = repr(float(f))
+    mant, _, exp = r.partition("e")
+    digits = mant.replace("-", "").replace(".", "").lstrip("0") or "0"
+    # decimal exponent of the first significant digit
+    from decimal import Decimal
+    d = Decimal(r)
+    sign = "-" if d < 0 else ""
+    t = d.as_tuple()
+    ds = "".join(map(str, t.digits)).rstrip("0") or "0"
+    e10 = len(t.digits) + t.exponent - 1  # exponent of the leading digit
+    a = abs(f)
+    if 1e-6 <= a < 1e21:
+        if e10 >= len(ds) - 1:
+            return sign + ds + "0" * (e10 - len(ds) + 1)
+        if e10 >= 0:
+            return sign + ds[:e10 + 1] + "." + ds[e10 + 1:]
+        return sign + "0." + "0" * (-e10 - 1) + ds
+    body = ds[0] + ("." + ds[1:] if len(ds) > 1 else "")
+    es = f"{abs(e10):02d}"
+    if es[0] == "0" and len(es) == 2:
+        es = es[1]
+    return f"{sign}{body}e{'-' if e10 < 0 else '+'}{es}"
+
+
+def marshal_float_map(m: dict) -> str:
+    return "{" + ",".join(f"{go_string(k)}:{go_float(v)}" for k, v in sorted(m.items(), key=lambda kv: _enc(kv[0]))) + "}"
+
+
+def is_gpu_resource_key(key: str) -> bool:
+    return key.endswith("gpu") or re.search(r"nvidia\.com/mig-\d+g\.\d+gb$", key) is not None
+
+
+CUSTOM_ACCELERATORS = {"aws.amazon.com/neuroncore": "neuron_cores", "google.com/tpu": "TPU"}
+
+
+def update_ray_start_params_resources(params: dict, group_resources: dict | None):
+    if not group_resources:
+        return
+    custom = {}
+    for name in sorted(group_resources, key=_enc):
+        q = parse_quantity(group_resources[name])
+        if q is None:
+            continue
+        nm = name.lower()
+        if nm == "cpu":
+            params["num-cpus"] = str(quantity_value(q))
+        elif nm == "memory":
+            params["memory"] = str(quantity_value(q))
+        elif is_gpu_resource_key(nm):
+            params["num-gpus"] = str(quantity_value(q))
+        else:
+            custom[name] = quantity_float(group_resources[name])
+    if custom:
+        params["resources"] = "'" + marshal_float_map(custom) + "'"
+
+
+def update_ray_start_params_labels(params: dict, group_labels: dict | None):
+    if not group_labels:
+        return
+    params["labels"] = ",".join(f"{k}={group_labels[k]}" for k in sorted(group_labels, key=_enc))
+
+
+def set_missing_ray_start_params(params: dict, node_type: str, head_port: str, fqdn_ray_ip: str):
+    if node_type == "worker" and "address" not in params:
+        params["address"] = f"{fqdn_ray_ip}:{head_port}"
+    if node_type == "head" and "dashboard-host" not in params:
+        params["dashboard-host"] = "0.0.0.0"
+    params.setdefault("metrics-export-port", "8080")
+    params["block"] = "true"
+    params.setdefault("dashboard-agent-listen-port", "52365")
+
+
+def convert_param_map(params: dict) -> str:
+    out = ""
+    for k in sorted(params, key=_enc):
+        v = params[k]
+        if v.lower() in ("true", "false") and k not in ("log-color", "include-dashboard"):
+            if v.lower() == "true":
+                out += f" --{k} "
+        else:
+            out += f" --{k}={v} "
+    return out
+
+
+def generate_ray_start_command(node_type: str, params: dict, limits: dict | None, requests: dict | None) -> str:
+    limits, requests = limits or {}, requests or {}
+
+    def nonzero(m, k):
+        q = parse_quantity(m[k]) if k in m else None
+        return q if q else None   # None for absent, unparsable or zero
+    if "num-cpus" not in params:
+        q = nonzero(limits, "cpu") or nonzero(requests, "cpu")
+        if q:
+            params["num-cpus"] = str(quantity_value(q))
+    if "memory" not in params:
+        q = nonzero(limits, "memory")
+        if q:
+            params["memory"] = str(quantity_value(q))
+    if limits:
+        res, ok = {}, True
+        if "resources" in params:
+            try:
+                res = json.loads(params["resources"].strip("'\"` "))
+                ok = res is None or (isinstance(res, dict) and all(v is None or (isinstance(v, (int, float)) and not isinstance(v, bool)) for v in res.values()))
+                res = {k: float(v) for k, v in (res or {}).items() if v is not None} if ok else {}
+            except ValueError:
+                ok = False
+        if ok:
+            have_custom = any(n in res for n in CUSTOM_ACCELERATORS.values())
+            for key in sorted(limits, key=_enc):
+                q = nonzero(limits, key)
+                if "num-gpus" not in params and is_gpu_resource_key(key) and q:
+                    params["num-gpus"] = str(quantity_value(q))
+                if not have_custom and key in CUSTOM_ACCELERATORS and q:
+                    if CUSTOM_ACCELERATORS[key] not in res:
+                        res[CUSTOM_ACCELERATORS[key]] = quantity_float(limits[key])
+                        params["resources"] = "'" + marshal_float_map(res) + "'"
+                    have_custom = True
+    if node_type == "head":
+        return "ray start --head " + convert_param_map(params)
+    if node_type == "worker":
+        return "ray start " + convert_param_map(params)
+    return ""
+
+
+def ray_start_command(node_type: str, ray_start_params: dict | None = None, *, group_labels=None, group_resources=None, limits=None, requests=None,
+                      command=None, args=None, head_port=None, fqdn_ray_ip="", autoscaling=False, overwrite_cmd=False, login_shell=False) -> dict:
+    """The composed step: DefaultHead/WorkerPodTemplate's parameter handling + BuildPod's command assembly."""
+    p = dict(ray_start_params or {})
+    update_ray_start_params_resources(p, group_resources)
+    update_ray_start_params_labels(p, group_labels)
+    set_missing_ray_start_params(p, node_type, head_port or "6379", fqdn_ray_ip)
+    if node_type == "head" and autoscaling:
+        p["no-monitor"] = "true"
+    line = generate_ray_start_command(node_type, p, limits, requests)
+    cmd = "".join(f" {v} " for v in (command or [])) + "".join(f" {v} " for v in (args or []))
+    generated = not overwrite_cmd and "ray start" not in cmd
+    out_cmd, out_args = list(command or []), list(args or [])
+    if generated:
+        out_cmd = ["/bin/bash", "-c" + ("l" if login_shell else ""), "--"]
+        gen = "ulimit -n 65536; " + line
+        out_args = [f"{cmd} && {gen}" if cmd else gen]
+    return {"rayStartParams": p, "rayStartCommand": line, "generated": generated, "command": out_cmd, "args": out_args}
