@@ -740,6 +740,19 @@ typedef struct kr_raystart_in {
  * generated == false: the container keeps the template's command / args (overwrite annotation, or they already contain "ray start").
  * *need = bytes required; KR_E_CAPACITY when cap is too small. */
 int kr_ray_start_command(const kr_raystart_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+/* The environment variables BuildPod appends to the Ray container (setContainerEnvVars, common/pod.go:815-933) or to an init container
+ * (setInitContainerEnvVars, :801-813), in its order: a JSON array of corev1.EnvVar in Go's encoding.  `existing` = the names the template's
+ * container already carries (the "already set by the user" checks read them and everything appended so far). */
+typedef struct kr_rayenv_in {
+  uint8_t node_type;        /* KR_NT_HEAD | KR_NT_WORKER (ignored for an init container) */
+  uint8_t crd_type;         /* KR_CRD_*: RayService clusters get three extra timeouts; the head's usage tag names the CRD */
+  uint8_t init_container;   /* 1: setInitContainerEnvVars (FQ_RAY_IP, RAY_IP) */
+  uint8_t reserved;
+  kr_str fqdn_ray_ip, head_port, ray_start_cmd, kuberay_version;
+  const kr_str *existing;       uint32_t n_existing;
+  const kr_kv *default_envs;    uint32_t n_default_envs;   /* the operator configuration's DefaultContainerEnvs (name -> value) */
+} kr_rayenv_in;
+int kr_ray_container_env(const kr_rayenv_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
 /* resource.Quantity as the builder reads it: Value() (rounded up), AsApproximateFloat64(), IsZero(); KR_E_INVALID: not a quantity. */
 int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, uint8_t *is_zero_out);
 const char *kr_ray_start_last_error(void);

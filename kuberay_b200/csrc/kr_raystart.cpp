@@ -345,6 +345,64 @@ int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, u
   return KR_OK;
 }
 
+// setContainerEnvVars (common/pod.go:815-933) / setInitContainerEnvVars (:801-813): the EnvVars BuildPod APPENDS to a container, in
+// its order, as a JSON array in Go's encoding ({"name":..,"value":..} — value omitted when empty — or
+// {"name":..,"valueFrom":{"fieldRef":{"fieldPath":..}}}).  "Exists" checks see the template's names and everything appended so far.
+int kr_ray_container_env(const kr_rayenv_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
+  if (!in || !need) { g_err = "kr_ray_container_env: null argument"; return KR_E_INVALID; }
+  if (!in->init_container && in->node_type != KR_NT_HEAD && in->node_type != KR_NT_WORKER) { g_err = "kr_ray_container_env: node_type must be KR_NT_HEAD or KR_NT_WORKER"; return KR_E_INVALID; }
+  std::vector<std::string> names;
+  for (uint32_t i = 0; i < in->n_existing; i++) names.push_back(str(in->existing[i]));
+  auto exists = [&](const char *n) { return std::find(names.begin(), names.end(), n) != names.end(); };
+  std::string js = "[";
+  auto sep = [&] { if (js.size() > 1) js += ','; };
+  auto add_value = [&](const std::string &name, const std::string &value) {
+    sep(); js += "{\"name\":"; kr_go_string_append(js, name);
+    if (!value.empty()) { js += ",\"value\":"; kr_go_string_append(js, value); }
+    js += '}'; names.push_back(name);
+  };
+  auto add_field = [&](const std::string &name, const std::string &path) {
+    sep(); js += "{\"name\":"; kr_go_string_append(js, name); js += ",\"valueFrom\":{\"fieldRef\":{\"fieldPath\":"; kr_go_string_append(js, path); js += "}}}";
+    names.push_back(name);
+  };
+  const std::string fqdn = str(in->fqdn_ray_ip), head_port = str(in->head_port);
+  const std::string short_ip = fqdn.substr(0, fqdn.find('.'));  // utils.ExtractRayIPFromFQDN (util.go:341-343)
+  if (in->init_container) {  // common/pod.go:801-813
+    add_value("FQ_RAY_IP", fqdn); add_value("RAY_IP", short_ip);
+  } else {
+    const bool head = in->node_type == KR_NT_HEAD;
+    for (uint32_t i = 0; i < in->n_default_envs; i++) {  // configuration defaults, unless the template already sets the name (:822-827)
+      const std::string n = str(in->default_envs[i].key);
+      if (!exists(n.c_str())) add_value(n, str(in->default_envs[i].value));
+    }
+    std::string ip = "127.0.0.1";
+    if (!head) { ip = fqdn; add_value("FQ_RAY_IP", ip); add_value("RAY_IP", short_ip); }
+    add_field("RAY_CLUSTER_NAME", "metadata.labels['ray.io/cluster']");
+    add_field("RAY_CLUSTER_NAMESPACE", "metadata.namespace");
+    add_field("RAY_CLOUD_INSTANCE_ID", "metadata.name");
+    add_field("RAY_NODE_TYPE_NAME", "metadata.labels['ray.io/group']");
+    add_value("KUBERAY_GEN_RAY_START_CMD", str(in->ray_start_cmd));
+    if (!exists("RAY_PORT")) add_value("RAY_PORT", head_port);
+    if (in->crd_type == KR_CRD_RAYSERVICE) {  // :895-909
+      if (!exists("RAY_timeout_ms_task_wait_for_death_info")) add_value("RAY_timeout_ms_task_wait_for_death_info", "0");
+      if (!exists("RAY_gcs_server_request_timeout_seconds")) add_value("RAY_gcs_server_request_timeout_seconds", "5");
+      if (!exists("RAY_SERVE_KV_TIMEOUT_S")) add_value("RAY_SERVE_KV_TIMEOUT_S", "5");
+    }
+    if (!exists("RAY_ADDRESS")) add_value("RAY_ADDRESS", ip + ":" + head_port);
+    if (!exists("RAY_USAGE_STATS_KUBERAY_IN_USE")) add_value("RAY_USAGE_STATS_KUBERAY_IN_USE", "1");
+    if (head) {
+      static const char *crd[] = {"RayCluster", "RayJob", "RayService"};
+      add_value("RAY_USAGE_STATS_EXTRA_TAGS", "kuberay_version=" + str(in->kuberay_version) + ";kuberay_crd=" + crd[in->crd_type <= KR_CRD_RAYSERVICE ? in->crd_type : 0]);
+    }
+    if (!exists("RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE")) add_value("RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE", "1");
+  }
+  js += ']';
+  *need = js.size();
+  if (js.size() > cap || (!out && !js.empty())) { g_err = "kr_ray_container_env: output buffer too small"; return KR_E_CAPACITY; }
+  memcpy(out, js.data(), js.size());
+  return KR_OK;
+}
+
 int kr_ray_start_command(const kr_raystart_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
   if (!in || !need) { g_err = "kr_ray_start_command: null argument"; return KR_E_INVALID; }
   if (in->node_type != KR_NT_HEAD && in->node_type != KR_NT_WORKER) { g_err = "kr_ray_start_command: node_type must be KR_NT_HEAD or KR_NT_WORKER"; return KR_E_INVALID; }

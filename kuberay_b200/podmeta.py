@@ -251,3 +251,31 @@ def ray_start_command(node_type: str, ray_start_params: dict | None = None, *, g
     if rc:
         raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
     return json.loads(bytes(buf)[:need.value])
+
+
+def ray_container_env(node_type: str, *, existing: list[str] | None = None, default_envs: dict | None = None, fqdn_ray_ip: str = "", head_port: str = "6379",
+                      ray_start_cmd: str = "", crd_type: str = "RayCluster", kuberay_version: str = "v1.5.0", init_container: bool = False) -> list[dict]:
+    """kr_ray_container_env: the EnvVars BuildPod appends (setContainerEnvVars / setInitContainerEnvVars, common/pod.go:801-933)."""
+    L = _bind_raystart()
+    if not getattr(L, "_kr_env_bound", False):
+        L.kr_ray_container_env.argtypes = [C.POINTER(abi.kr_rayenv_in), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L._kr_env_bound = True
+    keep = _Keep()
+    a = abi.kr_rayenv_in()
+    a.node_type = abi.NT_HEAD if node_type == "head" else abi.NT_WORKER if node_type == "worker" else abi.NT_NONE
+    a.crd_type, a.init_container = CRD_TYPES.get(crd_type, abi.CRD_RAYCLUSTER), int(init_container)
+    a.fqdn_ray_ip, a.head_port, a.ray_start_cmd, a.kuberay_version = keep.s(fqdn_ray_ip), keep.s(head_port), keep.s(ray_start_cmd), keep.s(kuberay_version)
+    ex = existing or []
+    arr = (abi.kr_str * max(len(ex), 1))(*[keep.s(x) for x in ex])
+    keep.refs.append(arr)
+    a.existing, a.n_existing = arr, len(ex)
+    a.default_envs, a.n_default_envs = keep.kvs(default_envs)
+    need = C.c_uint64()
+    rc = L.kr_ray_container_env(C.byref(a), None, 0, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = L.kr_ray_container_env(C.byref(a), buf, need.value, C.byref(need))
+    if rc:
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    return json.loads(bytes(buf)[:need.value])

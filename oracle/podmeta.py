@@ -380,3 +380,49 @@ def ray_start_command(node_type: str, ray_start_params: dict | None = None, *, g
         gen = "ulimit -n 65536; " + line
         out_args = [f"{cmd} && {gen}" if cmd else gen]
     return {"rayStartParams": p, "rayStartCommand": line, "generated": generated, "command": out_cmd, "args": out_args}
+
+
+def ray_container_env(node_type: str, *, existing=None, default_envs=None, fqdn_ray_ip="", head_port="6379", ray_start_cmd="", crd_type="RayCluster",
+                      kuberay_version="v1.5.0", init_container=False) -> list[dict]:
+    """setContainerEnvVars (common/pod.go:815-933) / setInitContainerEnvVars (:801-813): the EnvVars appended, in order."""
+    names = list(existing or [])
+    out = []
+
+    def value(n, v):
+        out.append({"name": n, **({"value": v} if v != "" else {})})
+        names.append(n)
+
+    def field(n, path):
+        out.append({"name": n, "valueFrom": {"fieldRef": {"fieldPath": path}}})
+        names.append(n)
+    short = fqdn_ray_ip.split(".")[0]
+    if init_container:
+        value("FQ_RAY_IP", fqdn_ray_ip); value("RAY_IP", short)
+        return out
+    for n, v in (default_envs or {}).items():
+        if n not in names:
+            value(n, v)
+    ip = "127.0.0.1"
+    if node_type == "worker":
+        ip = fqdn_ray_ip
+        value("FQ_RAY_IP", ip); value("RAY_IP", short)
+    field("RAY_CLUSTER_NAME", "metadata.labels['ray.io/cluster']")
+    field("RAY_CLUSTER_NAMESPACE", "metadata.namespace")
+    field("RAY_CLOUD_INSTANCE_ID", "metadata.name")
+    field("RAY_NODE_TYPE_NAME", "metadata.labels['ray.io/group']")
+    value("KUBERAY_GEN_RAY_START_CMD", ray_start_cmd)
+    if "RAY_PORT" not in names:
+        value("RAY_PORT", head_port)
+    if crd_type == "RayService":
+        for n, v in (("RAY_timeout_ms_task_wait_for_death_info", "0"), ("RAY_gcs_server_request_timeout_seconds", "5"), ("RAY_SERVE_KV_TIMEOUT_S", "5")):
+            if n not in names:
+                value(n, v)
+    if "RAY_ADDRESS" not in names:
+        value("RAY_ADDRESS", f"{ip}:{head_port}")
+    if "RAY_USAGE_STATS_KUBERAY_IN_USE" not in names:
+        value("RAY_USAGE_STATS_KUBERAY_IN_USE", "1")
+    if node_type == "head":
+        value("RAY_USAGE_STATS_EXTRA_TAGS", f"kuberay_version={kuberay_version};kuberay_crd={crd_type if crd_type in ('RayJob', 'RayService') else 'RayCluster'}")
+    if "RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE" not in names:
+        value("RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE", "1")
+    return out

@@ -198,3 +198,48 @@ def test_native_builder_matches_restatement(seed):
         got = pm.ray_start_command(node, dict(params), **args)
         want = ref.ray_start_command(node, dict(params), **args)
         assert got == want, (node, params, args)
+
+
+# ------------------------------------------------------------------------------------------------------------ container env (BuildPod)
+def _env(lst):
+    return {e["name"]: (e.get("value", "") if "valueFrom" not in e else e["valueFrom"]["fieldRef"]["fieldPath"]) for e in lst}
+
+
+def test_container_env_vectors():
+    """pod_test.go:641-728 (TestBuildPod), :988-1012 (created by RayService)."""
+    fqdn = "raycluster-sample-head-svc.default.svc.cluster.local"
+    head = pm.ray_container_env("head", existing=["TEST_ENV_NAME"], default_envs={"TEST_DEFAULT_ENV_NAME": "TEST_ENV_VALUE"}, head_port="6379",
+                                ray_start_cmd="ray start --head  --block ", kuberay_version="v9")
+    e = _env(head)
+    assert e["RAY_ADDRESS"] == "127.0.0.1:6379" and e["RAY_USAGE_STATS_KUBERAY_IN_USE"] == "1" and e["RAY_CLUSTER_NAME"] == "metadata.labels['ray.io/cluster']"
+    assert e["RAY_CLUSTER_NAMESPACE"] == "metadata.namespace" and e["RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE"] == "1" and e["RAY_NODE_TYPE_NAME"] == "metadata.labels['ray.io/group']"
+    assert e["RAY_USAGE_STATS_EXTRA_TAGS"] == "kuberay_version=v9;kuberay_crd=RayCluster" and "ray start" in e["KUBERAY_GEN_RAY_START_CMD"]
+    assert e["TEST_DEFAULT_ENV_NAME"] == "TEST_ENV_VALUE" and e["RAY_CLOUD_INSTANCE_ID"] == "metadata.name" and e["RAY_PORT"] == "6379"
+    assert "FQ_RAY_IP" not in e and "RAY_IP" not in e
+    worker = _env(pm.ray_container_env("worker", fqdn_ray_ip=fqdn, head_port="6379", ray_start_cmd="ray start  --block "))
+    assert worker["RAY_ADDRESS"] == fqdn + ":6379" and worker["FQ_RAY_IP"] == fqdn and worker["RAY_IP"] == "raycluster-sample-head-svc"
+    assert "RAY_USAGE_STATS_EXTRA_TAGS" not in worker
+    init = pm.ray_container_env("worker", fqdn_ray_ip=fqdn, init_container=True)
+    assert init == [{"name": "FQ_RAY_IP", "value": fqdn}, {"name": "RAY_IP", "value": "raycluster-sample-head-svc"}]
+    svc = _env(pm.ray_container_env("head", crd_type="RayService", existing=["RAY_SERVE_KV_TIMEOUT_S"]))
+    assert svc["RAY_timeout_ms_task_wait_for_death_info"] == "0" and svc["RAY_gcs_server_request_timeout_seconds"] == "5" and "RAY_SERVE_KV_TIMEOUT_S" not in svc
+    assert svc["RAY_USAGE_STATS_EXTRA_TAGS"].endswith("kuberay_crd=RayService")
+    # names the template already sets are left alone; a default env with such a name is skipped; a default named like a managed one counts as set
+    e = _env(pm.ray_container_env("head", existing=["RAY_ADDRESS", "RAY_PORT", "X"], default_envs={"X": "1", "RAY_USAGE_STATS_KUBERAY_IN_USE": "0"}))
+    assert "RAY_ADDRESS" not in e and "RAY_PORT" not in e and "X" not in e and e["RAY_USAGE_STATS_KUBERAY_IN_USE"] == "0"
+    # value omitted when empty (omitempty), as Go marshals it
+    raw = pm.ray_container_env("head", head_port="", ray_start_cmd="")
+    assert {"name": "RAY_PORT"} in raw and {"name": "KUBERAY_GEN_RAY_START_CMD"} in raw
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_container_env_matches_restatement(seed):
+    rng = random.Random(seed)
+    pool = ["RAY_ADDRESS", "RAY_PORT", "RAY_USAGE_STATS_KUBERAY_IN_USE", "RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE", "RAY_SERVE_KV_TIMEOUT_S", "RAY_timeout_ms_task_wait_for_death_info",
+            "FOO", "BAR", "RAY_CLUSTER_NAME", "a<b"]
+    for _ in range(200):
+        kw = dict(existing=rng.sample(pool, rng.randint(0, 4)), default_envs={rng.choice(pool): rng.choice(["", "1", "x&y"]) for _ in range(rng.randint(0, 3))} or None,
+                  fqdn_ray_ip=rng.choice(["", "svc", "svc.ns.svc.cluster.local"]), head_port=rng.choice(["", "6379"]), ray_start_cmd=rng.choice(["", "ray start --head  --block "]),
+                  crd_type=rng.choice(["RayCluster", "RayJob", "RayService"]), kuberay_version=rng.choice(["v1.5.0", "nightly"]), init_container=rng.random() < 0.15)
+        node = rng.choice(["head", "worker"])
+        assert pm.ray_container_env(node, **kw) == ref.ray_container_env(node, **kw), (node, kw)
