@@ -753,6 +753,18 @@ typedef struct kr_rayenv_in {
   const kr_kv *default_envs;    uint32_t n_default_envs;   /* the operator configuration's DefaultContainerEnvs (name -> value) */
 } kr_rayenv_in;
 int kr_ray_container_env(const kr_rayenv_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+/* The liveness / readiness probes BuildPod injects into the Ray container when the template has none (initLivenessAndReadinessProbe,
+ * common/pod.go:477-573; ENABLE_PROBES_INJECTION is the caller's business): {"livenessProbe":{...},"readinessProbe":{...}} in corev1.Probe's
+ * encoding, only the ones to inject.  Ray >= 2.53.0 (supportsUnifiedHealthCheck, :466-475) gets one HTTP check, older / unparsable versions the
+ * wget commands; a RayService worker's readiness probe always adds the Serve proxy check by exec. */
+typedef struct kr_rayprobe_in {
+  uint8_t node_type, crd_type;                       /* KR_NT_*, KR_CRD_* */
+  uint8_t has_liveness_probe, has_readiness_probe;   /* the template's Ray container already defines it: left alone */
+  int32_t serving_port;                              /* utils.FindContainerPort(rayContainer, "serve", 8000); <= 0: 8000 */
+  kr_str ray_version;                                /* spec.rayVersion */
+  const kr_kv *ray_start_params; uint32_t n_ray_start_params;  /* dashboard-agent-listen-port / dashboard-port are read from here */
+} kr_rayprobe_in;
+int kr_ray_probes(const kr_rayprobe_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
 /* resource.Quantity as the builder reads it: Value() (rounded up), AsApproximateFloat64(), IsZero(); KR_E_INVALID: not a quantity. */
 int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, uint8_t *is_zero_out);
 const char *kr_ray_start_last_error(void);

@@ -227,6 +227,11 @@ class kr_raystart_in(C.Structure):
 RS_UPDATE_RESOURCES, RS_UPDATE_LABELS, RS_SET_MISSING, RS_GENERATE = 1, 2, 4, 8
 
 
+class kr_rayprobe_in(C.Structure):
+    _fields_ = [("node_type", C.c_uint8), ("crd_type", C.c_uint8), ("has_liveness_probe", C.c_uint8), ("has_readiness_probe", C.c_uint8),
+                ("serving_port", C.c_int32), ("ray_version", kr_str), ("ray_start_params", C.POINTER(kr_kv)), ("n_ray_start_params", C.c_uint32)]
+
+
 class kr_rayenv_in(C.Structure):
     _fields_ = [("node_type", C.c_uint8), ("crd_type", C.c_uint8), ("init_container", C.c_uint8), ("reserved", C.c_uint8),
                 ("fqdn_ray_ip", kr_str), ("head_port", kr_str), ("ray_start_cmd", kr_str), ("kuberay_version", kr_str),
@@ -268,7 +273,7 @@ ENGINE_SYMBOLS = [
     "kr_packer_intern", "kr_packer_string", "kr_packer_cluster_row", "kr_packer_pod_row", "kr_packer_pod_key", "kr_packer_epoch",
     "kr_packer_cluster_epoch", "kr_packer_last_error",
     "kr_pod_name", "kr_check_name", "kr_check_label", "kr_pod_meta_build", "kr_pod_creates_expand", "kr_pod_meta_last_error",
-    "kr_ray_start_command", "kr_ray_container_env", "kr_quantity_value", "kr_ray_start_last_error",
+    "kr_ray_start_command", "kr_ray_container_env", "kr_ray_probes", "kr_quantity_value", "kr_ray_start_last_error",
 ]
 
 

@@ -403,6 +403,86 @@ int kr_ray_container_env(const kr_rayenv_in *in, uint8_t *out, uint64_t cap, uin
   return KR_OK;
 }
 
+// supportsUnifiedHealthCheck (common/pod.go:466-475): version.ParseGeneric(rayVersion).AtLeast(2.53.0) — optional "v", two or more
+// dot-separated numeric fields (the first without a leading zero), anything after them ignored (k8s.io/apimachinery pkg/util/version).
+bool ray_version_at_least(const std::string &text, const unsigned long long (&min)[3]) {
+  size_t i = 0, n = text.size();
+  while (i < n && (text[i] == ' ' || text[i] == '\t' || text[i] == '\n' || text[i] == '\r')) i++;
+  if (i < n && text[i] == 'v') i++;
+  std::vector<unsigned long long> comp;
+  while (i < n && text[i] >= '0' && text[i] <= '9') {
+    const size_t s0 = i;
+    unsigned long long v = 0;
+    while (i < n && text[i] >= '0' && text[i] <= '9') { if (v > (~0ull - 9) / 10) return false; v = v * 10 + (unsigned)(text[i] - '0'); i++; }
+    if (comp.empty() && i - s0 > 1 && text[s0] == '0') return false;  // zero-prefixed first component
+    comp.push_back(v);
+    if (i + 1 < n && text[i] == '.' && text[i + 1] >= '0' && text[i + 1] <= '9') i++; else break;
+  }
+  if (comp.size() < 2) return false;
+  for (size_t k = 0; k < 3 || k < comp.size(); k++) {
+    const unsigned long long a = k < comp.size() ? comp[k] : 0, b = k < 3 ? min[k] : 0;
+    if (a != b) return a > b;
+  }
+  return true;
+}
+
+// initLivenessAndReadinessProbe (common/pod.go:477-573): the probes KubeRay injects when the template's Ray container has none.
+int kr_ray_probes(const kr_rayprobe_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
+  if (!in || !need) { g_err = "kr_ray_probes: null argument"; return KR_E_INVALID; }
+  if (in->node_type != KR_NT_HEAD && in->node_type != KR_NT_WORKER) { g_err = "kr_ray_probes: node_type must be KR_NT_HEAD or KR_NT_WORKER"; return KR_E_INVALID; }
+  const bool head = in->node_type == KR_NT_HEAD;
+  StrMap p;
+  put_all(p, in->ray_start_params, in->n_ray_start_params);
+  auto port = [&](const char *key, long long dflt) -> long long {  // strconv.ParseInt(s, 10, 32)
+    auto it = p.find(key);
+    if (it == p.end() || it->second.empty()) return dflt;
+    const std::string &t = it->second;
+    size_t i = 0;
+    bool neg = false;
+    if (t[0] == '+' || t[0] == '-') { neg = t[0] == '-'; i = 1; }
+    if (i >= t.size()) return dflt;
+    long long v = 0;
+    for (; i < t.size(); i++) { if (t[i] < '0' || t[i] > '9') return dflt; v = v * 10 + (t[i] - '0'); if (v > 2147483648LL) return dflt; }
+    if (neg) v = -v;
+    return (v < -2147483648LL || v > 2147483647LL) ? dflt : v;
+  };
+  static const unsigned long long kMin[3] = {2, 53, 0};
+  const bool http = ray_version_at_least(str(in->ray_version), kMin);
+  const long long agent = port("dashboard-agent-listen-port", 52365), dash = port("dashboard-port", 8265);
+  auto wget = [](long long timeout, long long prt, const char *path) {
+    return "wget --tries 1 -T " + std::to_string(timeout) + " -q -O- http://localhost:" + std::to_string(prt) + "/" + path + " | grep success";
+  };
+  std::vector<std::string> commands = {wget(2, agent, "api/local_raylet_healthz")};
+  if (head) commands.push_back(wget(10, dash, "api/gcs_healthz"));  // (the second argument really is DefaultReadinessProbeFailureThreshold, :505)
+  auto join = [](const std::vector<std::string> &v) { std::string o; for (size_t i = 0; i < v.size(); i++) { if (i) o += " && "; o += v[i]; } return o; };
+  auto probe = [&](bool use_http, const std::vector<std::string> &cmds, int delay, int timeout, int period, int success, int failure) {
+    std::string js = "{";
+    if (use_http) js += "\"httpGet\":{\"path\":\"/api/healthz\",\"port\":" + std::to_string(agent) + "}";
+    else { js += "\"exec\":{\"command\":[\"bash\",\"-c\","; kr_go_string_append(js, join(cmds)); js += "]}"; }
+    js += ",\"initialDelaySeconds\":" + std::to_string(delay) + ",\"timeoutSeconds\":" + std::to_string(timeout) + ",\"periodSeconds\":" + std::to_string(period) +
+          ",\"successThreshold\":" + std::to_string(success) + ",\"failureThreshold\":" + std::to_string(failure) + "}";
+    return js;
+  };
+  std::string js = "{";
+  if (!in->has_liveness_probe) js += "\"livenessProbe\":" + probe(http, commands, 30, head ? 5 : 2, 5, 1, 120);
+  if (!in->has_readiness_probe) {
+    if (js.size() > 1) js += ',';
+    bool use_http = http;
+    int failure = 10;
+    if (in->crd_type == KR_CRD_RAYSERVICE && !head) {  // a worker that serves traffic also checks the Serve proxy, always by exec (:557-571)
+      failure = 1;
+      commands.push_back(wget(10, in->serving_port > 0 ? in->serving_port : 8000, "-/healthz"));
+      use_http = false;
+    }
+    js += "\"readinessProbe\":" + probe(use_http, commands, 10, head ? 5 : 2, 5, 1, failure);
+  }
+  js += '}';
+  *need = js.size();
+  if (js.size() > cap || (!out && !js.empty())) { g_err = "kr_ray_probes: output buffer too small"; return KR_E_CAPACITY; }
+  memcpy(out, js.data(), js.size());
+  return KR_OK;
+}
+
 int kr_ray_start_command(const kr_raystart_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
   if (!in || !need) { g_err = "kr_ray_start_command: null argument"; return KR_E_INVALID; }
   if (in->node_type != KR_NT_HEAD && in->node_type != KR_NT_WORKER) { g_err = "kr_ray_start_command: node_type must be KR_NT_HEAD or KR_NT_WORKER"; return KR_E_INVALID; }

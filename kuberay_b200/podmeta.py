@@ -279,3 +279,27 @@ def ray_container_env(node_type: str, *, existing: list[str] | None = None, defa
     if rc:
         raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
     return json.loads(bytes(buf)[:need.value])
+
+
+def ray_probes(node_type: str, ray_start_params: dict | None = None, *, crd_type: str = "RayCluster", ray_version: str = "", has_liveness: bool = False,
+               has_readiness: bool = False, serving_port: int = 0) -> dict:
+    """kr_ray_probes: the probes BuildPod injects (initLivenessAndReadinessProbe, common/pod.go:477-573)."""
+    L = _bind_raystart()
+    if not getattr(L, "_kr_probe_bound", False):
+        L.kr_ray_probes.argtypes = [C.POINTER(abi.kr_rayprobe_in), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L._kr_probe_bound = True
+    keep = _Keep()
+    a = abi.kr_rayprobe_in()
+    a.node_type = abi.NT_HEAD if node_type == "head" else abi.NT_WORKER if node_type == "worker" else abi.NT_NONE
+    a.crd_type, a.has_liveness_probe, a.has_readiness_probe, a.serving_port = CRD_TYPES.get(crd_type, abi.CRD_RAYCLUSTER), int(has_liveness), int(has_readiness), serving_port
+    a.ray_version = keep.s(ray_version)
+    a.ray_start_params, a.n_ray_start_params = keep.kvs(ray_start_params)
+    need = C.c_uint64()
+    rc = L.kr_ray_probes(C.byref(a), None, 0, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = L.kr_ray_probes(C.byref(a), buf, need.value, C.byref(need))
+    if rc:
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    return json.loads(bytes(buf)[:need.value])

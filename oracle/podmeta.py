@@ -426,3 +426,47 @@ def ray_container_env(node_type: str, *, existing=None, default_envs=None, fqdn_
     if "RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE" not in names:
         value("RAY_DASHBOARD_ENABLE_K8S_DISK_USAGE", "1")
     return out
+
+
+def ray_version_at_least(text: str, minimum=(2, 53, 0)) -> bool:
+    """supportsUnifiedHealthCheck (common/pod.go:466-475) through version.ParseGeneric / AtLeast."""
+    m = re.match(r"^\s*v?([0-9]+(?:\.[0-9]+)*)", text)
+    if not m:
+        return False
+    comp = m.group(1).split(".")
+    if len(comp) < 2 or (comp[0].startswith("0") and comp[0] != "0"):
+        return False
+    nums = [int(c) for c in comp]
+    n = max(len(nums), len(minimum))
+    return tuple(nums + [0] * (n - len(nums))) >= tuple(list(minimum) + [0] * (n - len(minimum)))
+
+
+def ray_probes(node_type: str, ray_start_params=None, *, crd_type="RayCluster", ray_version="", has_liveness=False, has_readiness=False, serving_port=0) -> dict:
+    """initLivenessAndReadinessProbe (common/pod.go:477-573)."""
+    p = ray_start_params or {}
+
+    def port(key, dflt):
+        s = p.get(key)
+        if s is None or not re.fullmatch(r"[+-]?[0-9]+", s):
+            return dflt
+        v = int(s)
+        return v if -(1 << 31) <= v < (1 << 31) else dflt
+    head = node_type == "head"
+    agent, dash = port("dashboard-agent-listen-port", 52365), port("dashboard-port", 8265)
+    http = ray_version_at_least(ray_version)
+    wget = lambda t, prt, path: f"wget --tries 1 -T {t} -q -O- http://localhost:{prt}/{path} | grep success"   # noqa: E731
+    commands = [wget(2, agent, "api/local_raylet_healthz")] + ([wget(10, dash, "api/gcs_healthz")] if head else [])
+
+    def probe(use_http, cmds, delay, timeout, period, success, failure):
+        handler = {"httpGet": {"path": "/api/healthz", "port": agent}} if use_http else {"exec": {"command": ["bash", "-c", " && ".join(cmds)]}}
+        return {**handler, "initialDelaySeconds": delay, "timeoutSeconds": timeout, "periodSeconds": period, "successThreshold": success, "failureThreshold": failure}
+    out = {}
+    if not has_liveness:
+        out["livenessProbe"] = probe(http, commands, 30, 5 if head else 2, 5, 1, 120)
+    if not has_readiness:
+        use_http, failure = http, 10
+        if crd_type == "RayService" and not head:
+            failure, use_http = 1, False
+            commands = commands + [wget(10, serving_port if serving_port > 0 else 8000, "-/healthz")]
+        out["readinessProbe"] = probe(use_http, commands, 10, 5 if head else 2, 5, 1, failure)
+    return out

@@ -243,3 +243,66 @@ def test_container_env_matches_restatement(seed):
                   crd_type=rng.choice(["RayCluster", "RayJob", "RayService"]), kuberay_version=rng.choice(["v1.5.0", "nightly"]), init_container=rng.random() < 0.15)
         node = rng.choice(["head", "worker"])
         assert pm.ray_container_env(node, **kw) == ref.ray_container_env(node, **kw), (node, kw)
+
+
+# ------------------------------------------------------------------------------------------------------------ probes (BuildPod)
+def _cmd(pr):
+    return " ".join(pr["exec"]["command"]) if "exec" in pr else ""
+
+
+def test_probe_vectors():
+    """pod_test.go:1824-1985 (TestInitLivenessAndReadinessProbe), the numbered cases."""
+    # 1: the user's own probes are left alone
+    assert pm.ray_probes("head", {}, has_liveness=True, has_readiness=True) == {}
+    # 2: RayService worker — exec probes, the Serve proxy check only in the readiness probe, 2 s timeouts
+    r = pm.ray_probes("worker", {}, crd_type="RayService")
+    assert "exec" in r["livenessProbe"] and "exec" in r["readinessProbe"] and "-/healthz" not in _cmd(r["livenessProbe"]) and "-/healthz" in _cmd(r["readinessProbe"])
+    assert r["livenessProbe"]["timeoutSeconds"] == 2 and r["readinessProbe"]["timeoutSeconds"] == 2 and r["readinessProbe"]["failureThreshold"] == 1
+    # 3: RayService head — no proxy check, 5 s timeouts
+    r = pm.ray_probes("head", {}, crd_type="RayService")
+    assert "-/healthz" not in _cmd(r["livenessProbe"]) + _cmd(r["readinessProbe"]) and r["livenessProbe"]["timeoutSeconds"] == 5 and r["readinessProbe"]["timeoutSeconds"] == 5
+    # 4: custom ports, head
+    r = pm.ray_probes("head", {"dashboard-agent-listen-port": "8266", "dashboard-port": "8365"})
+    for pr in r.values():
+        assert ":8266" in _cmd(pr) and ":8365" in _cmd(pr)
+    # 5: custom ports, worker: no dashboard-port check
+    r = pm.ray_probes("worker", {"dashboard-agent-listen-port": "9000"})
+    for pr in r.values():
+        assert ":9000" in _cmd(pr) and ":8265" not in _cmd(pr)
+    # 6: RayService worker with a custom agent port and the serve port
+    r = pm.ray_probes("worker", {"dashboard-agent-listen-port": "8500"}, crd_type="RayService", serving_port=8000)
+    assert ":8500" in _cmd(r["readinessProbe"]) and "-/healthz" in _cmd(r["readinessProbe"]) and r["readinessProbe"]["failureThreshold"] == 1
+    # 8: invalid ports fall back to the defaults
+    r = pm.ray_probes("head", {"dashboard-agent-listen-port": "invalid-port", "dashboard-port": "not-a-number"})
+    assert ":52365" in _cmd(r["livenessProbe"]) and ":8265" in _cmd(r["livenessProbe"])
+    # 9: Ray >= 2.53.0: one HTTP check; a RayService worker's readiness stays exec; 2.52.0: exec
+    r = pm.ray_probes("head", {}, ray_version="2.53.0")
+    assert r["livenessProbe"]["httpGet"] == {"path": "/api/healthz", "port": 52365} and "exec" not in r["livenessProbe"] and "httpGet" in r["readinessProbe"]
+    r = pm.ray_probes("worker", {}, ray_version="2.53.0")
+    assert "httpGet" in r["livenessProbe"] and "httpGet" in r["readinessProbe"]
+    r = pm.ray_probes("worker", {}, crd_type="RayService", ray_version="2.53.0")
+    assert "httpGet" in r["livenessProbe"] and "exec" in r["readinessProbe"] and "httpGet" not in r["readinessProbe"] and "-/healthz" in _cmd(r["readinessProbe"])
+    r = pm.ray_probes("head", {}, ray_version="2.52.0")
+    assert "exec" in r["livenessProbe"] and "exec" in r["readinessProbe"]
+    # the full head probe, literally
+    assert pm.ray_probes("head", {}, has_readiness=True) == {"livenessProbe": {"exec": {"command": ["bash", "-c",
+        "wget --tries 1 -T 2 -q -O- http://localhost:52365/api/local_raylet_healthz | grep success && wget --tries 1 -T 10 -q -O- http://localhost:8265/api/gcs_healthz | grep success"]},
+        "initialDelaySeconds": 30, "timeoutSeconds": 5, "periodSeconds": 5, "successThreshold": 1, "failureThreshold": 120}}
+
+
+@pytest.mark.parametrize("text,want", [("2.53.0", True), ("2.53", True), ("2.52.9", False), ("v2.53.1", True), ("3.0.0", True), ("2.53.0rc1", True), (" 2.100.0 ", True),
+                                       ("", False), ("nightly", False), ("2", False), ("02.53.0", False), ("2.053.0", True), ("2.53.0.1", True), ("1.99.99", False), ("2.9.0", False)])
+def test_ray_version_gate(text, want):
+    assert ref.ray_version_at_least(text) == want
+    assert ("httpGet" in pm.ray_probes("head", {}, ray_version=text)["livenessProbe"]) == want
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_probes_match_restatement(seed):
+    rng = random.Random(seed)
+    for _ in range(300):
+        params = {k: rng.choice(["8266", "abc", "", "-5", "99999999999", "+80"]) for k in rng.sample(["dashboard-agent-listen-port", "dashboard-port", "x"], rng.randint(0, 3))}
+        kw = dict(crd_type=rng.choice(["RayCluster", "RayJob", "RayService"]), ray_version=rng.choice(["", "2.52.0", "2.53.0", "v2.60", "x"]), has_liveness=rng.random() < 0.3,
+                  has_readiness=rng.random() < 0.3, serving_port=rng.choice([0, 8000, 9001]))
+        node = rng.choice(["head", "worker"])
+        assert pm.ray_probes(node, params, **kw) == ref.ray_probes(node, params, **kw), (node, params, kw)
