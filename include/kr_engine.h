@@ -765,6 +765,19 @@ typedef struct kr_rayprobe_in {
   const kr_kv *ray_start_params; uint32_t n_ray_start_params;  /* dashboard-agent-listen-port / dashboard-port are read from here */
 } kr_rayprobe_in;
 int kr_ray_probes(const kr_rayprobe_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+/* The emptyDir volumes BuildPod adds and their mounts (common/pod.go:600-615, 1137-1217): {"volumes":[..],"rayContainerVolumeMounts":[..],
+ * "autoscalerVolumeMounts":[..]} — corev1.Volume / corev1.VolumeMount objects to APPEND.  /dev/shm ("shared-mem", memory medium, sizeLimit =
+ * the Ray container's memory limit, else request, in resource.Quantity's canonical form) unless rayStartParams sets plasma-directory;
+ * /tmp/ray ("ray-logs") on the Ray and the autoscaler container when the head runs the autoscaler sidecar.  A path already mounted or a
+ * volume name already present is left alone. */
+typedef struct kr_rayvol_in {
+  uint8_t node_type, autoscaling_enabled, plasma_directory_set, reserved;
+  kr_str memory_limit, memory_request;                                  /* Ray container resources (quantity text; absent: p == NULL) */
+  const kr_str *volume_names;           uint32_t n_volume_names;          /* pod.Spec.Volumes[*].Name */
+  const kr_str *ray_mount_paths;        uint32_t n_ray_mount_paths;       /* Ray container VolumeMounts[*].MountPath */
+  const kr_str *autoscaler_mount_paths; uint32_t n_autoscaler_mount_paths;/* autoscaler container VolumeMounts[*].MountPath */
+} kr_rayvol_in;
+int kr_ray_volumes(const kr_rayvol_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
 /* resource.Quantity as the builder reads it: Value() (rounded up), AsApproximateFloat64(), IsZero(); KR_E_INVALID: not a quantity. */
 int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, uint8_t *is_zero_out);
 const char *kr_ray_start_last_error(void);

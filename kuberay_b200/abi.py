@@ -227,6 +227,12 @@ class kr_raystart_in(C.Structure):
 RS_UPDATE_RESOURCES, RS_UPDATE_LABELS, RS_SET_MISSING, RS_GENERATE = 1, 2, 4, 8
 
 
+class kr_rayvol_in(C.Structure):
+    _fields_ = [("node_type", C.c_uint8), ("autoscaling_enabled", C.c_uint8), ("plasma_directory_set", C.c_uint8), ("reserved", C.c_uint8),
+                ("memory_limit", kr_str), ("memory_request", kr_str), ("volume_names", C.POINTER(kr_str)), ("n_volume_names", C.c_uint32),
+                ("ray_mount_paths", C.POINTER(kr_str)), ("n_ray_mount_paths", C.c_uint32), ("autoscaler_mount_paths", C.POINTER(kr_str)), ("n_autoscaler_mount_paths", C.c_uint32)]
+
+
 class kr_rayprobe_in(C.Structure):
     _fields_ = [("node_type", C.c_uint8), ("crd_type", C.c_uint8), ("has_liveness_probe", C.c_uint8), ("has_readiness_probe", C.c_uint8),
                 ("serving_port", C.c_int32), ("ray_version", kr_str), ("ray_start_params", C.POINTER(kr_kv)), ("n_ray_start_params", C.c_uint32)]
@@ -273,7 +279,7 @@ ENGINE_SYMBOLS = [
     "kr_packer_intern", "kr_packer_string", "kr_packer_cluster_row", "kr_packer_pod_row", "kr_packer_pod_key", "kr_packer_epoch",
     "kr_packer_cluster_epoch", "kr_packer_last_error",
     "kr_pod_name", "kr_check_name", "kr_check_label", "kr_pod_meta_build", "kr_pod_creates_expand", "kr_pod_meta_last_error",
-    "kr_ray_start_command", "kr_ray_container_env", "kr_ray_probes", "kr_quantity_value", "kr_ray_start_last_error",
+    "kr_ray_start_command", "kr_ray_container_env", "kr_ray_probes", "kr_ray_volumes", "kr_quantity_value", "kr_ray_start_last_error",
 ]
 
 

@@ -483,6 +483,52 @@ int kr_ray_probes(const kr_rayprobe_in *in, uint8_t *out, uint64_t cap, uint64_t
   return KR_OK;
 }
 
+// The emptyDir volumes BuildPod adds (common/pod.go:600-615 through addEmptyDir :1137-1161, makeEmptyDirVolume :1163-1183,
+// findMemoryReqOrLimit :1204-1217): /dev/shm for the object store (memory medium, sized by the Ray container's memory limit, else
+// request) unless the user set plasma-directory, and the shared Ray log directory when the head runs the autoscaler sidecar.
+int kr_ray_volumes(const kr_rayvol_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
+  if (!in || !need) { g_err = "kr_ray_volumes: null argument"; return KR_E_INVALID; }
+  std::vector<std::string> vols, ray_mounts, as_mounts;
+  for (uint32_t i = 0; i < in->n_volume_names; i++) vols.push_back(str(in->volume_names[i]));
+  for (uint32_t i = 0; i < in->n_ray_mount_paths; i++) ray_mounts.push_back(str(in->ray_mount_paths[i]));
+  for (uint32_t i = 0; i < in->n_autoscaler_mount_paths; i++) as_mounts.push_back(str(in->autoscaler_mount_paths[i]));
+  std::string jv, jr, ja;
+  auto has = [](const std::vector<std::string> &v, const char *x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+  auto add = [&](std::vector<std::string> &mounts, std::string &jm, const char *name, const char *path, bool memory) -> int {
+    if (has(mounts, path)) return KR_OK;  // already mounted (checkIfVolumeMounted compares the PATH)
+    if (!has(vols, name)) {
+      if (!jv.empty()) jv += ',';
+      jv += "{\"name\":"; kr_go_string_append(jv, name); jv += ",\"emptyDir\":{";
+      if (memory) {
+        jv += "\"medium\":\"Memory\"";
+        const kr_str q = (in->memory_limit.p && in->memory_limit.n) ? in->memory_limit : in->memory_request;
+        if (q.p && q.n) {
+          char canon[128];
+          const std::string text = str(q);
+          if (kr_quantity_canonical(text.c_str(), canon, sizeof canon) != KR_OK) { g_err = "kr_ray_volumes: the memory quantity does not parse"; return KR_E_INVALID; }
+          jv += ",\"sizeLimit\":"; kr_go_string_append(jv, canon);
+        }
+      }
+      jv += "}}";
+      vols.push_back(name);
+    }
+    if (!jm.empty()) jm += ',';
+    jm += "{\"name\":"; kr_go_string_append(jm, name); jm += ",\"mountPath\":"; kr_go_string_append(jm, path); jm += '}';
+    mounts.push_back(path);
+    return KR_OK;
+  };
+  if (!in->plasma_directory_set) { if (int rc = add(ray_mounts, jr, "shared-mem", "/dev/shm", true)) return rc; }
+  if (in->node_type == KR_NT_HEAD && in->autoscaling_enabled) {
+    if (int rc = add(ray_mounts, jr, "ray-logs", "/tmp/ray", false)) return rc;
+    if (int rc = add(as_mounts, ja, "ray-logs", "/tmp/ray", false)) return rc;
+  }
+  const std::string js = "{\"volumes\":[" + jv + "],\"rayContainerVolumeMounts\":[" + jr + "],\"autoscalerVolumeMounts\":[" + ja + "]}";
+  *need = js.size();
+  if (js.size() > cap || (!out && !js.empty())) { g_err = "kr_ray_volumes: output buffer too small"; return KR_E_CAPACITY; }
+  memcpy(out, js.data(), js.size());
+  return KR_OK;
+}
+
 int kr_ray_start_command(const kr_raystart_in *in, uint8_t *out, uint64_t cap, uint64_t *need) {
   if (!in || !need) { g_err = "kr_ray_start_command: null argument"; return KR_E_INVALID; }
   if (in->node_type != KR_NT_HEAD && in->node_type != KR_NT_WORKER) { g_err = "kr_ray_start_command: node_type must be KR_NT_HEAD or KR_NT_WORKER"; return KR_E_INVALID; }

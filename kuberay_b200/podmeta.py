@@ -303,3 +303,32 @@ def ray_probes(node_type: str, ray_start_params: dict | None = None, *, crd_type
     if rc:
         raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
     return json.loads(bytes(buf)[:need.value])
+
+
+def ray_volumes(node_type: str, *, autoscaling: bool = False, plasma_directory_set: bool = False, memory_limit: str | None = None, memory_request: str | None = None,
+                volume_names: list[str] | None = None, ray_mount_paths: list[str] | None = None, autoscaler_mount_paths: list[str] | None = None) -> dict:
+    """kr_ray_volumes: the emptyDir volumes / mounts BuildPod adds (common/pod.go:600-615, 1137-1217)."""
+    L = _bind_raystart()
+    if not getattr(L, "_kr_vol_bound", False):
+        L.kr_ray_volumes.argtypes = [C.POINTER(abi.kr_rayvol_in), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L._kr_vol_bound = True
+    keep = _Keep()
+    a = abi.kr_rayvol_in()
+    a.node_type = abi.NT_HEAD if node_type == "head" else abi.NT_WORKER
+    a.autoscaling_enabled, a.plasma_directory_set = int(autoscaling), int(plasma_directory_set)
+    a.memory_limit, a.memory_request = keep.s(memory_limit), keep.s(memory_request)
+    for field, lst in (("volume_names", volume_names), ("ray_mount_paths", ray_mount_paths), ("autoscaler_mount_paths", autoscaler_mount_paths)):
+        lst = lst or []
+        arr = (abi.kr_str * max(len(lst), 1))(*[keep.s(x) for x in lst])
+        keep.refs.append(arr)
+        setattr(a, field, arr)
+        setattr(a, "n_" + field, len(lst))
+    need = C.c_uint64()
+    rc = L.kr_ray_volumes(C.byref(a), None, 0, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = L.kr_ray_volumes(C.byref(a), buf, need.value, C.byref(need))
+    if rc:
+        raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
+    return json.loads(bytes(buf)[:need.value])

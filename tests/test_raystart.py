@@ -306,3 +306,27 @@ def test_probes_match_restatement(seed):
                   has_readiness=rng.random() < 0.3, serving_port=rng.choice([0, 8000, 9001]))
         node = rng.choice(["head", "worker"])
         assert pm.ray_probes(node, params, **kw) == ref.ray_probes(node, params, **kw), (node, params, kw)
+
+
+# ------------------------------------------------------------------------------------------------------------ volumes (BuildPod)
+def test_volume_vectors():
+    """pod_test.go:222-256 (TestAddEmptyDirVolumes), :730-777 (TestBuildPod_WithPlasmaDirectory), :957-986 (autoscaler log volume)."""
+    shm = {"name": "shared-mem", "mountPath": "/dev/shm"}
+    r = pm.ray_volumes("head", memory_limit="1Gi")
+    assert r == {"volumes": [{"name": "shared-mem", "emptyDir": {"medium": "Memory", "sizeLimit": "1Gi"}}], "rayContainerVolumeMounts": [shm], "autoscalerVolumeMounts": []}
+    assert pm.ray_volumes("worker", memory_request="1500M")["volumes"][0]["emptyDir"] == {"medium": "Memory", "sizeLimit": "1500M"}   # limit absent: the request
+    assert pm.ray_volumes("worker", memory_limit="2048Mi", memory_request="1Gi")["volumes"][0]["emptyDir"]["sizeLimit"] == "2Gi"    # canonical form, limit wins
+    assert pm.ray_volumes("worker")["volumes"][0]["emptyDir"] == {"medium": "Memory"}                                               # no memory resource: no limit
+    # any plasma-directory (even /dev/shm itself) skips the shared-memory mount
+    assert pm.ray_volumes("head", plasma_directory_set=True, memory_limit="1Gi") == {"volumes": [], "rayContainerVolumeMounts": [], "autoscalerVolumeMounts": []}
+    # the path already mounted: nothing; the volume name already there: only the mount
+    assert pm.ray_volumes("worker", ray_mount_paths=["/dev/shm"], volume_names=["shared-mem"]) == {"volumes": [], "rayContainerVolumeMounts": [], "autoscalerVolumeMounts": []}
+    assert pm.ray_volumes("worker", volume_names=["shared-mem"]) == {"volumes": [], "rayContainerVolumeMounts": [shm], "autoscalerVolumeMounts": []}
+    # head with the autoscaler sidecar: one ray-logs volume, mounted in both containers
+    r = pm.ray_volumes("head", autoscaling=True, memory_limit="1Gi")
+    logs = {"name": "ray-logs", "mountPath": "/tmp/ray"}
+    assert r["volumes"] == [{"name": "shared-mem", "emptyDir": {"medium": "Memory", "sizeLimit": "1Gi"}}, {"name": "ray-logs", "emptyDir": {}}]
+    assert r["rayContainerVolumeMounts"] == [shm, logs] and r["autoscalerVolumeMounts"] == [logs]
+    assert pm.ray_volumes("worker", autoscaling=True)["autoscalerVolumeMounts"] == []
+    with pytest.raises(EngineError):
+        pm.ray_volumes("head", memory_limit="lots")
