@@ -55,6 +55,10 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
     pk[it] = v ? __ldg(&s.p_packed[p]) : 0u; ri[it] = v ? (uint32_t)__ldg(&s.p_replica_index[p]) : 0u;
   }
   pdl_wait(); pdl_trigger();
+  // (Keep this wait unconditional and in straight-line code: the table probes below use __ldg, i.e. loads the compiler treats as
+  //  invariant, and the tables are being written by the predecessor grid until the wait returns.  A persistent-CTA variant with the
+  //  wait inside `if (first tile)` had its probes hoisted above it and matched nothing; peeling the first tile fixed that but was
+  //  4 us slower in the graph than this one-tile-per-CTA form, so it was dropped.)
   // hash-join probe (namespace, ray.io/cluster) -> slot; the first probe of every pod goes out before anything waits
   uint32_t pi[kItems];
   uint4 sl[kItems];
