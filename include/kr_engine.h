@@ -717,7 +717,7 @@ const char *kr_pod_meta_last_error(void);
  *   setMissingRayStartParams + the head's no-monitor             (common/pod.go:935-978, 196-200)  KR_RS_SET_MISSING
  *   generateRayStartCommand, addWellKnownAcceleratorResources, convertParamMap (common/pod.go:980-1135)  KR_RS_GENERATE
  *   the container command / args assembly of BuildPod            (common/pod.go:617-650; utils.GetContainerCommand util.go:884-892)
- * The env vars, probes, volumes and the autoscaler sidecar of BuildPod stay in Go. */
+ * (env vars, probes, volumes, GCS-FT / token-auth additions, the autoscaler sidecar and the init container: the entry points below) */
 enum { KR_RS_UPDATE_RESOURCES = 1, KR_RS_UPDATE_LABELS = 2, KR_RS_SET_MISSING = 4, KR_RS_GENERATE = 8 };
 typedef struct kr_raystart_in {
   uint8_t node_type;                /* KR_NT_HEAD | KR_NT_WORKER */
@@ -781,6 +781,80 @@ int kr_ray_volumes(const kr_rayvol_in *in, uint8_t *out, uint64_t cap, uint64_t 
 /* resource.Quantity as the builder reads it: Value() (rounded up), AsApproximateFloat64(), IsZero(); KR_E_INVALID: not a quantity. */
 int64_t kr_quantity_value(kr_str text, int64_t *value_out, double *approx_out, uint8_t *is_zero_out);
 const char *kr_ray_start_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Pod template surgery (last part): the remaining pieces DefaultHeadPodTemplate / DefaultWorkerPodTemplate bolt onto the
+ * group's template before BuildPod — once per group and reconcile; host-side, no GPU.  Fragments of corev1 objects the caller already
+ * holds (an EnvVarSource, ResourceRequirements, a SecurityContext, env / envFrom / volumeMount lists) travel as RAW JSON text in Go's
+ * encoding (json.Marshal on the Go side) and are spliced into the output unchanged; p == NULL, "" or "null" means absent, and "[]"
+ * an empty list.  Every function writes ONE JSON document; *need = bytes required, KR_E_CAPACITY when cap is too small. */
+
+/* configureGCSFaultTolerance (common/pod.go:77-163): {"env":[...EnvVars to APPEND to the Ray container...],"rayStartParams":{...entries
+ * to SET on the head group's rayStartParams: redis-username / redis-password...}}.  The two annotations it writes are part of
+ * kr_pod_meta_build.  ft_enabled == 0 gives {"env":[],"rayStartParams":{}}. */
+typedef struct kr_rayft_in {
+  uint8_t node_type;                 /* KR_NT_HEAD | KR_NT_WORKER */
+  uint8_t ft_enabled;                /* utils.IsGCSFaultToleranceEnabled (util.go:753-756) */
+  uint8_t has_options;               /* spec.gcsFaultToleranceOptions != nil */
+  uint8_t has_redis_username, has_redis_password;   /* options.RedisUsername / RedisPassword != nil */
+  uint8_t reserved[3];
+  kr_str cluster_uid;                /* string(instance.UID): the default external storage namespace */
+  kr_str storage_ns_annotation;      /* instance.Annotations[ray.io/external-storage-namespace]; p == NULL: not set */
+  kr_str storage_ns_option;          /* options.ExternalStorageNamespace; absent or "": not set */
+  kr_str redis_address;              /* options.RedisAddress */
+  kr_str redis_username_value, redis_username_value_from;   /* RedisCredential.Value, .ValueFrom (raw EnvVarSource JSON) */
+  kr_str redis_password_value, redis_password_value_from;
+  kr_str head_redis_password_param;  /* head rayStartParams["redis-password"]; p == NULL: the key is absent (no-options path, :148-159) */
+  const kr_str *existing;  uint32_t n_existing;    /* the Ray container's env names */
+} kr_rayft_in;
+int kr_ray_ft_env(const kr_rayft_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+
+/* SetContainerTokenAuthEnvVars + AddRayTokenVolume (common/pod.go:254-335) for ONE container (the Ray container, the wait-gcs-ready init
+ * container or the autoscaler sidecar): {"env":[..],"volumeMounts":[..],"volumes":[..]} — objects to APPEND to the container's env /
+ * volumeMounts and to the pod's volumes (the projected service-account token, once per pod). */
+typedef struct kr_rayauth_in {
+  uint8_t k8s_token_auth;            /* utils.IsK8sAuthEnabled(authOptions) (util.go:763-765) */
+  uint8_t reserved[3];
+  kr_str cluster_name;               /* the default Secret is utils.CheckName(clusterName) */
+  kr_str secret_name;                /* authOptions.SecretName; absent or "": the default */
+  const kr_str *existing_env;          uint32_t n_existing_env;           /* container.Env[*].Name */
+  const kr_str *existing_mount_names;  uint32_t n_existing_mount_names;   /* container.VolumeMounts[*].Name */
+  const kr_str *existing_volume_names; uint32_t n_existing_volume_names;  /* podSpec.Volumes[*].Name */
+} kr_rayauth_in;
+int kr_ray_auth(const kr_rayauth_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+
+/* The autoscaler sidecar of the head Pod (common/pod.go:194-220: BuildAutoscalerContainer :673-724, token auth on it, then
+ * mergeAutoscalerOverrides :727-751, setAutoscalerV2EnvVars :242-251):
+ *   {"container":{...corev1.Container...},"serviceAccountName":"...","rayContainerEnv":[...],"restartPolicy":"Never"|""}
+ * rayContainerEnv / restartPolicy carry the autoscaler-v2 additions (empty / "" for v1).  With k8s token auth the sidecar mounts
+ * "ray-token"; the volume itself comes from kr_ray_auth on the Ray container (configureTokenAuth runs later, :234-236). */
+typedef struct kr_rayautoscaler_in {
+  uint8_t login_shell;               /* ENABLE_LOGIN_SHELL == "true" (utils.GetContainerCommand) */
+  uint8_t autoscaler_v2;             /* utils.IsAutoscalingV2Enabled(&instance.Spec) */
+  uint8_t auth_enabled;              /* utils.IsAuthEnabled(&instance.Spec) */
+  uint8_t k8s_token_auth;            /* utils.IsK8sAuthEnabled(authOptions) */
+  uint8_t has_options;               /* spec.autoscalerOptions != nil */
+  uint8_t reserved[3];
+  kr_str cluster_name, secret_name;  /* as kr_rayauth_in */
+  kr_str head_service_account;       /* head template spec.serviceAccountName; absent or "": the cluster's name (util.go:575-581) */
+  kr_str ray_image;                  /* the Ray head container's image: the sidecar's default */
+  kr_str image, image_pull_policy;   /* options.Image / ImagePullPolicy; p == NULL: not set (a set-but-empty string IS an override) */
+  kr_str resources_json;             /* options.Resources (raw ResourceRequirements); absent: 500m / 512Mi */
+  kr_str env_json, env_from_json, volume_mounts_json;   /* options.Env / EnvFrom / VolumeMounts (raw arrays) */
+  kr_str security_context_json;      /* options.SecurityContext (raw) */
+} kr_rayautoscaler_in;
+int kr_ray_autoscaler_container(const kr_rayautoscaler_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+
+/* The worker's wait-gcs-ready init container (common/pod.go:359-415; ENABLE_INIT_CONTAINER_INJECTION is the caller's business): one
+ * corev1.Container.  env / volumeMounts / securityContext are the Ray container's, copied. */
+typedef struct kr_rayinit_in {
+  uint8_t login_shell, reserved[3];
+  kr_str image, image_pull_policy;   /* the Ray container's */
+  kr_str fqdn_ray_ip, head_port;
+  kr_str env_json, volume_mounts_json, security_context_json;   /* the Ray container's Env / VolumeMounts / SecurityContext (raw) */
+} kr_rayinit_in;
+int kr_ray_init_container(const kr_rayinit_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
+const char *kr_ray_template_last_error(void);
 
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);

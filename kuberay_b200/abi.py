@@ -233,6 +233,31 @@ class kr_rayvol_in(C.Structure):
                 ("ray_mount_paths", C.POINTER(kr_str)), ("n_ray_mount_paths", C.c_uint32), ("autoscaler_mount_paths", C.POINTER(kr_str)), ("n_autoscaler_mount_paths", C.c_uint32)]
 
 
+class kr_rayft_in(C.Structure):
+    _fields_ = [("node_type", C.c_uint8), ("ft_enabled", C.c_uint8), ("has_options", C.c_uint8), ("has_redis_username", C.c_uint8), ("has_redis_password", C.c_uint8),
+                ("reserved", C.c_uint8 * 3), ("cluster_uid", kr_str), ("storage_ns_annotation", kr_str), ("storage_ns_option", kr_str), ("redis_address", kr_str),
+                ("redis_username_value", kr_str), ("redis_username_value_from", kr_str), ("redis_password_value", kr_str), ("redis_password_value_from", kr_str),
+                ("head_redis_password_param", kr_str), ("existing", C.POINTER(kr_str)), ("n_existing", C.c_uint32)]
+
+
+class kr_rayauth_in(C.Structure):
+    _fields_ = [("k8s_token_auth", C.c_uint8), ("reserved", C.c_uint8 * 3), ("cluster_name", kr_str), ("secret_name", kr_str),
+                ("existing_env", C.POINTER(kr_str)), ("n_existing_env", C.c_uint32), ("existing_mount_names", C.POINTER(kr_str)), ("n_existing_mount_names", C.c_uint32),
+                ("existing_volume_names", C.POINTER(kr_str)), ("n_existing_volume_names", C.c_uint32)]
+
+
+class kr_rayautoscaler_in(C.Structure):
+    _fields_ = [("login_shell", C.c_uint8), ("autoscaler_v2", C.c_uint8), ("auth_enabled", C.c_uint8), ("k8s_token_auth", C.c_uint8), ("has_options", C.c_uint8),
+                ("reserved", C.c_uint8 * 3), ("cluster_name", kr_str), ("secret_name", kr_str), ("head_service_account", kr_str), ("ray_image", kr_str),
+                ("image", kr_str), ("image_pull_policy", kr_str), ("resources_json", kr_str), ("env_json", kr_str), ("env_from_json", kr_str),
+                ("volume_mounts_json", kr_str), ("security_context_json", kr_str)]
+
+
+class kr_rayinit_in(C.Structure):
+    _fields_ = [("login_shell", C.c_uint8), ("reserved", C.c_uint8 * 3), ("image", kr_str), ("image_pull_policy", kr_str), ("fqdn_ray_ip", kr_str), ("head_port", kr_str),
+                ("env_json", kr_str), ("volume_mounts_json", kr_str), ("security_context_json", kr_str)]
+
+
 class kr_rayprobe_in(C.Structure):
     _fields_ = [("node_type", C.c_uint8), ("crd_type", C.c_uint8), ("has_liveness_probe", C.c_uint8), ("has_readiness_probe", C.c_uint8),
                 ("serving_port", C.c_int32), ("ray_version", kr_str), ("ray_start_params", C.POINTER(kr_kv)), ("n_ray_start_params", C.c_uint32)]
@@ -280,6 +305,7 @@ ENGINE_SYMBOLS = [
     "kr_packer_cluster_epoch", "kr_packer_last_error",
     "kr_pod_name", "kr_check_name", "kr_check_label", "kr_pod_meta_build", "kr_pod_creates_expand", "kr_pod_meta_last_error",
     "kr_ray_start_command", "kr_ray_container_env", "kr_ray_probes", "kr_ray_volumes", "kr_quantity_value", "kr_ray_start_last_error",
+    "kr_ray_ft_env", "kr_ray_auth", "kr_ray_autoscaler_container", "kr_ray_init_container", "kr_ray_template_last_error",
 ]
 
 

@@ -332,3 +332,99 @@ def ray_volumes(node_type: str, *, autoscaling: bool = False, plasma_directory_s
     if rc:
         raise EngineError(int(rc), (L.kr_ray_start_last_error() or b"").decode())
     return json.loads(bytes(buf)[:need.value])
+
+
+# ------------------------------------------------------------------------------------------------ template surgery (kr_raytemplate.cpp)
+def _template_call(name: str, arg) -> dict:
+    L = _lib()
+    fn = getattr(L, name)
+    if not getattr(L, "_kr_tpl_bound_" + name, False):
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.kr_ray_template_last_error.restype = C.c_char_p
+        setattr(L, "_kr_tpl_bound_" + name, True)
+    need = C.c_uint64()
+    rc = fn(C.byref(arg), None, 0, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise EngineError(int(rc), (L.kr_ray_template_last_error() or b"").decode())
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = fn(C.byref(arg), buf, need.value, C.byref(need))
+    if rc:
+        raise EngineError(int(rc), (L.kr_ray_template_last_error() or b"").decode())
+    return json.loads(bytes(buf)[:need.value])
+
+
+def _raw(keep: _Keep, obj) -> abi.kr_str:
+    """A corev1 fragment as the Go side would hand it over: json.Marshal text (None: absent)."""
+    if obj is None:
+        return abi.kr_str(None, 0)
+    return keep.s(obj if isinstance(obj, (str, bytes)) else json.dumps(obj, separators=(",", ":")))
+
+
+def _names(keep: _Keep, a, field: str, lst):
+    lst = lst or []
+    arr = (abi.kr_str * max(len(lst), 1))(*[keep.s(x) for x in lst])
+    keep.refs.append(arr)
+    setattr(a, field, arr)
+    setattr(a, "n_" + field, len(lst))
+
+
+def ray_ft_env(node_type: str, *, ft_enabled: bool, cluster_uid: str = "", storage_ns_annotation: str | None = None, options: dict | None = None,
+               head_redis_password_param: str | None = None, existing: list[str] | None = None) -> dict:
+    """kr_ray_ft_env: configureGCSFaultTolerance's env / rayStartParams additions (common/pod.go:77-163).  `options` mirrors
+    spec.gcsFaultToleranceOptions: redisAddress, externalStorageNamespace, redisUsername / redisPassword {value, valueFrom}."""
+    keep = _Keep()
+    a = abi.kr_rayft_in()
+    a.node_type = abi.NT_HEAD if node_type == "head" else abi.NT_WORKER
+    a.ft_enabled, a.has_options = int(ft_enabled), int(options is not None)
+    a.cluster_uid, a.storage_ns_annotation = keep.s(cluster_uid), keep.s(storage_ns_annotation)
+    o = options or {}
+    a.storage_ns_option, a.redis_address = keep.s(o.get("externalStorageNamespace")), keep.s(o.get("redisAddress", ""))
+    for key, flag, val, frm in (("redisUsername", "has_redis_username", "redis_username_value", "redis_username_value_from"),
+                                ("redisPassword", "has_redis_password", "redis_password_value", "redis_password_value_from")):
+        cred = o.get(key)
+        setattr(a, flag, int(cred is not None))
+        if cred is not None:
+            setattr(a, val, keep.s(cred.get("value", "")))
+            setattr(a, frm, _raw(keep, cred.get("valueFrom")))
+    a.head_redis_password_param = keep.s(head_redis_password_param)
+    _names(keep, a, "existing", existing)
+    return _template_call("kr_ray_ft_env", a)
+
+
+def ray_auth(cluster_name: str, *, k8s_token_auth: bool = False, secret_name: str | None = None, existing_env: list[str] | None = None,
+             existing_mount_names: list[str] | None = None, existing_volume_names: list[str] | None = None) -> dict:
+    """kr_ray_auth: the token-auth env / mount / volume for one container (common/pod.go:254-335)."""
+    keep = _Keep()
+    a = abi.kr_rayauth_in()
+    a.k8s_token_auth = int(k8s_token_auth)
+    a.cluster_name, a.secret_name = keep.s(cluster_name), keep.s(secret_name)
+    _names(keep, a, "existing_env", existing_env)
+    _names(keep, a, "existing_mount_names", existing_mount_names)
+    _names(keep, a, "existing_volume_names", existing_volume_names)
+    return _template_call("kr_ray_auth", a)
+
+
+def ray_autoscaler_container(cluster_name: str, ray_image: str, *, options: dict | None = None, autoscaler_v2: bool = False, auth_enabled: bool = False,
+                             k8s_token_auth: bool = False, secret_name: str | None = None, head_service_account: str | None = None, login_shell: bool = False) -> dict:
+    """kr_ray_autoscaler_container: the head's autoscaler sidecar (common/pod.go:194-220, 673-751).  `options` mirrors spec.autoscalerOptions:
+    image, imagePullPolicy, resources, env, envFrom, volumeMounts, securityContext."""
+    keep = _Keep()
+    a = abi.kr_rayautoscaler_in()
+    a.login_shell, a.autoscaler_v2, a.auth_enabled, a.k8s_token_auth, a.has_options = int(login_shell), int(autoscaler_v2), int(auth_enabled), int(k8s_token_auth), int(options is not None)
+    a.cluster_name, a.secret_name, a.head_service_account, a.ray_image = keep.s(cluster_name), keep.s(secret_name), keep.s(head_service_account), keep.s(ray_image)
+    o = options or {}
+    a.image, a.image_pull_policy = keep.s(o.get("image")), keep.s(o.get("imagePullPolicy"))
+    a.resources_json, a.env_json, a.env_from_json = _raw(keep, o.get("resources")), _raw(keep, o.get("env")), _raw(keep, o.get("envFrom"))
+    a.volume_mounts_json, a.security_context_json = _raw(keep, o.get("volumeMounts")), _raw(keep, o.get("securityContext"))
+    return _template_call("kr_ray_autoscaler_container", a)
+
+
+def ray_init_container(image: str, fqdn_ray_ip: str, head_port: str = "6379", *, image_pull_policy: str | None = None, env: list | None = None,
+                       volume_mounts: list | None = None, security_context: dict | None = None, login_shell: bool = False) -> dict:
+    """kr_ray_init_container: the worker's wait-gcs-ready init container (common/pod.go:359-415)."""
+    keep = _Keep()
+    a = abi.kr_rayinit_in()
+    a.login_shell = int(login_shell)
+    a.image, a.image_pull_policy, a.fqdn_ray_ip, a.head_port = keep.s(image), keep.s(image_pull_policy), keep.s(fqdn_ray_ip), keep.s(head_port)
+    a.env_json, a.volume_mounts_json, a.security_context_json = _raw(keep, env), _raw(keep, volume_mounts), _raw(keep, security_context)
+    return _template_call("kr_ray_init_container", a)

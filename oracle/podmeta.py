@@ -470,3 +470,208 @@ def ray_probes(node_type: str, ray_start_params=None, *, crd_type="RayCluster", 
             commands = commands + [wget(10, serving_port if serving_port > 0 else 8000, "-/healthz")]
         out["readinessProbe"] = probe(use_http, commands, 10, 5 if head else 2, 5, 1, failure)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- template surgery
+# Object-level restatements (they mutate plain-dict corev1 objects the way the Go code mutates its structs); the native builders
+# (kuberay_b200/csrc/kr_raytemplate.cpp) return fragments to append, and tests/test_raytemplate.py checks that applying those
+# fragments gives the same objects.
+def _env_exists(name: str, env: list) -> bool:
+    """utils.EnvVarExists (utils/util.go:691-698)."""
+    return any(e.get("name") == name for e in env)
+
+
+def _env_var(name: str, value: str = "", value_from=None) -> dict:
+    e = {"name": name}
+    if value != "":
+        e["value"] = value
+    if value_from is not None:
+        e["valueFrom"] = value_from
+    return e
+
+
+def configure_gcs_fault_tolerance(pod_template: dict, instance: dict, node_type: str, ft_enabled: bool) -> None:
+    """common/pod.go:77-163.  instance: {uid, annotations, spec{gcsFaultToleranceOptions, headGroupSpec{rayStartParams}}}."""
+    ann = pod_template.setdefault("metadata", {}).setdefault("annotations", {})
+    if node_type == "head":
+        ann["ray.io/ft-enabled"] = "true" if ft_enabled else "false"
+    if not ft_enabled:
+        return
+    options = instance["spec"].get("gcsFaultToleranceOptions")
+    container = pod_template["spec"]["containers"][0]
+    env = container.setdefault("env", [])
+    if not _env_exists("RAY_gcs_rpc_server_reconnect_timeout_s", env) and node_type == "worker":
+        env.append(_env_var("RAY_gcs_rpc_server_reconnect_timeout_s", "600"))
+    if node_type != "head":
+        return
+    storage_ns = instance.get("uid", "")
+    if "ray.io/external-storage-namespace" in (instance.get("annotations") or {}):
+        storage_ns = instance["annotations"]["ray.io/external-storage-namespace"]
+    if options is not None and options.get("externalStorageNamespace", "") != "":
+        storage_ns = options["externalStorageNamespace"]
+    ann["ray.io/external-storage-namespace"] = storage_ns
+    if not _env_exists("RAY_external_storage_namespace", env):
+        env.append(_env_var("RAY_external_storage_namespace", storage_ns))
+    params = instance["spec"]["headGroupSpec"].setdefault("rayStartParams", {})
+    if options is not None:
+        env.append(_env_var("RAY_REDIS_ADDRESS", options.get("redisAddress", "")))
+        if options.get("redisUsername") is not None:
+            params["redis-username"] = "$REDIS_USERNAME"
+            env.append(_env_var("REDIS_USERNAME", options["redisUsername"].get("value", ""), options["redisUsername"].get("valueFrom")))
+        if options.get("redisPassword") is not None:
+            params["redis-password"] = "$REDIS_PASSWORD"
+            env.append(_env_var("REDIS_PASSWORD", options["redisPassword"].get("value", ""), options["redisPassword"].get("valueFrom")))
+    elif not _env_exists("REDIS_PASSWORD", env) and "redis-password" in params:
+        env.append(_env_var("REDIS_PASSWORD", params["redis-password"]))
+
+
+def is_k8s_auth_enabled(auth_options: dict | None) -> bool:
+    """utils/util.go:763-765."""
+    return auth_options is not None and auth_options.get("enableK8sTokenAuth") is True
+
+
+def set_container_token_auth_env_vars(cluster_name: str, container: dict, auth_options: dict | None) -> None:
+    """common/pod.go:296-335."""
+    env = container.setdefault("env", [])
+    if not _env_exists("RAY_AUTH_MODE", env):
+        env.append(_env_var("RAY_AUTH_MODE", "token"))
+    if is_k8s_auth_enabled(auth_options):
+        if not _env_exists("RAY_ENABLE_K8S_TOKEN_AUTH", env):
+            env.append(_env_var("RAY_ENABLE_K8S_TOKEN_AUTH", "true"))
+        mounts = container.setdefault("volumeMounts", [])
+        if not any(m.get("name") == "ray-token" for m in mounts):
+            mounts.append({"name": "ray-token", "readOnly": True, "mountPath": "/var/run/secrets/ray.io/serviceaccount"})
+        return
+    secret = _dec(check_name(_enc(cluster_name)))
+    if auth_options is not None and auth_options.get("secretName"):
+        secret = auth_options["secretName"]
+    if not _env_exists("RAY_AUTH_TOKEN", env):
+        env.append(_env_var("RAY_AUTH_TOKEN", "", {"secretKeyRef": {"name": secret, "key": "auth_token"}}))
+
+
+def add_ray_token_volume(pod_spec: dict) -> None:
+    """common/pod.go:274-293."""
+    vols = pod_spec.setdefault("volumes", [])
+    if any(v.get("name") == "ray-token" for v in vols):
+        return
+    vols.append({"name": "ray-token", "projected": {"sources": [{"serviceAccountToken": {"path": "token"}}]}})
+
+
+def configure_token_auth(cluster_name: str, pod_template: dict, auth_options: dict | None) -> None:
+    """common/pod.go:254-271: the Ray container, the pod's token volume, and the wait-gcs-ready init container when present."""
+    set_container_token_auth_env_vars(cluster_name, pod_template["spec"]["containers"][0], auth_options)
+    if is_k8s_auth_enabled(auth_options):
+        add_ray_token_volume(pod_template["spec"])
+    for c in pod_template["spec"].get("initContainers") or []:
+        if c.get("name") == "wait-gcs-ready":
+            set_container_token_auth_env_vars(cluster_name, c, auth_options)
+
+
+def container_command(login_shell: bool = False) -> list:
+    """utils.GetContainerCommand([]string{}) (utils/util.go:884-892)."""
+    return ["/bin/bash", "-c" + ("l" if login_shell else ""), "--"]
+
+
+def build_autoscaler_container(image: str, login_shell: bool = False) -> dict:
+    """common/pod.go:673-724."""
+    small = {"cpu": "500m", "memory": "512Mi"}
+    c = {"name": "autoscaler"}
+    if image != "":
+        c["image"] = image
+    c.update({
+        "command": container_command(login_shell),
+        "args": ["ray kuberay-autoscaler --cluster-name $(RAY_CLUSTER_NAME) --cluster-namespace $(RAY_CLUSTER_NAMESPACE)"],
+        "env": [_env_var("RAY_CLUSTER_NAME", "", {"fieldRef": {"fieldPath": "metadata.labels['ray.io/cluster']"}}),
+                _env_var("RAY_CLUSTER_NAMESPACE", "", {"fieldRef": {"fieldPath": "metadata.namespace"}}),
+                _env_var("RAY_HEAD_POD_NAME", "", {"fieldRef": {"fieldPath": "metadata.name"}}),
+                _env_var("KUBERAY_CRD_VER", "v1")],
+        "resources": {"limits": dict(small), "requests": dict(small)},
+        "imagePullPolicy": "IfNotPresent",
+    })
+    return c
+
+
+def merge_autoscaler_overrides(container: dict, options: dict | None) -> None:
+    """common/pod.go:727-751."""
+    if options is None:
+        return
+    if options.get("resources") is not None:
+        container["resources"] = options["resources"]
+    for key in ("image", "imagePullPolicy"):  # a pointer that is set overrides, even with ""; the JSON form then drops the empty field
+        if options.get(key) is not None:
+            container[key] = options[key]
+            if options[key] == "":
+                del container[key]
+    if options.get("env"):
+        container["env"] = container.get("env", []) + list(options["env"])
+    if options.get("envFrom"):
+        container["envFrom"] = container.get("envFrom", []) + list(options["envFrom"])
+    if options.get("volumeMounts"):
+        container["volumeMounts"] = container.get("volumeMounts", []) + list(options["volumeMounts"])
+    if options.get("securityContext") is not None:
+        container["securityContext"] = options["securityContext"]
+
+
+def head_autoscaler_sidecar(instance: dict, pod_template: dict, login_shell: bool = False) -> None:
+    """The autoscaling block of DefaultHeadPodTemplate (common/pod.go:194-220) on a head template; instance: {name, spec{authOptions,
+    autoscalerOptions}}; the caller has established that autoscaling is on."""
+    spec = pod_template["spec"]
+    sa = spec.get("serviceAccountName") or instance["name"]  # utils.GetHeadGroupServiceAccountName
+    spec["serviceAccountName"] = _dec(check_name(_enc(sa)))
+    c = build_autoscaler_container(spec["containers"][0].get("image", ""), login_shell)
+    auth = instance["spec"].get("authOptions")
+    if auth is not None and auth.get("mode") == "token":
+        set_container_token_auth_env_vars(instance["name"], c, auth)
+    options = instance["spec"].get("autoscalerOptions")
+    merge_autoscaler_overrides(c, options)
+    spec["containers"].append(c)
+    if options is not None and options.get("version") == "v2":  # utils.IsAutoscalingV2Enabled as far as the spec goes
+        spec["containers"][0].setdefault("env", []).append(_env_var("RAY_enable_autoscaler_v2", "true"))
+        spec["restartPolicy"] = "Never"
+
+
+def wait_gcs_ready_script(fqdn_ray_ip: str, head_port: str) -> str:
+    """The polling loop of common/pod.go:372-390, with the indentation its Go raw string carries."""
+    addr = f"{fqdn_ray_ip}:{head_port}"
+    lines = [
+        (5, "SECONDS=0"),
+        (5, "while true; do"),
+        (6, "if (( SECONDS <= 120 )); then"),
+        (7, f"if ray health-check --address {addr} > /dev/null 2>&1; then"),
+        (8, 'echo "GCS is ready."'),
+        (8, "break"),
+        (7, "fi"),
+        (7, 'echo "$SECONDS seconds elapsed: Waiting for GCS to be ready."'),
+        (6, "else"),
+        (7, f"if ray health-check --address {addr}; then"),
+        (8, 'echo "GCS is ready. Any error messages above can be safely ignored."'),
+        (8, "break"),
+        (7, "fi"),
+        (7, 'echo "$SECONDS seconds elapsed: Still waiting for GCS to be ready. For troubleshooting, refer to the FAQ at '
+            'https://docs.ray.io/en/master/cluster/kubernetes/troubleshooting.html."'),
+        (6, "fi"),
+        (6, "sleep 5"),
+        (5, "done"),
+    ]
+    return "\n" + "".join("\t" * n + text + "\n" for n, text in lines) + "\t" * 4
+
+
+def wait_gcs_ready_container(ray_container: dict, fqdn_ray_ip: str, head_port: str, login_shell: bool = False) -> dict:
+    """The init container DefaultWorkerPodTemplate appends (common/pod.go:363-415)."""
+    import copy
+    small = {"cpu": "200m", "memory": "256Mi"}
+    c = {"name": "wait-gcs-ready"}
+    if ray_container.get("image"):
+        c["image"] = ray_container["image"]
+    c["command"] = container_command(login_shell)
+    c["args"] = [wait_gcs_ready_script(fqdn_ray_ip, head_port)]
+    if ray_container.get("env"):
+        c["env"] = copy.deepcopy(ray_container["env"])
+    c["resources"] = {"limits": dict(small), "requests": dict(small)}
+    if ray_container.get("volumeMounts"):
+        c["volumeMounts"] = copy.deepcopy(ray_container["volumeMounts"])
+    if ray_container.get("imagePullPolicy"):
+        c["imagePullPolicy"] = ray_container["imagePullPolicy"]
+    if ray_container.get("securityContext") is not None:
+        c["securityContext"] = copy.deepcopy(ray_container["securityContext"])
+    return c
