@@ -20,6 +20,7 @@ import copy
 from dataclasses import dataclass, field
 
 from . import abi
+from . import podbuilder
 from . import podmeta
 from . import snapshot as snapmod
 
@@ -300,11 +301,23 @@ class RayClusterReconciler:
     def _build_pod(self, cluster: dict, create: tuple, cluster_hash: str | None = None) -> dict:
         """The new Pod's ObjectMeta from the native builder (kr_pod_meta_build: buildHeadPod / buildWorkerPod metadata,
         raycluster_controller.go:1387-1433); the fake API server then turns generateName into a name (5 generated characters)."""
-        env = podmeta.PodMetaEnv(kuberay_version=snapmod.KUBERAY_VERSION, multihost_indexing_gate=bool(self.env.multihost_indexing_gate))
-        meta = podmeta.build_pod_meta(cluster, [create], env, cluster_hash=cluster_hash)[0]
+        spec = cluster.get("spec") or {}
+        grp = (spec.get("headGroupSpec") or {}) if create[0] < 0 else spec["workerGroupSpecs"][create[0]]
+        pod_spec = None
+        if ((grp.get("template") or {}).get("spec") or {}).get("containers"):
+            # the RayCluster carries real Pod templates: the whole manifest, container half included (podbuilder.py: DefaultHead/WorkerPodTemplate + BuildPod)
+            built = podbuilder.build_pod(cluster, create, podbuilder.BuilderEnv(kuberay_version=snapmod.KUBERAY_VERSION, multihost_indexing_gate=bool(self.env.multihost_indexing_gate)),
+                                         cluster_hash=cluster_hash)
+            meta, pod_spec = built["metadata"], built["spec"]
+        else:
+            env = podmeta.PodMetaEnv(kuberay_version=snapmod.KUBERAY_VERSION, multihost_indexing_gate=bool(self.env.multihost_indexing_gate))
+            meta = podmeta.build_pod_meta(cluster, [create], env, cluster_hash=cluster_hash)[0]
         name = meta.get("name") or meta["generateName"] + self.client.gen_suffix()
-        return {"namespace": meta["namespace"], "name": name, "phase": "", "restartPolicy": "Always", "labels": meta["labels"],
-                "annotations": meta["annotations"], "ownerReferences": meta["ownerReferences"]}
+        pod = {"namespace": meta["namespace"], "name": name, "phase": "", "restartPolicy": (pod_spec or {}).get("restartPolicy") or "Always", "labels": meta["labels"],
+               "annotations": meta["annotations"], "ownerReferences": meta["ownerReferences"]}
+        if pod_spec is not None:
+            pod["spec"] = pod_spec
+        return pod
 
     @staticmethod
     def _should_delete_reason(pod: dict, node_type: str) -> str:

@@ -675,3 +675,98 @@ def wait_gcs_ready_container(ray_container: dict, fqdn_ray_ip: str, head_port: s
     if ray_container.get("securityContext") is not None:
         c["securityContext"] = copy.deepcopy(ray_container["securityContext"])
     return c
+
+
+# ---------------------------------------------------------------------------------------------------------------- the whole Pod
+def add_empty_dir(container: dict, pod_spec: dict, volume_name: str, mount_path: str, memory: bool, canonical=lambda q: q) -> None:
+    """addEmptyDir / makeEmptyDirVolume / findMemoryReqOrLimit (common/pod.go:1137-1217).  `canonical`: resource.Quantity's String()."""
+    mounts = container.get("volumeMounts") or []
+    if any(m.get("mountPath") == mount_path for m in mounts):
+        return
+    vols = pod_spec.get("volumes") or []
+    if not any(v.get("name") == volume_name for v in vols):
+        empty = {}
+        if memory:
+            empty["medium"] = "Memory"
+            res = container.get("resources") or {}
+            q = (res.get("limits") or {}).get("memory", (res.get("requests") or {}).get("memory"))
+            if q is not None:
+                empty["sizeLimit"] = canonical(q)
+        pod_spec["volumes"] = vols + [{"name": volume_name, "emptyDir": empty}]
+    container["volumeMounts"] = mounts + [{"name": volume_name, "mountPath": mount_path}]
+
+
+def build_pod(cluster: dict, create: tuple, *, kuberay_version="v1.5.0", deterministic_head_name=False, multihost_indexing_gate=True, login_shell=False,
+              init_container_injection=True, probes_injection=True, cluster_domain="cluster.local", default_container_envs=None, cluster_hash=None,
+              canonical=lambda q: q) -> dict:
+    """buildHeadPod / buildWorkerPod (raycluster_controller.go:1387-1433) = DefaultHead/WorkerPodTemplate (common/pod.go:166-239,
+    352-464) + BuildPod (:577-669), followed statement by statement on plain dicts (maps shared and mutated as the Go code does)."""
+    import copy
+    g = create[0]
+    head = g < 0
+    node = "head" if head else "worker"
+    instance = copy.deepcopy(cluster)
+    spec = instance.setdefault("spec", {})
+    head_spec = spec.setdefault("headGroupSpec", {})
+    head_spec.setdefault("rayStartParams", {})
+    grp = head_spec if head else spec["workerGroupSpecs"][g]
+    params = grp.setdefault("rayStartParams", {})          # the map BuildPod receives; the template functions mutate it in place
+    annots = instance.get("annotations") or {}
+    head_port = head_spec["rayStartParams"].get("port", "6379")
+    svc = ((head_spec.get("headService") or {}).get("metadata") or {}).get("name") or (head_spec.get("headService") or {}).get("name") or f"{instance['name']}-head-svc"
+    fqdn = f"{svc}.{instance.get('namespace', 'default')}.svc.{cluster_domain}"
+    autoscaling = spec.get("enableInTreeAutoscaling") is True
+    auto_opts = spec.get("autoscalerOptions")
+    auto_v2 = auto_opts is not None and auto_opts.get("version") == "v2"
+    auth = spec.get("authOptions")
+    auth_on = auth is not None and auth.get("mode") == "token"
+    ft_opts = spec.get("gcsFaultToleranceOptions")
+    ft = ("ray.io/ft-enabled" in annots and annots["ray.io/ft-enabled"].lower() == "true") or ft_opts is not None
+    crd = (instance.get("labels") or {}).get("ray.io/originated-from-crd")
+    crd = crd if crd in ("RayJob", "RayService") else "RayCluster"
+
+    template = {"metadata": {}, "spec": copy.deepcopy((grp.get("template") or {}).get("spec") or {})}
+    pspec = template["spec"]
+    ray = pspec["containers"][0]
+    if not head and init_container_injection:                                                 # :359-415
+        pspec["initContainers"] = (pspec.get("initContainers") or []) + [wait_gcs_ready_container(ray, fqdn, head_port, login_shell)]
+    update_ray_start_params_resources(params, grp.get("resources"))                           # :181 / :421
+    update_ray_start_params_labels(params, grp.get("labels"))                                 # :184 / :424
+    set_missing_ray_start_params(params, node, head_port, "" if head else fqdn)               # :190 / :440
+    if head and autoscaling:                                                                  # :194-220
+        params["no-monitor"] = "true"
+        head_autoscaler_sidecar(instance, template, login_shell)
+    configure_gcs_fault_tolerance(template, instance, node, ft)                               # :222 / :443
+    if not any(p.get("name") == "metrics" for p in ray.get("ports") or []):                   # :224-232 / :445-453
+        ray["ports"] = (ray.get("ports") or []) + [{"name": "metrics", "containerPort": 8080}]
+    if not head and autoscaling and auto_v2:                                                  # :455-457
+        pspec["restartPolicy"] = "Never"
+    if auth_on:                                                                               # :234-236 / :459-461
+        configure_token_auth(instance["name"], template, auth)
+
+    # BuildPod (:577-669)
+    if "plasma-directory" not in params:
+        add_empty_dir(ray, pspec, "shared-mem", "/dev/shm", True, canonical)
+    if head and autoscaling:
+        side = next(c for c in pspec["containers"] if c.get("name") == "autoscaler")          # getAutoscalerContainerIndex (it panics when absent)
+        add_empty_dir(ray, pspec, "ray-logs", "/tmp/ray", False)
+        add_empty_dir(side, pspec, "ray-logs", "/tmp/ray", False)
+    meta = pod_meta(cluster, create, kuberay_version=kuberay_version, deterministic_head_name=deterministic_head_name,
+                    multihost_indexing_gate=multihost_indexing_gate, cluster_hash=cluster_hash)
+    cmd = "".join(f" {v} " for v in ray.get("command") or []) + "".join(f" {v} " for v in ray.get("args") or [])
+    res = ray.get("resources") or {}
+    line = generate_ray_start_command(node, params, res.get("limits"), res.get("requests"))
+    overwrite = meta["annotations"].get("ray.io/overwrite-container-cmd", "").lower() == "true"
+    if not overwrite and "ray start" not in cmd:
+        generated = "ulimit -n 65536; " + line
+        ray["command"] = container_command(login_shell)
+        ray["args"] = [f"{cmd} && {generated}" if cmd else generated]
+    for c in pspec.get("initContainers") or []:
+        c["env"] = (c.get("env") or []) + ray_container_env(node, fqdn_ray_ip=fqdn, init_container=True)
+    ray["env"] = (ray.get("env") or []) + ray_container_env(node, existing=[e.get("name") for e in ray.get("env") or []], default_envs=default_container_envs,
+                                                             fqdn_ray_ip=fqdn, head_port=head_port, ray_start_cmd=line, crd_type=crd, kuberay_version=kuberay_version)
+    if probes_injection:
+        serve = next((p.get("containerPort", 8000) for p in ray.get("ports") or [] if p.get("name") == "serve"), 8000)
+        ray.update(ray_probes(node, params, crd_type=crd, ray_version=spec.get("rayVersion", ""), has_liveness=ray.get("livenessProbe") is not None,
+                              has_readiness=ray.get("readinessProbe") is not None, serving_port=serve))
+    return {"apiVersion": "v1", "kind": "Pod", "metadata": meta, "spec": pspec}

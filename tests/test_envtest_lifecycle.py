@@ -241,3 +241,26 @@ def test_group_suspend_with_autoscaler_is_stopped_by_validation(backend):
     client.clusters[(NS, name)]["spec"]["workerGroupSpecs"][0]["suspend"] = True
     client.clusters[(NS, name)]["skip"] = True  # what the prelude's validation error amounts to for the batch
     assert consistently(r, name, lambda: len(workers(client, name)) == 3 and len(heads(client, name)) == 1)
+
+
+def test_created_pods_carry_the_built_manifest(backend):
+    """What reaches client.Create is the whole Pod of buildHeadPod / buildWorkerPod (raycluster_controller.go:1387-1433), not just the metadata the
+    engine's create tuples decide: generated `ray start` command, KubeRay's env, probes, /dev/shm, the worker's wait-gcs-ready init container."""
+    name = "raycluster-built"
+    tpl = cluster_template(name, autoscaling=True)
+    tpl["spec"]["headGroupSpec"]["template"]["spec"]["containers"][0].update(image="rayproject/ray:2.9.0", resources={"limits": {"cpu": "2", "memory": "4Gi"}})
+    tpl["spec"]["workerGroupSpecs"][0]["template"]["spec"]["containers"][0].update(image="rayproject/ray:2.9.0", resources={"limits": {"cpu": "4", "memory": "8Gi", "nvidia.com/gpu": "1"}})
+    client = FakeClient([tpl], [])
+    r = RayClusterReconciler(client, backend)
+    assert eventually(r, name, lambda: len(workers(client, name)) == 3 and len(heads(client, name)) == 1)
+    head = heads(client, name)[0]["spec"]
+    assert [c["name"] for c in head["containers"]] == ["ray-head", "autoscaler"] and head["serviceAccountName"] == name
+    assert head["containers"][0]["args"][0].startswith("ulimit -n 65536; ray start --head ") and "--no-monitor" in head["containers"][0]["args"][0]
+    assert "--num-cpus=2" in head["containers"][0]["args"][0] and "--memory=4294967296" in head["containers"][0]["args"][0]
+    assert {"name": "ray-logs", "emptyDir": {}} in head["volumes"] and "livenessProbe" in head["containers"][0]
+    for w in workers(client, name):
+        spec = w["spec"]
+        ray = spec["containers"][0]
+        assert f"--address={name}-head-svc.{NS}.svc.cluster.local:6379" in ray["args"][0] and "--num-gpus=1" in ray["args"][0]
+        assert spec["initContainers"][0]["name"] == "wait-gcs-ready" and spec["volumes"] == [{"name": "shared-mem", "emptyDir": {"medium": "Memory", "sizeLimit": "8Gi"}}]
+        assert any(e["name"] == "RAY_ADDRESS" and e["value"].endswith(":6379") for e in ray["env"]) and w["labels"]["ray.io/group"] == GROUP
