@@ -856,6 +856,34 @@ typedef struct kr_rayinit_in {
 int kr_ray_init_container(const kr_rayinit_in *in, uint8_t *out, uint64_t cap, uint64_t *need);
 const char *kr_ray_template_last_error(void);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * The whole Pod (assembled): buildHeadPod / buildWorkerPod (raycluster_controller.go:1387-1433) = DefaultHeadPodTemplate /
+ * DefaultWorkerPodTemplate (common/pod.go:166-239, 352-464) + BuildPod (:577-669) + the controller ownerReference, for every create
+ * tuple of ONE RayCluster in one call.  Host-side; no GPU.  The container half of a manifest depends only on the group, so it is
+ * built once per group and call; the ObjectMeta varies per tuple (kr_pod_meta_build).
+ *   cluster_json: the RayCluster as JSON — {"metadata":{"name","namespace","uid","labels","annotations"},"spec":{...}}, keys in any
+ *     order (what the API server serves, or json.Marshal(instance)).
+ *   out: one corev1.Pod per create, back to back (create i owns out[off[i] .. off[i+1])):
+ *     {"kind":"Pod","apiVersion":"v1","metadata":{...},"spec":{...},"status":{}} — struct fields in Go's declaration order, omitempty
+ *     honoured, maps sorted, quantities canonical; it decodes into the corev1.Pod the reference hands to client.Create.
+ * *need = bytes required; KR_E_CAPACITY when cap is too small (off[] is still filled in). */
+typedef struct kr_podbuild_env {       /* the operator process's contribution */
+  kr_str kuberay_version;              /* utils.KUBERAY_VERSION */
+  kr_str cluster_domain;               /* CLUSTER_DOMAIN; absent or "": cluster.local */
+  kr_str cluster_hash;                 /* createHeadPod's clusterHash (head annotations); absent or "": none */
+  uint8_t deterministic_head_name;     /* utils.IsDeterministicHeadPodNameEnabled() */
+  uint8_t gate_multihost_indexing;     /* features.RayMultiHostIndexing */
+  uint8_t login_shell;                 /* ENABLE_LOGIN_SHELL == "true" */
+  uint8_t no_init_container_injection; /* ENABLE_INIT_CONTAINER_INJECTION == "false" */
+  uint8_t no_probes_injection;         /* ENABLE_PROBES_INJECTION == "false" */
+  uint8_t reserved[3];
+  const kr_kv *default_envs; uint32_t n_default_envs;          /* configuration DefaultContainerEnvs */
+  kr_str head_sidecars_json, worker_sidecars_json;             /* configuration Head / WorkerSidecarContainers (raw []corev1.Container) */
+} kr_podbuild_env;
+int kr_pod_build(const uint8_t *cluster_json, uint64_t len, const kr_podbuild_env *env, const kr_podmeta_create *creates, uint32_t n_creates,
+                 uint8_t *out, uint64_t cap, uint64_t *off, uint64_t *need);
+const char *kr_pod_build_last_error(void);
+
 /* Last error text for this engine (never NULL). */
 const char *kr_last_error(kr_engine *e);
 

@@ -258,6 +258,12 @@ class kr_rayinit_in(C.Structure):
                 ("env_json", kr_str), ("volume_mounts_json", kr_str), ("security_context_json", kr_str)]
 
 
+class kr_podbuild_env(C.Structure):
+    _fields_ = [("kuberay_version", kr_str), ("cluster_domain", kr_str), ("cluster_hash", kr_str), ("deterministic_head_name", C.c_uint8),
+                ("gate_multihost_indexing", C.c_uint8), ("login_shell", C.c_uint8), ("no_init_container_injection", C.c_uint8), ("no_probes_injection", C.c_uint8),
+                ("reserved", C.c_uint8 * 3), ("default_envs", C.POINTER(kr_kv)), ("n_default_envs", C.c_uint32), ("head_sidecars_json", kr_str), ("worker_sidecars_json", kr_str)]
+
+
 class kr_rayprobe_in(C.Structure):
     _fields_ = [("node_type", C.c_uint8), ("crd_type", C.c_uint8), ("has_liveness_probe", C.c_uint8), ("has_readiness_probe", C.c_uint8),
                 ("serving_port", C.c_int32), ("ray_version", kr_str), ("ray_start_params", C.POINTER(kr_kv)), ("n_ray_start_params", C.c_uint32)]
@@ -305,7 +311,7 @@ ENGINE_SYMBOLS = [
     "kr_packer_cluster_epoch", "kr_packer_last_error",
     "kr_pod_name", "kr_check_name", "kr_check_label", "kr_pod_meta_build", "kr_pod_creates_expand", "kr_pod_meta_last_error",
     "kr_ray_start_command", "kr_ray_container_env", "kr_ray_probes", "kr_ray_volumes", "kr_quantity_value", "kr_ray_start_last_error",
-    "kr_ray_ft_env", "kr_ray_auth", "kr_ray_autoscaler_container", "kr_ray_init_container", "kr_ray_template_last_error",
+    "kr_pod_build", "kr_pod_build_last_error", "kr_ray_ft_env", "kr_ray_auth", "kr_ray_autoscaler_container", "kr_ray_init_container", "kr_ray_template_last_error",
 ]
 
 

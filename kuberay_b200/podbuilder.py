@@ -152,3 +152,46 @@ def build_pod(cluster: dict, create: tuple[int, int, int, str], env: BuilderEnv 
         ray.update(podmeta.ray_probes(node, rs["rayStartParams"], crd_type=crd, ray_version=spec.get("rayVersion", ""), has_liveness=ray.get("livenessProbe") is not None,
                                       has_readiness=ray.get("readinessProbe") is not None, serving_port=int(serve)))
     return {"apiVersion": "v1", "kind": "Pod", "metadata": meta, "spec": pspec}
+
+
+def build_pods_native(cluster: dict, creates: list[tuple[int, int, int, str]], env: BuilderEnv | None = None, cluster_hash: str | None = None, raw: bool = False) -> list:
+    """kr_pod_build: the same manifests from ONE native call for all of a RayCluster's create tuples (the container half assembled once per group
+    inside the library).  raw=True returns each Pod's JSON bytes exactly as written (Go field order)."""
+    import ctypes as C
+    import json
+
+    from . import abi
+    from .engine import EngineError
+    env = env or BuilderEnv()
+    L = podmeta._lib()
+    if not getattr(L, "_kr_pb_bound", False):
+        L.kr_pod_build.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(abi.kr_podbuild_env), C.POINTER(abi.kr_podmeta_create), C.c_uint32, C.c_void_p, C.c_uint64,
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.kr_pod_build_last_error.restype = C.c_char_p
+        L._kr_pb_bound = True
+    keep = podmeta._Keep()
+    # the RayCluster in its Kubernetes shape (what json.Marshal(instance) gives the Go shim)
+    doc = json.dumps({"metadata": {k: cluster[k] for k in ("name", "namespace", "uid", "labels", "annotations") if k in cluster}, "spec": cluster.get("spec") or {}}).encode()
+    e = abi.kr_podbuild_env()
+    e.kuberay_version, e.cluster_domain, e.cluster_hash = keep.s(env.kuberay_version), keep.s(env.cluster_domain), keep.s(cluster_hash or None)
+    e.deterministic_head_name, e.gate_multihost_indexing, e.login_shell = int(env.deterministic_head_name), int(env.multihost_indexing_gate), int(env.login_shell)
+    e.no_init_container_injection, e.no_probes_injection = int(not env.init_container_injection), int(not env.probes_injection)
+    e.default_envs, e.n_default_envs = keep.kvs(env.default_container_envs)
+    e.head_sidecars_json = keep.s(json.dumps(env.head_sidecar_containers) if env.head_sidecar_containers else None)
+    e.worker_sidecars_json = keep.s(json.dumps(env.worker_sidecar_containers) if env.worker_sidecar_containers else None)
+    tuples = (abi.kr_podmeta_create * max(len(creates), 1))()
+    for i, (g, ri, hi, rn) in enumerate(creates):
+        tuples[i].group, tuples[i].replica_index, tuples[i].host_index = int(g), int(ri), int(hi)
+        tuples[i].replica_name = keep.s(rn or "")
+    off = (C.c_uint64 * (len(creates) + 1))()
+    need = C.c_uint64()
+    rc = L.kr_pod_build(doc, len(doc), C.byref(e), tuples, len(creates), None, 0, off, C.byref(need))
+    if rc not in (0, abi.KR_E_CAPACITY):
+        raise EngineError(int(rc), (L.kr_pod_build_last_error() or b"").decode())
+    buf = (C.c_uint8 * max(need.value, 1))()
+    rc = L.kr_pod_build(doc, len(doc), C.byref(e), tuples, len(creates), buf, need.value, off, C.byref(need))
+    if rc:
+        raise EngineError(int(rc), (L.kr_pod_build_last_error() or b"").decode())
+    b = bytes(buf)
+    parts = [b[off[i]:off[i + 1]] for i in range(len(creates))]
+    return parts if raw else [json.loads(p) for p in parts]

@@ -305,9 +305,9 @@ class RayClusterReconciler:
         grp = (spec.get("headGroupSpec") or {}) if create[0] < 0 else spec["workerGroupSpecs"][create[0]]
         pod_spec = None
         if ((grp.get("template") or {}).get("spec") or {}).get("containers"):
-            # the RayCluster carries real Pod templates: the whole manifest, container half included (podbuilder.py: DefaultHead/WorkerPodTemplate + BuildPod)
-            built = podbuilder.build_pod(cluster, create, podbuilder.BuilderEnv(kuberay_version=snapmod.KUBERAY_VERSION, multihost_indexing_gate=bool(self.env.multihost_indexing_gate)),
-                                         cluster_hash=cluster_hash)
+            # the RayCluster carries real Pod templates: the whole manifest, container half included (kr_pod_build: DefaultHead/WorkerPodTemplate + BuildPod)
+            built = podbuilder.build_pods_native(cluster, [create], podbuilder.BuilderEnv(kuberay_version=snapmod.KUBERAY_VERSION,
+                                                                                          multihost_indexing_gate=bool(self.env.multihost_indexing_gate)), cluster_hash=cluster_hash)[0]
             meta, pod_spec = built["metadata"], built["spec"]
         else:
             env = podmeta.PodMetaEnv(kuberay_version=snapmod.KUBERAY_VERSION, multihost_indexing_gate=bool(self.env.multihost_indexing_gate))

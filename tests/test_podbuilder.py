@@ -315,3 +315,94 @@ def test_random_clusters_assemble_like_the_restatement(seed):
         hosts = int(grp.get("numOfHosts", 1))
         build_both(cluster, (gi, rng.randint(0, 5), rng.randint(0, hosts - 1), f"{grp['groupName']}-abcde" if hosts > 1 else ""), **kw)
     assert cluster == before     # neither builder touches its input (the Go code does mutate the cached object's maps; the shim must not rely on that)
+
+
+# ---- the one-call native builder (kr_pod_build) ---------------------------------------------------------------------------------------
+def go_form(obj, key=None):
+    """What a typed round trip through corev1 does to the Python assembly's dicts: empty slices vanish (omitempty), quantities print canonically."""
+    if isinstance(obj, dict):
+        out = {}
+        for k, v in obj.items():
+            if isinstance(v, list) and not v or v is None:
+                continue
+            if k in ("limits", "requests", "labels", "annotations", "nodeSelector") and v == {} and key != "metadata":
+                continue                                   # an empty map under omitempty
+            if k in ("limits", "requests") and isinstance(v, dict):
+                out[k] = {rk: engine.quantity_canonical(str(rv)) for rk, rv in v.items()}
+            elif k == "sizeLimit":
+                out[k] = engine.quantity_canonical(str(v))
+            else:
+                out[k] = go_form(v, k)
+        return out
+    if isinstance(obj, list):
+        return [go_form(v) for v in obj]
+    return obj
+
+
+def creates_of(cluster, rng):
+    out = [HEAD]
+    for gi, grp in enumerate(cluster["spec"]["workerGroupSpecs"]):
+        hosts = int(grp.get("numOfHosts", 1))
+        for _ in range(rng.randint(1, 3)):
+            out.append((gi, rng.randint(0, 7), rng.randint(0, hosts - 1), f"{grp['groupName']}-abcde" if hosts > 1 else ""))
+    rng.shuffle(out)
+    return out
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_native_one_call_builder_agrees_with_the_assembly(seed):
+    rng = random.Random(1000 + seed)
+    cluster = random_cluster(rng)
+    env = pb.BuilderEnv(login_shell=rng.random() < 0.2, init_container_injection=rng.random() < 0.85, probes_injection=rng.random() < 0.85,
+                        deterministic_head_name=rng.random() < 0.3, multihost_indexing_gate=rng.random() < 0.7, cluster_domain=rng.choice(["cluster.local", "corp.example"]),
+                        default_container_envs=rng.choice([{}, {"RAY_PORT": "1", "DEF": "d"}]),
+                        head_sidecar_containers=rng.choice([[], [{"name": "fluentbit", "image": "fb:1"}]]), worker_sidecar_containers=rng.choice([[], [{"name": "w", "image": "w:1"}]]))
+    creates = creates_of(cluster, rng)
+    chash = rng.choice([None, "0123456789ABCDEFGHIJKLMNOPQRSTUV"])
+    got = pb.build_pods_native(cluster, creates, env, cluster_hash=chash)
+    assert len(got) == len(creates)
+    for pod, create in zip(got, creates):
+        assert pod.pop("status") == {}
+        want = go_form(pb.build_pod(cluster, create, env, cluster_hash=chash))
+        for c in want["spec"]["containers"] + want["spec"].get("initContainers", []):
+            c.setdefault("resources", {})          # a struct value: encoding/json writes it even when empty
+        assert pod == want, create
+
+
+def test_native_builder_writes_go_field_order():
+    """Bytes, not just the decoded value: TypeMeta first, corev1.PodSpec / Container fields in declaration order, maps sorted, alphabetical API-server input reordered."""
+    import json
+    cluster = instance()
+    cluster["spec"]["enableInTreeAutoscaling"] = True
+    # the API server serves keys alphabetically: feed the builder that order
+    cluster = json.loads(json.dumps(cluster, sort_keys=True))
+    raw_head, raw_worker = pb.build_pods_native(cluster, [HEAD, WORKER], raw=True)
+    assert raw_head.startswith(b'{"kind":"Pod","apiVersion":"v1","metadata":{"generateName":"raycluster-sample-head-","namespace":"default","labels":{')
+    assert raw_head.endswith(b',"status":{}}')
+    head = json.loads(raw_head)
+    assert list(head) == ["kind", "apiVersion", "metadata", "spec", "status"]
+    assert list(head["spec"]) == ["volumes", "containers", "serviceAccountName"]
+    assert list(head["spec"]["containers"][0]) == ["name", "image", "command", "args", "ports", "env", "resources", "volumeMounts", "livenessProbe", "readinessProbe"]
+    assert list(head["spec"]["containers"][1]) == ["name", "image", "command", "args", "env", "resources", "volumeMounts", "imagePullPolicy"]
+    assert list(head["spec"]["containers"][0]["livenessProbe"]) == ["exec", "initialDelaySeconds", "timeoutSeconds", "periodSeconds", "successThreshold", "failureThreshold"]
+    worker = json.loads(raw_worker)
+    assert list(worker["spec"]) == ["volumes", "initContainers", "containers"]
+    assert list(worker["spec"]["initContainers"][0]) == ["name", "image", "command", "args", "env", "resources"]
+    assert list(worker["spec"]["containers"][0]["resources"]["limits"]) == ["cpu", "memory", "nvidia.com/gpu"]
+    assert b'"volumes":[{"name":"shared-mem","emptyDir":{"medium":"Memory","sizeLimit":"1Gi"}}]' in raw_worker
+    # one call, many tuples of the same group: the container half is byte-identical, only the ObjectMeta differs
+    many = pb.build_pods_native(cluster, [(0, i, 0, "") for i in range(50)], raw=True)
+    tails = {m[m.index(b',"spec":'):] for m in many}
+    assert len(tails) == 1 and len({m for m in many}) == 50
+
+
+def test_native_builder_errors():
+    from kuberay_b200.engine import EngineError
+    cluster = instance()
+    with pytest.raises(EngineError, match="worker group"):
+        pb.build_pods_native(cluster, [(5, 0, 0, "")])
+    broken = copy.deepcopy(cluster)
+    broken["spec"]["headGroupSpec"]["template"]["spec"]["containers"] = []
+    with pytest.raises(EngineError, match="Ray container"):
+        pb.build_pods_native(broken, [HEAD])
+    assert pb.build_pods_native(cluster, []) == []

@@ -84,9 +84,63 @@ def emit():
         spec_json_emit(spec)
 
 
+# ---- template surgery + the whole manifest (the assembly glue is Python here, Go in the shim: its cost is reported, not hidden)
+from kuberay_b200 import podbuilder  # noqa: E402
+
+ini = abi.kr_rayinit_in()
+ini.image, ini.fqdn_ray_ip, ini.head_port = keep.s("rayproject/ray:2.46.0"), rs.fqdn_ray_ip, rs.head_port
+ini.env_json = keep.s(json.dumps([{"name": f"E{i}", "value": str(i)} for i in range(10)], separators=(",", ":")))
+au = abi.kr_rayautoscaler_in()
+au.cluster_name, au.ray_image, au.auth_enabled = keep.s("raycluster-sample"), keep.s("rayproject/ray:2.46.0"), 1
+L.kr_ray_init_container.argtypes = L.kr_ray_autoscaler_container.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+
+
+def init_container():
+    for _ in range(20000):
+        assert L.kr_ray_init_container(C.byref(ini), small, len(small), C.byref(need)) == 0
+
+
+def autoscaler():
+    for _ in range(20000):
+        assert L.kr_ray_autoscaler_container(C.byref(au), small, len(small), C.byref(need)) == 0
+
+
+full = {"name": "raycluster-sample", "namespace": "default", "uid": "u", "spec": {"enableInTreeAutoscaling": True, **json.loads(spec)}}
+
+
+def whole_pods():
+    for i in range(300):
+        podbuilder.build_pod(full, (-1, 0, 0, "") if i % 4 == 0 else (0, i, 0, ""))
+
+
+# kr_pod_build straight through ctypes (arguments marshalled once, like the other lines): every create tuple of one RayCluster per call
+pb_doc = json.dumps({"metadata": {"name": "raycluster-sample", "namespace": "default", "uid": "u"}, "spec": full["spec"]}).encode()
+pb_env = abi.kr_podbuild_env()
+pb_env.kuberay_version, pb_env.gate_multihost_indexing = keep.s("v1.5.0"), 1
+pb_tuples = (abi.kr_podmeta_create * 1000)()
+for i in range(1000):
+    pb_tuples[i].group, pb_tuples[i].replica_index, pb_tuples[i].replica_name = (-1 if i == 0 else 0), i, keep.s("")
+pb_off = (C.c_uint64 * 1001)()
+pb_buf = (C.c_uint8 * (8 << 20))()
+L.kr_pod_build.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+
+
+def pod_build(n, reps):
+    def run():
+        for _ in range(reps):
+            assert L.kr_pod_build(pb_doc, len(pb_doc), C.byref(pb_env), pb_tuples, n, pb_buf, len(pb_buf), pb_off, C.byref(need)) == 0
+    return run
+
+
 out = {"host": os.uname().nodename, "cpus": os.cpu_count(), "threads_used": 1,
        "pod_meta_patches_per_s": round(timed(meta, 50 * N)), "pod_meta_bytes_per_patch": need.value and int(off[N] / N),
        "ray_start_commands_per_s": round(timed(start_cmd, 20000)), "container_env_lists_per_s": round(timed(env, 20000)),
        "muted_spec_json_emits_per_s": round(timed(emit, 2000)), "muted_spec_json_input_bytes": len(spec),
+       "init_containers_per_s": round(timed(init_container, 20000)), "autoscaler_containers_per_s": round(timed(autoscaler, 20000)),
+       "whole_pod_manifests_per_s_python_glue": round(timed(whole_pods, 300)),
+       "whole_pod_manifests_per_s_kr_pod_build_1000_per_call": round(timed(pod_build(1000, 20), 20 * 1000)),
+       "whole_pod_manifests_per_s_kr_pod_build_10_per_call": round(timed(pod_build(10, 500), 500 * 10)),
+       "whole_pod_manifests_per_s_kr_pod_build_1_per_call": round(timed(pod_build(1, 2000), 2000)),
+       "whole_pod_manifest_bytes": len(podbuilder.build_pods_native(full, [(0, 0, 0, "")], raw=True)[0]),
        "note": "one host thread through ctypes, arguments marshalled once; each call does all of its own work (no caching across calls)"}
 print(json.dumps(out))
