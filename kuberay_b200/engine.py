@@ -39,6 +39,15 @@ def lib() -> C.CDLL:
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
             raise FileNotFoundError(f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'`; there is no CPU fallback")
+        host_only = os.environ.get("KR_HOST_ONLY_LIB")  # development aid (tools/host_sanitize.sh): an ASan / UBSan build of the host-side builders alone
+        if host_only:
+            L = C.CDLL(host_only)
+            L.kr_spec_json_emit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+            L.kr_quantity_canonical.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
+            L.kr_spec_json_emit_arena.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+            L.kr_spec_json_last_error.restype = C.c_char_p
+            _LIB = L
+            return _LIB
         L = C.CDLL(LIB_PATH)
         P = C.POINTER
         L.kr_device_count.restype = C.c_int
