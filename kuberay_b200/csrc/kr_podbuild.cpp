@@ -410,7 +410,33 @@ int kr_pod_build(const uint8_t *cluster_json, uint64_t len, const kr_podbuild_en
     }
     off[i] = doc.size();
     doc += "{\"kind\":\"Pod\",\"apiVersion\":\"v1\",\"metadata\":";
-    doc.append(metas, moff[i], moff[i + 1] - moff[i]);
+    {
+      // ObjectMeta: podTemplateSpec.ObjectMeta (common/pod.go:598) — the template's own metadata with what the builders decided laid over it.
+      // The worker's name is cleared (:418); the head keeps a name its template brought when only generateName is set (:171-175).
+      const Node *grp = g < 0 ? c.head_spec : &c.groups->a[(size_t)g];
+      const Node *tmeta = child(child(grp, "template"), "metadata");
+      bool plain = true;  // nothing but what the patch replaces: the patch is the metadata
+      if (tmeta && tmeta->t == N_OBJ)
+        for (auto &kv : tmeta->o) {
+          const std::string &k = kv.first;
+          if (k == "labels" || k == "annotations" || k == "namespace" || k == "ownerReferences" || kv.second.t == N_NULL) continue;
+          if (k == "generateName" && !(g < 0 && env.deterministic_head_name && kv.second.t == N_STR && !kv.second.s.empty())) continue;
+          if (k == "name" && (g >= 0 || env.deterministic_head_name || kv.second.t != N_STR || kv.second.s.empty())) continue;
+          plain = false;
+        }
+      if (plain) doc.append(metas, moff[i], moff[i + 1] - moff[i]);
+      else {
+        Node base = *tmeta, patch;
+        if (g >= 0) base.erase("name");
+        Parser mp{metas.data() + moff[i], metas.data() + moff[i + 1], {}};
+        if (!mp.value(patch, 0) || patch.t != N_OBJ) { g_err = "kr_pod_build: kr_pod_meta_build returned malformed JSON"; return KR_E_INVALID; }
+        for (auto &kv : patch.o) member(base, kv.first.c_str()) = kv.second;
+        Emitter em;
+        em.strct("ObjectMeta", &base);
+        if (!em.err.empty()) { g_err = "kr_pod_build: " + em.err; return KR_E_INVALID; }
+        doc += em.out;
+      }
+    }
     doc += ",\"spec\":";
     doc += specs[slot];
     doc += ",\"status\":{}}";

@@ -151,7 +151,9 @@ def build_pod(cluster: dict, create: tuple[int, int, int, str], env: BuilderEnv 
         serve = next((p.get("containerPort", 8000) for p in ray.get("ports") or [] if p.get("name") == "serve"), 8000)
         ray.update(podmeta.ray_probes(node, rs["rayStartParams"], crd_type=crd, ray_version=spec.get("rayVersion", ""), has_liveness=ray.get("livenessProbe") is not None,
                                       has_readiness=ray.get("readinessProbe") is not None, serving_port=int(serve)))
-    return {"apiVersion": "v1", "kind": "Pod", "metadata": meta, "spec": pspec}
+    # ObjectMeta: the template's own metadata with the builders' decisions laid over it (common/pod.go:598); the worker's name is cleared (:418)
+    tmeta = {k: v for k, v in ((grp.get("template") or {}).get("metadata") or {}).items() if v is not None and not (k == "name" and not head)}
+    return {"apiVersion": "v1", "kind": "Pod", "metadata": {**copy.deepcopy(tmeta), **meta}, "spec": pspec}
 
 
 def build_pods_native(cluster: dict, creates: list[tuple[int, int, int, str]], env: BuilderEnv | None = None, cluster_hash: str | None = None, raw: bool = False) -> list:

@@ -769,4 +769,10 @@ def build_pod(cluster: dict, create: tuple, *, kuberay_version="v1.5.0", determi
         serve = next((p.get("containerPort", 8000) for p in ray.get("ports") or [] if p.get("name") == "serve"), 8000)
         ray.update(ray_probes(node, params, crd_type=crd, ray_version=spec.get("rayVersion", ""), has_liveness=ray.get("livenessProbe") is not None,
                               has_readiness=ray.get("readinessProbe") is not None, serving_port=serve))
-    return {"apiVersion": "v1", "kind": "Pod", "metadata": meta, "spec": pspec}
+    # ObjectMeta: podTemplateSpec.ObjectMeta (:598) — everything else the template's metadata carries rides along; DefaultWorkerPodTemplate
+    # clears the worker's name (:418), DefaultHeadPodTemplate sets name OR generateName and leaves the other as the template had it (:171-175)
+    tmeta = copy.deepcopy((grp.get("template") or {}).get("metadata") or {})
+    if not head:
+        tmeta.pop("name", None)
+    tmeta = {k: v for k, v in tmeta.items() if v is not None}
+    return {"apiVersion": "v1", "kind": "Pod", "metadata": {**tmeta, **meta}, "spec": pspec}

@@ -406,3 +406,24 @@ def test_native_builder_errors():
     with pytest.raises(EngineError, match="Ray container"):
         pb.build_pods_native(broken, [HEAD])
     assert pb.build_pods_native(cluster, []) == []
+
+
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_template_metadata_rides_along(deterministic):
+    """ObjectMeta: podTemplateSpec.ObjectMeta (common/pod.go:598): whatever else the template's metadata carries stays; the worker's name is cleared
+    (:418); the head gets name OR generateName and keeps the other as the template had it (:171-175)."""
+    cluster = instance()
+    for grp in (cluster["spec"]["headGroupSpec"], cluster["spec"]["workerGroupSpecs"][0]):
+        grp["template"]["metadata"] = {"name": "from-template", "generateName": "tpl-", "namespace": "elsewhere", "finalizers": ["example.com/hold"],
+                                       "labels": {"team": "a"}, "annotations": {"note": "x"}}
+    head, worker = build_both(cluster, HEAD, deterministic_head_name=deterministic), build_both(cluster, WORKER, deterministic_head_name=deterministic)
+    native = pb.build_pods_native(cluster, [HEAD, WORKER], pb.BuilderEnv(deterministic_head_name=deterministic))
+    for got, want in zip(native, (head, worker)):
+        order = ["name", "generateName", "namespace", "labels", "annotations", "ownerReferences", "finalizers"]      # metav1.ObjectMeta's declaration order
+        assert got["metadata"] == want["metadata"] and list(got["metadata"]) == [k for k in order if k in got["metadata"]]
+    assert worker["metadata"]["generateName"] == "raycluster-sample-small-group-worker-" and "name" not in worker["metadata"]
+    assert worker["metadata"]["finalizers"] == ["example.com/hold"] and worker["metadata"]["namespace"] == "default" and worker["metadata"]["labels"]["team"] == "a"
+    if deterministic:
+        assert head["metadata"]["name"] == "raycluster-sample-head" and head["metadata"]["generateName"] == "tpl-"
+    else:
+        assert head["metadata"]["name"] == "from-template" and head["metadata"]["generateName"] == "raycluster-sample-head-"
