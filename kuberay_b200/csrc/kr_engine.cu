@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kr_kernels.cuh"
@@ -1517,16 +1518,16 @@ int kr_results_fetch(kr_engine *e, kr_results_view *out) {
   return fetch_results(e, out);
 }
 
-int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, uint32_t n, char *out32xN) {
-  if (!e || (!bytes && n) || !offsets || (!out32xN && n)) return KR_E_INVALID;
+// Digests of n messages given as (pointer, length) pieces: staged 16-byte aligned in pinned memory (the copies run on `threads` host
+// threads when the batch is large), one upload, one SHA-1 launch, digests back.
+static int hash_pieces(kr_engine *e, const uint8_t *const *ptr, const uint64_t *len, uint32_t n, char *out32xN, uint32_t threads) {
   if (n == 0) return KR_OK;
   CK(cudaSetDevice(e->cfg.device));
-  // staging layout: [aligned offsets (n+0) u64 | lens u32 | bytes, each message 16-byte aligned | out 32n]
+  // staging layout: [aligned offsets (n+0) u64 | lens u32 | order u32 | bytes, each message 16-byte aligned | out 32n]
   size_t data = 0;
   for (uint32_t i = 0; i < n; i++) {
-    if (offsets[i + 1] < offsets[i]) return fail(e, KR_E_INVALID, "offsets must be non-decreasing");
-    if (offsets[i + 1] - offsets[i] > 0xFFFFFFFFull) return fail(e, KR_E_CAPACITY, "message %u longer than 4 GiB", i);
-    data += align_up(offsets[i + 1] - offsets[i], 16);
+    if (len[i] > 0xFFFFFFFFull) return fail(e, KR_E_CAPACITY, "message %u longer than 4 GiB", i);
+    data += align_up(len[i], 16);
   }
   size_t o_off = 0, o_len = align_up(8 * (size_t)n), o_ord = align_up(o_len + 4 * (size_t)n), o_data = align_up(o_ord + 4 * (size_t)n), o_out = align_up(o_data + data + 16), total = o_out + 32 * (size_t)n;
   if (total > e->hb_cap) {
@@ -1541,13 +1542,22 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
   uint64_t *so = reinterpret_cast<uint64_t *>(e->hb_h + o_off);
   uint32_t *sl = reinterpret_cast<uint32_t *>(e->hb_h + o_len);
   size_t cur = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    size_t len = offsets[i + 1] - offsets[i];
-    so[i] = cur; sl[i] = (uint32_t)len;
-    memcpy(e->hb_h + o_data + cur, bytes + offsets[i], len);
-    size_t pad = align_up(len, 16) - len;
-    if (pad) memset(e->hb_h + o_data + cur + len, 0, pad);
-    cur += len + pad;
+  for (uint32_t i = 0; i < n; i++) { so[i] = cur; sl[i] = (uint32_t)len[i]; cur += align_up(len[i], 16); }
+  auto fill = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; i++) {
+      uint8_t *dst = e->hb_h + o_data + so[i];
+      if (len[i]) memcpy(dst, ptr[i], len[i]);
+      const size_t pad = align_up(len[i], 16) - len[i];
+      if (pad) memset(dst + len[i], 0, pad);
+    }
+  };
+  threads = std::min<uint32_t>(threads, (uint32_t)(data >> 20) + 1);  // a thread per MiB at most
+  if (threads <= 1) fill(0, n);
+  else {
+    std::vector<std::thread> pool;
+    const uint32_t per = (n + threads - 1) / threads;
+    for (uint32_t t = 0; t < threads; t++) { const uint32_t lo = t * per, hi = std::min(n, lo + per); if (lo < hi) pool.emplace_back(fill, lo, hi); }
+    for (auto &th : pool) th.join();
   }
   // message ids by descending block count, staged behind the lengths
   uint32_t *ord = reinterpret_cast<uint32_t *>(e->hb_h + o_ord);
@@ -1569,6 +1579,18 @@ int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, u
   return KR_OK;
 }
 
+int kr_hash_batch(kr_engine *e, const uint8_t *bytes, const uint64_t *offsets, uint32_t n, char *out32xN) {
+  if (!e || (!bytes && n) || !offsets || (!out32xN && n)) return KR_E_INVALID;
+  if (n == 0) return KR_OK;
+  std::vector<const uint8_t *> ptr(n);
+  std::vector<uint64_t> len(n);
+  for (uint32_t i = 0; i < n; i++) {
+    if (offsets[i + 1] < offsets[i]) return fail(e, KR_E_INVALID, "offsets must be non-decreasing");
+    ptr[i] = bytes + offsets[i]; len[i] = offsets[i + 1] - offsets[i];
+  }
+  return hash_pieces(e, ptr.data(), len.data(), n, out32xN, 1);
+}
+
 // strconv.Atoi: optional sign, decimal digits only, no spaces / underscores, must fit an int
 static bool go_atoi(const char *t, uint32_t len, long long &v) {
   if (!t || len == 0 || len > 19) return false;
@@ -1587,30 +1609,50 @@ int kr_hash_compare_batch(kr_engine *e, const kr_hash_compare_row *rows, uint32_
   if (goal_hash_out32xN) memset(goal_hash_out32xN, 0, 32 * (size_t)n);
   // 1. goal specs -> canonical muted JSON (host), rows that need no hash are settled here
   std::vector<int32_t> msg_of(n, -1);  // row -> message index, -1 = goal hash is ""
-  std::string blob;
-  std::vector<uint64_t> offs{0};
-  for (uint32_t i = 0; i < n; i++) {
-    const kr_hash_compare_row &r = rows[i];
-    equal_out[i] = 2;  // undecided
-    long max_groups = -1;
-    if (r.partial) {
-      long long ng = 0;
-      if (!go_atoi(r.num_worker_groups, r.num_worker_groups_len, ng) || ng < 0 || ng > 0x7FFFFFFF) { equal_out[i] = 1; continue; }  // :1140-1142
-      max_groups = (long)ng;
+  std::vector<std::string> emitted(n);
+  std::vector<uint8_t> has_msg(n, 0);
+  auto emit_rows = [&](uint32_t lo, uint32_t hi) {  // rows are independent: mute + marshal on as many host threads as the batch is worth
+    for (uint32_t i = lo; i < hi; i++) {
+      const kr_hash_compare_row &r = rows[i];
+      equal_out[i] = 2;  // undecided
+      long max_groups = -1;
+      if (r.partial) {
+        long long ng = 0;
+        if (!go_atoi(r.num_worker_groups, r.num_worker_groups_len, ng) || ng < 0 || ng > 0x7FFFFFFF) { equal_out[i] = 1; continue; }  // :1140-1142
+        max_groups = (long)ng;
+      }
+      const int rc = kr_specjson_emit_string(r.goal_spec_json, r.goal_spec_len, true, max_groups, emitted[i], nullptr);
+      if (rc == KR_E_STATE) continue;                                   // fewer goal groups than the cluster has: goal hash stays ""
+      if (rc != KR_OK) { if (r.partial) equal_out[i] = 1; continue; }   // :1151-1153 / the dropped error of :1135
+      has_msg[i] = 1;
     }
-    std::string js;
-    const int rc = kr_specjson_emit_string(r.goal_spec_json, r.goal_spec_len, true, max_groups, js, nullptr);
-    if (rc == KR_E_STATE) continue;                                   // fewer goal groups than the cluster has: goal hash stays ""
-    if (rc != KR_OK) { if (r.partial) equal_out[i] = 1; continue; }   // :1151-1153 / the dropped error of :1135
-    msg_of[i] = (int32_t)(offs.size() - 1);
-    blob += js;
-    offs.push_back(blob.size());
+  };
+  uint32_t emit_threads = 1;
+  {
+    const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t nthreads = std::min<uint32_t>(std::min<uint32_t>(hw, 32u), n / 64u);  // a thread is worth ~64 rows (~2 ms of emitting)
+    emit_threads = std::max(1u, nthreads);
+    if (nthreads <= 1) emit_rows(0, n);
+    else {
+      std::vector<std::thread> pool;
+      const uint32_t per = (n + nthreads - 1) / nthreads;
+      for (uint32_t t = 0; t < nthreads; t++) { const uint32_t lo = t * per, hi = std::min(n, lo + per); if (lo < hi) pool.emplace_back(emit_rows, lo, hi); }
+      for (auto &th : pool) th.join();
+    }
   }
-  // 2. one GPU batch for every digest
-  const uint32_t nmsg = (uint32_t)(offs.size() - 1);
+  std::vector<const uint8_t *> mptr;
+  std::vector<uint64_t> mlen;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!has_msg[i]) continue;
+    msg_of[i] = (int32_t)mptr.size();
+    mptr.push_back(reinterpret_cast<const uint8_t *>(emitted[i].data()));
+    mlen.push_back(emitted[i].size());
+  }
+  // 2. one GPU batch for every digest (the emitted strings go straight into the pinned staging area)
+  const uint32_t nmsg = (uint32_t)mptr.size();
   std::vector<char> digests(32 * (size_t)nmsg);
   if (nmsg) {
-    int rc = kr_hash_batch(e, reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), nmsg, digests.data());
+    int rc = hash_pieces(e, mptr.data(), mlen.data(), nmsg, digests.data(), emit_threads);
     if (rc) return rc;
   }
   // 3. compare with the annotation
