@@ -30,6 +30,10 @@ struct Node {
     for (auto &kv : o) if (kv.first == k) return &kv.second;
     return nullptr;
   }
+  const Node *get(const std::string &k) const {
+    for (auto &kv : o) if (kv.first == k) return &kv.second;
+    return nullptr;
+  }
   void erase(const char *k) {
     o.erase(std::remove_if(o.begin(), o.end(), [&](const std::pair<std::string, Node> &kv) { return kv.first == k; }), o.end());
   }
@@ -86,7 +90,12 @@ struct Parser {
           }
           default: return fail("bad escape");
         }
-      } else out += *p++;
+      } else {
+        const char *q = p + 1;
+        while (q < end && *q != '"' && *q != '\\') q++;
+        out.append(p, q);
+        p = q;
+      }
     }
     if (p >= end) return fail("unterminated string");
     p++;
@@ -107,12 +116,15 @@ struct Parser {
         ws();
         if (p >= end || *p != ':') return fail("expected ':'");
         p++;
-        Node v;
-        if (!value(v, depth + 1)) return false;
-        // a repeated key: the last one wins (encoding/json)
-        bool replaced = false;
-        for (auto &kv : n.o) if (kv.first == k) { kv.second = std::move(v); replaced = true; break; }
-        if (!replaced) n.o.emplace_back(std::move(k), std::move(v));
+        // a repeated key: the last one wins (encoding/json); the value is parsed in place
+        Node *slot = nullptr;
+        for (auto &kv : n.o) if (kv.first == k) { kv.second = Node(); slot = &kv.second; break; }
+        if (!slot) {
+          if (n.o.empty()) n.o.reserve(6);
+          n.o.emplace_back(std::move(k), Node());
+          slot = &n.o.back().second;
+        }
+        if (!value(*slot, depth + 1)) return false;
         ws();
         if (p < end && *p == ',') { p++; continue; }
         if (p < end && *p == '}') { p++; return true; }
@@ -123,9 +135,9 @@ struct Parser {
       n.t = N_ARR; p++; ws();
       if (p < end && *p == ']') { p++; return true; }
       while (true) {
-        Node v;
-        if (!value(v, depth + 1)) return false;
-        n.a.push_back(std::move(v));
+        if (n.a.empty()) n.a.reserve(4);
+        n.a.emplace_back();
+        if (!value(n.a.back(), depth + 1)) return false;
         ws();
         if (p < end && *p == ',') { p++; continue; }
         if (p < end && *p == ']') { p++; return true; }
@@ -154,6 +166,13 @@ inline void go_string(std::string &out, const std::string &s) {  // encoding/jso
   size_t i = 0, n = s.size();
   while (i < n) {
     unsigned char c = (unsigned char)s[i];
+    if (c >= 0x20 && c < 0x80 && c != '"' && c != '\\' && c != '<' && c != '>' && c != '&') {  // the common case: a run of bytes written as they are
+      size_t j = i + 1;
+      while (j < n) { const unsigned char d = (unsigned char)s[j]; if (d < 0x20 || d >= 0x80 || d == '"' || d == '\\' || d == '<' || d == '>' || d == '&') break; j++; }
+      out.append(s, i, j - i);
+      i = j;
+      continue;
+    }
     if (c < 0x80) {
       switch (c) {
         case '"': out += "\\\""; break;
@@ -373,27 +392,65 @@ static const char *const kSchema[] = {
     "LoadBalancerStatus = ingress?raw",
 };
 
-struct Field { std::string name, kind; bool omitempty; };
+// The tables above, compiled once: every kind string becomes a small tree of KindNodes, every struct a vector of Fields.
+enum KindOp : uint8_t { K_RAW, K_MAP, K_MAPQ, K_BOOL, K_INT, K_STRING, K_QUANTITY, K_INTSTR, K_TIME, K_STRUCT, K_PTR, K_ARR };
+struct KindNode { KindOp op; int sub; };  // K_PTR / K_ARR: sub = kind id of the pointee / element; K_STRUCT: sub = type id (-1: not in the tables)
+struct Field { std::string name; int kind; bool omitempty; int inline_type; };  // inline_type >= 0: an embedded struct ("+Type")
 struct Schema {
-  std::map<std::string, std::vector<Field>> types;
+  std::map<std::string, int> type_id;
+  std::vector<std::string> type_name;
+  std::vector<std::vector<Field>> types;
+  std::vector<KindNode> kinds;
+  std::map<std::string, int> kind_id;
+  std::vector<std::string> unknown;  // struct names a kind refers to that no table defines (reported when reached)
+
+  int type_of(const std::string &name) const { auto it = type_id.find(name); return it == type_id.end() ? -1 : it->second; }
+  int compile(const std::string &k) {
+    auto it = kind_id.find(k);
+    if (it != kind_id.end()) return it->second;
+    KindNode kn{K_STRUCT, -1};
+    if (k.compare(0, 2, "[]") == 0) kn = {K_ARR, compile(k.substr(2))};
+    else if (k[0] == '*') kn = {K_PTR, compile(k.substr(1))};
+    else if (k == "raw") kn.op = K_RAW;
+    else if (k == "map") kn.op = K_MAP;
+    else if (k == "mapq") kn.op = K_MAPQ;
+    else if (k == "bool") kn.op = K_BOOL;
+    else if (k == "int") kn.op = K_INT;
+    else if (k == "string") kn.op = K_STRING;
+    else if (k == "quantity") kn.op = K_QUANTITY;
+    else if (k == "intstr") kn.op = K_INTSTR;
+    else if (k == "time") kn.op = K_TIME;
+    else {
+      kn.sub = type_of(k);
+      if (kn.sub < 0) { unknown.push_back(k); kn.sub = -(int)unknown.size() - 1; }  // -(index + 2)
+    }
+    kinds.push_back(kn);
+    kind_id[k] = (int)kinds.size() - 1;
+    return (int)kinds.size() - 1;
+  }
   Schema() {
+    std::vector<std::pair<std::string, std::string>> lines;
     for (const char *line : kSchema) {
       std::string l(line);
-      size_t eq = l.find(" = ");
-      std::string tname = l.substr(0, eq);
-      std::vector<Field> fields;
-      size_t i = eq + 3;
+      const size_t eq = l.find(" = ");
+      lines.emplace_back(l.substr(0, eq), l.substr(eq + 3));
+      type_id[lines.back().first] = (int)type_name.size();
+      type_name.push_back(lines.back().first);
+    }
+    types.resize(lines.size());
+    for (size_t t = 0; t < lines.size(); t++) {
+      const std::string &l = lines[t].second;
+      size_t i = 0;
       while (i < l.size()) {
         size_t j = l.find(' ', i);
         if (j == std::string::npos) j = l.size();
-        std::string tok = l.substr(i, j - i);
+        const std::string tok = l.substr(i, j - i);
         i = j + 1;
         if (tok.empty()) continue;
-        if (tok[0] == '+') { fields.push_back({"", tok, false}); continue; }
-        size_t sep = tok.find_first_of("?:");
-        fields.push_back({tok.substr(0, sep), tok.substr(sep + 1), tok[sep] == '?'});
+        if (tok[0] == '+') { types[t].push_back({"", -1, false, type_of(tok.substr(1))}); continue; }
+        const size_t sep = tok.find_first_of("?:");
+        types[t].push_back({tok.substr(0, sep), compile(tok.substr(sep + 1)), tok[sep] == '?', -1});
       }
-      types[tname] = std::move(fields);
     }
   }
 };
@@ -416,31 +473,39 @@ struct Emitter {
         break;
     }
   }
-  static bool is_scalar_kind(const std::string &k) { return k == "bool" || k == "int" || k == "string" || k == "quantity" || k == "intstr" || k == "time"; }
-  void scalar(const std::string &kind, const Node *n) {
-    if (kind == "bool") out += (n && n->t == N_BOOL && n->b) ? "true" : "false";
-    else if (kind == "int") out += (n && n->t == N_NUM) ? n->s : "0";
-    else if (kind == "string") go_string(out, (n && n->t == N_STR) ? n->s : std::string());
-    else if (kind == "quantity") {
-      std::string text = !n ? "0" : (n->t == N_STR || n->t == N_NUM) ? n->s : "0", canon;
-      go_string(out, canon_quantity(text, canon) ? canon : text);
-    } else if (kind == "intstr") {
-      if (n && n->t == N_STR) go_string(out, n->s);
-      else out += (n && n->t == N_NUM) ? n->s : "0";
-    } else if (kind == "time") {
-      if (n && n->t == N_STR) go_string(out, n->s); else out += "null";
+  static bool is_scalar(KindOp op) { return op >= K_BOOL && op <= K_TIME; }
+  void scalar(KindOp op, const Node *n) {
+    static const std::string kNone;
+    switch (op) {
+      case K_BOOL: out += (n && n->t == N_BOOL && n->b) ? "true" : "false"; break;
+      case K_INT: if (n && n->t == N_NUM) out += n->s; else out += '0'; break;
+      case K_STRING: go_string(out, (n && n->t == N_STR) ? n->s : kNone); break;
+      case K_QUANTITY: {
+        std::string text = !n ? "0" : (n->t == N_STR || n->t == N_NUM) ? n->s : "0", canon;
+        go_string(out, canon_quantity(text, canon) ? canon : text);
+        break;
+      }
+      case K_INTSTR:
+        if (n && n->t == N_STR) go_string(out, n->s);
+        else if (n && n->t == N_NUM) out += n->s; else out += '0';
+        break;
+      case K_TIME: if (n && n->t == N_STR) go_string(out, n->s); else out += "null"; break;
+      default: break;
     }
   }
-  static bool scalar_zero(const std::string &kind, const Node *n) {
+  static bool scalar_zero(KindOp op, const Node *n) {
     if (!n || n->t == N_NULL) return true;
-    if (kind == "bool") return !(n->t == N_BOOL && n->b);
-    if (kind == "int") return n->t != N_NUM || n->s == "0" || n->s == "-0";
-    if (kind == "string") return n->t != N_STR || n->s.empty();
-    if (kind == "time") return n->t != N_STR;
-    return false;  // quantity / intstr are struct values: omitempty never drops them
+    switch (op) {
+      case K_BOOL: return !(n->t == N_BOOL && n->b);
+      case K_INT: return n->t != N_NUM || n->s == "0" || n->s == "-0";
+      case K_STRING: return n->t != N_STR || n->s.empty();
+      case K_TIME: return n->t != N_STR;
+      default: return false;  // quantity / intstr are struct values: omitempty never drops them
+    }
   }
   void string_map(const Node &n, bool quantities) {
     std::vector<const std::pair<std::string, Node> *> items;
+    items.reserve(n.o.size());
     for (auto &kv : n.o) items.push_back(&kv);
     std::sort(items.begin(), items.end(), [](auto *a, auto *b) { return a->first < b->first; });  // bytewise, like encoding/json
     out += '{';
@@ -449,62 +514,68 @@ struct Emitter {
       go_string(out, items[i]->first);
       out += ':';
       const Node &v = items[i]->second;
-      if (quantities) scalar("quantity", &v);
+      if (quantities) scalar(K_QUANTITY, &v);
       else if (v.t == N_STR) go_string(out, v.s);
       else raw(v);
     }
     out += '}';
   }
-  // one value of `kind`; `n` may be null (absent)
-  void value(const std::string &kind, const Node *n) {
+  // one value of kind `k`; `n` may be null (absent)
+  void value(int k, const Node *n) {
+    const KindNode kn = schema().kinds[(size_t)k];
     const bool absent = !n || n->t == N_NULL;
-    if (kind == "raw") { if (absent) out += "null"; else raw(*n); return; }
-    if (kind == "map" || kind == "mapq") {
-      if (absent || n->t != N_OBJ) out += "null"; else string_map(*n, kind == "mapq");
-      return;
+    switch (kn.op) {
+      case K_RAW: if (absent) out += "null"; else raw(*n); return;
+      case K_MAP: case K_MAPQ:
+        if (absent || n->t != N_OBJ) out += "null"; else string_map(*n, kn.op == K_MAPQ);
+        return;
+      case K_ARR:
+        if (absent || n->t != N_ARR) { out += "null"; return; }
+        out += '[';
+        for (size_t i = 0; i < n->a.size(); i++) { if (i) out += ','; value(kn.sub, &n->a[i]); }
+        out += ']';
+        return;
+      case K_PTR: if (absent) out += "null"; else value(kn.sub, n); return;
+      case K_STRUCT: strct_id(kn.sub, absent || n->t != N_OBJ ? nullptr : n); return;
+      default: scalar(kn.op, absent ? nullptr : n); return;
     }
-    if (kind.compare(0, 2, "[]") == 0) {
-      if (absent || n->t != N_ARR) { out += "null"; return; }
-      const std::string elem = kind.substr(2);
-      out += '[';
-      for (size_t i = 0; i < n->a.size(); i++) { if (i) out += ','; value(elem, &n->a[i]); }
-      out += ']';
-      return;
-    }
-    if (kind[0] == '*') { if (absent) out += "null"; else value(kind.substr(1), n); return; }
-    if (is_scalar_kind(kind)) { scalar(kind, absent ? nullptr : n); return; }
-    strct(kind, absent || n->t != N_OBJ ? nullptr : n);
   }
   // does `omitempty` drop this field?
-  bool omitted(const std::string &kind, const Node *n) {
+  bool omitted(int k, const Node *n) {
+    const KindNode kn = schema().kinds[(size_t)k];
     const bool absent = !n || n->t == N_NULL;
-    if (kind == "raw") return absent || (n->t == N_ARR && n->a.empty()) || (n->t == N_OBJ && n->o.empty()) || (n->t == N_STR && n->s.empty()) ||
-                              (n->t == N_BOOL && !n->b) || (n->t == N_NUM && n->s == "0");
-    if (kind[0] == '*') return absent;
-    if (kind == "map" || kind == "mapq") return absent || n->t != N_OBJ || n->o.empty();
-    if (kind.compare(0, 2, "[]") == 0) return absent || n->t != N_ARR || n->a.empty();
-    if (is_scalar_kind(kind)) return scalar_zero(kind, n);
-    return false;  // a struct value is never empty for encoding/json
+    switch (kn.op) {
+      case K_RAW: return absent || (n->t == N_ARR && n->a.empty()) || (n->t == N_OBJ && n->o.empty()) || (n->t == N_STR && n->s.empty()) ||
+                         (n->t == N_BOOL && !n->b) || (n->t == N_NUM && n->s == "0");
+      case K_PTR: return absent;
+      case K_MAP: case K_MAPQ: return absent || n->t != N_OBJ || n->o.empty();
+      case K_ARR: return absent || n->t != N_ARR || n->a.empty();
+      case K_STRUCT: return false;  // a struct value is never empty for encoding/json
+      default: return scalar_zero(kn.op, n);
+    }
   }
-  void fields_of(const std::string &tname, const Node *n, bool &first) {
-    auto it = schema().types.find(tname);
-    if (it == schema().types.end()) { err = "unknown type " + tname; return; }
-    for (const Field &f : it->second) {
-      if (f.kind[0] == '+') { fields_of(f.kind.substr(1), n, first); continue; }
-      const Node *v = n ? n->get(f.name.c_str()) : nullptr;
+  void fields_of(int type, const Node *n, bool &first) {
+    if (type < 0) { err = "unknown type " + (type <= -2 ? schema().unknown[(size_t)(-type - 2)] : std::string("?")); return; }
+    for (const Field &f : schema().types[(size_t)type]) {
+      if (f.kind < 0) { fields_of(f.inline_type, n, first); continue; }  // an embedded struct
+      const Node *v = n ? n->get(f.name) : nullptr;
       if (f.omitempty && omitted(f.kind, v)) continue;
       if (!first) out += ',';
       first = false;
-      go_string(out, f.name);
-      out += ':';
+      out += '"'; out += f.name; out += "\":";  // field names are plain identifiers: nothing to escape
       value(f.kind, v);
     }
   }
-  void strct(const std::string &tname, const Node *n) {
+  void strct_id(int type, const Node *n) {
     out += '{';
     bool first = true;
-    fields_of(tname, n, first);
+    fields_of(type, n, first);
     out += '}';
+  }
+  void strct(const std::string &tname, const Node *n) {
+    const int t = schema().type_of(tname);
+    if (t < 0) { out += "{}"; err = "unknown type " + tname; return; }
+    strct_id(t, n);
   }
 };
 

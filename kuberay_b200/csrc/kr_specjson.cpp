@@ -75,6 +75,7 @@ int emit_impl(const uint8_t *spec_json, uint64_t len, bool muted, std::string &o
   }
   if (muted) mute(root);
   Emitter em;
+  em.out.reserve((size_t)len + 64);
   em.strct("RayClusterSpec", &root);
   if (!em.err.empty()) { g_err = "kr_spec_json: " + em.err; return KR_E_INVALID; }
   out.swap(em.out);
