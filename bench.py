@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--allgather", action="store_true", help="also all-gather the per-group delta records over NCCL each step (N>1)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: the workload per GPU (default); strong: the workload once, split over the GPUs")
     ap.add_argument("--no-pack-leg", action="store_true", help="skip the e2e_with_pack leg (tools/pack_bench)")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the f2-f4 extras (tools/f4_bench.py, tools/f3_bench.py --quick)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -571,6 +572,18 @@ def main():
                             "given beside it, and the last figure puts it ON the critical path"}
             except Exception as ex:  # noqa: BLE001
                 line["e2e_with_pack"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+        if world == 1 and not args.no_next_rows:
+            # the rows either side of the hot path, measured by their own tools on this box: the batched RayService hash
+            # comparison (GPU SHA-1 behind a host thread pool) and the host-side builders (one thread)
+            nxt = {}
+            for key, cmd in (("f4_hash_compare", [sys.executable, os.path.join(ROOT, "tools", "f4_bench.py"), "2000"]),
+                             ("f2_f3_host_builders", [sys.executable, os.path.join(ROOT, "tools", "f3_bench.py"), "--quick"])):
+                try:
+                    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+                    nxt[key] = json.loads(out.stdout.strip().splitlines()[-1])
+                except Exception as ex:  # noqa: BLE001
+                    nxt[key] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+            line["next_rows"] = nxt
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             arm = CpuArm(snap)

@@ -132,6 +132,14 @@ def pod_build(n, reps):
     return run
 
 
+if "--quick" in sys.argv:  # bench.py's extra: the one-call whole-Pod builder and the muted-spec emitter only
+    print(json.dumps({"whole_pod_manifests_per_s_kr_pod_build_1000_per_call": round(timed(pod_build(1000, 5), 5 * 1000)),
+                      "whole_pod_manifests_per_s_kr_pod_build_10_per_call": round(timed(pod_build(10, 100), 100 * 10)),
+                      "whole_pod_manifest_bytes": len(podbuilder.build_pods_native(full, [(0, 0, 0, "")], raw=True)[0]),
+                      "muted_spec_json_emits_per_s": round(timed(lambda: [spec_json_emit(spec) for _ in range(500)], 500)), "muted_spec_json_input_bytes": len(spec),
+                      "threads_used": 1}))
+    sys.exit(0)
+
 out = {"host": os.uname().nodename, "cpus": os.cpu_count(), "threads_used": 1,
        "pod_meta_patches_per_s": round(timed(meta, 50 * N)), "pod_meta_bytes_per_patch": need.value and int(off[N] / N),
        "ray_start_commands_per_s": round(timed(start_cmd, 20000)), "container_env_lists_per_s": round(timed(env, 20000)),
