@@ -14,7 +14,36 @@ static uint32_t pod_word(uint32_t node_type, uint32_t phase, uint32_t ready) {
   return (node_type << KR_PP_NODE_TYPE_SHIFT) | (phase << KR_PP_PHASE_SHIFT) | (ready << KR_PP_READY_SHIFT);
 }
 
+/* The host-side builders need no device: one worker Pod manifest for a RayCluster given as JSON (kr_pod_build). */
+static int host_builders(void) {
+  const char cluster[] =
+      "{\"metadata\":{\"name\":\"rc\",\"namespace\":\"ns\",\"uid\":\"u-1\"},\"spec\":{\"headGroupSpec\":{\"rayStartParams\":{},\"template\":{\"spec\":{\"containers\":[{\"name\":\"h\",\"image\":\"ray:2\"}]}}},"
+      "\"workerGroupSpecs\":[{\"groupName\":\"g\",\"rayStartParams\":{},\"template\":{\"spec\":{\"containers\":[{\"name\":\"w\",\"image\":\"ray:2\",\"resources\":{\"limits\":{\"cpu\":\"2\",\"memory\":\"1Gi\"}}}]}}}]}}";
+  static uint8_t out[16384];
+  kr_podbuild_env env;
+  kr_podmeta_create tuple;
+  uint64_t off[2], need = 0;
+  memset(&env, 0, sizeof env);
+  memset(&tuple, 0, sizeof tuple);
+  env.kuberay_version.p = "v1.5.0"; env.kuberay_version.n = 6; env.gate_multihost_indexing = 1;
+  tuple.group = 0; tuple.replica_index = 3; tuple.replica_name.p = ""; tuple.replica_name.n = 0;
+  if (kr_pod_build((const uint8_t *)cluster, sizeof cluster - 1, &env, &tuple, 1, out, sizeof out - 1, off, &need) != KR_OK) {
+    printf("kr_pod_build: %s\n", kr_pod_build_last_error());
+    return 1;
+  }
+  out[need] = 0;
+  if (off[0] != 0 || off[1] != need || strncmp((const char *)out, "{\"kind\":\"Pod\",\"apiVersion\":\"v1\",\"metadata\":{\"generateName\":\"rc-g-worker-\"", 72) != 0 ||
+      !strstr((const char *)out, "ray start  --address=rc-head-svc.ns.svc.cluster.local:6379 ") || !strstr((const char *)out, "\"ray.io/worker-group-replica-index\":\"3\"") ||
+      !strstr((const char *)out, "--num-cpus=2 ") || !strstr((const char *)out, "\"name\":\"wait-gcs-ready\"")) {
+    printf("kr_pod_build wrote an unexpected manifest:\n%s\n", (const char *)out);
+    return 1;
+  }
+  printf("host builders from C: OK (%lu-byte worker manifest)\n", (unsigned long)need);
+  return 0;
+}
+
 int main(void) {
+  if (host_builders()) return 1;
   int ndev = kr_device_count();
   if (ndev <= 0) { printf("no CUDA device (kr_device_count = %d): the engine refuses to run, as documented\n", ndev); return 0; }
 
