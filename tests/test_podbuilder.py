@@ -411,7 +411,7 @@ def test_native_builder_errors():
 @pytest.mark.parametrize("deterministic", [False, True])
 def test_template_metadata_rides_along(deterministic):
     """ObjectMeta: podTemplateSpec.ObjectMeta (common/pod.go:598): whatever else the template's metadata carries stays; the worker's name is cleared
-    (:418); the head gets name OR generateName and keeps the other as the template had it (:171-175)."""
+    (:418, TestDefaultWorkerPodTemplateWithName pod_test.go:1313-1327); the head gets name OR generateName and keeps the other as the template had it (:171-175)."""
     cluster = instance()
     for grp in (cluster["spec"]["headGroupSpec"], cluster["spec"]["workerGroupSpecs"][0]):
         grp["template"]["metadata"] = {"name": "from-template", "generateName": "tpl-", "namespace": "elsewhere", "finalizers": ["example.com/hold"],
