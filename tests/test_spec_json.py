@@ -252,3 +252,33 @@ def test_hash_compare_batch_is_cluster_spec_hash_equal():
         eng.close()
     assert got == want, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w]
     assert hashes[1] == base_hash and hashes[3] == base_hash and hashes[2] != base_hash and hashes[len(IS_EQUAL_TABLE) + 3] == ""
+
+
+# ---- property: arbitrary JSON through the parser and Go's string encoder ------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_json_leaf = st.one_of(st.none(), st.booleans(), st.integers(min_value=-2**53, max_value=2**53), st.text(max_size=40))
+_json_value = st.recursive(_json_leaf, lambda inner: st.one_of(st.lists(inner, max_size=5), st.dictionaries(st.text(max_size=12), inner, max_size=5)), max_leaves=40)
+
+
+@settings(max_examples=300, deadline=None)
+@given(payload=st.lists(_json_value, min_size=1, max_size=4), ascii_only=st.booleans())
+def test_any_json_survives_the_parser_and_the_go_string_encoder(payload, ascii_only):
+    """A field the tables leave untyped (`ephemeralContainers`, kind raw) carries arbitrary JSON: whatever the parser read must come back, value for
+    value, through the emitter — escapes (\\uXXXX input, HTML-safe output), multi-byte UTF-8, astral code points, control characters, nesting,
+    repeated structure — and the output must stay valid JSON that encoding/json would have produced (no raw <, >, &, U+2028/9)."""
+    spec = {"headGroupSpec": {"rayStartParams": {}, "template": {"spec": {"containers": [{"name": "c"}], "ephemeralContainers": payload}}}}
+    text = json.dumps(spec, ensure_ascii=ascii_only).encode("utf-8", "surrogatepass") if ascii_only else json.dumps(spec, ensure_ascii=False).encode("utf-8", "surrogatepass")
+    try:
+        text.decode("utf-8")
+    except UnicodeDecodeError:
+        return  # a lone surrogate written raw is not UTF-8: not a case the API server can produce
+    out = engine.spec_json_emit(text)
+    back = json.loads(out)["headGroupSpec"]["template"]["spec"]["ephemeralContainers"]
+    want = json.loads(text)["headGroupSpec"]["template"]["spec"]["ephemeralContainers"]
+    # a lone surrogate escape decodes to U+FFFD in Go
+    fix = lambda v: (v.encode("utf-16", "surrogatepass").decode("utf-16", "replace") if isinstance(v, str) else  # noqa: E731
+                     [fix(x) for x in v] if isinstance(v, list) else {fix(k): fix(x) for k, x in v.items()} if isinstance(v, dict) else v)
+    assert back == fix(want)
+    assert not any(ch in out for ch in (b"<", b">", b"&", " ".encode(), " ".encode()))
+    assert engine.spec_json_emit(out) == out                  # and the canonical bytes are a fixed point
