@@ -67,7 +67,8 @@ def test_struct_literals_name_real_fields():
     checked = 0
     for path in GO_FILES:
         for src in re.split(r"\nfunc ", open(path).read())[1:]:      # one function at a time: short variable names are reused across functions
-            for var, typ in re.findall(r"\b([a-z][A-Za-z0-9]*)\s*:=\s*C\.(kr_[a-z_0-9]+)\{", src) + re.findall(r"\bvar\s+([a-z][A-Za-z0-9]*)\s+C\.(kr_[a-z_0-9]+)\b", src):
+            for var, typ in re.findall(r"\b([a-z][A-Za-z0-9]*)\s*:=\s*C\.(kr_[a-z_0-9]+)\{", src) + re.findall(r"\bvar\s+([a-z][A-Za-z0-9]*)\s+C\.(kr_[a-z_0-9]+)\b", src) + \
+                    re.findall(r"[(,]\s*([a-z][A-Za-z0-9]*)\s+\*C\.(kr_[a-z_0-9]+)\b", src.split("{", 1)[0]):
                 if not re.search(r"typedef struct " + typ + r"\s*\{", HEADER):
                     continue
                 fields = struct_fields(typ)
