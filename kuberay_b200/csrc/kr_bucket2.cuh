@@ -27,7 +27,10 @@ namespace kr {
 
 __device__ __forceinline__ uint32_t inc_epoch_of(const ScratchDev &sc) { return __ldcg(&sc.inc[KR_INC_EPOCH]) + 1u; }  // stamp value of the running incremental epoch (kr_incr.cuh)
 
-static constexpr int kD2Warps = 8;  // RayClusters per k_decide2 CTA
+#ifndef KR_D2WARPS
+#define KR_D2WARPS 8
+#endif
+static constexpr int kD2Warps = KR_D2WARPS;  // RayClusters per k_decide2 CTA
 #define KR_ROW_UNHEALTHY (1u << 13)  // bucket record word: shouldDeletePod(pod) (k_match2 evaluates it once per pod)
 #define KR_ROW_FRESH (1u << 14)      // bucket record word: appended by k_inc_admit in the running incremental epoch (cleared by the decide warp)
 
@@ -175,7 +178,7 @@ struct Decide2Args {
 // arrival order) sits in registers.  Multi-host groups never reach this kernel.
 // kInc: the instantiation an incremental epoch launches (phase 2 only); the instantiation of the full pass carries none of its code.
 template <int K, bool kInc = false>
-__global__ void __launch_bounds__(kD2Warps * 32, K <= 4 ? 4 : 2) k_decide2(Decide2Args a) {
+__global__ void __launch_bounds__(kD2Warps * 32, (K <= 4 ? 32 : 16) / kD2Warps) k_decide2(Decide2Args a) {
   const int phase = kInc ? 2 : a.phase;
   KR_TL(phase ? 12 : 3);
   __shared__ int32_t s_acc[kD2Warps][3][KR_SMEM_GROUPS];   // n_list, n_unhealthy, n_wtd_own per group
