@@ -254,6 +254,43 @@ def test_hash_compare_batch_is_cluster_spec_hash_equal():
     assert hashes[1] == base_hash and hashes[3] == base_hash and hashes[2] != base_hash and hashes[len(IS_EQUAL_TABLE) + 3] == ""
 
 
+@pytest.mark.gpu
+def test_hash_compare_batch_in_bulk():
+    """Enough rows for the emit thread pool and the multi-threaded staging copy (>= 64 rows per thread), every decision and digest against
+    the row-by-row form (native emitter + hashlib) — including rows the host settles without a digest, interleaved."""
+    from kuberay_b200.engine import Engine
+    rng = random.Random(7)
+    rows, want_eq, want_hash = [], [], []
+    for i in range(700):
+        groups = [{"groupName": f"g{k}", "replicas": rng.randint(0, 9), "rayStartParams": {}, "template": {"spec": {"containers": [
+            {"name": "w", "image": f"ray:{i % 13}", "env": [{"name": f"E{j}", "value": "x" * rng.randint(0, 40)} for j in range(rng.randint(0, 30))]}]}}} for k in range(rng.randint(0, 3))]
+        spec = {"rayVersion": f"2.{i % 7}", "headGroupSpec": {"rayStartParams": {}, "template": {"spec": {"containers": [{"name": "h", "image": "ray"}]}}}, "workerGroupSpecs": groups}
+        text = json.dumps(spec).encode()
+        kind = rng.choice(["equal", "stale", "partial", "partial-short", "bad-atoi", "bad-json"])
+        full = base64.b32hexencode(hashlib.sha1(engine.spec_json_emit(text)).digest()).decode()
+        if kind == "equal":
+            rows.append((text, full, None, False)); want_eq.append(True); want_hash.append(full)
+        elif kind == "stale":
+            rows.append((text, "0" * 32, None, False)); want_eq.append(False); want_hash.append(full)
+        elif kind == "partial":          # the cluster was created from the first k groups
+            k = rng.randint(0, len(groups))
+            cut = dict(spec, workerGroupSpecs=groups[:k])
+            h = base64.b32hexencode(hashlib.sha1(engine.spec_json_emit(json.dumps(cut).encode())).digest()).decode()
+            rows.append((text, h, str(k), True)); want_eq.append(True); want_hash.append(h)
+        elif kind == "partial-short":    # the cluster has MORE groups than the goal: goal hash stays ""
+            rows.append((text, full, str(len(groups) + 1), True)); want_eq.append(False); want_hash.append("")
+        elif kind == "bad-atoi":
+            rows.append((text, full, "x1", True)); want_eq.append(True); want_hash.append("")
+        else:
+            rows.append((b"{" + text, "", None, False)); want_eq.append(True); want_hash.append("")
+    eng = Engine(0, max_clusters=1)
+    try:
+        got, hashes = eng.hash_compare_batch(rows)
+    finally:
+        eng.close()
+    assert got == want_eq and hashes == want_hash
+
+
 # ---- property: arbitrary JSON through the parser and Go's string encoder ------------------------------------------------------------
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
