@@ -277,6 +277,8 @@ def test_hash_batch_matches_hashlib():
         eng.close()
     want = [base64.b32hexencode(hashlib.sha1(m).digest()).decode() for m in msgs]
     assert got == want
+    from oracle import oracle as _oracle
+    assert got[:40] == [_oracle.hash32(m) for m in msgs[:40]]      # and the oracle's own SHA-1 / base32hex (kr_oracle_hash32) agrees with both
 
 
 def test_hash_batch_and_passes_share_an_engine(oracle_mod):
