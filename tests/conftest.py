@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    # a fresh checkout has no built libraries (they are git-ignored): build what is MISSING once, up front (nvcc cross-compiles without a GPU);
+    # an existing library is never rebuilt from here — that is __graft_entry__.build()'s job
+    from kuberay_b200 import engine
+    if not os.path.exists(engine.LIB_PATH) and not os.environ.get("KR_HOST_ONLY_LIB"):
+        engine.build()          # (the oracle's library builds itself on first use)
 
 
 @pytest.fixture(scope="session")
