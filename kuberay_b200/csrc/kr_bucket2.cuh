@@ -166,8 +166,14 @@ __global__ void __launch_bounds__(kSortThreads) k_match2(SnapDev s, ScratchDev s
 
 // ------------------------------------------------------------------------------------------------ k_decide2
 
+// Incremental epochs: the changed records, packed for one small D2H copy — per dirty cluster {idx, act_start, act_cnt, group_off,
+// group_cnt, first staged group record}, its kr_cluster_result, and its groups' kr_group_result records back to back.  Entry i belongs
+// to dirty_list[i]; the decide warp of that cluster writes it when it is done (k_decide2<K, true>).
+struct IncStage { uint32_t *meta; kr_cluster_result *clusters; kr_group_result *groups; uint32_t cap_clusters, cap_groups; };
+
 struct Decide2Args {
   SnapDev s; ScratchDev sc; ResDev r; Sizes n; kr_flags f;
+  IncStage st;  // phase 2 only
   uint32_t create_cap;
   int spin_hash;  // phase 0: a cluster whose Recreate gate reads a digest waits for the concurrently running hash kernel (no phase 1)
   int phase;  // 0: every RayCluster; 1: only the clusters phase 0 deferred (Recreate gate waiting for the hash kernel);
@@ -669,6 +675,32 @@ __global__ void __launch_bounds__(kD2Warps * 32, (K <= 4 ? 32 : 16) / kD2Warps) 
   } else if (G) {
     // no pod to create: every group of the cluster still gets its (empty) place in the arena
     for (uint32_t gi = lane; gi < G; gi += 32) { a.r.groups[g0 + gi].create_off = create_off; a.sc.gcreate[g0 + gi] = create_off; }
+  }
+  if (kInc) {
+    // the cluster's records as they now stand in the result arrays, packed at its place in the dirty list (the host copies the whole
+    // arrays instead when the list outgrew the staging area)
+    __syncwarp();  // this warp's own stores to r.clusters / r.groups above are ordered before the loads below
+    const uint32_t n_dirty = __ldcg(&a.sc.inc[KR_INC_DIRTY]);
+    if (n_dirty <= a.st.cap_clusters) {
+      const uint32_t i = blockIdx.x * kD2Warps + warp;
+      uint32_t at = 0;
+      if (lane == 0) at = atomicAdd(&a.sc.inc[KR_INC_GROUPS], G);
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      if (lane == 0) {
+        uint32_t *m = a.st.meta + 8 * (size_t)i;
+        m[0] = c; m[1] = act_off; m[2] = n_act; m[3] = g0; m[4] = G; m[5] = at; m[6] = 0; m[7] = 0;
+      }
+      static_assert(sizeof(kr_cluster_result) % 4 == 0 && sizeof(kr_cluster_result) / 4 <= 32 && sizeof(kr_group_result) % 4 == 0, "record sizes");
+      const uint32_t *csrc = reinterpret_cast<const uint32_t *>(&a.r.clusters[c]);
+      uint32_t *cdst = reinterpret_cast<uint32_t *>(&a.st.clusters[i]);
+      if (lane < sizeof(kr_cluster_result) / 4) cdst[lane] = __ldcg(csrc + lane);
+      if ((uint64_t)at + G <= a.st.cap_groups) {
+        const uint32_t words = G * (uint32_t)(sizeof(kr_group_result) / 4);
+        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(&a.r.groups[g0]);
+        uint32_t *gdst = reinterpret_cast<uint32_t *>(&a.st.groups[at]);
+        for (uint32_t w = lane; w < words; w += 32) gdst[w] = __ldcg(gsrc + w);
+      }
+    }
   }
 }
 

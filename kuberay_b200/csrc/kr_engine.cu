@@ -469,7 +469,7 @@ int launch_pass(kr_engine *e, const kr_flags &f, bool profile, bool capturing = 
       mark("k_match2");
       CK(launch_pdl(k_match2<kMatchItems>, dim3(mtiles), dim3(kSortThreads), n.n_wtd ? e->sl.wt_bits_n / 8 : 0, M, pdl, s, sc, r, z, n.n_wtd ? 1 : 0));
     }
-    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, spin ? 1 : 0, 0};
+    Decide2Args da{s, sc, r, z, f, IncStage{}, e->cfg.max_creates, spin ? 1 : 0, 0};
     auto launch_decide2 = [&](dim3 grid, bool with_pdl) -> cudaError_t {
       if (e->bstride <= 64) return launch_pdl(k_decide2<2>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
       if (e->bstride <= 128) return launch_pdl(k_decide2<4>, grid, dim3(kD2Warps * 32), 0, M, with_pdl, da);
@@ -682,21 +682,12 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
     k_inc_aux_clear<<<std::min<uint32_t>(grid, (e->sl.aux_slots + 255) / 256), 256, 0, M>>>(sc);
     k_inc_aux_insert<<<std::min<uint32_t>(grid, (n.n_heads + 255) / 256 + 1), 256, 0, M>>>(s, sc, z);
   }
-  mark("k_inc_refresh");
-  k_inc_refresh<<<std::min<uint32_t>(grid, (n.n_clusters + 255) / 256 + 1), 256, 0, M>>>(s, sc);
+  // (k_inc_refresh ran behind the object commits' diff kernels: the input records are current)
   mark("k_inc_admit");
   k_inc_admit<<<grid, 256, 0, M>>>(s, sc, r, z, n.n_wtd ? 1 : 0);
   if (do_hash && !profile) CK(cudaStreamWaitEvent(M, e->ev_hash, 0));
-  if (n.n_clusters) {
-    Decide2Args da{s, sc, r, z, f, e->cfg.max_creates, 0, 2};
-    const dim3 dgrid((n.n_clusters + kD2Warps - 1) / kD2Warps), dblock(kD2Warps * 32);
-    mark("k_decide2_dirty");
-    if (e->bstride <= 64) k_decide2<2, true><<<dgrid, dblock, 0, M>>>(da);
-    else if (e->bstride <= 128) k_decide2<4, true><<<dgrid, dblock, 0, M>>>(da);
-    else k_decide2<8, true><<<dgrid, dblock, 0, M>>>(da);
-  }
-  if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
   // staging for the changed records: up to a quarter of the RayClusters (beyond that the whole record arrays are as cheap to move)
+  IncStage st{};
   {
     const uint32_t capc = std::max<uint32_t>(64, n.n_clusters / 4), capg = (uint32_t)std::min<uint64_t>((uint64_t)capc * KR_SMEM_GROUPS, (uint64_t)n.n_groups + 1);
     const size_t need = align_up(32 * (size_t)capc) + align_up(sizeof(kr_cluster_result) * (size_t)capc) + sizeof(kr_group_result) * (size_t)capg + 1024;
@@ -709,14 +700,20 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
       e->inc_stage_cap = need;
     }
     e->inc_stage_clusters = capc; e->inc_stage_groups = capg;
-    IncStage st;
     st.meta = reinterpret_cast<uint32_t *>(e->d_inc_stage);
     st.clusters = reinterpret_cast<kr_cluster_result *>(e->d_inc_stage + align_up(32 * (size_t)capc));
     st.groups = reinterpret_cast<kr_group_result *>(e->d_inc_stage + align_up(32 * (size_t)capc) + align_up(sizeof(kr_cluster_result) * (size_t)capc));
     st.cap_clusters = capc; st.cap_groups = capg;
-    mark("k_inc_gather");
-    k_inc_gather<<<std::min<uint32_t>(grid, (capc + 255) / 256), 256, 0, M>>>(s, sc, r, st);
   }
+  if (n.n_clusters) {
+    Decide2Args da{s, sc, r, z, f, st, e->cfg.max_creates, 0, 2};
+    const dim3 dgrid((n.n_clusters + kD2Warps - 1) / kD2Warps), dblock(kD2Warps * 32);
+    mark("k_decide2_dirty");
+    if (e->bstride <= 64) k_decide2<2, true><<<dgrid, dblock, 0, M>>>(da);
+    else if (e->bstride <= 128) k_decide2<4, true><<<dgrid, dblock, 0, M>>>(da);
+    else k_decide2<8, true><<<dgrid, dblock, 0, M>>>(da);
+  }
+  if (n.n_jobs) { mark("k_jobs"); k_jobs<<<(n.n_jobs + 255) / 256, 256, 0, M>>>(s, sc, r, z); }
   if (profile && k <= KR_MAX_KERNEL_TIMES) cudaEventRecord(e->ev_k[k < KR_MAX_KERNEL_TIMES ? k : KR_MAX_KERNEL_TIMES], M);
   e->prof.n_kernels = (uint32_t)k;
   if (done) CK(cudaEventRecord(done, M));
@@ -984,7 +981,7 @@ int kr_engine_create(const kr_config *cfg, kr_engine **out) {
                         (const void *)k_match2<kMatchItems>, (const void *)k_decide2<2>, (const void *)k_decide2<4>, (const void *)k_decide2<8>, (const void *)k_hash3<1, 0>,
                         (const void *)k_inc_retire, (const void *)k_inc_objects, (const void *)k_inc_objects_keys, (const void *)k_inc_aux_clear, (const void *)k_inc_aux_insert,
                         (const void *)k_inc_mark_recreate, (const void *)k_decide2<2, true>, (const void *)k_decide2<4, true>, (const void *)k_decide2<8, true>, (const void *)k_inc_refresh, (const void *)k_inc_admit,
-                        (const void *)k_inc_gather, (const void *)k_inc_finish};
+                        (const void *)k_inc_finish};
     for (const void *k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   if (const char *g = getenv("KR_NO_GRAPH")) e->use_graph = !(g[0] == '1');
@@ -1235,6 +1232,8 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
     Sizes zz{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
     if (first) k_inc_objects<<<(first + 255) / 256, 256, 0, e->scopy>>>(oa, sd, scd, zz);
     if (n.n_heads) k_inc_objects_keys<<<(n.n_heads + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n.n_heads, nullptr);
+    // the input records (cl_in) of the RayClusters the diff found changed, now that every column of theirs is in place
+    if (n.n_clusters) k_inc_refresh<<<std::min<uint32_t>((uint32_t)e->sm_count * 2, (n.n_clusters + 255) / 256 + 1), 256, 0, e->scopy>>>(sd, scd);
     CK(cudaGetLastError());
   }
   if (parts & (KR_PART_COLUMNS | KR_PART_OBJECTS)) {
@@ -1422,6 +1421,7 @@ int kr_snapshot_commit_object_rows(kr_engine *e, const uint32_t *cluster_rows, u
   Sizes zz{n.n_clusters, n.n_groups, n.n_wtd, n.n_pods, n.n_heads, n.n_jobs};
   if (first) k_inc_objects<<<(first + 255) / 256, 256, 0, e->scopy>>>(oa, sd, scd, zz);
   if (n_hd) k_inc_objects_keys<<<(n_hd + 255) / 256, 256, 0, e->scopy>>>(oa.h_pod_idx_new, const_cast<uint32_t *>(sd.h_pod_idx), n_hd, reinterpret_cast<const uint32_t *>(e->orow_d + list_off[D_HEADS]));
+  if (n_cl) k_inc_refresh<<<std::min<uint32_t>((uint32_t)e->sm_count * 2, (n.n_clusters + 255) / 256 + 1), 256, 0, e->scopy>>>(sd, scd);  // (see kr_snapshot_commit_parts)
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev_h2d1, e->scopy));
   CK(cudaEventRecord(e->ev_cols, e->scopy));

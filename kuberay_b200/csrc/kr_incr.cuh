@@ -14,11 +14,12 @@
 // The pass then touches only what changed:
 //   k_inc_admit    (one thread per touched row) runs the selector match of k_match2 on the row's NEW values and appends the
 //                  record (marked KR_ROW_FRESH) to its RayCluster's bucket — marking that RayCluster dirty as well;
-//   k_inc_refresh  rewrites the 128-byte input record of the RayClusters whose RayCluster / group rows changed;
+//   k_inc_refresh  (launched by the object commit itself, behind its diff kernel) rewrites the 128-byte input record of the RayClusters whose
+//                  RayCluster / group rows changed;
 //   k_decide2<K>   phase 2: the decide kernel over the dirty list.  Each warp first drops the records of stamped rows from its bucket (stored back compacted, arrival order
 //                  kept) and recomputes the first head; then decides as in a full pass (digests are resident, so the Recreate
 //                  gate is decided in place); a cluster keeps its places in the action list / create arena while they suffice;
-//   k_inc_gather   packs the changed cluster / group records for one small D2H copy.
+//                  and packs the cluster's changed records for one small D2H copy (IncStage).
 // Results are bit-identical to a full pass over the same state (tests/test_live_arena.py, tests/test_packer.py run every epoch
 // against the oracle); anything the resident state cannot absorb — structural object changes, a bucket or arena overflow — voids
 // the attempt and the engine takes the full pass instead.
@@ -248,25 +249,8 @@ __global__ void __launch_bounds__(256) k_inc_admit(SnapDev s, ScratchDev sc, Res
   }
 }
 
-// ------------------------------------------------------------------------------------------------ k_inc_gather / k_inc_finish
-// The changed records, packed for one small D2H copy: per dirty cluster {idx, act_start, act_cnt, group_off, group_cnt, first
-// staged group record}, its kr_cluster_result, and its groups' kr_group_result records back to back.
-struct IncStage { uint32_t *meta; kr_cluster_result *clusters; kr_group_result *groups; uint32_t cap_clusters, cap_groups; };
-
-__global__ void __launch_bounds__(256) k_inc_gather(SnapDev s, ScratchDev sc, ResDev r, IncStage st) {
-  const uint32_t n_dirty = __ldcg(&sc.inc[KR_INC_DIRTY]);
-  if (n_dirty > st.cap_clusters) return;  // the host copies the whole record arrays instead
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_dirty; i += gridDim.x * blockDim.x) {
-    const uint32_t c = sc.dirty_list[i];
-    const uint32_t g0 = s.c_group_off[c], G = s.c_group_cnt[c];
-    const uint32_t at = atomicAdd(&sc.inc[KR_INC_GROUPS], G);
-    uint32_t *m = st.meta + 8 * (size_t)i;
-    m[0] = c; m[1] = r.act_start[c]; m[2] = r.act_cnt[c]; m[3] = g0; m[4] = G; m[5] = at; m[6] = 0; m[7] = 0;
-    st.clusters[i] = r.clusters[c];
-    if ((uint64_t)at + G <= st.cap_groups)
-      for (uint32_t gi = 0; gi < G; gi++) st.groups[at + gi] = r.groups[g0 + gi];
-  }
-}
+// ------------------------------------------------------------------------------------------------ k_inc_finish
+// (The changed records are packed for the host by the decide warps themselves: IncStage in kr_bucket2.cuh.)
 
 // closes the epoch (after the host's copy of the counters was enqueued): next epoch's stamps differ from every stamp written so far
 __global__ void k_inc_finish(ScratchDev sc) {

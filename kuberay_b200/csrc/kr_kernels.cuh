@@ -23,8 +23,9 @@
 //   (buckets restored to List order by an in-register bitonic sort), and for RayClusters with > 1024 pods the RADIX pipeline
 //   (k_match<radix>, k_hist, k_scan_rows, k_scatter: stable LSD sort) with the unfused scan kernels.
 // INCREMENTAL epochs (kr_incr.cuh, included by kr_engine.cu): after a full bucket pass everything stays resident; pod-row commits
-// run k_inc_retire on the rows' old values, object commits are diffed on the device (k_inc_objects), and the pass is
-//   k_inc_refresh -> k_inc_admit -> k_decide2<K, inc> over the dirty RayClusters -> k_inc_gather.
+// run k_inc_retire on the rows' old values, object commits are diffed on the device (k_inc_objects, then k_inc_refresh for the input
+// records of the RayClusters that changed), and the pass is
+//   k_inc_admit -> k_decide2<K, inc> over the dirty RayClusters (each warp also packs its changed records for the host).
 //   k_patch_pods / k_patch_pod_values (copy stream): rewritten pod rows pulled from the mapped pinned arena / scattered from a staged copy.
 //
 // Reference semantics restated here are cited per function (paths relative to
