@@ -1269,7 +1269,7 @@ int kr_snapshot_commit_parts(kr_engine *e, uint32_t parts) {
 }
 
 // Shared by the two incremental pod commits: stage the row list (and, journal style, the 7 values per row), upload, scatter.
-static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n) {
+static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n, bool rows_known_distinct = false) {
   if (!e || (!rows && n)) return KR_E_INVALID;
   if (!e->committed_full) return fail(e, KR_E_STATE, "an incremental pod commit needs a full commit of this layout first");
   if (n == 0) return KR_OK;
@@ -1287,7 +1287,7 @@ static int commit_pod_patch(kr_engine *e, const uint32_t *rows, const uint32_t *
   }
   for (uint32_t i = 0; i < n; i++)
     if (rows[i] >= e->sizes.n_pods) return fail(e, KR_E_INVALID, "pod row %u out of range", rows[i]);
-  if (values) {  // the scatter kernel writes one thread per entry: two entries for one row would race
+  if (values && !rows_known_distinct) {  // the scatter kernel writes one thread per entry: two entries for one row would race
     if (e->row_stamp.size() < e->sizes.n_pods) e->row_stamp.assign(e->sizes.n_pods, 0);
     if (++e->row_epoch == 0) { std::fill(e->row_stamp.begin(), e->row_stamp.end(), 0u); e->row_epoch = 1; }
     for (uint32_t i = 0; i < n; i++) {
@@ -1391,7 +1391,12 @@ int kr_snapshot_commit_object_rows(kr_engine *e, const uint32_t *cluster_rows, u
     const size_t rb = (size_t)kCols[i].elem * kCols[i].mult;
     const uint8_t *col = e->h_in + e->il.off[i];
     uint8_t *dst = e->orow_h + col_off[i];
-    for (uint32_t k = 0; k < cnt[d]; k++) memcpy(dst + k * rb, col + (size_t)lists[d][k] * rb, rb);
+    // (row sizes are 1, 4 or 8 bytes for almost every column: fixed-size copies instead of ~10 k variable-length memcpy calls per epoch)
+    const uint32_t *rl = lists[d];
+    if (rb == 4) { const uint32_t *c4 = reinterpret_cast<const uint32_t *>(col); uint32_t *d4 = reinterpret_cast<uint32_t *>(dst); for (uint32_t k = 0; k < cnt[d]; k++) d4[k] = c4[rl[k]]; }
+    else if (rb == 1) { for (uint32_t k = 0; k < cnt[d]; k++) dst[k] = col[rl[k]]; }
+    else if (rb == 8) { const uint64_t *c8 = reinterpret_cast<const uint64_t *>(col); uint64_t *d8 = reinterpret_cast<uint64_t *>(dst); for (uint32_t k = 0; k < cnt[d]; k++) d8[k] = c8[rl[k]]; }
+    else for (uint32_t k = 0; k < cnt[d]; k++) memcpy(dst + k * rb, col + (size_t)rl[k] * rb, rb);
     oa.src[nc] = e->orow_d + col_off[i];
     oa.rowlist[nc] = reinterpret_cast<const uint32_t *>(e->orow_d + list_off[d]);
     oa.dst[nc] = e->d_in + e->il.off[i];
@@ -1432,6 +1437,12 @@ int kr_snapshot_commit_object_rows(kr_engine *e, const uint32_t *cluster_rows, u
 }
 
 int kr_snapshot_commit_pod_rows(kr_engine *e, const uint32_t *rows, uint32_t n) { return commit_pod_patch(e, rows, nullptr, n); }
+
+// for kr_packer.cpp: its journal holds every row once (row_dirty), so the duplicate scan is skipped
+int kr_internal_commit_pod_values_distinct(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n) {
+  if (!values && n) return KR_E_INVALID;
+  return commit_pod_patch(e, rows, values, n, true);
+}
 
 int kr_snapshot_commit_pod_values(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n) {
   if (!values && n) return KR_E_INVALID;

@@ -33,6 +33,8 @@
 // kr_specjson.cpp
 int kr_specjson_emit_string(const uint8_t *spec_json, uint64_t len, bool muted, long max_groups, std::string &out, long *n_groups);
 
+extern "C" int kr_internal_commit_pod_values_distinct(kr_engine *e, const uint32_t *rows, const uint32_t *values, uint32_t n);  // kr_engine.cu (not in the public header)
+
 namespace {
 
 struct Key { uint32_t a, b; bool operator==(const Key &o) const { return a == o.a && b == o.b; } };
@@ -460,7 +462,7 @@ int kr_packer_flush(kr_packer *p, uint32_t *mode_out) {
     }
     if (trace) t3 = now();
     if (!p->dirty_rows.empty()) {  // the epoch's journal, as the handlers wrote it
-      if (int rc = kr_snapshot_commit_pod_values(p->e, p->dirty_rows.data(), p->stage_vals.data(), (uint32_t)p->dirty_rows.size())) return rc;
+      if (int rc = kr_internal_commit_pod_values_distinct(p->e, p->dirty_rows.data(), p->stage_vals.data(), (uint32_t)p->dirty_rows.size())) return rc;
       mode |= KR_PACK_POD_ROWS;
     }
   }
