@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1466,13 +1467,23 @@ int kr_reconcile_batch(kr_engine *e, const kr_flags *flags, kr_results_view *out
   if (!e || !flags || !out) return KR_E_INVALID;
   if (!e->committed) return fail(e, KR_E_STATE, "no committed snapshot");
   CK(cudaSetDevice(e->cfg.device));
+  static const bool trace = getenv("KR_ENGINE_TRACE") != nullptr;  // development aid: host time of the two halves of a call (stderr)
+  const auto t0 = std::chrono::steady_clock::now();
   CK(cudaEventRecord(e->ev_a, e->sm));
   int rc = run_pass(e, *flags, e->ev_k[KR_MAX_KERNEL_TIMES]);
   if (rc) return rc;
   e->ran = true;
   float ms = 0;
   if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_k[KR_MAX_KERNEL_TIMES]) == cudaSuccess) e->prof.kernels_ms = ms;
-  return fetch_results(e, out);  // d2h_ms = ev_b..ev_c
+  const auto t1 = std::chrono::steady_clock::now();
+  rc = fetch_results(e, out);  // d2h_ms = ev_b..ev_c
+  if (trace) {
+    const auto t2 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    fprintf(stderr, "kr_reconcile_batch: pass %.0f us (device %.0f us), fetch %.0f us (device copy %.0f us, %llu bytes)%s\n", us(t0, t1), e->prof.kernels_ms * 1e3, us(t1, t2),
+            e->prof.d2h_ms * 1e3, (unsigned long long)e->prof.d2h_bytes, e->ran_inc ? " [incremental]" : "");
+  }
+  return rc;
 }
 
 int kr_reconcile_batch_profiled(kr_engine *e, const kr_flags *flags, kr_profile *prof) {
