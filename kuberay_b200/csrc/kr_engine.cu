@@ -207,6 +207,7 @@ struct kr_engine {
   cudaStream_t sm = nullptr, sh = nullptr, sg = nullptr, scopy = nullptr;
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_cols = nullptr, ev_json = nullptr;  // commit: copy start, columns landed, JSON landed
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
+  cudaEvent_t ev_inc = nullptr;  // an incremental pass's counters have reached the host
   cudaEvent_t ev_fork = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   cudaEvent_t ev_k[KR_MAX_KERNEL_TIMES + 1]{};
   uint8_t *h_in = nullptr, *d_in = nullptr, *d_scratch = nullptr, *d_out = nullptr, *h_out = nullptr;
@@ -720,9 +721,11 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
   if (done) CK(cudaEventRecord(done, M));
   CK(cudaMemcpyAsync(e->h_totals, e->d_out + e->ol.totals, 48, cudaMemcpyDeviceToHost, M));
   CK(cudaMemcpyAsync(e->h_inc, sc.inc, 64, cudaMemcpyDeviceToHost, M));
-  k_inc_finish<<<1, 32, 0, M>>>(sc);
+  if (!e->ev_inc) CK(cudaEventCreateWithFlags(&e->ev_inc, cudaEventDisableTiming));
+  CK(cudaEventRecord(e->ev_inc, M));
+  k_inc_finish<<<1, 32, 0, M>>>(sc);  // (the host does not wait for it: whatever comes next is ordered behind it on this stream)
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(M));
+  CK(cudaEventSynchronize(e->ev_inc));
   e->order_pending = false;
   e->h2d_accum = 0;
   if (!e->h2d_timed) {
@@ -744,7 +747,7 @@ int run_pass_inc(kr_engine *e, const kr_flags &f, cudaEvent_t done, bool profile
 }
 
 // Runs the pass; if the fast pipeline met a bucket it cannot sort (> 1024 pods in one RayCluster or among the orphans),
-// switches this layout to the radix pipeline and runs again.  Leaves the stream synchronised.
+// switches this layout to the radix pipeline and runs again.  Leaves the stream synchronised (after an incremental pass only its one-thread epoch-closing kernel may still be in flight: it touches the epoch counters, nothing a reader of the results sees).
 int run_pass(kr_engine *e, const kr_flags &f, cudaEvent_t done) {
   e->last_flags = f;
   if (e->inc_valid && !e->no_incr && memcmp(&e->inc_flags, &f, sizeof f) == 0) {
@@ -1053,6 +1056,7 @@ void kr_engine_destroy(kr_engine *e) {
   if (e->sg) cudaStreamDestroy(e->sg);
   if (e->scopy) { cudaStreamSynchronize(e->scopy); cudaStreamDestroy(e->scopy); }
   for (auto ev : {e->ev_h2d0, e->ev_h2d1, e->ev_cols, e->ev_json, e->ev_pr}) if (ev) cudaEventDestroy(ev);
+  if (e->ev_inc) cudaEventDestroy(e->ev_inc);
   if (e->ev_fork2) cudaEventDestroy(e->ev_fork2);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_fork3) cudaEventDestroy(e->ev_fork3);
